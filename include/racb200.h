@@ -1,0 +1,186 @@
+/*
+ * racb200 -- C ABI of the B200-native planning hot path of penn-pal-lab/robot_aware_control.
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; each entry point below names the reference
+ * Python interface it replaces (file:line relative to the reference checkout). The Python package
+ * `robot_aware_control_b200` binds these with ctypes and mirrors the reference classes on top.
+ *
+ * Conventions: every function returns 0 on success or a negative rac_status; nothing throws across the boundary;
+ * rac_last_error() gives the message of the last failure on a handle. All tensor pointers are DEVICE pointers owned
+ * by the caller unless a parameter is documented as host memory. All work is enqueued on the caller's stream
+ * (cudaStream_t passed as void*); no call synchronises the device. One handle per (device, host thread); the
+ * recurrent state lives in the handle exactly as it lives on the reference module (lstm.py:216,255).
+ */
+#ifndef RACB200_H_
+#define RACB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAC_ABI_VERSION 1
+
+typedef enum {
+  RAC_OK = 0,
+  RAC_ERR_INVALID = -1,     /* bad argument / unsupported configuration (reference: ValueError, dynamics.py:470-473) */
+  RAC_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed */
+  RAC_ERR_STATE = -3,       /* call order violated (weights not loaded, batch not prepared, ...) */
+  RAC_ERR_UNSUPPORTED = -4  /* reference: NotImplementedError */
+} rac_status;
+
+typedef struct rac_handle rac_handle;
+
+/* Model configuration: the subset of the reference argparse Namespace the SVG path reads
+ * (src/config/__init__.py:165-249, dynamics.py:467-516). */
+typedef struct {
+  int image_height;            /* 48 */
+  int image_width;             /* 64 */
+  int g_dim;                   /* multiple of 64 */
+  int z_dim;                   /* <= 64 */
+  int action_dim;              /* model action channels (5 in BASELINE) */
+  int robot_dim;               /* 5 */
+  int use_mask;                /* cfg.model_use_mask */
+  int use_future_mask;         /* cfg.model_use_future_mask */
+  int use_robot_state;         /* cfg.model_use_robot_state */
+  int use_future_robot_state;  /* cfg.model_use_future_robot_state */
+  int conv_impl;               /* 0 = tcgen05/TMA product path; 1 = SIMT cross-check kernel (tests only) */
+} rac_config;
+
+/* Packed-layer ids: one per convolution of SVGConvModel (state_dict prefixes in SURVEY.md 8(a)). */
+enum {
+  RAC_L_ENC_C1_0 = 0, RAC_L_ENC_C1_1, RAC_L_ENC_C2_0, RAC_L_ENC_C2_1, RAC_L_ENC_C3_0, RAC_L_ENC_C3_1, RAC_L_ENC_C3_2,
+  RAC_L_ENC_C4_0, RAC_L_ENC_C4_1, RAC_L_ENC_C4_2,
+  RAC_L_PRIOR_IN, RAC_L_PRIOR_LSTM0, RAC_L_PRIOR_LSTM1, RAC_L_PRIOR_GAUSS,
+  RAC_L_FP_IN, RAC_L_FP_LSTM0, RAC_L_FP_LSTM1,
+  RAC_L_DEC_UPC2_0, RAC_L_DEC_UPC2_1, RAC_L_DEC_UPC2_2, RAC_L_DEC_UPC3_0, RAC_L_DEC_UPC3_1, RAC_L_DEC_UPC3_2,
+  RAC_L_DEC_UPC4_0, RAC_L_DEC_UPC4_1, RAC_L_DEC_UPC5_0, RAC_L_DEC_UPC5_1,
+  RAC_L_POST_IN, RAC_L_POST_LSTM0, RAC_L_POST_LSTM1, RAC_L_POST_GAUSS,
+  RAC_L_COUNT
+};
+
+int rac_abi_version(void);
+
+/* SVGConvModel.__init__ (dynamics.py:460-534). */
+int rac_create(const rac_config* cfg, rac_handle** out);
+int rac_destroy(rac_handle* h);
+const char* rac_last_error(const rac_handle* h);
+
+/* Expected packed sizes of a layer for this configuration: weight elements (bf16; fp32 for RAC_L_ENC_C1_0),
+ * bias elements (fp32), packed K (input channels incl. padding x taps) and packed N. */
+int rac_layer_shape(const rac_handle* h, int layer, int64_t* w_elems, int64_t* bias_elems, int* k_packed,
+                    int* n_packed);
+
+/* nn.Module.load_state_dict (widowx_VMPC_controller.py:98-101): one packed layer; the library copies into its own
+ * device memory. `w` / `bias` may be host or device pointers (cudaMemcpyDefault). */
+int rac_load_layer(rac_handle* h, int layer, const void* w, int64_t w_elems, const float* bias, int64_t bias_elems);
+
+/* Allocate activation workspace, recurrent state and TMA descriptors for `batch` candidates (idempotent). */
+int rac_prepare(rac_handle* h, int batch);
+
+/* SVGConvModel.init_hidden (dynamics.py:536-542): zero (h, c) of prior / posterior / frame predictor. */
+int rac_init_hidden(rac_handle* h, int batch, void* stream);
+
+/* SVGConvModel.forward (dynamics.py:544-644), eval-mode BatchNorm. */
+typedef struct {
+  int n;                    /* batch */
+  const float* image;       /* (n,3,H,W) fp32 NCHW in [0,1] */
+  const float* mask;        /* (n, 1 or 2, H, W) fp32 or NULL: channel 0 = mask_t, channel 1 = mask_{t+1} */
+  const float* robot;       /* (n, robot_dim) or NULL */
+  const float* robot_next;  /* (n, robot_dim) or NULL (model_use_future_robot_state) */
+  const float* action;      /* (n, action_dim) */
+  const float* eps;         /* (n, z_dim, H/8, W/8) prior noise or NULL -> Philox(seed, noise_ctr) */
+  unsigned long long seed;
+  unsigned int noise_ctr;
+  int sample_mean;          /* forward(..., sample_mean=) */
+  int use_posterior;        /* next_image given: run the posterior branch (dynamics.py:613-629) */
+  const float* next_robot;  /* (n, robot_dim) r_target or NULL */
+  const float* eps_post;    /* posterior noise or NULL */
+  int force_use_prior;
+  int keep_skip;            /* decoder uses the skip tensors already held by the handle (last_frame_skip False) */
+  float* x_pred;            /* out (n,4,H,W) fp32 NCHW */
+  float* mu_p;              /* out (n,z,H/8,W/8) or NULL */
+  float* logvar_p;
+  float* mu;                /* posterior outputs or NULL */
+  float* logvar;
+} rac_step;
+int rac_forward(rac_handle* h, const rac_step* s, void* stream);
+
+/* TrajectorySampler.generate_model_rollouts (trajectory_sampler.py:35-199) for one shard of candidates:
+ * autoregressive rollout + per-step RobotWorldCost accumulation, no host round trip. */
+typedef struct {
+  int n;                       /* candidates in this call */
+  int steps;                   /* rollout length L (= horizon - 1 in the reference) */
+  int cand_offset;             /* global id of candidate 0 (Philox noise is keyed on global ids) */
+  const float* actions;        /* (n, steps, action_dim) fp32 */
+  const uint8_t* start_img;    /* (H,W,3) uint8 */
+  const uint8_t* goal_imgs;    /* (G,H,W,3) uint8 */
+  int num_goals;
+  const float* goal_masks;     /* (G,H,W) fp32 {0,1} or NULL */
+  const float* states;         /* (steps+1, *, robot_dim) fp32 or NULL; pointer at this shard's first candidate */
+  int64_t state_t_stride;      /* elements between consecutive time steps of `states` */
+  const float* masks;          /* (steps+1, *, H, W) fp32 {0,1} or NULL; pointer at this shard's first candidate */
+  int64_t mask_t_stride;       /* elements between consecutive time steps of `masks` */
+  const float* eps;            /* (steps, n, z_dim, H/8, W/8) supplied prior noise or NULL -> Philox */
+  unsigned long long seed;
+  unsigned int noise_ctr_base; /* step t uses noise_ctr_base + t */
+  int sample_mean;             /* cfg.sample_mean */
+  int zero_robot;              /* "dontcare" in cfg.reconstruction_loss or cfg.black_robot_input */
+  int dontcare_cost;           /* cfg.reward_type == "dontcare" */
+  int sparse_cost;             /* cfg.sparse_cost */
+  float world_cost_weight;     /* cfg.world_cost_weight */
+  float* obs_out;              /* (steps, n, H, W, 4) fp32 (rgb + pad) or NULL */
+  float* step_cost_out;        /* (steps, n) fp32 or NULL */
+  double* sum_cost;            /* (n) fp64 out */
+} rac_rollout;
+int rac_rollout_cost(rac_handle* h, const rac_rollout* r, void* stream);
+
+/* CEMPolicy.get_action pieces (cem.py:76-104). */
+int rac_cem_sample(const float* mean, const float* stdv, const float* noise, unsigned long long seed, int iter,
+                   int n_total, int steps, int action_dim_model, int cand_offset, int n_local, float clamp,
+                   float* act2_out /* (n_total, steps, 2) */, float* act_model_out /* (n_local, steps, action_dim) */,
+                   void* stream);
+/* costs.topk(K) (cem.py:97): K largest, ties -> lowest index, output sorted (value desc, index asc). */
+int rac_topk(const double* costs, int n, int k, int64_t* idx_out, double* val_out_or_null, void* stream);
+/* torch.std_mean(top_act_seq, dim=0) + std floor (cem.py:101-104). */
+int rac_cem_refit(const float* act2, int steps, const int64_t* elite_idx, int k, float std_floor, float* mean_out,
+                  float* std_out, void* stream);
+
+/* Whole single-GPU plan: `iters` x (sample -> rollout+cost -> top-k -> refit), device resident. */
+typedef struct {
+  int n;               /* action_candidates */
+  int steps;           /* horizon - 1 */
+  int iters;           /* opt_iter */
+  int topk;            /* K */
+  float init_std;
+  float clamp;         /* 0.05 */
+  float std_floor;     /* 0.001 */
+  const float* noise;  /* (iters, n, steps, 2) standard normals or NULL -> Philox(seed) */
+  rac_rollout rollout; /* template: actions / sum_cost / n / steps are filled by the library */
+} rac_cem;
+int rac_cem_plan(rac_handle* h, const rac_cem* c, float* mean_out /* (steps,2) */, float* std_out /* (steps,2) */,
+                 int64_t* elite_idx_out /* (topk) or NULL */, double* last_costs_out /* (n) or NULL */, void* stream);
+
+/* ImgL2Cost._call_tensor / ImgDontcareCost._call_tensor (losses.py:224-235,244-263) in the reference tensor layout:
+ * curr (n,3,H,W), goal (3,H,W), curr_mask (n,1,H,W) or NULL, goal_mask (1,H,W) or NULL -> out (n) = -dist. */
+int rac_masked_cost(const float* curr, const float* goal, const float* curr_mask, const float* goal_mask,
+                    int dontcare, float* out, int n, int hw, void* stream);
+
+/* Training criteria, forward value (losses.py:13-19,35-50,97-106); out = 1 fp32 scalar. */
+int rac_l1_loss(const float* pred, const float* target, float* out, int64_t numel, void* stream);
+int rac_dontcare_l1_loss(const float* pred, const float* target, const float* mask, float robot_weight, float* out,
+                         int n, int hw, void* stream);
+int rac_kl_loss(const float* mu1, const float* logvar1, const float* mu2, const float* logvar2, float* out,
+                int64_t numel, int batch, void* stream);
+
+/* Test / inspection hook: device pointer and element count of a named internal buffer of the prepared workspace
+ * ("h1".."h4", "prior_in", "z", "h_pred", "img", ...). */
+int rac_debug_buffer(rac_handle* h, const char* name, void** ptr, int64_t* elems, int* elem_bytes);
+/* Number of kernels the library has launched on this handle since creation (bench.py gpu_launches). */
+int64_t rac_launch_count(const rac_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RACB200_H_ */

@@ -1,0 +1,90 @@
+// Shared definitions for the implicit-GEMM convolution kernels (tcgen05 product path and the SIMT
+// cross-check kernel) and their fused epilogues.
+//
+// Activations are NHWC bf16: tensor [B, H, W, C] with C a multiple of 64. A convolution is the GEMM
+//   D[m, n] = sum_{tap, c} A[(b, y + kh - pad, x + kw - pad), c] * Wp[n, tap * Ctot + c]
+// with m = (b, y, x). One M-tile is 128 rows = a TMA box {64 ch, W, BH, NB} (W * BH * NB == 128); zero padding
+// comes from TMA out-of-bounds fill, the channel concat of several inputs (reference: torch.cat at
+// src/prediction/models/dynamics.py:600-641, lstm.py:132, vgg_64.py:236-240) is a loop over source tensors.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace rac {
+
+enum EpiMode : int { EPI_ACT = 0, EPI_LSTM = 1, EPI_GAUSS = 2, EPI_FRAME = 3 };
+
+constexpr int kMaxSrc = 3;
+constexpr int kTileM = 128;
+constexpr int kBlockK = 64;  // bf16 channels per k-block = one 128-byte swizzle row
+
+struct ConvGeom {
+  int B, H, W;          // candidates, output (= input) spatial size
+  int BH, NB;           // rows / candidates per M-tile (W * BH * NB == 128)
+  int ks, pad;          // square filter, 'same' padding
+  int nsrc;             // concatenated inputs
+  int src_kb[kMaxSrc];  // k-blocks (channels / 64) per input
+  int ctot;             // total input channels (sum of padded source channels)
+  int num_m_tiles, num_n_tiles, tiles_per_img;  // tiles_per_img = H / BH
+  int w_shift, bhw_shift;                       // log2(W), log2(BH * W)
+};
+
+struct EpiParams {
+  const float* bias;  // [num_n_tiles * BLOCK_N], packed column order
+  int cout;           // valid packed output columns
+  // EPI_ACT: y = act(acc + bias) -> bf16 NHWC, optional channel offset into a concat buffer and 2x nearest upsample
+  __nv_bfloat16* out;
+  int out_cstride, out_coff, upsample, lrelu;
+  // EPI_LSTM (reference lstm.py:135-149): columns are (channel, gate) interleaved, gate order in/remember/out/cell
+  float* c_state;        // [B,H,W,hid] fp32, updated in place
+  __nv_bfloat16* h_out;  // [B,H,W,hid]
+  int hid;
+  // EPI_GAUSS (reference lstm.py:276-286): columns are (z channel, {mu, logvar}) interleaved
+  const float* eps;         // NCHW (B, z_dim, H, W) fp32 noise, or null -> Philox
+  float* mu_out;            // NCHW fp32 or null
+  float* logvar_out;        // NCHW fp32 or null
+  __nv_bfloat16* z_out;     // [B,H,W,64] (channels >= z_dim written as 0)
+  int z_dim, sample_mean;
+  unsigned long long seed;
+  unsigned int noise_ctr;   // (iteration, step) counter for Philox
+  int cand_offset;          // global id of candidate 0 of this rank
+  // EPI_FRAME (reference trajectory_sampler.py:148-168, losses.py:224-263, image.py:5-20)
+  const float* curr_img;   // [B,H,W,4] fp32 (rgb + pad)
+  float* next_img;         // [B,H,W,4] fp32
+  const float* mask_next;  // [B,H,W] fp32 {0,1} or null
+  const float* goal_img;   // [H,W,4] fp32
+  const float* goal_mask;  // [H,W] fp32 or null
+  float* xpred_out;        // NCHW (B,4,H,W) fp32 or null
+  float* cost_part;        // [B][tiles_per_img*4][2] (sum of squares, world pixel count) or null
+  int zero_robot, dontcare;
+};
+
+struct ConvTmaps {
+  CUtensorMap a[kMaxSrc];
+  CUtensorMap w;
+};
+
+// raw pointers for the SIMT cross-check kernel
+struct ConvRaw {
+  const __nv_bfloat16* src[kMaxSrc];
+  const __nv_bfloat16* w;  // [n_pad][ks*ks*ctot]
+};
+
+struct ConvOp {
+  ConvGeom g;
+  EpiParams e;
+  ConvTmaps tm;
+  ConvRaw raw;
+  int block_n;
+  int epi;
+  const char* name;
+};
+
+// host launchers (conv_tc.cu)
+cudaError_t launch_conv_tc(const ConvOp& op, int num_sms, cudaStream_t stream);
+cudaError_t launch_conv_simt(const ConvOp& op, cudaStream_t stream);
+cudaError_t conv_tc_set_attributes();
+
+}  // namespace rac

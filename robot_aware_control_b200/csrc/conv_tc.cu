@@ -1,0 +1,271 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), operands staged
+// by TMA into 128B-swizzled shared memory. Persistent, warp-specialised:
+//   warp 0   : TMA producer  (one thread)   -- A: 4-D box {64 ch, W, BH, NB} per filter tap, B: 2-D weight box
+//   warp 1   : MMA issuer    (one thread)   -- 4 x tcgen05.mma (M128 x BLOCK_N x K16) per 64-channel k-block
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue      (128 threads)  -- tcgen05.ld -> fused epilogue (epilogue.cuh) -> global
+// Two TMEM accumulator buffers let the epilogue of tile i overlap the main loop of tile i+1.
+//
+// Replaces the cuDNN/ATen calls behind nn.Conv2d / BatchNorm2d / LeakyReLU / ConvTranspose2d / Sigmoid and the
+// LSTM / reparameterisation / compositing / cost pointwise ops of the reference:
+//   src/prediction/models/vgg_64.py:8-18,122-129,223-241; lstm.py:129-149,276-286; dynamics.py:594-643;
+//   src/cem/trajectory_sampler.py:148-168.
+#include "conv.cuh"
+#include "epilogue.cuh"
+#include "ptx.cuh"
+
+namespace rac {
+
+template <int BLOCK_N>
+struct TcCfg {
+  static constexpr int kABytes = kTileM * kBlockK * 2;   // 16 KB
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;  // BLOCK_N rows of 128 B
+  static constexpr int kBBytesPad = (kBBytes + 1023) / 1024 * 1024;
+  static constexpr int kStageBytes = kABytes + kBBytesPad;
+  static constexpr int kStages = (BLOCK_N >= 128) ? 6 : 8;
+  static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : 256));
+  static constexpr int kBarBytes = 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024 alignment slack
+};
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(256, 1)
+conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const EpiParams e) {
+  using Cfg = TcCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bar_base = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = g.num_m_tiles * g.num_n_tiles;
+  const int taps = g.ks * g.ks;
+  int kb_per_tap = 0;
+  for (int s = 0; s < g.nsrc; ++s) kb_per_tap += g.src_kb[s];
+  const int num_kb = taps * kb_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < g.nsrc; ++s) tma_prefetch_desc(&tm.a[s]);
+    tma_prefetch_desc(&tm.w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_tile = tile / g.num_m_tiles;
+      const int m_tile = tile - n_tile * g.num_m_tiles;
+      const int grp = m_tile / g.tiles_per_img;
+      const int b0 = grp * g.NB;
+      const int y0 = (m_tile - grp * g.tiles_per_img) * g.BH;
+      int kidx = 0;
+      for (int kh = 0; kh < g.ks; ++kh) {
+        for (int kw = 0; kw < g.ks; ++kw) {
+          for (int s = 0; s < g.nsrc; ++s) {
+            for (int kb = 0; kb < g.src_kb[s]; ++kb, ++kidx) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * Cfg::kStageBytes;
+              uint8_t* sb = sa + Cfg::kABytes;
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
+              tma_load_4d(&tm.a[s], &full_bar[stage], sa, kb * kBlockK, kw - g.pad, y0 + kh - g.pad, b0);
+              tma_load_2d(&tm.w, &full_bar[stage], sb, kidx * kBlockK, n_tile * BLOCK_N);
+              if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint64_t adesc = umma_desc_sw128(sa);
+        const uint64_t bdesc = umma_desc_sw128(sa + Cfg::kABytes);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in the (addr >> 4) field
+          umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
+        if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int wq = warp - 4;  // TMEM lane quarter == warp_id % 4
+    const int r = wq * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    constexpr int CH = (BLOCK_N >= 32) ? 32 : 16;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_tile = tile / g.num_m_tiles;
+      const int m_tile = tile - n_tile * g.num_m_tiles;
+      const int grp = m_tile / g.tiles_per_img;
+      const int yb = m_tile - grp * g.tiles_per_img;
+      const int b = grp * g.NB + (r >> g.bhw_shift);
+      const int y = yb * g.BH + ((r >> g.w_shift) & (g.BH - 1));
+      const int x = r & (g.W - 1);
+      const bool valid = b < g.B;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / CH; ++c) {
+        float v[CH];
+        if constexpr (CH == 32) tmem_ld32(t_row + c * CH, v); else tmem_ld16(t_row + c * CH, v);
+        tmem_ld_wait();
+        const int n0 = n_tile * BLOCK_N + c * CH;
+        if constexpr (EPI == EPI_ACT) epi_act<CH>(g, e, b, y, x, valid, n0, v);
+        if constexpr (EPI == EPI_LSTM) epi_lstm(g, e, b, y, x, valid, n0, v);
+        if constexpr (EPI == EPI_GAUSS) epi_gauss(g, e, b, y, x, valid, n0, v);
+        if constexpr (EPI == EPI_FRAME) epi_frame(g, e, b, y, x, valid, yb * 4 + wq, v);
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SIMT cross-check kernel: same geometry, same packed weights, same epilogues, no tensor cores / TMA. It exists so
+// that the tcgen05 path can be validated tile by tile on the GPU (tests/, RAC_CONV_IMPL=simt); it is not a product
+// path and nothing dispatches to it by default.
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(128)
+conv_simt_kernel(const ConvRaw raw, const ConvGeom g, const EpiParams e) {
+  constexpr int CH = (BLOCK_N >= 32) ? 32 : 16;
+  constexpr int chunks = BLOCK_N / CH;
+  const int c = blockIdx.x % chunks;
+  const int tile = blockIdx.x / chunks;
+  const int n_tile = tile / g.num_m_tiles;
+  const int m_tile = tile - n_tile * g.num_m_tiles;
+  const int grp = m_tile / g.tiles_per_img;
+  const int yb = m_tile - grp * g.tiles_per_img;
+  const int r = threadIdx.x;
+  const int b = grp * g.NB + (r >> g.bhw_shift);
+  const int y = yb * g.BH + ((r >> g.w_shift) & (g.BH - 1));
+  const int x = r & (g.W - 1);
+  const bool valid = b < g.B;
+  const int n0 = n_tile * BLOCK_N + c * CH;
+  const int ktot = g.ks * g.ks * g.ctot;
+  float acc[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) acc[j] = 0.f;
+  if (valid) {
+    for (int kh = 0; kh < g.ks; ++kh) {
+      const int yy = y + kh - g.pad;
+      if (yy < 0 || yy >= g.H) continue;
+      for (int kw = 0; kw < g.ks; ++kw) {
+        const int xx = x + kw - g.pad;
+        if (xx < 0 || xx >= g.W) continue;
+        int coff = 0;
+        for (int s = 0; s < g.nsrc; ++s) {
+          const int cs = g.src_kb[s] * kBlockK;
+          const __nv_bfloat16* ap = raw.src[s] + (static_cast<size_t>(b * g.H + yy) * g.W + xx) * cs;
+          const __nv_bfloat16* wp = raw.w + static_cast<size_t>(n0) * ktot + (kh * g.ks + kw) * g.ctot + coff;
+          for (int ch = 0; ch < cs; ++ch) {
+            const float a = __bfloat162float(ap[ch]);
+#pragma unroll
+            for (int j = 0; j < CH; ++j) acc[j] += a * __bfloat162float(wp[static_cast<size_t>(j) * ktot + ch]);
+          }
+          coff += cs;
+        }
+      }
+    }
+  }
+  if constexpr (EPI == EPI_ACT) epi_act<CH>(g, e, b, y, x, valid, n0, acc);
+  if constexpr (EPI == EPI_LSTM) epi_lstm(g, e, b, y, x, valid, n0, acc);
+  if constexpr (EPI == EPI_GAUSS) epi_gauss(g, e, b, y, x, valid, n0, acc);
+  if constexpr (EPI == EPI_FRAME) epi_frame(g, e, b, y, x, valid, yb * 4 + (r >> 5), acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <int BLOCK_N, int EPI>
+static cudaError_t launch_tc_t(const ConvOp& op, int num_sms, cudaStream_t stream) {
+  const int num_tiles = op.g.num_m_tiles * op.g.num_n_tiles;
+  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  conv_tc_kernel<BLOCK_N, EPI><<<grid, 256, TcCfg<BLOCK_N>::kSmemBytes, stream>>>(op.tm, op.g, op.e);
+  return cudaGetLastError();
+}
+template <int BLOCK_N, int EPI>
+static cudaError_t launch_simt_t(const ConvOp& op, cudaStream_t stream) {
+  constexpr int CH = (BLOCK_N >= 32) ? 32 : 16;
+  const int grid = op.g.num_m_tiles * op.g.num_n_tiles * (BLOCK_N / CH);
+  conv_simt_kernel<BLOCK_N, EPI><<<grid, 128, 0, stream>>>(op.raw, op.g, op.e);
+  return cudaGetLastError();
+}
+
+#define RAC_CONV_DISPATCH(FN, ...)                                                                  \
+  if (op.block_n == 128 && op.epi == EPI_ACT) return FN<128, EPI_ACT>(__VA_ARGS__);                 \
+  if (op.block_n == 64 && op.epi == EPI_ACT) return FN<64, EPI_ACT>(__VA_ARGS__);                   \
+  if (op.block_n == 128 && op.epi == EPI_LSTM) return FN<128, EPI_LSTM>(__VA_ARGS__);               \
+  if (op.block_n == 128 && op.epi == EPI_GAUSS) return FN<128, EPI_GAUSS>(__VA_ARGS__);             \
+  if (op.block_n == 16 && op.epi == EPI_FRAME) return FN<16, EPI_FRAME>(__VA_ARGS__);               \
+  return cudaErrorInvalidValue;
+
+cudaError_t launch_conv_tc(const ConvOp& op, int num_sms, cudaStream_t stream) {
+  RAC_CONV_DISPATCH(launch_tc_t, op, num_sms, stream)
+}
+cudaError_t launch_conv_simt(const ConvOp& op, cudaStream_t stream) {
+  RAC_CONV_DISPATCH(launch_simt_t, op, stream)
+}
+
+template <int BLOCK_N, int EPI>
+static cudaError_t set_attr_t() {
+  return cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              TcCfg<BLOCK_N>::kSmemBytes);
+}
+cudaError_t conv_tc_set_attributes() {
+  cudaError_t err;
+  if ((err = set_attr_t<128, EPI_ACT>()) != cudaSuccess) return err;
+  if ((err = set_attr_t<64, EPI_ACT>()) != cudaSuccess) return err;
+  if ((err = set_attr_t<128, EPI_LSTM>()) != cudaSuccess) return err;
+  if ((err = set_attr_t<128, EPI_GAUSS>()) != cudaSuccess) return err;
+  if ((err = set_attr_t<16, EPI_FRAME>()) != cudaSuccess) return err;
+  return cudaSuccess;
+}
+
+}  // namespace rac

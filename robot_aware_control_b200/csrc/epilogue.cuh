@@ -1,0 +1,208 @@
+// Fused epilogues of the convolution kernels. One thread owns one output row (b, y, x) and receives CH consecutive
+// fp32 accumulator columns starting at packed column n0. The same functions serve the tcgen05 kernel (accumulators
+// read from TMEM) and the SIMT cross-check kernel.
+#pragma once
+#include "conv.cuh"
+
+namespace rac {
+
+// ---------------------------------------------------------------- Philox4x32-10 counter RNG
+struct Philox4 {
+  uint32_t v[4];
+};
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = static_cast<uint64_t>(M0) * c0;
+    const uint64_t p1 = static_cast<uint64_t>(M1) * c2;
+    const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n1 = static_cast<uint32_t>(p1);
+    const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n3 = static_cast<uint32_t>(p0);
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  Philox4 o;
+  o.v[0] = c0; o.v[1] = c1; o.v[2] = c2; o.v[3] = c3;
+  return o;
+}
+// two uniform 32-bit words -> two standard normals (Box-Muller)
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+  const float u1 = (static_cast<float>(a) + 1.0f) * 2.3283064365386963e-10f;  // (0, 1]
+  const float u2 = static_cast<float>(b) * 2.3283064365386963e-10f;           // [0, 1)
+  const float r = sqrtf(-2.0f * logf(u1));
+  float s, c;
+  sincosf(6.283185307179586f * u2, &s, &c);
+  n0 = r * c;
+  n1 = r * s;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---------------------------------------------------------------- EPI_ACT
+template <int CH>
+__device__ __forceinline__ void epi_act(const ConvGeom& g, const EpiParams& e, int b, int y, int x, bool valid, int n0,
+                                        const float* acc) {
+  if (!valid || n0 + CH > e.cout) return;
+  uint32_t pk[CH / 2];
+#pragma unroll
+  for (int j = 0; j < CH; j += 2) {
+    float v0 = acc[j] + __ldg(e.bias + n0 + j);
+    float v1 = acc[j + 1] + __ldg(e.bias + n0 + j + 1);
+    if (e.lrelu) {
+      v0 = v0 > 0.f ? v0 : 0.2f * v0;
+      v1 = v1 > 0.f ? v1 : 0.2f * v1;
+    }
+    pk[j / 2] = pack_bf16x2(v0, v1);
+  }
+  if (!e.upsample) {
+    __nv_bfloat16* dst = e.out + (static_cast<size_t>(b * g.H + y) * g.W + x) * e.out_cstride + e.out_coff + n0;
+#pragma unroll
+    for (int q = 0; q < CH / 8; ++q)
+      reinterpret_cast<uint4*>(dst)[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+  } else {
+    // nearest 2x upsample (reference vgg_64.py:221,235-239) folded into the store
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        __nv_bfloat16* dst =
+            e.out + (static_cast<size_t>(b * 2 * g.H + 2 * y + dy) * (2 * g.W) + 2 * x + dx) * e.out_cstride +
+            e.out_coff + n0;
+#pragma unroll
+        for (int q = 0; q < CH / 8; ++q)
+          reinterpret_cast<uint4*>(dst)[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      }
+  }
+}
+
+// ---------------------------------------------------------------- EPI_LSTM
+// columns n0 .. n0+31 = 8 channels x (in, remember, out, cell)
+__device__ __forceinline__ void epi_lstm(const ConvGeom& g, const EpiParams& e, int b, int y, int x, bool valid, int n0,
+                                         const float* acc) {
+  if (!valid || n0 + 32 > e.cout) return;
+  const int ch0 = n0 >> 2;
+  const size_t base = (static_cast<size_t>(b * g.H + y) * g.W + x) * e.hid + ch0;
+  float cprev[8];
+  *reinterpret_cast<float4*>(cprev) = *reinterpret_cast<const float4*>(e.c_state + base);
+  *reinterpret_cast<float4*>(cprev + 4) = *reinterpret_cast<const float4*>(e.c_state + base + 4);
+  float cn[8], hn[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float ig = sigmoidf_(acc[4 * q + 0] + __ldg(e.bias + n0 + 4 * q + 0));
+    const float fg = sigmoidf_(acc[4 * q + 1] + __ldg(e.bias + n0 + 4 * q + 1));
+    const float og = sigmoidf_(acc[4 * q + 2] + __ldg(e.bias + n0 + 4 * q + 2));
+    const float cg = tanhf(acc[4 * q + 3] + __ldg(e.bias + n0 + 4 * q + 3));
+    cn[q] = fg * cprev[q] + ig * cg;
+    hn[q] = og * tanhf(cn[q]);
+  }
+  *reinterpret_cast<float4*>(e.c_state + base) = *reinterpret_cast<float4*>(cn);
+  *reinterpret_cast<float4*>(e.c_state + base + 4) = *reinterpret_cast<float4*>(cn + 4);
+  *reinterpret_cast<uint4*>(e.h_out + base) = make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]),
+                                                         pack_bf16x2(hn[4], hn[5]), pack_bf16x2(hn[6], hn[7]));
+}
+
+// ---------------------------------------------------------------- EPI_GAUSS
+// columns n0 .. n0+31 = 16 z channels x (mu, logvar); z = mu + eps * exp(0.5 * logvar)
+__device__ __forceinline__ void epi_gauss(const ConvGeom& g, const EpiParams& e, int b, int y, int x, bool valid,
+                                          int n0, const float* acc) {
+  if (!valid || n0 >= 128) return;
+  const int zc0 = n0 >> 1;
+  const int hw = g.H * g.W;
+  const int pos = y * g.W + x;
+  float zv[16];
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    float nz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!e.sample_mean && e.eps == nullptr) {
+      const Philox4 r = philox4x32_10(static_cast<uint32_t>(e.cand_offset + b),
+                                      static_cast<uint32_t>(pos * 16 + (zc0 >> 2) + q4), e.noise_ctr, 0x5ac5u,
+                                      static_cast<uint32_t>(e.seed), static_cast<uint32_t>(e.seed >> 32));
+      box_muller(r.v[0], r.v[1], nz[0], nz[1]);
+      box_muller(r.v[2], r.v[3], nz[2], nz[3]);
+    }
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+      const int q = q4 * 4 + qq;
+      const int zc = zc0 + q;
+      float z = 0.f;
+      if (zc < e.z_dim) {
+        const float mu = acc[2 * q] + __ldg(e.bias + n0 + 2 * q);
+        const float lv = acc[2 * q + 1] + __ldg(e.bias + n0 + 2 * q + 1);
+        const size_t nchw = (static_cast<size_t>(b) * e.z_dim + zc) * hw + pos;
+        if (e.mu_out) e.mu_out[nchw] = mu;
+        if (e.logvar_out) e.logvar_out[nchw] = lv;
+        if (e.sample_mean) {
+          z = mu;
+        } else {
+          const float ep = e.eps ? __ldg(e.eps + nchw) : nz[qq];
+          z = ep * expf(0.5f * lv) + mu;
+        }
+      }
+      zv[q] = z;
+    }
+  }
+  __nv_bfloat16* dst = e.z_out + (static_cast<size_t>(b) * hw + pos) * 64 + zc0;
+  reinterpret_cast<uint4*>(dst)[0] = make_uint4(pack_bf16x2(zv[0], zv[1]), pack_bf16x2(zv[2], zv[3]),
+                                                pack_bf16x2(zv[4], zv[5]), pack_bf16x2(zv[6], zv[7]));
+  reinterpret_cast<uint4*>(dst)[1] = make_uint4(pack_bf16x2(zv[8], zv[9]), pack_bf16x2(zv[10], zv[11]),
+                                                pack_bf16x2(zv[12], zv[13]), pack_bf16x2(zv[14], zv[15]));
+}
+
+// ---------------------------------------------------------------- EPI_FRAME
+// columns 0..3 = (r, g, b, compositing mask) pre-sigmoid. All 32 lanes of a warp belong to one candidate (NB == 1).
+// Must be called by every lane of the warp (shuffle reduction).
+__device__ __forceinline__ void epi_frame(const ConvGeom& g, const EpiParams& e, int b, int y, int x, bool valid,
+                                          int part_idx, const float* acc) {
+  float sq = 0.f, cnt = 0.f;
+  if (valid) {
+    float xp[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) xp[c] = sigmoidf_(acc[c] + __ldg(e.bias + c));
+    const int pos = y * g.W + x;
+    const size_t pix = static_cast<size_t>(b) * g.H * g.W + pos;
+    if (e.xpred_out) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) e.xpred_out[(static_cast<size_t>(b) * 4 + c) * g.H * g.W + pos] = xp[c];
+    }
+    if (e.curr_img) {
+      const float4 cur = *reinterpret_cast<const float4*>(e.curr_img + pix * 4);
+      const float m = xp[3];
+      float nx[3] = {(1.f - m) * cur.x + m * xp[0], (1.f - m) * cur.y + m * xp[1], (1.f - m) * cur.z + m * xp[2]};
+      const bool robot = e.mask_next ? (__ldg(e.mask_next + pix) != 0.f) : false;
+      if (e.zero_robot && robot) nx[0] = nx[1] = nx[2] = 0.f;
+      *reinterpret_cast<float4*>(e.next_img + pix * 4) = make_float4(nx[0], nx[1], nx[2], 0.f);
+      if (e.cost_part) {
+        const float4 gl = __ldg(reinterpret_cast<const float4*>(e.goal_img) + pos);
+        const float d0 = 255.f * (nx[0] - gl.x), d1 = 255.f * (nx[1] - gl.y), d2 = 255.f * (nx[2] - gl.z);
+        sq = d0 * d0 + d1 * d1 + d2 * d2;
+        if (e.dontcare) {
+          const bool dc = robot || (e.goal_mask && __ldg(e.goal_mask + pos) != 0.f);
+          if (dc) sq = 0.f;
+          cnt = dc ? 0.f : 1.f;
+        }
+      }
+    }
+  }
+  if (e.cost_part) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0 && valid) {
+      float* dst = e.cost_part + (static_cast<size_t>(b) * (g.tiles_per_img * 4) + part_idx) * 2;
+      dst[0] = sq;
+      dst[1] = cnt;
+    }
+  }
+}
+
+}  // namespace rac

@@ -1,0 +1,351 @@
+// Small memory-bound kernels around the convolution stack: first encoder layer, pooling, tiled action channels,
+// image preparation, planning-cost reductions and the training criteria (forward values).
+#include "misc_kernels.cuh"
+#include "epilogue.cuh"
+
+namespace rac {
+
+// ---------------------------------------------------------------- encoder.c1.0
+// w: [9 * cin][64] fp32 (tap-major, BN folded), bias [64]. One thread per pixel, 64 output channels.
+__global__ void __launch_bounds__(128)
+first_conv_kernel(const float* __restrict__ img4, const float* __restrict__ mask_a, const float* __restrict__ mask_b,
+                  long long mask_bstride, const float* __restrict__ w, const float* __restrict__ bias,
+                  __nv_bfloat16* __restrict__ out, int B, int H, int W, int cin) {
+  __shared__ __align__(16) float sw[45 * 64];
+  __shared__ float sb[64];
+  for (int i = threadIdx.x; i < 9 * cin * 64; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(B) * H * W;
+  if (pix >= total) return;
+  const int x = static_cast<int>(pix % W);
+  const int y = static_cast<int>((pix / W) % H);
+  const size_t b = pix / (static_cast<size_t>(W) * H);
+  float in[45];
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int yy = y + kh - 1, xx = x + kw - 1;
+      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      const size_t q = (b * H + (ok ? yy : 0)) * W + (ok ? xx : 0);
+      const int t = (kh * 3 + kw) * cin;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) v = *reinterpret_cast<const float4*>(img4 + q * 4);
+      in[t + 0] = v.x; in[t + 1] = v.y; in[t + 2] = v.z;
+      const size_t mq = b * mask_bstride + (ok ? yy : 0) * W + (ok ? xx : 0);
+      if (cin > 3) in[t + 3] = ok ? mask_a[mq] : 0.f;
+      if (cin > 4) in[t + 4] = ok ? mask_b[mq] : 0.f;
+    }
+  }
+  __nv_bfloat16* dst = out + pix * 64;
+  const int K = 9 * cin;
+#pragma unroll 1
+  for (int o8 = 0; o8 < 64; o8 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = sb[o8 + j];
+    for (int k = 0; k < K; ++k) {
+      const float a = in[k];
+      const float4 w0 = *reinterpret_cast<const float4*>(&sw[k * 64 + o8]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&sw[k * 64 + o8 + 4]);
+      acc[0] += a * w0.x; acc[1] += a * w0.y; acc[2] += a * w0.z; acc[3] += a * w0.w;
+      acc[4] += a * w1.x; acc[5] += a * w1.y; acc[6] += a * w1.z; acc[7] += a * w1.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = acc[j] > 0.f ? acc[j] : 0.2f * acc[j];
+    *reinterpret_cast<uint4*>(dst + o8) = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                                     pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
+cudaError_t launch_first_conv(const float* img4, const float* mask_a, const float* mask_b, long long mask_bstride,
+                              const float* w, const float* bias, __nv_bfloat16* out, int B, int H, int W, int cin,
+                              cudaStream_t s) {
+  if (cin < 3 || cin > 5) return cudaErrorInvalidValue;
+  if ((cin > 3 && !mask_a) || (cin > 4 && !mask_b)) return cudaErrorInvalidValue;
+  const size_t total = static_cast<size_t>(B) * H * W;
+  first_conv_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, s>>>(img4, mask_a, mask_b, mask_bstride, w,
+                                                                                bias, out, B, H, W, cin);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- 2x2 max pool
+__device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+__global__ void __launch_bounds__(256)
+maxpool2_kernel(const __nv_bfloat16* __restrict__ in, int in_cstride, int in_coff, __nv_bfloat16* __restrict__ out,
+                int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
+  const size_t total = static_cast<size_t>(B) * Ho * Wo * C8;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = static_cast<int>(i % C8);
+  const int xo = static_cast<int>((i / C8) % Wo);
+  const int yo = static_cast<int>((i / (static_cast<size_t>(C8) * Wo)) % Ho);
+  const size_t b = i / (static_cast<size_t>(C8) * Wo * Ho);
+  const __nv_bfloat16* p = in + ((b * H + 2 * yo) * W + 2 * xo) * in_cstride + in_coff + c8 * 8;
+  const uint4 v00 = *reinterpret_cast<const uint4*>(p);
+  const uint4 v01 = *reinterpret_cast<const uint4*>(p + in_cstride);
+  const uint4 v10 = *reinterpret_cast<const uint4*>(p + static_cast<size_t>(W) * in_cstride);
+  const uint4 v11 = *reinterpret_cast<const uint4*>(p + static_cast<size_t>(W) * in_cstride + in_cstride);
+  *reinterpret_cast<uint4*>(out + ((b * Ho + yo) * Wo + xo) * C + c8 * 8) =
+      bf16x8_max(bf16x8_max(v00, v01), bf16x8_max(v10, v11));
+}
+cudaError_t launch_maxpool2(const __nv_bfloat16* in, int in_cstride, int in_coff, __nv_bfloat16* out, int B, int H,
+                            int W, int C, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(B) * (H / 2) * (W / 2) * (C / 8);
+  maxpool2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, in_cstride, in_coff, out, B, H, W, C);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- tiled action / state channels
+__global__ void __launch_bounds__(256)
+aux_tile_kernel(const float* __restrict__ action, int astride, int adim, const float* __restrict__ r,
+                const float* __restrict__ r2, int rdim, __nv_bfloat16* __restrict__ aux, int B, int HW) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // (b, pos, c8)
+  const size_t total = static_cast<size_t>(B) * HW * 8;
+  if (i >= total) return;
+  const int c8 = static_cast<int>(i & 7);
+  const size_t b = i / (static_cast<size_t>(HW) * 8);
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c8 * 8 + j;
+    float x = 0.f;
+    if (action && c < adim) x = action[b * astride + c];
+    else if (r && c < adim + rdim) x = r[b * rdim + (c - adim)];
+    else if (r && r2 && c < adim + 2 * rdim) x = r2[b * rdim + (c - adim - rdim)];
+    v[j] = x;
+  }
+  *reinterpret_cast<uint4*>(aux + i * 8) =
+      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+cudaError_t launch_aux_tile(const float* action, int astride, int adim, const float* r, const float* r2, int rdim,
+                            __nv_bfloat16* aux, int B, int HW, cudaStream_t s) {
+  if (adim + (r ? rdim : 0) + (r2 ? rdim : 0) > 64) return cudaErrorInvalidValue;
+  const size_t total = static_cast<size_t>(B) * HW * 8;
+  aux_tile_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(action, astride, adim, r, r2, rdim, aux, B,
+                                                                             HW);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- image preparation
+__global__ void __launch_bounds__(256)
+img_prep_u8_kernel(const uint8_t* __restrict__ img, const float* __restrict__ mask0, int zero_robot,
+                   float* __restrict__ img4, int B, int HW) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(B) * HW) return;
+  const int pos = static_cast<int>(i % HW);
+  float r = static_cast<float>(img[pos * 3 + 0]) / 255.f;
+  float g = static_cast<float>(img[pos * 3 + 1]) / 255.f;
+  float b = static_cast<float>(img[pos * 3 + 2]) / 255.f;
+  if (zero_robot && mask0 && mask0[i] != 0.f) r = g = b = 0.f;
+  *reinterpret_cast<float4*>(img4 + i * 4) = make_float4(r, g, b, 0.f);
+}
+cudaError_t launch_img_prep_u8(const uint8_t* img_hwc, const float* mask0, int zero_robot, float* img4, int B, int H,
+                               int W, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(B) * H * W;
+  img_prep_u8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(img_hwc, mask0, zero_robot, img4, B,
+                                                                                H * W);
+  return cudaGetLastError();
+}
+__global__ void __launch_bounds__(256)
+img_prep_nchw_kernel(const float* __restrict__ img, float* __restrict__ img4, int B, int HW) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(B) * HW) return;
+  const size_t b = i / HW;
+  const int pos = static_cast<int>(i % HW);
+  const float* p = img + b * 3 * HW + pos;
+  *reinterpret_cast<float4*>(img4 + i * 4) = make_float4(p[0], p[HW], p[2 * HW], 0.f);
+}
+cudaError_t launch_img_prep_nchw(const float* img_nchw, float* img4, int B, int H, int W, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(B) * H * W;
+  img_prep_nchw_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(img_nchw, img4, B, H * W);
+  return cudaGetLastError();
+}
+__global__ void __launch_bounds__(256)
+goal_prep_kernel(const uint8_t* __restrict__ g, float* __restrict__ g4, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  *reinterpret_cast<float4*>(g4 + static_cast<size_t>(i) * 4) =
+      make_float4(static_cast<float>(g[i * 3 + 0]) / 255.f, static_cast<float>(g[i * 3 + 1]) / 255.f,
+                  static_cast<float>(g[i * 3 + 2]) / 255.f, 0.f);
+}
+cudaError_t launch_goal_prep(const uint8_t* goal_hwc, float* goal4, int G, int H, int W, cudaStream_t s) {
+  const int total = G * H * W;
+  goal_prep_kernel<<<(total + 255) / 256, 256, 0, s>>>(goal_hwc, goal4, total);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- cost finish
+__global__ void __launch_bounds__(128)
+cost_finish_kernel(const float* __restrict__ part, int nparts, int dontcare, float weight, int accumulate,
+                   double* __restrict__ sum_cost, float* __restrict__ step_cost, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* p = part + static_cast<size_t>(b) * nparts * 2;
+  float sq = 0.f, cnt = 0.f;
+  for (int i = 0; i < nparts; ++i) {  // fixed order: deterministic
+    sq += p[2 * i];
+    cnt += p[2 * i + 1];
+  }
+  float dist = sqrtf(sq);
+  if (dontcare) dist = dist / cnt;  // reference divides without +1 (losses.py:259-260)
+  const float cost = weight * (-dist);
+  if (step_cost) step_cost[b] = cost;
+  if (accumulate) sum_cost[b] += static_cast<double>(cost);
+}
+cudaError_t launch_cost_finish(const float* cost_part, int nparts, int dontcare, float weight, int accumulate,
+                               double* sum_cost, float* step_cost, int B, cudaStream_t s) {
+  cost_finish_kernel<<<(B + 127) / 128, 128, 0, s>>>(cost_part, nparts, dontcare, weight, accumulate, sum_cost,
+                                                     step_cost, B);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- block reduction helper
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  T t = (threadIdx.x < nw) ? sh[threadIdx.x] : T(0);
+  if (w == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (l == 0) sh[0] = t;
+  }
+  __syncthreads();
+  return sh[0];
+}
+
+// ---------------------------------------------------------------- stand-alone planning cost (reference layout)
+// One CTA per candidate: reads 3 planes of `curr` (+ mask) once with 128-bit loads; goal image/mask stay L2-resident.
+__global__ void __launch_bounds__(256)
+masked_cost_kernel(const float* __restrict__ curr, const float* __restrict__ goal, const float* __restrict__ cmask,
+                   const float* __restrict__ gmask, int dontcare, float* __restrict__ out, int HW) {
+  __shared__ float sh[32];
+  const size_t b = blockIdx.x;
+  const int q4 = HW / 4;
+  const float4* c0 = reinterpret_cast<const float4*>(curr + b * 3 * HW);
+  const float4* g0 = reinterpret_cast<const float4*>(goal);
+  const float4* cm = cmask ? reinterpret_cast<const float4*>(cmask + b * HW) : nullptr;
+  const float4* gm = gmask ? reinterpret_cast<const float4*>(gmask) : nullptr;
+  float sq = 0.f, cnt = 0.f;
+  for (int i = threadIdx.x; i < q4; i += blockDim.x) {
+    float4 a[3], g[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      a[c] = __ldcs(c0 + c * q4 + i);
+      g[c] = __ldg(g0 + c * q4 + i);
+    }
+    float keep[4] = {1.f, 1.f, 1.f, 1.f};
+    if (dontcare) {
+      float4 m1 = make_float4(0.f, 0.f, 0.f, 0.f), m2 = m1;
+      if (cm) m1 = __ldcs(cm + i);
+      if (gm) m2 = __ldg(gm + i);
+      keep[0] = (m1.x != 0.f || m2.x != 0.f) ? 0.f : 1.f;
+      keep[1] = (m1.y != 0.f || m2.y != 0.f) ? 0.f : 1.f;
+      keep[2] = (m1.z != 0.f || m2.z != 0.f) ? 0.f : 1.f;
+      keep[3] = (m1.w != 0.f || m2.w != 0.f) ? 0.f : 1.f;
+      cnt += keep[0] + keep[1] + keep[2] + keep[3];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float d0 = 255.f * (a[c].x - g[c].x), d1 = 255.f * (a[c].y - g[c].y);
+      const float d2 = 255.f * (a[c].z - g[c].z), d3 = 255.f * (a[c].w - g[c].w);
+      sq += keep[0] * d0 * d0 + keep[1] * d1 * d1 + keep[2] * d2 * d2 + keep[3] * d3 * d3;
+    }
+  }
+  sq = block_sum(sq, sh);
+  if (dontcare) cnt = block_sum(cnt, sh);
+  if (threadIdx.x == 0) {
+    float d = sqrtf(sq);
+    if (dontcare) d = d / cnt;
+    out[b] = -d;
+  }
+}
+cudaError_t launch_masked_cost(const float* curr, const float* goal, const float* curr_mask, const float* goal_mask,
+                               int dontcare, float* out, int B, int HW, cudaStream_t s) {
+  if (HW % 4 != 0) return cudaErrorInvalidValue;
+  if (B == 0) return cudaSuccess;
+  masked_cost_kernel<<<B, 256, 0, s>>>(curr, goal, curr_mask, goal_mask, dontcare, out, HW);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- training criteria (forward values)
+__global__ void __launch_bounds__(1024) l1_loss_kernel(const float* __restrict__ p, const float* __restrict__ t,
+                                                       float* __restrict__ out, long long n) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) acc += static_cast<double>(fabsf(t[i] - p[i]));
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) out[0] = static_cast<float>(acc / static_cast<double>(n));
+}
+cudaError_t launch_l1_loss(const float* pred, const float* target, float* out, int64_t n, cudaStream_t s) {
+  l1_loss_kernel<<<1, 1024, 0, s>>>(pred, target, out, n);
+  return cudaGetLastError();
+}
+__global__ void __launch_bounds__(1024)
+dontcare_l1_kernel(const float* __restrict__ p, const float* __restrict__ t, const float* __restrict__ mask,
+                   float robot_weight, float* __restrict__ out, int B, int HW) {
+  __shared__ double sh[32];
+  double total = 0.0;
+  for (int b = 0; b < B; ++b) {
+    double acc = 0.0, world = 0.0;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      const bool rb = mask[static_cast<size_t>(b) * HW + i] != 0.f;
+      float sd = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const size_t q = (static_cast<size_t>(b) * 3 + c) * HW + i;
+        float d = t[q] - p[q];
+        if (rb) d *= robot_weight;
+        sd += fabsf(d);
+      }
+      acc += sd;
+      world += rb ? 0.0 : 3.0;
+    }
+    acc = block_sum(acc, sh);
+    world = block_sum(world, sh);
+    total += acc / (world + 1.0);
+  }
+  if (threadIdx.x == 0) out[0] = static_cast<float>(total / B);
+}
+cudaError_t launch_dontcare_l1_loss(const float* pred, const float* target, const float* mask, float robot_weight,
+                                    float* out, int B, int HW, cudaStream_t s) {
+  dontcare_l1_kernel<<<1, 1024, 0, s>>>(pred, target, mask, robot_weight, out, B, HW);
+  return cudaGetLastError();
+}
+__global__ void __launch_bounds__(1024)
+kl_loss_kernel(const float* __restrict__ mu1, const float* __restrict__ lv1, const float* __restrict__ mu2,
+               const float* __restrict__ lv2, float* __restrict__ out, long long n, int bs) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float s1 = expf(0.5f * lv1[i]), s2 = expf(0.5f * lv2[i]);
+    const float dm = mu1[i] - mu2[i];
+    const float k = logf(s2 / s1) + (expf(lv1[i]) + dm * dm) / (2.f * expf(lv2[i])) - 0.5f;
+    acc += static_cast<double>(k);
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) out[0] = static_cast<float>(acc / bs);
+}
+cudaError_t launch_kl_loss(const float* mu1, const float* lv1, const float* mu2, const float* lv2, float* out,
+                           int64_t n, int bs, cudaStream_t s) {
+  kl_loss_kernel<<<1, 1024, 0, s>>>(mu1, lv1, mu2, lv2, out, n, bs);
+  return cudaGetLastError();
+}
+
+}  // namespace rac

@@ -1,0 +1,54 @@
+// Host-side launchers of the small non-GEMM kernels (misc_kernels.cu, cem_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace rac {
+
+// encoder.c1.0 (reference vgg_64.py:99-101 via vgg_layer :8-18): 3x3 conv over [rgb | mask_t | mask_t+1], folded
+// eval BatchNorm, LeakyReLU(0.2). K = 27..45 is too small for a tensor-core tile; HBM-write bound.
+// mask planes of consecutive candidates are `mask_bstride` floats apart.
+cudaError_t launch_first_conv(const float* img4, const float* mask_a, const float* mask_b, long long mask_bstride,
+                              const float* w, const float* bias, __nv_bfloat16* out, int B, int H, int W, int cin,
+                              cudaStream_t s);
+// nn.MaxPool2d(2,2) (reference vgg_64.py:120,126-128) over a channel slice of an NHWC buffer
+cudaError_t launch_maxpool2(const __nv_bfloat16* in, int in_cstride, int in_coff, __nv_bfloat16* out, int B, int H,
+                            int W, int C, cudaStream_t s);
+// tiled action / robot-state channels (reference dynamics.py:591-603) as one zero-padded 64-channel k-block
+// action rows are `astride` floats apart (a time slice of an (n, steps, action_dim) tensor); action may be null
+// (posterior input: robot state only, reference dynamics.py:621-623)
+cudaError_t launch_aux_tile(const float* action, int astride, int adim, const float* r, const float* r2, int rdim,
+                            __nv_bfloat16* aux, int B, int HW, cudaStream_t s);
+// start image uint8 HWC -> per-candidate fp32 NHWC4 / 255, robot pixels of mask_0 zeroed
+// (reference trajectory_sampler.py:130-131,141-142)
+cudaError_t launch_img_prep_u8(const uint8_t* img_hwc, const float* mask0, int zero_robot, float* img4, int B, int H,
+                               int W, cudaStream_t s);
+// NCHW fp32 (B,3,H,W) -> NHWC4
+cudaError_t launch_img_prep_nchw(const float* img_nchw, float* img4, int B, int H, int W, cudaStream_t s);
+// goal images uint8 (G,H,W,3) -> fp32 (G,H,W,4) / 255 (reference trajectory_sampler.py:77-79)
+cudaError_t launch_goal_prep(const uint8_t* goal_hwc, float* goal4, int G, int H, int W, cudaStream_t s);
+// per-candidate cost from the per-tile partials of the frame epilogue (reference losses.py:224-235,244-263,307-335;
+// fp64 accumulation over steps as trajectory_sampler.py:74,169)
+cudaError_t launch_cost_finish(const float* cost_part, int nparts, int dontcare, float weight, int accumulate,
+                               double* sum_cost, float* step_cost, int B, cudaStream_t s);
+// stand-alone planning cost in the reference's own tensor layout (NCHW fp32): ImgL2Cost / ImgDontcareCost
+cudaError_t launch_masked_cost(const float* curr, const float* goal, const float* curr_mask, const float* goal_mask,
+                               int dontcare, float* out, int B, int HW, cudaStream_t s);
+// training criteria, forward value only (reference losses.py:13-19,35-50,97-106)
+cudaError_t launch_l1_loss(const float* pred, const float* target, float* out, int64_t n, cudaStream_t s);
+cudaError_t launch_dontcare_l1_loss(const float* pred, const float* target, const float* mask, float robot_weight,
+                                    float* out, int B, int HW, cudaStream_t s);
+cudaError_t launch_kl_loss(const float* mu1, const float* lv1, const float* mu2, const float* lv2, float* out,
+                           int64_t n, int bs, cudaStream_t s);
+
+// ---- CEM (cem_kernels.cu) ----
+cudaError_t launch_cem_sample(const float* mean, const float* stdv, const float* noise, unsigned long long seed,
+                              int iter, int n_total, int L, int adim_model, int cand_offset, int n_local,
+                              float clampv, float* act2, float* act5, cudaStream_t s);
+cudaError_t launch_topk(const double* costs, int n, int k, int64_t* idx_out, double* val_out, cudaStream_t s);
+cudaError_t launch_refit(const float* act2, int L2, const int64_t* idx, int k, float std_floor, float* mean_out,
+                         float* std_out, cudaStream_t s);
+cudaError_t cem_set_attributes();
+
+}  // namespace rac

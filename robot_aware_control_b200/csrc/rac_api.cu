@@ -1,0 +1,871 @@
+// C ABI (include/racb200.h): handle, packed weights, activation workspace, TMA descriptors and the launch sequences
+// for one SVG prediction step, the autoregressive rollout with fused planning cost, and the device-resident CEM loop.
+#include "../../include/racb200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "conv.cuh"
+#include "misc_kernels.cuh"
+
+namespace {
+
+using namespace rac;
+typedef __nv_bfloat16 bf16;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct LayerSpec {
+  int ks = 3;
+  int ctot = 0;     // padded input channels per tap
+  int n_packed = 0; // padded output columns
+  int cout = 0;     // valid output columns (packed order)
+  int block_n = 128;
+  bool first = false;  // fp32 first layer
+};
+
+struct Layer {
+  void* w = nullptr;
+  float* bias = nullptr;
+  bool loaded = false;
+};
+
+struct Workspace {
+  int B = 0;
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  float* img = nullptr;
+  bf16 *a1 = nullptr, *cat5 = nullptr, *p1 = nullptr, *a2 = nullptr, *cat4 = nullptr, *p2 = nullptr, *a3a = nullptr,
+       *a3b = nullptr, *cat3 = nullptr, *p3 = nullptr, *a4a = nullptr, *a4b = nullptr, *h4 = nullptr;
+  bf16 *s1 = nullptr, *s2 = nullptr, *s3 = nullptr;  // keep_skip alternates (lazy)
+  bf16 *aux = nullptr, *auxp = nullptr, *pin = nullptr, *postin = nullptr, *fin = nullptr, *z = nullptr,
+       *zpost = nullptr;
+  bf16* hs[3][2][2] = {};  // [prior, post, frame predictor][layer][ping-pong]
+  float* cs[3][2] = {};
+  bf16 *d2a = nullptr, *d2b = nullptr, *d3a = nullptr, *d3b = nullptr, *d4a = nullptr, *d5 = nullptr;
+  float* cost_part = nullptr;
+  float* goal4 = nullptr;
+  // CEM scratch
+  float *act2 = nullptr, *act5 = nullptr, *mean = nullptr, *stdv = nullptr;
+  double* sum_cost = nullptr;
+  int64_t* elite = nullptr;
+  int cem_n = 0, cem_steps = 0;
+  // ops
+  ConvOp enc[2][10];     // [keep_skip][layer 1..9]
+  bool enc_built[2] = {false, false};
+  ConvOp in_conv[3];     // prior_in, post_in, fp_in
+  ConvOp lstm[3][2][2];  // [which][layer][parity]
+  ConvOp gauss[2][2];    // [prior, post][parity]
+  ConvOp dec[10][2];     // [layer][parity] (only dec[0] depends on parity)
+  std::unordered_map<std::string, std::pair<void*, std::pair<int64_t, int>>> named;
+};
+
+constexpr int kMaxGoals = 16;
+
+}  // namespace
+
+struct rac_handle {
+  rac_config cfg;
+  int device = 0;
+  int num_sms = 148;
+  int H = 48, W = 64, hl = 6, wl = 8;
+  int enc_cin = 3;
+  LayerSpec spec[RAC_L_COUNT];
+  Layer layer[RAC_L_COUNT];
+  Workspace ws;
+  int cur[3] = {0, 0, 0};  // ping-pong index of the live hidden state per LSTM stack
+  EncodeTiledFn encode = nullptr;
+  int64_t launches = 0;
+  char err[512] = {0};
+};
+
+namespace {
+
+int fail(rac_handle* h, int code, const char* fmt, ...) {
+  if (h) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(h->err, sizeof(h->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(h, RAC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define CKR(call)                  \
+  do {                             \
+    int r_ = (call);               \
+    if (r_ != RAC_OK) return r_;   \
+  } while (0)
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+void fill_specs(rac_handle* h) {
+  const rac_config& c = h->cfg;
+  const int g = c.g_dim;
+  auto set = [&](int id, int ks, int ctot, int cout, int block_n) {
+    LayerSpec& s = h->spec[id];
+    s.ks = ks; s.ctot = ctot; s.cout = cout; s.block_n = block_n; s.n_packed = round_up(cout, block_n);
+  };
+  h->enc_cin = 3 + (c.use_mask ? 1 : 0) + ((c.use_mask && c.use_future_mask) ? 1 : 0);
+  h->spec[RAC_L_ENC_C1_0].first = true;
+  h->spec[RAC_L_ENC_C1_0].ks = 3; h->spec[RAC_L_ENC_C1_0].ctot = h->enc_cin;
+  h->spec[RAC_L_ENC_C1_0].cout = 64; h->spec[RAC_L_ENC_C1_0].n_packed = 64; h->spec[RAC_L_ENC_C1_0].block_n = 64;
+  set(RAC_L_ENC_C1_1, 3, 64, 64, 64);
+  set(RAC_L_ENC_C2_0, 3, 64, 128, 128);
+  set(RAC_L_ENC_C2_1, 3, 128, 128, 128);
+  set(RAC_L_ENC_C3_0, 3, 128, 256, 128);
+  set(RAC_L_ENC_C3_1, 3, 256, 256, 128);
+  set(RAC_L_ENC_C3_2, 3, 256, 256, 128);
+  set(RAC_L_ENC_C4_0, 3, 256, 512, 128);
+  set(RAC_L_ENC_C4_1, 3, 512, 512, 128);
+  set(RAC_L_ENC_C4_2, 3, 512, g, 128);
+  set(RAC_L_PRIOR_IN, 3, 64 + g, g, 128);
+  set(RAC_L_PRIOR_LSTM0, 5, 2 * g, 4 * g, 128);
+  set(RAC_L_PRIOR_LSTM1, 3, 2 * g, 4 * g, 128);
+  set(RAC_L_PRIOR_GAUSS, 3, g, 128, 128);
+  set(RAC_L_FP_IN, 3, 64 + g + 64, g, 128);
+  set(RAC_L_FP_LSTM0, 5, 2 * g, 4 * g, 128);
+  set(RAC_L_FP_LSTM1, 3, 2 * g, 4 * g, 128);
+  set(RAC_L_DEC_UPC2_0, 3, g, 512, 128);
+  set(RAC_L_DEC_UPC2_1, 3, 512, 512, 128);
+  set(RAC_L_DEC_UPC2_2, 3, 512, 256, 128);
+  set(RAC_L_DEC_UPC3_0, 3, 512, 256, 128);
+  set(RAC_L_DEC_UPC3_1, 3, 256, 256, 128);
+  set(RAC_L_DEC_UPC3_2, 3, 256, 128, 128);
+  set(RAC_L_DEC_UPC4_0, 3, 256, 128, 128);
+  set(RAC_L_DEC_UPC4_1, 3, 128, 64, 64);
+  set(RAC_L_DEC_UPC5_0, 3, 128, 64, 64);
+  set(RAC_L_DEC_UPC5_1, 3, 64, 4, 16);
+  set(RAC_L_POST_IN, 3, (c.use_robot_state ? 64 : 0) + g, g, 128);
+  set(RAC_L_POST_LSTM0, 5, 2 * g, 4 * g, 128);
+  set(RAC_L_POST_LSTM1, 3, 2 * g, 4 * g, 128);
+  set(RAC_L_POST_GAUSS, 3, g, 128, 128);
+}
+
+int64_t spec_w_elems(const LayerSpec& s) {
+  if (s.first) return static_cast<int64_t>(9) * s.ctot * 64;
+  return static_cast<int64_t>(s.n_packed) * s.ks * s.ks * s.ctot;
+}
+
+// ------------------------------------------------------------------ tensor maps
+int encode_act_map(rac_handle* h, CUtensorMap* m, const bf16* ptr, int C, int B, int H, int W, int BH, int NB) {
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
+                           static_cast<cuuint64_t>(H) * W * C * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(W), static_cast<cuuint32_t>(BH),
+                       static_cast<cuuint32_t>(NB)};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(ptr), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, RAC_ERR_CUDA, "cuTensorMapEncodeTiled(activation C=%d) failed: %d", C, (int)r);
+  return RAC_OK;
+}
+int encode_w_map(rac_handle* h, CUtensorMap* m, const bf16* ptr, int K, int N, int block_n) {
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(block_n)};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, RAC_ERR_CUDA, "cuTensorMapEncodeTiled(weights K=%d N=%d) failed: %d", K, N, (int)r);
+  return RAC_OK;
+}
+
+struct Src {
+  const bf16* p;
+  int C;
+};
+
+int ilog2(int v) {
+  int s = 0;
+  while ((1 << s) < v) ++s;
+  return s;
+}
+
+// Build one convolution op: geometry, TMA descriptors, raw pointers, constant epilogue fields.
+int make_conv(rac_handle* h, ConvOp* op, const char* name, int layer, int H, int W, std::vector<Src> srcs, int epi) {
+  const LayerSpec& s = h->spec[layer];
+  const int B = h->ws.B;
+  memset(op, 0, sizeof(*op));
+  op->name = name;
+  op->block_n = s.block_n;
+  op->epi = epi;
+  ConvGeom& g = op->g;
+  g.B = B; g.H = H; g.W = W; g.ks = s.ks; g.pad = s.ks / 2;
+  switch (W) {
+    case 64: g.BH = 2; g.NB = 1; break;
+    case 32: g.BH = 4; g.NB = 1; break;
+    case 16: g.BH = 4; g.NB = 2; break;
+    case 8: g.BH = 2; g.NB = 8; break;
+    default: return fail(h, RAC_ERR_INVALID, "unsupported feature-map width %d", W);
+  }
+  if (H % g.BH != 0) return fail(h, RAC_ERR_INVALID, "feature-map height %d not divisible by tile rows %d", H, g.BH);
+  g.nsrc = static_cast<int>(srcs.size());
+  g.ctot = 0;
+  for (int i = 0; i < g.nsrc; ++i) {
+    if (srcs[i].C % kBlockK != 0) return fail(h, RAC_ERR_INVALID, "%s: source channels %d not a multiple of 64", name, srcs[i].C);
+    g.src_kb[i] = srcs[i].C / kBlockK;
+    g.ctot += srcs[i].C;
+    op->raw.src[i] = srcs[i].p;
+    CKR(encode_act_map(h, &op->tm.a[i], srcs[i].p, srcs[i].C, B, H, W, g.BH, g.NB));
+  }
+  if (g.ctot != s.ctot) return fail(h, RAC_ERR_INVALID, "%s: channel mismatch %d vs packed %d", name, g.ctot, s.ctot);
+  g.tiles_per_img = H / g.BH;
+  g.num_m_tiles = ((B + g.NB - 1) / g.NB) * g.tiles_per_img;
+  g.num_n_tiles = s.n_packed / s.block_n;
+  g.w_shift = ilog2(W);
+  g.bhw_shift = ilog2(g.BH * W);
+  const bf16* wp = static_cast<const bf16*>(h->layer[layer].w);
+  op->raw.w = wp;
+  CKR(encode_w_map(h, &op->tm.w, wp, s.ks * s.ks * s.ctot, s.n_packed, s.block_n));
+  op->e.bias = h->layer[layer].bias;
+  op->e.cout = s.cout;
+  return RAC_OK;
+}
+
+void set_act(ConvOp* op, bf16* out, int cstride, int coff, int upsample, int lrelu) {
+  op->e.out = out; op->e.out_cstride = cstride; op->e.out_coff = coff; op->e.upsample = upsample; op->e.lrelu = lrelu;
+}
+
+int launch(rac_handle* h, const ConvOp& op, cudaStream_t st) {
+  cudaError_t e = h->cfg.conv_impl == 1 ? launch_conv_simt(op, st) : launch_conv_tc(op, h->num_sms, st);
+  if (e != cudaSuccess) return fail(h, RAC_ERR_CUDA, "launch of conv '%s' failed: %s", op.name, cudaGetErrorString(e));
+  h->launches++;
+  return RAC_OK;
+}
+
+// ------------------------------------------------------------------ workspace
+struct Bump {
+  size_t off = 0;
+  char* base = nullptr;
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 1023) / 1024 * 1024;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+void carve(rac_handle* h, Bump& bp, int B) {
+  Workspace& w = h->ws;
+  const size_t n = static_cast<size_t>(B);
+  const int g = h->cfg.g_dim;
+  const size_t P0 = 48 * 64, P1 = 24 * 32, P2 = 12 * 16, P3 = 6 * 8;
+  w.img = bp.take<float>(n * P0 * 4);
+  w.a1 = bp.take<bf16>(n * P0 * 64);
+  w.cat5 = bp.take<bf16>(n * P0 * 128);
+  w.p1 = bp.take<bf16>(n * P1 * 64);
+  w.a2 = bp.take<bf16>(n * P1 * 128);
+  w.cat4 = bp.take<bf16>(n * P1 * 256);
+  w.p2 = bp.take<bf16>(n * P2 * 128);
+  w.a3a = bp.take<bf16>(n * P2 * 256);
+  w.a3b = bp.take<bf16>(n * P2 * 256);
+  w.cat3 = bp.take<bf16>(n * P2 * 512);
+  w.p3 = bp.take<bf16>(n * P3 * 256);
+  w.a4a = bp.take<bf16>(n * P3 * 512);
+  w.a4b = bp.take<bf16>(n * P3 * 512);
+  w.h4 = bp.take<bf16>(n * P3 * g);
+  w.aux = bp.take<bf16>(n * P3 * 64);
+  w.auxp = bp.take<bf16>(n * P3 * 64);
+  w.pin = bp.take<bf16>(n * P3 * g);
+  w.postin = bp.take<bf16>(n * P3 * g);
+  w.fin = bp.take<bf16>(n * P3 * g);
+  w.z = bp.take<bf16>(n * P3 * 64);
+  w.zpost = bp.take<bf16>(n * P3 * 64);
+  for (int l = 0; l < 3; ++l)
+    for (int k = 0; k < 2; ++k) {
+      for (int p = 0; p < 2; ++p) w.hs[l][k][p] = bp.take<bf16>(n * P3 * g);
+      w.cs[l][k] = bp.take<float>(n * P3 * g);
+    }
+  w.d2a = bp.take<bf16>(n * P3 * 512);
+  w.d2b = bp.take<bf16>(n * P3 * 512);
+  w.d3a = bp.take<bf16>(n * P2 * 256);
+  w.d3b = bp.take<bf16>(n * P2 * 256);
+  w.d4a = bp.take<bf16>(n * P1 * 128);
+  w.d5 = bp.take<bf16>(n * P0 * 64);
+  w.cost_part = bp.take<float>(n * 96 * 2);
+  w.goal4 = bp.take<float>(static_cast<size_t>(kMaxGoals) * P0 * 4);
+}
+
+int build_enc_ops(rac_handle* h, int ks) {
+  Workspace& w = h->ws;
+  ConvOp* e = w.enc[ks];
+  const int g = h->cfg.g_dim;
+  // h1/h2/h3 normally land in the second channel half of the decoder concat buffers (torch.cat([up, skip]),
+  // vgg_64.py:236-240); with keep_skip they go to side buffers so that the held skip tensors survive.
+  bf16* o1 = ks ? w.s1 : w.cat5; const int c1s = ks ? 64 : 128, c1o = ks ? 0 : 64;
+  bf16* o2 = ks ? w.s2 : w.cat4; const int c2s = ks ? 128 : 256, c2o = ks ? 0 : 128;
+  bf16* o3 = ks ? w.s3 : w.cat3; const int c3s = ks ? 256 : 512, c3o = ks ? 0 : 256;
+  CKR(make_conv(h, &e[1], "encoder.c1.1", RAC_L_ENC_C1_1, 48, 64, {{w.a1, 64}}, EPI_ACT)); set_act(&e[1], o1, c1s, c1o, 0, 1);
+  CKR(make_conv(h, &e[2], "encoder.c2.0", RAC_L_ENC_C2_0, 24, 32, {{w.p1, 64}}, EPI_ACT)); set_act(&e[2], w.a2, 128, 0, 0, 1);
+  CKR(make_conv(h, &e[3], "encoder.c2.1", RAC_L_ENC_C2_1, 24, 32, {{w.a2, 128}}, EPI_ACT)); set_act(&e[3], o2, c2s, c2o, 0, 1);
+  CKR(make_conv(h, &e[4], "encoder.c3.0", RAC_L_ENC_C3_0, 12, 16, {{w.p2, 128}}, EPI_ACT)); set_act(&e[4], w.a3a, 256, 0, 0, 1);
+  CKR(make_conv(h, &e[5], "encoder.c3.1", RAC_L_ENC_C3_1, 12, 16, {{w.a3a, 256}}, EPI_ACT)); set_act(&e[5], w.a3b, 256, 0, 0, 1);
+  CKR(make_conv(h, &e[6], "encoder.c3.2", RAC_L_ENC_C3_2, 12, 16, {{w.a3b, 256}}, EPI_ACT)); set_act(&e[6], o3, c3s, c3o, 0, 1);
+  CKR(make_conv(h, &e[7], "encoder.c4.0", RAC_L_ENC_C4_0, 6, 8, {{w.p3, 256}}, EPI_ACT)); set_act(&e[7], w.a4a, 512, 0, 0, 1);
+  CKR(make_conv(h, &e[8], "encoder.c4.1", RAC_L_ENC_C4_1, 6, 8, {{w.a4a, 512}}, EPI_ACT)); set_act(&e[8], w.a4b, 512, 0, 0, 1);
+  CKR(make_conv(h, &e[9], "encoder.c4.2", RAC_L_ENC_C4_2, 6, 8, {{w.a4b, 512}}, EPI_ACT)); set_act(&e[9], w.h4, g, 0, 0, 1);
+  w.enc_built[ks] = true;
+  return RAC_OK;
+}
+
+int build_ops(rac_handle* h) {
+  Workspace& w = h->ws;
+  const rac_config& c = h->cfg;
+  const int g = c.g_dim;
+  CKR(build_enc_ops(h, 0));
+  // input convolutions (dynamics.py:496-498,512-513): tiled action/state channels arrive as the 64-channel `aux` block
+  CKR(make_conv(h, &w.in_conv[0], "prior_input_conv", RAC_L_PRIOR_IN, 6, 8, {{w.aux, 64}, {w.h4, g}}, EPI_ACT));
+  set_act(&w.in_conv[0], w.pin, g, 0, 0, 0);
+  if (c.use_robot_state) {
+    CKR(make_conv(h, &w.in_conv[1], "posterior_input_conv", RAC_L_POST_IN, 6, 8, {{w.auxp, 64}, {w.h4, g}}, EPI_ACT));
+  } else {
+    CKR(make_conv(h, &w.in_conv[1], "posterior_input_conv", RAC_L_POST_IN, 6, 8, {{w.h4, g}}, EPI_ACT));
+  }
+  set_act(&w.in_conv[1], w.postin, g, 0, 0, 0);
+  CKR(make_conv(h, &w.in_conv[2], "frame_pred_input_conv", RAC_L_FP_IN, 6, 8, {{w.aux, 64}, {w.h4, g}, {w.z, 64}}, EPI_ACT));
+  set_act(&w.in_conv[2], w.fin, g, 0, 0, 0);
+  const int l0[3] = {RAC_L_PRIOR_LSTM0, RAC_L_POST_LSTM0, RAC_L_FP_LSTM0};
+  const int l1[3] = {RAC_L_PRIOR_LSTM1, RAC_L_POST_LSTM1, RAC_L_FP_LSTM1};
+  bf16* xin[3] = {w.pin, w.postin, w.fin};
+  const char* n0[3] = {"prior.lstm.0", "posterior.lstm.0", "frame_predictor.lstm.0"};
+  const char* n1[3] = {"prior.lstm.1", "posterior.lstm.1", "frame_predictor.lstm.1"};
+  for (int l = 0; l < 3; ++l)
+    for (int p = 0; p < 2; ++p) {
+      ConvOp* a = &w.lstm[l][0][p];
+      CKR(make_conv(h, a, n0[l], l0[l], 6, 8, {{xin[l], g}, {w.hs[l][0][p], g}}, EPI_LSTM));
+      a->e.c_state = w.cs[l][0]; a->e.h_out = w.hs[l][0][p ^ 1]; a->e.hid = g;
+      ConvOp* b = &w.lstm[l][1][p];
+      CKR(make_conv(h, b, n1[l], l1[l], 6, 8, {{w.hs[l][0][p ^ 1], g}, {w.hs[l][1][p], g}}, EPI_LSTM));
+      b->e.c_state = w.cs[l][1]; b->e.h_out = w.hs[l][1][p ^ 1]; b->e.hid = g;
+    }
+  for (int p = 0; p < 2; ++p) {
+    CKR(make_conv(h, &w.gauss[0][p], "prior.mu_net|logvar_net", RAC_L_PRIOR_GAUSS, 6, 8, {{w.hs[0][1][p ^ 1], g}}, EPI_GAUSS));
+    CKR(make_conv(h, &w.gauss[1][p], "posterior.mu_net|logvar_net", RAC_L_POST_GAUSS, 6, 8, {{w.hs[1][1][p ^ 1], g}}, EPI_GAUSS));
+    for (int q = 0; q < 2; ++q) { w.gauss[q][p].e.z_dim = c.z_dim; w.gauss[q][p].e.z_out = w.z; }
+    CKR(make_conv(h, &w.dec[0][p], "decoder.upc2.0", RAC_L_DEC_UPC2_0, 6, 8, {{w.hs[2][1][p ^ 1], g}}, EPI_ACT));
+    set_act(&w.dec[0][p], w.d2a, 512, 0, 0, 1);
+  }
+  ConvOp(*d)[2] = w.dec;
+  CKR(make_conv(h, &d[1][0], "decoder.upc2.1", RAC_L_DEC_UPC2_1, 6, 8, {{w.d2a, 512}}, EPI_ACT)); set_act(&d[1][0], w.d2b, 512, 0, 0, 1);
+  CKR(make_conv(h, &d[2][0], "decoder.upc2.2", RAC_L_DEC_UPC2_2, 6, 8, {{w.d2b, 512}}, EPI_ACT)); set_act(&d[2][0], w.cat3, 512, 0, 1, 1);
+  CKR(make_conv(h, &d[3][0], "decoder.upc3.0", RAC_L_DEC_UPC3_0, 12, 16, {{w.cat3, 512}}, EPI_ACT)); set_act(&d[3][0], w.d3a, 256, 0, 0, 1);
+  CKR(make_conv(h, &d[4][0], "decoder.upc3.1", RAC_L_DEC_UPC3_1, 12, 16, {{w.d3a, 256}}, EPI_ACT)); set_act(&d[4][0], w.d3b, 256, 0, 0, 1);
+  CKR(make_conv(h, &d[5][0], "decoder.upc3.2", RAC_L_DEC_UPC3_2, 12, 16, {{w.d3b, 256}}, EPI_ACT)); set_act(&d[5][0], w.cat4, 256, 0, 1, 1);
+  CKR(make_conv(h, &d[6][0], "decoder.upc4.0", RAC_L_DEC_UPC4_0, 24, 32, {{w.cat4, 256}}, EPI_ACT)); set_act(&d[6][0], w.d4a, 128, 0, 0, 1);
+  CKR(make_conv(h, &d[7][0], "decoder.upc4.1", RAC_L_DEC_UPC4_1, 24, 32, {{w.d4a, 128}}, EPI_ACT)); set_act(&d[7][0], w.cat5, 128, 0, 1, 1);
+  CKR(make_conv(h, &d[8][0], "decoder.upc5.0", RAC_L_DEC_UPC5_0, 48, 64, {{w.cat5, 128}}, EPI_ACT)); set_act(&d[8][0], w.d5, 64, 0, 0, 1);
+  CKR(make_conv(h, &d[9][0], "decoder.upc5.1", RAC_L_DEC_UPC5_1, 48, 64, {{w.d5, 64}}, EPI_FRAME));
+  return RAC_OK;
+}
+
+void name_buffers(rac_handle* h) {
+  Workspace& w = h->ws;
+  const size_t n = static_cast<size_t>(w.B);
+  const int g = h->cfg.g_dim;
+  auto put = [&](const char* k, void* p, size_t elems, int eb) { w.named[k] = {p, {static_cast<int64_t>(elems), eb}}; };
+  put("img", w.img, n * 3072 * 4, 4);
+  put("a1", w.a1, n * 3072 * 64, 2);
+  put("cat5", w.cat5, n * 3072 * 128, 2);
+  put("cat4", w.cat4, n * 768 * 256, 2);
+  put("cat3", w.cat3, n * 192 * 512, 2);
+  put("p1", w.p1, n * 768 * 64, 2);
+  put("a2", w.a2, n * 768 * 128, 2);
+  put("h4", w.h4, n * 48 * g, 2);
+  put("aux", w.aux, n * 48 * 64, 2);
+  put("prior_in", w.pin, n * 48 * g, 2);
+  put("post_in", w.postin, n * 48 * g, 2);
+  put("frame_in", w.fin, n * 48 * g, 2);
+  put("z", w.z, n * 48 * 64, 2);
+  put("d2a", w.d2a, n * 48 * 512, 2);
+  put("d2b", w.d2b, n * 48 * 512, 2);
+  put("d3a", w.d3a, n * 192 * 256, 2);
+  put("d4a", w.d4a, n * 768 * 128, 2);
+  put("d5", w.d5, n * 3072 * 64, 2);
+  put("cost_part", w.cost_part, n * 96 * 2, 4);
+  const char* hn[3] = {"prior", "post", "fp"};
+  for (int l = 0; l < 3; ++l)
+    for (int k = 0; k < 2; ++k) {
+      for (int p = 0; p < 2; ++p) {
+        char key[64];
+        snprintf(key, sizeof(key), "%s.h%d.%d", hn[l], k, p);
+        put(key, w.hs[l][k][p], n * 48 * g, 2);
+      }
+      char key[64];
+      snprintf(key, sizeof(key), "%s.c%d", hn[l], k);
+      put(key, w.cs[l][k], n * 48 * g, 4);
+    }
+}
+
+void free_ws(rac_handle* h) {
+  Workspace& w = h->ws;
+  if (w.arena) cudaFree(w.arena);
+  if (w.s1) cudaFree(w.s1);
+  if (w.s2) cudaFree(w.s2);
+  if (w.s3) cudaFree(w.s3);
+  if (w.act2) cudaFree(w.act2);
+  if (w.act5) cudaFree(w.act5);
+  if (w.mean) cudaFree(w.mean);
+  if (w.sum_cost) cudaFree(w.sum_cost);
+  if (w.elite) cudaFree(w.elite);
+  w = Workspace();
+}
+
+int ensure_keep_skip(rac_handle* h) {
+  Workspace& w = h->ws;
+  if (w.enc_built[1]) return RAC_OK;
+  const size_t n = static_cast<size_t>(w.B);
+  CK(cudaMalloc(&w.s1, n * 3072 * 64 * 2));
+  CK(cudaMalloc(&w.s2, n * 768 * 128 * 2));
+  CK(cudaMalloc(&w.s3, n * 192 * 256 * 2));
+  return build_enc_ops(h, 1);
+}
+
+struct StepArgs {
+  int n;
+  const float* mask_a;  // mask_t      (n,H,W) or null
+  const float* mask_b;  // mask_{t+1}  (n,H,W) or null
+  long long mask_bstride;  // floats between the mask planes of consecutive candidates
+  const float* robot;
+  const float* robot_next;
+  const float* action;
+  int action_stride;
+  const float* eps;
+  unsigned long long seed;
+  unsigned int noise_ctr;
+  int cand_offset;
+  int sample_mean;
+  int use_posterior;
+  const float* next_robot;
+  const float* eps_post;
+  int force_use_prior;
+  int keep_skip;
+  float *mu_p, *logvar_p, *mu, *logvar;
+  // frame epilogue
+  const float* curr_img;  // composite source (null: raw x_pred only)
+  float* next_img;
+  const float* mask_next;
+  const float* goal_img;
+  const float* goal_mask;
+  float* xpred_out;
+  float* cost_part;
+  int zero_robot, dontcare;
+};
+
+// One SVGConvModel.forward (dynamics.py:544-644) + compositing / cost epilogue (trajectory_sampler.py:148-168).
+int run_step(rac_handle* h, const StepArgs& a, cudaStream_t st) {
+  Workspace& w = h->ws;
+  const rac_config& c = h->cfg;
+  const int B = w.B;
+  const int ks = a.keep_skip ? 1 : 0;
+  if (ks) CKR(ensure_keep_skip(h));
+  // ---- encoder (vgg_64.py:122-129)
+  CK(launch_first_conv(w.img, c.use_mask ? a.mask_a : nullptr, (c.use_mask && c.use_future_mask) ? a.mask_b : nullptr,
+                       a.mask_bstride, static_cast<const float*>(h->layer[RAC_L_ENC_C1_0].w), h->layer[RAC_L_ENC_C1_0].bias, w.a1, B,
+                       48, 64, h->enc_cin, st));
+  h->launches++;
+  ConvOp* e = w.enc[ks];
+  CKR(launch(h, e[1], st));
+  CK(launch_maxpool2(e[1].e.out, e[1].e.out_cstride, e[1].e.out_coff, w.p1, B, 48, 64, 64, st));
+  CKR(launch(h, e[2], st));
+  CKR(launch(h, e[3], st));
+  CK(launch_maxpool2(e[3].e.out, e[3].e.out_cstride, e[3].e.out_coff, w.p2, B, 24, 32, 128, st));
+  CKR(launch(h, e[4], st));
+  CKR(launch(h, e[5], st));
+  CKR(launch(h, e[6], st));
+  CK(launch_maxpool2(e[6].e.out, e[6].e.out_cstride, e[6].e.out_coff, w.p3, B, 12, 16, 256, st));
+  CKR(launch(h, e[7], st));
+  CKR(launch(h, e[8], st));
+  CKR(launch(h, e[9], st));
+  // ---- tiled action / state channels (dynamics.py:591-603)
+  CK(launch_aux_tile(a.action, a.action_stride, c.action_dim, c.use_robot_state ? a.robot : nullptr,
+                     (c.use_robot_state && c.use_future_robot_state) ? a.robot_next : nullptr, c.robot_dim, w.aux, B,
+                     48, st));
+  h->launches += 4;
+  // ---- learned prior (dynamics.py:594-610)
+  CKR(launch(h, w.in_conv[0], st));
+  {
+    const int p = h->cur[0];
+    CKR(launch(h, w.lstm[0][0][p], st));
+    CKR(launch(h, w.lstm[0][1][p], st));
+    ConvOp gop = w.gauss[0][p];
+    gop.e.eps = a.eps; gop.e.mu_out = a.mu_p; gop.e.logvar_out = a.logvar_p; gop.e.sample_mean = a.sample_mean;
+    gop.e.seed = a.seed; gop.e.noise_ctr = a.noise_ctr; gop.e.cand_offset = a.cand_offset; gop.e.z_out = w.z;
+    CKR(launch(h, gop, st));
+    h->cur[0] ^= 1;
+  }
+  // ---- posterior (dynamics.py:613-629); h_target re-encodes the CURRENT frame (reference quirk, :619) == h4
+  if (a.use_posterior) {
+    if (c.use_robot_state) {
+      CK(launch_aux_tile(nullptr, 0, 0, a.next_robot, nullptr, c.robot_dim, w.auxp, B, 48, st));
+      h->launches++;
+    }
+    CKR(launch(h, w.in_conv[1], st));
+    const int p = h->cur[1];
+    CKR(launch(h, w.lstm[1][0][p], st));
+    CKR(launch(h, w.lstm[1][1][p], st));
+    ConvOp gop = w.gauss[1][p];
+    gop.e.eps = a.eps_post; gop.e.mu_out = a.mu; gop.e.logvar_out = a.logvar; gop.e.sample_mean = 0;
+    gop.e.seed = a.seed ^ 0x9e3779b97f4a7c15ull; gop.e.noise_ctr = a.noise_ctr; gop.e.cand_offset = a.cand_offset;
+    gop.e.z_out = a.force_use_prior ? w.zpost : w.z;
+    CKR(launch(h, gop, st));
+    h->cur[1] ^= 1;
+  }
+  // ---- frame predictor (dynamics.py:631-641)
+  CKR(launch(h, w.in_conv[2], st));
+  const int pf = h->cur[2];
+  CKR(launch(h, w.lstm[2][0][pf], st));
+  CKR(launch(h, w.lstm[2][1][pf], st));
+  h->cur[2] ^= 1;
+  // ---- decoder (vgg_64.py:223-241)
+  CKR(launch(h, w.dec[0][pf], st));
+  for (int i = 1; i < 9; ++i) CKR(launch(h, w.dec[i][0], st));
+  ConvOp fop = w.dec[9][0];
+  fop.e.curr_img = a.curr_img; fop.e.next_img = a.next_img; fop.e.mask_next = a.mask_next;
+  fop.e.goal_img = a.goal_img; fop.e.goal_mask = a.goal_mask; fop.e.xpred_out = a.xpred_out;
+  fop.e.cost_part = a.cost_part; fop.e.zero_robot = a.zero_robot; fop.e.dontcare = a.dontcare;
+  CKR(launch(h, fop, st));
+  return RAC_OK;
+}
+
+int check_ready(rac_handle* h, int n) {
+  if (!h) return RAC_ERR_INVALID;
+  if (h->ws.B != n || h->ws.arena == nullptr)
+    return fail(h, RAC_ERR_STATE, "workspace prepared for batch %d, call needs %d (rac_prepare first)", h->ws.B, n);
+  return RAC_OK;
+}
+
+__global__ void fill_kernel(float* p, float v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace
+
+// =================================================================================================== C ABI
+extern "C" {
+
+int rac_abi_version(void) { return RAC_ABI_VERSION; }
+
+int rac_create(const rac_config* cfg, rac_handle** out) {
+  if (!cfg || !out) return RAC_ERR_INVALID;
+  *out = nullptr;
+  rac_handle* h = new rac_handle();
+  h->cfg = *cfg;
+  *out = h;  // returned even on failure so that rac_last_error() is readable; caller must rac_destroy it
+  if (cfg->image_height != 48 || cfg->image_width != 64)
+    return fail(h, RAC_ERR_INVALID, "only 48x64 images are supported (got %dx%d)", cfg->image_height, cfg->image_width);
+  if (cfg->g_dim < 64 || cfg->g_dim % 64 != 0) return fail(h, RAC_ERR_INVALID, "g_dim must be a positive multiple of 64");
+  if (cfg->z_dim < 1 || cfg->z_dim > 64) return fail(h, RAC_ERR_INVALID, "z_dim must be in [1, 64]");
+  const int aux_c = cfg->action_dim + (cfg->use_robot_state ? cfg->robot_dim : 0) +
+                    ((cfg->use_robot_state && cfg->use_future_robot_state) ? cfg->robot_dim : 0);
+  if (cfg->action_dim < 1 || aux_c > 64) return fail(h, RAC_ERR_INVALID, "action_dim + robot dims must be in [1, 64]");
+  if (cfg->use_future_mask && !cfg->use_mask) return fail(h, RAC_ERR_INVALID, "use_future_mask requires use_mask");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(h, RAC_ERR_CUDA, "no CUDA device: racb200 has no CPU path");
+  CK(cudaGetDevice(&h->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, h->device));
+  if (prop.major != 10) return fail(h, RAC_ERR_CUDA, "racb200 is built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
+  h->num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return fail(h, RAC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+  h->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  CK(conv_tc_set_attributes());
+  CK(cem_set_attributes());
+  fill_specs(h);
+  return RAC_OK;
+}
+
+int rac_destroy(rac_handle* h) {
+  if (!h) return RAC_OK;
+  free_ws(h);
+  for (int i = 0; i < RAC_L_COUNT; ++i) {
+    if (h->layer[i].w) cudaFree(h->layer[i].w);
+    if (h->layer[i].bias) cudaFree(h->layer[i].bias);
+  }
+  delete h;
+  return RAC_OK;
+}
+
+const char* rac_last_error(const rac_handle* h) { return h ? h->err : "null handle"; }
+
+int rac_layer_shape(const rac_handle* h, int layer, int64_t* w_elems, int64_t* bias_elems, int* k_packed,
+                    int* n_packed) {
+  if (!h || layer < 0 || layer >= RAC_L_COUNT) return RAC_ERR_INVALID;
+  const LayerSpec& s = h->spec[layer];
+  if (w_elems) *w_elems = spec_w_elems(s);
+  if (bias_elems) *bias_elems = s.n_packed;
+  if (k_packed) *k_packed = s.ks * s.ks * s.ctot;
+  if (n_packed) *n_packed = s.n_packed;
+  return RAC_OK;
+}
+
+int rac_load_layer(rac_handle* h, int layer, const void* wsrc, int64_t w_elems, const float* bias, int64_t bias_elems) {
+  if (!h || layer < 0 || layer >= RAC_L_COUNT || !wsrc || !bias) return fail(h, RAC_ERR_INVALID, "bad layer argument");
+  const LayerSpec& s = h->spec[layer];
+  if (w_elems != spec_w_elems(s) || bias_elems != s.n_packed)
+    return fail(h, RAC_ERR_INVALID, "layer %d: packed size mismatch (w %lld vs %lld, bias %lld vs %d)", layer,
+                (long long)w_elems, (long long)spec_w_elems(s), (long long)bias_elems, s.n_packed);
+  Layer& L = h->layer[layer];
+  const size_t wb = static_cast<size_t>(w_elems) * (s.first ? 4 : 2);
+  if (!L.w) CK(cudaMalloc(&L.w, wb));
+  if (!L.bias) CK(cudaMalloc(reinterpret_cast<void**>(&L.bias), static_cast<size_t>(bias_elems) * 4));
+  CK(cudaMemcpy(L.w, wsrc, wb, cudaMemcpyDefault));
+  CK(cudaMemcpy(L.bias, bias, static_cast<size_t>(bias_elems) * 4, cudaMemcpyDefault));
+  L.loaded = true;
+  return RAC_OK;
+}
+
+int rac_prepare(rac_handle* h, int batch) {
+  if (!h || batch < 1) return fail(h, RAC_ERR_INVALID, "batch must be >= 1");
+  for (int i = 0; i < RAC_L_COUNT; ++i)
+    if (!h->layer[i].loaded) return fail(h, RAC_ERR_STATE, "layer %d not loaded (rac_load_layer)", i);
+  if (h->ws.B == batch && h->ws.arena) return RAC_OK;
+  CK(cudaDeviceSynchronize());
+  free_ws(h);
+  h->ws.B = batch;
+  Bump count;
+  carve(h, count, batch);
+  h->ws.arena_bytes = count.off + 1024;
+  CK(cudaMalloc(&h->ws.arena, h->ws.arena_bytes));
+  CK(cudaMemset(h->ws.arena, 0, h->ws.arena_bytes));
+  Bump bp;
+  bp.base = static_cast<char*>(h->ws.arena);
+  carve(h, bp, batch);
+  CKR(build_ops(h));
+  name_buffers(h);
+  h->cur[0] = h->cur[1] = h->cur[2] = 0;
+  return RAC_OK;
+}
+
+int rac_init_hidden(rac_handle* h, int batch, void* stream) {
+  CKR(check_ready(h, batch));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Workspace& w = h->ws;
+  const size_t ne = static_cast<size_t>(batch) * 48 * h->cfg.g_dim;
+  for (int l = 0; l < 3; ++l)
+    for (int k = 0; k < 2; ++k) {
+      for (int p = 0; p < 2; ++p) CK(cudaMemsetAsync(w.hs[l][k][p], 0, ne * 2, st));
+      CK(cudaMemsetAsync(w.cs[l][k], 0, ne * 4, st));
+    }
+  h->cur[0] = h->cur[1] = h->cur[2] = 0;
+  return RAC_OK;
+}
+
+int rac_forward(rac_handle* h, const rac_step* s, void* stream) {
+  if (!h || !s) return RAC_ERR_INVALID;
+  CKR(check_ready(h, s->n));
+  const rac_config& c = h->cfg;
+  if (!s->image || !s->action || !s->x_pred) return fail(h, RAC_ERR_INVALID, "image, action and x_pred are required");
+  if (c.use_mask && !s->mask) return fail(h, RAC_ERR_INVALID, "model_use_mask is set but mask is NULL");
+  if (c.use_robot_state && !s->robot) return fail(h, RAC_ERR_INVALID, "model_use_robot_state is set but robot is NULL");
+  if (c.use_robot_state && c.use_future_robot_state && !s->robot_next)
+    return fail(h, RAC_ERR_INVALID, "model_use_future_robot_state is set but robot_next is NULL");
+  if (s->use_posterior && c.use_robot_state && !s->next_robot)
+    return fail(h, RAC_ERR_INVALID, "posterior branch needs next_robot");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CK(launch_img_prep_nchw(s->image, h->ws.img, s->n, 48, 64, st));
+  h->launches++;
+  StepArgs a{};
+  a.n = s->n;
+  const int mask_ch = (c.use_mask && c.use_future_mask) ? 2 : 1;  // mask is (n, mask_ch, H, W)
+  a.mask_a = s->mask;
+  a.mask_b = (s->mask && mask_ch == 2) ? s->mask + 48 * 64 : nullptr;
+  a.mask_bstride = static_cast<long long>(mask_ch) * 48 * 64;
+  a.robot = s->robot; a.robot_next = s->robot_next;
+  a.action = s->action; a.action_stride = c.action_dim;
+  a.eps = s->eps; a.seed = s->seed; a.noise_ctr = s->noise_ctr; a.cand_offset = 0; a.sample_mean = s->sample_mean;
+  a.use_posterior = s->use_posterior; a.next_robot = s->next_robot; a.eps_post = s->eps_post;
+  a.force_use_prior = s->force_use_prior; a.keep_skip = s->keep_skip;
+  a.mu_p = s->mu_p; a.logvar_p = s->logvar_p; a.mu = s->mu; a.logvar = s->logvar;
+  a.xpred_out = s->x_pred;
+  return run_step(h, a, st);
+}
+
+int rac_rollout_cost(rac_handle* h, const rac_rollout* r, void* stream) {
+  if (!h || !r) return RAC_ERR_INVALID;
+  CKR(check_ready(h, r->n));
+  const rac_config& c = h->cfg;
+  Workspace& w = h->ws;
+  if (r->steps < 1 || !r->actions || !r->start_img || !r->goal_imgs || !r->sum_cost || r->num_goals < 1)
+    return fail(h, RAC_ERR_INVALID, "rollout: steps, actions, start_img, goal_imgs, sum_cost are required");
+  if (r->num_goals > kMaxGoals) return fail(h, RAC_ERR_INVALID, "at most %d goal images", kMaxGoals);
+  const bool need_masks = c.use_mask || r->zero_robot || r->dontcare_cost;
+  if (need_masks && !r->masks)
+    // reference: zero_robot_region(None, img) raises
+    return fail(h, RAC_ERR_INVALID, "robot masks are required by this configuration but masks is NULL");
+  if (c.use_robot_state && !r->states) return fail(h, RAC_ERR_INVALID, "model_use_robot_state is set but states is NULL");
+  if (r->dontcare_cost && !r->goal_masks) return fail(h, RAC_ERR_INVALID, "dontcare cost needs goal masks");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = r->n;
+  const size_t P0 = 48 * 64;
+  CKR(rac_init_hidden(h, n, stream));
+  CK(launch_goal_prep(r->goal_imgs, w.goal4, r->num_goals, 48, 64, st));
+  CK(launch_img_prep_u8(r->start_img, r->masks, r->zero_robot, w.img, n, 48, 64, st));
+  CK(cudaMemsetAsync(r->sum_cost, 0, sizeof(double) * n, st));
+  h->launches += 2;
+  const int zc = c.z_dim * 48;
+  for (int t = 0; t < r->steps; ++t) {
+    StepArgs a{};
+    a.n = n;
+    a.mask_a = r->masks ? r->masks + static_cast<size_t>(t) * r->mask_t_stride : nullptr;
+    a.mask_b = r->masks ? r->masks + static_cast<size_t>(t + 1) * r->mask_t_stride : nullptr;
+    a.mask_bstride = 48 * 64;
+    a.robot = r->states ? r->states + static_cast<size_t>(t) * r->state_t_stride : nullptr;
+    a.robot_next = r->states ? r->states + static_cast<size_t>(t + 1) * r->state_t_stride : nullptr;
+    a.action = r->actions + static_cast<size_t>(t) * c.action_dim;
+    a.action_stride = r->steps * c.action_dim;
+    a.eps = r->eps ? r->eps + static_cast<size_t>(t) * n * zc : nullptr;
+    a.seed = r->seed; a.noise_ctr = r->noise_ctr_base + t; a.cand_offset = r->cand_offset;
+    a.sample_mean = r->sample_mean;
+    a.curr_img = w.img;
+    a.next_img = w.img;  // in place: every thread reads and writes only its own pixel
+    a.mask_next = (r->zero_robot || r->dontcare_cost) ? a.mask_b : nullptr;
+    const int gi = t < r->num_goals ? t : r->num_goals - 1;  // trajectory_sampler.py:154
+    a.goal_img = w.goal4 + static_cast<size_t>(gi) * P0 * 4;
+    a.goal_mask = r->goal_masks ? r->goal_masks + static_cast<size_t>(gi) * P0 : nullptr;
+    a.cost_part = w.cost_part;
+    a.zero_robot = r->zero_robot; a.dontcare = r->dontcare_cost;
+    CKR(run_step(h, a, st));
+    if (r->obs_out)
+      CK(cudaMemcpyAsync(r->obs_out + static_cast<size_t>(t) * n * P0 * 4, w.img, sizeof(float) * n * P0 * 4,
+                         cudaMemcpyDeviceToDevice, st));
+    const int use = (!r->sparse_cost || t == r->steps - 1) ? 1 : 0;  // trajectory_sampler.py:167
+    CK(launch_cost_finish(w.cost_part, 96, r->dontcare_cost, r->world_cost_weight, use, r->sum_cost,
+                          r->step_cost_out ? r->step_cost_out + static_cast<size_t>(t) * n : nullptr, n, st));
+    h->launches++;
+  }
+  return RAC_OK;
+}
+
+int rac_cem_sample(const float* mean, const float* stdv, const float* noise, unsigned long long seed, int iter,
+                   int n_total, int steps, int action_dim_model, int cand_offset, int n_local, float clamp,
+                   float* act2_out, float* act_model_out, void* stream) {
+  if (!mean || !stdv || !act2_out || !act_model_out || n_total < 1 || steps < 1 || action_dim_model < 2)
+    return RAC_ERR_INVALID;
+  cudaError_t e = launch_cem_sample(mean, stdv, noise, seed, iter, n_total, steps, action_dim_model, cand_offset,
+                                    n_local, clamp, act2_out, act_model_out, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? RAC_OK : RAC_ERR_CUDA;
+}
+
+int rac_topk(const double* costs, int n, int k, int64_t* idx_out, double* val_out, void* stream) {
+  if (!costs || !idx_out || n < 1 || k < 1 || k > n || k > 4096) return RAC_ERR_INVALID;
+  static bool attr = false;
+  if (!attr) {
+    if (cem_set_attributes() != cudaSuccess) return RAC_ERR_CUDA;
+    attr = true;
+  }
+  cudaError_t e = launch_topk(costs, n, k, idx_out, val_out, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? RAC_OK : RAC_ERR_CUDA;
+}
+
+int rac_cem_refit(const float* act2, int steps, const int64_t* elite_idx, int k, float std_floor, float* mean_out,
+                  float* std_out, void* stream) {
+  if (!act2 || !elite_idx || !mean_out || !std_out || steps < 1 || k < 1) return RAC_ERR_INVALID;
+  cudaError_t e = launch_refit(act2, steps * 2, elite_idx, k, std_floor, mean_out, std_out,
+                               static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? RAC_OK : RAC_ERR_CUDA;
+}
+
+int rac_cem_plan(rac_handle* h, const rac_cem* c, float* mean_out, float* std_out, int64_t* elite_idx_out,
+                 double* last_costs_out, void* stream) {
+  if (!h || !c || !mean_out) return RAC_ERR_INVALID;
+  CKR(check_ready(h, c->n));
+  if (c->steps < 1 || c->iters < 1 || c->topk < 1 || c->topk > c->n || c->topk > 4096)
+    return fail(h, RAC_ERR_INVALID, "cem: need steps>=1, iters>=1, 1<=topk<=min(n,4096)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Workspace& w = h->ws;
+  const int n = c->n, L = c->steps, A = h->cfg.action_dim;
+  if (w.cem_n != n || w.cem_steps != L) {
+    CK(cudaStreamSynchronize(st));
+    if (w.act2) { cudaFree(w.act2); cudaFree(w.act5); cudaFree(w.mean); cudaFree(w.sum_cost); cudaFree(w.elite); }
+    CK(cudaMalloc(reinterpret_cast<void**>(&w.act2), sizeof(float) * n * L * 2));
+    CK(cudaMalloc(reinterpret_cast<void**>(&w.act5), sizeof(float) * n * L * A));
+    CK(cudaMalloc(reinterpret_cast<void**>(&w.mean), sizeof(float) * 64 * 2));
+    w.stdv = w.mean + 64;
+    CK(cudaMalloc(reinterpret_cast<void**>(&w.sum_cost), sizeof(double) * n));
+    CK(cudaMalloc(reinterpret_cast<void**>(&w.elite), sizeof(int64_t) * 4096));
+    w.cem_n = n; w.cem_steps = L;
+  }
+  if (2 * L > 32) return fail(h, RAC_ERR_INVALID, "cem: steps must be <= 16");
+  // mean = 0, std = init_std (cem.py:71-73)
+  CK(cudaMemsetAsync(w.mean, 0, sizeof(float) * 2 * L, st));
+  fill_kernel<<<1, 64, 0, st>>>(w.stdv, c->init_std, 2 * L);
+  CK(cudaGetLastError());
+  h->launches++;
+  for (int it = 0; it < c->iters; ++it) {
+    const float* nz = c->noise ? c->noise + static_cast<size_t>(it) * n * L * 2 : nullptr;
+    CK(launch_cem_sample(w.mean, w.stdv, nz, c->rollout.seed, it, n, L, A, 0, n, c->clamp, w.act2, w.act5, st));
+    rac_rollout r = c->rollout;
+    r.n = n; r.steps = L; r.cand_offset = 0; r.actions = w.act5; r.sum_cost = w.sum_cost;
+    r.noise_ctr_base = c->rollout.noise_ctr_base + static_cast<unsigned>(it * L);
+    if (c->rollout.eps) r.eps = c->rollout.eps + static_cast<size_t>(it) * L * n * h->cfg.z_dim * 48;
+    CKR(rac_rollout_cost(h, &r, stream));
+    CK(launch_topk(w.sum_cost, n, c->topk, w.elite, nullptr, st));
+    CK(launch_refit(w.act2, 2 * L, w.elite, c->topk, c->std_floor, w.mean, w.stdv, st));
+    h->launches += 3;
+  }
+  CK(cudaMemcpyAsync(mean_out, w.mean, sizeof(float) * 2 * L, cudaMemcpyDeviceToDevice, st));
+  if (std_out) CK(cudaMemcpyAsync(std_out, w.stdv, sizeof(float) * 2 * L, cudaMemcpyDeviceToDevice, st));
+  if (elite_idx_out) CK(cudaMemcpyAsync(elite_idx_out, w.elite, sizeof(int64_t) * c->topk, cudaMemcpyDeviceToDevice, st));
+  if (last_costs_out) CK(cudaMemcpyAsync(last_costs_out, w.sum_cost, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+  return RAC_OK;
+}
+
+int rac_masked_cost(const float* curr, const float* goal, const float* curr_mask, const float* goal_mask, int dontcare,
+                    float* out, int n, int hw, void* stream) {
+  if (!curr || !goal || !out || n < 0) return RAC_ERR_INVALID;
+  if (dontcare && (!curr_mask || !goal_mask)) return RAC_ERR_INVALID;
+  cudaError_t e = launch_masked_cost(curr, goal, curr_mask, goal_mask, dontcare, out, n, hw,
+                                     static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? RAC_OK : RAC_ERR_CUDA;
+}
+
+int rac_l1_loss(const float* pred, const float* target, float* out, int64_t numel, void* stream) {
+  if (!pred || !target || !out || numel < 1) return RAC_ERR_INVALID;
+  return launch_l1_loss(pred, target, out, numel, static_cast<cudaStream_t>(stream)) == cudaSuccess ? RAC_OK : RAC_ERR_CUDA;
+}
+int rac_dontcare_l1_loss(const float* pred, const float* target, const float* mask, float robot_weight, float* out,
+                         int n, int hw, void* stream) {
+  if (!pred || !target || !mask || !out || n < 1) return RAC_ERR_INVALID;
+  return launch_dontcare_l1_loss(pred, target, mask, robot_weight, out, n, hw, static_cast<cudaStream_t>(stream)) == cudaSuccess ? RAC_OK : RAC_ERR_CUDA;
+}
+int rac_kl_loss(const float* mu1, const float* logvar1, const float* mu2, const float* logvar2, float* out,
+                int64_t numel, int batch, void* stream) {
+  if (!mu1 || !logvar1 || !mu2 || !logvar2 || !out || numel < 1 || batch < 1) return RAC_ERR_INVALID;
+  return launch_kl_loss(mu1, logvar1, mu2, logvar2, out, numel, batch, static_cast<cudaStream_t>(stream)) == cudaSuccess ? RAC_OK : RAC_ERR_CUDA;
+}
+
+int rac_debug_buffer(rac_handle* h, const char* name, void** ptr, int64_t* elems, int* elem_bytes) {
+  if (!h || !name || !ptr) return RAC_ERR_INVALID;
+  auto it = h->ws.named.find(name);
+  if (it == h->ws.named.end()) return fail(h, RAC_ERR_INVALID, "no buffer named '%s'", name);
+  *ptr = it->second.first;
+  if (elems) *elems = it->second.second.first;
+  if (elem_bytes) *elem_bytes = it->second.second.second;
+  return RAC_OK;
+}
+
+int64_t rac_launch_count(const rac_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"
