@@ -140,6 +140,12 @@ class SVGOracle:
         self.cfg = cfg
         self.sd = {k: v.detach().to(torch.float32) if v.is_floating_point() else v for k, v in state_dict.items()}
         self.hidden = None
+        self.trace = None  # set to {} to record intermediate activations (NCHW) for layer-by-layer GPU diagnosis
+
+    def _rec(self, name, t):
+        if self.trace is not None:
+            self.trace[name] = t.clone()
+        return t
 
     # vgg_layer: conv3x3(no bias) -> BatchNorm2d(eval) -> LeakyReLU(0.2)  (vgg_64.py:8-18)
     def _vgg(self, x, prefix):
@@ -151,14 +157,16 @@ class SVGOracle:
 
     # ConvEncoder.forward (vgg_64.py:122-129)
     def encode(self, x):
-        h1 = self._vgg(self._vgg(x, "encoder.c1.0"), "encoder.c1.1")
-        h2 = self._vgg(self._vgg(F.max_pool2d(h1, 2, 2), "encoder.c2.0"), "encoder.c2.1")
+        h1 = self._vgg(self._rec("a1", self._vgg(x, "encoder.c1.0")), "encoder.c1.1")
+        h2 = self._vgg(self._rec("a2", self._vgg(F.max_pool2d(h1, 2, 2), "encoder.c2.0")), "encoder.c2.1")
         h3 = F.max_pool2d(h2, 2, 2)
         for i in range(3):
             h3 = self._vgg(h3, f"encoder.c3.{i}")
         h4 = F.max_pool2d(h3, 2, 2)
         for i in range(3):
             h4 = self._vgg(h4, f"encoder.c4.{i}")
+        for n_, t_ in (("h1", h1), ("h2", h2), ("h3", h3), ("h4", h4)):
+            self._rec(n_, t_)
         return h4, [h1, h2, h3, h4]
 
     # ConvDecoder.forward (vgg_64.py:223-241)
@@ -167,6 +175,7 @@ class SVGOracle:
         d = vec
         for i in range(3):
             d = self._vgg(d, f"decoder.upc2.{i}")
+            self._rec(f"d2.{i}", d)
         d = torch.cat([F.interpolate(d, scale_factor=2, mode="nearest"), skip[2]], 1)
         for i in range(3):
             d = self._vgg(d, f"decoder.upc3.{i}")
@@ -174,7 +183,7 @@ class SVGOracle:
         for i in range(2):
             d = self._vgg(d, f"decoder.upc4.{i}")
         d = torch.cat([F.interpolate(d, scale_factor=2, mode="nearest"), skip[0]], 1)
-        d = self._vgg(d, "decoder.upc5.0")
+        d = self._rec("d5", self._vgg(d, "decoder.upc5.0"))
         d = F.conv_transpose2d(d, sd["decoder.upc5.1.weight"], sd["decoder.upc5.1.bias"], 1, 1)
         return torch.sigmoid(d)
 
@@ -196,6 +205,8 @@ class SVGOracle:
             c = torch.sigmoid(f) * c_prev + torch.sigmoid(i) * torch.tanh(g_)
             h = torch.sigmoid(o) * torch.tanh(c)
             self.hidden[name][layer] = (h, c)
+            self._rec(f"{name}.h{layer}", h)
+            self._rec(f"{name}.c{layer}", c)
             x = h
         return x
 
@@ -229,6 +240,7 @@ class SVGOracle:
             else:
                 parts += [self._tile(robot)]
         prior_in = F.conv2d(torch.cat(parts + [h], 1), sd["prior_input_conv.weight"], sd["prior_input_conv.bias"], 1, 1)
+        self._rec("prior_in", prior_in)
         z_p, mu_p, logvar_p = self._gaussian(prior_in, "prior", eps)
         z = mu_p if sample_mean else z_p
         mu = logvar = None
@@ -243,6 +255,8 @@ class SVGOracle:
                 z = z_t
         frame_in = F.conv2d(torch.cat(parts + [h, z], 1), sd["frame_pred_input_conv.weight"],
                             sd["frame_pred_input_conv.bias"], 1, 1)
+        self._rec("z", z)
+        self._rec("frame_in", frame_in)
         h_pred = self._convlstm(frame_in, "frame_predictor")
         x_pred = self.decode(h_pred, skip)
         return x_pred, skip, mu, logvar, mu_p, logvar_p

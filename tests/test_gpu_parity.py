@@ -1,0 +1,352 @@
+"""GPU parity tests (run on a B200 with `pytest -m gpu`): every call goes through the C ABI of libracb200.so (ctypes)
+and is compared with the CPU oracle (oracle/svg_oracle.py) and with the committed reference outputs (tests/golden).
+
+Tolerances (BASELINE.json north_star): frames / pixels within 1e-2 max-abs on [0,1] (bf16 tensor-core path);
+top-k / elite index sets bit-exact; costs compared relatively (they carry a factor 255 * sqrt(#pixels))."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import svg_oracle as so
+from oracle.make_golden import G_DIM, Z_DIM, inputs_forward, synth_masks
+
+pytestmark = pytest.mark.gpu
+
+PIX_TOL = 1e-2
+
+
+def _model(cfg, sd, impl="tc"):
+    from robot_aware_control_b200 import SVGConvModel
+
+    m = SVGConvModel(cfg, conv_impl=1 if impl == "simt" else 0)
+    m.load_state_dict(sd)
+    m.eval()
+    return m
+
+
+def _cfg(tag, **kw):
+    if tag == "vanilla":
+        return so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, **kw)
+    return so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, model_use_mask=True, model_use_robot_state=True,
+                       reconstruction_loss="dontcare_l1", reward_type="dontcare", **kw)
+
+
+@pytest.fixture(scope="module")
+def scene(golden_dir):
+    return np.load(os.path.join(golden_dir, "scene.npz"))
+
+
+# ------------------------------------------------------------------------------------------------ forward
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("tag", ["vanilla", "ra"])
+def test_forward_matches_reference_golden(golden_dir, tag, impl):
+    """SVGConvModel.forward, two recurrent steps + posterior branch, against the reference's own outputs."""
+    gold = np.load(os.path.join(golden_dir, f"forward_{tag}.npz"))
+    extra = dict(model_use_future_mask=True, model_use_future_robot_state=True) if tag == "ra" else {}
+    cfg = _cfg(tag, **extra)
+    m = _model(cfg, so.make_state_dict(cfg, int(gold["weight_seed"])), impl)
+    B = int(gold["B"])
+    d = inputs_forward(int(gold["input_seed"]), B, cfg)
+    m.init_hidden(B)
+    for t in range(2):
+        mask = torch.cat([d["mask"][t], d["mask"][t + 1]], 1) if cfg.model_use_mask else None
+        robot = (d["robot"][t], d["robot"][t + 1]) if cfg.model_use_robot_state else None
+        m.set_noise(eps=d["eps"][t])
+        x_pred, skip, mu, logvar, mu_p, logvar_p = m.forward(d["image"][t], mask, robot, None, d["action"][t])
+        assert mu is None and logvar is None  # prior path (dynamics.py:644 with next_image=None)
+        assert np.abs(x_pred.cpu().numpy() - gold[f"x_pred{t}"]).max() < PIX_TOL
+        assert np.abs(mu_p.cpu().numpy() - gold[f"mu_p{t}"]).max() < 5e-2
+        assert np.abs(logvar_p.cpu().numpy() - gold[f"logvar_p{t}"]).max() < 5e-2
+        if t == 0:
+            assert np.abs(skip[3].cpu().numpy() - gold["h4"]).max() < 5e-2
+            assert np.abs(skip[0][:, :8].cpu().numpy() - gold["h1_sample"]).max() < 5e-2
+    m.init_hidden(B)
+    mask = torch.cat([d["mask"][0], d["mask"][1]], 1) if cfg.model_use_mask else None
+    robot = (d["robot"][0], d["robot"][1]) if cfg.model_use_robot_state else None
+    nr = d["robot"][1] if cfg.model_use_robot_state else None
+    m.set_noise(eps=d["eps"][0], eps_post=d["eps_post"][0])
+    x_pred, _, mu, logvar, _, _ = m.forward(d["image"][0], mask, robot, None, d["action"][0], d["image"][1], mask, nr)
+    assert np.abs(x_pred.cpu().numpy() - gold["post_x_pred"]).max() < PIX_TOL
+    assert np.abs(mu.cpu().numpy() - gold["post_mu"]).max() < 5e-2
+    assert np.abs(logvar.cpu().numpy() - gold["post_logvar"]).max() < 5e-2
+
+
+def test_tc_matches_simt_layer_by_layer():
+    """tcgen05 path vs the SIMT cross-check kernel on the same packed operands: only the accumulation order differs."""
+    cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM)
+    sd = so.make_state_dict(cfg, 3)
+    B = 5  # not a multiple of the 8-candidate latent tile: exercises the out-of-range rows
+    g = torch.Generator().manual_seed(4)
+    img = torch.rand(B, 3, 48, 64, generator=g)
+    act = (torch.rand(B, 5, generator=g) - 0.5) * 0.1
+    eps = torch.randn(B, Z_DIM, 6, 8, generator=g)
+    outs = {}
+    for impl in ("simt", "tc"):
+        m = _model(cfg, sd, impl)
+        m.init_hidden(B)
+        m.set_noise(eps=eps)
+        x = m.forward(img, None, None, None, act)[0]
+        outs[impl] = {"x": x.cpu()}
+        for name, shape in (("cat5", (B, 48, 64, 128)), ("cat3", (B, 12, 16, 512)), ("h4", (B, 6, 8, G_DIM)),
+                            ("prior.h0.1", (B, 6, 8, G_DIM)), ("fp.h1.1", (B, 6, 8, G_DIM)), ("d5", (B, 48, 64, 64))):
+            outs[impl][name] = m._buffer_view(name, shape).float().cpu()
+    for k in outs["tc"]:
+        err = (outs["tc"][k] - outs["simt"][k]).abs().max().item()
+        assert err < 2e-2, (k, err)
+    assert (outs["tc"]["x"] - outs["simt"]["x"]).abs().max().item() < 2e-3
+
+
+def test_forward_baseline_config_g512():
+    """BASELINE.json model size (g_dim 512, z_dim 64, action_dim 5) against the oracle, 2 steps."""
+    cfg = so.make_cfg(g_dim=512, z_dim=64)
+    sd = so.make_state_dict(cfg, 2)
+    B = 4
+    g = torch.Generator().manual_seed(5)
+    oracle = so.SVGOracle(cfg, sd)
+    m = _model(cfg, sd)
+    oracle.init_hidden(B)
+    m.init_hidden(B)
+    cur_o = cur_m = torch.rand(B, 3, 48, 64, generator=g)
+    for t in range(2):
+        act = (torch.rand(B, 5, generator=g) - 0.5) * 0.1
+        eps = torch.randn(B, 64, 6, 8, generator=g)
+        xo = oracle.forward(cur_o, None, None, act, eps)[0]
+        m.set_noise(eps=eps)
+        xm = m.forward(cur_m, None, None, None, act)[0].cpu()
+        assert (xo - xm).abs().max().item() < PIX_TOL
+        cur_o = (1 - xo[:, 3:4]) * cur_o + xo[:, 3:4] * xo[:, :3]
+        cur_m = (1 - xm[:, 3:4]) * cur_m + xm[:, 3:4] * xm[:, :3]
+
+
+def test_state_dict_roundtrip_and_errors():
+    cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM)
+    sd = so.make_state_dict(cfg, 1)
+    m = _model(cfg, sd)
+    out = m.state_dict()
+    assert list(out.keys()) == list(sd.keys())
+    for k in sd:
+        assert torch.equal(out[k].cpu(), sd[k])
+    with pytest.raises(RuntimeError):  # forward before init_hidden for that batch
+        m.forward(torch.rand(2, 3, 48, 64), None, None, None, torch.zeros(2, 5))
+    m.train()
+    m.init_hidden(2)
+    with pytest.raises(NotImplementedError):
+        m.forward(torch.rand(2, 3, 48, 64), None, None, None, torch.zeros(2, 5))
+
+
+# ------------------------------------------------------------------------------------------------ rollout + cost
+@pytest.mark.parametrize("tag", ["vanilla", "ra", "ra_sparse"])
+def test_rollout_cost_matches_reference_golden(golden_dir, scene, tag):
+    """TrajectorySampler.generate_model_rollouts against the reference's frames and summed costs."""
+    from robot_aware_control_b200 import DemoGoalState, State, TrajectorySampler
+
+    gold = np.load(os.path.join(golden_dir, f"rollout_{tag}.npz"))
+    extra = {}
+    if tag == "ra":
+        extra = dict(model_use_future_mask=True)
+    if tag == "ra_sparse":
+        extra = dict(sparse_cost=True)
+    N, L = int(gold["N"]), int(gold["L"])
+    cfg = _cfg("vanilla" if tag == "vanilla" else "ra", topk=N, **extra)
+    m = _model(cfg, so.make_state_dict(cfg, int(gold["weight_seed"])))
+    g = torch.Generator().manual_seed(int(gold["input_seed"]))
+    actions = torch.cat([(torch.rand(N, L, 2, generator=g) - 0.5) * 0.1, torch.zeros(N, L, 3)], 2)
+    eps = torch.randn(L, N, cfg.z_dim, 6, 8, generator=g)
+    states = torch.rand(L + 1, N, 5, generator=g)
+    masks = synth_masks(int(gold["mask_seed"]), L, N)
+    ts = TrajectorySampler(cfg, m)
+    ts.set_noise(eps)
+    start = State(img=scene["start_img"], state=np.array([0.3, 0.0, 0.2, 0.0, 0.0], dtype=np.float32), qpos=np.zeros(6))
+    goal = DemoGoalState(imgs=list(scene["goal_imgs"]), masks=list(scene["goal_masks"]))
+    r = ts.generate_model_rollouts(actions, start, goal, ret_obs=True, ret_step_cost=True, states=states, masks=masks)
+    assert r["sum_cost"].dtype == np.float64 and r["sum_cost"].shape == (N,)
+    inv = np.empty(N, dtype=np.int64)
+    inv[r["topk_idx"]] = np.arange(N)
+    obs = r["obs"][inv]
+    assert obs.shape == (N, L, 3, 48, 64)
+    assert np.abs(obs - gold["obs"]).max() < PIX_TOL
+    np.testing.assert_allclose(r["sum_cost"], gold["sum_cost"], rtol=3e-3)
+    np.testing.assert_allclose(r["step_cost"].sum(1), r["sum_cost"], rtol=1e-6)
+
+
+def test_rollout_is_batch_independent_and_deterministic(scene):
+    """Size-independent properties at a planner-sized batch: a candidate's cost depends only on its own actions and
+    its GLOBAL id (Philox noise), not on the batch it is rolled out in; identical calls give identical bits."""
+    from robot_aware_control_b200 import DemoGoalState, State, TrajectorySampler
+
+    cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM)
+    m = _model(cfg, so.make_state_dict(cfg, 9))
+    N, L = 200, 4
+    g = torch.Generator().manual_seed(1)
+    actions = torch.cat([(torch.rand(N, L, 2, generator=g) - 0.5) * 0.1, torch.zeros(N, L, 3)], 2)
+    actions[7] = actions[3]  # same actions, different global id -> different z noise -> (almost surely) different cost
+    start = State(img=scene["start_img"])
+    goal = DemoGoalState(imgs=list(scene["goal_imgs"]), masks=list(scene["goal_masks"]))
+    ts = TrajectorySampler(cfg, m)
+    ts._noise_ctr = 0
+    full = ts.generate_model_rollouts(actions, start, goal)["sum_cost"]
+    ts._noise_ctr = 0
+    again = ts.generate_model_rollouts(actions, start, goal)["sum_cost"]
+    np.testing.assert_array_equal(full, again)
+    ts._noise_ctr = 0
+    ts.cand_offset = 64
+    part = ts.generate_model_rollouts(actions[64:96], start, goal)["sum_cost"]
+    np.testing.assert_allclose(part, full[64:96], rtol=1e-6)
+    assert np.all(np.isfinite(full)) and np.all(full < 0)
+
+
+def test_masked_cost_kernel_matches_reference_golden(golden_dir):
+    """rac_masked_cost through RobotWorldCost in the reference's tensor layout (losses.py:224-263,307-335)."""
+    from robot_aware_control_b200 import RobotWorldCost, State
+
+    gold = np.load(os.path.join(golden_dir, "costs.npz"))
+    g = torch.Generator().manual_seed(int(gold["input_seed"]))
+    B = 5
+    curr = torch.rand(B, 3, 48, 64, generator=g)
+    goal = torch.rand(3, 48, 64, generator=g)
+    cmask = (torch.rand(B, 1, 48, 64, generator=g) > 0.7).float()
+    gmask = (torch.rand(1, 48, 64, generator=g) > 0.7).float()
+    pred = torch.rand(B, 3, 48, 64, generator=g)
+    mu1, lv1, mu2, lv2 = (torch.randn(B, Z_DIM, 6, 8, generator=g) * 0.5 for _ in range(4))
+    l2 = RobotWorldCost(so.make_cfg())(State(img=curr.cuda()), State(img=goal.cuda()))
+    dc = RobotWorldCost(so.make_cfg(reward_type="dontcare"))(State(img=curr.cuda(), mask=cmask.cuda()),
+                                                             State(img=goal.cuda(), mask=gmask.cuda()))
+    assert l2.dtype == np.float32 and l2.shape == (B,)
+    np.testing.assert_allclose(l2, gold["img_l2"], rtol=2e-6)
+    np.testing.assert_allclose(dc, gold["img_dontcare"], rtol=2e-6)
+    # empty batch and the single-image form (losses.py:229-230)
+    from robot_aware_control_b200.losses import _masked_cost, dontcare_l1_criterion, kl_criterion, l1_criterion
+
+    assert _masked_cost(curr[:0].cuda(), goal.cuda(), None, None, False).shape == (0,)
+    np.testing.assert_allclose(_masked_cost(curr[0].cuda(), goal.cuda(), None, None, False), gold["img_l2"][0], rtol=2e-6)
+    np.testing.assert_allclose(l1_criterion(pred, curr).item(), gold["l1"], rtol=1e-5)
+    np.testing.assert_allclose(dontcare_l1_criterion(pred, curr, cmask, 0.0).item(), gold["dontcare_l1_w0"], rtol=1e-5)
+    np.testing.assert_allclose(dontcare_l1_criterion(pred, curr, cmask, 0.5).item(), gold["dontcare_l1_w05"], rtol=1e-5)
+    np.testing.assert_allclose(kl_criterion(mu1, lv1, mu2, lv2, B).item(), gold["kl"], rtol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ CEM kernels
+def _topk(costs, k):
+    import ctypes as C
+    from robot_aware_control_b200 import _lib
+
+    lib = _lib.load()
+    c = torch.as_tensor(costs, dtype=torch.float64).cuda()
+    idx = torch.empty(k, dtype=torch.int64, device="cuda")
+    val = torch.empty(k, dtype=torch.float64, device="cuda")
+    _lib.check(lib.rac_topk(_lib.ptr(c), len(costs), k, _lib.ptr(idx), _lib.ptr(val), _lib.stream_ptr()), None, "rac_topk")
+    return idx.cpu().numpy(), val.cpu().numpy()
+
+
+def test_topk_bit_exact(golden_dir):
+    """Elite selection is integer work: bit-exact against torch.topk (golden, no ties at the boundary), against the
+    stable-sort tie rule, and on edge cases (K == N, K == 1, all-equal, -0.0 / +0.0, maximum K)."""
+    gold = np.load(os.path.join(golden_dir, "costs.npz"))
+    for name in "abcd":
+        c, ref = gold[f"topk_{name}_costs"], gold[f"topk_{name}_idx"]
+        idx, val = _topk(c, len(ref))
+        np.testing.assert_array_equal(idx, ref)
+        np.testing.assert_array_equal(val, c[ref])
+    idx, _ = _topk(gold["topk_ties_costs"], 37)
+    np.testing.assert_array_equal(idx, gold["topk_ties_idx"])
+    rs = np.random.RandomState(0)
+    for n, k in ((1, 1), (5, 5), (33, 1), (1025, 1024), (16385, 1638), (20000, 4096), (4096, 4096)):
+        c = np.round(rs.randn(n) * 50) / 4 - 1000  # many ties
+        idx, _ = _topk(c, k)
+        np.testing.assert_array_equal(idx, so.topk_largest(c, k))
+        tv, ti = torch.from_numpy(c).topk(k)
+        np.testing.assert_array_equal(np.sort(c[idx])[::-1], tv.numpy())  # same multiset of values as torch.topk
+    c = np.array([0.0, -0.0, 0.0, -1.0, -0.0])
+    np.testing.assert_array_equal(_topk(c, 3)[0], [0, 1, 2])
+    np.testing.assert_array_equal(_topk(np.full(100, -7.5), 10)[0], np.arange(10))
+    from robot_aware_control_b200 import _lib
+    lib = _lib.load()
+    assert lib.rac_topk(None, 10, 3, None, None, None) == _lib.RAC_ERR_INVALID
+    c = torch.zeros(10, dtype=torch.float64, device="cuda")
+    i = torch.zeros(10, dtype=torch.int64, device="cuda")
+    assert lib.rac_topk(_lib.ptr(c), 10, 11, _lib.ptr(i), None, None) == _lib.RAC_ERR_INVALID
+
+
+def test_sample_and_refit_match_oracle(golden_dir):
+    from robot_aware_control_b200 import _lib
+
+    lib = _lib.load()
+    gold = np.load(os.path.join(golden_dir, "costs.npz"))
+    N, L, A = 64, 4, 5
+    g = torch.Generator().manual_seed(2)
+    noise = torch.randn(N, L, 2, generator=g)
+    mean = torch.randn(L, 2, generator=g) * 0.01
+    std = torch.rand(L, 2, generator=g) * 0.05
+    for it in (0, 1):
+        act2 = torch.empty(N, L, 2, device="cuda")
+        act5 = torch.full((16, L, A), 9.0, device="cuda")
+        _lib.check(lib.rac_cem_sample(_lib.ptr(mean.cuda()), _lib.ptr(std.cuda()), _lib.ptr(noise.cuda()), 0, it, N, L,
+                                      A, 32, 16, 0.05, _lib.ptr(act2), _lib.ptr(act5), _lib.stream_ptr()), None, "sample")
+        ref = so.cem_sample(mean, std, noise.clone(), it)
+        np.testing.assert_allclose(act2.cpu().numpy(), ref.numpy(), rtol=0, atol=1e-9)
+        np.testing.assert_array_equal(act5.cpu().numpy()[:, :, :2], ref.numpy()[32:48])
+        assert float(act5[:, :, 2:].abs().max()) == 0.0
+    # Philox path: deterministic, clamped, iteration-0 do-nothing candidate, shard-independent
+    a = torch.empty(N, L, 2, device="cuda"); a5 = torch.empty(N, L, A, device="cuda")
+    b = torch.empty(N, L, 2, device="cuda"); b5 = torch.empty(8, L, A, device="cuda")
+    one = torch.ones(L, 2, device="cuda")
+    lib.rac_cem_sample(_lib.ptr(one * 0), _lib.ptr(one * 0.03), None, 77, 0, N, L, A, 0, N, 0.05, _lib.ptr(a), _lib.ptr(a5), _lib.stream_ptr())
+    lib.rac_cem_sample(_lib.ptr(one * 0), _lib.ptr(one * 0.03), None, 77, 0, N, L, A, 40, 8, 0.05, _lib.ptr(b), _lib.ptr(b5), _lib.stream_ptr())
+    assert torch.equal(a, b) and torch.equal(a5[40:48], b5)
+    assert float(a.abs().max()) <= 0.05 and float(a[-1].abs().max()) == 0.0
+    assert 0.015 < float(a[:-1].std()) < 0.04
+    # refit (cem.py:98-104)
+    elite = torch.from_numpy(gold["refit_act"]).cuda()
+    idx = torch.arange(elite.shape[0], dtype=torch.int64, device="cuda")
+    m_out = torch.empty(4, 2, device="cuda"); s_out = torch.empty(4, 2, device="cuda")
+    _lib.check(lib.rac_cem_refit(_lib.ptr(elite), 4, _lib.ptr(idx), elite.shape[0], 0.001, _lib.ptr(m_out), _lib.ptr(s_out),
+                                 _lib.stream_ptr()), None, "refit")
+    np.testing.assert_allclose(m_out.cpu().numpy(), gold["refit_mean"], rtol=2e-6, atol=1e-9)
+    np.testing.assert_allclose(s_out.cpu().numpy(), gold["refit_std"], rtol=2e-6)
+    tiny = (torch.ones(8, 4, 2) * 0.01).cuda()
+    lib.rac_cem_refit(_lib.ptr(tiny), 4, _lib.ptr(idx[:8]), 8, 0.001, _lib.ptr(m_out), _lib.ptr(s_out), _lib.stream_ptr())
+    assert torch.all(s_out == 0.001)  # std floor (cem.py:104)
+
+
+def test_cem_get_action_vs_oracle_and_fused_plan(scene):
+    """CEMPolicy.get_action: (1) one iteration against the oracle (costs by tolerance, elite set bit-exact on the
+    kernel's own cost vector, refit mean); (2) the device-resident rac_cem_plan loop is bit-identical to the
+    per-iteration path driven from Python with the same kernels and noise."""
+    from robot_aware_control_b200 import CEMPolicy, DemoGoalState, State
+
+    cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, sample_mean=True)  # sample_mean: no z noise, so both paths agree
+    sd = so.make_state_dict(cfg, 13)
+    m = _model(cfg, sd)
+    I, N, L, K = 3, 32, 3, 6
+    g = torch.Generator().manual_seed(51)
+    noise = torch.randn(I, N, L, 2, generator=g)
+    start = State(img=scene["start_img"])
+    goal = DemoGoalState(imgs=list(scene["goal_imgs"]), masks=list(scene["goal_masks"]))
+    pol = CEMPolicy(cfg, m, horizon=L + 1, opt_iter=1, action_candidates=N, topk=K, init_std=0.03)
+    pol.set_noise(noise[:1])
+    mean1 = pol.get_action(start, goal, 0, 0)
+    assert mean1.shape == (L, 2) and mean1.dtype == np.float32
+    costs = pol.last_costs.cpu().numpy()
+    elite = pol.last_elite_idx.cpu().numpy()
+    oracle = so.SVGOracle(cfg, sd)
+    eps0 = torch.zeros(1, L, N, Z_DIM, 6, 8)
+    _, hist = so.cem_plan(oracle, cfg, noise[:1], K, 0.03, scene["start_img"], list(scene["goal_imgs"]),
+                          list(scene["goal_masks"]), eps=eps0)
+    np.testing.assert_allclose(costs, hist[0]["sum_cost"], rtol=3e-3)
+    np.testing.assert_array_equal(elite, so.topk_largest(costs, K))
+    ref_mean, _ = so.cem_refit(torch.from_numpy(hist[0]["act"]), elite)
+    np.testing.assert_allclose(mean1, ref_mean.numpy(), rtol=1e-5, atol=1e-8)
+    # (2) fused loop vs per-iteration loop
+    pol3 = CEMPolicy(cfg, m, horizon=L + 1, opt_iter=I, action_candidates=N, topk=K, init_std=0.03)
+    pol3.set_noise(noise)
+    fused = pol3.get_action(start, goal, 0, 0)
+    fused_costs = pol3.last_costs.cpu().numpy()
+    pol3.set_noise(noise)
+    pol3.plot_rollouts = True  # forces the per-iteration path
+    cfg.topk = 5
+    stepwise = pol3.get_action(start, goal, 0, 0)
+    np.testing.assert_array_equal(fused, stepwise)
+    np.testing.assert_array_equal(fused_costs, pol3.last_costs.cpu().numpy())
+    assert pol3.last_rollouts["obs"].shape == (5, L, 3, 48, 64)
