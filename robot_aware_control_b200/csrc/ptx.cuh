@@ -42,9 +42,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must become a launch failure, never a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) { __trap(); }
+    if (clock64() - t0 > 4000000000ll) { __trap(); }  // ~2 s at 1.9 GHz: far beyond any legitimate wait
   }
 }
 
