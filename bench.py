@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path named by BASELINE.json: SVG rollout frames/sec inside CEM planning.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" is one complete CEM plan: I iterations x N candidates x L predicted frames, each frame including its
+compositing and planning-cost contribution. N=1 GPU runs BASELINE.json configs[1] (2000 candidates, L=5, 10
+iterations, 10 % elites, g_dim 512 / z_dim 64 / action_dim 5 on 48x64 RGB). N>1 (torchrun, one rank per GPU) runs
+configs[2]: 16384 candidates sharded across the ranks, per-candidate costs all-gathered over NCCL, replicated refit.
+
+`value`  : frames/s with every input resident in HBM (CEMPolicy.plan_device), CUDA-event timed, max over ranks.
+`e2e`    : same metric through the reference-facing API CEMPolicy.get_action with HOST inputs (uint8 images and the
+           sampling noise from pinned memory are copied in, the plan's mean is copied out, inside the timed region).
+`roofline`: the dominant kernel (tcgen05 implicit-GEMM of the two 5x5 ConvLSTM gate convolutions, 55 % of all FLOPs),
+           timed live with CUDA events on its launch stream during the timed steps.
+`cpu_baseline`: the CPU oracle port of the reference path (oracle/svg_oracle.py) on the host cores, bounded sample.
+`--impl reference`: the reference arm = the same CPU port timed as the thing measured.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+G_DIM, Z_DIM, A_DIM = 512, 64, 5
+L_STEPS, ITERS = 5, 10
+FLOP_PER_FRAME = 18.334e9          # sum of 2*M*N*K over the layer table, vanilla model
+FLOP_LSTM0_PER_CAND = 5033.2e6     # one 5x5 gate convolution: 2 * 48 * 2048 * 25600
+METRIC = "cem_rollout_frames_per_sec"
+UNIT = "frames/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("hbm_gbs"), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def scene():
+    rs = np.random.RandomState(0)
+    start = rs.randint(0, 256, (48, 64, 3)).astype(np.uint8)
+    goals = [rs.randint(0, 256, (48, 64, 3)).astype(np.uint8)]
+    gmask = np.zeros((1, 48, 64), dtype=np.float32)
+    gmask[:, :15] = 1  # widowx_VMPC_controller.py:338-340
+    return start, goals, [gmask]
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.stop_flag = threading.Event()
+        self.rows = []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_run(n_cand, iters, threads):
+    """Times the CPU oracle port of CEMPolicy.get_action on a bounded sample; returns (frames, seconds)."""
+    from oracle import svg_oracle as so
+
+    torch.set_num_threads(threads)
+    cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, action_dim=A_DIM)
+    model = so.SVGOracle(cfg, so.make_state_dict(cfg, 0))
+    start, goals, gmasks = scene()
+    g = torch.Generator().manual_seed(0)
+    noise = torch.randn(iters, n_cand, L_STEPS, 2, generator=g)
+    eps = torch.randn(iters, L_STEPS, n_cand, Z_DIM, 6, 8, generator=g)
+    t0 = time.perf_counter()
+    so.cem_plan(model, cfg, noise, max(1, n_cand // 10), 0.03, start, goals, gmasks, eps=eps)
+    dt = time.perf_counter() - t0
+    return n_cand * L_STEPS * iters, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_cand, iters = 32, 1
+    cpu_port_run(8, 1, threads)  # warm-up of the thread pool / allocator
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_port_run(n_cand, iters, threads)
+    frames = secs = 0.0
+    for _ in range(args.steps):
+        f, s = cpu_port_run(n_cand, iters, threads)
+        frames += f
+        secs += s
+    val = frames / secs
+    sample = f"{n_cand} candidates x {L_STEPS} frames x {iters} iteration per step (linear in N*L*I), fp32, torch CPU"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, 1),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference arm = CPU port of the reference's own PyTorch path (oracle/svg_oracle.py, pinned to "
+                "reference outputs in tests/golden); the reference is Python and /root/reference is absent on this box",
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus, world):
+    n_total = 2000 if n_gpus == 1 else 16384
+    return {
+        "workload": (f"CEM plan: {n_total} candidates x L={L_STEPS} predicted frames x {ITERS} iterations, 10% elites, "
+                     f"SVG g_dim {G_DIM} z_dim {Z_DIM} action_dim {A_DIM}, 48x64 RGB, ImgL2 planning cost"
+                     + ("" if n_gpus == 1 else f", candidates sharded over {n_gpus} GPUs, cost all-gather (NCCL) + replicated refit")),
+        "candidates": n_total, "rollout_steps": L_STEPS, "cem_iterations": ITERS, "elites": n_total // 10,
+        "l2": "activation working set per plan (>9 GB) is far larger than the 126 MB L2; no explicit flush",
+        "noise": "Philox on device (value) / torch CPU generator uploaded from pinned memory (e2e)",
+    }
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--candidates", type=int, default=0, help="override the candidate count (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch.distributed as dist
+    from oracle import svg_oracle as so  # only for the deterministic synthetic weights + the cpu_baseline leg
+    from robot_aware_control_b200 import CEMPolicy, DemoGoalState, State, SVGConvModel, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        group = dist.group.WORLD
+    dev = torch.device("cuda", local_rank)
+
+    n_total = args.candidates or (2000 if args.gpus == 1 else 16384)
+    topk = max(1, n_total // 10)
+    cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, action_dim=A_DIM)
+    torch.manual_seed(0)
+    model = SVGConvModel(cfg)
+    model.load_state_dict(so.make_state_dict(cfg, 0))
+    model.eval()
+    policy = CEMPolicy(cfg, model, horizon=L_STEPS + 1, opt_iter=ITERS, action_candidates=n_total, topk=topk,
+                       init_std=0.03, process_group=group, noise_source="philox")
+    start_np, goals_np, gmasks_np = scene()
+    start = State(img=start_np)
+    goal = DemoGoalState(imgs=goals_np, masks=gmasks_np)
+    start_dev = torch.from_numpy(start_np).to(dev)
+    goals_dev = torch.from_numpy(np.stack(goals_np)).to(dev)
+    gmask_dev = torch.from_numpy(np.stack(gmasks_np).reshape(-1, 48, 64)).to(dev)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """CUDA events on the launch stream, barrier + synchronize on both sides, max over ranks."""
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        sync_all()
+        return float(ms.item())
+
+    frames_per_step = n_total * L_STEPS * ITERS
+    # ---- device-resident arm ("value")
+    dev_plan = lambda: policy.plan_device(start_dev, goals_dev, gmask_dev, None)
+    for _ in range(args.warmup):
+        dev_plan()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = model.launch_count()
+    n_prof = args.steps * ITERS * L_STEPS * 2 + 8
+    _lib.check(_lib.load().rac_profile_begin(model.handle, b"lstm.0", n_prof), model.handle, "rac_profile_begin")
+    ms = timed(dev_plan, args.steps)
+    import ctypes as C
+    pl, pms = C.c_int64(), C.c_double()
+    _lib.check(_lib.load().rac_profile_end(model.handle, C.byref(pl), C.byref(pms)), model.handle, "rac_profile_end")
+    launches = model.launch_count() - launches0
+    value = frames_per_step * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end arm through the reference-facing API (host inputs, pinned noise upload, result read-back)
+    policy.noise_source = "torch"
+    e2e_plan = lambda: policy.get_action(start, goal, 0, 0)
+    e2e_plan()
+    ms_e2e = timed(e2e_plan, args.steps)
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    e2e_value = frames_per_step * args.steps / (ms_e2e * 1e-3)
+    h2d = start_np.nbytes + sum(g.nbytes for g in goals_np) + sum(g.nbytes for g in gmasks_np) + ITERS * n_total * L_STEPS * 2 * 4
+    d2h = L_STEPS * 2 * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    bf16_peak, hbm_peak, peak_src = peaks()
+    n_local = n_total // world
+    k_launches = max(1, pl.value)
+    avg_ms = pms.value / k_launches
+    flops_per_launch = FLOP_LSTM0_PER_CAND * n_local
+    achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12
+    roofline = {
+        "bound": "tensor", "kernel": "conv_tc_kernel<128, EPI_LSTM> on {prior,frame_predictor}.lstm.0.gates (5x5, 1024->2048)",
+        "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak, "traffic": None,
+        "peak_source": peak_src, "launches_timed": int(pl.value), "avg_launch_ms": avg_ms,
+        "algorithmic_flops_per_launch": flops_per_launch,
+        "kernel_share_of_step": pms.value / ms,
+    }
+    whole = {"achieved": value * FLOP_PER_FRAME / world / 1e12, "peak": bf16_peak, "unit": "TFLOP/s per GPU",
+             "frac": value * FLOP_PER_FRAME / world / 1e12 / bf16_peak, "flop_per_frame": FLOP_PER_FRAME}
+    cpu = None
+    if not args.no_cpu_baseline and args.gpus == 1:
+        threads = os.cpu_count() or 1
+        cpu_port_run(8, 1, threads)
+        f, s = cpu_port_run(32, 2, threads)
+        cpu = {"value": f / s, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"32 candidates x {L_STEPS} frames x 2 iterations = {f} frames in {s:.1f} s (work is linear in N*L*I), fp32 torch CPU"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "config": workload_config(args.gpus, world),
+        "plan_latency_ms": ms / args.steps,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
+        "roofline_whole_step": whole, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -180,6 +180,12 @@ int rac_debug_buffer(rac_handle* h, const char* name, void** ptr, int64_t* elems
 /* Number of kernels the library has launched on this handle since creation (bench.py gpu_launches). */
 int64_t rac_launch_count(const rac_handle* h);
 
+/* Live timing of one kernel family for the roofline line of bench.py: CUDA event pairs are recorded on the launch
+ * stream around every convolution launch whose layer name contains `name_substr` (e.g. "lstm.0"), up to
+ * `max_launches`. rac_profile_end waits for the recorded events and returns their count and summed duration. */
+int rac_profile_begin(rac_handle* h, const char* name_substr, int max_launches);
+int rac_profile_end(rac_handle* h, int64_t* launches, double* total_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -235,21 +235,34 @@ class CEMPolicy(object):
     @torch.no_grad()
     def get_action(self, start, goal, ep_num, step, opt_traj=None):
         """cem.py:56-111. Returns the refit mean, np.float32 (horizon-1, 2)."""
-        cfg = self.cfg
-        T, N, I, K = self.horizon, self.num_actions, self.optimization_iter, self.K
-        L = T - 1
         self.ep_num, self.step = ep_num, step
         m = self.model
         dev = m._device
-        ts = self.traj_sampler
         if m.training:
             raise NotImplementedError("planning needs an eval-mode model: call model.eval()")
+        noise = self._draw_noise(self.optimization_iter, self.num_actions, self.horizon - 1, dev)
+        goal_imgs, goal_masks = self.traj_sampler._goal_tensors(goal)
+        start_img = torch.from_numpy(np.ascontiguousarray(start.img).astype(np.uint8)).to(dev, non_blocking=True)
+        mean = self.plan_device(start_img, goal_imgs, goal_masks, noise, start=start, goal=goal, opt_traj=opt_traj)
+        out = mean.cpu().numpy()  # the one device->host read of the plan
+        if self.verbose:
+            print("Mean actions:", out)
+        return out
+
+    @torch.no_grad()
+    def plan_device(self, start_img, goal_imgs, goal_masks=None, noise=None, start=None, goal=None, opt_traj=None):
+        """The plan on device-resident inputs: start_img uint8 (H,W,3), goal_imgs uint8 (G,H,W,3), goal_masks fp32
+        (G,H,W) or None, noise fp32 (opt_iter, N, horizon-1, 2) or None (Philox). Returns the mean as a (horizon-1, 2)
+        CUDA tensor without synchronising. `start` / `goal` are only needed when a host-side robot model runs."""
+        cfg = self.cfg
+        T, N, I, K = self.horizon, self.num_actions, self.optimization_iter, self.K
+        L = T - 1
+        m = self.model
+        dev = m._device
+        ts = self.traj_sampler
         world, rank = parallel.world_info(self.process_group)
         lo, hi = parallel.shard_range(N, rank, world)
         n_local = hi - lo
-        noise = self._draw_noise(I, N, L, dev)
-        goal_imgs, goal_masks = ts._goal_tensors(goal)
-        start_img = torch.from_numpy(np.ascontiguousarray(start.img).astype(np.uint8)).to(dev, non_blocking=True)
         host_robot = _needs_robot(cfg) and self.precomputed_robot is None
         A = m._c.action_dim
         plan_seed = (self._seed + 0x9E3779B97F4A7C15 * (self._plans + 1)) & 0xFFFFFFFFFFFFFFFF
@@ -257,7 +270,7 @@ class CEMPolicy(object):
         ts._seed = plan_seed
 
         if world == 1 and not host_robot and opt_traj is None and not self.plot_rollouts:
-            # ---- whole plan on the device: one C call, one result read
+            # ---- whole plan on the device: one C call
             m.prepare(N)
             c = _lib.RacCem()
             c.n, c.steps, c.iters, c.topk = N, L, I, K
@@ -266,7 +279,6 @@ class CEMPolicy(object):
             r = c.rollout
             r.start_img, r.goal_imgs, r.num_goals = _lib.ptr(start_img), _lib.ptr(goal_imgs), goal_imgs.shape[0]
             r.goal_masks = _lib.ptr(goal_masks)
-            states = masks = None
             if self.precomputed_robot is not None:
                 states, masks = self.precomputed_robot
                 if getattr(cfg, "model_use_robot_state", False):
@@ -285,7 +297,7 @@ class CEMPolicy(object):
             _lib.check(self._lib.rac_cem_plan(m.handle, C.byref(c), _lib.ptr(mean), _lib.ptr(std), _lib.ptr(elite),
                                               _lib.ptr(costs), _lib.stream_ptr()), m.handle, "rac_cem_plan")
             self.last_costs, self.last_elite_idx, self.last_std = costs, elite, std
-            return mean.cpu().numpy()
+            return mean
 
         # ---- per-iteration path: sharded candidates and / or a host-side robot model
         m.prepare(n_local)
@@ -311,11 +323,10 @@ class CEMPolicy(object):
                 states = masks = None
                 if self.precomputed_robot is not None:
                     states, masks = self.precomputed_robot
-                    states = states[:, lo:hi] if getattr(cfg, "model_use_robot_state", False) else None
-                    masks = masks[:, lo:hi]
-                    # a shard of (T+1, N, ...) is strided over time; the C ABI takes the time stride explicitly
-                    states = None if states is None else _StridedView(states)
-                    masks = _StridedView(masks)
+                    # a shard of (T+1, N, ...) is contiguous per time step and strided across steps; the C ABI takes
+                    # the time stride explicitly
+                    states = _StridedView(states[:, lo:hi]) if getattr(cfg, "model_use_robot_state", False) else None
+                    masks = _StridedView(masks[:, lo:hi])
                 ts._rollout_device(act5, start_img, goal_imgs, goal_masks, states, masks, None, n_local, L, local_cost,
                                    cand_offset=lo, noise_ctr=i * L)
             costs = parallel.all_gather_costs(local_cost, N, self.process_group)
@@ -325,10 +336,7 @@ class CEMPolicy(object):
                                                _lib.ptr(std), _lib.stream_ptr()), None, "rac_cem_refit")
         self.last_costs, self.last_elite_idx, self.last_std = costs, elite, std
         self.last_rollouts = rollouts
-        out = mean.cpu().numpy()
-        if self.verbose:
-            print("Mean actions:", out)
-        return out
+        return mean
 
 
 class _StridedView:

@@ -201,7 +201,7 @@ cost_finish_kernel(const float* __restrict__ part, int nparts, int dontcare, flo
   float dist = sqrtf(sq);
   if (dontcare) dist = dist / cnt;  // reference divides without +1 (losses.py:259-260)
   const float cost = weight * (-dist);
-  if (step_cost) step_cost[b] = cost;
+  if (step_cost) step_cost[b] = accumulate ? cost : 0.f;  // unused steps report rew = 0 (trajectory_sampler.py:165-173)
   if (accumulate) sum_cost[b] += static_cast<double>(cost);
 }
 cudaError_t launch_cost_finish(const float* cost_part, int nparts, int dontcare, float weight, int accumulate,

@@ -83,6 +83,11 @@ struct rac_handle {
   EncodeTiledFn encode = nullptr;
   int64_t launches = 0;
   char err[512] = {0};
+  // live per-kernel timing (bench.py roofline): CUDA event pairs around every launch whose op name has this prefix
+  std::string prof_prefix;
+  std::vector<cudaEvent_t> prof_ev;
+  size_t prof_used = 0;
+  int64_t prof_dropped = 0;
 };
 
 namespace {
@@ -243,7 +248,20 @@ void set_act(ConvOp* op, bf16* out, int cstride, int coff, int upsample, int lre
 }
 
 int launch(rac_handle* h, const ConvOp& op, cudaStream_t st) {
+  bool timed = false;
+  if (!h->prof_prefix.empty() && strstr(op.name, h->prof_prefix.c_str()) != nullptr) {
+    if (h->prof_used + 2 <= h->prof_ev.size()) {
+      timed = true;
+      cudaEventRecord(h->prof_ev[h->prof_used], st);
+    } else {
+      h->prof_dropped++;
+    }
+  }
   cudaError_t e = h->cfg.conv_impl == 1 ? launch_conv_simt(op, st) : launch_conv_tc(op, h->num_sms, st);
+  if (timed) {
+    cudaEventRecord(h->prof_ev[h->prof_used + 1], st);
+    h->prof_used += 2;
+  }
   if (e != cudaSuccess) return fail(h, RAC_ERR_CUDA, "launch of conv '%s' failed: %s", op.name, cudaGetErrorString(e));
   h->launches++;
   return RAC_OK;
@@ -599,6 +617,7 @@ int rac_create(const rac_config* cfg, rac_handle** out) {
 int rac_destroy(rac_handle* h) {
   if (!h) return RAC_OK;
   free_ws(h);
+  for (cudaEvent_t ev : h->prof_ev) cudaEventDestroy(ev);
   for (int i = 0; i < RAC_L_COUNT; ++i) {
     if (h->layer[i].w) cudaFree(h->layer[i].w);
     if (h->layer[i].bias) cudaFree(h->layer[i].bias);
@@ -867,5 +886,34 @@ int rac_debug_buffer(rac_handle* h, const char* name, void** ptr, int64_t* elems
 }
 
 int64_t rac_launch_count(const rac_handle* h) { return h ? h->launches : 0; }
+
+int rac_profile_begin(rac_handle* h, const char* name_substr, int max_launches) {
+  if (!h || !name_substr || max_launches < 1) return RAC_ERR_INVALID;
+  for (cudaEvent_t ev : h->prof_ev) cudaEventDestroy(ev);
+  h->prof_ev.assign(static_cast<size_t>(max_launches) * 2, nullptr);
+  for (auto& ev : h->prof_ev) CK(cudaEventCreate(&ev));
+  h->prof_prefix = name_substr;
+  h->prof_used = 0;
+  h->prof_dropped = 0;
+  return RAC_OK;
+}
+
+int rac_profile_end(rac_handle* h, int64_t* launches, double* total_ms) {
+  if (!h || !launches || !total_ms) return RAC_ERR_INVALID;
+  double acc = 0.0;
+  for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+    CK(cudaEventSynchronize(h->prof_ev[i + 1]));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]));
+    acc += ms;
+  }
+  *launches = static_cast<int64_t>(h->prof_used / 2);
+  *total_ms = acc;
+  for (cudaEvent_t ev : h->prof_ev) cudaEventDestroy(ev);
+  h->prof_ev.clear();
+  h->prof_prefix.clear();
+  h->prof_used = 0;
+  return RAC_OK;
+}
 
 }  // extern "C"

@@ -23,6 +23,8 @@ def _masked_cost(curr_img, goal_img, curr_mask, goal_mask, dontcare):
         raise NotImplementedError(f"Tensor shape {tuple(curr_img.shape)} not supported")
     lib = _lib.load()
     n, ch, h, w = curr_img.shape
+    if n == 0:
+        return np.zeros(0, dtype=np.float32)
     curr = _dev(curr_img)
     goal = _dev(goal_img.expand(ch, h, w) if goal_img.dim() == 3 else goal_img)
     cm = _dev(curr_mask) if dontcare else None

@@ -279,10 +279,11 @@ def test_sample_and_refit_match_oracle(golden_dir):
     noise = torch.randn(N, L, 2, generator=g)
     mean = torch.randn(L, 2, generator=g) * 0.01
     std = torch.rand(L, 2, generator=g) * 0.05
+    mean_d, std_d, noise_d = mean.cuda(), std.cuda(), noise.cuda()  # keep alive: the ABI takes raw pointers
     for it in (0, 1):
         act2 = torch.empty(N, L, 2, device="cuda")
         act5 = torch.full((16, L, A), 9.0, device="cuda")
-        _lib.check(lib.rac_cem_sample(_lib.ptr(mean.cuda()), _lib.ptr(std.cuda()), _lib.ptr(noise.cuda()), 0, it, N, L,
+        _lib.check(lib.rac_cem_sample(_lib.ptr(mean_d), _lib.ptr(std_d), _lib.ptr(noise_d), 0, it, N, L,
                                       A, 32, 16, 0.05, _lib.ptr(act2), _lib.ptr(act5), _lib.stream_ptr()), None, "sample")
         ref = so.cem_sample(mean, std, noise.clone(), it)
         np.testing.assert_allclose(act2.cpu().numpy(), ref.numpy(), rtol=0, atol=1e-9)
@@ -291,9 +292,10 @@ def test_sample_and_refit_match_oracle(golden_dir):
     # Philox path: deterministic, clamped, iteration-0 do-nothing candidate, shard-independent
     a = torch.empty(N, L, 2, device="cuda"); a5 = torch.empty(N, L, A, device="cuda")
     b = torch.empty(N, L, 2, device="cuda"); b5 = torch.empty(8, L, A, device="cuda")
-    one = torch.ones(L, 2, device="cuda")
-    lib.rac_cem_sample(_lib.ptr(one * 0), _lib.ptr(one * 0.03), None, 77, 0, N, L, A, 0, N, 0.05, _lib.ptr(a), _lib.ptr(a5), _lib.stream_ptr())
-    lib.rac_cem_sample(_lib.ptr(one * 0), _lib.ptr(one * 0.03), None, 77, 0, N, L, A, 40, 8, 0.05, _lib.ptr(b), _lib.ptr(b5), _lib.stream_ptr())
+    zero_d = torch.zeros(L, 2, device="cuda")
+    s03_d = torch.full((L, 2), 0.03, device="cuda")
+    lib.rac_cem_sample(_lib.ptr(zero_d), _lib.ptr(s03_d), None, 77, 0, N, L, A, 0, N, 0.05, _lib.ptr(a), _lib.ptr(a5), _lib.stream_ptr())
+    lib.rac_cem_sample(_lib.ptr(zero_d), _lib.ptr(s03_d), None, 77, 0, N, L, A, 40, 8, 0.05, _lib.ptr(b), _lib.ptr(b5), _lib.stream_ptr())
     assert torch.equal(a, b) and torch.equal(a5[40:48], b5)
     assert float(a.abs().max()) <= 0.05 and float(a[-1].abs().max()) == 0.0
     assert 0.015 < float(a[:-1].std()) < 0.04
@@ -306,7 +308,8 @@ def test_sample_and_refit_match_oracle(golden_dir):
     np.testing.assert_allclose(m_out.cpu().numpy(), gold["refit_mean"], rtol=2e-6, atol=1e-9)
     np.testing.assert_allclose(s_out.cpu().numpy(), gold["refit_std"], rtol=2e-6)
     tiny = (torch.ones(8, 4, 2) * 0.01).cuda()
-    lib.rac_cem_refit(_lib.ptr(tiny), 4, _lib.ptr(idx[:8]), 8, 0.001, _lib.ptr(m_out), _lib.ptr(s_out), _lib.stream_ptr())
+    idx8 = idx[:8].contiguous()
+    lib.rac_cem_refit(_lib.ptr(tiny), 4, _lib.ptr(idx8), 8, 0.001, _lib.ptr(m_out), _lib.ptr(s_out), _lib.stream_ptr())
     assert torch.all(s_out == 0.001)  # std floor (cem.py:104)
 
 
