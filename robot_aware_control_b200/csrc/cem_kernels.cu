@@ -24,8 +24,9 @@ cem_sample_kernel(const float* __restrict__ mean, const float* __restrict__ stdv
                                     0xce3u, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
     box_muller(r.v[0], r.v[1], z0, z1);
   }
-  float a0 = mean[t * 2] + stdv[t * 2] * z0;
-  float a1 = mean[t * 2 + 1] + stdv[t * 2 + 1] * z1;
+  // separate multiply and add (no FMA contraction): bit-identical to torch's `mean + std * noise` on the host
+  float a0 = __fadd_rn(mean[t * 2], __fmul_rn(stdv[t * 2], z0));
+  float a1 = __fadd_rn(mean[t * 2 + 1], __fmul_rn(stdv[t * 2 + 1], z1));
   if (iter == 0 && n == n_total - 1) a0 = a1 = 0.f;
   a0 = fminf(fmaxf(a0, -clampv), clampv);
   a1 = fminf(fmaxf(a1, -clampv), clampv);
