@@ -34,10 +34,17 @@ def all_gather_costs(local_costs, n_total, group=None):
     if world == 1:
         return local_costs
     sizes = [shard_range(n_total, r, world) for r in range(world)]
-    if all(hi - lo == sizes[0][1] - sizes[0][0] for lo, hi in sizes):
+    width = max(hi - lo for lo, hi in sizes)
+    lo, hi = sizes[rank]
+    if local_costs.numel() != hi - lo:
+        raise ValueError(f"rank {rank} holds {local_costs.numel()} costs, its shard has {hi - lo}")
+    if all(b - a == width for a, b in sizes):
         out = torch.empty(n_total, dtype=local_costs.dtype, device=local_costs.device)
         dist.all_gather_into_tensor(out, local_costs.contiguous(), group=group)
         return out
-    parts = [torch.empty(hi - lo, dtype=local_costs.dtype, device=local_costs.device) for lo, hi in sizes]
-    dist.all_gather(parts, local_costs.contiguous(), group=group)
-    return torch.cat(parts)
+    # uneven split: collectives need equal sizes, so pad every shard to the widest one and cut the padding out
+    padded = torch.zeros(width, dtype=local_costs.dtype, device=local_costs.device)
+    padded[: hi - lo] = local_costs
+    out = torch.empty(world * width, dtype=local_costs.dtype, device=local_costs.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return torch.cat([out[r * width: r * width + (b - a)] for r, (a, b) in enumerate(sizes)])
