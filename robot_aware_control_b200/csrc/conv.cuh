@@ -3,7 +3,7 @@
 //
 // Activations are NHWC bf16: tensor [B, H, W, C] with C a multiple of 64. A convolution is the GEMM
 //   D[m, n] = sum_{tap, c} A[(b, y + kh - pad, x + kw - pad), c] * Wp[n, tap * Ctot + c]
-// with m = (b, y, x). One M-tile is 128 rows = a TMA box {64 ch, W, BH, NB} (W * BH * NB == 128); zero padding
+// with m = (b, y, x). One M-tile is BLOCK_M (128 or 256) rows = a TMA box {64 ch, W, BH, NB} (W * BH * NB == BLOCK_M); zero padding
 // comes from TMA out-of-bounds fill, the channel concat of several inputs (reference: torch.cat at
 // src/prediction/models/dynamics.py:600-641, lstm.py:132, vgg_64.py:236-240) is a loop over source tensors.
 #pragma once
@@ -22,7 +22,7 @@ constexpr int kBlockK = 64;  // bf16 channels per k-block = one 128-byte swizzle
 
 struct ConvGeom {
   int B, H, W;          // candidates, output (= input) spatial size
-  int BH, NB;           // rows / candidates per M-tile (W * BH * NB == 128)
+  int BH, NB;           // rows / candidates per M-tile (W * BH * NB == BLOCK_M)
   int ks, pad;          // square filter, 'same' padding
   int nsrc;             // concatenated inputs
   int src_kb[kMaxSrc];  // k-blocks (channels / 64) per input
@@ -57,7 +57,7 @@ struct EpiParams {
   const float* goal_img;   // [H,W,4] fp32
   const float* goal_mask;  // [H,W] fp32 or null
   float* xpred_out;        // NCHW (B,4,H,W) fp32 or null
-  float* cost_part;        // [B][tiles_per_img*4][2] (sum of squares, world pixel count) or null
+  float* cost_part;        // [B][H*W/32][2] (sum of squares, world pixel count), one partial per warp, or null
   int zero_robot, dontcare;
 };
 
@@ -77,6 +77,7 @@ struct ConvOp {
   EpiParams e;
   ConvTmaps tm;
   ConvRaw raw;
+  int block_m;
   int block_n;
   int epi;
   const char* name;

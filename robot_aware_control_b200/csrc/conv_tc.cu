@@ -1,10 +1,13 @@
 // Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), operands staged
 // by TMA into 128B-swizzled shared memory. Persistent, warp-specialised:
 //   warp 0   : TMA producer  (one thread)   -- A: 4-D box {64 ch, W, BH, NB} per filter tap, B: 2-D weight box
-//   warp 1   : MMA issuer    (one thread)   -- 4 x tcgen05.mma (M128 x BLOCK_N x K16) per 64-channel k-block
+//   warp 1   : MMA issuer    (one thread)   -- 4 x (BLOCK_M/128) tcgen05.mma (M128 x BLOCK_N x K16) per 64-channel k-block
 //   warp 2   : TMEM allocator
-//   warps 4-7: epilogue      (128 threads)  -- tcgen05.ld -> fused epilogue (epilogue.cuh) -> global
-// Two TMEM accumulator buffers let the epilogue of tile i overlap the main loop of tile i+1.
+//   warps 4.. : epilogue     (one thread per output row: 128 or 256) -- tcgen05.ld -> fused epilogue -> global
+// A CTA tile is BLOCK_M (128 or 256 rows = 1 or 2 MMA sub-tiles sharing the weight tile) x BLOCK_N. Two TMEM accumulator
+// stages let the epilogue of tile i overlap the main loop of tile i+1 whenever 2 x (BLOCK_M/128) x BLOCK_N <= 512 columns;
+// the 256x256 tile of the LSTM gate convolutions uses all 512 columns single-buffered (its main loop is 150-400
+// k-blocks long, the exposed epilogue is a few per cent) to halve the L2->SMEM bytes per FLOP.
 //
 // Replaces the cuDNN/ATen calls behind nn.Conv2d / BatchNorm2d / LeakyReLU / ConvTranspose2d / Sigmoid and the
 // LSTM / reparameterisation / compositing / cost pointwise ops of the reference:
@@ -16,22 +19,38 @@
 
 namespace rac {
 
-template <int BLOCK_N>
+template <int BLOCK_M, int BLOCK_N>
 struct TcCfg {
-  static constexpr int kABytes = kTileM * kBlockK * 2;   // 16 KB
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;  // BLOCK_N rows of 128 B
+  static constexpr int kSub = BLOCK_M / kTileM;              // 128-row MMA sub-tiles per CTA tile
+  static constexpr int kABytes = BLOCK_M * kBlockK * 2;      // BLOCK_M rows of 128 B
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;      // BLOCK_N rows of 128 B
   static constexpr int kBBytesPad = (kBBytes + 1023) / 1024 * 1024;
   static constexpr int kStageBytes = kABytes + kBBytesPad;
-  static constexpr int kStages = (BLOCK_N >= 128) ? 6 : 8;
-  static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : 256));
+  static constexpr int kStagesFit = (200 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+  static constexpr int kAccCols = kSub * BLOCK_N;            // TMEM columns of one accumulator stage
+  static constexpr int kNumAcc = (2 * kAccCols <= 512) ? 2 : 1;
+  static constexpr int kTmemNeed = kNumAcc * kAccCols;
+  static constexpr int kTmemCols = kTmemNeed <= 32 ? 32 : (kTmemNeed <= 64 ? 64 : (kTmemNeed <= 128 ? 128 : (kTmemNeed <= 256 ? 256 : 512)));
+  static constexpr int kEpiThreads = BLOCK_M;                // one thread per output row
+  static constexpr int kThreads = 128 + kEpiThreads;
   static constexpr int kBarBytes = 1024;
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024 alignment slack
+  static_assert(kTmemNeed <= 512, "accumulators do not fit TMEM");
+  static_assert(kStages >= 2, "pipeline needs at least two stages");
 };
 
-template <int BLOCK_N, int EPI>
-__global__ void __launch_bounds__(256, 1)
+// A filter row kh contributes nothing to a tile whose input rows y0+kh-pad .. +BH-1 all fall into the zero padding
+// (top / bottom tiles of the 6x8 latent maps with the 5x5 filter): producer and MMA issuer both skip it.
+__device__ __forceinline__ bool tap_row_live(const ConvGeom& g, int y0, int kh) {
+  const int ylo = y0 + kh - g.pad;
+  return ylo + g.BH > 0 && ylo < g.H;
+}
+
+template <int BLOCK_M, int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(TcCfg<BLOCK_M, BLOCK_N>::kThreads, 1)
 conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const EpiParams e) {
-  using Cfg = TcCfg<BLOCK_N>;
+  using Cfg = TcCfg<BLOCK_M, BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* bar_base = smem + Cfg::kStages * Cfg::kStageBytes;
@@ -44,10 +63,8 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = g.num_m_tiles * g.num_n_tiles;
-  const int taps = g.ks * g.ks;
   int kb_per_tap = 0;
   for (int s = 0; s < g.nsrc; ++s) kb_per_tap += g.src_kb[s];
-  const int num_kb = taps * kb_per_tap;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < g.nsrc; ++s) tma_prefetch_desc(&tm.a[s]);
@@ -60,7 +77,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], Cfg::kEpiThreads);
     }
     fence_barrier_init();
   }
@@ -83,9 +100,10 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
       const int grp = m_tile / g.tiles_per_img;
       const int b0 = grp * g.NB;
       const int y0 = (m_tile - grp * g.tiles_per_img) * g.BH;
-      int kidx = 0;
       for (int kh = 0; kh < g.ks; ++kh) {
+        if (!tap_row_live(g, y0, kh)) continue;
         for (int kw = 0; kw < g.ks; ++kw) {
+          int kidx = (kh * g.ks + kw) * kb_per_tap;
           for (int s = 0; s < g.nsrc; ++s) {
             for (int kb = 0; kb < g.src_kb[s]; ++kb, ++kidx) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -108,9 +126,15 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_tile = tile / g.num_m_tiles;
+      const int m_tile = tile - n_tile * g.num_m_tiles;
+      const int y0 = (m_tile % g.tiles_per_img) * g.BH;
+      int live = 0;
+      for (int kh = 0; kh < g.ks; ++kh) live += tap_row_live(g, y0, kh) ? 1 : 0;
+      const int num_kb = live * g.ks * kb_per_tap;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -119,19 +143,26 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
         const uint64_t bdesc = umma_desc_sw128(sa + Cfg::kABytes);
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k) {
-          // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in the (addr >> 4) field
-          umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+          for (int sub = 0; sub < Cfg::kSub; ++sub) {
+            // +2 in the (addr >> 4) field = 32 B = 16 bf16 along K inside the 128B swizzle row;
+            // sub-tile s starts 128 rows * 128 B = 16 KB further (1024-B aligned, swizzle phase preserved)
+            umma_bf16_ss(d_tmem + sub * BLOCK_N, adesc + 2 * k + sub * (kTileM * 128 / 16), bdesc + 2 * k, idesc,
+                         (kb | k) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
         if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == Cfg::kNumAcc) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int wq = warp - 4;  // TMEM lane quarter == warp_id % 4
-    const int r = wq * 32 + lane;
+    const int we = warp - 4;       // epilogue warp index
+    const int wq = we & 3;         // TMEM lane quarter == warp_id % 4
+    const int sub = we >> 2;       // 128-row sub-tile
+    const int r = we * 32 + lane;  // row inside the BLOCK_M tile
     int acc = 0;
     uint32_t acc_phase = 0;
     constexpr int CH = (BLOCK_N >= 32) ? 32 : 16;
@@ -146,7 +177,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
       const bool valid = b < g.B;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BLOCK_N;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * Cfg::kAccCols + sub * BLOCK_N;
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / CH; ++c) {
         float v[CH];
@@ -156,11 +187,11 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
         if constexpr (EPI == EPI_ACT) epi_act<CH>(g, e, b, y, x, valid, n0, v);
         if constexpr (EPI == EPI_LSTM) epi_lstm(g, e, b, y, x, valid, n0, v);
         if constexpr (EPI == EPI_GAUSS) epi_gauss(g, e, b, y, x, valid, n0, v);
-        if constexpr (EPI == EPI_FRAME) epi_frame(g, e, b, y, x, valid, yb * 4 + wq, v);
+        if constexpr (EPI == EPI_FRAME) epi_frame(g, e, b, y, x, valid, yb * (BLOCK_M / 32) + we, v);
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == Cfg::kNumAcc) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -173,8 +204,8 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
 // SIMT cross-check kernel: same geometry, same packed weights, same epilogues, no tensor cores / TMA. It exists so
 // that the tcgen05 path can be validated tile by tile on the GPU (tests/, RAC_CONV_IMPL=simt); it is not a product
 // path and nothing dispatches to it by default.
-template <int BLOCK_N, int EPI>
-__global__ void __launch_bounds__(128)
+template <int BLOCK_M, int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(BLOCK_M)
 conv_simt_kernel(const ConvRaw raw, const ConvGeom g, const EpiParams e) {
   constexpr int CH = (BLOCK_N >= 32) ? 32 : 16;
   constexpr int chunks = BLOCK_N / CH;
@@ -219,52 +250,60 @@ conv_simt_kernel(const ConvRaw raw, const ConvGeom g, const EpiParams e) {
   if constexpr (EPI == EPI_ACT) epi_act<CH>(g, e, b, y, x, valid, n0, acc);
   if constexpr (EPI == EPI_LSTM) epi_lstm(g, e, b, y, x, valid, n0, acc);
   if constexpr (EPI == EPI_GAUSS) epi_gauss(g, e, b, y, x, valid, n0, acc);
-  if constexpr (EPI == EPI_FRAME) epi_frame(g, e, b, y, x, valid, yb * 4 + (r >> 5), acc);
+  if constexpr (EPI == EPI_FRAME) epi_frame(g, e, b, y, x, valid, yb * (BLOCK_M / 32) + (r >> 5), acc);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-template <int BLOCK_N, int EPI>
+template <int BLOCK_M, int BLOCK_N, int EPI>
 static cudaError_t launch_tc_t(const ConvOp& op, int num_sms, cudaStream_t stream) {
+  using Cfg = TcCfg<BLOCK_M, BLOCK_N>;
   const int num_tiles = op.g.num_m_tiles * op.g.num_n_tiles;
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  conv_tc_kernel<BLOCK_N, EPI><<<grid, 256, TcCfg<BLOCK_N>::kSmemBytes, stream>>>(op.tm, op.g, op.e);
+  conv_tc_kernel<BLOCK_M, BLOCK_N, EPI><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(op.tm, op.g, op.e);
   return cudaGetLastError();
 }
-template <int BLOCK_N, int EPI>
+template <int BLOCK_M, int BLOCK_N, int EPI>
 static cudaError_t launch_simt_t(const ConvOp& op, cudaStream_t stream) {
   constexpr int CH = (BLOCK_N >= 32) ? 32 : 16;
   const int grid = op.g.num_m_tiles * op.g.num_n_tiles * (BLOCK_N / CH);
-  conv_simt_kernel<BLOCK_N, EPI><<<grid, 128, 0, stream>>>(op.raw, op.g, op.e);
+  conv_simt_kernel<BLOCK_M, BLOCK_N, EPI><<<grid, BLOCK_M, 0, stream>>>(op.raw, op.g, op.e);
   return cudaGetLastError();
 }
 
-#define RAC_CONV_DISPATCH(FN, ...)                                                                  \
-  if (op.block_n == 128 && op.epi == EPI_ACT) return FN<128, EPI_ACT>(__VA_ARGS__);                 \
-  if (op.block_n == 64 && op.epi == EPI_ACT) return FN<64, EPI_ACT>(__VA_ARGS__);                   \
-  if (op.block_n == 128 && op.epi == EPI_LSTM) return FN<128, EPI_LSTM>(__VA_ARGS__);               \
-  if (op.block_n == 128 && op.epi == EPI_GAUSS) return FN<128, EPI_GAUSS>(__VA_ARGS__);             \
-  if (op.block_n == 16 && op.epi == EPI_FRAME) return FN<16, EPI_FRAME>(__VA_ARGS__);               \
-  return cudaErrorInvalidValue;
+// the (BLOCK_M, BLOCK_N, epilogue) instantiations the layer table uses (rac_api.cu::fill_specs / make_conv)
+#define RAC_CONV_CASES(X)   \
+  X(256, 256, EPI_ACT)      \
+  X(256, 128, EPI_ACT)      \
+  X(256, 64, EPI_ACT)       \
+  X(256, 256, EPI_LSTM)     \
+  X(256, 128, EPI_GAUSS)    \
+  X(256, 16, EPI_FRAME)     \
+  X(128, 128, EPI_ACT)      \
+  X(128, 64, EPI_ACT)       \
+  X(128, 128, EPI_LSTM)     \
+  X(128, 128, EPI_GAUSS)    \
+  X(128, 16, EPI_FRAME)
 
 cudaError_t launch_conv_tc(const ConvOp& op, int num_sms, cudaStream_t stream) {
-  RAC_CONV_DISPATCH(launch_tc_t, op, num_sms, stream)
+#define X(M, N, E) if (op.block_m == M && op.block_n == N && op.epi == E) return launch_tc_t<M, N, E>(op, num_sms, stream);
+  RAC_CONV_CASES(X)
+#undef X
+  return cudaErrorInvalidValue;
 }
 cudaError_t launch_conv_simt(const ConvOp& op, cudaStream_t stream) {
-  RAC_CONV_DISPATCH(launch_simt_t, op, stream)
-}
-
-template <int BLOCK_N, int EPI>
-static cudaError_t set_attr_t() {
-  return cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              TcCfg<BLOCK_N>::kSmemBytes);
+#define X(M, N, E) if (op.block_m == M && op.block_n == N && op.epi == E) return launch_simt_t<M, N, E>(op, stream);
+  RAC_CONV_CASES(X)
+#undef X
+  return cudaErrorInvalidValue;
 }
 cudaError_t conv_tc_set_attributes() {
   cudaError_t err;
-  if ((err = set_attr_t<128, EPI_ACT>()) != cudaSuccess) return err;
-  if ((err = set_attr_t<64, EPI_ACT>()) != cudaSuccess) return err;
-  if ((err = set_attr_t<128, EPI_LSTM>()) != cudaSuccess) return err;
-  if ((err = set_attr_t<128, EPI_GAUSS>()) != cudaSuccess) return err;
-  if ((err = set_attr_t<16, EPI_FRAME>()) != cudaSuccess) return err;
+#define X(M, N, E)                                                                                         \
+  if ((err = cudaFuncSetAttribute(conv_tc_kernel<M, N, E>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                  TcCfg<M, N>::kSmemBytes)) != cudaSuccess)                                \
+    return err;
+  RAC_CONV_CASES(X)
+#undef X
   return cudaSuccess;
 }
 

@@ -198,7 +198,7 @@ __device__ __forceinline__ void epi_frame(const ConvGeom& g, const EpiParams& e,
       cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     }
     if ((threadIdx.x & 31) == 0 && valid) {
-      float* dst = e.cost_part + (static_cast<size_t>(b) * (g.tiles_per_img * 4) + part_idx) * 2;
+      float* dst = e.cost_part + (static_cast<size_t>(b) * (g.H * g.W / 32) + part_idx) * 2;  // one partial per warp
       dst[0] = sq;
       dst[1] = cnt;
     }

@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -26,7 +27,7 @@ struct LayerSpec {
   int ctot = 0;     // padded input channels per tap
   int n_packed = 0; // padded output columns
   int cout = 0;     // valid output columns (packed order)
-  int block_n = 128;
+  int block_n = 128;   // packing granularity of the output columns (pack.py); the launch tile may be wider
   bool first = false;  // fp32 first layer
 };
 
@@ -79,6 +80,7 @@ struct rac_handle {
   LayerSpec spec[RAC_L_COUNT];
   Layer layer[RAC_L_COUNT];
   Workspace ws;
+  int tile_m = 256;        // rows per CTA tile (RAC_TILE_M=128 selects the 128-row tiles, for A/B measurements)
   int cur[3] = {0, 0, 0};  // ping-pong index of the live hidden state per LSTM stack
   EncodeTiledFn encode = nullptr;
   int64_t launches = 0;
@@ -208,15 +210,18 @@ int make_conv(rac_handle* h, ConvOp* op, const char* name, int layer, int H, int
   const int B = h->ws.B;
   memset(op, 0, sizeof(*op));
   op->name = name;
+  op->block_m = h->tile_m;
   op->block_n = s.block_n;
+  if (h->tile_m == 256 && s.n_packed % 256 == 0 && (epi == EPI_ACT || epi == EPI_LSTM)) op->block_n = 256;
   op->epi = epi;
   ConvGeom& g = op->g;
   g.B = B; g.H = H; g.W = W; g.ks = s.ks; g.pad = s.ks / 2;
-  switch (W) {
-    case 64: g.BH = 2; g.NB = 1; break;
-    case 32: g.BH = 4; g.NB = 1; break;
-    case 16: g.BH = 4; g.NB = 2; break;
-    case 8: g.BH = 2; g.NB = 8; break;
+  const bool big = h->tile_m == 256;
+  switch (W) {  // TMA box {64 ch, W, BH, NB} with W * BH * NB == tile_m
+    case 64: g.BH = big ? 4 : 2; g.NB = 1; break;
+    case 32: g.BH = big ? 8 : 4; g.NB = 1; break;
+    case 16: g.BH = 4; g.NB = big ? 4 : 2; break;
+    case 8: g.BH = 2; g.NB = big ? 16 : 8; break;
     default: return fail(h, RAC_ERR_INVALID, "unsupported feature-map width %d", W);
   }
   if (H % g.BH != 0) return fail(h, RAC_ERR_INVALID, "feature-map height %d not divisible by tile rows %d", H, g.BH);
@@ -232,12 +237,12 @@ int make_conv(rac_handle* h, ConvOp* op, const char* name, int layer, int H, int
   if (g.ctot != s.ctot) return fail(h, RAC_ERR_INVALID, "%s: channel mismatch %d vs packed %d", name, g.ctot, s.ctot);
   g.tiles_per_img = H / g.BH;
   g.num_m_tiles = ((B + g.NB - 1) / g.NB) * g.tiles_per_img;
-  g.num_n_tiles = s.n_packed / s.block_n;
+  g.num_n_tiles = s.n_packed / op->block_n;
   g.w_shift = ilog2(W);
   g.bhw_shift = ilog2(g.BH * W);
   const bf16* wp = static_cast<const bf16*>(h->layer[layer].w);
   op->raw.w = wp;
-  CKR(encode_w_map(h, &op->tm.w, wp, s.ks * s.ks * s.ctot, s.n_packed, s.block_n));
+  CKR(encode_w_map(h, &op->tm.w, wp, s.ks * s.ks * s.ctot, s.n_packed, op->block_n));
   op->e.bias = h->layer[layer].bias;
   op->e.cout = s.cout;
   return RAC_OK;
@@ -608,6 +613,11 @@ int rac_create(const rac_config* cfg, rac_handle** out) {
   CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   if (!fn || qres != cudaDriverEntryPointSuccess) return fail(h, RAC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
   h->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  if (const char* tm = getenv("RAC_TILE_M")) {
+    const int v = atoi(tm);
+    if (v != 128 && v != 256) return fail(h, RAC_ERR_INVALID, "RAC_TILE_M must be 128 or 256");
+    h->tile_m = v;
+  }
   CK(conv_tc_set_attributes());
   CK(cem_set_attributes());
   fill_specs(h);
