@@ -26,6 +26,7 @@ struct ConvGeom {
   int ks, pad;          // square filter, 'same' padding
   int nsrc;             // concatenated inputs
   int src_kb[kMaxSrc];  // k-blocks (channels / 64) per input
+  int src_dead[kMaxSrc];  // 1: this input is known to be all zero (LSTM h_prev right after init_hidden) -> its k-blocks are skipped
   int ctot;             // total input channels (sum of padded source channels)
   int num_m_tiles, num_n_tiles, tiles_per_img;  // tiles_per_img = H / BH
   int w_shift, bhw_shift;                       // log2(W), log2(BH * W)

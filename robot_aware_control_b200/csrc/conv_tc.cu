@@ -63,8 +63,11 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = g.num_m_tiles * g.num_n_tiles;
-  int kb_per_tap = 0;
-  for (int s = 0; s < g.nsrc; ++s) kb_per_tap += g.src_kb[s];
+  int kb_per_tap = 0, live_kb_per_tap = 0;
+  for (int s = 0; s < g.nsrc; ++s) {
+    kb_per_tap += g.src_kb[s];
+    if (!g.src_dead[s]) live_kb_per_tap += g.src_kb[s];
+  }
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < g.nsrc; ++s) tma_prefetch_desc(&tm.a[s]);
@@ -105,6 +108,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
         for (int kw = 0; kw < g.ks; ++kw) {
           int kidx = (kh * g.ks + kw) * kb_per_tap;
           for (int s = 0; s < g.nsrc; ++s) {
+            if (g.src_dead[s]) { kidx += g.src_kb[s]; continue; }
             for (int kb = 0; kb < g.src_kb[s]; ++kb, ++kidx) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* sa = smem + stage * Cfg::kStageBytes;
@@ -131,7 +135,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
       const int y0 = (m_tile % g.tiles_per_img) * g.BH;
       int live = 0;
       for (int kh = 0; kh < g.ks; ++kh) live += tap_row_live(g, y0, kh) ? 1 : 0;
-      const int num_kb = live * g.ks * kb_per_tap;
+      const int num_kb = live * g.ks * live_kb_per_tap;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
@@ -235,6 +239,7 @@ conv_simt_kernel(const ConvRaw raw, const ConvGeom g, const EpiParams e) {
         int coff = 0;
         for (int s = 0; s < g.nsrc; ++s) {
           const int cs = g.src_kb[s] * kBlockK;
+          if (g.src_dead[s]) { coff += cs; continue; }
           const __nv_bfloat16* ap = raw.src[s] + (static_cast<size_t>(b * g.H + yy) * g.W + xx) * cs;
           const __nv_bfloat16* wp = raw.w + static_cast<size_t>(n0) * ktot + (kh * g.ks + kw) * g.ctot + coff;
           for (int ch = 0; ch < cs; ++ch) {

@@ -18,43 +18,45 @@ first_conv_kernel(const float* __restrict__ img4, const float* __restrict__ mask
   for (int i = threadIdx.x; i < 9 * cin * 64; i += blockDim.x) sw[i] = w[i];
   if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
-  const size_t gid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t pix = gid >> 3;
-  const int o8 = static_cast<int>(gid & 7) * 8;
   const size_t total = static_cast<size_t>(B) * H * W;
-  if (pix >= total) return;
-  const int x = static_cast<int>(pix % W);
-  const int y = static_cast<int>((pix / W) % H);
-  const size_t b = pix / (static_cast<size_t>(W) * H);
-  float acc[8];
+  const int o8 = static_cast<int>(threadIdx.x & 7) * 8;
+  // persistent over pixels: the 11.5 KB weight tile is staged once per CTA, not once per 32 pixels
+  for (size_t pix = static_cast<size_t>(blockIdx.x) * 32 + (threadIdx.x >> 3); pix < total;
+       pix += static_cast<size_t>(gridDim.x) * 32) {
+    const int x = static_cast<int>(pix % W);
+    const int y = static_cast<int>((pix / W) % H);
+    const size_t b = pix / (static_cast<size_t>(W) * H);
+    float acc[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = sb[o8 + j];
+    for (int j = 0; j < 8; ++j) acc[j] = sb[o8 + j];
 #pragma unroll
-  for (int kh = 0; kh < 3; ++kh) {
+    for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-    for (int kw = 0; kw < 3; ++kw) {
-      const int yy = y + kh - 1, xx = x + kw - 1;
-      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-      const size_t q = (b * H + yy) * W + xx;
-      const float4 v = __ldg(reinterpret_cast<const float4*>(img4 + q * 4));
-      float in[5] = {v.x, v.y, v.z, 0.f, 0.f};
-      const size_t mq = b * mask_bstride + static_cast<size_t>(yy) * W + xx;
-      if (cin > 3) in[3] = __ldg(mask_a + mq);
-      if (cin > 4) in[4] = __ldg(mask_b + mq);
-      const float* wt = &sw[(kh * 3 + kw) * cin * 64 + o8];
-      for (int c = 0; c < cin; ++c) {
-        const float a = in[c];
-        const float4 w0 = *reinterpret_cast<const float4*>(wt + c * 64);
-        const float4 w1 = *reinterpret_cast<const float4*>(wt + c * 64 + 4);
-        acc[0] += a * w0.x; acc[1] += a * w0.y; acc[2] += a * w0.z; acc[3] += a * w0.w;
-        acc[4] += a * w1.x; acc[5] += a * w1.y; acc[6] += a * w1.z; acc[7] += a * w1.w;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int yy = y + kh - 1, xx = x + kw - 1;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        const size_t q = (b * H + yy) * W + xx;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(img4 + q * 4));
+        float in[5] = {v.x, v.y, v.z, 0.f, 0.f};
+        const size_t mq = b * mask_bstride + static_cast<size_t>(yy) * W + xx;
+        if (cin > 3) in[3] = __ldg(mask_a + mq);
+        if (cin > 4) in[4] = __ldg(mask_b + mq);
+        const float* wt = &sw[(kh * 3 + kw) * cin * 64 + o8];
+        for (int c = 0; c < cin; ++c) {
+          const float a = in[c];
+          const float4 w0 = *reinterpret_cast<const float4*>(wt + c * 64);
+          const float4 w1 = *reinterpret_cast<const float4*>(wt + c * 64 + 4);
+          acc[0] += a * w0.x; acc[1] += a * w0.y; acc[2] += a * w0.z; acc[3] += a * w0.w;
+          acc[4] += a * w1.x; acc[5] += a * w1.y; acc[6] += a * w1.z; acc[7] += a * w1.w;
+        }
       }
     }
-  }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = acc[j] > 0.f ? acc[j] : 0.2f * acc[j];
-  *reinterpret_cast<uint4*>(out + pix * 64 + o8) = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
-                                                              pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+    for (int j = 0; j < 8; ++j) acc[j] = acc[j] > 0.f ? acc[j] : 0.2f * acc[j];
+    *reinterpret_cast<uint4*>(out + pix * 64 + o8) =
+        make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                   pack_bf16x2(acc[6], acc[7]));
+  }
 }
 
 cudaError_t launch_first_conv(const float* img4, const float* mask_a, const float* mask_b, long long mask_bstride,
@@ -62,9 +64,11 @@ cudaError_t launch_first_conv(const float* img4, const float* mask_a, const floa
                               cudaStream_t s) {
   if (cin < 3 || cin > 5) return cudaErrorInvalidValue;
   if ((cin > 3 && !mask_a) || (cin > 4 && !mask_b)) return cudaErrorInvalidValue;
-  const size_t total = static_cast<size_t>(B) * H * W * 8;
-  first_conv_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(img4, mask_a, mask_b, mask_bstride, w,
-                                                                                bias, out, B, H, W, cin);
+  const size_t groups = (static_cast<size_t>(B) * H * W + 31) / 32;  // 32 pixels per CTA iteration
+  const size_t cap = 148 * 8;
+  first_conv_kernel<<<static_cast<unsigned>(groups < cap ? groups : cap), 256, 0, s>>>(img4, mask_a, mask_b,
+                                                                                       mask_bstride, w, bias, out, B,
+                                                                                       H, W, cin);
   return cudaGetLastError();
 }
 

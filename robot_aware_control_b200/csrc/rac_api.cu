@@ -82,6 +82,8 @@ struct rac_handle {
   Workspace ws;
   int tile_m = 256;        // rows per CTA tile (RAC_TILE_M=128 selects the 128-row tiles, for A/B measurements)
   int cur[3] = {0, 0, 0};  // ping-pong index of the live hidden state per LSTM stack
+  bool hidden_zero[3] = {false, false, false};  // h == 0 since init_hidden: the h_prev half of K is skipped
+  int skip_zero_hidden = 1;  // RAC_SKIP_ZERO_H=0 disables the skip (A/B measurements)
   EncodeTiledFn encode = nullptr;
   int64_t launches = 0;
   char err[512] = {0};
@@ -491,6 +493,18 @@ struct StepArgs {
   int zero_robot, dontcare;
 };
 
+// ConvLSTM stack l (two cells). Right after init_hidden h_prev is all zero, so its half of the K loop is skipped (exact).
+int launch_lstm(rac_handle* h, int l, cudaStream_t st) {
+  Workspace& w = h->ws;
+  const int p = h->cur[l];
+  ConvOp a = w.lstm[l][0][p], b = w.lstm[l][1][p];
+  if (h->hidden_zero[l] && h->skip_zero_hidden) a.g.src_dead[1] = b.g.src_dead[1] = 1;
+  CKR(launch(h, a, st));
+  CKR(launch(h, b, st));
+  h->hidden_zero[l] = false;
+  return RAC_OK;
+}
+
 // One SVGConvModel.forward (dynamics.py:544-644) + compositing / cost epilogue (trajectory_sampler.py:148-168).
 int run_step(rac_handle* h, const StepArgs& a, cudaStream_t st) {
   Workspace& w = h->ws;
@@ -525,8 +539,7 @@ int run_step(rac_handle* h, const StepArgs& a, cudaStream_t st) {
   CKR(launch(h, w.in_conv[0], st));
   {
     const int p = h->cur[0];
-    CKR(launch(h, w.lstm[0][0][p], st));
-    CKR(launch(h, w.lstm[0][1][p], st));
+    CKR(launch_lstm(h, 0, st));
     ConvOp gop = w.gauss[0][p];
     gop.e.eps = a.eps; gop.e.mu_out = a.mu_p; gop.e.logvar_out = a.logvar_p; gop.e.sample_mean = a.sample_mean;
     gop.e.seed = a.seed; gop.e.noise_ctr = a.noise_ctr; gop.e.cand_offset = a.cand_offset; gop.e.z_out = w.z;
@@ -541,8 +554,7 @@ int run_step(rac_handle* h, const StepArgs& a, cudaStream_t st) {
     }
     CKR(launch(h, w.in_conv[1], st));
     const int p = h->cur[1];
-    CKR(launch(h, w.lstm[1][0][p], st));
-    CKR(launch(h, w.lstm[1][1][p], st));
+    CKR(launch_lstm(h, 1, st));
     ConvOp gop = w.gauss[1][p];
     gop.e.eps = a.eps_post; gop.e.mu_out = a.mu; gop.e.logvar_out = a.logvar; gop.e.sample_mean = 0;
     gop.e.seed = a.seed ^ 0x9e3779b97f4a7c15ull; gop.e.noise_ctr = a.noise_ctr; gop.e.cand_offset = a.cand_offset;
@@ -553,8 +565,7 @@ int run_step(rac_handle* h, const StepArgs& a, cudaStream_t st) {
   // ---- frame predictor (dynamics.py:631-641)
   CKR(launch(h, w.in_conv[2], st));
   const int pf = h->cur[2];
-  CKR(launch(h, w.lstm[2][0][pf], st));
-  CKR(launch(h, w.lstm[2][1][pf], st));
+  CKR(launch_lstm(h, 2, st));
   h->cur[2] ^= 1;
   // ---- decoder (vgg_64.py:223-241)
   CKR(launch(h, w.dec[0][pf], st));
@@ -613,6 +624,7 @@ int rac_create(const rac_config* cfg, rac_handle** out) {
   CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   if (!fn || qres != cudaDriverEntryPointSuccess) return fail(h, RAC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
   h->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  if (const char* sz = getenv("RAC_SKIP_ZERO_H")) h->skip_zero_hidden = atoi(sz) != 0;
   if (const char* tm = getenv("RAC_TILE_M")) {
     const int v = atoi(tm);
     if (v != 128 && v != 256) return fail(h, RAC_ERR_INVALID, "RAC_TILE_M must be 128 or 256");
@@ -698,6 +710,7 @@ int rac_init_hidden(rac_handle* h, int batch, void* stream) {
       CK(cudaMemsetAsync(w.cs[l][k], 0, ne * 4, st));
     }
   h->cur[0] = h->cur[1] = h->cur[2] = 0;
+  h->hidden_zero[0] = h->hidden_zero[1] = h->hidden_zero[2] = true;
   return RAC_OK;
 }
 
