@@ -182,16 +182,29 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * Cfg::kAccCols + sub * BLOCK_N;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / CH; ++c) {
-        float v[CH];
-        if constexpr (CH == 32) tmem_ld32(t_row + c * CH, v); else tmem_ld16(t_row + c * CH, v);
+      // software pipeline over column chunks: the TMEM load (and, for the LSTM, the cell-state load) of chunk c+1 is
+      // in flight while chunk c is processed -- the epilogue is exposed when the tile uses all of TMEM
+      constexpr int kChunks = BLOCK_N / CH;
+      float v[2][CH];
+      float cprev[2][8];
+      auto issue = [&](int c, float* dst) {
+        if constexpr (CH == 32) tmem_ld32(t_row + c * CH, dst); else tmem_ld16(t_row + c * CH, dst);
+      };
+      issue(0, v[0]);
+      if constexpr (EPI == EPI_LSTM) lstm_load_c(g, e, b, y, x, valid, n_tile * BLOCK_N, cprev[0]);
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const int cur = c & 1;
         tmem_ld_wait();
+        if (c + 1 < kChunks) {
+          issue(c + 1, v[cur ^ 1]);
+          if constexpr (EPI == EPI_LSTM) lstm_load_c(g, e, b, y, x, valid, n_tile * BLOCK_N + (c + 1) * CH, cprev[cur ^ 1]);
+        }
         const int n0 = n_tile * BLOCK_N + c * CH;
-        if constexpr (EPI == EPI_ACT) epi_act<CH>(g, e, b, y, x, valid, n0, v);
-        if constexpr (EPI == EPI_LSTM) epi_lstm(g, e, b, y, x, valid, n0, v);
-        if constexpr (EPI == EPI_GAUSS) epi_gauss(g, e, b, y, x, valid, n0, v);
-        if constexpr (EPI == EPI_FRAME) epi_frame(g, e, b, y, x, valid, yb * (BLOCK_M / 32) + we, v);
+        if constexpr (EPI == EPI_ACT) epi_act<CH>(g, e, b, y, x, valid, n0, v[cur]);
+        if constexpr (EPI == EPI_LSTM) epi_lstm(g, e, b, y, x, valid, n0, v[cur], cprev[cur]);
+        if constexpr (EPI == EPI_GAUSS) epi_gauss(g, e, b, y, x, valid, n0, v[cur]);
+        if constexpr (EPI == EPI_FRAME) epi_frame(g, e, b, y, x, valid, yb * (BLOCK_M / 32) + we, v[cur]);
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
@@ -253,7 +266,11 @@ conv_simt_kernel(const ConvRaw raw, const ConvGeom g, const EpiParams e) {
     }
   }
   if constexpr (EPI == EPI_ACT) epi_act<CH>(g, e, b, y, x, valid, n0, acc);
-  if constexpr (EPI == EPI_LSTM) epi_lstm(g, e, b, y, x, valid, n0, acc);
+  if constexpr (EPI == EPI_LSTM) {
+    float cprev[8];
+    lstm_load_c(g, e, b, y, x, valid, n0, cprev);
+    epi_lstm(g, e, b, y, x, valid, n0, acc, cprev);
+  }
   if constexpr (EPI == EPI_GAUSS) epi_gauss(g, e, b, y, x, valid, n0, acc);
   if constexpr (EPI == EPI_FRAME) epi_frame(g, e, b, y, x, valid, yb * (BLOCK_M / 32) + (r >> 5), acc);
 }

@@ -40,6 +40,13 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// MUFU.TANH: max relative error 2^-11, well below the bf16 rounding (2^-9) of the hidden state it feeds
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -84,24 +91,33 @@ __device__ __forceinline__ void epi_act(const ConvGeom& g, const EpiParams& e, i
 }
 
 // ---------------------------------------------------------------- EPI_LSTM
-// columns n0 .. n0+31 = 8 channels x (in, remember, out, cell)
-__device__ __forceinline__ void epi_lstm(const ConvGeom& g, const EpiParams& e, int b, int y, int x, bool valid, int n0,
-                                         const float* acc) {
-  if (!valid || n0 + 32 > e.cout) return;
-  const int ch0 = n0 >> 2;
-  const size_t base = (static_cast<size_t>(b * g.H + y) * g.W + x) * e.hid + ch0;
-  float cprev[8];
+// columns n0 .. n0+31 = 8 channels x (in, remember, out, cell). The previous cell state of a chunk is fetched with
+// lstm_load_c one chunk ahead so that its global-load latency hides behind the gate math of the current chunk.
+__device__ __forceinline__ bool lstm_chunk_live(const EpiParams& e, bool valid, int n0) {
+  return valid && n0 + 32 <= e.cout;
+}
+__device__ __forceinline__ void lstm_load_c(const ConvGeom& g, const EpiParams& e, int b, int y, int x, bool valid,
+                                            int n0, float* cprev) {
+  if (!lstm_chunk_live(e, valid, n0)) return;
+  const size_t base = (static_cast<size_t>(b * g.H + y) * g.W + x) * e.hid + (n0 >> 2);
   *reinterpret_cast<float4*>(cprev) = *reinterpret_cast<const float4*>(e.c_state + base);
   *reinterpret_cast<float4*>(cprev + 4) = *reinterpret_cast<const float4*>(e.c_state + base + 4);
+}
+__device__ __forceinline__ void epi_lstm(const ConvGeom& g, const EpiParams& e, int b, int y, int x, bool valid, int n0,
+                                         const float* acc, const float* cprev) {
+  if (!lstm_chunk_live(e, valid, n0)) return;
+  const size_t base = (static_cast<size_t>(b * g.H + y) * g.W + x) * e.hid + (n0 >> 2);
+  const float4* bias4 = reinterpret_cast<const float4*>(e.bias + n0);
   float cn[8], hn[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const float ig = sigmoidf_(acc[4 * q + 0] + __ldg(e.bias + n0 + 4 * q + 0));
-    const float fg = sigmoidf_(acc[4 * q + 1] + __ldg(e.bias + n0 + 4 * q + 1));
-    const float og = sigmoidf_(acc[4 * q + 2] + __ldg(e.bias + n0 + 4 * q + 2));
-    const float cg = tanhf(acc[4 * q + 3] + __ldg(e.bias + n0 + 4 * q + 3));
+    const float4 bq = __ldg(bias4 + q);
+    const float ig = sigmoid_fast(acc[4 * q + 0] + bq.x);
+    const float fg = sigmoid_fast(acc[4 * q + 1] + bq.y);
+    const float og = sigmoid_fast(acc[4 * q + 2] + bq.z);
+    const float cg = tanh_fast(acc[4 * q + 3] + bq.w);
     cn[q] = fg * cprev[q] + ig * cg;
-    hn[q] = og * tanhf(cn[q]);
+    hn[q] = og * tanh_fast(cn[q]);
   }
   *reinterpret_cast<float4*>(e.c_state + base) = *reinterpret_cast<float4*>(cn);
   *reinterpret_cast<float4*>(e.c_state + base + 4) = *reinterpret_cast<float4*>(cn + 4);
