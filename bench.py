@@ -134,11 +134,13 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-def workload_config(n_gpus, world):
+def workload_config(n_gpus, world, robot_aware=False):
     n_total = 2000 if n_gpus == 1 else 16384
+    kind = ("robot-aware SVG (robot state + mask + future mask), dontcare world cost, precomputed synthetic robot "
+            "states/masks" if robot_aware else "ImgL2 planning cost")
     return {
         "workload": (f"CEM plan: {n_total} candidates x L={L_STEPS} predicted frames x {ITERS} iterations, 10% elites, "
-                     f"SVG g_dim {G_DIM} z_dim {Z_DIM} action_dim {A_DIM}, 48x64 RGB, ImgL2 planning cost"
+                     f"SVG g_dim {G_DIM} z_dim {Z_DIM} action_dim {A_DIM}, 48x64 RGB, {kind}"
                      + ("" if n_gpus == 1 else f", candidates sharded over {n_gpus} GPUs, cost all-gather (NCCL) + replicated refit")),
         "candidates": n_total, "rollout_steps": L_STEPS, "cem_iterations": ITERS, "elites": n_total // 10,
         "l2": "activation working set per plan (>9 GB) is far larger than the 126 MB L2; no explicit flush",
@@ -189,6 +191,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--candidates", type=int, default=0, help="override the candidate count (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--robot-aware", action="store_true",
+                    help="BASELINE configs[4]: model_use_robot_state + model_use_mask(+future mask), dontcare cost, "
+                         "synthetic per-candidate robot states / rectangle masks resident on the device")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -210,13 +215,31 @@ def main():
 
     n_total = args.candidates or (2000 if args.gpus == 1 else 16384)
     topk = max(1, n_total // 10)
-    cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, action_dim=A_DIM)
+    if args.robot_aware:
+        cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, action_dim=A_DIM, model_use_mask=True, model_use_future_mask=True,
+                          model_use_robot_state=True, reconstruction_loss="dontcare_l1", reward_type="dontcare")
+    else:
+        cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, action_dim=A_DIM)
     torch.manual_seed(0)
     model = SVGConvModel(cfg)
     model.load_state_dict(so.make_state_dict(cfg, 0))
     model.eval()
     policy = CEMPolicy(cfg, model, horizon=L_STEPS + 1, opt_iter=ITERS, action_candidates=n_total, topk=topk,
                        init_std=0.03, process_group=group, noise_source="philox")
+    if args.robot_aware:
+        # synthetic stand-in for robot_model.predict_batch: states ~ U(0,1), masks = one
+        # random rectangle per (step, candidate), 15-25 % coverage, float {0,1}, layout (L+1, N, 1, H, W)
+        gen = torch.Generator(device="cuda").manual_seed(5)
+        T1 = L_STEPS + 1
+        states = torch.rand(T1, n_total, 5, device=dev, generator=gen)
+        hh = torch.randint(16, 28, (T1, n_total, 1, 1, 1), device=dev, generator=gen)
+        ww = torch.randint(20, 32, (T1, n_total, 1, 1, 1), device=dev, generator=gen)
+        y0 = (torch.rand(T1, n_total, 1, 1, 1, device=dev, generator=gen) * (48 - hh)).long()
+        x0 = (torch.rand(T1, n_total, 1, 1, 1, device=dev, generator=gen) * (64 - ww)).long()
+        ys = torch.arange(48, device=dev).view(1, 1, 1, 48, 1)
+        xs = torch.arange(64, device=dev).view(1, 1, 1, 1, 64)
+        masks = ((ys >= y0) & (ys < y0 + hh) & (xs >= x0) & (xs < x0 + ww)).float().contiguous()
+        policy.precomputed_robot = (states, masks)
     start_np, goals_np, gmasks_np = scene()
     start = State(img=start_np)
     goal = DemoGoalState(imgs=goals_np, masks=gmasks_np)
@@ -291,7 +314,10 @@ def main():
     roofline = {
         "bound": "tensor",
         "kernel": "conv_tc_kernel<256, 256, EPI_LSTM> on {prior,frame_predictor}.lstm.0.gates (5x5, 1024->2048)",
-        "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak, "traffic": None,
+        "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2000 candidates, ncu --set full capture
+        # profiles/r01_lstm_gates_ncu_tile256.txt (2.133 GB + 0.289 GB); not re-measured by this run
+        "traffic": 2.42e9 if n_local == 2000 else None,
         "peak_source": peak_src, "launches_timed": int(pl.value), "avg_launch_ms": avg_ms,
         "algorithmic_flops_per_launch": flops_per_launch,
         "executed_flops_per_launch": flops_per_launch * executed_frac,
@@ -312,7 +338,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic", "config": workload_config(args.gpus, world),
+        "dtype": "bf16", "data": "synthetic", "config": workload_config(args.gpus, world, args.robot_aware),
         "plan_latency_ms": ms / args.steps,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e / args.steps},
