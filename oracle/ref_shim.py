@@ -55,6 +55,7 @@ def import_reference():
         "src.utils.image",
         "src.cem.trajectory_sampler",
         "src.cem.cem",
+        "src.prediction.trainer",
     ]
     mods = {}
     for n in names:

@@ -141,6 +141,7 @@ class SVGOracle:
         self.sd = {k: v.detach().to(torch.float32) if v.is_floating_point() else v for k, v in state_dict.items()}
         self.hidden = None
         self.trace = None  # set to {} to record intermediate activations (NCHW) for layer-by-layer GPU diagnosis
+        self.bn_training = False  # True: BatchNorm uses batch statistics and updates running stats (trainer.py:754)
 
     def _rec(self, name, t):
         if self.trace is not None:
@@ -152,7 +153,7 @@ class SVGOracle:
         sd = self.sd
         x = F.conv2d(x, sd[f"{prefix}.main.0.weight"], None, 1, 1)
         x = F.batch_norm(x, sd[f"{prefix}.main.1.running_mean"], sd[f"{prefix}.main.1.running_var"],
-                         sd[f"{prefix}.main.1.weight"], sd[f"{prefix}.main.1.bias"], False, 0.1, 1e-5)
+                         sd[f"{prefix}.main.1.weight"], sd[f"{prefix}.main.1.bias"], self.bn_training, 0.1, 1e-5)
         return F.leaky_relu(x, 0.2)
 
     # ConvEncoder.forward (vgg_64.py:122-129)
@@ -224,8 +225,12 @@ class SVGOracle:
         return v[:, :, None, None].expand(-1, -1, H_IMG // 8, W_IMG // 8)
 
     @torch.no_grad()
-    def forward(self, image, mask, robot, action, eps, next_robot=None, eps_post=None, use_posterior=False,
-                force_use_prior=False, sample_mean=False, skip=None):
+    def forward(self, *args, **kw):
+        """SVGConvModel.forward (dynamics.py:544-644) without autograd; see forward_grad for the arguments."""
+        return self.forward_grad(*args, **kw)
+
+    def forward_grad(self, image, mask, robot, action, eps, next_robot=None, eps_post=None, use_posterior=False,
+                     force_use_prior=False, sample_mean=False, skip=None):
         """SVGConvModel.forward (dynamics.py:544-644). `robot` is a tensor or an (r, r_next) tuple (:596-597).
         Returns (x_pred, skip, mu, logvar, mu_p, logvar_p)."""
         cfg, sd = self.cfg, self.sd
@@ -245,8 +250,9 @@ class SVGOracle:
         z = mu_p if sample_mean else z_p
         mu = logvar = None
         if use_posterior:
-            # dynamics.py:619 encodes `img` (the CURRENT frame) again: h_target == h in eval mode
-            h_t = h
+            # dynamics.py:619 encodes `img` (the CURRENT frame) again: same values as h; in train mode the second
+            # pass updates the BatchNorm running statistics a second time and is a second autograd path
+            h_t = self.encode(img)[0] if self.bn_training else h
             post_parts = [self._tile(next_robot)] if cfg.model_use_robot_state else []
             post_in = F.conv2d(torch.cat(post_parts + [h_t], 1), sd["posterior_input_conv.weight"],
                                sd["posterior_input_conv.bias"], 1, 1)

@@ -1,0 +1,39 @@
+"""Pins oracle/train_oracle.py (training step: BPTT loss, gradients, Adam, BatchNorm running statistics) against the
+UNMODIFIED reference trainer (tests/golden/train_*.npz from oracle/make_golden_train.py). CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import svg_oracle as so
+from oracle.make_golden import G_DIM, Z_DIM
+from oracle.make_golden_train import make_batch, summarize
+from oracle.train_oracle import TrainOracle
+
+
+@pytest.mark.parametrize("tag", ["vanilla", "ra"])
+def test_train_step_matches_reference(golden_dir, tag):
+    gold = np.load(os.path.join(golden_dir, f"train_{tag}.npz"))
+    if tag == "vanilla":
+        cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM)
+    else:
+        cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, model_use_mask=True, model_use_future_mask=True,
+                          model_use_robot_state=True, reconstruction_loss="dontcare_l1", reward_type="dontcare")
+    tr = TrainOracle(cfg, so.make_state_dict(cfg, int(gold["weight_seed"])), lr=float(gold["lr"]), beta=float(gold["beta"]))
+    batch, eps_p, eps_q = make_batch(int(gold["input_seed"]), cfg, tag == "ra")
+    for step in range(2):
+        info, grads = tr.train_step(batch, eps_p, eps_q)
+        np.testing.assert_allclose(info["recon_loss"], gold[f"recon{step}"], rtol=2e-5)
+        np.testing.assert_allclose(info["kld"], gold[f"kld{step}"], rtol=2e-4)
+        keys, gn, gs = summarize(grads)
+        assert keys == list(gold["keys"])
+        np.testing.assert_allclose(gn, gold[f"grad_norm{step}"], rtol=2e-3, atol=1e-7)
+        params = {k: tr.model.sd[k].detach() for k in tr.param_keys}
+        _, pn, ps = summarize(params)
+        np.testing.assert_allclose(pn, gold[f"param_norm{step}"], rtol=1e-5)
+        np.testing.assert_allclose(ps, gold[f"param_sample{step}"], rtol=1e-3, atol=2e-5)
+        bufs = {k: v.float() for k, v in tr.model.sd.items() if "running_" in k}
+        bkeys, bn, _ = summarize(bufs)
+        assert bkeys == list(gold["running_keys"])
+        np.testing.assert_allclose(bn, gold[f"running_norm{step}"], rtol=1e-5)
