@@ -180,6 +180,49 @@ int rac_debug_buffer(rac_handle* h, const char* name, void** ptr, int64_t* elems
 /* Number of kernels the library has launched on this handle since creation (bench.py gpu_launches). */
 int64_t rac_launch_count(const rac_handle* h);
 
+/* ---- Training step: PredictionTrainer._train_step (trainer.py:326-465), Adam from _init_models (:109-122).
+ * Parameters / BatchNorm running statistics / gradients / Adam moments are flat fp32 device buffers owned by the
+ * caller; the per-layer tables say where each convolution's tensors live in them. */
+typedef struct {
+  const long long* row_off;  /* device int64[n_packed]: params offset of packed output column n (weight row), -1 = zero */
+  const int* col_off;        /* device int32[ctot]: offset of packed input channel c inside a weight row, -1 = zero */
+  const long long* bias_off; /* device int64[n_packed]: params offset of the bias of column n, or NULL (no bias) */
+  long long gamma_off, beta_off;   /* BatchNorm affine in params, -1 if the layer has no BatchNorm */
+  long long rmean_off, rvar_off;   /* BatchNorm running statistics in buffers */
+  long long w_off;                 /* RAC_L_ENC_C1_0 only: offset of its (64, cin, 3, 3) weight */
+  int flip;                        /* 1: ConvTranspose2d weight (taps stored flipped) */
+} rac_train_layer;
+
+typedef struct {
+  int batch;                 /* B (multiple of 4) */
+  int steps;                 /* n_past + n_future - 1 predicted frames */
+  float lr, beta1, beta2, adam_eps;
+  float kl_beta;             /* cfg.beta */
+  float robot_pixel_weight;  /* cfg.robot_pixel_weight */
+  int recon_kind;            /* 0 = l1, 1 = dontcare_l1 (cfg.reconstruction_loss) */
+  int zero_robot;            /* "dontcare" in reconstruction_loss or black_robot_input */
+  long long n_params, n_buffers;
+} rac_train_config;
+
+typedef struct {
+  const float* images;     /* (steps+1, B, 3, H, W) time-first, as the reference loader (robonet_dataset.py:434-451) */
+  const float* masks;      /* (steps+1, B, 1, H, W) or NULL */
+  const float* states;     /* (steps+1, B, robot_dim) or NULL */
+  const float* actions;    /* (steps, B, action_dim) */
+  const float* eps_prior;  /* (steps, B, z_dim, H/8, W/8) or NULL -> Philox(seed) */
+  const float* eps_post;
+  unsigned long long seed;
+  float* losses;           /* out, device float[2]: sum over steps of the reconstruction loss, of the KL term */
+} rac_train_batch;
+
+int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train_layer* layers /* [RAC_L_COUNT] */,
+                     float* params, float* buffers, float* grads, float* adam_m, float* adam_v);
+int rac_train_destroy(rac_handle* h);
+/* forward (train-mode BatchNorm, posterior) + BPTT backward: fills `grads` (caller may all-reduce it) */
+int rac_train_forward_backward(rac_handle* h, const rac_train_batch* batch, void* stream);
+/* params <- Adam(params, grads) */
+int rac_train_adam_step(rac_handle* h, void* stream);
+
 /* Live timing of one kernel family for the roofline line of bench.py: CUDA event pairs are recorded on the launch
  * stream around every convolution launch whose layer name contains `name_substr` (e.g. "lstm.0"), up to
  * `max_launches`. rac_profile_end waits for the recorded events and returns their count and summed duration. */

@@ -11,9 +11,10 @@ from .losses import RobotWorldCost, ImgL2Cost, ImgDontcareCost, RobotL2Cost  # n
 from .losses import l1_criterion, dontcare_l1_criterion, kl_criterion  # noqa: F401
 from .image import zero_robot_region  # noqa: F401
 from .cem import CEMPolicy, TrajectorySampler  # noqa: F401
+from .trainer import SVGTrainer  # noqa: F401
 
 __all__ = [
     "SVGConvModel", "CEMPolicy", "TrajectorySampler", "RobotWorldCost", "ImgL2Cost", "ImgDontcareCost",
     "RobotL2Cost", "State", "DemoGoalState", "zero_robot_region", "l1_criterion", "dontcare_l1_criterion",
-    "kl_criterion", "svg_config_from",
+    "kl_criterion", "svg_config_from", "SVGTrainer",
 ]

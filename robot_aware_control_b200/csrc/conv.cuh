@@ -14,7 +14,15 @@
 
 namespace rac {
 
-enum EpiMode : int { EPI_ACT = 0, EPI_LSTM = 1, EPI_GAUSS = 2, EPI_FRAME = 3 };
+enum EpiMode : int { EPI_ACT = 0, EPI_LSTM = 1, EPI_GAUSS = 2, EPI_FRAME = 3, EPI_F32 = 4 };
+
+// One destination of the fp32 epilogue: packed columns [n_begin, n_end) of the GEMM go to dst (row-major NHWC rows,
+// `cstride` floats per row, starting at channel `coff`); accumulate: += instead of =. Bounds are multiples of 32.
+struct F32Seg {
+  int n_begin, n_end;
+  float* dst;
+  int cstride, coff, accumulate;
+};
 
 constexpr int kMaxSrc = 3;
 constexpr int kTileM = 128;
@@ -42,6 +50,11 @@ struct EpiParams {
   float* c_state;        // [B,H,W,hid] fp32, updated in place
   __nv_bfloat16* h_out;  // [B,H,W,hid]
   int hid;
+  const float* c_in;     // training: previous cell state read from here (null: c_state, in place)
+  float* gates_out;      // training: post-activation gates fp32 [B*H*W, 4*hid] in packed column order (null: not saved)
+  // EPI_F32 (training: raw pre-BatchNorm conv output, dgrad into gradient accumulators, wgrad into packed dW)
+  F32Seg seg[3];
+  int nseg;
   // EPI_GAUSS (reference lstm.py:276-286): columns are (z channel, {mu, logvar}) interleaved
   const float* eps;         // NCHW (B, z_dim, H, W) fp32 noise, or null -> Philox
   float* mu_out;            // NCHW fp32 or null

@@ -205,6 +205,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
         if constexpr (EPI == EPI_LSTM) epi_lstm(g, e, b, y, x, valid, n0, v[cur], cprev[cur]);
         if constexpr (EPI == EPI_GAUSS) epi_gauss(g, e, b, y, x, valid, n0, v[cur]);
         if constexpr (EPI == EPI_FRAME) epi_frame(g, e, b, y, x, valid, yb * (BLOCK_M / 32) + we, v[cur]);
+        if constexpr (EPI == EPI_F32) epi_f32<CH>(g, e, b, y, x, valid, n0, v[cur]);
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
@@ -273,6 +274,7 @@ conv_simt_kernel(const ConvRaw raw, const ConvGeom g, const EpiParams e) {
   }
   if constexpr (EPI == EPI_GAUSS) epi_gauss(g, e, b, y, x, valid, n0, acc);
   if constexpr (EPI == EPI_FRAME) epi_frame(g, e, b, y, x, valid, yb * (BLOCK_M / 32) + (r >> 5), acc);
+  if constexpr (EPI == EPI_F32) epi_f32<CH>(g, e, b, y, x, valid, n0, acc);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -300,6 +302,9 @@ static cudaError_t launch_simt_t(const ConvOp& op, cudaStream_t stream) {
   X(256, 256, EPI_LSTM)     \
   X(256, 128, EPI_GAUSS)    \
   X(256, 16, EPI_FRAME)     \
+  X(256, 256, EPI_F32)      \
+  X(256, 128, EPI_F32)      \
+  X(256, 64, EPI_F32)       \
   X(128, 128, EPI_ACT)      \
   X(128, 64, EPI_ACT)       \
   X(128, 128, EPI_LSTM)     \

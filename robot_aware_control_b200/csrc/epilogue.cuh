@@ -100,8 +100,9 @@ __device__ __forceinline__ void lstm_load_c(const ConvGeom& g, const EpiParams& 
                                             int n0, float* cprev) {
   if (!lstm_chunk_live(e, valid, n0)) return;
   const size_t base = (static_cast<size_t>(b * g.H + y) * g.W + x) * e.hid + (n0 >> 2);
-  *reinterpret_cast<float4*>(cprev) = *reinterpret_cast<const float4*>(e.c_state + base);
-  *reinterpret_cast<float4*>(cprev + 4) = *reinterpret_cast<const float4*>(e.c_state + base + 4);
+  const float* src = e.c_in ? e.c_in : e.c_state;
+  *reinterpret_cast<float4*>(cprev) = *reinterpret_cast<const float4*>(src + base);
+  *reinterpret_cast<float4*>(cprev + 4) = *reinterpret_cast<const float4*>(src + base + 4);
 }
 __device__ __forceinline__ void epi_lstm(const ConvGeom& g, const EpiParams& e, int b, int y, int x, bool valid, int n0,
                                          const float* acc, const float* cprev) {
@@ -109,6 +110,9 @@ __device__ __forceinline__ void epi_lstm(const ConvGeom& g, const EpiParams& e, 
   const size_t base = (static_cast<size_t>(b * g.H + y) * g.W + x) * e.hid + (n0 >> 2);
   const float4* bias4 = reinterpret_cast<const float4*>(e.bias + n0);
   float cn[8], hn[8];
+  float4* gsave = e.gates_out
+                      ? reinterpret_cast<float4*>(e.gates_out + (static_cast<size_t>(b * g.H + y) * g.W + x) * (4 * e.hid) + n0)
+                      : nullptr;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 bq = __ldg(bias4 + q);
@@ -118,11 +122,43 @@ __device__ __forceinline__ void epi_lstm(const ConvGeom& g, const EpiParams& e, 
     const float cg = tanh_fast(acc[4 * q + 3] + bq.w);
     cn[q] = fg * cprev[q] + ig * cg;
     hn[q] = og * tanh_fast(cn[q]);
+    if (gsave) gsave[q] = make_float4(ig, fg, og, cg);
   }
   *reinterpret_cast<float4*>(e.c_state + base) = *reinterpret_cast<float4*>(cn);
   *reinterpret_cast<float4*>(e.c_state + base + 4) = *reinterpret_cast<float4*>(cn + 4);
   *reinterpret_cast<uint4*>(e.h_out + base) = make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]),
                                                          pack_bf16x2(hn[4], hn[5]), pack_bf16x2(hn[6], hn[7]));
+}
+
+// ---------------------------------------------------------------- EPI_F32
+// fp32 store / accumulate of CH columns into one of up to three destinations (training path)
+template <int CH>
+__device__ __forceinline__ void epi_f32(const ConvGeom& g, const EpiParams& e, int b, int y, int x, bool valid, int n0,
+                                        const float* acc) {
+  if (!valid || n0 + CH > e.cout) return;
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    if (s >= e.nseg) break;
+    const F32Seg& sg = e.seg[s];
+    if (n0 < sg.n_begin || n0 >= sg.n_end) continue;
+    if (sg.dst == nullptr) return;
+    float* dst = sg.dst + (static_cast<size_t>(b * g.H + y) * g.W + x) * sg.cstride + sg.coff + (n0 - sg.n_begin);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int q = 0; q < CH / 4; ++q) {
+      float4 v = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+      if (e.bias) {
+        v.x += __ldg(e.bias + n0 + 4 * q); v.y += __ldg(e.bias + n0 + 4 * q + 1);
+        v.z += __ldg(e.bias + n0 + 4 * q + 2); v.w += __ldg(e.bias + n0 + 4 * q + 3);
+      }
+      if (sg.accumulate) {
+        const float4 o = d4[q];
+        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+      }
+      d4[q] = v;
+    }
+    return;
+  }
 }
 
 // ---------------------------------------------------------------- EPI_GAUSS

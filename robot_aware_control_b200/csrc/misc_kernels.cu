@@ -12,7 +12,7 @@ namespace rac {
 __global__ void __launch_bounds__(256)
 first_conv_kernel(const float* __restrict__ img4, const float* __restrict__ mask_a, const float* __restrict__ mask_b,
                   long long mask_bstride, const float* __restrict__ w, const float* __restrict__ bias,
-                  __nv_bfloat16* __restrict__ out, int B, int H, int W, int cin) {
+                  __nv_bfloat16* __restrict__ out, float* __restrict__ raw_out, int B, int H, int W, int cin) {
   __shared__ __align__(16) float sw[45 * 64];
   __shared__ float sb[64];
   for (int i = threadIdx.x; i < 9 * cin * 64; i += blockDim.x) sw[i] = w[i];
@@ -51,6 +51,11 @@ first_conv_kernel(const float* __restrict__ img4, const float* __restrict__ mask
         }
       }
     }
+    if (raw_out) {  // training: pre-BatchNorm fp32 output, activation applied later with batch statistics
+      *reinterpret_cast<float4*>(raw_out + pix * 64 + o8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(raw_out + pix * 64 + o8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = acc[j] > 0.f ? acc[j] : 0.2f * acc[j];
     *reinterpret_cast<uint4*>(out + pix * 64 + o8) =
@@ -61,14 +66,13 @@ first_conv_kernel(const float* __restrict__ img4, const float* __restrict__ mask
 
 cudaError_t launch_first_conv(const float* img4, const float* mask_a, const float* mask_b, long long mask_bstride,
                               const float* w, const float* bias, __nv_bfloat16* out, int B, int H, int W, int cin,
-                              cudaStream_t s) {
+                              cudaStream_t s, float* raw_out) {
   if (cin < 3 || cin > 5) return cudaErrorInvalidValue;
   if ((cin > 3 && !mask_a) || (cin > 4 && !mask_b)) return cudaErrorInvalidValue;
   const size_t groups = (static_cast<size_t>(B) * H * W + 31) / 32;  // 32 pixels per CTA iteration
   const size_t cap = 148 * 8;
-  first_conv_kernel<<<static_cast<unsigned>(groups < cap ? groups : cap), 256, 0, s>>>(img4, mask_a, mask_b,
-                                                                                       mask_bstride, w, bias, out, B,
-                                                                                       H, W, cin);
+  first_conv_kernel<<<static_cast<unsigned>(groups < cap ? groups : cap), 256, 0, s>>>(
+      img4, mask_a, mask_b, mask_bstride, w, bias, out, raw_out, B, H, W, cin);
   return cudaGetLastError();
 }
 

@@ -11,7 +11,7 @@ namespace rac {
 // mask planes of consecutive candidates are `mask_bstride` floats apart.
 cudaError_t launch_first_conv(const float* img4, const float* mask_a, const float* mask_b, long long mask_bstride,
                               const float* w, const float* bias, __nv_bfloat16* out, int B, int H, int W, int cin,
-                              cudaStream_t s);
+                              cudaStream_t s, float* raw_out = nullptr);
 // nn.MaxPool2d(2,2) (reference vgg_64.py:120,126-128) over a channel slice of an NHWC buffer
 cudaError_t launch_maxpool2(const __nv_bfloat16* in, int in_cstride, int in_coff, __nv_bfloat16* out, int B, int H,
                             int W, int C, cudaStream_t s);

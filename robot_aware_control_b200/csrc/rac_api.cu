@@ -92,6 +92,7 @@ struct rac_handle {
   std::vector<cudaEvent_t> prof_ev;
   size_t prof_used = 0;
   int64_t prof_dropped = 0;
+  void* train = nullptr;  // TrainState (rac_train.inc.cu)
 };
 
 namespace {
@@ -636,8 +637,11 @@ int rac_create(const rac_config* cfg, rac_handle** out) {
   return RAC_OK;
 }
 
+int rac_train_destroy(rac_handle* h);
+
 int rac_destroy(rac_handle* h) {
   if (!h) return RAC_OK;
+  rac_train_destroy(h);
   free_ws(h);
   for (cudaEvent_t ev : h->prof_ev) cudaEventDestroy(ev);
   for (int i = 0; i < RAC_L_COUNT; ++i) {
@@ -940,3 +944,5 @@ int rac_profile_end(rac_handle* h, int64_t* launches, double* total_ms) {
 }
 
 }  // extern "C"
+
+#include "rac_train.inc.cu"

@@ -1,0 +1,635 @@
+// Non-GEMM kernels of the SVG training step (see train_kernels.cuh). Batch 16 per GPU: these are small,
+// memory-bound kernels; the FLOPs of the step live in conv_tc_kernel (forward, dgrad, wgrad).
+#include "train_kernels.cuh"
+#include "epilogue.cuh"
+
+namespace rac {
+
+// ------------------------------------------------------------------------------------------------ weights
+__global__ void __launch_bounds__(256)
+pack_weights_kernel(const float* __restrict__ params, const long long* __restrict__ row_off,
+                    const int* __restrict__ col_off, int n_packed, int taps, int ctot, int flip,
+                    __nv_bfloat16* __restrict__ wp) {
+  const long long total = static_cast<long long>(n_packed) * taps * ctot;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % ctot);
+    const int tap = static_cast<int>((i / ctot) % taps);
+    const int n = static_cast<int>(i / (static_cast<long long>(ctot) * taps));
+    const long long ro = row_off[n];
+    const int co = col_off[c];
+    float v = 0.f;
+    if (ro >= 0 && co >= 0) v = params[ro + co + (flip ? taps - 1 - tap : tap)];
+    wp[i] = __float2bfloat16(v);
+  }
+}
+cudaError_t launch_pack_weights(const float* params, const long long* row_off, const int* col_off, int n_packed,
+                                int taps, int ctot, int flip, __nv_bfloat16* wp, cudaStream_t s) {
+  pack_weights_kernel<<<148 * 8, 256, 0, s>>>(params, row_off, col_off, n_packed, taps, ctot, flip, wp);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+transpose_flip_kernel(const __nv_bfloat16* __restrict__ wp, int n_packed, int taps, int ctot, int kpad,
+                      __nv_bfloat16* __restrict__ wd) {
+  const long long total = static_cast<long long>(ctot) * taps * kpad;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i % kpad);
+    const int tap = static_cast<int>((i / kpad) % taps);
+    const int c = static_cast<int>(i / (static_cast<long long>(kpad) * taps));
+    __nv_bfloat16 v = __float2bfloat16(0.f);
+    if (n < n_packed) v = wp[(static_cast<long long>(n) * taps + (taps - 1 - tap)) * ctot + c];
+    wd[i] = v;
+  }
+}
+cudaError_t launch_transpose_flip(const __nv_bfloat16* wp, int n_packed, int taps, int ctot, int kpad,
+                                  __nv_bfloat16* wd, cudaStream_t s) {
+  transpose_flip_kernel<<<148 * 8, 256, 0, s>>>(wp, n_packed, taps, ctot, kpad, wd);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+unpack_grads_kernel(const float* __restrict__ dwp, const long long* __restrict__ row_off,
+                    const int* __restrict__ col_off, int n_packed, int taps, int ctot, int flip,
+                    float* __restrict__ grads) {
+  const long long total = static_cast<long long>(n_packed) * taps * ctot;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % ctot);
+    const int tap = static_cast<int>((i / ctot) % taps);
+    const int n = static_cast<int>(i / (static_cast<long long>(ctot) * taps));
+    const long long ro = row_off[n];
+    const int co = col_off[c];
+    if (ro >= 0 && co >= 0) grads[ro + co + (flip ? taps - 1 - tap : tap)] = dwp[i];
+  }
+}
+cudaError_t launch_unpack_grads(const float* dwp, const long long* row_off, const int* col_off, int n_packed, int taps,
+                                int ctot, int flip, float* grads, cudaStream_t s) {
+  unpack_grads_kernel<<<148 * 8, 256, 0, s>>>(dwp, row_off, col_off, n_packed, taps, ctot, flip, grads);
+  return cudaGetLastError();
+}
+
+__global__ void pack_first_kernel(const float* __restrict__ w, int cin, float* __restrict__ wf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (tap, c, o)
+  if (i >= 9 * cin * 64) return;
+  const int o = i & 63;
+  const int c = (i >> 6) % cin;
+  const int tap = (i >> 6) / cin;
+  wf[i] = w[(o * cin + c) * 9 + tap];
+}
+cudaError_t launch_pack_first(const float* w, int cin, float* wf, cudaStream_t s) {
+  pack_first_kernel<<<(9 * cin * 64 + 255) / 256, 256, 0, s>>>(w, cin, wf);
+  return cudaGetLastError();
+}
+
+// dW[o][c][tap] += sum_pix in[pix][tap, c] * draw[pix][o]
+__global__ void __launch_bounds__(256)
+first_wgrad_kernel(const float* __restrict__ img4, const float* __restrict__ mask_a, const float* __restrict__ mask_b,
+                   long long mask_bstride, const float* __restrict__ draw, float* __restrict__ gw, int B, int H, int W,
+                   int cin) {
+  __shared__ float sin_[64][46];
+  __shared__ float sdr[64][65];
+  const size_t total = static_cast<size_t>(B) * H * W;
+  const size_t p0 = static_cast<size_t>(blockIdx.x) * 64;
+  const int K = 9 * cin;
+  for (int i = threadIdx.x; i < 64 * K; i += blockDim.x) {
+    const int px = i / K, k = i - px * K;
+    const size_t pix = p0 + px;
+    float v = 0.f;
+    if (pix < total) {
+      const int tap = k / cin, c = k - tap * cin;
+      const int x = static_cast<int>(pix % W), y = static_cast<int>((pix / W) % H);
+      const size_t b = pix / (static_cast<size_t>(W) * H);
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        if (c < 3) v = img4[((b * H + yy) * W + xx) * 4 + c];
+        else if (c == 3) v = mask_a[b * mask_bstride + static_cast<size_t>(yy) * W + xx];
+        else v = mask_b[b * mask_bstride + static_cast<size_t>(yy) * W + xx];
+      }
+    }
+    sin_[px][k] = v;
+  }
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+    const int px = i >> 6, o = i & 63;
+    const size_t pix = p0 + px;
+    sdr[px][o] = pix < total ? draw[pix * 64 + o] : 0.f;
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < K * 64; p += blockDim.x) {
+    const int k = p >> 6, o = p & 63;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int px = 0; px < 64; ++px) acc += sin_[px][k] * sdr[px][o];
+    const int tap = k / cin, c = k - tap * cin;
+    atomicAdd(&gw[(o * cin + c) * 9 + tap], acc);
+  }
+}
+cudaError_t launch_first_wgrad(const float* img4, const float* mask_a, const float* mask_b, long long mask_bstride,
+                               const float* draw, float* gw, int B, int H, int W, int cin, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(B) * H * W;
+  first_wgrad_kernel<<<static_cast<unsigned>((total + 63) / 64), 256, 0, s>>>(img4, mask_a, mask_b, mask_bstride, draw,
+                                                                              gw, B, H, W, cin);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ BatchNorm
+// block (32 channels, 32 row lanes); per-channel reduction over all M rows in fp64
+template <typename F>
+__device__ __forceinline__ void column_reduce2(int M, int C, F load, double& s1, double& s2) {
+  __shared__ double sh1[32][33], sh2[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    for (int m = threadIdx.y; m < M; m += 32) {
+      float v1, v2;
+      load(m, c, v1, v2);
+      a += v1;
+      b += v2;
+    }
+  }
+  sh1[threadIdx.y][threadIdx.x] = a;
+  sh2[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  s1 = s2 = 0.0;
+  if (threadIdx.y == 0) {
+    for (int i = 0; i < 32; ++i) {
+      s1 += sh1[i][threadIdx.x];
+      s2 += sh2[i][threadIdx.x];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+bn_stats_kernel(const float* __restrict__ raw, int M, int C, float* __restrict__ mean, float* __restrict__ rstd,
+                float* __restrict__ rmean, float* __restrict__ rvar, int updates) {
+  double s1, s2;
+  column_reduce2(M, C, [&](int m, int c, float& v1, float& v2) {
+    const float x = raw[static_cast<size_t>(m) * C + c];
+    v1 = x;
+    v2 = x * x;
+  }, s1, s2);
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  if (threadIdx.y == 0 && c < C) {
+    const double mu = s1 / M;
+    double var = s2 / M - mu * mu;
+    if (var < 0.0) var = 0.0;
+    mean[c] = static_cast<float>(mu);
+    rstd[c] = static_cast<float>(1.0 / sqrt(var + 1e-5));
+    const double unbiased = var * M / (M - 1);
+    float rm = rmean[c], rv = rvar[c];
+    for (int u = 0; u < updates; ++u) {  // reference: momentum 0.1, the encoder runs twice per step (dynamics.py:619)
+      rm = 0.9f * rm + 0.1f * static_cast<float>(mu);
+      rv = 0.9f * rv + 0.1f * static_cast<float>(unbiased);
+    }
+    rmean[c] = rm;
+    rvar[c] = rv;
+  }
+}
+cudaError_t launch_bn_stats(const float* raw, int M, int C, float* mean, float* rstd, float* running_mean,
+                            float* running_var, int updates, cudaStream_t s) {
+  bn_stats_kernel<<<(C + 31) / 32, dim3(32, 32), 0, s>>>(raw, M, C, mean, rstd, running_mean, running_var, updates);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+bn_act_kernel(const float* __restrict__ raw, const float* __restrict__ mean, const float* __restrict__ rstd,
+              const float* __restrict__ gamma, const float* __restrict__ beta, int B, int H, int W, int C,
+              __nv_bfloat16* __restrict__ out, int cstride, int coff, int upsample) {
+  const int C8 = C / 8;
+  const size_t total = static_cast<size_t>(B) * H * W * C8;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c0 = static_cast<int>(i % C8) * 8;
+  const size_t m = i / C8;
+  const int x = static_cast<int>(m % W), y = static_cast<int>((m / W) % H);
+  const size_t b = m / (static_cast<size_t>(W) * H);
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    float t = (raw[m * C + c] - mean[c]) * rstd[c] * gamma[c] + beta[c];
+    v[j] = t > 0.f ? t : 0.2f * t;
+  }
+  const uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                              pack_bf16x2(v[6], v[7]));
+  if (!upsample) {
+    *reinterpret_cast<uint4*>(out + m * cstride + coff + c0) = pk;
+  } else {
+    for (int dy = 0; dy < 2; ++dy)
+      for (int dx = 0; dx < 2; ++dx)
+        *reinterpret_cast<uint4*>(out + ((b * 2 * H + 2 * y + dy) * (2 * W) + 2 * x + dx) * cstride + coff + c0) = pk;
+  }
+}
+cudaError_t launch_bn_act(const float* raw, const float* mean, const float* rstd, const float* gamma,
+                          const float* beta, int B, int H, int W, int C, __nv_bfloat16* out, int cstride, int coff,
+                          int upsample, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(B) * H * W * (C / 8);
+  bn_act_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(raw, mean, rstd, gamma, beta, B, H, W, C,
+                                                                           out, cstride, coff, upsample);
+  return cudaGetLastError();
+}
+
+struct BnBwdArgs {
+  const float* dy;
+  int dy_cstride, dy_coff, upsample;
+  const float* raw;
+  const float* mean;
+  const float* rstd;
+  const float* gamma;
+  const float* beta;
+  int H, W, C;
+};
+// gradient w.r.t. the BN output after the LeakyReLU derivative, and the normalised activation
+__device__ __forceinline__ void bn_bwd_point(const BnBwdArgs& a, int m, int c, float& dz, float& xhat) {
+  const int x = m % a.W, y = (m / a.W) % a.H;
+  const size_t b = static_cast<size_t>(m) / (a.W * a.H);
+  float g;
+  if (!a.upsample) {
+    g = a.dy[static_cast<size_t>(m) * a.dy_cstride + a.dy_coff + c];
+  } else {
+    g = 0.f;
+    for (int dy = 0; dy < 2; ++dy)
+      for (int dx = 0; dx < 2; ++dx)
+        g += a.dy[((b * 2 * a.H + 2 * y + dy) * (2 * a.W) + 2 * x + dx) * a.dy_cstride + a.dy_coff + c];
+  }
+  xhat = (a.raw[static_cast<size_t>(m) * a.C + c] - a.mean[c]) * a.rstd[c];
+  const float bn = xhat * a.gamma[c] + a.beta[c];
+  dz = bn > 0.f ? g : 0.2f * g;
+}
+__global__ void __launch_bounds__(1024)
+bn_bwd_reduce_kernel(BnBwdArgs a, int M, float* __restrict__ scratch, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta) {
+  double s1, s2;
+  column_reduce2(M, a.C, [&](int m, int c, float& v1, float& v2) {
+    float dz, xh;
+    bn_bwd_point(a, m, c, dz, xh);
+    v1 = dz;
+    v2 = dz * xh;
+  }, s1, s2);
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  if (threadIdx.y == 0 && c < a.C) {
+    scratch[c] = static_cast<float>(s1);
+    scratch[a.C + c] = static_cast<float>(s2);
+    dbeta[c] += static_cast<float>(s1);
+    dgamma[c] += static_cast<float>(s2);
+  }
+}
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(BnBwdArgs a, int M, const float* __restrict__ scratch, __nv_bfloat16* __restrict__ draw,
+                    float* __restrict__ draw32) {
+  const size_t total = static_cast<size_t>(M) * a.C;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % a.C);
+  const int m = static_cast<int>(i / a.C);
+  float dz, xh;
+  bn_bwd_point(a, m, c, dz, xh);
+  const float inv = 1.f / M;
+  const float dx = a.gamma[c] * a.rstd[c] * (dz - scratch[c] * inv - xh * scratch[a.C + c] * inv);
+  draw[i] = __float2bfloat16(dx);
+  if (draw32) draw32[i] = dx;
+}
+cudaError_t launch_bn_bwd(const float* dy, int dy_cstride, int dy_coff, int upsample, const float* raw,
+                          const float* mean, const float* rstd, const float* gamma, const float* beta, int B, int H,
+                          int W, int C, float* scratch, __nv_bfloat16* draw, float* draw_f32_or_null, float* dgamma,
+                          float* dbeta, cudaStream_t s) {
+  BnBwdArgs a{dy, dy_cstride, dy_coff, upsample, raw, mean, rstd, gamma, beta, H, W, C};
+  const int M = B * H * W;
+  bn_bwd_reduce_kernel<<<(C + 31) / 32, dim3(32, 32), 0, s>>>(a, M, scratch, dgamma, dbeta);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const size_t total = static_cast<size_t>(M) * C;
+  bn_bwd_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(a, M, scratch, draw, draw_f32_or_null);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ LSTM cell
+__global__ void __launch_bounds__(256)
+lstm_bwd_kernel(const float* __restrict__ dh, float* __restrict__ dc, const float* __restrict__ gates,
+                const float* __restrict__ c_prev, const float* __restrict__ c_new, size_t total,
+                __nv_bfloat16* __restrict__ dgates) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // (m, channel)
+  if (i >= total) return;
+  const float4 gt = reinterpret_cast<const float4*>(gates)[i];  // i, f, o, g (post-activation)
+  const float cp = c_prev ? c_prev[i] : 0.f;
+  const float tc = tanh_fast(c_new[i]);  // same function as the forward epilogue
+  const float dhv = dh[i];
+  const float dcv = dc[i] + dhv * gt.z * (1.f - tc * tc);
+  const float d_o = dhv * tc;
+  const float di = dcv * gt.w, dg = dcv * gt.x, df = dcv * cp;
+  dc[i] = dcv * gt.y;
+  const float pi = di * gt.x * (1.f - gt.x), pf = df * gt.y * (1.f - gt.y), po = d_o * gt.z * (1.f - gt.z);
+  const float pg = dg * (1.f - gt.w * gt.w);
+  reinterpret_cast<uint2*>(dgates)[i] = make_uint2(pack_bf16x2(pi, pf), pack_bf16x2(po, pg));
+}
+cudaError_t launch_lstm_bwd(const float* dh, float* dc, const float* gates, const float* c_prev_or_null,
+                            const float* c_new, int M, int hid, __nv_bfloat16* dgates, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(M) * hid;
+  lstm_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(dh, dc, gates, c_prev_or_null, c_new,
+                                                                             total, dgates);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(1024)
+bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, int M, int ncols, int nvalid,
+                 const long long* __restrict__ bias_off, float* __restrict__ grads) {
+  double s1, s2;
+  column_reduce2(M, nvalid, [&](int m, int c, float& v1, float& v2) {
+    v1 = __bfloat162float(dy[static_cast<size_t>(m) * ncols + c]);
+    v2 = 0.f;
+  }, s1, s2);
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  if (threadIdx.y == 0 && c < nvalid && bias_off[c] >= 0) grads[bias_off[c]] += static_cast<float>(s1);
+}
+cudaError_t launch_bias_grad(const __nv_bfloat16* dy, int M, int ncols, int nvalid, const long long* bias_off,
+                             float* grads, cudaStream_t s) {
+  bias_grad_kernel<<<(nvalid + 31) / 32, dim3(32, 32), 0, s>>>(dy, M, ncols, nvalid, bias_off, grads);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ z / KL
+__global__ void __launch_bounds__(256)
+gauss_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ mu, const float* __restrict__ lv,
+                 const float* __restrict__ eps, const float* __restrict__ mu_p, const float* __restrict__ lv_p, int B,
+                 int z_dim, int hw, float klw, int bs, __nv_bfloat16* __restrict__ dpost,
+                 __nv_bfloat16* __restrict__ dprior) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // (m, zc in 0..63)
+  const size_t total = static_cast<size_t>(B) * hw * 64;
+  if (i >= total) return;
+  const int zc = static_cast<int>(i & 63);
+  const size_t m = i >> 6;
+  float a0 = 0.f, a1 = 0.f, p0 = 0.f, p1 = 0.f;
+  if (zc < z_dim) {
+    const size_t b = m / hw;
+    const int pos = static_cast<int>(m % hw);
+    const size_t q = (b * z_dim + zc) * hw + pos;
+    const float m1 = mu[q], l1 = lv[q], m2 = mu_p[q], l2 = lv_p[q], e = eps[q];
+    const float g = dz ? dz[m * 64 + zc] : 0.f;
+    const float inv2 = expf(-l2), e1 = expf(l1), d = m1 - m2;
+    const float s = klw / bs;
+    a0 = g + s * d * inv2;                                   // d/d mu (posterior)
+    a1 = g * e * 0.5f * expf(0.5f * l1) + s * (-0.5f + 0.5f * e1 * inv2);  // d/d logvar (posterior)
+    p0 = -s * d * inv2;                                      // d/d mu_p (prior)
+    p1 = s * (0.5f - 0.5f * (e1 + d * d) * inv2);            // d/d logvar_p (prior)
+  }
+  reinterpret_cast<uint32_t*>(dpost)[i] = pack_bf16x2(a0, a1);
+  reinterpret_cast<uint32_t*>(dprior)[i] = pack_bf16x2(p0, p1);
+}
+cudaError_t launch_gauss_bwd(const float* dz, const float* mu, const float* lv, const float* eps, const float* mu_p,
+                             const float* lv_p, int B, int z_dim, int hw, float kl_weight, int bs,
+                             __nv_bfloat16* dpost, __nv_bfloat16* dprior, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(B) * hw * 64;
+  gauss_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(dz, mu, lv, eps, mu_p, lv_p, B, z_dim, hw,
+                                                                              kl_weight, bs, dpost, dprior);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ frame loss
+__global__ void __launch_bounds__(1024)
+frame_loss_kernel(const float* __restrict__ x4, const float* __restrict__ xj, const float* __restrict__ xi,
+                  const float* __restrict__ mask, int kind, float rw, int B, int HW, float* __restrict__ loss_out,
+                  __nv_bfloat16* __restrict__ dlogit) {
+  __shared__ double sh[32];
+  __shared__ float s_scale;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto block_sum = [&](double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < 32; ++i) t += sh[i];
+    return t;
+  };
+  if (kind == 1) {
+    double cnt = 0.0;
+    for (int p = tid; p < HW; p += blockDim.x) cnt += mask[static_cast<size_t>(b) * HW + p] != 0.f ? 0.0 : 3.0;
+    cnt = block_sum(cnt);
+    if (tid == 0) s_scale = static_cast<float>(1.0 / ((cnt + 1.0) * B));
+  } else {
+    if (tid == 0) s_scale = 1.f / (static_cast<float>(B) * 3.f * HW);
+  }
+  __syncthreads();
+  const float scale = s_scale;
+  double acc = 0.0;
+  for (int p = tid; p < HW; p += blockDim.x) {
+    const float mh = x4[(static_cast<size_t>(b) * 4 + 3) * HW + p];
+    const bool robot = kind == 1 && mask[static_cast<size_t>(b) * HW + p] != 0.f;
+    const float w = robot ? rw : 1.f;
+    float dm = 0.f, dl[4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float xh = x4[(static_cast<size_t>(b) * 4 + c) * HW + p];
+      const float j = xj[(static_cast<size_t>(b) * 3 + c) * HW + p];
+      const float t = xi[(static_cast<size_t>(b) * 3 + c) * HW + p];
+      const float pr = (1.f - mh) * j + mh * xh;  // blends with the un-blacked x_j (trainer.py:406-407)
+      const float diff = (t - pr) * w;
+      acc += fabsf(diff);
+      const float sg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+      const float dp = -sg * w * scale;           // dL / d pred
+      dm += dp * (xh - j);
+      dl[c] = dp * mh * xh * (1.f - xh);
+    }
+    dl[3] = dm * mh * (1.f - mh);
+    uint4* d = reinterpret_cast<uint4*>(dlogit + (static_cast<size_t>(b) * HW + p) * 64);
+    d[0] = make_uint4(pack_bf16x2(dl[0], dl[1]), pack_bf16x2(dl[2], dl[3]), 0u, 0u);
+#pragma unroll
+    for (int q = 1; q < 8; ++q) d[q] = make_uint4(0u, 0u, 0u, 0u);  // the operand is 64 channels wide, 4 are real
+  }
+  acc = block_sum(acc);
+  if (tid == 0) loss_out[b] = static_cast<float>(acc * scale);
+}
+cudaError_t launch_frame_loss(const float* x4, const float* xj, const float* xi, const float* mask, int kind,
+                              float robot_weight, int B, int HW, float* loss_out, __nv_bfloat16* dlogit,
+                              cudaStream_t s) {
+  if (kind == 1 && !mask) return cudaErrorInvalidValue;
+  frame_loss_kernel<<<B, 1024, 0, s>>>(x4, xj, xi, mask, kind, robot_weight, B, HW, loss_out, dlogit);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ max pool backward
+__global__ void __launch_bounds__(256)
+pool_bwd_kernel(const __nv_bfloat16* __restrict__ in, int in_cstride, int in_coff, const float* __restrict__ dout,
+                int B, int H, int W, int C, float* __restrict__ din, int din_cstride, int din_coff, int accumulate) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = static_cast<size_t>(B) * Ho * Wo * C;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % C);
+  const int xo = static_cast<int>((i / C) % Wo);
+  const int yo = static_cast<int>((i / (static_cast<size_t>(C) * Wo)) % Ho);
+  const size_t b = i / (static_cast<size_t>(C) * Wo * Ho);
+  size_t pos[4];
+  float v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    pos[k] = (b * H + 2 * yo + (k >> 1)) * W + 2 * xo + (k & 1);
+    v[k] = __bfloat162float(in[pos[k] * in_cstride + in_coff + c]);
+  }
+  int best = 0;
+#pragma unroll
+  for (int k = 1; k < 4; ++k)
+    if (v[k] > v[best]) best = k;  // first maximum in scan order
+  const float g = dout[i];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float* d = din + pos[k] * din_cstride + din_coff + c;
+    if (accumulate) {
+      if (k == best) *d += g;
+    } else {
+      *d = (k == best) ? g : 0.f;
+    }
+  }
+}
+cudaError_t launch_pool_bwd(const __nv_bfloat16* in, int in_cstride, int in_coff, const float* dout, int B, int H,
+                            int W, int C, float* din, int din_cstride, int din_coff, int accumulate, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(B) * (H / 2) * (W / 2) * C;
+  pool_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, in_cstride, in_coff, dout, B, H, W, C,
+                                                                             din, din_cstride, din_coff, accumulate);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ layout helpers
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, long long n,
+                                                        __nv_bfloat16* __restrict__ dst) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16(src[i]);
+}
+cudaError_t launch_cast_bf16(const float* src, long long n, __nv_bfloat16* dst, cudaStream_t s) {
+  cast_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(src, n, dst);
+  return cudaGetLastError();
+}
+
+// dst[c][m] = src[m][c], zero padded to [rows_pad][mpad]
+__global__ void __launch_bounds__(1024)
+transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int M, int C, int mpad, int rows_pad,
+                      __nv_bfloat16* __restrict__ dst) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int m = m0 + threadIdx.y, c = c0 + threadIdx.x;
+  tile[threadIdx.y][threadIdx.x] = (m < M && c < C) ? src[static_cast<size_t>(m) * C + c] : __float2bfloat16(0.f);
+  __syncthreads();
+  const int co = c0 + threadIdx.y, mo = m0 + threadIdx.x;
+  if (co < rows_pad && mo < mpad) dst[static_cast<size_t>(co) * mpad + mo] = tile[threadIdx.x][threadIdx.y];
+}
+cudaError_t launch_transpose_bf16(const __nv_bfloat16* src, int M, int C, int mpad, int rows_pad,
+                                  __nv_bfloat16* dst, cudaStream_t s) {
+  transpose_bf16_kernel<<<dim3((mpad + 31) / 32, (rows_pad + 31) / 32), dim3(32, 32), 0, s>>>(src, M, C, mpad, rows_pad,
+                                                                                              dst);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(1024)
+im2col_t_kernel(const __nv_bfloat16* __restrict__ src, int B, int H, int W, int C, int ks, int ctot, int coff,
+                int mpad, __nv_bfloat16* __restrict__ dst) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int M = B * H * W;
+  const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 32, tap = blockIdx.z;
+  const int dy = tap / ks - ks / 2, dx = tap % ks - ks / 2;
+  const int m = m0 + threadIdx.y, c = c0 + threadIdx.x;
+  __nv_bfloat16 v = __float2bfloat16(0.f);
+  if (m < M && c < C) {
+    const int x = m % W, y = (m / W) % H, b = m / (W * H);
+    const int yy = y + dy, xx = x + dx;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = src[(static_cast<size_t>(b * H + yy) * W + xx) * C + c];
+  }
+  tile[threadIdx.y][threadIdx.x] = v;
+  __syncthreads();
+  const int co = c0 + threadIdx.y, mo = m0 + threadIdx.x;
+  if (co < C && mo < mpad)
+    dst[(static_cast<size_t>(tap) * ctot + coff + co) * mpad + mo] = tile[threadIdx.x][threadIdx.y];
+}
+cudaError_t launch_im2col_t(const __nv_bfloat16* src, int B, int H, int W, int C, int ks, int ctot, int coff, int mpad,
+                            __nv_bfloat16* dst, cudaStream_t s) {
+  im2col_t_kernel<<<dim3((mpad + 31) / 32, (C + 31) / 32, ks * ks), dim3(32, 32), 0, s>>>(src, B, H, W, C, ks, ctot,
+                                                                                          coff, mpad, dst);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ optimiser, noise
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  p[i] -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+}
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
+                        float eps, int t, cudaStream_t s) {
+  const float bc1 = 1.f - powf(b1, static_cast<float>(t));
+  const float bc2 = sqrtf(1.f - powf(b2, static_cast<float>(t)));
+  adam_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+normal_fill_kernel(float* __restrict__ dst, long long n, unsigned long long seed, unsigned int ctr) {
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // 4 values per thread
+  if (q * 4 >= n) return;
+  const Philox4 r = philox4x32_10(static_cast<uint32_t>(q), static_cast<uint32_t>(q >> 32), ctr, 0x7a1u,
+                                  static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  float z[4];
+  box_muller(r.v[0], r.v[1], z[0], z[1]);
+  box_muller(r.v[2], r.v[3], z[2], z[3]);
+  for (int k = 0; k < 4 && q * 4 + k < n; ++k) dst[q * 4 + k] = z[k];
+}
+cudaError_t launch_normal_fill(float* dst, long long n, unsigned long long seed, unsigned int ctr, cudaStream_t s) {
+  const long long quads = (n + 3) / 4;
+  normal_fill_kernel<<<static_cast<unsigned>((quads + 255) / 256), 256, 0, s>>>(dst, n, seed, ctr);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) sum_f32_kernel(const float* __restrict__ src, int n, float* __restrict__ dst) {
+  __shared__ double sh[8];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) a += src[i];
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    dst[0] += static_cast<float>(t);
+  }
+}
+cudaError_t launch_sum_f32(const float* src, int n, float* dst_accum, cudaStream_t s) {
+  sum_f32_kernel<<<1, 256, 0, s>>>(src, n, dst_accum);
+  return cudaGetLastError();
+}
+
+__global__ void gather_f32_kernel(const float* __restrict__ params, const long long* __restrict__ off, int n,
+                                  float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = off[i] >= 0 ? params[off[i]] : 0.f;
+}
+cudaError_t launch_gather_f32(const float* params, const long long* off, int n, float* dst, cudaStream_t s) {
+  gather_f32_kernel<<<(n + 255) / 256, 256, 0, s>>>(params, off, n, dst);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+img_prep_train_kernel(const float* __restrict__ img, const float* __restrict__ mask, float* __restrict__ img4, int B,
+                      int HW) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(B) * HW) return;
+  const size_t b = i / HW;
+  const int pos = static_cast<int>(i % HW);
+  const float* p = img + b * 3 * HW + pos;
+  float r = p[0], g = p[HW], bl = p[2 * HW];
+  if (mask && mask[i] != 0.f) r = g = bl = 0.f;
+  *reinterpret_cast<float4*>(img4 + i * 4) = make_float4(r, g, bl, 0.f);
+}
+cudaError_t launch_img_prep_train(const float* img_nchw, const float* mask, float* img4, int B, int HW, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(B) * HW;
+  img_prep_train_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(img_nchw, mask, img4, B, HW);
+  return cudaGetLastError();
+}
+
+}  // namespace rac

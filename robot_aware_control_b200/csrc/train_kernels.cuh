@@ -1,0 +1,86 @@
+// Launchers of the non-GEMM kernels of the SVG training step (train_kernels.cu). The GEMM-shaped work of the
+// backward pass (dgrad, wgrad) reuses conv_tc_kernel with the fp32 segmented epilogue (EPI_F32).
+// Reference: PredictionTrainer._train_step (src/prediction/trainer.py:326-465), losses.py:13-50,97-106,
+// vgg_layer in train mode (vgg_64.py:8-18), ConvLSTMCell (lstm.py:129-149), reparameterize (lstm.py:276-279).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace rac {
+
+// ---- weights: fp32 master (flat) <-> packed bf16 GEMM operands
+// Wp[n][tap][c] = params[row_off[n] + col_off[c] + (flip ? taps-1-tap : tap)]  (0 where an offset is negative)
+cudaError_t launch_pack_weights(const float* params, const long long* row_off, const int* col_off, int n_packed,
+                                int taps, int ctot, int flip, __nv_bfloat16* wp, cudaStream_t s);
+// dgrad operand: Wd[c][tap][n] = Wp[n][taps-1-tap][c], n padded with zeros to kpad
+cudaError_t launch_transpose_flip(const __nv_bfloat16* wp, int n_packed, int taps, int ctot, int kpad,
+                                  __nv_bfloat16* wd, cudaStream_t s);
+// grads[row_off[n] + col_off[c] + tap'] = dWp[n][tap][c]
+cudaError_t launch_unpack_grads(const float* dwp, const long long* row_off, const int* col_off, int n_packed, int taps,
+                                int ctot, int flip, float* grads, cudaStream_t s);
+// first layer (encoder.c1.0): master w[64][cin][3][3] <-> fp32 [9*cin][64]
+cudaError_t launch_pack_first(const float* w, int cin, float* wf, cudaStream_t s);
+cudaError_t launch_first_wgrad(const float* img4, const float* mask_a, const float* mask_b, long long mask_bstride,
+                               const float* draw /* [pix][64] fp32 */, float* gw /* master layout, += */, int B,
+                               int H, int W, int cin, cudaStream_t s);
+
+// ---- BatchNorm (train mode) + LeakyReLU(0.2)
+// raw: [M, C] fp32 (pre-BN conv output). mean / rstd: [C]. running stats updated `updates` times (momentum 0.1).
+cudaError_t launch_bn_stats(const float* raw, int M, int C, float* mean, float* rstd, float* running_mean,
+                            float* running_var, int updates, cudaStream_t s);
+cudaError_t launch_bn_act(const float* raw, const float* mean, const float* rstd, const float* gamma,
+                          const float* beta, int B, int H, int W, int C, __nv_bfloat16* out, int cstride, int coff,
+                          int upsample, cudaStream_t s);
+// dy: gradient w.r.t. the layer output, fp32 rows of `dy_cstride` floats starting at channel dy_coff; with
+// upsample=1 it lives on the 2H x 2W grid and the four replicated positions are summed.
+// Produces draw [M, C] bf16 (gradient w.r.t. the raw conv output) and accumulates dgamma / dbeta.
+cudaError_t launch_bn_bwd(const float* dy, int dy_cstride, int dy_coff, int upsample, const float* raw,
+                          const float* mean, const float* rstd, const float* gamma, const float* beta, int B, int H,
+                          int W, int C, float* scratch /* [2*C] */, __nv_bfloat16* draw, float* draw_f32_or_null,
+                          float* dgamma, float* dbeta, cudaStream_t s);
+
+// ---- ConvLSTM cell backward (elementwise). gates: saved post-activation (i,f,o,g) interleaved [M, 4*hid];
+// dgates: bf16 [M, 4*hid] w.r.t. the gate pre-activations; dc is updated in place (dc_next -> dc_prev).
+cudaError_t launch_lstm_bwd(const float* dh, float* dc, const float* gates, const float* c_prev_or_null,
+                            const float* c_new, int M, int hid, __nv_bfloat16* dgates, cudaStream_t s);
+// grads[bias_off[n]] += sum_m dy[m][n] for n < nvalid   (dy bf16 [M, ncols])
+cudaError_t launch_bias_grad(const __nv_bfloat16* dy, int M, int ncols, int nvalid, const long long* bias_off,
+                             float* grads, cudaStream_t s);
+
+// ---- reparameterisation + KL backward. dz: fp32 [M, 64] (gradient w.r.t. z from the frame predictor input conv).
+// mu/lv/eps tensors are NCHW (B, z, hw). Outputs bf16 [M, 128] interleaved (z channel, {mu, logvar}).
+cudaError_t launch_gauss_bwd(const float* dz, const float* mu, const float* lv, const float* eps, const float* mu_p,
+                             const float* lv_p, int B, int z_dim, int hw, float kl_weight, int bs,
+                             __nv_bfloat16* dpost, __nv_bfloat16* dprior, cudaStream_t s);
+
+// ---- frame loss (forward value + gradient w.r.t. the pre-sigmoid decoder output)
+// x4: (B,4,H,W) sigmoid outputs; xj, xi: (B,3,H,W); mask: (B,1,H,W) or null. kind 0 = l1, 1 = dontcare_l1.
+// loss_out[b] = per-sample contribution (already scaled so that the step loss is sum_b loss_out[b]).
+cudaError_t launch_frame_loss(const float* x4, const float* xj, const float* xi, const float* mask, int kind,
+                              float robot_weight, int B, int HW, float* loss_out, __nv_bfloat16* dlogit /* [B*HW, 64] */,
+                              cudaStream_t s);
+
+// ---- 2x2 max-pool backward (first maximum in scan order, as torch): din (+)= route(dout)
+cudaError_t launch_pool_bwd(const __nv_bfloat16* in, int in_cstride, int in_coff, const float* dout, int B, int H,
+                            int W, int C, float* din, int din_cstride, int din_coff, int accumulate, cudaStream_t s);
+
+// ---- layout helpers for wgrad: transposed operands (contraction dimension = rows m, padded to mpad)
+cudaError_t launch_cast_bf16(const float* src, long long n, __nv_bfloat16* dst, cudaStream_t s);
+cudaError_t launch_transpose_bf16(const __nv_bfloat16* src /* [M, C] */, int M, int C, int mpad, int rows_pad,
+                                  __nv_bfloat16* dst /* [rows_pad, mpad] */, cudaStream_t s);
+// dst[(tap * ctot + coff + c) * mpad + m] = src[b, y + dy, x + dx, c]  (0 outside the image)
+cudaError_t launch_im2col_t(const __nv_bfloat16* src, int B, int H, int W, int C, int ks, int ctot, int coff, int mpad,
+                            __nv_bfloat16* dst, cudaStream_t s);
+
+// ---- optimiser (torch.optim.Adam, no weight decay) and noise
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
+                        float eps, int t, cudaStream_t s);
+cudaError_t launch_normal_fill(float* dst, long long n, unsigned long long seed, unsigned int ctr, cudaStream_t s);
+cudaError_t launch_sum_f32(const float* src, int n, float* dst_accum, cudaStream_t s);
+// dst[i] = off[i] >= 0 ? params[off[i]] : 0   (packed bias vector of a convolution)
+cudaError_t launch_gather_f32(const float* params, const long long* off, int n, float* dst, cudaStream_t s);
+// (B,3,H,W) fp32 -> [B,H,W,4]; robot pixels of `mask` (B,1,H,W) zeroed when given (trainer.py:365-368)
+cudaError_t launch_img_prep_train(const float* img_nchw, const float* mask, float* img4, int B, int HW, cudaStream_t s);
+
+}  // namespace rac

@@ -1,0 +1,246 @@
+"""SVG training step on B200: the arithmetic of the reference `PredictionTrainer._train_step`
+(src/prediction/trainer.py:326-465) + Adam (`_init_models`, :109-122) through libracb200.so.
+
+    trainer = SVGTrainer(cfg, model)                  # model: robot_aware_control_b200.SVGConvModel
+    losses = trainer.train_step(batch)                # batch as the reference loader yields it, time-first
+
+`batch` = {"images": (T,B,3,H,W), "masks": (T,B,1,H,W), "states": (T,B,5), "actions": (T-1,B,A)} (reference
+robonet_dataset.py:434-451). Returned dict = the reference's logged losses (divided by n_future, trainer.py:463-464).
+
+Parameters, BatchNorm running statistics, gradients and Adam moments live in flat fp32 CUDA tensors; the model's
+nn.Parameters are VIEWS into them, so `model.state_dict()` / checkpoints always see the trained values.
+Data parallel (new, the reference is single-process): pass `process_group`; every rank runs its own batch of B, the
+flat gradient buffer is all-reduced (NCCL) and averaged before the Adam update, BatchNorm statistics stay per rank.
+
+Limits (raise): scheduled sampling with model-sampled frames, heatmaps, multiview, movement weighting.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, pack
+from .config import svg_config_from
+
+
+def _layer_tables(model, offsets, boffsets):
+    """For each packed layer: where its tensors live in the flat buffers + the packed-column / packed-channel maps of
+    pack.py expressed as offsets (see rac_train_layer in include/racb200.h)."""
+    c = model._c
+    g, z, a, r = c.g_dim, c.z_dim, c.action_dim, c.robot_dim
+    use_r = bool(c.model_use_robot_state)
+    use_r2 = use_r and bool(c.model_use_future_robot_state)
+    naux = a + (r if use_r else 0) + (r if use_r2 else 0)
+    sd_shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    out = {}
+
+    def cols(splits, k2, in_stride=None):
+        res, ci = [], 0
+        for real, padded in splits:
+            res += [(ci + i) * (in_stride or k2) for i in range(real)] + [-1] * (padded - real)
+            ci += real
+        return res
+
+    def conv_entry(prefix, splits, col_src, n_packed, bias=True, bn=None):
+        w_key = f"{prefix}.weight" if bn is None else f"{prefix}.main.0.weight"
+        cout, cin, k, _ = sd_shapes[w_key]
+        k2 = k * k
+        w_off = offsets[w_key]
+        rows = [(w_off + cs * cin * k2) if cs >= 0 else -1 for cs in col_src] + [-1] * (n_packed - len(col_src))
+        b = None
+        if bias:
+            b_off = offsets[f"{prefix}.bias"]
+            b = [(b_off + cs) if cs >= 0 else -1 for cs in col_src] + [-1] * (n_packed - len(col_src))
+        e = dict(row_off=rows, col_off=cols(splits, k2), bias_off=b, flip=0, w_off=w_off)
+        if bn is not None:
+            e.update(gamma_off=offsets[f"{prefix}.main.1.weight"], beta_off=offsets[f"{prefix}.main.1.bias"],
+                     rmean_off=boffsets[f"{prefix}.main.1.running_mean"], rvar_off=boffsets[f"{prefix}.main.1.running_var"])
+        return e
+
+    rup = lambda x, m: (x + m - 1) // m * m
+    out["ENC_C1_0"] = conv_entry("encoder.c1.0", [(sd_shapes["encoder.c1.0.main.0.weight"][1],) * 2], list(range(64)), 64,
+                                 bias=False, bn=True)
+    for name, prefix in pack._VGG.items():
+        cout, cin = sd_shapes[f"{prefix}.main.0.weight"][:2]
+        out[name] = conv_entry(prefix, [(cin, cin)], list(range(cout)), rup(cout, 64 if cout == 64 else 128), bias=False, bn=True)
+    out["PRIOR_IN"] = conv_entry("prior_input_conv", [(naux, 64), (g, g)], list(range(g)), rup(g, 128))
+    out["FP_IN"] = conv_entry("frame_pred_input_conv", [(naux, 64), (g, g), (z, 64)], list(range(g)), rup(g, 128))
+    out["POST_IN"] = conv_entry("posterior_input_conv", ([(r, 64)] if use_r else []) + [(g, g)], list(range(g)), rup(g, 128))
+    gate_cols = [gate * g + ch for ch in range(g) for gate in range(4)]
+    for tag, prefix in (("PRIOR", "prior"), ("POST", "posterior"), ("FP", "frame_predictor")):
+        for layer in (0, 1):
+            out[f"{tag}_LSTM{layer}"] = conv_entry(f"{prefix}.lstm.{layer}.gates", [(g, g), (g, g)], gate_cols, rup(4 * g, 128))
+    for tag, prefix in (("PRIOR", "prior"), ("POST", "posterior")):
+        wm, wl = offsets[f"{prefix}.mu_net.weight"], offsets[f"{prefix}.logvar_net.weight"]
+        bm, bl = offsets[f"{prefix}.mu_net.bias"], offsets[f"{prefix}.logvar_net.bias"]
+        rows, bias = [], []
+        for zc in range(64):
+            if zc < z:
+                rows += [wm + zc * g * 9, wl + zc * g * 9]
+                bias += [bm + zc, bl + zc]
+            else:
+                rows += [-1, -1]
+                bias += [-1, -1]
+        out[f"{tag}_GAUSS"] = dict(row_off=rows, col_off=cols([(g, g)], 9), bias_off=bias, flip=0, w_off=wm)
+    # ConvTranspose2d(64, 4, 3, 1, 1): weight (in, out, kh, kw); as a conv the taps are flipped (pack.py)
+    wt, bt = offsets["decoder.upc5.1.weight"], offsets["decoder.upc5.1.bias"]
+    nout = sd_shapes["decoder.upc5.1.weight"][1]
+    out["DEC_UPC5_1"] = dict(row_off=[wt + co * 9 for co in range(nout)] + [-1] * (16 - nout),
+                             col_off=[ci * nout * 9 for ci in range(64)],
+                             bias_off=[bt + co for co in range(nout)] + [-1] * (16 - nout), flip=1, w_off=wt)
+    return out
+
+
+class RacTrainLayer(C.Structure):
+    _fields_ = [("row_off", C.c_void_p), ("col_off", C.c_void_p), ("bias_off", C.c_void_p),
+                ("gamma_off", C.c_longlong), ("beta_off", C.c_longlong), ("rmean_off", C.c_longlong),
+                ("rvar_off", C.c_longlong), ("w_off", C.c_longlong), ("flip", C.c_int)]
+
+
+class RacTrainConfig(C.Structure):
+    _fields_ = [("batch", C.c_int), ("steps", C.c_int), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("adam_eps", C.c_float), ("kl_beta", C.c_float), ("robot_pixel_weight", C.c_float),
+                ("recon_kind", C.c_int), ("zero_robot", C.c_int), ("n_params", C.c_longlong), ("n_buffers", C.c_longlong)]
+
+
+class RacTrainBatch(C.Structure):
+    _fields_ = [("images", C.c_void_p), ("masks", C.c_void_p), ("states", C.c_void_p), ("actions", C.c_void_p),
+                ("eps_prior", C.c_void_p), ("eps_post", C.c_void_p), ("seed", C.c_ulonglong), ("losses", C.c_void_p)]
+
+
+class SVGTrainer:
+    def __init__(self, config, model, process_group=None):
+        self._config = config
+        self.model = model
+        c = svg_config_from(config)
+        self.n_future = getattr(config, "n_future", 5)
+        self.n_past = getattr(config, "n_past", 1)
+        if self.n_past != 1:
+            raise NotImplementedError("n_past must be 1 (the reference training recipe, README.md:103)")
+        if getattr(config, "scheduled_sampling", False):
+            raise NotImplementedError("scheduled sampling with model-sampled frames is not implemented on the B200 path")
+        kind = c.reconstruction_loss
+        if kind not in ("l1", "dontcare_l1"):
+            raise NotImplementedError(f"reconstruction_loss {kind!r}: the B200 path implements l1 and dontcare_l1")
+        if not c.last_frame_skip:
+            raise NotImplementedError("last_frame_skip False is not implemented for training")
+        self.process_group = process_group
+        self._lib = _lib.load()
+        dev = model._device
+        # ---- flat fp32 storage; the module's parameters / running stats become views into it
+        params = [(k, p) for k, p in model.named_parameters()]
+        bufs = [(k, b) for k, b in model.named_buffers() if b.is_floating_point()]
+        self._offsets, self._boffsets = {}, {}
+        n = 0
+        for k, p in params:
+            self._offsets[k] = n
+            n += p.numel()
+        nb = 0
+        for k, b in bufs:
+            self._boffsets[k] = nb
+            nb += b.numel()
+        self.params = torch.empty(n, device=dev)
+        self.buffers = torch.empty(max(nb, 1), device=dev)
+        for k, p in params:
+            o = self._offsets[k]
+            view = self.params[o:o + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+        for k, b in bufs:
+            o = self._boffsets[k]
+            view = self.buffers[o:o + b.numel()].view(b.shape)
+            view.copy_(b.data)
+            b.data = view
+        self.grads = torch.zeros(n, device=dev)
+        self.adam_m = torch.zeros(n, device=dev)
+        self.adam_v = torch.zeros(n, device=dev)
+        self.losses = torch.zeros(2, device=dev)
+        self._tables = _layer_tables(model, self._offsets, self._boffsets)
+        self._keep = []  # device index arrays referenced by the library
+        layers = (RacTrainLayer * len(pack.LAYER_IDS))()
+        for i, name in enumerate(pack.LAYER_IDS):
+            t = self._tables[name]
+            ro = torch.tensor(t["row_off"], dtype=torch.int64, device=dev)
+            co = torch.tensor(t["col_off"], dtype=torch.int32, device=dev)
+            self._keep += [ro, co]
+            layers[i].row_off, layers[i].col_off = ro.data_ptr(), co.data_ptr()
+            if t.get("bias_off") is not None:
+                bo = torch.tensor(t["bias_off"], dtype=torch.int64, device=dev)
+                self._keep.append(bo)
+                layers[i].bias_off = bo.data_ptr()
+            for f in ("gamma_off", "beta_off", "rmean_off", "rvar_off"):
+                setattr(layers[i], f, t.get(f, -1))
+            layers[i].w_off = t["w_off"]
+            layers[i].flip = t["flip"]
+        self._layers = layers
+        self._created_for = None
+        self._lr = float(getattr(config, "lr", 1e-4))
+        self._beta1 = float(getattr(config, "beta1", 0.9))
+        self._kl_beta = float(getattr(config, "beta", 1e-4))
+        self._rpw = float(getattr(config, "robot_pixel_weight", 0.0))
+        self._kind = 0 if kind == "l1" else 1
+        self._zero_robot = int("dontcare" in kind or bool(c.black_robot_input))
+        self._seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        self._eps = None
+        self._step = 0
+
+    def set_noise(self, eps_prior, eps_post):
+        """Test hook: (T-1, B, z_dim, 6, 8) reparameterisation noise for the next step (prior drawn first, lstm.py:276-279)."""
+        self._eps = (eps_prior, eps_post)
+
+    def _ensure(self, B, S):
+        if self._created_for == (B, S):
+            return
+        cfg = RacTrainConfig(batch=B, steps=S, lr=self._lr, beta1=self._beta1, beta2=0.999, adam_eps=1e-8,
+                             kl_beta=self._kl_beta, robot_pixel_weight=self._rpw, recon_kind=self._kind,
+                             zero_robot=self._zero_robot, n_params=self.params.numel(), n_buffers=self.buffers.numel())
+        m = self.model
+        _lib.check(self._lib.rac_train_create(m.handle, C.byref(cfg), self._layers, _lib.ptr(self.params),
+                                              _lib.ptr(self.buffers), _lib.ptr(self.grads), _lib.ptr(self.adam_m),
+                                              _lib.ptr(self.adam_v)), m.handle, "rac_train_create")
+        self._created_for = (B, S)
+
+    def forward_backward(self, batch):
+        """Fills self.grads and self.losses (sum over steps of recon, of KL). Returns (recon_sum, kld_sum) tensors."""
+        m = self.model
+        dev = m._device
+        f32 = lambda t: None if t is None else t.to(device=dev, dtype=torch.float32).contiguous()
+        images, actions = f32(batch["images"]), f32(batch["actions"])
+        masks, states = f32(batch.get("masks")), f32(batch.get("states"))
+        T, B = images.shape[0], images.shape[1]
+        self._ensure(B, T - 1)
+        eps_p = eps_q = None
+        if self._eps is not None:
+            eps_p, eps_q = f32(self._eps[0]), f32(self._eps[1])
+            self._eps = None
+        bt = RacTrainBatch(images=_lib.ptr(images), masks=_lib.ptr(masks), states=_lib.ptr(states),
+                           actions=_lib.ptr(actions), eps_prior=_lib.ptr(eps_p), eps_post=_lib.ptr(eps_q),
+                           seed=self._seed, losses=_lib.ptr(self.losses))
+        _lib.check(self._lib.rac_train_forward_backward(m.handle, C.byref(bt), _lib.stream_ptr()), m.handle,
+                   "rac_train_forward_backward")
+        self._keep_batch = (images, actions, masks, states, eps_p, eps_q)  # alive until the stream has consumed them
+        return self.losses
+
+    def optimizer_step(self):
+        m = self.model
+        if self.process_group is not None and dist.get_world_size(self.process_group) > 1:
+            dist.all_reduce(self.grads, group=self.process_group)
+            self.grads.div_(dist.get_world_size(self.process_group))
+        _lib.check(self._lib.rac_train_adam_step(m.handle, _lib.stream_ptr()), m.handle, "rac_train_adam_step")
+        m._packed_dirty = True  # the eval-mode packed copy (folded BatchNorm) is stale now
+        self._step += 1
+
+    def train_step(self, batch):
+        """One reference `_train_step`: returns {"recon_loss", "kld"} averaged over n_future (trainer.py:463-464)."""
+        if not self.model.training:
+            raise RuntimeError("call model.train() before train_step (reference trainer.py:754)")
+        losses = self.forward_backward(batch)
+        self.optimizer_step()
+        nf = batch["images"].shape[0] - 1
+        vals = losses.cpu()
+        return {"recon_loss": float(vals[0]) / nf, "kld": float(vals[1]) / nf}
+
+    def grad_of(self, key):
+        o = self._offsets[key]
+        p = dict(self.model.named_parameters())[key]
+        return self.grads[o:o + p.numel()].view(p.shape)
