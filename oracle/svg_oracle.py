@@ -142,6 +142,15 @@ class SVGOracle:
         self.hidden = None
         self.trace = None  # set to {} to record intermediate activations (NCHW) for layer-by-layer GPU diagnosis
         self.bn_training = False  # True: BatchNorm uses batch statistics and updates running stats (trainer.py:754)
+        # emulate_bf16: round conv weights and inter-layer activations to bf16 (straight-through for autograd) at the
+        # points where the CUDA path stores bf16, so that ReLU / max-pool / |.| decisions agree with it. Used only to
+        # separate rounding-induced gradient noise from implementation errors in the training tests.
+        self.emulate_bf16 = False
+
+    def _q(self, x):
+        if not self.emulate_bf16:
+            return x
+        return x + (x.to(torch.bfloat16).float() - x).detach()
 
     def _rec(self, name, t):
         if self.trace is not None:
@@ -151,10 +160,10 @@ class SVGOracle:
     # vgg_layer: conv3x3(no bias) -> BatchNorm2d(eval) -> LeakyReLU(0.2)  (vgg_64.py:8-18)
     def _vgg(self, x, prefix):
         sd = self.sd
-        x = F.conv2d(x, sd[f"{prefix}.main.0.weight"], None, 1, 1)
+        x = F.conv2d(x, self._q(sd[f"{prefix}.main.0.weight"]), None, 1, 1)
         x = F.batch_norm(x, sd[f"{prefix}.main.1.running_mean"], sd[f"{prefix}.main.1.running_var"],
                          sd[f"{prefix}.main.1.weight"], sd[f"{prefix}.main.1.bias"], self.bn_training, 0.1, 1e-5)
-        return F.leaky_relu(x, 0.2)
+        return self._q(F.leaky_relu(x, 0.2))
 
     # ConvEncoder.forward (vgg_64.py:122-129)
     def encode(self, x):
@@ -185,7 +194,7 @@ class SVGOracle:
             d = self._vgg(d, f"decoder.upc4.{i}")
         d = torch.cat([F.interpolate(d, scale_factor=2, mode="nearest"), skip[0]], 1)
         d = self._rec("d5", self._vgg(d, "decoder.upc5.0"))
-        d = F.conv_transpose2d(d, sd["decoder.upc5.1.weight"], sd["decoder.upc5.1.bias"], 1, 1)
+        d = F.conv_transpose2d(d, self._q(sd["decoder.upc5.1.weight"]), sd["decoder.upc5.1.bias"], 1, 1)
         return torch.sigmoid(d)
 
     # ConvLSTM.init_hidden (lstm.py:218-250), SVGConvModel.init_hidden (dynamics.py:536-542)
@@ -200,11 +209,11 @@ class SVGOracle:
         sd = self.sd
         for layer, pad in ((0, 2), (1, 1)):
             h_prev, c_prev = self.hidden[name][layer]
-            gates = F.conv2d(torch.cat([x, h_prev], 1), sd[f"{name}.lstm.{layer}.gates.weight"],
+            gates = F.conv2d(torch.cat([x, h_prev], 1), self._q(sd[f"{name}.lstm.{layer}.gates.weight"]),
                              sd[f"{name}.lstm.{layer}.gates.bias"], 1, pad)
             i, f, o, g_ = gates.chunk(4, 1)
             c = torch.sigmoid(f) * c_prev + torch.sigmoid(i) * torch.tanh(g_)
-            h = torch.sigmoid(o) * torch.tanh(c)
+            h = self._q(torch.sigmoid(o) * torch.tanh(c))
             self.hidden[name][layer] = (h, c)
             self._rec(f"{name}.h{layer}", h)
             self._rec(f"{name}.c{layer}", c)
@@ -215,9 +224,9 @@ class SVGOracle:
     def _gaussian(self, x, name, eps):
         sd = self.sd
         h = self._convlstm(x, name)
-        mu = F.conv2d(h, sd[f"{name}.mu_net.weight"], sd[f"{name}.mu_net.bias"], 1, 1)
-        logvar = F.conv2d(h, sd[f"{name}.logvar_net.weight"], sd[f"{name}.logvar_net.bias"], 1, 1)
-        z = eps * torch.exp(0.5 * logvar) + mu
+        mu = F.conv2d(h, self._q(sd[f"{name}.mu_net.weight"]), sd[f"{name}.mu_net.bias"], 1, 1)
+        logvar = F.conv2d(h, self._q(sd[f"{name}.logvar_net.weight"]), sd[f"{name}.logvar_net.bias"], 1, 1)
+        z = self._q(eps * torch.exp(0.5 * logvar) + mu)
         return z, mu, logvar
 
     @staticmethod
@@ -238,13 +247,14 @@ class SVGOracle:
         h, curr_skip = self.encode(img)
         if cfg.last_frame_skip or skip is None:
             skip = curr_skip
-        parts = [self._tile(action)]
+        parts = [self._q(self._tile(action))]
         if cfg.model_use_robot_state:
             if cfg.model_use_future_robot_state:
-                parts += [self._tile(robot[0]), self._tile(robot[1])]
+                parts += [self._q(self._tile(robot[0])), self._q(self._tile(robot[1]))]
             else:
-                parts += [self._tile(robot)]
-        prior_in = F.conv2d(torch.cat(parts + [h], 1), sd["prior_input_conv.weight"], sd["prior_input_conv.bias"], 1, 1)
+                parts += [self._q(self._tile(robot))]
+        prior_in = self._q(F.conv2d(torch.cat(parts + [h], 1), self._q(sd["prior_input_conv.weight"]),
+                                    sd["prior_input_conv.bias"], 1, 1))
         self._rec("prior_in", prior_in)
         z_p, mu_p, logvar_p = self._gaussian(prior_in, "prior", eps)
         z = mu_p if sample_mean else z_p
@@ -253,14 +263,14 @@ class SVGOracle:
             # dynamics.py:619 encodes `img` (the CURRENT frame) again: same values as h; in train mode the second
             # pass updates the BatchNorm running statistics a second time and is a second autograd path
             h_t = self.encode(img)[0] if self.bn_training else h
-            post_parts = [self._tile(next_robot)] if cfg.model_use_robot_state else []
-            post_in = F.conv2d(torch.cat(post_parts + [h_t], 1), sd["posterior_input_conv.weight"],
-                               sd["posterior_input_conv.bias"], 1, 1)
+            post_parts = [self._q(self._tile(next_robot))] if cfg.model_use_robot_state else []
+            post_in = self._q(F.conv2d(torch.cat(post_parts + [h_t], 1), self._q(sd["posterior_input_conv.weight"]),
+                                       sd["posterior_input_conv.bias"], 1, 1))
             z_t, mu, logvar = self._gaussian(post_in, "posterior", eps_post)
             if not force_use_prior:
                 z = z_t
-        frame_in = F.conv2d(torch.cat(parts + [h, z], 1), sd["frame_pred_input_conv.weight"],
-                            sd["frame_pred_input_conv.bias"], 1, 1)
+        frame_in = self._q(F.conv2d(torch.cat(parts + [h, z], 1), self._q(sd["frame_pred_input_conv.weight"]),
+                                    sd["frame_pred_input_conv.bias"], 1, 1))
         self._rec("z", z)
         self._rec("frame_in", frame_in)
         h_pred = self._convlstm(frame_in, "frame_predictor")
