@@ -154,7 +154,11 @@ class SVGOracle:
 
     def _rec(self, name, t):
         if self.trace is not None:
-            self.trace[name] = t.clone()
+            if t.requires_grad:
+                t.retain_grad()  # training diagnosis: intermediate gradients are compared layer by layer
+                self.trace[name] = t
+            else:
+                self.trace[name] = t.clone()
         return t
 
     # vgg_layer: conv3x3(no bias) -> BatchNorm2d(eval) -> LeakyReLU(0.2)  (vgg_64.py:8-18)
@@ -186,13 +190,13 @@ class SVGOracle:
         for i in range(3):
             d = self._vgg(d, f"decoder.upc2.{i}")
             self._rec(f"d2.{i}", d)
-        d = torch.cat([F.interpolate(d, scale_factor=2, mode="nearest"), skip[2]], 1)
+        d = self._rec("cat3", torch.cat([F.interpolate(d, scale_factor=2, mode="nearest"), skip[2]], 1))
         for i in range(3):
-            d = self._vgg(d, f"decoder.upc3.{i}")
-        d = torch.cat([F.interpolate(d, scale_factor=2, mode="nearest"), skip[1]], 1)
+            d = self._rec(f"d3.{i}", self._vgg(d, f"decoder.upc3.{i}"))
+        d = self._rec("cat4", torch.cat([F.interpolate(d, scale_factor=2, mode="nearest"), skip[1]], 1))
         for i in range(2):
-            d = self._vgg(d, f"decoder.upc4.{i}")
-        d = torch.cat([F.interpolate(d, scale_factor=2, mode="nearest"), skip[0]], 1)
+            d = self._rec(f"d4.{i}", self._vgg(d, f"decoder.upc4.{i}"))
+        d = self._rec("cat5", torch.cat([F.interpolate(d, scale_factor=2, mode="nearest"), skip[0]], 1))
         d = self._rec("d5", self._vgg(d, "decoder.upc5.0"))
         d = F.conv_transpose2d(d, self._q(sd["decoder.upc5.1.weight"]), sd["decoder.upc5.1.bias"], 1, 1)
         return torch.sigmoid(d)

@@ -52,6 +52,7 @@ struct EpiParams {
   int hid;
   const float* c_in;     // training: previous cell state read from here (null: c_state, in place)
   float* gates_out;      // training: post-activation gates fp32 [B*H*W, 4*hid] in packed column order (null: not saved)
+  int exact_math;        // training: libm tanh / exp instead of MUFU.TANH (gradients are checked against fp32 autograd)
   // EPI_F32 (training: raw pre-BatchNorm conv output, dgrad into gradient accumulators, wgrad into packed dW)
   F32Seg seg[3];
   int nseg;

@@ -116,12 +116,18 @@ __device__ __forceinline__ void epi_lstm(const ConvGeom& g, const EpiParams& e, 
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 bq = __ldg(bias4 + q);
-    const float ig = sigmoid_fast(acc[4 * q + 0] + bq.x);
-    const float fg = sigmoid_fast(acc[4 * q + 1] + bq.y);
-    const float og = sigmoid_fast(acc[4 * q + 2] + bq.z);
-    const float cg = tanh_fast(acc[4 * q + 3] + bq.w);
-    cn[q] = fg * cprev[q] + ig * cg;
-    hn[q] = og * tanh_fast(cn[q]);
+    float ig, fg, og, cg;
+    if (e.exact_math) {
+      ig = sigmoidf_(acc[4 * q + 0] + bq.x); fg = sigmoidf_(acc[4 * q + 1] + bq.y);
+      og = sigmoidf_(acc[4 * q + 2] + bq.z); cg = tanhf(acc[4 * q + 3] + bq.w);
+      cn[q] = fg * cprev[q] + ig * cg;
+      hn[q] = og * tanhf(cn[q]);
+    } else {
+      ig = sigmoid_fast(acc[4 * q + 0] + bq.x); fg = sigmoid_fast(acc[4 * q + 1] + bq.y);
+      og = sigmoid_fast(acc[4 * q + 2] + bq.z); cg = tanh_fast(acc[4 * q + 3] + bq.w);
+      cn[q] = fg * cprev[q] + ig * cg;
+      hn[q] = og * tanh_fast(cn[q]);
+    }
     if (gsave) gsave[q] = make_float4(ig, fg, og, cg);
   }
   *reinterpret_cast<float4*>(e.c_state + base) = *reinterpret_cast<float4*>(cn);

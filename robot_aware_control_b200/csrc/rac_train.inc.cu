@@ -204,7 +204,7 @@ int lstm_forward(rac_handle* h, TrainState* T, int s, int t, const bf16* xin, cu
     EpiParams e{};
     e.bias = L.bias; e.cout = 4 * g; e.hid = g;
     e.c_in = t > 0 ? T->tape[t - 1].cs[s][l] : T->czero;
-    e.c_state = tp.cs[s][l]; e.h_out = tp.hs[s][l]; e.gates_out = tp.gates[s][l];
+    e.c_state = tp.cs[s][l]; e.h_out = tp.hs[s][l]; e.gates_out = tp.gates[s][l]; e.exact_math = 1;
     const int ks = l == 0 ? 5 : 3;
     CKR(t_gemm(h, "train.lstm.fwd", {B, 6, 8, ks, false}, {{x, g}, {hprev, g}}, L.wp, ks * ks * 2 * g, L.n_packed,
                tile_block_n(L.n_packed, EPI_LSTM), EPI_LSTM, e, st));
@@ -611,6 +611,30 @@ int rac_train_forward_backward(rac_handle* h, const rac_train_batch* bt, void* s
   }
   T->step_count++;
   return RAC_OK;
+}
+
+int rac_train_debug_buffer(rac_handle* h, const char* name, int step, void** ptr) {
+  if (!h || !h->train || !name || !ptr) return RAC_ERR_INVALID;
+  TrainState* T = static_cast<TrainState*>(h->train);
+  if (step < 0 || step >= static_cast<int>(T->tape.size())) return fail(h, RAC_ERR_INVALID, "bad step %d", step);
+  Tape& tp = T->tape[step];
+  struct { const char* n; void* p; } tab[] = {
+      {"G_d5", T->G_d5}, {"G_cat5", T->G_cat5}, {"G_d4a", T->G_d4a}, {"G_cat4", T->G_cat4}, {"G_d3b", T->G_d3b},
+      {"G_d3a", T->G_d3a}, {"G_cat3", T->G_cat3}, {"G_d2b", T->G_d2b}, {"G_d2a", T->G_d2a}, {"G_fin", T->G_fin},
+      {"G_pin", T->G_pin}, {"G_postin", T->G_postin}, {"G_z", T->G_z}, {"G_h4", T->G_h4}, {"G_a4b", T->G_a4b},
+      {"G_a4a", T->G_a4a}, {"G_p3", T->G_p3}, {"G_a3b", T->G_a3b}, {"G_a3a", T->G_a3a}, {"G_p2", T->G_p2},
+      {"G_a2", T->G_a2}, {"G_p1", T->G_p1}, {"G_a1", T->G_a1},
+      {"img4", tp.img4}, {"a1", tp.a1}, {"cat5", tp.cat5}, {"p1", tp.p1}, {"a2", tp.a2}, {"cat4", tp.cat4},
+      {"p2", tp.p2}, {"a3a", tp.a3a}, {"a3b", tp.a3b}, {"cat3", tp.cat3}, {"p3", tp.p3}, {"a4a", tp.a4a},
+      {"a4b", tp.a4b}, {"h4", tp.h4}, {"d2a", tp.d2a}, {"d2b", tp.d2b}, {"d3a", tp.d3a}, {"d3b", tp.d3b},
+      {"d4a", tp.d4a}, {"d5", tp.d5}, {"x4", tp.x4}, {"hfp1", tp.hs[2][1]}};
+  for (auto& e : tab)
+    if (!strcmp(e.n, name)) { *ptr = e.p; return RAC_OK; }
+  if (!strncmp(name, "raw", 3)) {
+    const int i = atoi(name + 3);
+    if (i >= 0 && i < 19) { *ptr = tp.vgg[i].raw; return RAC_OK; }
+  }
+  return fail(h, RAC_ERR_INVALID, "no training buffer named '%s'", name);
 }
 
 int rac_train_adam_step(rac_handle* h, void* stream) {

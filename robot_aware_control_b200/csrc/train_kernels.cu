@@ -313,7 +313,7 @@ lstm_bwd_kernel(const float* __restrict__ dh, float* __restrict__ dc, const floa
   if (i >= total) return;
   const float4 gt = reinterpret_cast<const float4*>(gates)[i];  // i, f, o, g (post-activation)
   const float cp = c_prev ? c_prev[i] : 0.f;
-  const float tc = tanh_fast(c_new[i]);  // same function as the forward epilogue
+  const float tc = tanhf(c_new[i]);  // the training forward uses libm tanh as well (EpiParams::exact_math)
   const float dhv = dh[i];
   const float dcv = dc[i] + dhv * gt.z * (1.f - tc * tc);
   const float d_o = dhv * tc;
