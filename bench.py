@@ -182,6 +182,73 @@ def cost_kernel_roofline(dev, hbm_peak, n=16384, reps=20):
             "candidate_steps_per_sec": n / (ms * 1e-3)}
 
 
+def run_train_bench(args):
+    """Extra (not the headline metric): samples/s of the SVG training step, one JSON line."""
+    os.environ["NCCL_DEBUG"] = os.environ.get("RAC_NCCL_DEBUG", "WARN")
+    import torch.distributed as dist
+    from oracle import svg_oracle as so
+    from robot_aware_control_b200 import SVGConvModel, SVGTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        group = dist.group.WORLD
+    dev = torch.device("cuda", local_rank)
+    ra = args.robot_aware
+    kw = dict(lr=1e-4, beta=1e-4, beta1=0.9, n_future=5, n_past=1)
+    if ra:
+        cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, action_dim=A_DIM, model_use_mask=True, model_use_future_mask=True,
+                          model_use_robot_state=True, reconstruction_loss="dontcare_l1", reward_type="dontcare", **kw)
+    else:
+        cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, action_dim=A_DIM, **kw)
+    model = SVGConvModel(cfg)
+    model.load_state_dict(so.make_state_dict(cfg, 0))
+    model.train()
+    trainer = SVGTrainer(cfg, model, process_group=group)
+    Bt, T = 16, 6
+    g = torch.Generator(device="cuda").manual_seed(rank)
+    batch = {"images": torch.rand(T, Bt, 3, 48, 64, device=dev, generator=g),
+             "actions": torch.rand(T - 1, Bt, A_DIM, device=dev, generator=g) * 0.1 - 0.05,
+             "states": torch.rand(T, Bt, 5, device=dev, generator=g),
+             "masks": (torch.rand(T, Bt, 1, 48, 64, device=dev, generator=g) > 0.8).float()}
+
+    def step():
+        trainer.forward_backward(batch)
+        trainer.optimizer_step()
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    loss = trainer.losses.cpu().tolist()
+    if rank == 0:
+        per = float(ms.item()) / args.steps
+        print(json.dumps({
+            "metric": "svg_train_samples_per_sec", "value": Bt * world / (per * 1e-3), "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"SVG training step, batch {Bt}/GPU, n_past 1 / n_future 5, g_dim {G_DIM} z_dim {Z_DIM}, "
+                                   + ("dontcare_l1 robot-aware" if ra else "l1 vanilla") + ", Adam, data parallel",
+                       "algorithmic_tflop_per_step_per_gpu": 6.52},
+            "achieved_tflops_per_gpu": 6.52 / (per * 1e-3), "last_losses": loss}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -191,12 +258,17 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--candidates", type=int, default=0, help="override the candidate count (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train", action="store_true",
+                    help="BASELINE configs[0]/[3]: SVG training step (batch 16 per GPU, n_past 1 / n_future 5), "
+                         "forward + BPTT backward + Adam; data parallel over --gpus")
     ap.add_argument("--robot-aware", action="store_true",
                     help="BASELINE configs[4]: model_use_robot_state + model_use_mask(+future mask), dontcare cost, "
                          "synthetic per-candidate robot states / rectangle masks resident on the device")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.train:
+        return run_train_bench(args)
 
     os.environ["NCCL_DEBUG"] = os.environ.get("RAC_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
     import torch.distributed as dist
