@@ -305,6 +305,8 @@ static cudaError_t launch_simt_t(const ConvOp& op, cudaStream_t stream) {
   X(256, 256, EPI_F32)      \
   X(256, 128, EPI_F32)      \
   X(256, 64, EPI_F32)       \
+  X(128, 128, EPI_F32)      \
+  X(128, 64, EPI_F32)       \
   X(128, 128, EPI_ACT)      \
   X(128, 64, EPI_ACT)       \
   X(128, 128, EPI_LSTM)     \

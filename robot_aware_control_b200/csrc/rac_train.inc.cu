@@ -83,18 +83,32 @@ int t_gemm(rac_handle* h, const char* name, const GemmGeom& gg, const std::vecto
   ConvOp op;
   memset(&op, 0, sizeof(op));
   op.name = name;
-  op.block_m = 256;
-  op.block_n = block_n;
   op.epi = epi;
   ConvGeom& g = op.g;
   g.B = gg.B; g.H = gg.H; g.W = gg.W; g.ks = gg.ks; g.pad = gg.ks / 2;
-  if (gg.plain) { g.BH = 1; g.NB = 4; }
-  else switch (gg.W) {
-    case 64: g.BH = 4; g.NB = 1; break;
-    case 32: g.BH = 8; g.NB = 1; break;
-    case 16: g.BH = 4; g.NB = 4; break;
-    case 8: g.BH = 2; g.NB = 16; break;
-    default: return fail(h, RAC_ERR_INVALID, "train gemm %s: bad width %d", name, gg.W);
+  // batch-16 training GEMMs are small: when 256-row tiles would leave most of the 148 SMs idle, use 128 x <=128 tiles
+  auto geom = [&](int bm) -> bool {
+    const bool big = bm == 256;
+    if (gg.plain) { g.BH = 1; g.NB = big ? 4 : 2; return true; }
+    switch (gg.W) {
+      case 64: g.BH = big ? 4 : 2; g.NB = 1; return true;
+      case 32: g.BH = big ? 8 : 4; g.NB = 1; return true;
+      case 16: g.BH = 4; g.NB = big ? 4 : 2; return true;
+      case 8: g.BH = 2; g.NB = big ? 16 : 8; return true;
+      default: return false;
+    }
+  };
+  if (!geom(256)) return fail(h, RAC_ERR_INVALID, "train gemm %s: bad width %d", name, gg.W);
+  op.block_m = 256;
+  op.block_n = block_n;
+  {
+    const long long tiles = static_cast<long long>((gg.B + g.NB - 1) / g.NB) * (gg.H / g.BH) * (n_rows_w / block_n);
+    if (tiles < 120) {
+      op.block_m = 128;
+      geom(128);
+      if (op.block_n > 128) op.block_n = 128;
+      block_n = op.block_n;
+    }
   }
   g.nsrc = static_cast<int>(srcs.size());
   for (int i = 0; i < g.nsrc; ++i) {

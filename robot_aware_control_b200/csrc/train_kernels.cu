@@ -134,14 +134,21 @@ cudaError_t launch_first_wgrad(const float* img4, const float* mask_a, const flo
 }
 
 // ------------------------------------------------------------------------------------------------ BatchNorm
-// block (32 channels, 32 row lanes); per-channel reduction over all M rows in fp64
+// Per-channel reductions over all M rows, fp64, deterministic: grid (C/32, R) blocks of (32 channels x 32 row lanes)
+// write R partial sums per channel; a second tiny kernel folds them in a fixed order.
+constexpr int kRedSplit = 64;
+__device__ double g_red_part[2 * kRedSplit * 2048];  // [which][split][channel], channels <= 2048
+
 template <typename F>
-__device__ __forceinline__ void column_reduce2(int M, int C, F load, double& s1, double& s2) {
+__device__ __forceinline__ void column_partial2(int M, int C, F load) {
   __shared__ double sh1[32][33], sh2[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int m_lo = blockIdx.y * rows_per;
+  const int m_hi = min(M, m_lo + rows_per);
   double a = 0.0, b = 0.0;
   if (c < C) {
-    for (int m = threadIdx.y; m < M; m += 32) {
+    for (int m = m_lo + threadIdx.y; m < m_hi; m += 32) {
       float v1, v2;
       load(m, c, v1, v2);
       a += v1;
@@ -151,44 +158,61 @@ __device__ __forceinline__ void column_reduce2(int M, int C, F load, double& s1,
   sh1[threadIdx.y][threadIdx.x] = a;
   sh2[threadIdx.y][threadIdx.x] = b;
   __syncthreads();
-  s1 = s2 = 0.0;
-  if (threadIdx.y == 0) {
+  if (threadIdx.y == 0 && c < C) {
+    double s1 = 0.0, s2 = 0.0;
     for (int i = 0; i < 32; ++i) {
       s1 += sh1[i][threadIdx.x];
       s2 += sh2[i][threadIdx.x];
     }
+    g_red_part[(0 * kRedSplit + blockIdx.y) * 2048 + c] = s1;
+    g_red_part[(1 * kRedSplit + blockIdx.y) * 2048 + c] = s2;
   }
 }
+__device__ __forceinline__ void column_fold2(int c, int nsplit, double& s1, double& s2) {
+  s1 = s2 = 0.0;
+  for (int r = 0; r < nsplit; ++r) {
+    s1 += g_red_part[(0 * kRedSplit + r) * 2048 + c];
+    s2 += g_red_part[(1 * kRedSplit + r) * 2048 + c];
+  }
+}
+inline int red_split(int M) {
+  int r = M / 512;
+  return r < 1 ? 1 : (r > kRedSplit ? kRedSplit : r);
+}
 
-__global__ void __launch_bounds__(1024)
-bn_stats_kernel(const float* __restrict__ raw, int M, int C, float* __restrict__ mean, float* __restrict__ rstd,
-                float* __restrict__ rmean, float* __restrict__ rvar, int updates) {
-  double s1, s2;
-  column_reduce2(M, C, [&](int m, int c, float& v1, float& v2) {
+__global__ void __launch_bounds__(1024) bn_stats_partial_kernel(const float* __restrict__ raw, int M, int C) {
+  column_partial2(M, C, [&](int m, int c, float& v1, float& v2) {
     const float x = raw[static_cast<size_t>(m) * C + c];
     v1 = x;
     v2 = x * x;
-  }, s1, s2);
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  if (threadIdx.y == 0 && c < C) {
-    const double mu = s1 / M;
-    double var = s2 / M - mu * mu;
-    if (var < 0.0) var = 0.0;
-    mean[c] = static_cast<float>(mu);
-    rstd[c] = static_cast<float>(1.0 / sqrt(var + 1e-5));
-    const double unbiased = var * M / (M - 1);
-    float rm = rmean[c], rv = rvar[c];
-    for (int u = 0; u < updates; ++u) {  // reference: momentum 0.1, the encoder runs twice per step (dynamics.py:619)
-      rm = 0.9f * rm + 0.1f * static_cast<float>(mu);
-      rv = 0.9f * rv + 0.1f * static_cast<float>(unbiased);
-    }
-    rmean[c] = rm;
-    rvar[c] = rv;
+  });
+}
+__global__ void bn_stats_final_kernel(int M, int C, int nsplit, float* __restrict__ mean, float* __restrict__ rstd,
+                                      float* __restrict__ rmean, float* __restrict__ rvar, int updates) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1, s2;
+  column_fold2(c, nsplit, s1, s2);
+  const double mu = s1 / M;
+  double var = s2 / M - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[c] = static_cast<float>(mu);
+  rstd[c] = static_cast<float>(1.0 / sqrt(var + 1e-5));
+  const double unbiased = var * M / (M - 1);
+  float rm = rmean[c], rv = rvar[c];
+  for (int u = 0; u < updates; ++u) {  // reference: momentum 0.1, the encoder runs twice per step (dynamics.py:619)
+    rm = 0.9f * rm + 0.1f * static_cast<float>(mu);
+    rv = 0.9f * rv + 0.1f * static_cast<float>(unbiased);
   }
+  rmean[c] = rm;
+  rvar[c] = rv;
 }
 cudaError_t launch_bn_stats(const float* raw, int M, int C, float* mean, float* rstd, float* running_mean,
                             float* running_var, int updates, cudaStream_t s) {
-  bn_stats_kernel<<<(C + 31) / 32, dim3(32, 32), 0, s>>>(raw, M, C, mean, rstd, running_mean, running_var, updates);
+  if (C > 2048) return cudaErrorInvalidValue;
+  const int R = red_split(M);
+  bn_stats_partial_kernel<<<dim3((C + 31) / 32, R), dim3(32, 32), 0, s>>>(raw, M, C);
+  bn_stats_final_kernel<<<(C + 127) / 128, 128, 0, s>>>(M, C, R, mean, rstd, running_mean, running_var, updates);
   return cudaGetLastError();
 }
 
@@ -257,23 +281,24 @@ __device__ __forceinline__ void bn_bwd_point(const BnBwdArgs& a, int m, int c, f
   const float bn = xhat * a.gamma[c] + a.beta[c];
   dz = bn > 0.f ? g : 0.2f * g;
 }
-__global__ void __launch_bounds__(1024)
-bn_bwd_reduce_kernel(BnBwdArgs a, int M, float* __restrict__ scratch, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta) {
-  double s1, s2;
-  column_reduce2(M, a.C, [&](int m, int c, float& v1, float& v2) {
+__global__ void __launch_bounds__(1024) bn_bwd_partial_kernel(BnBwdArgs a, int M) {
+  column_partial2(M, a.C, [&](int m, int c, float& v1, float& v2) {
     float dz, xh;
     bn_bwd_point(a, m, c, dz, xh);
     v1 = dz;
     v2 = dz * xh;
-  }, s1, s2);
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  if (threadIdx.y == 0 && c < a.C) {
-    scratch[c] = static_cast<float>(s1);
-    scratch[a.C + c] = static_cast<float>(s2);
-    dbeta[c] += static_cast<float>(s1);
-    dgamma[c] += static_cast<float>(s2);
-  }
+  });
+}
+__global__ void bn_bwd_final_kernel(int C, int nsplit, float* __restrict__ scratch, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1, s2;
+  column_fold2(c, nsplit, s1, s2);
+  scratch[c] = static_cast<float>(s1);
+  scratch[C + c] = static_cast<float>(s2);
+  dbeta[c] += static_cast<float>(s1);
+  dgamma[c] += static_cast<float>(s2);
 }
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(BnBwdArgs a, int M, const float* __restrict__ scratch, __nv_bfloat16* __restrict__ draw,
@@ -296,7 +321,10 @@ cudaError_t launch_bn_bwd(const float* dy, int dy_cstride, int dy_coff, int upsa
                           float* dbeta, cudaStream_t s) {
   BnBwdArgs a{dy, dy_cstride, dy_coff, upsample, raw, mean, rstd, gamma, beta, H, W, C};
   const int M = B * H * W;
-  bn_bwd_reduce_kernel<<<(C + 31) / 32, dim3(32, 32), 0, s>>>(a, M, scratch, dgamma, dbeta);
+  if (C > 2048) return cudaErrorInvalidValue;
+  const int R = red_split(M);
+  bn_bwd_partial_kernel<<<dim3((C + 31) / 32, R), dim3(32, 32), 0, s>>>(a, M);
+  bn_bwd_final_kernel<<<(C + 127) / 128, 128, 0, s>>>(C, R, scratch, dgamma, dbeta);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const size_t total = static_cast<size_t>(M) * C;
@@ -331,20 +359,27 @@ cudaError_t launch_lstm_bwd(const float* dh, float* dc, const float* gates, cons
   return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(1024)
-bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, int M, int ncols, int nvalid,
-                 const long long* __restrict__ bias_off, float* __restrict__ grads) {
-  double s1, s2;
-  column_reduce2(M, nvalid, [&](int m, int c, float& v1, float& v2) {
+__global__ void __launch_bounds__(1024) bias_grad_partial_kernel(const __nv_bfloat16* __restrict__ dy, int M, int ncols,
+                                                                  int nvalid) {
+  column_partial2(M, nvalid, [&](int m, int c, float& v1, float& v2) {
     v1 = __bfloat162float(dy[static_cast<size_t>(m) * ncols + c]);
     v2 = 0.f;
-  }, s1, s2);
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  if (threadIdx.y == 0 && c < nvalid && bias_off[c] >= 0) grads[bias_off[c]] += static_cast<float>(s1);
+  });
+}
+__global__ void bias_grad_final_kernel(int nvalid, int nsplit, const long long* __restrict__ bias_off,
+                                       float* __restrict__ grads) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nvalid || bias_off[c] < 0) return;
+  double s1, s2;
+  column_fold2(c, nsplit, s1, s2);
+  grads[bias_off[c]] += static_cast<float>(s1);
 }
 cudaError_t launch_bias_grad(const __nv_bfloat16* dy, int M, int ncols, int nvalid, const long long* bias_off,
                              float* grads, cudaStream_t s) {
-  bias_grad_kernel<<<(nvalid + 31) / 32, dim3(32, 32), 0, s>>>(dy, M, ncols, nvalid, bias_off, grads);
+  if (nvalid > 2048) return cudaErrorInvalidValue;
+  const int R = red_split(M);
+  bias_grad_partial_kernel<<<dim3((nvalid + 31) / 32, R), dim3(32, 32), 0, s>>>(dy, M, ncols, nvalid);
+  bias_grad_final_kernel<<<(nvalid + 127) / 128, 128, 0, s>>>(nvalid, R, bias_off, grads);
   return cudaGetLastError();
 }
 
@@ -521,30 +556,43 @@ cudaError_t launch_transpose_bf16(const __nv_bfloat16* src, int M, int C, int mp
   return cudaGetLastError();
 }
 
+// 64 (rows m) x 64 (channels) tiles, two bf16 per thread: 128-byte segments on both the NHWC read and the
+// transposed write side
 __global__ void __launch_bounds__(1024)
 im2col_t_kernel(const __nv_bfloat16* __restrict__ src, int B, int H, int W, int C, int ks, int ctot, int coff,
                 int mpad, __nv_bfloat16* __restrict__ dst) {
-  __shared__ __nv_bfloat16 tile[32][33];
+  __shared__ uint32_t tile[64][33];
   const int M = B * H * W;
-  const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 32, tap = blockIdx.z;
+  const int m0 = blockIdx.x * 64, c0 = blockIdx.y * 64, tap = blockIdx.z;
   const int dy = tap / ks - ks / 2, dx = tap % ks - ks / 2;
-  const int m = m0 + threadIdx.y, c = c0 + threadIdx.x;
-  __nv_bfloat16 v = __float2bfloat16(0.f);
-  if (m < M && c < C) {
-    const int x = m % W, y = (m / W) % H, b = m / (W * H);
-    const int yy = y + dy, xx = x + dx;
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = src[(static_cast<size_t>(b * H + yy) * W + xx) * C + c];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int m = m0 + ty + 32 * rr;
+    uint32_t v = 0u;
+    if (m < M) {
+      const int x = m % W, y = (m / W) % H, b = m / (W * H);
+      const int yy = y + dy, xx = x + dx;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+        v = *reinterpret_cast<const uint32_t*>(src + (static_cast<size_t>(b * H + yy) * W + xx) * C + c0 + 2 * tx);
+    }
+    tile[ty + 32 * rr][tx] = v;
   }
-  tile[threadIdx.y][threadIdx.x] = v;
   __syncthreads();
-  const int co = c0 + threadIdx.y, mo = m0 + threadIdx.x;
-  if (co < C && mo < mpad)
-    dst[(static_cast<size_t>(tap) * ctot + coff + co) * mpad + mo] = tile[threadIdx.x][threadIdx.y];
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int cl = ty + 32 * rr;  // channel inside the tile
+    const uint32_t a = tile[2 * tx][cl >> 1], b2 = tile[2 * tx + 1][cl >> 1];
+    const uint32_t lo = (cl & 1) ? (a >> 16) : (a & 0xffffu);
+    const uint32_t hi = (cl & 1) ? (b2 >> 16) : (b2 & 0xffffu);
+    *reinterpret_cast<uint32_t*>(dst + (static_cast<size_t>(tap) * ctot + coff + c0 + cl) * mpad + m0 + 2 * tx) =
+        lo | (hi << 16);
+  }
 }
 cudaError_t launch_im2col_t(const __nv_bfloat16* src, int B, int H, int W, int C, int ks, int ctot, int coff, int mpad,
                             __nv_bfloat16* dst, cudaStream_t s) {
-  im2col_t_kernel<<<dim3((mpad + 31) / 32, (C + 31) / 32, ks * ks), dim3(32, 32), 0, s>>>(src, B, H, W, C, ks, ctot,
-                                                                                          coff, mpad, dst);
+  if (C % 64 != 0 || mpad % 64 != 0) return cudaErrorInvalidValue;
+  im2col_t_kernel<<<dim3(mpad / 64, C / 64, ks * ks), dim3(32, 32), 0, s>>>(src, B, H, W, C, ks, ctot, coff, mpad, dst);
   return cudaGetLastError();
 }
 
