@@ -235,6 +235,12 @@ def run_train_bench(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     loss = trainer.losses.cpu().tolist()
+    identical = None
+    if world > 1:  # replicated Adam on all-reduced gradients: parameters must stay bit-identical across ranks
+        chk = torch.stack([trainer.params.double().sum(), trainer.params.double().abs().sum()])
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        identical = all(torch.equal(allc[0], c) for c in allc)
     if rank == 0:
         per = float(ms.item()) / args.steps
         print(json.dumps({
@@ -244,7 +250,8 @@ def run_train_bench(args):
             "config": {"workload": f"SVG training step, batch {Bt}/GPU, n_past 1 / n_future 5, g_dim {G_DIM} z_dim {Z_DIM}, "
                                    + ("dontcare_l1 robot-aware" if ra else "l1 vanilla") + ", Adam, data parallel",
                        "algorithmic_tflop_per_step_per_gpu": 6.52},
-            "achieved_tflops_per_gpu": 6.52 / (per * 1e-3), "last_losses": loss}))
+            "achieved_tflops_per_gpu": 6.52 / (per * 1e-3), "last_losses": loss,
+            "ddp_params_identical_across_ranks": identical}))
     if world > 1:
         dist.destroy_process_group()
 
