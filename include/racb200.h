@@ -213,6 +213,8 @@ typedef struct {
   const float* eps_post;
   unsigned long long seed;
   float* losses;           /* out, device float[2]: sum over steps of the reconstruction loss, of the KL term */
+  const int* true_token;   /* HOST int[steps] or NULL: 0 at step t >= 1 = feed the model's own previous prediction
+                              (scheduled sampling, trainer.py:132-147,353-356); NULL = always the ground-truth frame */
 } rac_train_batch;
 
 int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train_layer* layers /* [RAC_L_COUNT] */,

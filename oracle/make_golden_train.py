@@ -46,7 +46,8 @@ def main():
     trainer_mod = importlib.import_module("src.prediction.trainer")
     feeder = EpsFeeder()
     lstm_mod.GaussianConvLSTM.reparameterize = lambda self, mu, logvar: feeder(self, mu, logvar)
-    for tag, kw in (("vanilla", dict(robot_aware=False)), ("ra", dict(robot_aware=True, future_mask=True))):
+    for tag, kw in (("vanilla", dict(robot_aware=False)), ("ra", dict(robot_aware=True, future_mask=True)),
+                    ("ra_sampled", dict(robot_aware=True, future_mask=True))):
         cfg = ref_shim.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, extra=("--n_future", str(T - 1), "--batch_size", str(B),
                                                                 "--lr", "1e-3", "--beta", "1e-2"), **kw)
         cfg.multiview = False
@@ -57,8 +58,12 @@ def main():
         tr._init_models(cfg)
         tr.model.load_state_dict(sd)
         tr._scheduled_sampling = False
+        if tag.endswith("sampled"):  # scheduled sampling with the model's own frame at every step i > 1
+            tr._scheduled_sampling = True
+            tr._use_true_token = lambda: False
         tr._step = 0
         tr.model.train()
+        kw = dict(kw)
         batch, eps_p, eps_q = make_batch(23, cfg, kw["robot_aware"])
         batch_ref = dict(batch, qpos=torch.zeros(T, B, 6), robot=["sawyer"] * B, folder=["x"] * B)
         out = {}

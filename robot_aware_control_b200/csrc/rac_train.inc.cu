@@ -7,8 +7,10 @@
 // (tcgen05 / TMA); the rest are the small kernels of train_kernels.cu. Parameters, gradients and Adam moments are
 // flat fp32 buffers owned by the caller (torch tensors): the gradient buffer can be all-reduced as one message.
 //
-// Not implemented: model-sampled input frames (scheduled sampling picks the ground-truth frame; its probability is
-// 4000/4001 at step 0, trainer.py:132-147), heatmaps, multiview, batch_weight.
+// Scheduled sampling (trainer.py:132-147,353-356): per step the caller says whether the input frame is the ground
+// truth or the model's previous composited prediction; in the latter case the gradient flows back through the
+// composite and the encoder input into the previous step, as in the reference (x_pred.clone(), not detached).
+// Not implemented: heatmaps, multiview, batch_weight.
 
 #include <algorithm>
 
@@ -42,6 +44,9 @@ struct Tape {  // everything the backward pass of one time step needs
   VggRt vgg[19];
   float *mu_p, *lv_p, *mu, *lv, *x4;
   float *eps_p, *eps_q;
+  float* xp;          // composited prediction (B,3,H,W): the next step's input under scheduled sampling
+  const float* xj;    // this step's input frame (ground truth or the previous step's xp)
+  int sampled;        // 1: xj is the model's own previous prediction (gradient flows back, trainer.py:354)
 };
 
 struct TrainState {
@@ -57,6 +62,9 @@ struct TrainState {
   float *G_a4b, *G_a4a, *G_p3, *G_a3b, *G_a3a, *G_p2, *G_a2, *G_p1, *G_a1;
   float* G_hs[3][2][2];
   float* G_dc[3][2];
+  float* G_img[2];       // gradient w.r.t. a sampled input frame, ping-pong across steps
+  float* dbg_draw32 = nullptr;  // RAC_TRAIN_DEBUG_KEEP=1: first-layer raw gradient of the last SAMPLED step (tests)
+  int dbg_keep = 0;
   bf16 *dy_a, *dy_b;     // bf16 gradient operands (largest [M, C])
   bf16 *xcolT, *dyT;     // transposed wgrad operands
   float* bn_scratch;
@@ -263,7 +271,9 @@ int train_forward_step(rac_handle* h, TrainState* T, const rac_train_batch* bt, 
   const int B = T->cfg.batch, g = c.g_dim, z = c.z_dim;
   const size_t HW = 48 * 64;
   Tape& tp = T->tape[t];
-  const float* x_j = bt->images + static_cast<size_t>(t) * B * 3 * HW;
+  tp.sampled = (t > 0 && bt->true_token && !bt->true_token[t]) ? 1 : 0;
+  const float* x_j = tp.sampled ? T->tape[t - 1].xp : bt->images + static_cast<size_t>(t) * B * 3 * HW;
+  tp.xj = x_j;
   const float* m_j = bt->masks ? bt->masks + static_cast<size_t>(t) * B * HW : nullptr;
   const float* m_i = bt->masks ? bt->masks + static_cast<size_t>(t + 1) * B * HW : nullptr;
   const float* r_j = bt->states ? bt->states + static_cast<size_t>(t) * B * c.robot_dim : nullptr;
@@ -338,6 +348,7 @@ int train_forward_step(rac_handle* h, TrainState* T, const rac_train_batch* bt, 
     e.bias = L.bias; e.cout = 4; e.xpred_out = tp.x4;
     CKR(t_gemm(h, "train.frame.fwd", {B, 48, 64, 3, false}, {{tp.d5, 64}}, L.wp, 9 * 64, 16, 16, EPI_FRAME, e, st));
   }
+  CK(launch_composite(tp.x4, x_j, tp.xp, B, static_cast<int>(HW), st));
   // KL(posterior || prior) value (trainer.py:454-458)
   CK(launch_kl_loss(tp.mu, tp.lv, tp.mu_p, tp.lv_p, T->kl_tmp, static_cast<int64_t>(B) * z * 48, B, st));
   CK(launch_sum_f32(T->kl_tmp, 1, bt->losses + 1, st));
@@ -349,13 +360,16 @@ int train_backward_step(rac_handle* h, TrainState* T, const rac_train_batch* bt,
   const int B = T->cfg.batch, g = c.g_dim, z = c.z_dim;
   const size_t HW = 48 * 64;
   Tape& tp = T->tape[t];
-  const float* x_j = bt->images + static_cast<size_t>(t) * B * 3 * HW;
+  const float* x_j = tp.xj;
   const float* x_i = bt->images + static_cast<size_t>(t + 1) * B * 3 * HW;
+  const int S = T->cfg.steps;
+  const float* gp_in = (t + 1 < S && T->tape[t + 1].sampled) ? T->G_img[cur] : nullptr;
+  float* gxj_out = tp.sampled ? T->G_img[cur ^ 1] : nullptr;
   const float* m_j = bt->masks ? bt->masks + static_cast<size_t>(t) * B * HW : nullptr;
   const float* m_i = bt->masks ? bt->masks + static_cast<size_t>(t + 1) * B * HW : nullptr;
   // ---- reconstruction loss and its gradient w.r.t. the decoder logits (trainer.py:406-433)
   CK(launch_frame_loss(tp.x4, x_j, x_i, m_i, T->cfg.recon_kind, T->cfg.robot_pixel_weight, B, static_cast<int>(HW),
-                       T->loss_part, T->dy_b, st));
+                       T->loss_part, T->dy_b, gp_in, gxj_out, st));
   CK(launch_sum_f32(T->loss_part, B, bt->losses + 0, st));
   F32Seg seg[3];
   // ---- decoder
@@ -443,6 +457,11 @@ int train_backward_step(rac_handle* h, TrainState* T, const rac_train_batch* bt,
                      T->grads + L.d.gamma_off, T->grads + L.d.beta_off, st));
     CK(launch_first_wgrad(tp.img4, c.use_mask ? m_j : nullptr, (c.use_mask && c.use_future_mask) ? m_i : nullptr,
                           static_cast<long long>(HW), T->draw32, T->grads + L.d.w_off, B, 48, 64, h->enc_cin, st));
+    // a model-sampled input frame also receives gradient through the encoder (zeroed robot pixels get none)
+    if (tp.sampled && T->dbg_keep)
+      CK(cudaMemcpyAsync(T->dbg_draw32, T->draw32, sizeof(float) * static_cast<size_t>(B) * HW * 64, cudaMemcpyDeviceToDevice, st));
+    if (tp.sampled)
+      CK(launch_first_dgrad(T->draw32, T->wfirst, h->enc_cin, T->cfg.zero_robot ? m_j : nullptr, gxj_out, B, 48, 64, st));
   }
   return RAC_OK;
 }
@@ -471,6 +490,7 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
   h->train = T;
   T->cfg = *cfg;
   T->params = params; T->buffers = buffers; T->grads = grads; T->m = adam_m; T->v = adam_v;
+  if (const char* dk = getenv("RAC_TRAIN_DEBUG_KEEP")) T->dbg_keep = atoi(dk);
   const int B = cfg->batch, S = cfg->steps, g = h->cfg.g_dim, z = h->cfg.z_dim;
   const size_t M0 = static_cast<size_t>(B) * 3072, M1 = static_cast<size_t>(B) * 768, M2 = static_cast<size_t>(B) * 192,
                M3 = static_cast<size_t>(B) * 48;
@@ -539,6 +559,7 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
       tp.mu_p = bp.take<float>(zn); tp.lv_p = bp.take<float>(zn); tp.mu = bp.take<float>(zn); tp.lv = bp.take<float>(zn);
       tp.eps_p = bp.take<float>(zn); tp.eps_q = bp.take<float>(zn);
       tp.x4 = bp.take<float>(M0 * 4);
+      tp.xp = bp.take<float>(M0 * 3);
     }
     T->G_d5 = bp.take<float>(M0 * 64); T->G_cat5 = bp.take<float>(M0 * 128); T->G_d4a = bp.take<float>(M1 * 128);
     T->G_cat4 = bp.take<float>(M1 * 256); T->G_d3b = bp.take<float>(M2 * 256); T->G_d3a = bp.take<float>(M2 * 256);
@@ -560,6 +581,8 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
     T->bn_scratch = bp.take<float>(2 * 2048);
     T->draw32 = bp.take<float>(M0 * 64);
     T->hzero = bp.take<bf16>(M3 * g); T->czero = bp.take<float>(M3 * g);
+    T->G_img[0] = bp.take<float>(M0 * 3); T->G_img[1] = bp.take<float>(M0 * 3);
+    T->dbg_draw32 = bp.take<float>(M0 * 64);
     T->loss_part = bp.take<float>(B); T->kl_tmp = bp.take<float>(4);
     if (!pass) {
       CK(cudaMalloc(&T->arena, bp.off + 1024));
@@ -641,7 +664,8 @@ int rac_train_debug_buffer(rac_handle* h, const char* name, int step, void** ptr
       {"img4", tp.img4}, {"a1", tp.a1}, {"cat5", tp.cat5}, {"p1", tp.p1}, {"a2", tp.a2}, {"cat4", tp.cat4},
       {"p2", tp.p2}, {"a3a", tp.a3a}, {"a3b", tp.a3b}, {"cat3", tp.cat3}, {"p3", tp.p3}, {"a4a", tp.a4a},
       {"a4b", tp.a4b}, {"h4", tp.h4}, {"d2a", tp.d2a}, {"d2b", tp.d2b}, {"d3a", tp.d3a}, {"d3b", tp.d3b},
-      {"d4a", tp.d4a}, {"d5", tp.d5}, {"x4", tp.x4}, {"hfp1", tp.hs[2][1]}};
+      {"d4a", tp.d4a}, {"d5", tp.d5}, {"x4", tp.x4}, {"hfp1", tp.hs[2][1]}, {"xp", tp.xp},
+      {"G_img0", T->G_img[0]}, {"G_img1", T->G_img[1]}, {"dbg_draw32", T->dbg_draw32}};
   for (auto& e : tab)
     if (!strcmp(e.n, name)) { *ptr = e.p; return RAC_OK; }
   if (!strncmp(name, "raw", 3)) {

@@ -424,7 +424,7 @@ cudaError_t launch_gauss_bwd(const float* dz, const float* mu, const float* lv, 
 __global__ void __launch_bounds__(1024)
 frame_loss_kernel(const float* __restrict__ x4, const float* __restrict__ xj, const float* __restrict__ xi,
                   const float* __restrict__ mask, int kind, float rw, int B, int HW, float* __restrict__ loss_out,
-                  __nv_bfloat16* __restrict__ dlogit) {
+                  __nv_bfloat16* __restrict__ dlogit, const float* __restrict__ gp_in, float* __restrict__ gxj_out) {
   __shared__ double sh[32];
   __shared__ float s_scale;
   const int b = blockIdx.x;
@@ -463,7 +463,9 @@ frame_loss_kernel(const float* __restrict__ x4, const float* __restrict__ xj, co
       const float diff = (t - pr) * w;
       acc += fabsf(diff);
       const float sg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
-      const float dp = -sg * w * scale;           // dL / d pred
+      float dp = -sg * w * scale;                 // dL / d pred
+      if (gp_in) dp += gp_in[(static_cast<size_t>(b) * 3 + c) * HW + p];
+      if (gxj_out) gxj_out[(static_cast<size_t>(b) * 3 + c) * HW + p] = dp * (1.f - mh);
       dm += dp * (xh - j);
       dl[c] = dp * mh * xh * (1.f - xh);
     }
@@ -478,9 +480,64 @@ frame_loss_kernel(const float* __restrict__ x4, const float* __restrict__ xj, co
 }
 cudaError_t launch_frame_loss(const float* x4, const float* xj, const float* xi, const float* mask, int kind,
                               float robot_weight, int B, int HW, float* loss_out, __nv_bfloat16* dlogit,
-                              cudaStream_t s) {
+                              const float* gp_in, float* gxj_out, cudaStream_t s) {
   if (kind == 1 && !mask) return cudaErrorInvalidValue;
-  frame_loss_kernel<<<B, 1024, 0, s>>>(x4, xj, xi, mask, kind, robot_weight, B, HW, loss_out, dlogit);
+  frame_loss_kernel<<<B, 1024, 0, s>>>(x4, xj, xi, mask, kind, robot_weight, B, HW, loss_out, dlogit, gp_in, gxj_out);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+composite_kernel(const float* __restrict__ x4, const float* __restrict__ xj, float* __restrict__ xp, int B, int HW) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // (b, c, p)
+  if (i >= static_cast<size_t>(B) * 3 * HW) return;
+  const int p = static_cast<int>(i % HW);
+  const int c = static_cast<int>((i / HW) % 3);
+  const size_t b = i / (static_cast<size_t>(HW) * 3);
+  const float mh = x4[(b * 4 + 3) * HW + p];
+  xp[i] = (1.f - mh) * xj[i] + mh * x4[(b * 4 + c) * HW + p];
+}
+cudaError_t launch_composite(const float* x4, const float* xj, float* xp, int B, int HW, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(B) * 3 * HW;
+  composite_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(x4, xj, xp, B, HW);
+  return cudaGetLastError();
+}
+
+// out[p] = sum_tap in[p + off(tap)] * w[tap]  =>  d in[q] = sum_tap d out[q - off(tap)] * w[tap]
+__global__ void __launch_bounds__(256)
+first_dgrad_kernel(const float* __restrict__ draw, const float* __restrict__ wf, int cin,
+                   const float* __restrict__ zero_mask, float* __restrict__ gimg, int B, int H, int W) {
+  __shared__ float sw[9 * 3 * 64];
+  for (int i = threadIdx.x; i < 9 * 3 * 64; i += blockDim.x) {
+    const int o = i & 63, c = (i >> 6) % 3, tap = (i >> 6) / 3;
+    sw[i] = wf[(tap * cin + c) * 64 + o];
+  }
+  __syncthreads();
+  const size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(B) * H * W;
+  if (pix >= total) return;
+  const int x = static_cast<int>(pix % W), y = static_cast<int>((pix / W) % H);
+  const size_t b = pix / (static_cast<size_t>(W) * H);
+  if (zero_mask && zero_mask[pix] != 0.f) return;
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = y - (tap / 3 - 1), xx = x - (tap % 3 - 1);
+    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+    const float* d = draw + ((b * H + yy) * W + xx) * 64;
+    const float* w0 = &sw[(tap * 3) * 64];
+    for (int o = 0; o < 64; ++o) {
+      const float dv = d[o];
+      acc[0] += dv * w0[o];
+      acc[1] += dv * w0[64 + o];
+      acc[2] += dv * w0[128 + o];
+    }
+  }
+  const size_t hw = static_cast<size_t>(H) * W, pos = static_cast<size_t>(y) * W + x;
+  for (int c = 0; c < 3; ++c) gimg[(b * 3 + c) * hw + pos] += acc[c];
+}
+cudaError_t launch_first_dgrad(const float* draw, const float* wf, int cin, const float* zero_mask, float* gimg, int B,
+                               int H, int W, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(B) * H * W;
+  first_dgrad_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(draw, wf, cin, zero_mask, gimg, B, H, W);
   return cudaGetLastError();
 }
 

@@ -12,10 +12,13 @@ nn.Parameters are VIEWS into them, so `model.state_dict()` / checkpoints always 
 Data parallel (new, the reference is single-process): pass `process_group`; every rank runs its own batch of B, the
 flat gradient buffer is all-reduced (NCCL) and averaged before the Adam update, BatchNorm statistics stay per rank.
 
-Limits (raise): scheduled sampling with model-sampled frames, heatmaps, multiview, movement weighting.
+Scheduled sampling follows the reference (same probability schedule, same global numpy generator); when the model's
+own prediction is fed back, its gradient flows into the previous step as in the reference (`x_pred.clone()`).
+Limits (raise): heatmaps, multiview, movement weighting, n_past != 1, last_frame_skip False.
 """
 import ctypes as C
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -105,7 +108,8 @@ class RacTrainConfig(C.Structure):
 
 class RacTrainBatch(C.Structure):
     _fields_ = [("images", C.c_void_p), ("masks", C.c_void_p), ("states", C.c_void_p), ("actions", C.c_void_p),
-                ("eps_prior", C.c_void_p), ("eps_post", C.c_void_p), ("seed", C.c_ulonglong), ("losses", C.c_void_p)]
+                ("eps_prior", C.c_void_p), ("eps_post", C.c_void_p), ("seed", C.c_ulonglong), ("losses", C.c_void_p),
+                ("true_token", C.c_void_p)]
 
 
 class SVGTrainer:
@@ -117,8 +121,9 @@ class SVGTrainer:
         self.n_past = getattr(config, "n_past", 1)
         if self.n_past != 1:
             raise NotImplementedError("n_past must be 1 (the reference training recipe, README.md:103)")
-        if getattr(config, "scheduled_sampling", False):
-            raise NotImplementedError("scheduled sampling with model-sampled frames is not implemented on the B200 path")
+        self._scheduled_sampling = bool(getattr(config, "scheduled_sampling", False))
+        self._ss_k = float(getattr(config, "scheduled_sampling_k", 4000))
+        self._forced_tokens = None
         kind = c.reconstruction_loss
         if kind not in ("l1", "dontcare_l1"):
             raise NotImplementedError(f"reconstruction_loss {kind!r}: the B200 path implements l1 and dontcare_l1")
@@ -184,6 +189,20 @@ class SVGTrainer:
         self._eps = None
         self._step = 0
 
+    # ---- scheduled sampling (reference trainer.py:132-147): same formula, same use of the global numpy generator
+    def _schedule_prob(self):
+        use_truth = self._ss_k / (self._ss_k + np.exp(self._step / self._ss_k))
+        return [use_truth, 1 - use_truth]
+
+    def _use_true_token(self):
+        if not self._scheduled_sampling:
+            return True
+        return bool(np.random.choice([True, False], p=self._schedule_prob()))
+
+    def set_true_tokens(self, tokens):
+        """Test hook: per-step decisions (index 0 is ignored, the first frame is always ground truth) for the next step."""
+        self._forced_tokens = tokens
+
     def set_noise(self, eps_prior, eps_post):
         """Test hook: (T-1, B, z_dim, 6, 8) reparameterisation noise for the next step (prior drawn first, lstm.py:276-279)."""
         self._eps = (eps_prior, eps_post)
@@ -213,9 +232,15 @@ class SVGTrainer:
         if self._eps is not None:
             eps_p, eps_q = f32(self._eps[0]), f32(self._eps[1])
             self._eps = None
+        if self._forced_tokens is not None:
+            decisions, self._forced_tokens = [bool(x) for x in self._forced_tokens], None
+        else:  # one draw per step i > 1, in step order, exactly as the reference loop (trainer.py:352-356)
+            decisions = [True] + [self._use_true_token() for _ in range(1, T - 1)]
+        tokens = np.ascontiguousarray(np.array([1] + [int(d) for d in decisions[1:T - 1]], dtype=np.int32))
         bt = RacTrainBatch(images=_lib.ptr(images), masks=_lib.ptr(masks), states=_lib.ptr(states),
                            actions=_lib.ptr(actions), eps_prior=_lib.ptr(eps_p), eps_post=_lib.ptr(eps_q),
-                           seed=self._seed, losses=_lib.ptr(self.losses))
+                           seed=self._seed, losses=_lib.ptr(self.losses),
+                           true_token=None if all(tokens) else tokens.ctypes.data)
         _lib.check(self._lib.rac_train_forward_backward(m.handle, C.byref(bt), _lib.stream_ptr()), m.handle,
                    "rac_train_forward_backward")
         self._keep_batch = (images, actions, masks, states, eps_p, eps_q)  # alive until the stream has consumed them

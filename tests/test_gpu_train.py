@@ -42,7 +42,7 @@ def _setup(tag, n_future, lr=1e-3, beta=1e-2):
     model.load_state_dict(sd)
     model.train()
     trainer = SVGTrainer(cfg, model)
-    batch, ep, eq = make_batch(23, cfg, tag == "ra")
+    batch, ep, eq = make_batch(23, cfg, tag != "vanilla")
     T = n_future + 1
     batch = {k: (v[:T] if k != "actions" else v[:T - 1]) for k, v in batch.items()}
     return cfg, sd, model, trainer, batch, ep[:T - 1], eq[:T - 1]
@@ -52,12 +52,15 @@ def _rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-20))
 
 
-@pytest.mark.parametrize("tag", ["vanilla", "ra"])
+@pytest.mark.parametrize("tag", ["vanilla", "ra", "ra_sampled"])
 def test_train_step_losses_smooth_grads_adam(golden_dir, tag):
     gold = np.load(os.path.join(golden_dir, f"train_{tag}.npz"))
     cfg, sd, model, trainer, batch, ep, eq = _setup(tag, 3)
     oracle = TrainOracle(cfg, sd, lr=1e-3, beta=1e-2)
-    info, ref = oracle.loss_and_grads(batch, ep, eq)
+    tokens = [True, False, False] if tag.endswith("sampled") else None  # scheduled sampling: model frame at i > 1
+    info, ref = oracle.loss_and_grads(batch, ep, eq, true_token=None if tokens is None else tokens + [False])
+    if tokens is not None:
+        trainer.set_true_tokens(tokens)
     trainer.set_noise(ep, eq)
     losses = trainer.forward_backward(batch).cpu().numpy()
     # losses against the reference trainer itself
@@ -66,8 +69,8 @@ def test_train_step_losses_smooth_grads_adam(golden_dir, tag):
     # smooth-path gradients
     for k in oracle.param_keys:
         g = trainer.grad_of(k).cpu()
-        if k.startswith("prior.") or k.startswith("prior_input_conv"):
-            assert _rel(g, ref[k]) < 2e-2, (k, _rel(g, ref[k]))
+        if (k.startswith("prior.") or k.startswith("prior_input_conv")) and tokens is None:
+            assert _rel(g, ref[k]) < 2e-2, (k, _rel(g, ref[k]))  # (with sampled frames the prior input is chaotic too)
         # global sanity for every tensor: right scale and direction (chaos-limited, see module docstring)
         cos = float((g * ref[k]).sum() / (g.norm() * ref[k].norm() + 1e-30))
         assert cos > 0.85 and 0.8 < float(g.norm() / ref[k].norm()) < 1.25, (k, cos)
@@ -89,6 +92,8 @@ def test_train_step_losses_smooth_grads_adam(golden_dir, tag):
         if "running_" in k:
             np.testing.assert_allclose(v.cpu().numpy(), oracle.model.sd[k].numpy(), rtol=2e-2, atol=2e-3)
     # reference-style wrapper: second step returns the logged (averaged) losses
+    if tokens is not None:
+        trainer.set_true_tokens(tokens)
     trainer.set_noise(ep, eq)
     out = trainer.train_step(batch)
     assert set(out) == {"recon_loss", "kld"} and np.isfinite(out["recon_loss"]) and np.isfinite(out["kld"])
@@ -192,6 +197,31 @@ def test_backward_is_locally_exact_on_its_own_tape():
     pool_check(cat5, Gcat5, dx5, G("G_p1", (B, 24, 32, 64)), 64)
     pool_check(cat4, Gcat4, dx4, G("G_p2", (B, 12, 16, 128)), 128)
     pool_check(cat3, Gcat3, dx3, G("G_p3", (B, 6, 8, 256)), 256)
+
+
+def test_sampled_frame_gradient_is_locally_exact(monkeypatch):
+    """Scheduled sampling with the model's own frame at step 1 (T = 3): the gradient handed back to step 0's
+    prediction = composite path (1 - m) * dL/dpred + encoder path (dgrad of encoder.c1.0, robot pixels masked),
+    re-derived with torch from the CUDA path's own tensors."""
+    monkeypatch.setenv("RAC_TRAIN_DEBUG_KEEP", "1")
+    cfg, sd, model, trainer, batch, ep, eq = _setup("ra", 2)
+    trainer.set_true_tokens([True, False])
+    trainer.set_noise(ep, eq)
+    trainer.forward_backward(batch)
+    torch.cuda.synchronize()
+    HW = 48 * 64
+    x4 = _tape(trainer, "x4", (B, 4, 48, 64), step=1, bf16=False)
+    xj = _tape(trainer, "xp", (B, 3, 48, 64), step=0, bf16=False).requires_grad_(True)
+    pred = (1 - x4[:, 3:4]) * xj + x4[:, 3:4] * x4[:, :3]
+    so.dontcare_l1_criterion(pred, batch["images"][2], batch["masks"][2], 0.0).backward()
+    comp = xj.grad.clone()
+    draw = _tape(trainer, "dbg_draw32", (B, 48, 64, 64), bf16=False).permute(0, 3, 1, 2).contiguous()
+    w0 = sd["encoder.c1.0.main.0.weight"]  # (64, 5, 3, 3): rgb + mask_t + mask_t+1
+    gin = torch.nn.grad.conv2d_input((B, w0.shape[1], 48, 64), w0, draw, padding=1)[:, :3]
+    gin = gin * (1 - batch["masks"][1])  # zero_robot_region(m_j, x_j) blocks the gradient on robot pixels
+    got = _tape(trainer, "G_img1", (B, 3, 48, 64), bf16=False)
+    assert _rel(got, comp + gin) < 1e-3
+    assert float(gin.norm()) > 0 and float(comp.norm()) > 0
 
 
 def test_train_oracle_bf16_sensitivity_is_inherent():

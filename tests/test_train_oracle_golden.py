@@ -12,7 +12,7 @@ from oracle.make_golden_train import make_batch, summarize
 from oracle.train_oracle import TrainOracle
 
 
-@pytest.mark.parametrize("tag", ["vanilla", "ra"])
+@pytest.mark.parametrize("tag", ["vanilla", "ra", "ra_sampled"])
 def test_train_step_matches_reference(golden_dir, tag):
     gold = np.load(os.path.join(golden_dir, f"train_{tag}.npz"))
     if tag == "vanilla":
@@ -21,9 +21,10 @@ def test_train_step_matches_reference(golden_dir, tag):
         cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, model_use_mask=True, model_use_future_mask=True,
                           model_use_robot_state=True, reconstruction_loss="dontcare_l1", reward_type="dontcare")
     tr = TrainOracle(cfg, so.make_state_dict(cfg, int(gold["weight_seed"])), lr=float(gold["lr"]), beta=float(gold["beta"]))
-    batch, eps_p, eps_q = make_batch(int(gold["input_seed"]), cfg, tag == "ra")
+    batch, eps_p, eps_q = make_batch(int(gold["input_seed"]), cfg, tag != "vanilla")
+    tokens = [True, False, False, False] if tag.endswith("sampled") else None  # model frame at every step i > 1
     for step in range(2):
-        info, grads = tr.train_step(batch, eps_p, eps_q)
+        info, grads = tr.train_step(batch, eps_p, eps_q, true_token=tokens)
         np.testing.assert_allclose(info["recon_loss"], gold[f"recon{step}"], rtol=2e-5)
         np.testing.assert_allclose(info["kld"], gold[f"kld{step}"], rtol=2e-4)
         keys, gn, gs = summarize(grads)
