@@ -182,6 +182,38 @@ def cost_kernel_roofline(dev, hbm_peak, n=16384, reps=20):
             "candidate_steps_per_sec": n / (ms * 1e-3)}
 
 
+def run_train_reference_arm(args):
+    """BASELINE configs[0]: one l1 forward+backward(+Adam) step of the SVG model on the host cores (CPU port of the
+    reference trainer, oracle/train_oracle.py, pinned to the reference's own outputs)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import svg_oracle as so
+    from oracle.train_oracle import TrainOracle
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, action_dim=A_DIM)
+    tr = TrainOracle(cfg, so.make_state_dict(cfg, 0), lr=1e-4, beta=1e-4)
+    Bt, T = 16, 6
+    g = torch.Generator().manual_seed(0)
+    batch = {"images": torch.rand(T, Bt, 3, 48, 64, generator=g), "actions": torch.rand(T - 1, Bt, A_DIM, generator=g) * 0.1 - 0.05,
+             "states": torch.rand(T, Bt, 5, generator=g), "masks": torch.zeros(T, Bt, 1, 48, 64)}
+    eps = torch.randn(2, T - 1, Bt, Z_DIM, 6, 8, generator=g)
+    steps = max(1, min(args.steps, 2))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.train_step(batch, eps[0], eps[1])
+    per = (time.perf_counter() - t0) / steps
+    print(json.dumps({"impl": "reference", "metric": "svg_train_samples_per_sec", "value": Bt / per, "unit": "samples/s",
+                      "n_gpus": args.gpus, "steps": steps, "warmup": 0, "ms_per_step": per * 1e3, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": f"SVG training step, batch {Bt}, n_past 1 / n_future 5, g_dim {G_DIM} z_dim {Z_DIM}, l1, Adam"},
+                      "cpu_baseline": {"value": Bt / per, "unit": "samples/s", "cores": threads, "kind": "port",
+                                       "sample": f"{steps} full step(s) of batch {Bt}"},
+                      "e2e": {"value": Bt / per, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0}))
+
+
 def run_train_bench(args):
     """Extra (not the headline metric): samples/s of the SVG training step, one JSON line."""
     os.environ["NCCL_DEBUG"] = os.environ.get("RAC_NCCL_DEBUG", "WARN")
@@ -272,6 +304,8 @@ def main():
                     help="BASELINE configs[4]: model_use_robot_state + model_use_mask(+future mask), dontcare cost, "
                          "synthetic per-candidate robot states / rectangle masks resident on the device")
     args = ap.parse_args()
+    if args.impl == "reference" and args.train:
+        return run_train_reference_arm(args)
     if args.impl == "reference":
         return run_reference_arm(args)
     if args.train:

@@ -171,6 +171,9 @@ int rac_masked_cost(const float* curr, const float* goal, const float* curr_mask
 int rac_l1_loss(const float* pred, const float* target, float* out, int64_t numel, void* stream);
 int rac_dontcare_l1_loss(const float* pred, const float* target, const float* mask, float robot_weight, float* out,
                          int n, int hw, void* stream);
+/* robot_mse_criterion / world_mse_criterion (losses.py:52-78): out2[0] += robot, out2[1] += world (accumulating). */
+int rac_robot_world_mse(const float* pred, const float* target, const float* mask, float* out2, int n, int hw,
+                        void* stream);
 int rac_kl_loss(const float* mu1, const float* logvar1, const float* mu2, const float* logvar2, float* out,
                 int64_t numel, int batch, void* stream);
 
@@ -212,7 +215,8 @@ typedef struct {
   const float* eps_prior;  /* (steps, B, z_dim, H/8, W/8) or NULL -> Philox(seed) */
   const float* eps_post;
   unsigned long long seed;
-  float* losses;           /* out, device float[2]: sum over steps of the reconstruction loss, of the KL term */
+  float* losses;           /* out, device float[4]: sums over steps of reconstruction loss, KL term, and (when masks
+                              are given) the logged robot_mse / world_mse metrics (trainer.py:436-439) */
   const int* true_token;   /* HOST int[steps] or NULL: 0 at step t >= 1 = feed the model's own previous prediction
                               (scheduled sampling, trainer.py:132-147,353-356); NULL = always the ground-truth frame */
 } rac_train_batch;

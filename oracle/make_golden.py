@@ -222,6 +222,8 @@ def main():
         "dontcare_l1_w0": losses.dontcare_l1_criterion(pred.clone(), curr.clone(), cmask, 0.0).numpy(),
         "dontcare_l1_w05": losses.dontcare_l1_criterion(pred.clone(), curr.clone(), cmask, 0.5).numpy(),
         "kl": losses.kl_criterion(mu1, lv1, mu2, lv2, B).numpy(),
+        "robot_mse": losses.robot_mse_criterion(pred.clone(), curr.clone(), cmask).numpy(),
+        "world_mse": losses.world_mse_criterion(pred.clone(), curr.clone(), cmask).numpy(),
     }
     # top-k: torch.topk (cem.py:97) on vectors without ties at the K boundary; torch.sort(stable) for the tie rule
     rs = np.random.RandomState(7)

@@ -80,6 +80,8 @@ def main():
             bkeys, bn, _ = summarize(bufs)
             out[f"recon{step}"] = losses["recon_loss"] * cfg.n_future  # undo the logging average (trainer.py:463-464)
             out[f"kld{step}"] = losses["kld"] * cfg.n_future
+            out[f"robot{step}"] = losses["robot_loss"] * cfg.n_future  # logged metrics (trainer.py:436-439)
+            out[f"world{step}"] = losses["world_loss"] * cfg.n_future
             out[f"grad_norm{step}"], out[f"grad_sample{step}"] = gn, gs
             out[f"param_norm{step}"], out[f"param_sample{step}"] = pn, ps
             out[f"running_norm{step}"] = bn

@@ -318,6 +318,15 @@ def dontcare_l1_criterion(pred, target, mask, robot_weight):
     return (diff.abs().sum((1, 2, 3)) / world).mean()
 
 
+def robot_world_mse(pred, target, mask):
+    """robot_mse_criterion / world_mse_criterion (losses.py:52-78)."""
+    m3 = mask.bool().expand(-1, 3, -1, -1)
+    d2 = (target - pred) ** 2
+    robot = (torch.where(m3, d2, torch.zeros_like(d2)).sum((1, 2, 3)) / (m3.sum((1, 2, 3)) + 1)).mean()
+    world = (torch.where(m3, torch.zeros_like(d2), d2).sum((1, 2, 3)) / ((~m3).sum((1, 2, 3)) + 1)).mean()
+    return robot, world
+
+
 def kl_criterion(mu1, logvar1, mu2, logvar2, bs):
     """losses.py:97-106."""
     s1, s2 = torch.exp(0.5 * logvar1), torch.exp(0.5 * logvar2)

@@ -333,6 +333,43 @@ cudaError_t launch_dontcare_l1_loss(const float* pred, const float* target, cons
   dontcare_l1_kernel<<<1, 1024, 0, s>>>(pred, target, mask, robot_weight, out, B, HW);
   return cudaGetLastError();
 }
+// robot_mse_criterion / world_mse_criterion (losses.py:52-78): per sample sum(diff^2) over robot (world) pixels of
+// all 3 channels / (#those elements + 1), mean over the batch. out[0] += robot, out[1] += world.
+__global__ void __launch_bounds__(1024)
+robot_world_mse_kernel(const float* __restrict__ p, const float* __restrict__ t, const float* __restrict__ mask,
+                       float* __restrict__ out, int B, int HW) {
+  __shared__ double sh[32];
+  double tot_r = 0.0, tot_w = 0.0;
+  for (int b = 0; b < B; ++b) {
+    double sr = 0.0, sw = 0.0, cr = 0.0;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      const bool rb = mask[static_cast<size_t>(b) * HW + i] != 0.f;
+      float sd = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const size_t q = (static_cast<size_t>(b) * 3 + c) * HW + i;
+        const float d = t[q] - p[q];
+        sd += d * d;
+      }
+      if (rb) { sr += sd; cr += 3.0; } else { sw += sd; }
+    }
+    sr = block_sum(sr, sh);
+    sw = block_sum(sw, sh);
+    cr = block_sum(cr, sh);
+    tot_r += sr / (cr + 1.0);
+    tot_w += sw / (3.0 * HW - cr + 1.0);
+  }
+  if (threadIdx.x == 0) {
+    out[0] += static_cast<float>(tot_r / B);
+    out[1] += static_cast<float>(tot_w / B);
+  }
+}
+cudaError_t launch_robot_world_mse(const float* pred, const float* target, const float* mask, float* out2, int B,
+                                   int HW, cudaStream_t s) {
+  robot_world_mse_kernel<<<1, 1024, 0, s>>>(pred, target, mask, out2, B, HW);
+  return cudaGetLastError();
+}
+
 __global__ void __launch_bounds__(1024)
 kl_loss_kernel(const float* __restrict__ mu1, const float* __restrict__ lv1, const float* __restrict__ mu2,
                const float* __restrict__ lv2, float* __restrict__ out, long long n, int bs) {

@@ -39,6 +39,9 @@ cudaError_t launch_masked_cost(const float* curr, const float* goal, const float
 cudaError_t launch_l1_loss(const float* pred, const float* target, float* out, int64_t n, cudaStream_t s);
 cudaError_t launch_dontcare_l1_loss(const float* pred, const float* target, const float* mask, float robot_weight,
                                     float* out, int B, int HW, cudaStream_t s);
+// out2[0] += robot_mse_criterion, out2[1] += world_mse_criterion (losses.py:52-78)
+cudaError_t launch_robot_world_mse(const float* pred, const float* target, const float* mask, float* out2, int B,
+                                   int HW, cudaStream_t s);
 cudaError_t launch_kl_loss(const float* mu1, const float* lv1, const float* mu2, const float* lv2, float* out,
                            int64_t n, int bs, cudaStream_t s);
 

@@ -896,6 +896,11 @@ int rac_dontcare_l1_loss(const float* pred, const float* target, const float* ma
   if (!pred || !target || !mask || !out || n < 1) return RAC_ERR_INVALID;
   return launch_dontcare_l1_loss(pred, target, mask, robot_weight, out, n, hw, static_cast<cudaStream_t>(stream)) == cudaSuccess ? RAC_OK : RAC_ERR_CUDA;
 }
+int rac_robot_world_mse(const float* pred, const float* target, const float* mask, float* out2, int n, int hw,
+                        void* stream) {
+  if (!pred || !target || !mask || !out2 || n < 1) return RAC_ERR_INVALID;
+  return launch_robot_world_mse(pred, target, mask, out2, n, hw, static_cast<cudaStream_t>(stream)) == cudaSuccess ? RAC_OK : RAC_ERR_CUDA;
+}
 int rac_kl_loss(const float* mu1, const float* logvar1, const float* mu2, const float* logvar2, float* out,
                 int64_t numel, int batch, void* stream) {
   if (!mu1 || !logvar1 || !mu2 || !logvar2 || !out || numel < 1 || batch < 1) return RAC_ERR_INVALID;

@@ -349,6 +349,9 @@ int train_forward_step(rac_handle* h, TrainState* T, const rac_train_batch* bt, 
     CKR(t_gemm(h, "train.frame.fwd", {B, 48, 64, 3, false}, {{tp.d5, 64}}, L.wp, 9 * 64, 16, 16, EPI_FRAME, e, st));
   }
   CK(launch_composite(tp.x4, x_j, tp.xp, B, static_cast<int>(HW), st));
+  if (m_i)  // logging metrics of the reference step (trainer.py:436-439)
+    CK(launch_robot_world_mse(tp.xp, bt->images + static_cast<size_t>(t + 1) * B * 3 * HW, m_i, bt->losses + 2, B,
+                              static_cast<int>(HW), st));
   // KL(posterior || prior) value (trainer.py:454-458)
   CK(launch_kl_loss(tp.mu, tp.lv, tp.mu_p, tp.lv_p, T->kl_tmp, static_cast<int64_t>(B) * z * 48, B, st));
   CK(launch_sum_f32(T->kl_tmp, 1, bt->losses + 1, st));
@@ -619,7 +622,7 @@ int rac_train_forward_backward(rac_handle* h, const rac_train_batch* bt, void* s
   }
   CK(launch_pack_first(T->params + T->L[RAC_L_ENC_C1_0].d.w_off, h->enc_cin, T->wfirst, st));
   CK(cudaMemsetAsync(T->grads, 0, sizeof(float) * T->cfg.n_params, st));
-  CK(cudaMemsetAsync(bt->losses, 0, sizeof(float) * 2, st));
+  CK(cudaMemsetAsync(bt->losses, 0, sizeof(float) * 4, st));
   const size_t zn = static_cast<size_t>(B) * z * 48;
   for (int t = 0; t < S; ++t) {
     Tape& tp = T->tape[t];

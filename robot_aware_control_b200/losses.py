@@ -141,6 +141,26 @@ def dontcare_l1_criterion(prediction, target, mask, robot_weight, batch_weight=N
     return out[0]
 
 
+def _robot_world_mse(prediction, target, mask):
+    lib = _lib.load()
+    p, t, m = _dev(prediction), _dev(target), _dev(mask)
+    n, _, h, w = p.shape
+    out = torch.zeros(2, device="cuda")
+    _lib.check(lib.rac_robot_world_mse(_lib.ptr(p), _lib.ptr(t), _lib.ptr(m), _lib.ptr(out), n, h * w,
+                                       _lib.stream_ptr()), None, "rac_robot_world_mse")
+    return out
+
+
+def robot_mse_criterion(prediction, target, mask):
+    """losses.py:52-64."""
+    return _robot_world_mse(prediction, target, mask)[0]
+
+
+def world_mse_criterion(prediction, target, mask):
+    """losses.py:66-78."""
+    return _robot_world_mse(prediction, target, mask)[1]
+
+
 def kl_criterion(mu1, logvar1, mu2, logvar2, bs):
     assert mu1.shape[0] == bs, f"{mu1.shape[0]} != {bs}"
     lib = _lib.load()

@@ -159,7 +159,7 @@ class SVGTrainer:
         self.grads = torch.zeros(n, device=dev)
         self.adam_m = torch.zeros(n, device=dev)
         self.adam_v = torch.zeros(n, device=dev)
-        self.losses = torch.zeros(2, device=dev)
+        self.losses = torch.zeros(4, device=dev)
         self._tables = _layer_tables(model, self._offsets, self._boffsets)
         self._keep = []  # device index arrays referenced by the library
         layers = (RacTrainLayer * len(pack.LAYER_IDS))()
@@ -263,7 +263,10 @@ class SVGTrainer:
         self.optimizer_step()
         nf = batch["images"].shape[0] - 1
         vals = losses.cpu()
-        return {"recon_loss": float(vals[0]) / nf, "kld": float(vals[1]) / nf}
+        out = {"recon_loss": float(vals[0]) / nf, "kld": float(vals[1]) / nf}
+        if batch.get("masks") is not None:  # the reference logs these for every step (trainer.py:436-439)
+            out["robot_loss"], out["world_loss"] = float(vals[2]) / nf, float(vals[3]) / nf
+        return out
 
     def grad_of(self, key):
         o = self._offsets[key]

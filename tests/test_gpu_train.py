@@ -66,6 +66,8 @@ def test_train_step_losses_smooth_grads_adam(golden_dir, tag):
     # losses against the reference trainer itself
     np.testing.assert_allclose(losses[0], gold["recon0"], rtol=2e-3)
     np.testing.assert_allclose(losses[1], gold["kld0"], rtol=3e-3)
+    np.testing.assert_allclose(losses[2], gold["robot0"], rtol=5e-3)  # logged robot / world MSE (trainer.py:436-439)
+    np.testing.assert_allclose(losses[3], gold["world0"], rtol=5e-3)
     # smooth-path gradients
     for k in oracle.param_keys:
         g = trainer.grad_of(k).cpu()
