@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RAC_ABI_VERSION 1
+#define RAC_ABI_VERSION 2
 
 typedef enum {
   RAC_OK = 0,
@@ -46,6 +46,7 @@ typedef struct {
   int use_robot_state;         /* cfg.model_use_robot_state */
   int use_future_robot_state;  /* cfg.model_use_future_robot_state */
   int conv_impl;               /* 0 = tcgen05/TMA product path; 1 = SIMT cross-check kernel (tests only) */
+  int lstm_group_norm;         /* cfg.lstm_group_norm: NormConvLSTMCell instead of ConvLSTMCell (lstm.py:151-198,206) */
 } rac_config;
 
 /* Packed-layer ids: one per convolution of SVGConvModel (state_dict prefixes in SURVEY.md 8(a)). */
@@ -58,6 +59,13 @@ enum {
   RAC_L_DEC_UPC4_0, RAC_L_DEC_UPC4_1, RAC_L_DEC_UPC5_0, RAC_L_DEC_UPC5_1,
   RAC_L_POST_IN, RAC_L_POST_LSTM0, RAC_L_POST_LSTM1, RAC_L_POST_GAUSS,
   RAC_L_COUNT
+};
+/* cfg.lstm_group_norm only: the RAC_L_*_LSTMk ids above are then the `ih_gates.0` convolutions (g -> 4g) and the ids
+ * below the `hh_gates.0` convolutions of the same cells (lstm.py:163-171). */
+enum {
+  RAC_L_PRIOR_LSTM0_HH = RAC_L_COUNT, RAC_L_PRIOR_LSTM1_HH, RAC_L_FP_LSTM0_HH, RAC_L_FP_LSTM1_HH,
+  RAC_L_POST_LSTM0_HH, RAC_L_POST_LSTM1_HH,
+  RAC_L_COUNT_GN
 };
 
 int rac_abi_version(void);
@@ -75,6 +83,11 @@ int rac_layer_shape(const rac_handle* h, int layer, int64_t* w_elems, int64_t* b
 /* nn.Module.load_state_dict (widowx_VMPC_controller.py:98-101): one packed layer; the library copies into its own
  * device memory. `w` / `bias` may be host or device pointers (cudaMemcpyDefault). */
 int rac_load_layer(rac_handle* h, int layer, const void* w, int64_t w_elems, const float* bias, int64_t bias_elems);
+
+/* cfg.lstm_group_norm: GroupNorm affine parameters of one NormConvLSTMCell (lstm.py:163-172), `layer` = the cell's
+ * RAC_L_*_LSTMk id. `packed` (host or device, 18*g floats): [ih gamma | ih beta | hh gamma | hh beta], 4g each, in
+ * packed gate-column order (channel * 4 + gate), then [c_norm gamma | c_norm beta], g each. */
+int rac_load_lstm_norm(rac_handle* h, int layer, const float* packed, int64_t elems);
 
 /* Allocate activation workspace, recurrent state and TMA descriptors for `batch` candidates (idempotent). */
 int rac_prepare(rac_handle* h, int batch);

@@ -72,8 +72,17 @@ def state_dict_spec(cfg):
         spec[f"{prefix}.bias"] = (cout,)
 
     def convlstm(prefix):
-        conv(f"{prefix}.lstm.0.gates", 2 * g, 4 * g, 5)
-        conv(f"{prefix}.lstm.1.gates", 2 * g, 4 * g, 3)
+        for layer, k in ((0, 5), (1, 3)):
+            if getattr(cfg, "lstm_group_norm", False):
+                # NormConvLSTMCell (lstm.py:151-175): Sequential(Conv2d, GroupNorm(16, 4g)) x2 + GroupNorm(16, g)
+                for gate in ("ih_gates", "hh_gates"):
+                    conv(f"{prefix}.lstm.{layer}.{gate}.0", g, 4 * g, k)
+                    spec[f"{prefix}.lstm.{layer}.{gate}.1.weight"] = (4 * g,)
+                    spec[f"{prefix}.lstm.{layer}.{gate}.1.bias"] = (4 * g,)
+                spec[f"{prefix}.lstm.{layer}.c_norm.weight"] = (g,)
+                spec[f"{prefix}.lstm.{layer}.c_norm.bias"] = (g,)
+            else:
+                conv(f"{prefix}.lstm.{layer}.gates", 2 * g, 4 * g, k)
 
     nc = encoder_in_channels(cfg)
     for name, cin, cout in [("c1.0", nc, 64), ("c1.1", 64, 64), ("c2.0", 64, 128), ("c2.1", 128, 128),
@@ -121,7 +130,7 @@ def make_state_dict(cfg, seed=0):
             sd[key] = torch.rand(shape, generator=gen) + 0.5
         elif key.endswith("running_mean"):
             sd[key] = torch.randn(shape, generator=gen) * 0.1
-        elif ".main.1.weight" in key:
+        elif ".main.1.weight" in key or "_gates.1.weight" in key or key.endswith("c_norm.weight"):
             sd[key] = torch.rand(shape, generator=gen) + 0.5
         elif ".main.1.bias" in key:
             sd[key] = torch.randn(shape, generator=gen) * 0.1
@@ -211,12 +220,21 @@ class SVGOracle:
     # ConvLSTMCell.forward (lstm.py:129-149) x2, ConvLSTM.forward (lstm.py:252-257)
     def _convlstm(self, x, name):
         sd = self.sd
+        norm = getattr(self.cfg, "lstm_group_norm", False)
         for layer, pad in ((0, 2), (1, 1)):
             h_prev, c_prev = self.hidden[name][layer]
-            gates = F.conv2d(torch.cat([x, h_prev], 1), self._q(sd[f"{name}.lstm.{layer}.gates.weight"]),
-                             sd[f"{name}.lstm.{layer}.gates.bias"], 1, pad)
+            p = f"{name}.lstm.{layer}"
+            if norm:
+                # NormConvLSTMCell.forward (lstm.py:177-198): GroupNorm(16) on each gate convolution and on the cell
+                gates = sum(F.group_norm(F.conv2d(t, self._q(sd[f"{p}.{gk}.0.weight"]), sd[f"{p}.{gk}.0.bias"], 1, pad),
+                                         16, sd[f"{p}.{gk}.1.weight"], sd[f"{p}.{gk}.1.bias"], 1e-5)
+                            for gk, t in (("ih_gates", x), ("hh_gates", h_prev)))
+            else:
+                gates = F.conv2d(torch.cat([x, h_prev], 1), self._q(sd[f"{p}.gates.weight"]), sd[f"{p}.gates.bias"], 1, pad)
             i, f, o, g_ = gates.chunk(4, 1)
             c = torch.sigmoid(f) * c_prev + torch.sigmoid(i) * torch.tanh(g_)
+            if norm:
+                c = F.group_norm(c, 16, sd[f"{p}.c_norm.weight"], sd[f"{p}.c_norm.bias"], 1e-5)
             h = self._q(torch.sigmoid(o) * torch.tanh(c))
             self.hidden[name][layer] = (h, c)
             self._rec(f"{name}.h{layer}", h)

@@ -13,7 +13,7 @@ RAC_OK, RAC_ERR_INVALID, RAC_ERR_CUDA, RAC_ERR_STATE, RAC_ERR_UNSUPPORTED = 0, -
 class RacConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "image_height", "image_width", "g_dim", "z_dim", "action_dim", "robot_dim", "use_mask", "use_future_mask",
-        "use_robot_state", "use_future_robot_state", "conv_impl")]
+        "use_robot_state", "use_future_robot_state", "conv_impl", "lstm_group_norm")]
 
 
 class RacStep(C.Structure):
@@ -54,6 +54,7 @@ EXPORTS = {
     "rac_layer_shape": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                   C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rac_load_layer": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
+    "rac_load_lstm_norm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
     "rac_prepare": (C.c_int, [C.c_void_p, C.c_int]),
     "rac_init_hidden": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "rac_forward": (C.c_int, [C.c_void_p, C.POINTER(RacStep), C.c_void_p]),

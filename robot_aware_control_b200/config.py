@@ -29,8 +29,8 @@ def validate_model_config(c):
         raise ValueError(f"unsupported image size {c.image_height}x{c.image_width}: the B200 path handles 48x64")
     if c.model_use_heatmap:
         raise NotImplementedError("model_use_heatmap is outside the B200 hot path (SURVEY.md section 8)")
-    if c.lstm_group_norm:
-        raise NotImplementedError("lstm_group_norm (NormConvLSTMCell) is a 'next' row of SURVEY.md 8(f)")
+    if c.lstm_group_norm and (c.g_dim > 512 or c.g_dim % 64):
+        raise NotImplementedError("lstm_group_norm (NormConvLSTMCell) is implemented for g_dim <= 512")
     if c.g_dim % 64 != 0 or c.g_dim < 64:
         raise ValueError("g_dim must be a multiple of 64 for the tcgen05 tiles")
     if not 1 <= c.z_dim <= 64:

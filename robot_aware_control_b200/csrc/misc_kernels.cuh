@@ -45,6 +45,13 @@ cudaError_t launch_robot_world_mse(const float* pred, const float* target, const
 cudaError_t launch_kl_loss(const float* mu1, const float* lv1, const float* mu2, const float* lv2, float* out,
                            int64_t n, int bs, cudaStream_t s);
 
+// ---- NormConvLSTMCell pointwise part (norm_lstm.cu; reference lstm.py:177-198) ----
+// ih / hh: raw gate convolutions [B, P, 4*hid] fp32, packed column (channel, gate); gn_params: packed GroupNorm affine
+// [ih gamma | ih beta | hh gamma | hh beta] (4*hid each, packed column order) + [cell gamma | cell beta] (hid each)
+cudaError_t launch_norm_lstm_cell(const float* ih, const float* hh, const float* gn_params, float* c_state,
+                                  __nv_bfloat16* h_out, int B, int P, int hid, cudaStream_t s);
+cudaError_t norm_lstm_set_attributes();
+
 // ---- CEM (cem_kernels.cu) ----
 cudaError_t launch_cem_sample(const float* mean, const float* stdv, const float* noise, unsigned long long seed,
                               int iter, int n_total, int L, int adim_model, int cand_offset, int n_local,

@@ -62,6 +62,8 @@ struct Workspace {
   bool enc_built[2] = {false, false};
   ConvOp in_conv[3];     // prior_in, post_in, fp_in
   ConvOp lstm[3][2][2];  // [which][layer][parity]
+  ConvOp lstm_hh[3][2][2];  // lstm_group_norm: hh_gates convolution (lstm[][][] is then the ih_gates one)
+  float *gn_ih = nullptr, *gn_hh = nullptr;  // lstm_group_norm: raw gate convolutions [B, 48, 4g] fp32
   ConvOp gauss[2][2];    // [prior, post][parity]
   ConvOp dec[10][2];     // [layer][parity] (only dec[0] depends on parity)
   std::unordered_map<std::string, std::pair<void*, std::pair<int64_t, int>>> named;
@@ -77,8 +79,10 @@ struct rac_handle {
   int num_sms = 148;
   int H = 48, W = 64, hl = 6, wl = 8;
   int enc_cin = 3;
-  LayerSpec spec[RAC_L_COUNT];
-  Layer layer[RAC_L_COUNT];
+  LayerSpec spec[RAC_L_COUNT_GN];
+  Layer layer[RAC_L_COUNT_GN];
+  float* gn_params[3][2] = {};  // lstm_group_norm: packed GroupNorm affine per cell [prior, post, fp][layer]
+  int num_layers = RAC_L_COUNT;  // RAC_L_COUNT_GN with lstm_group_norm
   Workspace ws;
   int tile_m = 256;        // rows per CTA tile (RAC_TILE_M=128 selects the 128-row tiles, for A/B measurements)
   int cur[3] = {0, 0, 0};  // ping-pong index of the live hidden state per LSTM stack
@@ -162,6 +166,16 @@ void fill_specs(rac_handle* h) {
   set(RAC_L_POST_LSTM0, 5, 2 * g, 4 * g, 128);
   set(RAC_L_POST_LSTM1, 3, 2 * g, 4 * g, 128);
   set(RAC_L_POST_GAUSS, 3, g, 128, 128);
+  if (c.lstm_group_norm) {
+    // NormConvLSTMCell (lstm.py:163-171): separate ih / hh gate convolutions, each g -> 4g
+    const int ih[6] = {RAC_L_PRIOR_LSTM0, RAC_L_PRIOR_LSTM1, RAC_L_FP_LSTM0, RAC_L_FP_LSTM1, RAC_L_POST_LSTM0, RAC_L_POST_LSTM1};
+    for (int i = 0; i < 6; ++i) {
+      const int ks = (i & 1) ? 3 : 5;
+      set(ih[i], ks, g, 4 * g, 128);
+      set(RAC_L_PRIOR_LSTM0_HH + i, ks, g, 4 * g, 128);
+    }
+    h->num_layers = RAC_L_COUNT_GN;
+  }
 }
 
 int64_t spec_w_elems(const LayerSpec& s) {
@@ -215,7 +229,7 @@ int make_conv(rac_handle* h, ConvOp* op, const char* name, int layer, int H, int
   op->name = name;
   op->block_m = h->tile_m;
   op->block_n = s.block_n;
-  if (h->tile_m == 256 && s.n_packed % 256 == 0 && (epi == EPI_ACT || epi == EPI_LSTM)) op->block_n = 256;
+  if (h->tile_m == 256 && s.n_packed % 256 == 0 && (epi == EPI_ACT || epi == EPI_LSTM || epi == EPI_F32)) op->block_n = 256;
   op->epi = epi;
   ConvGeom& g = op->g;
   g.B = B; g.H = H; g.W = W; g.ks = s.ks; g.pad = s.ks / 2;
@@ -325,6 +339,10 @@ void carve(rac_handle* h, Bump& bp, int B) {
   w.d3b = bp.take<bf16>(n * P2 * 256);
   w.d4a = bp.take<bf16>(n * P1 * 128);
   w.d5 = bp.take<bf16>(n * P0 * 64);
+  if (h->cfg.lstm_group_norm) {
+    w.gn_ih = bp.take<float>(n * P3 * 4 * g);
+    w.gn_hh = bp.take<float>(n * P3 * 4 * g);
+  }
   w.cost_part = bp.take<float>(n * 96 * 2);
   w.goal4 = bp.take<float>(static_cast<size_t>(kMaxGoals) * P0 * 4);
 }
@@ -372,7 +390,25 @@ int build_ops(rac_handle* h) {
   bf16* xin[3] = {w.pin, w.postin, w.fin};
   const char* n0[3] = {"prior.lstm.0", "posterior.lstm.0", "frame_predictor.lstm.0"};
   const char* n1[3] = {"prior.lstm.1", "posterior.lstm.1", "frame_predictor.lstm.1"};
-  for (int l = 0; l < 3; ++l)
+  if (c.lstm_group_norm) {
+    const int hh0[3] = {RAC_L_PRIOR_LSTM0_HH, RAC_L_POST_LSTM0_HH, RAC_L_FP_LSTM0_HH};
+    auto f32_out = [&](ConvOp* op, float* dst) {
+      op->e.nseg = 1;
+      op->e.seg[0] = F32Seg{0, 4 * g, dst, 4 * g, 0, 0};
+    };
+    for (int l = 0; l < 3; ++l)
+      for (int p = 0; p < 2; ++p) {
+        CKR(make_conv(h, &w.lstm[l][0][p], n0[l], l0[l], 6, 8, {{xin[l], g}}, EPI_F32));
+        CKR(make_conv(h, &w.lstm_hh[l][0][p], n0[l], hh0[l], 6, 8, {{w.hs[l][0][p], g}}, EPI_F32));
+        CKR(make_conv(h, &w.lstm[l][1][p], n1[l], l1[l], 6, 8, {{w.hs[l][0][p ^ 1], g}}, EPI_F32));
+        CKR(make_conv(h, &w.lstm_hh[l][1][p], n1[l], hh0[l] + 1, 6, 8, {{w.hs[l][1][p], g}}, EPI_F32));
+        for (int k = 0; k < 2; ++k) {
+          f32_out(&w.lstm[l][k][p], w.gn_ih);
+          f32_out(&w.lstm_hh[l][k][p], w.gn_hh);
+        }
+      }
+  }
+  for (int l = 0; l < 3 && !c.lstm_group_norm; ++l)
     for (int p = 0; p < 2; ++p) {
       ConvOp* a = &w.lstm[l][0][p];
       CKR(make_conv(h, a, n0[l], l0[l], 6, 8, {{xin[l], g}, {w.hs[l][0][p], g}}, EPI_LSTM));
@@ -498,6 +534,18 @@ struct StepArgs {
 int launch_lstm(rac_handle* h, int l, cudaStream_t st) {
   Workspace& w = h->ws;
   const int p = h->cur[l];
+  if (h->cfg.lstm_group_norm) {
+    // NormConvLSTMCell (lstm.py:177-198): ih / hh gate convolutions -> GroupNorm + cell kernel, twice
+    const int g = h->cfg.g_dim;
+    for (int k = 0; k < 2; ++k) {
+      CKR(launch(h, w.lstm[l][k][p], st));
+      CKR(launch(h, w.lstm_hh[l][k][p], st));
+      CK(launch_norm_lstm_cell(w.gn_ih, w.gn_hh, h->gn_params[l][k], w.cs[l][k], w.hs[l][k][p ^ 1], w.B, 48, g, st));
+      h->launches++;
+    }
+    h->hidden_zero[l] = false;
+    return RAC_OK;
+  }
   ConvOp a = w.lstm[l][0][p], b = w.lstm[l][1][p];
   if (h->hidden_zero[l] && h->skip_zero_hidden) a.g.src_dead[1] = b.g.src_dead[1] = 1;
   CKR(launch(h, a, st));
@@ -633,6 +681,10 @@ int rac_create(const rac_config* cfg, rac_handle** out) {
   }
   CK(conv_tc_set_attributes());
   CK(cem_set_attributes());
+  if (cfg->lstm_group_norm) {
+    if (cfg->g_dim > 512) return fail(h, RAC_ERR_UNSUPPORTED, "lstm_group_norm supports g_dim <= 512");
+    CK(norm_lstm_set_attributes());
+  }
   fill_specs(h);
   return RAC_OK;
 }
@@ -644,10 +696,13 @@ int rac_destroy(rac_handle* h) {
   rac_train_destroy(h);
   free_ws(h);
   for (cudaEvent_t ev : h->prof_ev) cudaEventDestroy(ev);
-  for (int i = 0; i < RAC_L_COUNT; ++i) {
+  for (int i = 0; i < RAC_L_COUNT_GN; ++i) {
     if (h->layer[i].w) cudaFree(h->layer[i].w);
     if (h->layer[i].bias) cudaFree(h->layer[i].bias);
   }
+  for (int l = 0; l < 3; ++l)
+    for (int k = 0; k < 2; ++k)
+      if (h->gn_params[l][k]) cudaFree(h->gn_params[l][k]);
   delete h;
   return RAC_OK;
 }
@@ -656,7 +711,7 @@ const char* rac_last_error(const rac_handle* h) { return h ? h->err : "null hand
 
 int rac_layer_shape(const rac_handle* h, int layer, int64_t* w_elems, int64_t* bias_elems, int* k_packed,
                     int* n_packed) {
-  if (!h || layer < 0 || layer >= RAC_L_COUNT) return RAC_ERR_INVALID;
+  if (!h || layer < 0 || layer >= h->num_layers) return RAC_ERR_INVALID;
   const LayerSpec& s = h->spec[layer];
   if (w_elems) *w_elems = spec_w_elems(s);
   if (bias_elems) *bias_elems = s.n_packed;
@@ -666,7 +721,7 @@ int rac_layer_shape(const rac_handle* h, int layer, int64_t* w_elems, int64_t* b
 }
 
 int rac_load_layer(rac_handle* h, int layer, const void* wsrc, int64_t w_elems, const float* bias, int64_t bias_elems) {
-  if (!h || layer < 0 || layer >= RAC_L_COUNT || !wsrc || !bias) return fail(h, RAC_ERR_INVALID, "bad layer argument");
+  if (!h || layer < 0 || layer >= h->num_layers || !wsrc || !bias) return fail(h, RAC_ERR_INVALID, "bad layer argument");
   const LayerSpec& s = h->spec[layer];
   if (w_elems != spec_w_elems(s) || bias_elems != s.n_packed)
     return fail(h, RAC_ERR_INVALID, "layer %d: packed size mismatch (w %lld vs %lld, bias %lld vs %d)", layer,
@@ -681,10 +736,34 @@ int rac_load_layer(rac_handle* h, int layer, const void* wsrc, int64_t w_elems, 
   return RAC_OK;
 }
 
+int rac_load_lstm_norm(rac_handle* h, int layer, const float* packed, int64_t elems) {
+  if (!h || !packed) return RAC_ERR_INVALID;
+  if (!h->cfg.lstm_group_norm) return fail(h, RAC_ERR_STATE, "rac_load_lstm_norm: the handle was created without lstm_group_norm");
+  int l = -1, k = -1;
+  switch (layer) {
+    case RAC_L_PRIOR_LSTM0: l = 0; k = 0; break;
+    case RAC_L_PRIOR_LSTM1: l = 0; k = 1; break;
+    case RAC_L_POST_LSTM0: l = 1; k = 0; break;
+    case RAC_L_POST_LSTM1: l = 1; k = 1; break;
+    case RAC_L_FP_LSTM0: l = 2; k = 0; break;
+    case RAC_L_FP_LSTM1: l = 2; k = 1; break;
+    default: return fail(h, RAC_ERR_INVALID, "rac_load_lstm_norm: layer %d is not an LSTM cell", layer);
+  }
+  const int64_t need = static_cast<int64_t>(18) * h->cfg.g_dim;
+  if (elems != need) return fail(h, RAC_ERR_INVALID, "rac_load_lstm_norm: %lld floats given, %lld expected", (long long)elems, (long long)need);
+  if (!h->gn_params[l][k]) CK(cudaMalloc(reinterpret_cast<void**>(&h->gn_params[l][k]), static_cast<size_t>(need) * 4));
+  CK(cudaMemcpy(h->gn_params[l][k], packed, static_cast<size_t>(need) * 4, cudaMemcpyDefault));
+  return RAC_OK;
+}
+
 int rac_prepare(rac_handle* h, int batch) {
   if (!h || batch < 1) return fail(h, RAC_ERR_INVALID, "batch must be >= 1");
-  for (int i = 0; i < RAC_L_COUNT; ++i)
+  for (int i = 0; i < h->num_layers; ++i)
     if (!h->layer[i].loaded) return fail(h, RAC_ERR_STATE, "layer %d not loaded (rac_load_layer)", i);
+  if (h->cfg.lstm_group_norm)
+    for (int l = 0; l < 3; ++l)
+      for (int k = 0; k < 2; ++k)
+        if (!h->gn_params[l][k]) return fail(h, RAC_ERR_STATE, "GroupNorm parameters of LSTM stack %d cell %d not loaded (rac_load_lstm_norm)", l, k);
   if (h->ws.B == batch && h->ws.arena) return RAC_OK;
   CK(cudaDeviceSynchronize());
   free_ws(h);

@@ -488,6 +488,7 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
   if (cfg->batch < 1 || cfg->steps < 1 || (cfg->batch * 48) % 64 != 0)
     return fail(h, RAC_ERR_INVALID, "training batch must be a positive multiple of 4 (rows per map must be 64-aligned)");
   if (h->cfg.g_dim % 128 != 0) return fail(h, RAC_ERR_INVALID, "training needs g_dim %% 128 == 0");
+  if (h->cfg.lstm_group_norm) return fail(h, RAC_ERR_UNSUPPORTED, "training with lstm_group_norm is not implemented (inference only)");
   train_free(h);
   TrainState* T = new TrainState();
   h->train = T;

@@ -6,7 +6,7 @@ trainer.py:829-837) loads with `load_state_dict`. The arithmetic is done by libr
 into bf16 weights, tcgen05 implicit-GEMM convolutions with fused LSTM / z-sample / sigmoid epilogues.
 
 Not supported (raises): train-mode forward (batch-statistics BatchNorm + backward are not part of this round),
-heatmaps, lstm_group_norm.
+heatmaps. lstm_group_norm=True (NormConvLSTMCell, lstm.py:151-198) is supported for inference / planning.
 """
 import ctypes as C
 from collections import OrderedDict
@@ -35,6 +35,17 @@ def _spec(c):
         spec[f"{prefix}.weight"] = ((cout, cin, k, k), "conv_w")
         spec[f"{prefix}.bias"] = ((cout,), "zero")
 
+    def lstm_cell(prefix, k):
+        if c.lstm_group_norm:  # NormConvLSTMCell (lstm.py:151-175); GroupNorm is not touched by init_weights
+            for gk in ("ih_gates", "hh_gates"):
+                conv(f"{prefix}.{gk}.0", g, 4 * g, k)
+                spec[f"{prefix}.{gk}.1.weight"] = ((4 * g,), "one")
+                spec[f"{prefix}.{gk}.1.bias"] = ((4 * g,), "zero")
+            spec[f"{prefix}.c_norm.weight"] = ((g,), "one")
+            spec[f"{prefix}.c_norm.bias"] = ((g,), "zero")
+        else:
+            conv(f"{prefix}.gates", 2 * g, 4 * g, k)
+
     nc = c.channels + (1 if c.model_use_mask else 0) + (1 if (c.model_use_mask and c.model_use_future_mask) else 0)
     for name, cin, cout in [("c1.0", nc, 64), ("c1.1", 64, 64), ("c2.0", 64, 128), ("c2.1", 128, 128),
                             ("c3.0", 128, 256), ("c3.1", 256, 256), ("c3.2", 256, 256), ("c4.0", 256, 512),
@@ -44,12 +55,12 @@ def _spec(c):
     extra2 = (r if c.model_use_future_robot_state else 0)
     conv("frame_pred_input_conv", g + a + z + extra + extra2, g)
     for layer, k in ((0, 5), (1, 3)):
-        conv(f"frame_predictor.lstm.{layer}.gates", 2 * g, 4 * g, k)
+        lstm_cell(f"frame_predictor.lstm.{layer}", k)
     conv("posterior_input_conv", g + extra, g)
     conv("prior_input_conv", g + a + extra + extra2, g)
     for p in ("posterior", "prior"):
         for layer, k in ((0, 5), (1, 3)):
-            conv(f"{p}.lstm.{layer}.gates", 2 * g, 4 * g, k)
+            lstm_cell(f"{p}.lstm.{layer}", k)
         conv(f"{p}.mu_net", g, z)
         conv(f"{p}.logvar_net", g, z)
     for name, cin, cout in [("upc2.0", g, 512), ("upc2.1", 512, 512), ("upc2.2", 512, 256), ("upc3.0", 512, 256),
@@ -110,7 +121,7 @@ class SVGConvModel(nn.Module):
                 t = torch.empty(shape).normal_(0.0, 0.02)
             elif kind == "bn_w":
                 t = torch.empty(shape).normal_(1.0, 0.02)
-            elif kind == "buf_one":
+            elif kind in ("buf_one", "one"):
                 t = torch.ones(shape)
             elif kind == "buf_long":
                 t = torch.tensor(0, dtype=torch.long)
@@ -125,7 +136,8 @@ class SVGConvModel(nn.Module):
         rc = _lib.RacConfig(c.image_height, c.image_width, c.g_dim, c.z_dim, c.action_dim, c.robot_dim,
                             int(bool(c.model_use_mask)), int(bool(c.model_use_mask and c.model_use_future_mask)),
                             int(bool(c.model_use_robot_state)),
-                            int(bool(c.model_use_robot_state and c.model_use_future_robot_state)), int(conv_impl))
+                            int(bool(c.model_use_robot_state and c.model_use_future_robot_state)), int(conv_impl),
+                            int(bool(c.lstm_group_norm)))
         h = C.c_void_p()
         code = self._lib.rac_create(C.byref(rc), C.byref(h))
         self._h = h
@@ -171,6 +183,10 @@ class SVGConvModel(nn.Module):
             b = b.contiguous()
             _lib.check(self._lib.rac_load_layer(self._h, pack.LAYER_INDEX[name], _lib.ptr(w), w.numel(), _lib.ptr(b),
                                                 b.numel()), self._h, f"rac_load_layer({name})")
+        if self._c.lstm_group_norm:
+            for name, t in pack.pack_lstm_norm(sd, self._c).items():
+                _lib.check(self._lib.rac_load_lstm_norm(self._h, pack.LAYER_INDEX[name], _lib.ptr(t), t.numel()),
+                           self._h, f"rac_load_lstm_norm({name})")
         self._packed_dirty = False
 
     def __del__(self):

@@ -20,7 +20,9 @@ LAYER_IDS = [
     "DEC_UPC2_0", "DEC_UPC2_1", "DEC_UPC2_2", "DEC_UPC3_0", "DEC_UPC3_1", "DEC_UPC3_2", "DEC_UPC4_0", "DEC_UPC4_1",
     "DEC_UPC5_0", "DEC_UPC5_1", "POST_IN", "POST_LSTM0", "POST_LSTM1", "POST_GAUSS",
 ]
-LAYER_INDEX = {n: i for i, n in enumerate(LAYER_IDS)}
+# cfg.lstm_group_norm only (RAC_L_*_HH): hh_gates convolutions of the NormConvLSTMCells (lstm.py:168-171)
+GN_LAYER_IDS = ["PRIOR_LSTM0_HH", "PRIOR_LSTM1_HH", "FP_LSTM0_HH", "FP_LSTM1_HH", "POST_LSTM0_HH", "POST_LSTM1_HH"]
+LAYER_INDEX = {n: i for i, n in enumerate(LAYER_IDS + GN_LAYER_IDS)}
 
 _VGG = OrderedDict([
     ("ENC_C1_1", "encoder.c1.1"), ("ENC_C2_0", "encoder.c2.0"), ("ENC_C2_1", "encoder.c2.1"),
@@ -98,10 +100,17 @@ def pack_state_dict(sd, cfg):
     out["POST_IN"] = pack_gemm(w, b, ([(r, 64)] if use_r else []) + [(g, g)], 128)
 
     gate_cols = [gate * g + ch for ch in range(g) for gate in range(4)]  # packed col = ch * 4 + gate
+    group_norm = bool(getattr(cfg, "lstm_group_norm", False))
     for tag, prefix in (("PRIOR", "prior"), ("POST", "posterior"), ("FP", "frame_predictor")):
         for layer in (0, 1):
-            w, b = conv(f"{prefix}.lstm.{layer}.gates")
-            out[f"{tag}_LSTM{layer}"] = pack_gemm(w, b, [(g, g), (g, g)], 128, col_src=gate_cols)
+            if group_norm:  # NormConvLSTMCell: separate ih / hh convolutions (lstm.py:163-171)
+                w, b = conv(f"{prefix}.lstm.{layer}.ih_gates.0")
+                out[f"{tag}_LSTM{layer}"] = pack_gemm(w, b, [(g, g)], 128, col_src=gate_cols)
+                w, b = conv(f"{prefix}.lstm.{layer}.hh_gates.0")
+                out[f"{tag}_LSTM{layer}_HH"] = pack_gemm(w, b, [(g, g)], 128, col_src=gate_cols)
+            else:
+                w, b = conv(f"{prefix}.lstm.{layer}.gates")
+                out[f"{tag}_LSTM{layer}"] = pack_gemm(w, b, [(g, g), (g, g)], 128, col_src=gate_cols)
     for tag, prefix in (("PRIOR", "prior"), ("POST", "posterior")):
         wm, bm = conv(f"{prefix}.mu_net")
         wl, bl = conv(f"{prefix}.logvar_net")
@@ -116,4 +125,19 @@ def pack_state_dict(sd, cfg):
     wc = wt.transpose(0, 1).flip(2, 3).contiguous()
     out["DEC_UPC5_1"] = pack_gemm(wc, sd["decoder.upc5.1.bias"].float(), [(64, 64)], 16)
 
-    return OrderedDict((n, out[n]) for n in LAYER_IDS)
+    return OrderedDict((n, out[n]) for n in LAYER_IDS + (GN_LAYER_IDS if group_norm else []))
+
+
+def pack_lstm_norm(sd, cfg):
+    """cfg.lstm_group_norm: OrderedDict cell layer name -> fp32 [18 g] GroupNorm affine parameters of that
+    NormConvLSTMCell for rac_load_lstm_norm: ih / hh gamma and beta in packed gate-column order, then c_norm."""
+    g = cfg.g_dim
+    cols = torch.tensor([gate * g + ch for ch in range(g) for gate in range(4)], dtype=torch.long)
+    out = OrderedDict()
+    for tag, prefix in (("PRIOR", "prior"), ("POST", "posterior"), ("FP", "frame_predictor")):
+        for layer in (0, 1):
+            p = f"{prefix}.lstm.{layer}"
+            parts = [sd[f"{p}.{gk}.1.{wb}"].float()[cols] for gk in ("ih_gates", "hh_gates") for wb in ("weight", "bias")]
+            parts += [sd[f"{p}.c_norm.weight"].float(), sd[f"{p}.c_norm.bias"].float()]
+            out[f"{tag}_LSTM{layer}"] = torch.cat(parts).contiguous()
+    return out

@@ -129,6 +129,8 @@ class SVGTrainer:
             raise NotImplementedError(f"reconstruction_loss {kind!r}: the B200 path implements l1 and dontcare_l1")
         if not c.last_frame_skip:
             raise NotImplementedError("last_frame_skip False is not implemented for training")
+        if c.lstm_group_norm:
+            raise NotImplementedError("lstm_group_norm is implemented for inference / planning only")
         self.process_group = process_group
         self._lib = _lib.load()
         dev = model._device

@@ -96,14 +96,14 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.rac_abi_version() == 1
+    assert lib.rac_abi_version() == 2
 
 
 def test_model_spec_matches_oracle_spec():
     from robot_aware_control_b200.model import _spec
     from robot_aware_control_b200.config import svg_config_from
 
-    for kw in CONFIGS.values():
+    for kw in list(CONFIGS.values()) + [dict(lstm_group_norm=True)]:
         cfg = so.make_cfg(g_dim=128, z_dim=10, **kw)
         mine = {k: tuple(v[0]) for k, v in _spec(svg_config_from(cfg)).items()}
         ref = {k: tuple(v) for k, v in so.state_dict_spec(cfg).items()}
@@ -131,6 +131,31 @@ def test_config_validation_errors_match_reference_types():
     with pytest.raises(ValueError):  # reference: ValueError for unsupported image_width (dynamics.py:470-473)
         validate_model_config(svg_config_from(so.make_cfg(image_width=32)))
     with pytest.raises(NotImplementedError):
-        validate_model_config(svg_config_from(so.make_cfg(lstm_group_norm=True)))
+        validate_model_config(svg_config_from(so.make_cfg(lstm_group_norm=True, g_dim=1024)))
+    validate_model_config(svg_config_from(so.make_cfg(lstm_group_norm=True, g_dim=256)))  # the deployed checkpoints
     with pytest.raises(ValueError):
         validate_model_config(svg_config_from(so.make_cfg(g_dim=100)))
+
+
+def test_group_norm_lstm_packing():
+    """NormConvLSTMCell (lstm.py:151-175): ih / hh gate convolutions pack separately with (channel, gate) interleaved
+    columns; the GroupNorm affine vectors follow the same column order."""
+    from robot_aware_control_b200 import pack
+
+    cfg = so.make_cfg(g_dim=128, z_dim=10, lstm_group_norm=True)
+    sd = so.make_state_dict(cfg, 1)
+    packed = pack.pack_state_dict(sd, cfg)
+    assert list(packed)[-6:] == pack.GN_LAYER_IDS and len(packed) == len(pack.LAYER_IDS) + 6
+    g = cfg.g_dim
+    w, b = packed["FP_LSTM0_HH"]
+    assert w.shape == (4 * g, 25 * g) and b.shape == (4 * g,)
+    ref_w = sd["frame_predictor.lstm.0.hh_gates.0.weight"]  # (4g, g, 5, 5)
+    ch, gate, tap, cin = 37, 2, 7, 91
+    assert w[ch * 4 + gate, tap * g + cin].float() == ref_w[gate * g + ch, cin, tap // 5, tap % 5].to(torch.bfloat16).float()
+    assert b[ch * 4 + gate] == sd["frame_predictor.lstm.0.hh_gates.0.bias"][gate * g + ch]
+    norm = pack.pack_lstm_norm(sd, cfg)
+    v = norm["PRIOR_LSTM1"]
+    assert v.shape == (18 * g,)
+    assert v[ch * 4 + gate] == sd["prior.lstm.1.ih_gates.1.weight"][gate * g + ch]
+    assert v[3 * 4 * g + ch * 4 + gate] == sd["prior.lstm.1.hh_gates.1.bias"][gate * g + ch]
+    assert v[16 * g + ch] == sd["prior.lstm.1.c_norm.weight"][ch] and v[17 * g + ch] == sd["prior.lstm.1.c_norm.bias"][ch]
