@@ -190,6 +190,23 @@ int rac_robot_world_mse(const float* pred, const float* target, const float* mas
 int rac_kl_loss(const float* mu1, const float* logvar1, const float* mu2, const float* logvar2, float* out,
                 int64_t numel, int batch, void* stream);
 
+/* Evaluation metrics of PredictionTrainer._eval_step (trainer.py:685-700). `mask` (n,1,H,W) or NULL: robot pixels
+ * of BOTH images are zeroed first (zero_robot_region with the true mask, image.py:5-20).
+ * rac_psnr: psnr(estimates, targets) of src/utils/metrics.py:57-78 (data_dims 3; inputs pass through (x+1)/2),
+ *           clamp01 != 0 applies clamp(0, 1) after the masking (trainer.py:689) -> out (n).
+ * rac_world_psnr: world_psnr_criterion (losses.py:80-94) -> out (n).
+ * rac_ssim: ssim(img1, img2, window_size=11) of src/utils/metrics.py:22-54: map_out (n,c,H,W) and / or
+ *           plane_mean_out (n*c) = mean of the map over (H,W); either may be NULL. */
+int rac_psnr(const float* est, const float* target, const float* mask, int clamp01, float* out, int n, int c, int hw,
+             void* stream);
+int rac_world_psnr(const float* pred, const float* target, const float* mask, float* out, int n, int hw, void* stream);
+int rac_ssim(const float* img1, const float* img2, const float* mask, float* map_out, float* plane_mean_out, int n,
+             int c, int h, int w, void* stream);
+
+/* Compositing of the decoder output (trainer.py:653-654, trajectory_sampler.py:149-150): x_pred4 (n,4,H,W) = rgb +
+ * blend mask, x_j (n,3,H,W) -> out (n,3,H,W) = (1 - m) * x_j + m * rgb. */
+int rac_composite(const float* x_pred4, const float* x_j, float* out, int n, int hw, void* stream);
+
 /* Test / inspection hook: device pointer and element count of a named internal buffer of the prepared workspace
  * ("h1".."h4", "prior_in", "z", "h_pred", "img", ...). */
 int rac_debug_buffer(rac_handle* h, const char* name, void** ptr, int64_t* elems, int* elem_bytes);

@@ -10,6 +10,7 @@ from .model import SVGConvModel  # noqa: F401
 from .losses import RobotWorldCost, ImgL2Cost, ImgDontcareCost, RobotL2Cost  # noqa: F401
 from .losses import l1_criterion, dontcare_l1_criterion, kl_criterion  # noqa: F401
 from .losses import robot_mse_criterion, world_mse_criterion  # noqa: F401
+from .metrics import psnr, ssim, world_psnr_criterion  # noqa: F401
 from .image import zero_robot_region  # noqa: F401
 from .cem import CEMPolicy, TrajectorySampler  # noqa: F401
 from .trainer import SVGTrainer  # noqa: F401
@@ -18,4 +19,5 @@ __all__ = [
     "SVGConvModel", "CEMPolicy", "TrajectorySampler", "RobotWorldCost", "ImgL2Cost", "ImgDontcareCost",
     "RobotL2Cost", "State", "DemoGoalState", "zero_robot_region", "l1_criterion", "dontcare_l1_criterion",
     "kl_criterion", "robot_mse_criterion", "world_mse_criterion", "svg_config_from", "SVGTrainer",
+    "psnr", "ssim", "world_psnr_criterion",
 ]

@@ -45,6 +45,17 @@ cudaError_t launch_robot_world_mse(const float* pred, const float* target, const
 cudaError_t launch_kl_loss(const float* mu1, const float* lv1, const float* mu2, const float* lv2, float* out,
                            int64_t n, int bs, cudaStream_t s);
 
+// ---- evaluation metrics (metric_kernels.cu; reference src/utils/metrics.py:13-78, losses.py:80-94) ----
+// mode 0: psnr of metrics.py (both images through (x + 1) / 2), optional robot-region zeroing + clamp; mode 1: world_psnr
+cudaError_t launch_psnr(const float* est, const float* tgt, const float* mask, int mode, int clamp01, float* out,
+                        int B, int C, int HW, cudaStream_t s);
+// 11x11 gaussian SSIM map (B,C,H,W) and / or its per-plane means (B*C); optional robot-region zeroing of both images
+cudaError_t launch_ssim(const float* img1, const float* img2, const float* mask, float* map_out, float* plane_mean,
+                        int B, int C, int H, int W, cudaStream_t s);
+
+// (1 - m) * x_j + m * rgb from the 4-channel decoder output, NCHW fp32 (trainer.py:653-654)
+cudaError_t launch_composite_nchw(const float* x4, const float* xj, float* out, int B, int HW, cudaStream_t s);
+
 // ---- NormConvLSTMCell pointwise part (norm_lstm.cu; reference lstm.py:177-198) ----
 // ih / hh: raw gate convolutions [B, P, 4*hid] fp32, packed column (channel, gate); gn_params: packed GroupNorm affine
 // [ih gamma | ih beta | hh gamma | hh beta] (4*hid each, packed column order) + [cell gamma | cell beta] (hid each)

@@ -986,6 +986,27 @@ int rac_kl_loss(const float* mu1, const float* logvar1, const float* mu2, const 
   return launch_kl_loss(mu1, logvar1, mu2, logvar2, out, numel, batch, static_cast<cudaStream_t>(stream)) == cudaSuccess ? RAC_OK : RAC_ERR_CUDA;
 }
 
+int rac_psnr(const float* est, const float* target, const float* mask, int clamp01, float* out, int n, int c, int hw,
+             void* stream) {
+  if (!est || !target || !out || n < 0 || c < 1 || hw < 1) return RAC_ERR_INVALID;
+  return launch_psnr(est, target, mask, 0, clamp01, out, n, c, hw, static_cast<cudaStream_t>(stream)) == cudaSuccess ? RAC_OK : RAC_ERR_CUDA;
+}
+int rac_world_psnr(const float* pred, const float* target, const float* mask, float* out, int n, int hw, void* stream) {
+  if (!pred || !target || !mask || !out || n < 0 || hw < 1) return RAC_ERR_INVALID;
+  return launch_psnr(pred, target, mask, 1, 0, out, n, 3, hw, static_cast<cudaStream_t>(stream)) == cudaSuccess ? RAC_OK : RAC_ERR_CUDA;
+}
+int rac_ssim(const float* img1, const float* img2, const float* mask, float* map_out, float* plane_mean_out, int n,
+             int c, int h, int w, void* stream) {
+  if (!img1 || !img2 || (!map_out && !plane_mean_out) || n < 0 || c < 1 || h < 1 || w < 1) return RAC_ERR_INVALID;
+  if (static_cast<size_t>(7) * h * w * 4 > 226 * 1024) return RAC_ERR_UNSUPPORTED;
+  return launch_ssim(img1, img2, mask, map_out, plane_mean_out, n, c, h, w, static_cast<cudaStream_t>(stream)) == cudaSuccess ? RAC_OK : RAC_ERR_CUDA;
+}
+
+int rac_composite(const float* x_pred4, const float* x_j, float* out, int n, int hw, void* stream) {
+  if (!x_pred4 || !x_j || !out || n < 0 || hw < 1) return RAC_ERR_INVALID;
+  return launch_composite_nchw(x_pred4, x_j, out, n, hw, static_cast<cudaStream_t>(stream)) == cudaSuccess ? RAC_OK : RAC_ERR_CUDA;
+}
+
 int rac_debug_buffer(rac_handle* h, const char* name, void** ptr, int64_t* elems, int* elem_bytes) {
   if (!h || !name || !ptr) return RAC_ERR_INVALID;
   auto it = h->ws.named.find(name);

@@ -270,6 +270,76 @@ class SVGTrainer:
             out["robot_loss"], out["world_loss"] = float(vals[2]) / nf, float(vals[3]) / nf
         return out
 
+    @torch.no_grad()
+    def _eval_step(self, data, autoregressive=False):
+        """PredictionTrainer._eval_step (trainer.py:566-734) for the svg model, single view: evaluates a snippet of
+        cfg.n_eval frames with the eval-mode model (prior z, posterior only for the KL), returning the reference's
+        dict of averaged metrics ("1step_*" / "autoreg_*", plus "<i>_step_*" for autoregressive rollouts).
+        data: images (T,B,3,H,W), states, actions, masks (true masks, metrics), pred_masks (model inputs)."""
+        from . import losses as L
+        from . import metrics as M
+        from .image import zero_robot_region
+
+        m = self.model
+        if m.training:
+            raise RuntimeError("call model.eval() before _eval_step (reference trainer.py:785-790)")
+        c = m._c
+        dev = m._device
+        f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
+        x, states, ac = f32(data["images"]), f32(data["states"]), f32(data["actions"])
+        true_masks, masks = f32(data["masks"]), f32(data["pred_masks"])
+        n_eval = int(getattr(self._config, "n_eval", x.shape[0]))
+        bs = min(int(getattr(self._config, "test_batch_size", x.shape[1])), x.shape[1])
+        if bs != x.shape[1]:
+            raise ValueError("test_batch_size smaller than the batch: the reference would fail in forward as well")
+        m.init_hidden(bs)
+        eps = self._eps
+        self._eps = None
+        prefix = "autoreg" if autoregressive else "1step"
+        acc = torch.zeros(6, device=dev)  # recon, robot, world, psnr, ssim, kld: summed on device, one read at the end
+        per_step = []
+        dontcare = ("dontcare" in c.reconstruction_loss) or bool(c.black_robot_input)
+        x_pred = skip = None
+        for i in range(1, n_eval):
+            x_j = x_pred if (autoregressive and i > 1) else x[i - 1]
+            m_j, r_j, a_j = masks[i - 1], states[i - 1], ac[i - 1]
+            x_i, m_i, r_i = x[i], masks[i], states[i]
+            x_j_black = zero_robot_region(m_j, x_j) if dontcare else x_j
+            if c.last_frame_skip:
+                skip = None
+            m_in = torch.cat([m_j, m_i], 1) if c.model_use_future_mask else m_j
+            r_in = (r_j, r_i) if c.model_use_future_robot_state else r_j
+            if eps is not None:
+                m.set_noise(eps=eps[0][i - 1], eps_post=eps[1][i - 1])
+            x4, curr_skip, mu, logvar, mu_p, logvar_p = m.forward(
+                x_j_black, m_in if c.model_use_mask else None, r_in if c.model_use_robot_state else None, None, a_j,
+                x_i, None, r_i if c.model_use_robot_state else None, None, skip, force_use_prior=True)
+            x_pred = torch.empty_like(x_j)
+            _lib.check(self._lib.rac_composite(_lib.ptr(x4), _lib.ptr(x_j), _lib.ptr(x_pred), bs, 48 * 64,
+                                               _lib.stream_ptr()), m.handle, "rac_composite")
+            if i <= self.n_past:
+                skip = curr_skip
+            tm = true_masks[i]
+            if c.reconstruction_loss == "l1":
+                recon = L.l1_criterion(x_pred, x_i)
+            else:
+                recon = L.dontcare_l1_criterion(x_pred, x_i, tm, self._rpw)
+            rw = L._robot_world_mse(x_pred, x_i, tm)
+            p = M.psnr(x_i, x_pred, mask=tm, clamp01=True).mean()
+            s = M.ssim_mean(x_i, x_pred, mask=tm)
+            kl = L.kl_criterion(mu, logvar, mu_p, logvar_p, bs)
+            step = torch.stack([recon, rw[0], rw[1], p, s, kl])
+            acc += step
+            per_step.append(step)
+        vals = (acc / (n_eval - 1)).cpu().tolist()
+        out = {f"{prefix}_{k}": v for k, v in zip(("recon_loss", "robot_loss", "world_loss", "psnr", "ssim", "kld"), vals)}
+        if autoregressive:
+            for i, st in enumerate(torch.stack(per_step).cpu().tolist(), start=1):
+                out[f"{i}_step_psnr"], out[f"{i}_step_ssim"], out[f"{i}_step_world_loss"] = st[3], st[4], st[2]
+        return out
+
+    eval_step = _eval_step
+
     def grad_of(self, key):
         o = self._offsets[key]
         p = dict(self.model.named_parameters())[key]

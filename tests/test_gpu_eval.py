@@ -1,0 +1,85 @@
+"""GPU parity of the evaluation metrics (psnr / ssim / world_psnr, csrc/metric_kernels.cu) and of
+SVGTrainer._eval_step against the reference's own outputs (tests/golden/eval_*.npz from oracle/make_golden_eval.py)
+and the CPU oracle (oracle/eval_oracle.py). Metric kernels are fp32: 1e-5-level agreement; the evaluation step runs
+the bf16 tensor-core model, so its losses carry the 1e-2 pixel tolerance of BASELINE.json."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import eval_oracle as eo
+from oracle import svg_oracle as so
+from oracle.make_golden_eval import make_eval_batch, G_DIM, Z_DIM, T
+from tests.test_eval_oracle_golden import eval_cfg, metric_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def test_metric_kernels_match_reference_golden(golden_dir):
+    from robot_aware_control_b200 import metrics as M
+
+    gold = np.load(os.path.join(golden_dir, "eval_metrics.npz"))
+    a, b, mask = metric_inputs(int(gold["input_seed"]))
+    smap = M.ssim(a, b)
+    assert smap.shape == (5, 3, 48, 64) and isinstance(smap, np.ndarray)
+    # fp32 on both sides: sigma = E[x^2] - mu^2 cancels to ~1e-7 absolute against C2 = 9e-4, so single map elements
+    # move by ~1e-4 with the summation order (separable here, 121-tap in the reference); the mean is stable
+    np.testing.assert_allclose(smap, gold["ssim_map"], rtol=0, atol=3e-4)
+    assert np.abs(smap - gold["ssim_map"]).mean() < 2e-5
+    np.testing.assert_allclose(M.ssim_mean(a, b).item(), gold["ssim_map"].mean(), rtol=1e-5)
+    np.testing.assert_allclose(M.psnr(a, b).cpu().numpy(), gold["psnr"], rtol=1e-5)
+    np.testing.assert_allclose(M.world_psnr_criterion(b, a, mask).cpu().numpy(), gold["world_psnr"], rtol=1e-5)
+    # fused robot-region zeroing + clamp == the reference composition zero_robot_region -> clamp -> metric
+    ab, bb = so.zero_robot_region(mask, a), so.zero_robot_region(mask, b * 1.3 - 0.1)
+    np.testing.assert_allclose(M.psnr(a, b * 1.3 - 0.1, mask=mask, clamp01=True).cpu().numpy(),
+                               eo.psnr(ab.clamp(0, 1), bb.clamp(0, 1)).numpy(), rtol=1e-5)
+    np.testing.assert_allclose(M.ssim(a, b * 1.3 - 0.1, mask=mask), eo.ssim_map(ab, bb).numpy(), rtol=0, atol=3e-4)
+
+
+def test_metric_kernels_edge_cases():
+    from robot_aware_control_b200 import metrics as M
+
+    g = torch.Generator().manual_seed(3)
+    a = torch.rand(1, 1, 48, 64, generator=g)
+    # identical images: SSIM == 1 everywhere, also along the zero-padded border
+    np.testing.assert_allclose(M.ssim(a, a), np.ones((1, 1, 48, 64), np.float32), rtol=0, atol=1e-5)
+    # one sample, 3 channels, a fully masked image: both blacked images are zero -> SSIM 1, PSNR inf (1 / 0)
+    b = torch.rand(2, 3, 48, 64, generator=g)
+    full = torch.ones(2, 1, 48, 64)
+    assert np.allclose(M.ssim(b, b.flip(0), mask=full), 1.0)
+    assert torch.isinf(M.psnr(b, b.flip(0), mask=full)).all()
+    # empty batch
+    assert M.psnr(torch.zeros(0, 3, 48, 64), torch.zeros(0, 3, 48, 64)).shape == (0,)
+
+
+@pytest.mark.parametrize("tag", ["vanilla", "ra"])
+def test_eval_step_matches_reference_golden(golden_dir, tag):
+    from robot_aware_control_b200 import SVGConvModel, SVGTrainer
+
+    gold = np.load(os.path.join(golden_dir, f"eval_step_{tag}.npz"))
+    ref = dict(zip(gold["keys"].tolist(), gold["values"].tolist()))
+    cfg = eval_cfg(tag)
+    cfg.n_eval, cfg.test_batch_size = T, int(gold["B"])
+    model = SVGConvModel(cfg)
+    model.load_state_dict(so.make_state_dict(cfg, int(gold["weight_seed"])))
+    trainer = SVGTrainer(cfg, model)
+    model.eval()
+    batch, eps_p, eps_q = make_eval_batch(int(gold["input_seed"]), cfg, tag == "ra")
+    got = {}
+    for autoreg in (False, True):
+        trainer.set_noise(eps_p, eps_q)
+        got.update(trainer._eval_step(batch, autoregressive=autoreg))
+    assert set(got) == set(ref)
+    for k, v in ref.items():
+        if k.endswith("psnr"):
+            assert abs(got[k] - v) < 0.05, (k, got[k], v)        # dB
+        elif k.endswith("ssim"):
+            assert abs(got[k] - v) < 5e-3, (k, got[k], v)
+        elif k.endswith("kld"):
+            assert abs(got[k] - v) < 2e-2 * abs(v), (k, got[k], v)
+        else:
+            assert abs(got[k] - v) < 5e-3 * max(abs(v), 1e-3) + 1e-6, (k, got[k], v)
+    model.train()
+    with pytest.raises(RuntimeError):
+        trainer._eval_step(batch)
