@@ -6,73 +6,111 @@
 namespace rac {
 
 // ---------------------------------------------------------------- encoder.c1.0
-// w: [9 * cin][64] fp32 (tap-major, BN folded), bias [64]. One thread per (pixel, 8 output channels): the 8 threads
-// of a pixel share its 3x3 input window through L1 and together write the pixel's 128-byte output row, so a warp
-// stores 512 contiguous bytes (HBM-write bound layer: 393 KB per candidate).
-__global__ void __launch_bounds__(256)
+// w: [9 * cin][64] fp32 (tap-major, BN folded), bias [64]. K = 27..45 is too small for a tensor tile, so this layer is
+// CUDA-core work next to an HBM-write stream (393 KB bf16 out per candidate). Register tile: one thread = 4
+// consecutive pixels x 8 output channels, so every weight float4 read from shared memory feeds 16 FMAs and every
+// input value 8. The 8 threads of a pixel group cover the 64 channels: their weight reads are one conflict-free
+// 128-byte row (layout [tap][c][half][group][4]) and together they write each pixel's 128-byte output row; input
+// pixels are broadcast loads shared through L1. Persistent over pixel groups (weights staged once per CTA).
+template <int CIN>
+__global__ void __launch_bounds__(256, 2)
 first_conv_kernel(const float* __restrict__ img4, const float* __restrict__ mask_a, const float* __restrict__ mask_b,
                   long long mask_bstride, const float* __restrict__ w, const float* __restrict__ bias,
-                  __nv_bfloat16* __restrict__ out, float* __restrict__ raw_out, int B, int H, int W, int cin) {
-  __shared__ __align__(16) float sw[45 * 64];
+                  __nv_bfloat16* __restrict__ out, float* __restrict__ raw_out, int B, int H, int W) {
+  __shared__ __align__(16) float sw[9 * CIN * 64];
   __shared__ float sb[64];
-  for (int i = threadIdx.x; i < 9 * cin * 64; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < 9 * CIN * 64; i += blockDim.x) {
+    const int o = i & 63, tc = i >> 6;  // source [tap*CIN + c][o]; o = group * 8 + half * 4 + j
+    sw[(tc * 2 + ((o >> 2) & 1)) * 32 + (o >> 3) * 4 + (o & 3)] = w[i];
+  }
   if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
-  const size_t total = static_cast<size_t>(B) * H * W;
-  const int o8 = static_cast<int>(threadIdx.x & 7) * 8;
-  // persistent over pixels: the 11.5 KB weight tile is staged once per CTA, not once per 32 pixels
-  for (size_t pix = static_cast<size_t>(blockIdx.x) * 32 + (threadIdx.x >> 3); pix < total;
-       pix += static_cast<size_t>(gridDim.x) * 32) {
-    const int x = static_cast<int>(pix % W);
-    const int y = static_cast<int>((pix / W) % H);
-    const size_t b = pix / (static_cast<size_t>(W) * H);
-    float acc[8];
+  const int grp = threadIdx.x & 7;           // output channels grp*8 .. grp*8+7
+  const int gpr = W >> 2;                    // pixel groups per image row
+  const int total = B * H * gpr;             // pixel groups
+  for (int pg = blockIdx.x * 32 + (threadIdx.x >> 3); pg < total; pg += gridDim.x * 32) {
+    const int xg = pg % gpr;
+    const int row = pg / gpr;                // b * H + y
+    const int y = row % H;
+    const int b = row / H;
+    const int x0 = xg * 4;
+    float acc[4][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = sb[o8 + j];
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[p][j] = sb[grp * 8 + j];
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
+      const int yy = y + kh - 1;
+      if (yy < 0 || yy >= H) continue;
+      // input row segment x0-1 .. x0+4 (6 pixels), zero outside the image
+      float in[6][CIN];
+      const size_t rbase = (static_cast<size_t>(b) * H + yy) * W;
+      const size_t mbase = static_cast<size_t>(b) * mask_bstride + static_cast<size_t>(yy) * W;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const int xx = x0 + q - 1;
+        const bool ok = xx >= 0 && xx < W;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) v = __ldg(reinterpret_cast<const float4*>(img4) + rbase + xx);
+        in[q][0] = v.x; in[q][1] = v.y; in[q][2] = v.z;
+        if constexpr (CIN > 3) in[q][3] = ok ? __ldg(mask_a + mbase + xx) : 0.f;
+        if constexpr (CIN > 4) in[q][4] = ok ? __ldg(mask_b + mbase + xx) : 0.f;
+      }
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
-        const int yy = y + kh - 1, xx = x + kw - 1;
-        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-        const size_t q = (b * H + yy) * W + xx;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(img4 + q * 4));
-        float in[5] = {v.x, v.y, v.z, 0.f, 0.f};
-        const size_t mq = b * mask_bstride + static_cast<size_t>(yy) * W + xx;
-        if (cin > 3) in[3] = __ldg(mask_a + mq);
-        if (cin > 4) in[4] = __ldg(mask_b + mq);
-        const float* wt = &sw[(kh * 3 + kw) * cin * 64 + o8];
-        for (int c = 0; c < cin; ++c) {
-          const float a = in[c];
-          const float4 w0 = *reinterpret_cast<const float4*>(wt + c * 64);
-          const float4 w1 = *reinterpret_cast<const float4*>(wt + c * 64 + 4);
-          acc[0] += a * w0.x; acc[1] += a * w0.y; acc[2] += a * w0.z; acc[3] += a * w0.w;
-          acc[4] += a * w1.x; acc[5] += a * w1.y; acc[6] += a * w1.z; acc[7] += a * w1.w;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+          const float* wt = &sw[(((kh * 3 + kw) * CIN + c) * 2) * 32 + grp * 4];
+          const float4 w0 = *reinterpret_cast<const float4*>(wt);
+          const float4 w1 = *reinterpret_cast<const float4*>(wt + 32);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float a = in[p + kw][c];
+            acc[p][0] = fmaf(a, w0.x, acc[p][0]); acc[p][1] = fmaf(a, w0.y, acc[p][1]);
+            acc[p][2] = fmaf(a, w0.z, acc[p][2]); acc[p][3] = fmaf(a, w0.w, acc[p][3]);
+            acc[p][4] = fmaf(a, w1.x, acc[p][4]); acc[p][5] = fmaf(a, w1.y, acc[p][5]);
+            acc[p][6] = fmaf(a, w1.z, acc[p][6]); acc[p][7] = fmaf(a, w1.w, acc[p][7]);
+          }
         }
       }
     }
+    const size_t pix0 = (static_cast<size_t>(b) * H + y) * W + x0;
     if (raw_out) {  // training: pre-BatchNorm fp32 output, activation applied later with batch statistics
-      *reinterpret_cast<float4*>(raw_out + pix * 64 + o8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      *reinterpret_cast<float4*>(raw_out + pix * 64 + o8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        float* dst = raw_out + (pix0 + p) * 64 + grp * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[p][4], acc[p][5], acc[p][6], acc[p][7]);
+      }
       continue;
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = acc[j] > 0.f ? acc[j] : 0.2f * acc[j];
-    *reinterpret_cast<uint4*>(out + pix * 64 + o8) =
-        make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
-                   pack_bf16x2(acc[6], acc[7]));
+    for (int p = 0; p < 4; ++p) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = acc[p][j] > 0.f ? acc[p][j] : 0.2f * acc[p][j];
+      *reinterpret_cast<uint4*>(out + (pix0 + p) * 64 + grp * 8) =
+          make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
   }
 }
 
 cudaError_t launch_first_conv(const float* img4, const float* mask_a, const float* mask_b, long long mask_bstride,
                               const float* w, const float* bias, __nv_bfloat16* out, int B, int H, int W, int cin,
                               cudaStream_t s, float* raw_out) {
-  if (cin < 3 || cin > 5) return cudaErrorInvalidValue;
+  if (cin < 3 || cin > 5 || W % 4 != 0) return cudaErrorInvalidValue;
   if ((cin > 3 && !mask_a) || (cin > 4 && !mask_b)) return cudaErrorInvalidValue;
-  const size_t groups = (static_cast<size_t>(B) * H * W + 31) / 32;  // 32 pixels per CTA iteration
-  const size_t cap = 148 * 8;
-  first_conv_kernel<<<static_cast<unsigned>(groups < cap ? groups : cap), 256, 0, s>>>(
-      img4, mask_a, mask_b, mask_bstride, w, bias, out, raw_out, B, H, W, cin);
+  const long long groups = (static_cast<long long>(B) * H * (W / 4) + 31) / 32;  // 32 pixel groups per CTA iteration
+  if (static_cast<long long>(B) * H * (W / 4) >= (1ll << 31)) return cudaErrorInvalidValue;
+  const long long cap = 148 * 2;
+  const unsigned grid = static_cast<unsigned>(groups < cap ? groups : cap);
+  if (cin == 3)
+    first_conv_kernel<3><<<grid, 256, 0, s>>>(img4, mask_a, mask_b, mask_bstride, w, bias, out, raw_out, B, H, W);
+  else if (cin == 4)
+    first_conv_kernel<4><<<grid, 256, 0, s>>>(img4, mask_a, mask_b, mask_bstride, w, bias, out, raw_out, B, H, W);
+  else
+    first_conv_kernel<5><<<grid, 256, 0, s>>>(img4, mask_a, mask_b, mask_bstride, w, bias, out, raw_out, B, H, W);
   return cudaGetLastError();
 }
 

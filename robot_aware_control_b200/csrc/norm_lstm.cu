@@ -25,7 +25,7 @@ __device__ __forceinline__ double warp_sum_strided(const float* scr, int n, int 
 }
 
 // block = hid * R threads (R = rows of positions processed concurrently); thread t owns channel t % hid
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(512)
 norm_lstm_cell_kernel(const float* __restrict__ ih, const float* __restrict__ hh, const float* __restrict__ gnp,
                       float* __restrict__ c_state, __nv_bfloat16* __restrict__ h_out, int P, int hid, int stats_off,
                       float eps) {
@@ -45,6 +45,7 @@ norm_lstm_cell_kernel(const float* __restrict__ ih, const float* __restrict__ hh
 
   // ---- pass 1: per-thread partial sums of the 4 gates of its channel, both tensors
   float s[2][4] = {}, q[2][4] = {};
+#pragma unroll 4  // 8 independent 16-byte loads in flight per thread: the pass is latency-bound otherwise (1 CTA / SM)
   for (int p = r0; p < P; p += R) {
     const float4 a = ih4[static_cast<size_t>(p) * hid + ch];
     const float4 c = hh4[static_cast<size_t>(p) * hid + ch];
@@ -95,6 +96,7 @@ norm_lstm_cell_kernel(const float* __restrict__ ih, const float* __restrict__ hh
   __syncthreads();  // everyone has read the scratch-derived stats before c_pre / o_gate overwrite the scratch
   float cs = 0.f, cq = 0.f;
   float* cst = c_state + b * P * hid;
+#pragma unroll 4
   for (int p = r0; p < P; p += R) {
     const float4 a = ih4[static_cast<size_t>(p) * hid + ch];
     const float4 c = hh4[static_cast<size_t>(p) * hid + ch];
@@ -135,6 +137,7 @@ norm_lstm_cell_kernel(const float* __restrict__ ih, const float* __restrict__ hh
   const float cg = gnp[16 * hid + ch], cb = gnp[17 * hid + ch];
   const float mc = stats[32 + ch / cw], rc = stats[48 + 32 + ch / cw];
   __nv_bfloat16* ho = h_out + b * P * hid;
+#pragma unroll 4
   for (int p = r0; p < P; p += R) {
     const size_t i = static_cast<size_t>(p) * hid + ch;
     const float c = (c_pre[i] - mc) * rc * cg + cb;
@@ -157,12 +160,12 @@ cudaError_t norm_lstm_set_attributes() {
 
 cudaError_t launch_norm_lstm_cell(const float* ih, const float* hh, const float* gn_params, float* c_state,
                                   __nv_bfloat16* h_out, int B, int P, int hid, cudaStream_t s) {
-  if (hid % 64 != 0 || hid > 1024) return cudaErrorInvalidValue;
+  if (hid % 64 != 0 || hid > 512) return cudaErrorInvalidValue;
   const int R = hid >= 512 ? 1 : 512 / hid;
   const int T = hid * R;
   const size_t off = norm_lstm_stats_off(P, hid, T);
   const size_t smem = (off + 96 + 2 * static_cast<size_t>(T)) * 4;
-  if (T > 1024 || smem > 227 * 1024) return cudaErrorInvalidValue;
+  if (T > 512 || smem > 227 * 1024) return cudaErrorInvalidValue;
   norm_lstm_cell_kernel<<<B, T, smem, s>>>(ih, hh, gn_params, c_state, h_out, P, hid, static_cast<int>(off), 1e-5f);
   return cudaGetLastError();
 }

@@ -269,6 +269,29 @@ void set_act(ConvOp* op, bf16* out, int cstride, int coff, int upsample, int lre
   op->e.out = out; op->e.out_cstride = cstride; op->e.out_coff = coff; op->e.upsample = upsample; op->e.lrelu = lrelu;
 }
 
+// live timing of the small non-GEMM kernels through the same hook (rac_profile_begin with their name)
+struct ProfScope {
+  rac_handle* h;
+  cudaStream_t st;
+  bool timed = false;
+  ProfScope(rac_handle* h_, const char* name, cudaStream_t st_) : h(h_), st(st_) {
+    if (!h->prof_prefix.empty() && strstr(name, h->prof_prefix.c_str()) != nullptr) {
+      if (h->prof_used + 2 <= h->prof_ev.size()) {
+        timed = true;
+        cudaEventRecord(h->prof_ev[h->prof_used], st);
+      } else {
+        h->prof_dropped++;
+      }
+    }
+  }
+  ~ProfScope() {
+    if (timed) {
+      cudaEventRecord(h->prof_ev[h->prof_used + 1], st);
+      h->prof_used += 2;
+    }
+  }
+};
+
 int launch(rac_handle* h, const ConvOp& op, cudaStream_t st) {
   bool timed = false;
   if (!h->prof_prefix.empty() && strstr(op.name, h->prof_prefix.c_str()) != nullptr) {
@@ -540,7 +563,10 @@ int launch_lstm(rac_handle* h, int l, cudaStream_t st) {
     for (int k = 0; k < 2; ++k) {
       CKR(launch(h, w.lstm[l][k][p], st));
       CKR(launch(h, w.lstm_hh[l][k][p], st));
-      CK(launch_norm_lstm_cell(w.gn_ih, w.gn_hh, h->gn_params[l][k], w.cs[l][k], w.hs[l][k][p ^ 1], w.B, 48, g, st));
+      {
+        ProfScope ps(h, "norm_lstm_cell", st);
+        CK(launch_norm_lstm_cell(w.gn_ih, w.gn_hh, h->gn_params[l][k], w.cs[l][k], w.hs[l][k][p ^ 1], w.B, 48, g, st));
+      }
       h->launches++;
     }
     h->hidden_zero[l] = false;
@@ -562,20 +588,32 @@ int run_step(rac_handle* h, const StepArgs& a, cudaStream_t st) {
   const int ks = a.keep_skip ? 1 : 0;
   if (ks) CKR(ensure_keep_skip(h));
   // ---- encoder (vgg_64.py:122-129)
-  CK(launch_first_conv(w.img, c.use_mask ? a.mask_a : nullptr, (c.use_mask && c.use_future_mask) ? a.mask_b : nullptr,
-                       a.mask_bstride, static_cast<const float*>(h->layer[RAC_L_ENC_C1_0].w), h->layer[RAC_L_ENC_C1_0].bias, w.a1, B,
-                       48, 64, h->enc_cin, st));
+  {
+    ProfScope ps(h, "encoder.c1.0", st);
+    CK(launch_first_conv(w.img, c.use_mask ? a.mask_a : nullptr, (c.use_mask && c.use_future_mask) ? a.mask_b : nullptr,
+                         a.mask_bstride, static_cast<const float*>(h->layer[RAC_L_ENC_C1_0].w), h->layer[RAC_L_ENC_C1_0].bias, w.a1, B,
+                         48, 64, h->enc_cin, st));
+  }
   h->launches++;
   ConvOp* e = w.enc[ks];
   CKR(launch(h, e[1], st));
-  CK(launch_maxpool2(e[1].e.out, e[1].e.out_cstride, e[1].e.out_coff, w.p1, B, 48, 64, 64, st));
+  {
+    ProfScope ps(h, "maxpool.1", st);
+    CK(launch_maxpool2(e[1].e.out, e[1].e.out_cstride, e[1].e.out_coff, w.p1, B, 48, 64, 64, st));
+  }
   CKR(launch(h, e[2], st));
   CKR(launch(h, e[3], st));
-  CK(launch_maxpool2(e[3].e.out, e[3].e.out_cstride, e[3].e.out_coff, w.p2, B, 24, 32, 128, st));
+  {
+    ProfScope ps(h, "maxpool.2", st);
+    CK(launch_maxpool2(e[3].e.out, e[3].e.out_cstride, e[3].e.out_coff, w.p2, B, 24, 32, 128, st));
+  }
   CKR(launch(h, e[4], st));
   CKR(launch(h, e[5], st));
   CKR(launch(h, e[6], st));
-  CK(launch_maxpool2(e[6].e.out, e[6].e.out_cstride, e[6].e.out_coff, w.p3, B, 12, 16, 256, st));
+  {
+    ProfScope ps(h, "maxpool.3", st);
+    CK(launch_maxpool2(e[6].e.out, e[6].e.out_cstride, e[6].e.out_coff, w.p3, B, 12, 16, 256, st));
+  }
   CKR(launch(h, e[7], st));
   CKR(launch(h, e[8], st));
   CKR(launch(h, e[9], st));
@@ -876,8 +914,11 @@ int rac_rollout_cost(rac_handle* h, const rac_rollout* r, void* stream) {
       CK(cudaMemcpyAsync(r->obs_out + static_cast<size_t>(t) * n * P0 * 4, w.img, sizeof(float) * n * P0 * 4,
                          cudaMemcpyDeviceToDevice, st));
     const int use = (!r->sparse_cost || t == r->steps - 1) ? 1 : 0;  // trajectory_sampler.py:167
-    CK(launch_cost_finish(w.cost_part, 96, r->dontcare_cost, r->world_cost_weight, use, r->sum_cost,
-                          r->step_cost_out ? r->step_cost_out + static_cast<size_t>(t) * n : nullptr, n, st));
+    {
+      ProfScope ps(h, "cost_finish", st);
+      CK(launch_cost_finish(w.cost_part, 96, r->dontcare_cost, r->world_cost_weight, use, r->sum_cost,
+                            r->step_cost_out ? r->step_cost_out + static_cast<size_t>(t) * n : nullptr, n, st));
+    }
     h->launches++;
   }
   return RAC_OK;
