@@ -14,7 +14,9 @@
 
 namespace rac {
 
-enum EpiMode : int { EPI_ACT = 0, EPI_LSTM = 1, EPI_GAUSS = 2, EPI_FRAME = 3, EPI_F32 = 4 };
+// EPI_LSTM = inference cell (MUFU math, epilogue-private cell-state layout); EPI_LSTM_TRAIN = training cell (libm math,
+// NHWC cell state read from c_in, gates saved for the backward pass) -- separate instantiations keep each one's code small
+enum EpiMode : int { EPI_ACT = 0, EPI_LSTM = 1, EPI_GAUSS = 2, EPI_FRAME = 3, EPI_F32 = 4, EPI_LSTM_TRAIN = 5 };
 
 // One destination of the fp32 epilogue: packed columns [n_begin, n_end) of the GEMM go to dst (row-major NHWC rows,
 // `cstride` floats per row, starting at channel `coff`); accumulate: += instead of =. Bounds are multiples of 32.
@@ -52,7 +54,8 @@ struct EpiParams {
   int hid;
   const float* c_in;     // training: previous cell state read from here (null: c_state, in place)
   float* gates_out;      // training: post-activation gates fp32 [B*H*W, 4*hid] in packed column order (null: not saved)
-  int exact_math;        // training: libm tanh / exp instead of MUFU.TANH (gradients are checked against fp32 autograd)
+  int c_tiled;           // EPI_LSTM: c_state uses the epilogue-private tiled layout (epilogue.cuh::lstm_load_c)
+  int exact_math;        // (set by the training path; EPI_LSTM_TRAIN always uses libm tanh / exp: gradients are checked against fp32 autograd)
   // EPI_F32 (training: raw pre-BatchNorm conv output, dgrad into gradient accumulators, wgrad into packed dW)
   F32Seg seg[3];
   int nseg;

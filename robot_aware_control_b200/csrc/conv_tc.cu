@@ -34,7 +34,7 @@ struct TcCfg {
   static constexpr int kTmemCols = kTmemNeed <= 32 ? 32 : (kTmemNeed <= 64 ? 64 : (kTmemNeed <= 128 ? 128 : (kTmemNeed <= 256 ? 256 : 512)));
   static constexpr int kEpiThreads = BLOCK_M;                // one thread per output row
   static constexpr int kThreads = 128 + kEpiThreads;
-  static constexpr int kBarBytes = 1024;
+  static constexpr int kBarBytes = 2048;  // mbarriers + TMEM slot (first 512 B) + LSTM bias tile (BLOCK_N floats at +1024)
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024 alignment slack
   static_assert(kTmemNeed <= 512, "accumulators do not fit TMEM");
   static_assert(kStages >= 2, "pipeline needs at least two stages");
@@ -170,6 +170,8 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
     int acc = 0;
     uint32_t acc_phase = 0;
     constexpr int CH = (BLOCK_N >= 32) ? 32 : 16;
+    float* s_bias = reinterpret_cast<float*>(bar_base + 1024);
+    int bias_tile = -1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_tile = tile / g.num_m_tiles;
       const int m_tile = tile - n_tile * g.num_m_tiles;
@@ -179,33 +181,63 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
       const int y = yb * g.BH + ((r >> g.w_shift) & (g.BH - 1));
       const int x = r & (g.W - 1);
       const bool valid = b < g.B;
+      constexpr bool kLstm = (EPI == EPI_LSTM || EPI == EPI_LSTM_TRAIN);
+      constexpr bool kTrain = (EPI == EPI_LSTM_TRAIN);
+      const size_t ctile = (static_cast<size_t>(m_tile) * (e.hid >> 3) * 2 * BLOCK_M + r) * 4;
+      if constexpr (kLstm) {
+        // the BLOCK_N gate biases of this column tile go to shared memory while the main loop is still running
+        // (every epilogue thread needs all of them: 8 broadcast LDS.128 per chunk instead of 8 global loads)
+        if (n_tile != bias_tile) {
+          epi_bar_sync(Cfg::kEpiThreads);  // nobody still reads the previous tile's values
+          for (int i = r; i < BLOCK_N; i += Cfg::kEpiThreads) s_bias[i] = __ldg(e.bias + n_tile * BLOCK_N + i);
+          epi_bar_sync(Cfg::kEpiThreads);
+          bias_tile = n_tile;
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * Cfg::kAccCols + sub * BLOCK_N;
-      // software pipeline over column chunks: the TMEM load (and, for the LSTM, the cell-state load) of chunk c+1 is
-      // in flight while chunk c is processed -- the epilogue is exposed when the tile uses all of TMEM
+      // Software pipeline over column chunks, two chunks per (rolled) iteration: the TMEM load and, for the LSTM, the
+      // cell-state load of the next chunk are in flight while a chunk is processed. The loop is NOT fully unrolled:
+      // the straight-line epilogue of the 256-column tile was 37 KB of code and lost a third of its time to
+      // instruction fetch (ncu stall_no_inst); the epilogue of this tile is exposed (single TMEM stage).
       constexpr int kChunks = BLOCK_N / CH;
       float v[2][CH];
       float cprev[2][8];
       auto issue = [&](int c, float* dst) {
         if constexpr (CH == 32) tmem_ld32(t_row + c * CH, dst); else tmem_ld16(t_row + c * CH, dst);
       };
-      issue(0, v[0]);
-      if constexpr (EPI == EPI_LSTM) lstm_load_c(g, e, b, y, x, valid, n_tile * BLOCK_N, cprev[0]);
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        const int cur = c & 1;
-        tmem_ld_wait();
-        if (c + 1 < kChunks) {
-          issue(c + 1, v[cur ^ 1]);
-          if constexpr (EPI == EPI_LSTM) lstm_load_c(g, e, b, y, x, valid, n_tile * BLOCK_N + (c + 1) * CH, cprev[cur ^ 1]);
-        }
+      auto load_c = [&](int c, float* dst) {
+        if constexpr (kLstm) lstm_load_c<kTrain>(g, e, b, y, x, valid, n_tile * BLOCK_N + c * CH, dst, ctile, BLOCK_M);
+      };
+      auto process = [&](int c, const float* acc_v, const float* cp) {
         const int n0 = n_tile * BLOCK_N + c * CH;
-        if constexpr (EPI == EPI_ACT) epi_act<CH>(g, e, b, y, x, valid, n0, v[cur]);
-        if constexpr (EPI == EPI_LSTM) epi_lstm(g, e, b, y, x, valid, n0, v[cur], cprev[cur]);
-        if constexpr (EPI == EPI_GAUSS) epi_gauss(g, e, b, y, x, valid, n0, v[cur]);
-        if constexpr (EPI == EPI_FRAME) epi_frame(g, e, b, y, x, valid, yb * (BLOCK_M / 32) + we, v[cur]);
-        if constexpr (EPI == EPI_F32) epi_f32<CH>(g, e, b, y, x, valid, n0, v[cur]);
+        if constexpr (EPI == EPI_ACT) epi_act<CH>(g, e, b, y, x, valid, n0, acc_v);
+        if constexpr (kLstm) epi_lstm<kTrain>(g, e, b, y, x, valid, n0, acc_v, cp, ctile, BLOCK_M, s_bias + c * CH);
+        if constexpr (EPI == EPI_GAUSS) epi_gauss(g, e, b, y, x, valid, n0, acc_v);
+        if constexpr (EPI == EPI_FRAME) epi_frame(g, e, b, y, x, valid, yb * (BLOCK_M / 32) + we, acc_v);
+        if constexpr (EPI == EPI_F32) epi_f32<CH>(g, e, b, y, x, valid, n0, acc_v);
+      };
+      issue(0, v[0]);
+      load_c(0, cprev[0]);
+      if constexpr (kChunks == 1) {
+        tmem_ld_wait();
+        process(0, v[0], cprev[0]);
+      } else {
+        static_assert(kChunks == 1 || kChunks % 2 == 0, "column chunks are processed in pairs");
+#pragma unroll 1
+        for (int c = 0; c < kChunks; c += 2) {
+          tmem_ld_wait();
+          issue(c + 1, v[1]);
+          load_c(c + 1, cprev[1]);
+          process(c, v[0], cprev[0]);
+          tmem_ld_wait();
+          if (c + 2 < kChunks) {
+            issue(c + 2, v[0]);
+            load_c(c + 2, cprev[0]);
+          }
+          process(c + 1, v[1], cprev[1]);
+        }
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
@@ -267,10 +299,12 @@ conv_simt_kernel(const ConvRaw raw, const ConvGeom g, const EpiParams e) {
     }
   }
   if constexpr (EPI == EPI_ACT) epi_act<CH>(g, e, b, y, x, valid, n0, acc);
-  if constexpr (EPI == EPI_LSTM) {
+  if constexpr (EPI == EPI_LSTM || EPI == EPI_LSTM_TRAIN) {
+    constexpr bool kTrain = (EPI == EPI_LSTM_TRAIN);
     float cprev[8];
-    lstm_load_c(g, e, b, y, x, valid, n0, cprev);
-    epi_lstm(g, e, b, y, x, valid, n0, acc, cprev);
+    const size_t ctile = (static_cast<size_t>(m_tile) * (e.hid >> 3) * 2 * BLOCK_M + r) * 4;
+    lstm_load_c<kTrain>(g, e, b, y, x, valid, n0, cprev, ctile, BLOCK_M);
+    epi_lstm<kTrain>(g, e, b, y, x, valid, n0, acc, cprev, ctile, BLOCK_M, e.bias + n0);
   }
   if constexpr (EPI == EPI_GAUSS) epi_gauss(g, e, b, y, x, valid, n0, acc);
   if constexpr (EPI == EPI_FRAME) epi_frame(g, e, b, y, x, valid, yb * (BLOCK_M / 32) + (r >> 5), acc);
@@ -310,6 +344,8 @@ static cudaError_t launch_simt_t(const ConvOp& op, cudaStream_t stream) {
   X(128, 128, EPI_ACT)      \
   X(128, 64, EPI_ACT)       \
   X(128, 128, EPI_LSTM)     \
+  X(256, 256, EPI_LSTM_TRAIN) \
+  X(128, 128, EPI_LSTM_TRAIN) \
   X(128, 128, EPI_GAUSS)    \
   X(128, 16, EPI_FRAME)
 

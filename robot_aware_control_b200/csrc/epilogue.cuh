@@ -96,28 +96,43 @@ __device__ __forceinline__ void epi_act(const ConvGeom& g, const EpiParams& e, i
 __device__ __forceinline__ bool lstm_chunk_live(const EpiParams& e, bool valid, int n0) {
   return valid && n0 + 32 <= e.cout;
 }
+// Cell-state layout. Training keeps c in NHWC [B,H,W,hid] (its backward kernels read it). Inference (e.c_tiled) uses a
+// layout private to this epilogue -- c is read and written by nothing else: [m_tile][8-channel group][half][row][4],
+// so that the 32 lanes of a warp (32 consecutive tile rows) touch 512 contiguous bytes per 16-byte access instead of
+// 32 different 128-byte lines (row stride hid * 4 B), which made the exposed epilogue of the 256x256 tile store-bound.
+// `ctile` = float offset of (m_tile, row) in that layout: (m_tile * (hid / 8) * 2 * BLOCK_M + row) * 4; bm = BLOCK_M.
+template <bool TRAIN>
 __device__ __forceinline__ void lstm_load_c(const ConvGeom& g, const EpiParams& e, int b, int y, int x, bool valid,
-                                            int n0, float* cprev) {
+                                            int n0, float* cprev, size_t ctile, int bm) {
   if (!lstm_chunk_live(e, valid, n0)) return;
+  if (!TRAIN && e.c_tiled) {
+    const float* src = e.c_state + ctile + static_cast<size_t>(n0 >> 5) * (8 * bm);
+    *reinterpret_cast<float4*>(cprev) = *reinterpret_cast<const float4*>(src);
+    *reinterpret_cast<float4*>(cprev + 4) = *reinterpret_cast<const float4*>(src + 4 * bm);
+    return;
+  }
   const size_t base = (static_cast<size_t>(b * g.H + y) * g.W + x) * e.hid + (n0 >> 2);
-  const float* src = e.c_in ? e.c_in : e.c_state;
+  const float* src = (TRAIN && e.c_in) ? e.c_in : e.c_state;
   *reinterpret_cast<float4*>(cprev) = *reinterpret_cast<const float4*>(src + base);
   *reinterpret_cast<float4*>(cprev + 4) = *reinterpret_cast<const float4*>(src + base + 4);
 }
+// bias: the 32 bias values of this chunk (global or shared memory)
+template <bool TRAIN>
 __device__ __forceinline__ void epi_lstm(const ConvGeom& g, const EpiParams& e, int b, int y, int x, bool valid, int n0,
-                                         const float* acc, const float* cprev) {
+                                         const float* acc, const float* cprev, size_t ctile, int bm,
+                                         const float* bias) {
   if (!lstm_chunk_live(e, valid, n0)) return;
   const size_t base = (static_cast<size_t>(b * g.H + y) * g.W + x) * e.hid + (n0 >> 2);
-  const float4* bias4 = reinterpret_cast<const float4*>(e.bias + n0);
+  const float4* bias4 = reinterpret_cast<const float4*>(bias);
   float cn[8], hn[8];
-  float4* gsave = e.gates_out
+  float4* gsave = (TRAIN && e.gates_out)
                       ? reinterpret_cast<float4*>(e.gates_out + (static_cast<size_t>(b * g.H + y) * g.W + x) * (4 * e.hid) + n0)
                       : nullptr;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const float4 bq = __ldg(bias4 + q);
+    const float4 bq = bias4[q];
     float ig, fg, og, cg;
-    if (e.exact_math) {
+    if (TRAIN) {
       ig = sigmoidf_(acc[4 * q + 0] + bq.x); fg = sigmoidf_(acc[4 * q + 1] + bq.y);
       og = sigmoidf_(acc[4 * q + 2] + bq.z); cg = tanhf(acc[4 * q + 3] + bq.w);
       cn[q] = fg * cprev[q] + ig * cg;
@@ -128,10 +143,16 @@ __device__ __forceinline__ void epi_lstm(const ConvGeom& g, const EpiParams& e, 
       cn[q] = fg * cprev[q] + ig * cg;
       hn[q] = og * tanh_fast(cn[q]);
     }
-    if (gsave) gsave[q] = make_float4(ig, fg, og, cg);
+    if (TRAIN && gsave) gsave[q] = make_float4(ig, fg, og, cg);
   }
-  *reinterpret_cast<float4*>(e.c_state + base) = *reinterpret_cast<float4*>(cn);
-  *reinterpret_cast<float4*>(e.c_state + base + 4) = *reinterpret_cast<float4*>(cn + 4);
+  if (!TRAIN && e.c_tiled) {
+    float* dst = e.c_state + ctile + static_cast<size_t>(n0 >> 5) * (8 * bm);
+    *reinterpret_cast<float4*>(dst) = *reinterpret_cast<float4*>(cn);
+    *reinterpret_cast<float4*>(dst + 4 * bm) = *reinterpret_cast<float4*>(cn + 4);
+  } else {
+    *reinterpret_cast<float4*>(e.c_state + base) = *reinterpret_cast<float4*>(cn);
+    *reinterpret_cast<float4*>(e.c_state + base + 4) = *reinterpret_cast<float4*>(cn + 4);
+  }
   *reinterpret_cast<uint4*>(e.h_out + base) = make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]),
                                                          pack_bf16x2(hn[4], hn[5]), pack_bf16x2(hn[6], hn[7]));
 }

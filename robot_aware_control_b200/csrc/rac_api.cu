@@ -88,6 +88,7 @@ struct rac_handle {
   int cur[3] = {0, 0, 0};  // ping-pong index of the live hidden state per LSTM stack
   bool hidden_zero[3] = {false, false, false};  // h == 0 since init_hidden: the h_prev half of K is skipped
   int skip_zero_hidden = 1;  // RAC_SKIP_ZERO_H=0 disables the skip (A/B measurements)
+  int c_tiled = 1;           // RAC_C_TILED=0: cell state in NHWC instead of the epilogue-private tiled layout (diagnosis)
   EncodeTiledFn encode = nullptr;
   int64_t launches = 0;
   char err[512] = {0};
@@ -354,7 +355,7 @@ void carve(rac_handle* h, Bump& bp, int B) {
   for (int l = 0; l < 3; ++l)
     for (int k = 0; k < 2; ++k) {
       for (int p = 0; p < 2; ++p) w.hs[l][k][p] = bp.take<bf16>(n * P3 * g);
-      w.cs[l][k] = bp.take<float>(n * P3 * g);
+      w.cs[l][k] = bp.take<float>(((n + 15) / 16 * 16) * P3 * g);  // whole latent tiles: the tiled layout pads the batch
     }
   w.d2a = bp.take<bf16>(n * P3 * 512);
   w.d2b = bp.take<bf16>(n * P3 * 512);
@@ -435,10 +436,10 @@ int build_ops(rac_handle* h) {
     for (int p = 0; p < 2; ++p) {
       ConvOp* a = &w.lstm[l][0][p];
       CKR(make_conv(h, a, n0[l], l0[l], 6, 8, {{xin[l], g}, {w.hs[l][0][p], g}}, EPI_LSTM));
-      a->e.c_state = w.cs[l][0]; a->e.h_out = w.hs[l][0][p ^ 1]; a->e.hid = g;
+      a->e.c_state = w.cs[l][0]; a->e.h_out = w.hs[l][0][p ^ 1]; a->e.hid = g; a->e.c_tiled = h->c_tiled;
       ConvOp* b = &w.lstm[l][1][p];
       CKR(make_conv(h, b, n1[l], l1[l], 6, 8, {{w.hs[l][0][p ^ 1], g}, {w.hs[l][1][p], g}}, EPI_LSTM));
-      b->e.c_state = w.cs[l][1]; b->e.h_out = w.hs[l][1][p ^ 1]; b->e.hid = g;
+      b->e.c_state = w.cs[l][1]; b->e.h_out = w.hs[l][1][p ^ 1]; b->e.hid = g; b->e.c_tiled = h->c_tiled;
     }
   for (int p = 0; p < 2; ++p) {
     CKR(make_conv(h, &w.gauss[0][p], "prior.mu_net|logvar_net", RAC_L_PRIOR_GAUSS, 6, 8, {{w.hs[0][1][p ^ 1], g}}, EPI_GAUSS));
@@ -712,6 +713,7 @@ int rac_create(const rac_config* cfg, rac_handle** out) {
   if (!fn || qres != cudaDriverEntryPointSuccess) return fail(h, RAC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
   h->encode = reinterpret_cast<EncodeTiledFn>(fn);
   if (const char* sz = getenv("RAC_SKIP_ZERO_H")) h->skip_zero_hidden = atoi(sz) != 0;
+  if (const char* ct = getenv("RAC_C_TILED")) h->c_tiled = atoi(ct) != 0;
   if (const char* tm = getenv("RAC_TILE_M")) {
     const int v = atoi(tm);
     if (v != 128 && v != 256) return fail(h, RAC_ERR_INVALID, "RAC_TILE_M must be 128 or 256");
@@ -828,7 +830,7 @@ int rac_init_hidden(rac_handle* h, int batch, void* stream) {
   for (int l = 0; l < 3; ++l)
     for (int k = 0; k < 2; ++k) {
       for (int p = 0; p < 2; ++p) CK(cudaMemsetAsync(w.hs[l][k][p], 0, ne * 2, st));
-      CK(cudaMemsetAsync(w.cs[l][k], 0, ne * 4, st));
+      CK(cudaMemsetAsync(w.cs[l][k], 0, static_cast<size_t>((batch + 15) / 16 * 16) * 48 * h->cfg.g_dim * 4, st));
     }
   h->cur[0] = h->cur[1] = h->cur[2] = 0;
   h->hidden_zero[0] = h->hidden_zero[1] = h->hidden_zero[2] = true;

@@ -229,7 +229,7 @@ int lstm_forward(rac_handle* h, TrainState* T, int s, int t, const bf16* xin, cu
     e.c_state = tp.cs[s][l]; e.h_out = tp.hs[s][l]; e.gates_out = tp.gates[s][l]; e.exact_math = 1;
     const int ks = l == 0 ? 5 : 3;
     CKR(t_gemm(h, "train.lstm.fwd", {B, 6, 8, ks, false}, {{x, g}, {hprev, g}}, L.wp, ks * ks * 2 * g, L.n_packed,
-               tile_block_n(L.n_packed, EPI_LSTM), EPI_LSTM, e, st));
+               tile_block_n(L.n_packed, EPI_LSTM_TRAIN), EPI_LSTM_TRAIN, e, st));
     x = tp.hs[s][l];
   }
   return RAC_OK;
