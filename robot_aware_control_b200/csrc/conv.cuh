@@ -75,7 +75,8 @@ struct EpiParams {
   const float* goal_img;   // [H,W,4] fp32
   const float* goal_mask;  // [H,W] fp32 or null
   float* xpred_out;        // NCHW (B,4,H,W) fp32 or null
-  float* cost_part;        // [B][H*W/32][2] (sum of squares, world pixel count), one partial per warp, or null
+  float* cost_part;        // [B][cost_nparts][2] (sum of squares, world pixel count), one partial per warp, or null
+  int cost_nparts;         // partials per candidate: H*W/32 (generic kernel) or 128 (halo kernel: 16 tiles x 8 warps)
   int zero_robot, dontcare;
 };
 
@@ -95,6 +96,9 @@ struct ConvOp {
   EpiParams e;
   ConvTmaps tm;
   ConvRaw raw;
+  CUtensorMap tm_halo;   // halo kernel (conv_halo.cu): activation map with a column-major box
+  int halo;              // 1: launch conv_halo_kernel instead of conv_tc_kernel
+  int halo_column_loads; // 1: tm_halo is the per-column fallback map
   int block_m;
   int block_n;
   int epi;
@@ -105,5 +109,10 @@ struct ConvOp {
 cudaError_t launch_conv_tc(const ConvOp& op, int num_sms, cudaStream_t stream);
 cudaError_t launch_conv_simt(const ConvOp& op, cudaStream_t stream);
 cudaError_t conv_tc_set_attributes();
+// halo-tile kernel for the 64-wide full-resolution 3x3 layers (conv_halo.cu)
+bool conv_halo_supported(const ConvOp& op);
+cudaError_t launch_conv_halo(const ConvOp& op, const CUtensorMap& tm_a, int column_loads, int use_base_offset,
+                             int num_sms, cudaStream_t stream);
+cudaError_t conv_halo_set_attributes();
 
 }  // namespace rac

@@ -276,8 +276,10 @@ __device__ __forceinline__ void epi_frame(const ConvGeom& g, const EpiParams& e,
       sq += __shfl_xor_sync(0xffffffffu, sq, o);
       cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     }
-    if ((threadIdx.x & 31) == 0 && valid) {
-      float* dst = e.cost_part + (static_cast<size_t>(b) * (g.H * g.W / 32) + part_idx) * 2;  // one partial per warp
+    // all lanes of a warp belong to one candidate; lane 0 itself may be a discarded halo row (halo kernel)
+    const bool any_valid = __any_sync(0xffffffffu, valid);
+    if ((threadIdx.x & 31) == 0 && any_valid) {
+      float* dst = e.cost_part + (static_cast<size_t>(b) * e.cost_nparts + part_idx) * 2;  // one partial per warp
       dst[0] = sq;
       dst[1] = cnt;
     }

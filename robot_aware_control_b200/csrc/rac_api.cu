@@ -88,6 +88,10 @@ struct rac_handle {
   int cur[3] = {0, 0, 0};  // ping-pong index of the live hidden state per LSTM stack
   bool hidden_zero[3] = {false, false, false};  // h == 0 since init_hidden: the h_prev half of K is skipped
   int skip_zero_hidden = 1;  // RAC_SKIP_ZERO_H=0 disables the skip (A/B measurements)
+  int use_halo = 1;          // RAC_HALO=0: generic kernel for the 64-wide full-resolution layers too (A/B measurements)
+  int halo_base_offset = 0;  // RAC_HALO_BASE_OFFSET=1 sets the descriptor base-offset field for the row-shifted operands: WRONG on
+                             // B200 (measured: the 128B swizzle phase follows the absolute smem address bits [7:9])
+  int halo_force_columns = 0;  // RAC_HALO_COLUMNS=1: per-column TMA loads even if the permuted-stride map encodes
   int c_tiled = 1;           // RAC_C_TILED=0: cell state in NHWC instead of the epilogue-private tiled layout (diagnosis)
   EncodeTiledFn encode = nullptr;
   int64_t launches = 0;
@@ -211,6 +215,35 @@ int encode_w_map(rac_handle* h, CUtensorMap* m, const bf16* ptr, int K, int N, i
   return RAC_OK;
 }
 
+// Halo kernel activation map. Preferred: dims (C, H, W, B) -- H and W swapped through the strides -- so that ONE box
+// {64, 8, 34, 1} lands column-major (8 rows of a column = one swizzle atom). If the driver rejects the non-monotonic
+// strides: dims (C, W, H, B) with a one-column box {64, 1, 8, 1}, loaded 34 times per tile.
+int encode_halo_map(rac_handle* h, CUtensorMap* m, const bf16* ptr, int C, int B, int H, int W, int* column_loads) {
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  if (!h->halo_force_columns) {
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(W),
+                          static_cast<cuuint64_t>(B)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(W) * C * 2, static_cast<cuuint64_t>(C) * 2,
+                             static_cast<cuuint64_t>(H) * W * C * 2};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(kBlockK), 8, 34, 1};
+    CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(ptr), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) { *column_loads = 0; return RAC_OK; }
+  }
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
+                           static_cast<cuuint64_t>(H) * W * C * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(kBlockK), 1, 8, 1};
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(ptr), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, RAC_ERR_CUDA, "cuTensorMapEncodeTiled(halo column map C=%d) failed: %d", C, (int)r);
+  *column_loads = 1;
+  return RAC_OK;
+}
+
 struct Src {
   const bf16* p;
   int C;
@@ -263,6 +296,12 @@ int make_conv(rac_handle* h, ConvOp* op, const char* name, int layer, int H, int
   CKR(encode_w_map(h, &op->tm.w, wp, s.ks * s.ks * s.ctot, s.n_packed, op->block_n));
   op->e.bias = h->layer[layer].bias;
   op->e.cout = s.cout;
+  op->e.cost_nparts = H * W / 32;
+  if (h->use_halo && h->cfg.conv_impl == 0 && h->tile_m == 256 && conv_halo_supported(*op)) {
+    CKR(encode_halo_map(h, &op->tm_halo, srcs[0].p, srcs[0].C, B, H, W, &op->halo_column_loads));
+    op->halo = 1;
+    op->e.cost_nparts = 128;
+  }
   return RAC_OK;
 }
 
@@ -303,7 +342,9 @@ int launch(rac_handle* h, const ConvOp& op, cudaStream_t st) {
       h->prof_dropped++;
     }
   }
-  cudaError_t e = h->cfg.conv_impl == 1 ? launch_conv_simt(op, st) : launch_conv_tc(op, h->num_sms, st);
+  cudaError_t e = h->cfg.conv_impl == 1 ? launch_conv_simt(op, st)
+                  : op.halo ? launch_conv_halo(op, op.tm_halo, op.halo_column_loads, h->halo_base_offset, h->num_sms, st)
+                            : launch_conv_tc(op, h->num_sms, st);
   if (timed) {
     cudaEventRecord(h->prof_ev[h->prof_used + 1], st);
     h->prof_used += 2;
@@ -367,7 +408,7 @@ void carve(rac_handle* h, Bump& bp, int B) {
     w.gn_ih = bp.take<float>(n * P3 * 4 * g);
     w.gn_hh = bp.take<float>(n * P3 * 4 * g);
   }
-  w.cost_part = bp.take<float>(n * 96 * 2);
+  w.cost_part = bp.take<float>(n * 128 * 2);
   w.goal4 = bp.take<float>(static_cast<size_t>(kMaxGoals) * P0 * 4);
 }
 
@@ -484,7 +525,7 @@ void name_buffers(rac_handle* h) {
   put("d3a", w.d3a, n * 192 * 256, 2);
   put("d4a", w.d4a, n * 768 * 128, 2);
   put("d5", w.d5, n * 3072 * 64, 2);
-  put("cost_part", w.cost_part, n * 96 * 2, 4);
+  put("cost_part", w.cost_part, n * 128 * 2, 4);
   const char* hn[3] = {"prior", "post", "fp"};
   for (int l = 0; l < 3; ++l)
     for (int k = 0; k < 2; ++k) {
@@ -714,6 +755,10 @@ int rac_create(const rac_config* cfg, rac_handle** out) {
   h->encode = reinterpret_cast<EncodeTiledFn>(fn);
   if (const char* sz = getenv("RAC_SKIP_ZERO_H")) h->skip_zero_hidden = atoi(sz) != 0;
   if (const char* ct = getenv("RAC_C_TILED")) h->c_tiled = atoi(ct) != 0;
+  if (const char* v = getenv("RAC_HALO")) h->use_halo = atoi(v) != 0;
+  if (const char* v = getenv("RAC_HALO_BASE_OFFSET")) h->halo_base_offset = atoi(v) != 0;
+  if (const char* v = getenv("RAC_HALO_COLUMNS")) h->halo_force_columns = atoi(v) != 0;
+  CK(conv_halo_set_attributes());
   if (const char* tm = getenv("RAC_TILE_M")) {
     const int v = atoi(tm);
     if (v != 128 && v != 256) return fail(h, RAC_ERR_INVALID, "RAC_TILE_M must be 128 or 256");
@@ -918,7 +963,7 @@ int rac_rollout_cost(rac_handle* h, const rac_rollout* r, void* stream) {
     const int use = (!r->sparse_cost || t == r->steps - 1) ? 1 : 0;  // trajectory_sampler.py:167
     {
       ProfScope ps(h, "cost_finish", st);
-      CK(launch_cost_finish(w.cost_part, 96, r->dontcare_cost, r->world_cost_weight, use, r->sum_cost,
+      CK(launch_cost_finish(w.cost_part, w.dec[9][0].e.cost_nparts, r->dontcare_cost, r->world_cost_weight, use, r->sum_cost,
                             r->step_cost_out ? r->step_cost_out + static_cast<size_t>(t) * n : nullptr, n, st));
     }
     h->launches++;
