@@ -216,7 +216,7 @@ def run_train_reference_arm(args):
 
 def run_train_bench(args):
     """Extra (not the headline metric): samples/s of the SVG training step, one JSON line."""
-    os.environ["NCCL_DEBUG"] = os.environ.get("RAC_NCCL_DEBUG", "WARN")
+    quiet_nccl()
     import torch.distributed as dist
     from oracle import svg_oracle as so
     from robot_aware_control_b200 import SVGConvModel, SVGTrainer
@@ -289,6 +289,16 @@ def run_train_bench(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def quiet_nccl():
+    """stdout must carry exactly one JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=WARN/VERSION/INFO,
+    so debugging output is opt-in (RAC_NCCL_DEBUG=INFO) and always sent to stderr."""
+    os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+    if "RAC_NCCL_DEBUG" in os.environ:
+        os.environ["NCCL_DEBUG"] = os.environ["RAC_NCCL_DEBUG"]
+    else:
+        os.environ.pop("NCCL_DEBUG", None)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -311,7 +321,7 @@ def main():
     if args.train:
         return run_train_bench(args)
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("RAC_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+    quiet_nccl()  # keep stdout to the one JSON line
     import torch.distributed as dist
     from oracle import svg_oracle as so  # only for the deterministic synthetic weights + the cpu_baseline leg
     from robot_aware_control_b200 import CEMPolicy, DemoGoalState, State, SVGConvModel, _lib
@@ -429,8 +439,8 @@ def main():
         "kernel": "conv_tc_kernel<256, 256, EPI_LSTM> on {prior,frame_predictor}.lstm.0.gates (5x5, 1024->2048)",
         "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2000 candidates, ncu --set full capture
-        # profiles/r01_lstm_gates_ncu_tile256.txt (2.133 GB + 0.289 GB); not re-measured by this run
-        "traffic": 2.42e9 if n_local == 2000 else None,
+        # profiles/r01_lstm_gates_ncu_s2.txt (2.189 GB + 0.291 GB); not re-measured by this run
+        "traffic": 2.48e9 if n_local == 2000 else None,
         "peak_source": peak_src, "launches_timed": int(pl.value), "avg_launch_ms": avg_ms,
         "algorithmic_flops_per_launch": flops_per_launch,
         "executed_flops_per_launch": flops_per_launch * executed_frac,
