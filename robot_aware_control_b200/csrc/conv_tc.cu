@@ -210,9 +210,27 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
       auto load_c = [&](int c, float* dst) {
         if constexpr (kLstm) lstm_load_c<kTrain>(g, e, b, y, x, valid, n_tile * BLOCK_N + c * CH, dst, ctile, BLOCK_M);
       };
+      // row index inside the tile -> output pixel (the coalesced activation store addresses 8 neighbouring rows)
+      auto row_of = [&](int rr, int& ob, int& oy, int& ox, bool& ov) {
+        ob = grp * g.NB + (rr >> g.bhw_shift);
+        oy = yb * g.BH + ((rr >> g.w_shift) & (g.BH - 1));
+        ox = rr & (g.W - 1);
+        ov = ob < g.B;
+      };
+      // Coalesced (warp-transposed) activation stores pay off where the epilogue is the bottleneck because the K loop
+      // is short and TMEM is double-buffered (BLOCK_N <= 128: encoder.c2.x, decoder.upc2.2 / upc3.2 measured 10-20 %
+      // faster); in the exposed epilogue of the 256-column tile the extra ~200 shuffle / select instructions per row
+      // cost more issue slots than the stores save (measured 8-10 % slower), so it keeps the per-row stores.
+      constexpr bool kCoalesced = (EPI == EPI_ACT && BLOCK_N <= 128);
+      uint4 packed[kCoalesced ? 8 : 1];
       auto process = [&](int c, const float* acc_v, const float* cp) {
         const int n0 = n_tile * BLOCK_N + c * CH;
-        if constexpr (EPI == EPI_ACT) epi_act<CH>(g, e, b, y, x, valid, n0, acc_v);
+        if constexpr (kCoalesced) {
+          act_pack32(e, n0, acc_v, packed + (c & 1) * 4);
+          if (c & 1) epi_act_store64(g, e, r, n0 - CH, packed, row_of);
+        } else if constexpr (EPI == EPI_ACT) {
+          epi_act<CH>(g, e, b, y, x, valid, n0, acc_v);
+        }
         if constexpr (kLstm) epi_lstm<kTrain>(g, e, b, y, x, valid, n0, acc_v, cp, ctile, BLOCK_M, s_bias + c * CH);
         if constexpr (EPI == EPI_GAUSS) epi_gauss(g, e, b, y, x, valid, n0, acc_v);
         if constexpr (EPI == EPI_FRAME) epi_frame(g, e, b, y, x, valid, yb * (BLOCK_M / 32) + we, acc_v);

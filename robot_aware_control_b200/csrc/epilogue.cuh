@@ -54,20 +54,28 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 
 // ---------------------------------------------------------------- EPI_ACT
+// bias + LeakyReLU(0.2) + bf16 pack of 8 consecutive columns: the epilogue of the 256-column tile is exposed and
+// instruction-issue bound (8 warps), so this is 2 x LDG.128 + per value FADD, FMUL, FMNMX (+ half a pack)
+__device__ __forceinline__ uint4 act_pack8(const EpiParams& e, int n, const float* a) {
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+  const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + n + 4));
+  float v[8] = {a[0] + b0.x, a[1] + b0.y, a[2] + b0.z, a[3] + b0.w, a[4] + b1.x, a[5] + b1.y, a[6] + b1.z, a[7] + b1.w};
+  if (e.lrelu) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]);  // == v > 0 ? v : 0.2 v
+  }
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
 template <int CH>
 __device__ __forceinline__ void epi_act(const ConvGeom& g, const EpiParams& e, int b, int y, int x, bool valid, int n0,
                                         const float* acc) {
   if (!valid || n0 + CH > e.cout) return;
   uint32_t pk[CH / 2];
 #pragma unroll
-  for (int j = 0; j < CH; j += 2) {
-    float v0 = acc[j] + __ldg(e.bias + n0 + j);
-    float v1 = acc[j + 1] + __ldg(e.bias + n0 + j + 1);
-    if (e.lrelu) {
-      v0 = v0 > 0.f ? v0 : 0.2f * v0;
-      v1 = v1 > 0.f ? v1 : 0.2f * v1;
-    }
-    pk[j / 2] = pack_bf16x2(v0, v1);
+  for (int q = 0; q < CH / 8; ++q) {
+    const uint4 t = act_pack8(e, n0 + 8 * q, acc + 8 * q);
+    pk[4 * q] = t.x; pk[4 * q + 1] = t.y; pk[4 * q + 2] = t.z; pk[4 * q + 3] = t.w;
   }
   if (!e.upsample) {
     __nv_bfloat16* dst = e.out + (static_cast<size_t>(b * g.H + y) * g.W + x) * e.out_cstride + e.out_coff + n0;
@@ -87,6 +95,67 @@ __device__ __forceinline__ void epi_act(const ConvGeom& g, const EpiParams& e, i
         for (int q = 0; q < CH / 8; ++q)
           reinterpret_cast<uint4*>(dst)[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       }
+  }
+}
+
+// ---------------------------------------------------------------- EPI_ACT, coalesced variant (tcgen05 kernels)
+// One thread owns one output row, so a plain per-thread store sends the 32 lanes of a warp to 32 different 128-byte
+// lines with 16 B each: the L1 processes 32 requests per instruction and the (exposed) epilogue of the 256-column tile
+// became store-issue bound. Here 64 channels (two 32-column chunks = 8 units of 16 B) are first transposed inside
+// groups of 8 lanes (3 butterfly stages of warp shuffles), after which lane j of a group holds unit j of all 8 rows of
+// the group: every store instruction then writes 4 complete 128-byte segments (one per group).
+__device__ __forceinline__ void act_pack32(const EpiParams& e, int n0, const float* acc, uint4* u) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) u[q] = act_pack8(e, n0 + 8 * q, acc + 8 * q);
+}
+__device__ __forceinline__ uint4 shfl_xor_u4(uint4 v, int m) {
+  return make_uint4(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m),
+                    __shfl_xor_sync(0xffffffffu, v.z, m), __shfl_xor_sync(0xffffffffu, v.w, m));
+}
+// u[k] of lane (8G + i)  ->  u[i] of lane (8G + k)
+__device__ __forceinline__ void transpose8x8_u4(uint4* u, int lane) {
+#pragma unroll
+  for (int bit = 1; bit < 8; bit <<= 1) {
+    const bool hi = (lane & bit) != 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k & bit) continue;
+      const uint4 send = hi ? u[k] : u[k | bit];
+      const uint4 recv = shfl_xor_u4(send, bit);
+      if (hi) u[k] = recv; else u[k | bit] = recv;
+    }
+  }
+}
+// RowFn: (row index inside the tile) -> (b, y, x, valid). Must be called by all 32 lanes (shuffles). u[0..7] = the 64
+// packed channels n0 .. n0+63 of this thread's row r.
+template <typename RowFn>
+__device__ __forceinline__ void epi_act_store64(const ConvGeom& g, const EpiParams& e, int r, int n0, uint4* u,
+                                                RowFn row_of) {
+  const int lane = threadIdx.x & 31;
+  transpose8x8_u4(u, lane);
+  if (n0 + 64 > e.cout) return;
+  const int rbase = r - (lane & 7);
+  const int unit = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int b, y, x;
+    bool valid;
+    row_of(rbase + i, b, y, x, valid);
+    if (!valid) continue;
+    if (!e.upsample) {
+      __nv_bfloat16* dst = e.out + (static_cast<size_t>(b * g.H + y) * g.W + x) * e.out_cstride + e.out_coff + n0 + unit * 8;
+      *reinterpret_cast<uint4*>(dst) = u[i];
+    } else {
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          __nv_bfloat16* dst =
+              e.out + (static_cast<size_t>(b * 2 * g.H + 2 * y + dy) * (2 * g.W) + 2 * x + dx) * e.out_cstride +
+              e.out_coff + n0 + unit * 8;
+          *reinterpret_cast<uint4*>(dst) = u[i];
+        }
+    }
   }
 }
 

@@ -88,6 +88,7 @@ struct rac_handle {
   int cur[3] = {0, 0, 0};  // ping-pong index of the live hidden state per LSTM stack
   bool hidden_zero[3] = {false, false, false};  // h == 0 since init_hidden: the h_prev half of K is skipped
   int skip_zero_hidden = 1;  // RAC_SKIP_ZERO_H=0 disables the skip (A/B measurements)
+  int act_block_n = 256;     // RAC_ACT_BN=128: 256x128 tiles (double-buffered TMEM) for the BN+LeakyReLU layers (A/B measurements)
   int use_halo = 1;          // RAC_HALO=0: generic kernel for the 64-wide full-resolution layers too (A/B measurements)
   int halo_base_offset = 0;  // RAC_HALO_BASE_OFFSET=1 sets the descriptor base-offset field for the row-shifted operands: WRONG on
                              // B200 (measured: the 128B swizzle phase follows the absolute smem address bits [7:9])
@@ -264,6 +265,7 @@ int make_conv(rac_handle* h, ConvOp* op, const char* name, int layer, int H, int
   op->block_m = h->tile_m;
   op->block_n = s.block_n;
   if (h->tile_m == 256 && s.n_packed % 256 == 0 && (epi == EPI_ACT || epi == EPI_LSTM || epi == EPI_F32)) op->block_n = 256;
+  if (epi == EPI_ACT && h->act_block_n == 128 && op->block_n == 256) op->block_n = 128;
   op->epi = epi;
   ConvGeom& g = op->g;
   g.B = B; g.H = H; g.W = W; g.ks = s.ks; g.pad = s.ks / 2;
@@ -756,6 +758,7 @@ int rac_create(const rac_config* cfg, rac_handle** out) {
   if (const char* sz = getenv("RAC_SKIP_ZERO_H")) h->skip_zero_hidden = atoi(sz) != 0;
   if (const char* ct = getenv("RAC_C_TILED")) h->c_tiled = atoi(ct) != 0;
   if (const char* v = getenv("RAC_HALO")) h->use_halo = atoi(v) != 0;
+  if (const char* v = getenv("RAC_ACT_BN")) h->act_block_n = atoi(v);
   if (const char* v = getenv("RAC_HALO_BASE_OFFSET")) h->halo_base_offset = atoi(v) != 0;
   if (const char* v = getenv("RAC_HALO_COLUMNS")) h->halo_force_columns = atoi(v) != 0;
   CK(conv_halo_set_attributes());
