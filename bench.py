@@ -231,7 +231,9 @@ def run_train_bench(args):
         group = dist.group.WORLD
     dev = torch.device("cuda", local_rank)
     ra = args.robot_aware
-    kw = dict(lr=1e-4, beta=1e-4, beta1=0.9, n_future=5, n_past=1)
+    kw = dict(lr=1e-4, beta=1e-4, beta1=0.9, n_future=5, n_past=1, robot_pixel_weight=0.0,
+              scheduled_sampling=bool(args.scheduled_sampling), scheduled_sampling_k=4000)
+    np.random.seed(0)  # the reference draws the scheduled-sampling decisions from the global numpy generator
     if ra:
         cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, action_dim=A_DIM, model_use_mask=True, model_use_future_mask=True,
                           model_use_robot_state=True, reconstruction_loss="dontcare_l1", reward_type="dontcare", **kw)
@@ -258,11 +260,17 @@ def run_train_bench(args):
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ar_ms = 0.0
+    ar_events = []
     e0.record()
     for _ in range(args.steps):
+        if world > 1:  # gradient all-reduce (+ the 1 / world scaling) timed with its own event pair on the same stream
+            trainer.allreduce_events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ar_events.append(trainer.allreduce_events)
         step()
     e1.record()
     torch.cuda.synchronize()
+    ar_ms = sum(a.elapsed_time(b) for a, b in ar_events)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -280,9 +288,14 @@ def run_train_bench(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"SVG training step, batch {Bt}/GPU, n_past 1 / n_future 5, g_dim {G_DIM} z_dim {Z_DIM}, "
-                                   + ("dontcare_l1 robot-aware" if ra else "l1 vanilla") + ", Adam, data parallel",
+                                   + ("dontcare_l1 robot-aware (mask + future mask + robot state)" if ra else "l1 vanilla")
+                                   + (", scheduled sampling k=4000" if args.scheduled_sampling else "")
+                                   + ", Adam, data parallel (flat fp32 gradient all-reduce over NCCL)",
                        "algorithmic_tflop_per_step_per_gpu": 6.52},
             "achieved_tflops_per_gpu": 6.52 / (per * 1e-3), "last_losses": loss,
+            "scheduled_sampling": bool(args.scheduled_sampling),
+            "allreduce_ms_per_step": ar_ms / args.steps, "allreduce_share": ar_ms / float(ms.item()),
+            "allreduce_bytes": int(trainer.grads.numel()) * 4 if world > 1 else 0,
             "ddp_params_identical_across_ranks": identical}))
     if world > 1:
         dist.destroy_process_group()
@@ -310,6 +323,8 @@ def main():
     ap.add_argument("--train", action="store_true",
                     help="BASELINE configs[0]/[3]: SVG training step (batch 16 per GPU, n_past 1 / n_future 5), "
                          "forward + BPTT backward + Adam; data parallel over --gpus")
+    ap.add_argument("--scheduled-sampling", action="store_true",
+                    help="with --train: cfg.scheduled_sampling (k = 4000, numpy seed 0), as BASELINE configs[3]")
     ap.add_argument("--robot-aware", action="store_true",
                     help="BASELINE configs[4]: model_use_robot_state + model_use_mask(+future mask), dontcare cost, "
                          "synthetic per-candidate robot states / rectangle masks resident on the device")

@@ -132,6 +132,7 @@ class SVGTrainer:
         if c.lstm_group_norm:
             raise NotImplementedError("lstm_group_norm is implemented for inference / planning only")
         self.process_group = process_group
+        self.allreduce_events = None
         self._lib = _lib.load()
         dev = model._device
         # ---- flat fp32 storage; the module's parameters / running stats become views into it
@@ -251,8 +252,13 @@ class SVGTrainer:
     def optimizer_step(self):
         m = self.model
         if self.process_group is not None and dist.get_world_size(self.process_group) > 1:
+            ev = self.allreduce_events  # optional (start, end) CUDA events: bench.py reports the all-reduce share
+            if ev is not None:
+                ev[0].record()
             dist.all_reduce(self.grads, group=self.process_group)
             self.grads.div_(dist.get_world_size(self.process_group))
+            if ev is not None:
+                ev[1].record()
         _lib.check(self._lib.rac_train_adam_step(m.handle, _lib.stream_ptr()), m.handle, "rac_train_adam_step")
         m._packed_dirty = True  # the eval-mode packed copy (folded BatchNorm) is stale now
         self._step += 1
