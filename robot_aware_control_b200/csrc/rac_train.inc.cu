@@ -24,6 +24,11 @@ struct TLayer {
   bf16* wd = nullptr;    // [ctot][taps*kpad]
   float* dwp = nullptr;  // [kpad][taps*ctot]
   float* bias = nullptr; // [n_packed]
+  // wgrad operands of ALL time steps, transposed: xcolT [taps*ctot][steps*mpad], dyT [kpad][steps*mpad]. The weight
+  // gradient is a sum over time, so the contraction simply runs over steps * rows: ONE GEMM per layer with K = steps *
+  // mpad after the last BPTT step instead of one K = mpad GEMM (+ a read-modify-write of dW) per step.
+  bf16* xcolT = nullptr;
+  bf16* dyT = nullptr;
   int taps = 0, ctot = 0, n_packed = 0, kpad = 0;
 };
 
@@ -66,7 +71,7 @@ struct TrainState {
   float* dbg_draw32 = nullptr;  // RAC_TRAIN_DEBUG_KEEP=1: first-layer raw gradient of the last SAMPLED step (tests)
   int dbg_keep = 0;
   bf16 *dy_a, *dy_b;     // bf16 gradient operands (largest [M, C])
-  bf16 *xcolT, *dyT;     // transposed wgrad operands
+  int cur_t = 0;         // time step being processed by the backward pass (column block of the wgrad operands)
   float* bn_scratch;
   float* draw32;         // fp32 copy of the first layer's raw gradient
   bf16* hzero;
@@ -174,20 +179,23 @@ int conv_backward(rac_handle* h, TrainState* T, int layer, int H, int W, const s
   const int B = T->cfg.batch;
   const int M = B * H * W, mpad = round_up(M, 64);
   const int ks = (L.taps == 25) ? 5 : 3;
-  // ---- wgrad: dWp[n][tap*ctot + c] += sum_m dY[m][n] * X[shift_tap(m)][c]
+  // ---- wgrad: dWp[n][tap*ctot + c] = sum_t sum_m dY_t[m][n] * X_t[shift_tap(m)][c]: this step's operands go to
+  // column block t of the layer's transposed buffers; the GEMM runs once, after the last processed step (t == 0)
+  const int S = T->cfg.steps;
+  const int ld = S * mpad;
   int coff = 0;
   for (const Src& s : xs) {
-    CK(launch_im2col_t(s.p, B, H, W, s.C, ks, L.ctot, coff, mpad, T->xcolT, st));
+    CK(launch_im2col_t(s.p, B, H, W, s.C, ks, L.ctot, coff, mpad, L.xcolT + static_cast<size_t>(T->cur_t) * mpad, st, ld));
     coff += s.C;
   }
-  CK(launch_transpose_bf16(dY, M, L.kpad, mpad, L.kpad, T->dyT, st));
-  {
+  CK(launch_transpose_bf16(dY, M, L.kpad, mpad, L.kpad, L.dyT + static_cast<size_t>(T->cur_t) * mpad, st, ld));
+  if (T->cur_t == 0) {
     EpiParams e{};
     const int ncols = L.taps * L.ctot;
     e.cout = ncols;
     e.nseg = 1;
     e.seg[0] = {0, ncols, L.dwp, ncols, 0, 1};
-    CKR(t_gemm(h, "train.wgrad", {L.kpad / 64, 1, 64, 1, true}, {{T->dyT, mpad}}, T->xcolT, mpad, ncols, pick_bn(ncols),
+    CKR(t_gemm(h, "train.wgrad", {L.kpad / 64, 1, 64, 1, true}, {{L.dyT, ld}}, L.xcolT, ld, ncols, pick_bn(ncols),
                EPI_F32, e, st));
   }
   // ---- dgrad: dX = conv(dY, Wd)
@@ -499,7 +507,6 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
   const size_t M0 = static_cast<size_t>(B) * 3072, M1 = static_cast<size_t>(B) * 768, M2 = static_cast<size_t>(B) * 192,
                M3 = static_cast<size_t>(B) * 48;
   T->M[0] = static_cast<int>(M0); T->M[1] = static_cast<int>(M1); T->M[2] = static_cast<int>(M2); T->M[3] = static_cast<int>(M3);
-  size_t max_xcol = 0, max_dyT = 0;
   for (int i = 0; i < RAC_L_COUNT; ++i) {
     TLayer& L = T->L[i];
     L.d = layers[i];
@@ -516,18 +523,17 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
       default: return M3;
     }
   };
-  for (int i = 1; i < RAC_L_COUNT; ++i) {
-    const TLayer& L = T->L[i];
-    const size_t mpad = round_up(static_cast<int>(rows_of(i)), 64);
-    max_xcol = std::max(max_xcol, static_cast<size_t>(L.taps) * L.ctot * mpad);
-    max_dyT = std::max(max_dyT, static_cast<size_t>(L.kpad) * mpad);
-  }
   for (int pass = 0; pass < 2; ++pass) {
     Bump bp;
     bp.base = pass ? static_cast<char*>(T->arena) : nullptr;
     for (int i = 1; i < RAC_L_COUNT; ++i) {
       TLayer& L = T->L[i];
       L.wp = bp.take<bf16>(static_cast<size_t>(L.n_packed) * L.taps * L.ctot);
+      {
+        const size_t ld = static_cast<size_t>(S) * round_up(static_cast<int>(rows_of(i)), 64);
+        L.xcolT = bp.take<bf16>(static_cast<size_t>(L.taps) * L.ctot * ld);
+        L.dyT = bp.take<bf16>(static_cast<size_t>(L.kpad) * ld);
+      }
       L.wd = bp.take<bf16>(static_cast<size_t>(L.ctot) * L.taps * L.kpad);
       L.dwp = bp.take<float>(static_cast<size_t>(L.kpad) * L.taps * L.ctot);
       L.bias = bp.take<float>(L.n_packed);
@@ -581,7 +587,6 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
       }
     const size_t dy_elems = std::max(M0 * 64, M3 * static_cast<size_t>(4 * g));
     T->dy_a = bp.take<bf16>(dy_elems); T->dy_b = bp.take<bf16>(dy_elems);
-    T->xcolT = bp.take<bf16>(max_xcol); T->dyT = bp.take<bf16>(max_dyT);
     T->bn_scratch = bp.take<float>(2 * 2048);
     T->draw32 = bp.take<float>(M0 * 64);
     T->hzero = bp.take<bf16>(M3 * g); T->czero = bp.take<float>(M3 * g);
@@ -642,6 +647,7 @@ int rac_train_forward_backward(rac_handle* h, const rac_train_batch* bt, void* s
     }
   int cur = 0;
   for (int t = S - 1; t >= 0; --t) {
+    T->cur_t = t;
     CKR(train_backward_step(h, T, bt, t, cur, st));
     cur ^= 1;
   }

@@ -596,7 +596,7 @@ cudaError_t launch_cast_bf16(const float* src, long long n, __nv_bfloat16* dst, 
 
 // dst[c][m] = src[m][c], zero padded to [rows_pad][mpad]
 __global__ void __launch_bounds__(1024)
-transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int M, int C, int mpad, int rows_pad,
+transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int M, int C, int mpad, int rows_pad, int ld,
                       __nv_bfloat16* __restrict__ dst) {
   __shared__ __nv_bfloat16 tile[32][33];
   const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -604,12 +604,13 @@ transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int M, int C, int m
   tile[threadIdx.y][threadIdx.x] = (m < M && c < C) ? src[static_cast<size_t>(m) * C + c] : __float2bfloat16(0.f);
   __syncthreads();
   const int co = c0 + threadIdx.y, mo = m0 + threadIdx.x;
-  if (co < rows_pad && mo < mpad) dst[static_cast<size_t>(co) * mpad + mo] = tile[threadIdx.x][threadIdx.y];
+  if (co < rows_pad && mo < mpad) dst[static_cast<size_t>(co) * ld + mo] = tile[threadIdx.x][threadIdx.y];
 }
 cudaError_t launch_transpose_bf16(const __nv_bfloat16* src, int M, int C, int mpad, int rows_pad,
-                                  __nv_bfloat16* dst, cudaStream_t s) {
+                                  __nv_bfloat16* dst, cudaStream_t s, int ld) {
+  if (ld <= 0) ld = mpad;
   transpose_bf16_kernel<<<dim3((mpad + 31) / 32, (rows_pad + 31) / 32), dim3(32, 32), 0, s>>>(src, M, C, mpad, rows_pad,
-                                                                                              dst);
+                                                                                              ld, dst);
   return cudaGetLastError();
 }
 
@@ -617,7 +618,7 @@ cudaError_t launch_transpose_bf16(const __nv_bfloat16* src, int M, int C, int mp
 // transposed write side
 __global__ void __launch_bounds__(1024)
 im2col_t_kernel(const __nv_bfloat16* __restrict__ src, int B, int H, int W, int C, int ks, int ctot, int coff,
-                int mpad, __nv_bfloat16* __restrict__ dst) {
+                int ld, __nv_bfloat16* __restrict__ dst) {
   __shared__ uint32_t tile[64][33];
   const int M = B * H * W;
   const int m0 = blockIdx.x * 64, c0 = blockIdx.y * 64, tap = blockIdx.z;
@@ -642,14 +643,15 @@ im2col_t_kernel(const __nv_bfloat16* __restrict__ src, int B, int H, int W, int 
     const uint32_t a = tile[2 * tx][cl >> 1], b2 = tile[2 * tx + 1][cl >> 1];
     const uint32_t lo = (cl & 1) ? (a >> 16) : (a & 0xffffu);
     const uint32_t hi = (cl & 1) ? (b2 >> 16) : (b2 & 0xffffu);
-    *reinterpret_cast<uint32_t*>(dst + (static_cast<size_t>(tap) * ctot + coff + c0 + cl) * mpad + m0 + 2 * tx) =
+    *reinterpret_cast<uint32_t*>(dst + (static_cast<size_t>(tap) * ctot + coff + c0 + cl) * ld + m0 + 2 * tx) =
         lo | (hi << 16);
   }
 }
 cudaError_t launch_im2col_t(const __nv_bfloat16* src, int B, int H, int W, int C, int ks, int ctot, int coff, int mpad,
-                            __nv_bfloat16* dst, cudaStream_t s) {
-  if (C % 64 != 0 || mpad % 64 != 0) return cudaErrorInvalidValue;
-  im2col_t_kernel<<<dim3(mpad / 64, C / 64, ks * ks), dim3(32, 32), 0, s>>>(src, B, H, W, C, ks, ctot, coff, mpad, dst);
+                            __nv_bfloat16* dst, cudaStream_t s, int ld) {
+  if (ld <= 0) ld = mpad;
+  if (C % 64 != 0 || mpad % 64 != 0 || ld % 2 != 0) return cudaErrorInvalidValue;
+  im2col_t_kernel<<<dim3(mpad / 64, C / 64, ks * ks), dim3(32, 32), 0, s>>>(src, B, H, W, C, ks, ctot, coff, ld, dst);
   return cudaGetLastError();
 }
 
