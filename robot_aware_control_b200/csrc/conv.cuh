@@ -40,6 +40,7 @@ struct ConvGeom {
   int ctot;             // total input channels (sum of padded source channels)
   int num_m_tiles, num_n_tiles, tiles_per_img;  // tiles_per_img = H / BH
   int w_shift, bhw_shift;                       // log2(W), log2(BH * W)
+  int no_split_tail;                            // 1: disable the tail splitting of conv_tc_kernel (A/B measurements)
 };
 
 struct EpiParams {

@@ -63,6 +63,19 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = g.num_m_tiles * g.num_n_tiles;
+  // Tail splitting against wave quantisation: the persistent grid processes floor(tiles / grid) full rounds; if the
+  // remaining `rem` tiles would occupy at most half of the CTAs for one more full tile time (e.g. 3000 LSTM tiles =
+  // 20 x 148 + 40), each of them becomes two work items, one per 128-row MMA sub-tile (same operand loads, half the
+  // MMAs, half the epilogue rows), so the last round takes about half a tile time on twice as many SMs.
+  const int full_items = (num_tiles / static_cast<int>(gridDim.x)) * static_cast<int>(gridDim.x);
+  const int rem = num_tiles - full_items;
+  const bool split_tail = Cfg::kSub == 2 && !g.no_split_tail && rem > 0 && 2 * rem <= static_cast<int>(gridDim.x);
+  const int num_items = split_tail ? full_items + 2 * rem : num_tiles;
+  auto item_tile = [&](int item, int& half) {  // half: -1 = both sub-tiles
+    if (item < full_items || !split_tail) { half = -1; return item; }
+    half = (item - full_items) & 1;
+    return full_items + ((item - full_items) >> 1);
+  };
   int kb_per_tap = 0, live_kb_per_tap = 0;
   for (int s = 0; s < g.nsrc; ++s) {
     kb_per_tap += g.src_kb[s];
@@ -97,7 +110,9 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int half;
+      const int tile = item_tile(item, half);
       const int n_tile = tile / g.num_m_tiles;
       const int m_tile = tile - n_tile * g.num_m_tiles;
       const int grp = m_tile / g.tiles_per_img;
@@ -129,7 +144,9 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int half;
+      const int tile = item_tile(item, half);
       const int n_tile = tile / g.num_m_tiles;
       const int m_tile = tile - n_tile * g.num_m_tiles;
       const int y0 = (m_tile % g.tiles_per_img) * g.BH;
@@ -149,6 +166,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
         for (int k = 0; k < kBlockK / 16; ++k) {
 #pragma unroll
           for (int sub = 0; sub < Cfg::kSub; ++sub) {
+            if (half >= 0 && sub != half) continue;  // split tail item: only this sub-tile
             // +2 in the (addr >> 4) field = 32 B = 16 bf16 along K inside the 128B swizzle row;
             // sub-tile s starts 128 rows * 128 B = 16 KB further (1024-B aligned, swizzle phase preserved)
             umma_bf16_ss(d_tmem + sub * BLOCK_N, adesc + 2 * k + sub * (kTileM * 128 / 16), bdesc + 2 * k, idesc,
@@ -172,7 +190,10 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
     constexpr int CH = (BLOCK_N >= 32) ? 32 : 16;
     float* s_bias = reinterpret_cast<float*>(bar_base + 1024);
     int bias_tile = -1;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int half;
+      const int tile = item_tile(item, half);
+      const bool mine = half < 0 || sub == half;  // split tail item: the other sub-tile's rows belong to another CTA
       const int n_tile = tile / g.num_m_tiles;
       const int m_tile = tile - n_tile * g.num_m_tiles;
       const int grp = m_tile / g.tiles_per_img;
@@ -236,12 +257,16 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
         if constexpr (EPI == EPI_FRAME) epi_frame(g, e, b, y, x, valid, yb * (BLOCK_M / 32) + we, acc_v);
         if constexpr (EPI == EPI_F32) epi_f32<CH>(g, e, b, y, x, valid, n0, acc_v);
       };
-      issue(0, v[0]);
-      load_c(0, cprev[0]);
-      if constexpr (kChunks == 1) {
+      if (!mine) {
+        // nothing to read: still hand the accumulator stage back (the barrier counts every epilogue thread)
+      } else if constexpr (kChunks == 1) {
+        issue(0, v[0]);
+        load_c(0, cprev[0]);
         tmem_ld_wait();
         process(0, v[0], cprev[0]);
       } else {
+        issue(0, v[0]);
+        load_c(0, cprev[0]);
         static_assert(kChunks == 1 || kChunks % 2 == 0, "column chunks are processed in pairs");
 #pragma unroll 1
         for (int c = 0; c < kChunks; c += 2) {

@@ -88,6 +88,7 @@ struct rac_handle {
   int cur[3] = {0, 0, 0};  // ping-pong index of the live hidden state per LSTM stack
   bool hidden_zero[3] = {false, false, false};  // h == 0 since init_hidden: the h_prev half of K is skipped
   int skip_zero_hidden = 1;  // RAC_SKIP_ZERO_H=0 disables the skip (A/B measurements)
+  int split_tail = 1;        // RAC_SPLIT_TAIL=0: no tail splitting in conv_tc_kernel (A/B measurements)
   int act_block_n = 256;     // RAC_ACT_BN=128: 256x128 tiles (double-buffered TMEM) for the BN+LeakyReLU layers (A/B measurements)
   int use_halo = 1;          // RAC_HALO=0: generic kernel for the 64-wide full-resolution layers too (A/B measurements)
   int halo_base_offset = 0;  // RAC_HALO_BASE_OFFSET=1 sets the descriptor base-offset field for the row-shifted operands: WRONG on
@@ -293,6 +294,7 @@ int make_conv(rac_handle* h, ConvOp* op, const char* name, int layer, int H, int
   g.num_n_tiles = s.n_packed / op->block_n;
   g.w_shift = ilog2(W);
   g.bhw_shift = ilog2(g.BH * W);
+  g.no_split_tail = h->split_tail ? 0 : 1;
   const bf16* wp = static_cast<const bf16*>(h->layer[layer].w);
   op->raw.w = wp;
   CKR(encode_w_map(h, &op->tm.w, wp, s.ks * s.ks * s.ctot, s.n_packed, op->block_n));
@@ -759,6 +761,7 @@ int rac_create(const rac_config* cfg, rac_handle** out) {
   if (const char* ct = getenv("RAC_C_TILED")) h->c_tiled = atoi(ct) != 0;
   if (const char* v = getenv("RAC_HALO")) h->use_halo = atoi(v) != 0;
   if (const char* v = getenv("RAC_ACT_BN")) h->act_block_n = atoi(v);
+  if (const char* v = getenv("RAC_SPLIT_TAIL")) h->split_tail = atoi(v) != 0;
   if (const char* v = getenv("RAC_HALO_BASE_OFFSET")) h->halo_base_offset = atoi(v) != 0;
   if (const char* v = getenv("RAC_HALO_COLUMNS")) h->halo_force_columns = atoi(v) != 0;
   CK(conv_halo_set_attributes());
