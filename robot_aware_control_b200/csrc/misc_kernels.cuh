@@ -59,7 +59,8 @@ cudaError_t launch_composite_nchw(const float* x4, const float* xj, float* out, 
 // ---- NormConvLSTMCell pointwise part (norm_lstm.cu; reference lstm.py:177-198) ----
 // ih / hh: raw gate convolutions [B, P, 4*hid] fp32, packed column (channel, gate); gn_params: packed GroupNorm affine
 // [ih gamma | ih beta | hh gamma | hh beta] (4*hid each, packed column order) + [cell gamma | cell beta] (hid each)
-cudaError_t launch_norm_lstm_cell(const float* ih, const float* hh, const float* gn_params, float* c_state,
+// (ih is also scratch: its `out` gate slot carries the output gate from pass 2 to pass 3)
+cudaError_t launch_norm_lstm_cell(float* ih, const float* hh, const float* gn_params, float* c_state,
                                   __nv_bfloat16* h_out, int B, int P, int hid, cudaStream_t s);
 cudaError_t norm_lstm_set_attributes();
 
