@@ -159,3 +159,27 @@ def test_group_norm_lstm_packing():
     assert v[ch * 4 + gate] == sd["prior.lstm.1.ih_gates.1.weight"][gate * g + ch]
     assert v[3 * 4 * g + ch * 4 + gate] == sd["prior.lstm.1.hh_gates.1.bias"][gate * g + ch]
     assert v[16 * g + ch] == sd["prior.lstm.1.c_norm.weight"][ch] and v[17 * g + ch] == sd["prior.lstm.1.c_norm.bias"][ch]
+
+
+def test_product_path_fails_loudly_without_a_gpu():
+    """No CPU / PyTorch fallback: on a box without a CUDA device the C ABI refuses to create a handle (negative status +
+    message) and the Python model class raises; nothing silently routes through the oracle."""
+    import ctypes as C
+
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the CPU-only box")
+    from robot_aware_control_b200 import SVGConvModel, _lib
+
+    lib = _lib.load()
+    cfg = _lib.RacConfig(48, 64, 128, 10, 5, 5, 0, 0, 0, 0, 0, 0)
+    h = C.c_void_p()
+    code = lib.rac_create(C.byref(cfg), C.byref(h))
+    assert code < 0
+    msg = lib.rac_last_error(h).decode()
+    assert "no CUDA device" in msg or "failed" in msg, msg
+    lib.rac_destroy(h)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        SVGConvModel(so.make_cfg(g_dim=128, z_dim=10))
+    # stand-alone kernels: argument validation happens before any launch
+    assert lib.rac_topk(None, 10, 3, None, None, None) < 0
+    assert lib.rac_psnr(None, None, None, 0, None, 1, 3, 3072, None) < 0
