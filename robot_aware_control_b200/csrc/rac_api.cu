@@ -88,6 +88,11 @@ struct rac_handle {
   int cur[3] = {0, 0, 0};  // ping-pong index of the live hidden state per LSTM stack
   bool hidden_zero[3] = {false, false, false};  // h == 0 since init_hidden: the h_prev half of K is skipped
   int skip_zero_hidden = 1;  // RAC_SKIP_ZERO_H=0 disables the skip (A/B measurements)
+  // RAC_2CTA bit 1: CTA-pair (cta_group::2) kernel for the 256-wide BN+LeakyReLU layers (default on: +2.5 % of the
+  // rollout, their exposed epilogue is hidden by the second TMEM stage); bit 0: for the LSTM gate convolutions too
+  // (default off: measured neutral to -1 % -- those kernels run at the power cap, hiding their epilogue only lowers
+  // the clock of the main loop)
+  int two_cta = 2;
   int split_tail = 1;        // RAC_SPLIT_TAIL=0: no tail splitting in conv_tc_kernel (A/B measurements)
   int act_block_n = 256;     // RAC_ACT_BN=128: 256x128 tiles (double-buffered TMEM) for the BN+LeakyReLU layers (A/B measurements)
   int use_halo = 1;          // RAC_HALO=0: generic kernel for the 64-wide full-resolution layers too (A/B measurements)
@@ -301,6 +306,13 @@ int make_conv(rac_handle* h, ConvOp* op, const char* name, int layer, int H, int
   op->e.bias = h->layer[layer].bias;
   op->e.cout = s.cout;
   op->e.cost_nparts = H * W / 32;
+  if (h->cfg.conv_impl == 0 && conv_tc2_supported(*op) &&
+      (((h->two_cta & 1) && epi == EPI_LSTM) || ((h->two_cta & 2) && epi == EPI_ACT))) {
+    for (int i = 0; i < g.nsrc; ++i)
+      CKR(encode_act_map(h, &op->tm2.a[i], srcs[i].p, srcs[i].C, B, H, W, g.BH, g.NB / 2));
+    CKR(encode_w_map(h, &op->tm2.w, wp, s.ks * s.ks * s.ctot, s.n_packed, 128));
+    op->two_cta = 1;
+  }
   if (h->use_halo && h->cfg.conv_impl == 0 && h->tile_m == 256 && conv_halo_supported(*op)) {
     CKR(encode_halo_map(h, &op->tm_halo, srcs[0].p, srcs[0].C, B, H, W, &op->halo_column_loads));
     op->halo = 1;
@@ -347,6 +359,7 @@ int launch(rac_handle* h, const ConvOp& op, cudaStream_t st) {
     }
   }
   cudaError_t e = h->cfg.conv_impl == 1 ? launch_conv_simt(op, st)
+                  : op.two_cta ? launch_conv_tc2(op, op.tm2, h->num_sms, st)
                   : op.halo ? launch_conv_halo(op, op.tm_halo, op.halo_column_loads, h->halo_base_offset, h->num_sms, st)
                             : launch_conv_tc(op, h->num_sms, st);
   if (timed) {
@@ -762,6 +775,8 @@ int rac_create(const rac_config* cfg, rac_handle** out) {
   if (const char* v = getenv("RAC_HALO")) h->use_halo = atoi(v) != 0;
   if (const char* v = getenv("RAC_ACT_BN")) h->act_block_n = atoi(v);
   if (const char* v = getenv("RAC_SPLIT_TAIL")) h->split_tail = atoi(v) != 0;
+  if (const char* v = getenv("RAC_2CTA")) h->two_cta = atoi(v);
+  CK(conv_tc2_set_attributes());
   if (const char* v = getenv("RAC_HALO_BASE_OFFSET")) h->halo_base_offset = atoi(v) != 0;
   if (const char* v = getenv("RAC_HALO_COLUMNS")) h->halo_force_columns = atoi(v) != 0;
   CK(conv_halo_set_attributes());
