@@ -12,6 +12,12 @@ namespace rac {
 cudaError_t launch_first_conv(const float* img4, const float* mask_a, const float* mask_b, long long mask_bstride,
                               const float* w, const float* bias, __nv_bfloat16* out, int B, int H, int W, int cin,
                               cudaStream_t s, float* raw_out = nullptr);
+// the same layer on the tensor cores (first_conv_tc.cu): per-thread im2col rows written in the swizzled UMMA layout,
+// 6 MMAs per 256-pixel tile; inference only (bf16 inputs, fused activation)
+cudaError_t launch_first_conv_tc(const float* img4, const float* mask_a, const float* mask_b, long long mask_bstride,
+                                 const float* w, const float* bias, __nv_bfloat16* out, int B, int H, int W, int cin,
+                                 int num_sms, cudaStream_t s);
+cudaError_t first_conv_tc_set_attributes();
 // nn.MaxPool2d(2,2) (reference vgg_64.py:120,126-128) over a channel slice of an NHWC buffer
 cudaError_t launch_maxpool2(const __nv_bfloat16* in, int in_cstride, int in_coff, __nv_bfloat16* out, int B, int H,
                             int W, int C, cudaStream_t s);

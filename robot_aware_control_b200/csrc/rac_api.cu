@@ -93,6 +93,7 @@ struct rac_handle {
   // (default off: measured neutral to -1 % -- those kernels run at the power cap, hiding their epilogue only lowers
   // the clock of the main loop)
   int two_cta = 2;
+  int first_conv_tc = 1;     // RAC_FIRST_TC=0: encoder.c1.0 on the CUDA cores (fp32 inputs) instead of the tensor-core kernel
   int split_tail = 1;        // RAC_SPLIT_TAIL=0: no tail splitting in conv_tc_kernel (A/B measurements)
   int act_block_n = 256;     // RAC_ACT_BN=128: 256x128 tiles (double-buffered TMEM) for the BN+LeakyReLU layers (A/B measurements)
   int use_halo = 1;          // RAC_HALO=0: generic kernel for the 64-wide full-resolution layers too (A/B measurements)
@@ -649,9 +650,14 @@ int run_step(rac_handle* h, const StepArgs& a, cudaStream_t st) {
   // ---- encoder (vgg_64.py:122-129)
   {
     ProfScope ps(h, "encoder.c1.0", st);
-    CK(launch_first_conv(w.img, c.use_mask ? a.mask_a : nullptr, (c.use_mask && c.use_future_mask) ? a.mask_b : nullptr,
-                         a.mask_bstride, static_cast<const float*>(h->layer[RAC_L_ENC_C1_0].w), h->layer[RAC_L_ENC_C1_0].bias, w.a1, B,
-                         48, 64, h->enc_cin, st));
+    if (h->first_conv_tc && c.conv_impl == 0)
+      CK(launch_first_conv_tc(w.img, c.use_mask ? a.mask_a : nullptr, (c.use_mask && c.use_future_mask) ? a.mask_b : nullptr,
+                              a.mask_bstride, static_cast<const float*>(h->layer[RAC_L_ENC_C1_0].w), h->layer[RAC_L_ENC_C1_0].bias,
+                              w.a1, B, 48, 64, h->enc_cin, h->num_sms, st));
+    else
+      CK(launch_first_conv(w.img, c.use_mask ? a.mask_a : nullptr, (c.use_mask && c.use_future_mask) ? a.mask_b : nullptr,
+                           a.mask_bstride, static_cast<const float*>(h->layer[RAC_L_ENC_C1_0].w), h->layer[RAC_L_ENC_C1_0].bias, w.a1, B,
+                           48, 64, h->enc_cin, st));
   }
   h->launches++;
   ConvOp* e = w.enc[ks];
@@ -776,6 +782,8 @@ int rac_create(const rac_config* cfg, rac_handle** out) {
   if (const char* v = getenv("RAC_ACT_BN")) h->act_block_n = atoi(v);
   if (const char* v = getenv("RAC_SPLIT_TAIL")) h->split_tail = atoi(v) != 0;
   if (const char* v = getenv("RAC_2CTA")) h->two_cta = atoi(v);
+  if (const char* v = getenv("RAC_FIRST_TC")) h->first_conv_tc = atoi(v) != 0;
+  CK(first_conv_tc_set_attributes());
   CK(conv_tc2_set_attributes());
   if (const char* v = getenv("RAC_HALO_BASE_OFFSET")) h->halo_base_offset = atoi(v) != 0;
   if (const char* v = getenv("RAC_HALO_COLUMNS")) h->halo_force_columns = atoi(v) != 0;

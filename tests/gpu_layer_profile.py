@@ -1,7 +1,7 @@
 """Diagnostic (not a test): live CUDA-event time of every convolution layer inside one CEM rollout at the BASELINE
 size, via rac_profile_begin/end (events on the launch stream around every launch whose name contains the key).
 
-    python tests/gpu_layer_profile.py [candidates] [--gn]
+    python tests/gpu_layer_profile.py [candidates] [--gn] [--ra]
 """
 import ctypes as C
 import os
@@ -35,7 +35,10 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 2000
     gn = "--gn" in sys.argv
     L = 5
-    cfg = so.make_cfg(g_dim=512, z_dim=64, lstm_group_norm=gn)
+    ra = "--ra" in sys.argv  # robot-aware model: mask + future mask + robot state, dontcare cost (BASELINE configs[4])
+    kw = dict(model_use_mask=True, model_use_future_mask=True, model_use_robot_state=True,
+              reconstruction_loss="dontcare_l1", reward_type="dontcare") if ra else {}
+    cfg = so.make_cfg(g_dim=512, z_dim=64, lstm_group_norm=gn, **kw)
     model = SVGConvModel(cfg)
     model.load_state_dict(so.make_state_dict(cfg, 0))
     model.eval()
@@ -46,12 +49,19 @@ def main():
     g = torch.Generator().manual_seed(0)
     actions = torch.cat([(torch.rand(n, L, 2, generator=g) - 0.5) * 0.1, torch.zeros(n, L, 3)], 2).cuda()
     lib = _lib.load()
+    states = masks = None
+    if ra:
+        states = torch.rand(L + 1, n, 5, generator=g).cuda()
+        masks = torch.zeros(L + 1, n, 1, 48, 64)
+        masks[:, :, :, 10:30, 20:44] = 1
+        masks = masks.cuda()
+    rollout = lambda: ts.generate_model_rollouts(actions, start, goal, states=states, masks=masks)
     for _ in range(2):
-        ts.generate_model_rollouts(actions, start, goal)
+        rollout()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    ts.generate_model_rollouts(actions, start, goal)
+    rollout()
     e1.record()
     torch.cuda.synchronize()
     total = e0.elapsed_time(e1)
@@ -61,7 +71,7 @@ def main():
         if name == "norm_lstm_cell" and not gn:
             continue
         _lib.check(lib.rac_profile_begin(model.handle, name.encode(), 64), model.handle, "begin")
-        ts.generate_model_rollouts(actions, start, goal)
+        rollout()
         pl, pms = C.c_int64(), C.c_double()
         _lib.check(lib.rac_profile_end(model.handle, C.byref(pl), C.byref(pms)), model.handle, "end")
         per_step = pms.value / L
