@@ -16,7 +16,8 @@ namespace rac {
 
 // EPI_LSTM = inference cell (MUFU math, epilogue-private cell-state layout); EPI_LSTM_TRAIN = training cell (libm math,
 // NHWC cell state read from c_in, gates saved for the backward pass) -- separate instantiations keep each one's code small
-enum EpiMode : int { EPI_ACT = 0, EPI_LSTM = 1, EPI_GAUSS = 2, EPI_FRAME = 3, EPI_F32 = 4, EPI_LSTM_TRAIN = 5 };
+// EPI_GATES = raw fp32 gate pre-activations of a NormConvLSTMCell convolution + per-sample GroupNorm partial sums
+enum EpiMode : int { EPI_ACT = 0, EPI_LSTM = 1, EPI_GAUSS = 2, EPI_FRAME = 3, EPI_F32 = 4, EPI_LSTM_TRAIN = 5, EPI_GATES = 6 };
 
 // One destination of the fp32 epilogue: packed columns [n_begin, n_end) of the GEMM go to dst (row-major NHWC rows,
 // `cstride` floats per row, starting at channel `coff`); accumulate: += instead of =. Bounds are multiples of 32.
@@ -60,6 +61,11 @@ struct EpiParams {
   // EPI_F32 (training: raw pre-BatchNorm conv output, dgrad into gradient accumulators, wgrad into packed dW)
   F32Seg seg[3];
   int nseg;
+  // EPI_GATES (lstm_group_norm, reference lstm.py:163-171,181-183): acc + bias -> seg[0].dst (fp32 [rows, 4*hid], packed
+  // (channel, gate) columns) and GroupNorm(16, 4*hid) partial sums of this tile: gn_part[b][gn_tensor][gate*4 + quarter]
+  // [slot][{sum, sumsq}], slot = row tile * gn_ntq + column tile inside the quarter (6 slots reserved)
+  float* gn_part;
+  int gn_tensor, gn_ntq;
   // EPI_GAUSS (reference lstm.py:276-286): columns are (z channel, {mu, logvar}) interleaved
   const float* eps;         // NCHW (B, z_dim, H, W) fp32 noise, or null -> Philox
   float* mu_out;            // NCHW fp32 or null

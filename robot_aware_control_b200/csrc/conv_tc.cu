@@ -244,6 +244,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
       // cost more issue slots than the stores save (measured 8-10 % slower), so it keeps the per-row stores.
       constexpr bool kCoalesced = (EPI == EPI_ACT && BLOCK_N <= 128);
       uint4 packed[kCoalesced ? 8 : 1];
+      float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};  // EPI_GATES: GroupNorm partial sums of this row
       auto process = [&](int c, const float* acc_v, const float* cp) {
         const int n0 = n_tile * BLOCK_N + c * CH;
         if constexpr (kCoalesced) {
@@ -256,6 +257,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
         if constexpr (EPI == EPI_GAUSS) epi_gauss(g, e, b, y, x, valid, n0, acc_v);
         if constexpr (EPI == EPI_FRAME) epi_frame(g, e, b, y, x, valid, yb * (BLOCK_M / 32) + we, acc_v);
         if constexpr (EPI == EPI_F32) epi_f32<CH>(g, e, b, y, x, valid, n0, acc_v);
+        if constexpr (EPI == EPI_GATES) epi_gates(g, e, b, y, x, valid, n0, acc_v, gs, gq);
       };
       if (!mine) {
         // nothing to read: still hand the accumulator stage back (the barrier counts every epilogue thread)
@@ -281,6 +283,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
           }
           process(c + 1, v[1], cprev[1]);
         }
+        if constexpr (EPI == EPI_GATES) epi_gates_finish(e, b, valid, n_tile, yb, gs, gq);
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
@@ -352,6 +355,10 @@ conv_simt_kernel(const ConvRaw raw, const ConvGeom g, const EpiParams e) {
   if constexpr (EPI == EPI_GAUSS) epi_gauss(g, e, b, y, x, valid, n0, acc);
   if constexpr (EPI == EPI_FRAME) epi_frame(g, e, b, y, x, valid, yb * (BLOCK_M / 32) + (r >> 5), acc);
   if constexpr (EPI == EPI_F32) epi_f32<CH>(g, e, b, y, x, valid, n0, acc);
+  if constexpr (EPI == EPI_GATES) {  // cross-check kernel: raw gates only (the 3-pass cell kernel computes its own statistics)
+    float gs[4] = {}, gq[4] = {};
+    epi_gates(g, e, b, y, x, valid, n0, acc, gs, gq);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -380,6 +387,7 @@ static cudaError_t launch_simt_t(const ConvOp& op, cudaStream_t stream) {
   X(256, 128, EPI_GAUSS)    \
   X(256, 16, EPI_FRAME)     \
   X(256, 256, EPI_F32)      \
+  X(256, 256, EPI_GATES)    \
   X(256, 128, EPI_F32)      \
   X(256, 64, EPI_F32)       \
   X(128, 128, EPI_F32)      \

@@ -257,6 +257,46 @@ __device__ __forceinline__ void epi_f32(const ConvGeom& g, const EpiParams& e, i
   }
 }
 
+// ---------------------------------------------------------------- EPI_GATES
+// 32 columns = 8 channels x (in, remember, out, cell) raw gate pre-activations of one NormConvLSTMCell convolution:
+// bias added, stored fp32, and summed per gate for the GroupNorm statistics (gs / gq live in registers across the
+// column chunks of a tile: all 64 channels of a 256-column tile belong to the same GroupNorm quarter).
+__device__ __forceinline__ void epi_gates(const ConvGeom& g, const EpiParams& e, int b, int y, int x, bool valid, int n0,
+                                          const float* acc, float* gs, float* gq) {
+  if (!valid || n0 + 32 > e.cout) return;
+  float* dst = e.seg[0].dst + (static_cast<size_t>(b * g.H + y) * g.W + x) * e.seg[0].cstride + n0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 bq = __ldg(reinterpret_cast<const float4*>(e.bias + n0) + q);
+    const float4 v = make_float4(acc[4 * q] + bq.x, acc[4 * q + 1] + bq.y, acc[4 * q + 2] + bq.z, acc[4 * q + 3] + bq.w);
+    reinterpret_cast<float4*>(dst)[q] = v;
+    gs[0] += v.x; gs[1] += v.y; gs[2] += v.z; gs[3] += v.w;
+    gq[0] += v.x * v.x; gq[1] += v.y * v.y; gq[2] += v.z * v.z; gq[3] += v.w * v.w;
+  }
+}
+// After the last chunk: the 16 rows of a sample inside the tile are 16 consecutive lanes; their sums go to the
+// sample's slot of this (row tile, column tile) -- a fixed place, so the later reduction order is fixed too.
+__device__ __forceinline__ void epi_gates_finish(const EpiParams& e, int b, bool valid, int n_tile, int yb, float* gs,
+                                                 float* gq) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      gs[k] += __shfl_xor_sync(0xffffffffu, gs[k], o);
+      gq[k] += __shfl_xor_sync(0xffffffffu, gq[k], o);
+    }
+  if ((threadIdx.x & 15) == 0 && valid) {
+    const int quarter = n_tile / e.gn_ntq;
+    const int slot = yb * e.gn_ntq + (n_tile - quarter * e.gn_ntq);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float* p = e.gn_part + ((((static_cast<size_t>(b) * 2 + e.gn_tensor) * 16 + (k * 4 + quarter)) * 6 + slot) * 2);
+      p[0] = gs[k];
+      p[1] = gq[k];
+    }
+  }
+}
+
 // ---------------------------------------------------------------- EPI_GAUSS
 // columns n0 .. n0+31 = 16 z channels x (mu, logvar); z = mu + eps * exp(0.5 * logvar)
 __device__ __forceinline__ void epi_gauss(const ConvGeom& g, const EpiParams& e, int b, int y, int x, bool valid,

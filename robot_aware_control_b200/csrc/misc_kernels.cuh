@@ -68,6 +68,11 @@ cudaError_t launch_composite_nchw(const float* x4, const float* xj, float* out, 
 // (ih is also scratch: its `out` gate slot carries the output gate from pass 2 to pass 3)
 cudaError_t launch_norm_lstm_cell(float* ih, const float* hh, const float* gn_params, float* c_state,
                                   __nv_bfloat16* h_out, int B, int P, int hid, cudaStream_t s);
+// gate convolutions ran with EPI_GATES: GroupNorm partial sums gn_part[B][2][16][6][2] come from their epilogues
+// (nslots used per group), obuf = fp32 scratch [B, P, hid] for the output gate
+cudaError_t launch_norm_lstm_cell_fused(const float* ih, const float* hh, const float* gn_part, int nslots,
+                                        const float* gn_params, float* c_state, float* obuf, __nv_bfloat16* h_out,
+                                        int B, int P, int hid, cudaStream_t s);
 cudaError_t norm_lstm_set_attributes();
 
 // ---- CEM (cem_kernels.cu) ----

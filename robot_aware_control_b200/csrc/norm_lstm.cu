@@ -150,12 +150,118 @@ norm_lstm_cell_kernel(float* __restrict__ ih, const float* __restrict__ hh, cons
   }
 }
 
+// Variant for gate convolutions that ran with the EPI_GATES epilogue: the GroupNorm sums of both gate tensors arrive
+// as per-tile partials (gn_part[b][tensor][group][slot][2], written by conv_tc_kernel), so the 786 KB of gates of a
+// sample are read ONCE. Phase A forms the pre-norm cell state (-> c_state) and the output gate (-> obuf, fp32) and
+// reduces the cell statistics; phase B re-reads those 2 x 98 KB (L1 / L2 resident) and writes c / h.
+__global__ void __launch_bounds__(512, 2)
+norm_lstm_cell_fused_kernel(const float* __restrict__ ih, const float* __restrict__ hh, const float* __restrict__ part,
+                            int nslots, const float* __restrict__ gnp, float* __restrict__ c_state,
+                            float* __restrict__ obuf, __nv_bfloat16* __restrict__ h_out, int P, int hid, float eps) {
+  extern __shared__ float smem[];
+  float* stats = smem;       // mean[48], rstd[48]
+  float* cscr = smem + 96;   // [2][T]
+  const int T = blockDim.x;
+  const int R = T / hid;
+  const int ch = threadIdx.x % hid;
+  const int r0 = threadIdx.x / hid;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = T >> 5;
+  const size_t b = blockIdx.x;
+  const float4* ih4 = reinterpret_cast<const float4*>(ih + b * P * 4 * hid);
+  const float4* hh4 = reinterpret_cast<const float4*>(hh + b * P * 4 * hid);
+  const int qw = hid / 4;
+  if (threadIdx.x < 32) {  // (tensor, group): sum of the tile partials in slot order
+    const float* p = part + (b * 32 + threadIdx.x) * 6 * 2;
+    double sum = 0.0, sq = 0.0;
+    for (int s = 0; s < nslots; ++s) {
+      sum += static_cast<double>(p[2 * s]);
+      sq += static_cast<double>(p[2 * s + 1]);
+    }
+    const double n = static_cast<double>(P) * qw;
+    const double mean = sum / n;
+    double var = sq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[threadIdx.x] = static_cast<float>(mean);
+    stats[48 + threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  const int quarter = ch / qw;
+  const float4* gp4 = reinterpret_cast<const float4*>(gnp);
+  const float4 ga = gp4[ch], ba = gp4[hid + ch], gb = gp4[2 * hid + ch], bb = gp4[3 * hid + ch];
+  float ma[4], ra[4], mb[4], rb[4];
+#pragma unroll
+  for (int gte = 0; gte < 4; ++gte) {
+    ma[gte] = stats[gte * 4 + quarter]; ra[gte] = stats[48 + gte * 4 + quarter];
+    mb[gte] = stats[16 + gte * 4 + quarter]; rb[gte] = stats[48 + 16 + gte * 4 + quarter];
+  }
+  float cs = 0.f, cq = 0.f;
+  float* cst = c_state + b * P * hid;
+  float* ob = obuf + b * P * hid;
+#pragma unroll 4
+  for (int p = r0; p < P; p += R) {
+    const size_t i = static_cast<size_t>(p) * hid + ch;
+    const float4 a = __ldcs(ih4 + i);
+    const float4 c = __ldcs(hh4 + i);
+    const float gi = ((a.x - ma[0]) * ra[0] * ga.x + ba.x) + ((c.x - mb[0]) * rb[0] * gb.x + bb.x);
+    const float gf = ((a.y - ma[1]) * ra[1] * ga.y + ba.y) + ((c.y - mb[1]) * rb[1] * gb.y + bb.y);
+    const float go = ((a.z - ma[2]) * ra[2] * ga.z + ba.z) + ((c.z - mb[2]) * rb[2] * gb.z + bb.z);
+    const float gc = ((a.w - ma[3]) * ra[3] * ga.w + ba.w) + ((c.w - mb[3]) * rb[3] * gb.w + bb.w);
+    const float cp = sigmoid_exact(gf) * cst[i] + sigmoid_exact(gi) * tanhf(gc);
+    cst[i] = cp;
+    ob[i] = sigmoid_exact(go);
+    cs += cp;
+    cq += cp * cp;
+  }
+  cscr[threadIdx.x] = cs;
+  cscr[T + threadIdx.x] = cq;
+  __syncthreads();
+  const int cw = hid / 16;
+  for (int job = warp; job < 16; job += nwarps) {
+    double sum = 0.0, sq = 0.0;
+    for (int r = 0; r < R; ++r) {
+      sum += warp_sum_strided(cscr + r * hid + job * cw, cw, 1, lane);
+      sq += warp_sum_strided(cscr + T + r * hid + job * cw, cw, 1, lane);
+    }
+    if (lane == 0) {
+      const double n = static_cast<double>(P) * cw;
+      const double mean = sum / n;
+      double var = sq / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      stats[32 + job] = static_cast<float>(mean);
+      stats[48 + 32 + job] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+  }
+  __syncthreads();
+  const float cg = gnp[16 * hid + ch], cb = gnp[17 * hid + ch];
+  const float mc = stats[32 + ch / cw], rc = stats[48 + 32 + ch / cw];
+  __nv_bfloat16* ho = h_out + b * P * hid;
+#pragma unroll 4
+  for (int p = r0; p < P; p += R) {
+    const size_t i = static_cast<size_t>(p) * hid + ch;
+    const float c = (cst[i] - mc) * rc * cg + cb;
+    cst[i] = c;
+    ho[i] = __float2bfloat16(ob[i] * tanhf(c));
+  }
+}
+
 }  // namespace
 
 static size_t norm_lstm_stats_off(int, int, int T) { return static_cast<size_t>(16) * T; }  // after the pass-1 scratch
 
 cudaError_t norm_lstm_set_attributes() {
   return cudaFuncSetAttribute(norm_lstm_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+cudaError_t launch_norm_lstm_cell_fused(const float* ih, const float* hh, const float* gn_part, int nslots,
+                                        const float* gn_params, float* c_state, float* obuf, __nv_bfloat16* h_out,
+                                        int B, int P, int hid, cudaStream_t s) {
+  if (hid % 64 != 0 || hid > 512 || nslots < 1 || nslots > 6) return cudaErrorInvalidValue;
+  const int R = hid >= 512 ? 1 : 512 / hid;
+  const int T = hid * R;
+  if (T > 512) return cudaErrorInvalidValue;
+  const size_t smem = (96 + 2 * static_cast<size_t>(T)) * sizeof(float);
+  norm_lstm_cell_fused_kernel<<<B, T, smem, s>>>(ih, hh, gn_part, nslots, gn_params, c_state, obuf, h_out, P, hid, 1e-5f);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_norm_lstm_cell(float* ih, const float* hh, const float* gn_params, float* c_state,

@@ -64,6 +64,7 @@ struct Workspace {
   ConvOp lstm[3][2][2];  // [which][layer][parity]
   ConvOp lstm_hh[3][2][2];  // lstm_group_norm: hh_gates convolution (lstm[][][] is then the ih_gates one)
   float *gn_ih = nullptr, *gn_hh = nullptr;  // lstm_group_norm: raw gate convolutions [B, 48, 4g] fp32
+  float *gn_part = nullptr, *gn_o = nullptr; // fused GroupNorm statistics: per-tile partial sums, output-gate scratch
   ConvOp gauss[2][2];    // [prior, post][parity]
   ConvOp dec[10][2];     // [layer][parity] (only dec[0] depends on parity)
   std::unordered_map<std::string, std::pair<void*, std::pair<int64_t, int>>> named;
@@ -93,6 +94,8 @@ struct rac_handle {
   // (default off: measured neutral to -1 % -- those kernels run at the power cap, hiding their epilogue only lowers
   // the clock of the main loop)
   int two_cta = 2;
+  int gn_fuse_stats = 1;     // RAC_GN_FUSE=0: lstm_group_norm statistics by the 3-pass cell kernel instead of the gate-conv epilogue
+  bool gn_fused = false;
   int first_conv_tc = 1;     // RAC_FIRST_TC=0: encoder.c1.0 on the CUDA cores (fp32 inputs) instead of the tensor-core kernel
   int split_tail = 1;        // RAC_SPLIT_TAIL=0: no tail splitting in conv_tc_kernel (A/B measurements)
   int act_block_n = 256;     // RAC_ACT_BN=128: 256x128 tiles (double-buffered TMEM) for the BN+LeakyReLU layers (A/B measurements)
@@ -271,7 +274,7 @@ int make_conv(rac_handle* h, ConvOp* op, const char* name, int layer, int H, int
   op->name = name;
   op->block_m = h->tile_m;
   op->block_n = s.block_n;
-  if (h->tile_m == 256 && s.n_packed % 256 == 0 && (epi == EPI_ACT || epi == EPI_LSTM || epi == EPI_F32)) op->block_n = 256;
+  if (h->tile_m == 256 && s.n_packed % 256 == 0 && (epi == EPI_ACT || epi == EPI_LSTM || epi == EPI_F32 || epi == EPI_GATES)) op->block_n = 256;
   if (epi == EPI_ACT && h->act_block_n == 128 && op->block_n == 256) op->block_n = 128;
   op->epi = epi;
   ConvGeom& g = op->g;
@@ -425,6 +428,8 @@ void carve(rac_handle* h, Bump& bp, int B) {
   if (h->cfg.lstm_group_norm) {
     w.gn_ih = bp.take<float>(n * P3 * 4 * g);
     w.gn_hh = bp.take<float>(n * P3 * 4 * g);
+    w.gn_part = bp.take<float>(((n + 15) / 16 * 16) * 2 * 16 * 6 * 2);
+    w.gn_o = bp.take<float>(n * P3 * g);
   }
   w.cost_part = bp.take<float>(n * 128 * 2);
   w.goal4 = bp.take<float>(static_cast<size_t>(kMaxGoals) * P0 * 4);
@@ -475,19 +480,25 @@ int build_ops(rac_handle* h) {
   const char* n1[3] = {"prior.lstm.1", "posterior.lstm.1", "frame_predictor.lstm.1"};
   if (c.lstm_group_norm) {
     const int hh0[3] = {RAC_L_PRIOR_LSTM0_HH, RAC_L_POST_LSTM0_HH, RAC_L_FP_LSTM0_HH};
-    auto f32_out = [&](ConvOp* op, float* dst) {
+    // GroupNorm sums fused into the gate-conv epilogue when a 256-column tile lies inside one GroupNorm quarter
+    h->gn_fused = h->gn_fuse_stats && c.conv_impl == 0 && h->tile_m == 256 && (g == 256 || g == 512);
+    const int gates_epi = h->gn_fused ? EPI_GATES : EPI_F32;
+    auto f32_out = [&](ConvOp* op, float* dst, int tensor) {
       op->e.nseg = 1;
       op->e.seg[0] = F32Seg{0, 4 * g, dst, 4 * g, 0, 0};
+      op->e.gn_part = w.gn_part;
+      op->e.gn_tensor = tensor;
+      op->e.gn_ntq = g / 256;  // 256-column tiles (64 channels) per GroupNorm quarter (g / 4 channels)
     };
     for (int l = 0; l < 3; ++l)
       for (int p = 0; p < 2; ++p) {
-        CKR(make_conv(h, &w.lstm[l][0][p], n0[l], l0[l], 6, 8, {{xin[l], g}}, EPI_F32));
-        CKR(make_conv(h, &w.lstm_hh[l][0][p], n0[l], hh0[l], 6, 8, {{w.hs[l][0][p], g}}, EPI_F32));
-        CKR(make_conv(h, &w.lstm[l][1][p], n1[l], l1[l], 6, 8, {{w.hs[l][0][p ^ 1], g}}, EPI_F32));
-        CKR(make_conv(h, &w.lstm_hh[l][1][p], n1[l], hh0[l] + 1, 6, 8, {{w.hs[l][1][p], g}}, EPI_F32));
+        CKR(make_conv(h, &w.lstm[l][0][p], n0[l], l0[l], 6, 8, {{xin[l], g}}, gates_epi));
+        CKR(make_conv(h, &w.lstm_hh[l][0][p], n0[l], hh0[l], 6, 8, {{w.hs[l][0][p], g}}, gates_epi));
+        CKR(make_conv(h, &w.lstm[l][1][p], n1[l], l1[l], 6, 8, {{w.hs[l][0][p ^ 1], g}}, gates_epi));
+        CKR(make_conv(h, &w.lstm_hh[l][1][p], n1[l], hh0[l] + 1, 6, 8, {{w.hs[l][1][p], g}}, gates_epi));
         for (int k = 0; k < 2; ++k) {
-          f32_out(&w.lstm[l][k][p], w.gn_ih);
-          f32_out(&w.lstm_hh[l][k][p], w.gn_hh);
+          f32_out(&w.lstm[l][k][p], w.gn_ih, 0);
+          f32_out(&w.lstm_hh[l][k][p], w.gn_hh, 1);
         }
       }
   }
@@ -625,7 +636,11 @@ int launch_lstm(rac_handle* h, int l, cudaStream_t st) {
       CKR(launch(h, w.lstm_hh[l][k][p], st));
       {
         ProfScope ps(h, "norm_lstm_cell", st);
-        CK(launch_norm_lstm_cell(w.gn_ih, w.gn_hh, h->gn_params[l][k], w.cs[l][k], w.hs[l][k][p ^ 1], w.B, 48, g, st));
+        if (h->gn_fused)
+          CK(launch_norm_lstm_cell_fused(w.gn_ih, w.gn_hh, w.gn_part, 3 * (g / 256), h->gn_params[l][k], w.cs[l][k],
+                                         w.gn_o, w.hs[l][k][p ^ 1], w.B, 48, g, st));
+        else
+          CK(launch_norm_lstm_cell(w.gn_ih, w.gn_hh, h->gn_params[l][k], w.cs[l][k], w.hs[l][k][p ^ 1], w.B, 48, g, st));
       }
       h->launches++;
     }
@@ -783,6 +798,7 @@ int rac_create(const rac_config* cfg, rac_handle** out) {
   if (const char* v = getenv("RAC_SPLIT_TAIL")) h->split_tail = atoi(v) != 0;
   if (const char* v = getenv("RAC_2CTA")) h->two_cta = atoi(v);
   if (const char* v = getenv("RAC_FIRST_TC")) h->first_conv_tc = atoi(v) != 0;
+  if (const char* v = getenv("RAC_GN_FUSE")) h->gn_fuse_stats = atoi(v) != 0;
   CK(first_conv_tc_set_attributes());
   CK(conv_tc2_set_attributes());
   if (const char* v = getenv("RAC_HALO_BASE_OFFSET")) h->halo_base_offset = atoi(v) != 0;

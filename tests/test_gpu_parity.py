@@ -73,11 +73,13 @@ def test_forward_matches_reference_golden(golden_dir, tag, impl):
     assert np.abs(logvar.cpu().numpy() - gold["post_logvar"]).max() < 5e-2
 
 
-def test_tc_matches_simt_layer_by_layer():
-    """tcgen05 path vs the SIMT cross-check kernel on the same packed operands: only the accumulation order differs."""
+@pytest.mark.parametrize("B", [1, 5, 33])
+def test_tc_matches_simt_layer_by_layer(B):
+    """tcgen05 paths (generic, CTA-pair, halo, tensor-core first conv) vs the SIMT cross-check kernel on the same packed
+    operands: only the accumulation order (and the bf16 rounding of the first layer's inputs) differs. B = 1, 5, 33 are
+    not multiples of the 16-candidate latent tile: out-of-range rows, single-tile grids, ragged CTA pairs."""
     cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM)
     sd = so.make_state_dict(cfg, 3)
-    B = 5  # not a multiple of the 8-candidate latent tile: exercises the out-of-range rows
     g = torch.Generator().manual_seed(4)
     img = torch.rand(B, 3, 48, 64, generator=g)
     act = (torch.rand(B, 5, generator=g) - 0.5) * 0.1
