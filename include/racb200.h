@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RAC_ABI_VERSION 2
+#define RAC_ABI_VERSION 3
 
 typedef enum {
   RAC_OK = 0,
@@ -146,8 +146,22 @@ typedef struct {
   float* obs_out;              /* (steps, n, H, W, 4) fp32 (rgb + pad) or NULL */
   float* step_cost_out;        /* (steps, n) fp32 or NULL */
   double* sum_cost;            /* (n) fp64 out */
+  /* Multi-GPU (candidates sharded over the GPUs of one NVLink / NVSwitch node): when peer_world > 0 the kernel that
+   * finishes the per-candidate cost of the LAST step also stores it straight into the gathered cost vector of every
+   * rank through peer memory -- peer_cost_bufs = DEVICE array of peer_world pointers to each rank's (N) fp64 buffer
+   * mapped into this process (e.g. torch symmetric memory), element peer_offset + i for local candidate i. This is
+   * the all-gather of cem.py:96 fused into the cost kernel; rac_peer_barrier() orders it against the consumers. */
+  double* const* peer_cost_bufs;
+  int peer_world;
+  int64_t peer_offset;
 } rac_rollout;
 int rac_rollout_cost(rac_handle* h, const rac_rollout* r, void* stream);
+
+/* Cross-GPU barrier after the fused cost exchange: every rank stores `seq` into slot [rank] of every peer's signal pad
+ * (system-scope release), then waits until all peer_world slots of its own pad hold `seq` (acquire). signal_pads =
+ * DEVICE array of peer_world pointers to the ranks' uint32 pads; words [slot_base, slot_base + peer_world) of each pad
+ * are used (zero-initialised; seq must increase by one per call). A rank that never arrives makes the kernel trap after ~2 s instead of hanging. */
+int rac_peer_barrier(uint32_t* const* signal_pads, int slot_base, int rank, int peer_world, uint32_t seq, void* stream);
 
 /* CEMPolicy.get_action pieces (cem.py:76-104). */
 int rac_cem_sample(const float* mean, const float* stdv, const float* noise, unsigned long long seed, int iter,

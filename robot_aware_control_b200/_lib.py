@@ -34,7 +34,8 @@ class RacRollout(C.Structure):
         ("eps", C.c_void_p), ("seed", C.c_ulonglong), ("noise_ctr_base", C.c_uint), ("sample_mean", C.c_int),
         ("zero_robot", C.c_int), ("dontcare_cost", C.c_int), ("sparse_cost", C.c_int),
         ("world_cost_weight", C.c_float), ("obs_out", C.c_void_p), ("step_cost_out", C.c_void_p),
-        ("sum_cost", C.c_void_p),
+        ("sum_cost", C.c_void_p), ("peer_cost_bufs", C.c_void_p), ("peer_world", C.c_int),
+        ("peer_offset", C.c_int64),
     ]
 
 
@@ -59,6 +60,7 @@ EXPORTS = {
     "rac_init_hidden": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "rac_forward": (C.c_int, [C.c_void_p, C.POINTER(RacStep), C.c_void_p]),
     "rac_rollout_cost": (C.c_int, [C.c_void_p, C.POINTER(RacRollout), C.c_void_p]),
+    "rac_peer_barrier": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p]),
     "rac_cem_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rac_topk": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -88,8 +88,10 @@ class TrajectorySampler(object):
         return self.robot_model.predict_batch(data, thick=True)
 
     def _rollout_device(self, actions_dev, start_img_dev, goal_imgs, goal_masks, states, masks, eps, n, steps,
-                        sum_cost, obs_out=None, step_cost=None, cand_offset=0, noise_ctr=None):
-        """One rac_rollout_cost call on device tensors (no host traffic)."""
+                        sum_cost, obs_out=None, step_cost=None, cand_offset=0, noise_ctr=None, peer=None):
+        """One rac_rollout_cost call on device tensors (no host traffic). `peer` = (device pointer of the array of
+        per-rank gathered-cost buffers, world size, element offset of this shard): the cost kernel of the last step
+        then stores the finished costs into every rank's buffer over NVLink peer memory."""
         cfg = self.cfg
         m = self.model
         m.prepare(n)
@@ -117,6 +119,8 @@ class TrajectorySampler(object):
         r.obs_out = _lib.ptr(obs_out)
         r.step_cost_out = _lib.ptr(step_cost)
         r.sum_cost = _lib.ptr(sum_cost)
+        if peer is not None:
+            r.peer_cost_bufs, r.peer_world, r.peer_offset = C.c_void_p(int(peer[0])), int(peer[1]), int(peer[2])
         # robot_cost_weight: RobotL2Cost contributes 0.0 inside CEM because State.state is None (losses.py:189-190)
         _lib.check(self._lib.rac_rollout_cost(m.handle, C.byref(r), _lib.stream_ptr()), m.handle, "rac_rollout_cost")
         if noise_ctr is None:
@@ -308,6 +312,7 @@ class CEMPolicy(object):
         local_cost = torch.empty(n_local, dtype=torch.float64, device=dev)
         elite = torch.empty(K, dtype=torch.int64, device=dev)
         rollouts = None
+        peer = parallel.PeerCostExchange.get(self, N, self.process_group, dev) if (world > 1 and not host_robot) else None
         for i in range(I):
             nz = noise[i] if noise is not None else None
             _lib.check(self._lib.rac_cem_sample(_lib.ptr(mean), _lib.ptr(std), _lib.ptr(nz), plan_seed, i, N, L, A, lo,
@@ -327,8 +332,18 @@ class CEMPolicy(object):
                     # the time stride explicitly
                     states = _StridedView(states[:, lo:hi]) if getattr(cfg, "model_use_robot_state", False) else None
                     masks = _StridedView(masks[:, lo:hi])
+                fused = peer is not None and not (last and (opt_traj is not None or self.plot_rollouts))
                 ts._rollout_device(act5, start_img, goal_imgs, goal_masks, states, masks, None, n_local, L, local_cost,
-                                   cand_offset=lo, noise_ctr=i * L)
+                                   cand_offset=lo, noise_ctr=i * L, peer=peer.target(lo) if fused else None)
+                if fused:
+                    # the per-candidate costs are already in every rank's buffer (stored by the cost kernel through
+                    # NVLink peer memory); one flag barrier orders them against the replicated top-k
+                    costs = peer.finish(self._lib)
+                    _lib.check(self._lib.rac_topk(_lib.ptr(costs), N, K, _lib.ptr(elite), None, _lib.stream_ptr()), None,
+                               "rac_topk")
+                    _lib.check(self._lib.rac_cem_refit(_lib.ptr(act2), L, _lib.ptr(elite), K, 0.001, _lib.ptr(mean),
+                                                       _lib.ptr(std), _lib.stream_ptr()), None, "rac_cem_refit")
+                    continue
             costs = parallel.all_gather_costs(local_cost, N, self.process_group)
             _lib.check(self._lib.rac_topk(_lib.ptr(costs), N, K, _lib.ptr(elite), None, _lib.stream_ptr()), None,
                        "rac_topk")

@@ -232,7 +232,8 @@ cudaError_t launch_goal_prep(const uint8_t* goal_hwc, float* goal4, int G, int H
 // ---------------------------------------------------------------- cost finish
 __global__ void __launch_bounds__(128)
 cost_finish_kernel(const float* __restrict__ part, int nparts, int dontcare, float weight, int accumulate,
-                   double* __restrict__ sum_cost, float* __restrict__ step_cost, int B) {
+                   double* __restrict__ sum_cost, float* __restrict__ step_cost, int B, double* const* peers,
+                   int peer_world, long long peer_offset) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const float* p = part + static_cast<size_t>(b) * nparts * 2;
@@ -246,11 +247,41 @@ cost_finish_kernel(const float* __restrict__ part, int nparts, int dontcare, flo
   const float cost = weight * (-dist);
   if (step_cost) step_cost[b] = accumulate ? cost : 0.f;  // unused steps report rew = 0 (trajectory_sampler.py:165-173)
   if (accumulate) sum_cost[b] += static_cast<double>(cost);
+  if (peers) {
+    // last rollout step on a sharded plan: the finished cost goes straight into every rank's gathered cost vector
+    // (stores over NVLink peer memory; the all-gather of cem.py:96 without a collective call)
+    const double v = sum_cost[b];
+    for (int p = 0; p < peer_world; ++p) peers[p][peer_offset + b] = v;
+    __threadfence_system();
+  }
+}
+
+// Cross-GPU flag barrier: lane p publishes `seq` in slot [rank] of rank p's pad, then waits for slot [p] of its own pad.
+__global__ void __launch_bounds__(32) peer_barrier_kernel(uint32_t* const* pads, int base, int rank, int world,
+                                                          uint32_t seq) {
+  const int p = threadIdx.x;
+  if (p >= world) return;
+  __threadfence_system();  // the peer stores of the preceding kernels on this stream are ordered before the flag
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pads[p] + base + rank), "r"(seq) : "memory");
+  const uint32_t* mine = pads[rank] + base + p;
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if (static_cast<int32_t>(v - seq) >= 0) break;
+    if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a missing rank must not hang the GPU
+  }
+}
+cudaError_t launch_peer_barrier(uint32_t* const* pads, int base, int rank, int world, uint32_t seq, cudaStream_t s) {
+  if (world < 1 || world > 32 || rank < 0 || rank >= world || base < 0) return cudaErrorInvalidValue;
+  peer_barrier_kernel<<<1, 32, 0, s>>>(pads, base, rank, world, seq);
+  return cudaGetLastError();
 }
 cudaError_t launch_cost_finish(const float* cost_part, int nparts, int dontcare, float weight, int accumulate,
-                               double* sum_cost, float* step_cost, int B, cudaStream_t s) {
+                               double* sum_cost, float* step_cost, int B, cudaStream_t s, double* const* peers,
+                               int peer_world, long long peer_offset) {
   cost_finish_kernel<<<(B + 127) / 128, 128, 0, s>>>(cost_part, nparts, dontcare, weight, accumulate, sum_cost,
-                                                     step_cost, B);
+                                                     step_cost, B, peers, peer_world, peer_offset);
   return cudaGetLastError();
 }
 

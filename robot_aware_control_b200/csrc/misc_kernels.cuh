@@ -36,8 +36,11 @@ cudaError_t launch_img_prep_nchw(const float* img_nchw, float* img4, int B, int 
 cudaError_t launch_goal_prep(const uint8_t* goal_hwc, float* goal4, int G, int H, int W, cudaStream_t s);
 // per-candidate cost from the per-tile partials of the frame epilogue (reference losses.py:224-235,244-263,307-335;
 // fp64 accumulation over steps as trajectory_sampler.py:74,169)
+// peers != null (last step of a sharded plan): the finished cost is also stored into every rank's gathered vector
 cudaError_t launch_cost_finish(const float* cost_part, int nparts, int dontcare, float weight, int accumulate,
-                               double* sum_cost, float* step_cost, int B, cudaStream_t s);
+                               double* sum_cost, float* step_cost, int B, cudaStream_t s,
+                               double* const* peers = nullptr, int peer_world = 0, long long peer_offset = 0);
+cudaError_t launch_peer_barrier(uint32_t* const* pads, int base, int rank, int world, uint32_t seq, cudaStream_t s);
 // stand-alone planning cost in the reference's own tensor layout (NCHW fp32): ImgL2Cost / ImgDontcareCost
 cudaError_t launch_masked_cost(const float* curr, const float* goal, const float* curr_mask, const float* goal_mask,
                                int dontcare, float* out, int B, int HW, cudaStream_t s);

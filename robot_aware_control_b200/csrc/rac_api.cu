@@ -1008,12 +1008,20 @@ int rac_rollout_cost(rac_handle* h, const rac_rollout* r, void* stream) {
     const int use = (!r->sparse_cost || t == r->steps - 1) ? 1 : 0;  // trajectory_sampler.py:167
     {
       ProfScope ps(h, "cost_finish", st);
+      const bool push = r->peer_world > 0 && r->peer_cost_bufs && t == r->steps - 1;
       CK(launch_cost_finish(w.cost_part, w.dec[9][0].e.cost_nparts, r->dontcare_cost, r->world_cost_weight, use, r->sum_cost,
-                            r->step_cost_out ? r->step_cost_out + static_cast<size_t>(t) * n : nullptr, n, st));
+                            r->step_cost_out ? r->step_cost_out + static_cast<size_t>(t) * n : nullptr, n, st,
+                            push ? r->peer_cost_bufs : nullptr, r->peer_world, r->peer_offset));
     }
     h->launches++;
   }
   return RAC_OK;
+}
+
+int rac_peer_barrier(uint32_t* const* signal_pads, int slot_base, int rank, int peer_world, uint32_t seq, void* stream) {
+  if (!signal_pads) return RAC_ERR_INVALID;
+  return launch_peer_barrier(signal_pads, slot_base, rank, peer_world, seq, static_cast<cudaStream_t>(stream)) == cudaSuccess ? RAC_OK
+                                                                                                                  : RAC_ERR_INVALID;
 }
 
 int rac_cem_sample(const float* mean, const float* stdv, const float* noise, unsigned long long seed, int iter,
