@@ -146,7 +146,7 @@ def workload_config(n_gpus, world, robot_aware=False):
     return {
         "workload": (f"CEM plan: {n_total} candidates x L={L_STEPS} predicted frames x {ITERS} iterations, 10% elites, "
                      f"SVG g_dim {G_DIM} z_dim {Z_DIM} action_dim {A_DIM}, 48x64 RGB, {kind}"
-                     + ("" if n_gpus == 1 else f", candidates sharded over {n_gpus} GPUs, cost all-gather (NCCL) + replicated refit")),
+                     + ("" if n_gpus == 1 else f", candidates sharded over {n_gpus} GPUs, per-candidate costs stored into every rank's vector over NVLink peer memory by the cost kernel (NCCL all-gather as fallback) + replicated refit")),
         "candidates": n_total, "rollout_steps": L_STEPS, "cem_iterations": ITERS, "elites": n_total // 10,
         "l2": "activation working set per plan (>9 GB) is far larger than the 126 MB L2; no explicit flush",
         "noise": "Philox on device (value) / torch CPU generator uploaded from pinned memory (e2e)",
