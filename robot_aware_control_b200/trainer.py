@@ -346,6 +346,35 @@ class SVGTrainer:
 
     eval_step = _eval_step
 
+    def _eval_video(self, data, autoregressive=False, noise=None):
+        """PredictionTrainer._eval_video (trainer.py:489-565): the video is cut into floor(T / n_eval) windows, every
+        window is evaluated with `_eval_step` (3 samples for autoregressive svg evaluation of a "finetune" experiment,
+        else 1), the samples are ranked by "autoreg_psnr" and the best one is averaged over the windows.
+        `data["pred_masks"]` (model-input masks, e.g. from the analytical robot model) is used when present, else the
+        true masks -- the reference obtains them from `self.robot_model.predict_batch` inside this function, which
+        needs the simulator and stays outside this package. `noise[sample][window]` = (eps_prior, eps_post) is a test
+        hook for `set_noise`."""
+        cf = self._config
+        num_samples = 3 if (autoregressive and "finetune" in str(getattr(cf, "experiment", ""))) else 1
+        x = data["images"]
+        T = len(x)
+        window = int(getattr(cf, "n_eval", T))
+        nwin = T // window
+        sampled = [dict() for _ in range(num_samples)]
+        pm = data.get("pred_masks", data["masks"])
+        for i in range(nwin):
+            s, e = i * window, (i + 1) * window
+            batch = {"images": x[s:e], "states": data["states"][s:e], "actions": data["actions"][s:e - 1],
+                     "masks": data["masks"][s:e], "pred_masks": pm[s:e]}
+            for k in range(num_samples):
+                if noise is not None:
+                    self.set_noise(*noise[k][i])
+                for key, v in self._eval_step(batch, autoregressive).items():
+                    sampled[k][key] = sampled[k].get(key, 0.0) + v
+        if autoregressive:
+            sampled.sort(key=lambda d: d["autoreg_psnr"], reverse=True)
+        return {k: v / nwin for k, v in sampled[0].items()}
+
     def grad_of(self, key):
         o = self._offsets[key]
         p = dict(self.model.named_parameters())[key]

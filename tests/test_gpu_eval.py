@@ -10,7 +10,7 @@ import torch
 
 from oracle import eval_oracle as eo
 from oracle import svg_oracle as so
-from oracle.make_golden_eval import make_eval_batch, G_DIM, Z_DIM, T
+from oracle.make_golden_eval import make_eval_batch, make_eval_video, G_DIM, Z_DIM, T
 from tests.test_eval_oracle_golden import eval_cfg, metric_inputs
 
 pytestmark = pytest.mark.gpu
@@ -83,3 +83,24 @@ def test_eval_step_matches_reference_golden(golden_dir, tag):
     model.train()
     with pytest.raises(RuntimeError):
         trainer._eval_step(batch)
+
+
+def test_eval_video_best_of_3_matches_reference_golden(golden_dir):
+    """SVGTrainer._eval_video against the reference's _eval_video (2 windows, best of 3 samples by autoreg_psnr)."""
+    from robot_aware_control_b200 import SVGConvModel, SVGTrainer
+
+    gold = np.load(os.path.join(golden_dir, "eval_video_ra.npz"))
+    ref = dict(zip(gold["keys"].tolist(), gold["values"].tolist()))
+    cfg = eval_cfg("ra")
+    cfg.n_eval, cfg.test_batch_size, cfg.experiment = int(gold["n_eval"]), int(gold["B"]), "finetune_synthetic"
+    model = SVGConvModel(cfg)
+    model.load_state_dict(so.make_state_dict(cfg, int(gold["weight_seed"])))
+    trainer = SVGTrainer(cfg, model)
+    model.eval()
+    vid, eps_p, eps_q = make_eval_video(int(gold["input_seed"]), cfg)
+    noise = [[(eps_p[k][w], eps_q[k][w]) for w in range(2)] for k in range(3)]
+    got = trainer._eval_video(vid, autoregressive=True, noise=noise)
+    assert set(got) == set(ref)
+    for k, v in ref.items():
+        tol = 0.05 if k.endswith("psnr") else (5e-3 if k.endswith("ssim") else 2e-2 * abs(v) + 1e-6)
+        assert abs(got[k] - v) < tol, (k, got[k], v)
