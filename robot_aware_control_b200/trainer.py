@@ -14,7 +14,7 @@ flat gradient buffer is all-reduced (NCCL) and averaged before the Adam update, 
 
 Scheduled sampling follows the reference (same probability schedule, same global numpy generator); when the model's
 own prediction is fed back, its gradient flows into the previous step as in the reference (`x_pred.clone()`).
-Limits (raise): heatmaps, multiview, movement weighting, n_past != 1, last_frame_skip False.
+Limits (raise): heatmaps, multiview, movement weighting, last_frame_skip False, lstm_group_norm.
 """
 import ctypes as C
 
@@ -119,8 +119,8 @@ class SVGTrainer:
         c = svg_config_from(config)
         self.n_future = getattr(config, "n_future", 5)
         self.n_past = getattr(config, "n_past", 1)
-        if self.n_past != 1:
-            raise NotImplementedError("n_past must be 1 (the reference training recipe, README.md:103)")
+        # n_past only sets the clip length (n_past + n_future frames, trainer.py:352) and, with last_frame_skip False
+        # (refused below), which step's skip tensors the decoder keeps (trainer.py:409-411)
         self._scheduled_sampling = bool(getattr(config, "scheduled_sampling", False))
         self._ss_k = float(getattr(config, "scheduled_sampling_k", 4000))
         self._forced_tokens = None
@@ -269,7 +269,8 @@ class SVGTrainer:
             raise RuntimeError("call model.train() before train_step (reference trainer.py:754)")
         losses = self.forward_backward(batch)
         self.optimizer_step()
-        nf = batch["images"].shape[0] - 1
+        # the reference divides the logged sums by cfg.n_future whatever the clip length is (trainer.py:463-464)
+        nf = int(getattr(self._config, "n_future", batch["images"].shape[0] - 1))
         vals = losses.cpu()
         out = {"recon_loss": float(vals[0]) / nf, "kld": float(vals[1]) / nf}
         if batch.get("masks") is not None:  # the reference logs these for every step (trainer.py:436-439)
