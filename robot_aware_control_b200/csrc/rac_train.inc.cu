@@ -207,7 +207,8 @@ int conv_backward(rac_handle* h, TrainState* T, int layer, int H, int W, const s
     CKR(t_gemm(h, "train.dgrad", {B, H, W, ks, false}, {{dY, L.kpad}}, L.wd, L.taps * L.kpad, L.ctot, pick_bn(L.ctot),
                EPI_F32, e, st));
   }
-  if (L.d.bias_off) CK(launch_bias_grad(dY, M, L.kpad, L.n_packed, L.d.bias_off, T->grads, st));
+  // bias gradient = row sums of the all-time-steps dY^T: once, after the last processed step
+  if (L.d.bias_off && T->cur_t == 0) CK(launch_bias_grad_rows(L.dyT, ld, L.n_packed, L.d.bias_off, T->grads, st));
   return RAC_OK;
 }
 

@@ -383,6 +383,36 @@ cudaError_t launch_bias_grad(const __nv_bfloat16* dy, int M, int ncols, int nval
   return cudaGetLastError();
 }
 
+// bias gradient from the all-time-steps transposed operand dyT [rows, ld] (row n = packed output column, the ld columns
+// = every output position of every time step, zero-padded): one warp per row, fixed summation order
+__global__ void __launch_bounds__(256)
+bias_grad_rows_kernel(const __nv_bfloat16* __restrict__ dyT, int ld, int nvalid, const long long* __restrict__ bias_off,
+                      float* __restrict__ grads) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= nvalid) return;
+  const uint4* row = reinterpret_cast<const uint4*>(dyT + static_cast<size_t>(n) * ld);
+  float acc = 0.f;
+  for (int i = lane; i < ld / 8; i += 32) {
+    const uint4 v = row[i];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(h[j]);
+      acc += f.x + f.y;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0 && bias_off[n] >= 0) grads[bias_off[n]] += acc;
+}
+cudaError_t launch_bias_grad_rows(const __nv_bfloat16* dyT, int ld, int nvalid, const long long* bias_off, float* grads,
+                                  cudaStream_t s) {
+  if (ld % 8 != 0) return cudaErrorInvalidValue;
+  bias_grad_rows_kernel<<<(nvalid + 7) / 8, 256, 0, s>>>(dyT, ld, nvalid, bias_off, grads);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ z / KL
 __global__ void __launch_bounds__(256)
 gauss_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ mu, const float* __restrict__ lv,

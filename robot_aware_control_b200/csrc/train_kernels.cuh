@@ -45,6 +45,9 @@ cudaError_t launch_bn_bwd(const float* dy, int dy_cstride, int dy_coff, int upsa
 cudaError_t launch_lstm_bwd(const float* dh, float* dc, const float* gates, const float* c_prev_or_null,
                             const float* c_new, int M, int hid, __nv_bfloat16* dgates, cudaStream_t s);
 // grads[bias_off[n]] += sum_m dy[m][n] for n < nvalid   (dy bf16 [M, ncols])
+// the same sum over ALL time steps at once, from the transposed wgrad operand dyT [rows, ld]
+cudaError_t launch_bias_grad_rows(const __nv_bfloat16* dyT, int ld, int nvalid, const long long* bias_off, float* grads,
+                                  cudaStream_t s);
 cudaError_t launch_bias_grad(const __nv_bfloat16* dy, int M, int ncols, int nvalid, const long long* bias_off,
                              float* grads, cudaStream_t s);
 
