@@ -6,46 +6,55 @@
 namespace rac {
 
 // ------------------------------------------------------------------------------------------------ weights
+// Packed operand <-> flat parameter buffer, one CTA per (packed row n, 64-channel block). In the PyTorch layout
+// (cout, cin, kh, kw) the `taps` weights of one (n, c) are contiguous and consecutive channels follow each other, so the
+// flat side is walked linearly (j = c_local * taps + tap: coalesced) and the packed side [n][tap][c] is written /
+// read through a shared-memory tile with c fastest (coalesced too). col_off[c] < 0 marks padding channels.
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(const float* __restrict__ params, const long long* __restrict__ row_off,
                     const int* __restrict__ col_off, int n_packed, int taps, int ctot, int flip,
                     __nv_bfloat16* __restrict__ wp) {
-  const long long total = static_cast<long long>(n_packed) * taps * ctot;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % ctot);
-    const int tap = static_cast<int>((i / ctot) % taps);
-    const int n = static_cast<int>(i / (static_cast<long long>(ctot) * taps));
-    const long long ro = row_off[n];
-    const int co = col_off[c];
+  __shared__ float tile[25][65];
+  const int n = blockIdx.x, c0 = blockIdx.y * 64;
+  const long long ro = row_off[n];
+  for (int j = threadIdx.x; j < 64 * taps; j += blockDim.x) {
+    const int cl = j / taps, tap = j - cl * taps;
+    const int co = col_off[c0 + cl];
     float v = 0.f;
-    if (ro >= 0 && co >= 0) v = params[ro + co + (flip ? taps - 1 - tap : tap)];
-    wp[i] = __float2bfloat16(v);
+    if (ro >= 0 && co >= 0) v = params[ro + co + tap];
+    tile[flip ? taps - 1 - tap : tap][cl] = v;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 64 * taps; j += blockDim.x) {
+    const int tap = j >> 6, cl = j & 63;
+    wp[(static_cast<long long>(n) * taps + tap) * ctot + c0 + cl] = __float2bfloat16(tile[tap][cl]);
   }
 }
 cudaError_t launch_pack_weights(const float* params, const long long* row_off, const int* col_off, int n_packed,
                                 int taps, int ctot, int flip, __nv_bfloat16* wp, cudaStream_t s) {
-  pack_weights_kernel<<<148 * 8, 256, 0, s>>>(params, row_off, col_off, n_packed, taps, ctot, flip, wp);
+  if (ctot % 64 != 0 || taps > 25) return cudaErrorInvalidValue;
+  pack_weights_kernel<<<dim3(n_packed, ctot / 64), 256, 0, s>>>(params, row_off, col_off, n_packed, taps, ctot, flip, wp);
   return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(256)
+// wd[c][tap][n] = wp[n][taps - 1 - tap][c] (n padded to kpad with zeros): 32 x 32 shared-memory transposes per tap
+__global__ void __launch_bounds__(1024)
 transpose_flip_kernel(const __nv_bfloat16* __restrict__ wp, int n_packed, int taps, int ctot, int kpad,
                       __nv_bfloat16* __restrict__ wd) {
-  const long long total = static_cast<long long>(ctot) * taps * kpad;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int n = static_cast<int>(i % kpad);
-    const int tap = static_cast<int>((i / kpad) % taps);
-    const int c = static_cast<int>(i / (static_cast<long long>(kpad) * taps));
-    __nv_bfloat16 v = __float2bfloat16(0.f);
-    if (n < n_packed) v = wp[(static_cast<long long>(n) * taps + (taps - 1 - tap)) * ctot + c];
-    wd[i] = v;
-  }
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int tap = blockIdx.z;
+  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int n = n0 + threadIdx.y, c = c0 + threadIdx.x;
+  tile[threadIdx.y][threadIdx.x] =
+      (n < n_packed && c < ctot) ? wp[(static_cast<long long>(n) * taps + (taps - 1 - tap)) * ctot + c] : __float2bfloat16(0.f);
+  __syncthreads();
+  const int co = c0 + threadIdx.y, no = n0 + threadIdx.x;
+  if (co < ctot && no < kpad) wd[(static_cast<long long>(co) * taps + tap) * kpad + no] = tile[threadIdx.x][threadIdx.y];
 }
 cudaError_t launch_transpose_flip(const __nv_bfloat16* wp, int n_packed, int taps, int ctot, int kpad,
                                   __nv_bfloat16* wd, cudaStream_t s) {
-  transpose_flip_kernel<<<148 * 8, 256, 0, s>>>(wp, n_packed, taps, ctot, kpad, wd);
+  transpose_flip_kernel<<<dim3((kpad + 31) / 32, (ctot + 31) / 32, taps), dim3(32, 32), 0, s>>>(wp, n_packed, taps, ctot,
+                                                                                              kpad, wd);
   return cudaGetLastError();
 }
 
@@ -53,20 +62,25 @@ __global__ void __launch_bounds__(256)
 unpack_grads_kernel(const float* __restrict__ dwp, const long long* __restrict__ row_off,
                     const int* __restrict__ col_off, int n_packed, int taps, int ctot, int flip,
                     float* __restrict__ grads) {
-  const long long total = static_cast<long long>(n_packed) * taps * ctot;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % ctot);
-    const int tap = static_cast<int>((i / ctot) % taps);
-    const int n = static_cast<int>(i / (static_cast<long long>(ctot) * taps));
-    const long long ro = row_off[n];
-    const int co = col_off[c];
-    if (ro >= 0 && co >= 0) grads[ro + co + (flip ? taps - 1 - tap : tap)] = dwp[i];
+  __shared__ float tile[25][65];
+  const int n = blockIdx.x, c0 = blockIdx.y * 64;
+  const long long ro = row_off[n];
+  if (ro < 0) return;
+  for (int j = threadIdx.x; j < 64 * taps; j += blockDim.x) {
+    const int tap = j >> 6, cl = j & 63;
+    tile[tap][cl] = dwp[(static_cast<long long>(n) * taps + tap) * ctot + c0 + cl];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 64 * taps; j += blockDim.x) {
+    const int cl = j / taps, tap = j - cl * taps;
+    const int co = col_off[c0 + cl];
+    if (co >= 0) grads[ro + co + tap] = tile[flip ? taps - 1 - tap : tap][cl];
   }
 }
 cudaError_t launch_unpack_grads(const float* dwp, const long long* row_off, const int* col_off, int n_packed, int taps,
                                 int ctot, int flip, float* grads, cudaStream_t s) {
-  unpack_grads_kernel<<<148 * 8, 256, 0, s>>>(dwp, row_off, col_off, n_packed, taps, ctot, flip, grads);
+  if (ctot % 64 != 0 || taps > 25) return cudaErrorInvalidValue;
+  unpack_grads_kernel<<<dim3(n_packed, ctot / 64), 256, 0, s>>>(dwp, row_off, col_off, n_packed, taps, ctot, flip, grads);
   return cudaGetLastError();
 }
 
