@@ -409,3 +409,44 @@ def test_cem_get_action_vs_oracle_and_fused_plan(scene):
     np.testing.assert_array_equal(fused, stepwise)
     np.testing.assert_array_equal(fused_costs, pol3.last_costs.cpu().numpy())
     assert pol3.last_rollouts["obs"].shape == (5, L, 3, 48, 64)
+
+
+VARIANTS = {
+    "generic_only": {"RAC_HALO": "0", "RAC_2CTA": "0", "RAC_FIRST_TC": "0", "RAC_SPLIT_TAIL": "0", "RAC_C_TILED": "0"},
+    "cta_pair_everywhere": {"RAC_2CTA": "3"},
+    "halo_column_loads": {"RAC_HALO_COLUMNS": "1"},
+    "tile128": {"RAC_TILE_M": "128"},
+}
+
+
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_kernel_variants_agree_with_default(name, monkeypatch):
+    """Every alternative code path kept behind an environment switch (generic kernel instead of the halo / CTA-pair /
+    tensor-core-first-conv kernels, CTA pairs for the LSTM convolutions too, per-column halo loads, 128-row tiles)
+    computes the same two recurrent steps as the default configuration: same packed operands, fp32 accumulation,
+    only the summation order (and the first layer's input rounding) differs."""
+    cfg = so.make_cfg(g_dim=256, z_dim=Z_DIM, model_use_mask=True, model_use_robot_state=True)
+    sd = so.make_state_dict(cfg, 21)
+    B = 19
+    g = torch.Generator().manual_seed(6)
+    img = torch.rand(B, 3, 48, 64, generator=g)
+    mask = (torch.rand(B, 1, 48, 64, generator=g) > 0.8).float()
+    robot = torch.rand(B, 5, generator=g)
+    act = (torch.rand(2, B, 5, generator=g) - 0.5) * 0.1
+    eps = torch.randn(2, B, Z_DIM, 6, 8, generator=g)
+
+    def run():
+        m = _model(cfg, sd)
+        m.init_hidden(B)
+        outs = []
+        for t in range(2):
+            m.set_noise(eps=eps[t])
+            outs.append(m.forward(img, mask, robot, None, act[t])[0].cpu())
+        return outs
+
+    base = run()
+    for k, v in VARIANTS[name].items():
+        monkeypatch.setenv(k, v)
+    alt = run()
+    for a, b in zip(base, alt):
+        assert (a - b).abs().max().item() < 3e-3
