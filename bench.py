@@ -453,7 +453,9 @@ def main():
     # executed work is lower than the algorithmic count: filter rows that only see zero padding are skipped
     # (13 of 15 row-taps survive on the 6x8 map with the 5x5 filter) and at rollout step 0 the h_prev half of K is
     # all zero after init_hidden and skipped (1 of L steps)
-    executed_frac = (13.0 / 15.0) * ((L_STEPS - 1) + 0.5) / L_STEPS
+    # MMAs issued / algorithmic: per map row only the filter rows that do not fall into the zero padding (24 of 30 (row,
+    # tap-row) pairs of the 5x5 filter on the 6-row map), and the all-zero h_prev half of K is skipped at the first step
+    executed_frac = (24.0 / 30.0) * ((L_STEPS - 1) + 0.5) / L_STEPS
     roofline = {
         "bound": "tensor",
         "kernel": "conv_tc_kernel<256, 256, EPI_LSTM> on {prior,frame_predictor}.lstm.0.gates (5x5, 1024->2048)",

@@ -42,7 +42,25 @@ struct ConvGeom {
   int num_m_tiles, num_n_tiles, tiles_per_img;  // tiles_per_img = H / BH
   int w_shift, bhw_shift;                       // log2(W), log2(BH * W)
   int no_split_tail;                            // 1: disable the tail splitting of conv_tc_kernel (A/B measurements)
+  // 1: the rows of an M-tile are ordered (row of the map, candidate, column) instead of (candidate, row, column): the TMA
+  // box is {64, W, NB, BH} on a (C, W, B, H) view of the tensor. With NB * W == 128 each 128-row MMA sub-tile is then
+  // ONE row of the 6x8 latent map, and the MMAs of a sub-tile whose input row for a filter tap lies in the zero
+  // padding are not issued at all (the ConvLSTM gate convolutions run at the power cap: fewer MMAs = faster).
+  int y_major;
+  int nbw_shift;                                // log2(NB * W)
 };
+
+// row r of an M-tile -> (candidate, y, x)
+__device__ __forceinline__ void tile_row_to_pixel(const ConvGeom& g, int grp, int yb, int r, int& b, int& y, int& x) {
+  if (g.y_major) {
+    b = grp * g.NB + ((r >> g.w_shift) & (g.NB - 1));
+    y = yb * g.BH + (r >> g.nbw_shift);
+  } else {
+    b = grp * g.NB + (r >> g.bhw_shift);
+    y = yb * g.BH + ((r >> g.w_shift) & (g.BH - 1));
+  }
+  x = r & (g.W - 1);
+}
 
 struct EpiParams {
   const float* bias;  // [num_n_tiles * BLOCK_N], packed column order

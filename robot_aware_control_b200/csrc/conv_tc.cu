@@ -129,7 +129,8 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
               uint8_t* sa = smem + stage * Cfg::kStageBytes;
               uint8_t* sb = sa + Cfg::kABytes;
               mbar_arrive_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
-              tma_load_4d(&tm.a[s], &full_bar[stage], sa, kb * kBlockK, kw - g.pad, y0 + kh - g.pad, b0);
+              if (g.y_major) tma_load_4d(&tm.a[s], &full_bar[stage], sa, kb * kBlockK, kw - g.pad, b0, y0 + kh - g.pad);
+              else tma_load_4d(&tm.a[s], &full_bar[stage], sa, kb * kBlockK, kw - g.pad, y0 + kh - g.pad, b0);
               tma_load_2d(&tm.w, &full_bar[stage], sb, kidx * kBlockK, n_tile * BLOCK_N);
               if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
@@ -156,26 +157,44 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-        const uint64_t adesc = umma_desc_sw128(sa);
-        const uint64_t bdesc = umma_desc_sw128(sa + Cfg::kABytes);
-#pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-#pragma unroll
-          for (int sub = 0; sub < Cfg::kSub; ++sub) {
-            if (half >= 0 && sub != half) continue;  // split tail item: only this sub-tile
-            // +2 in the (addr >> 4) field = 32 B = 16 bf16 along K inside the 128B swizzle row;
-            // sub-tile s starts 128 rows * 128 B = 16 KB further (1024-B aligned, swizzle phase preserved)
-            umma_bf16_ss(d_tmem + sub * BLOCK_N, adesc + 2 * k + sub * (kTileM * 128 / 16), bdesc + 2 * k, idesc,
-                         (kb | k) != 0 ? 1u : 0u);
+      // y_major tiles: sub-tile s is the single map row y0 + s, so for filter row kh its MMAs are dead when that
+      // input row is zero padding (the operand rows TMA wrote are all zero)
+      const bool per_sub = g.y_major != 0 && Cfg::kSub == 2;
+      uint32_t started = 0;  // bit s: sub-tile s has received its first (non-accumulating) MMA
+      int kb = 0;
+      for (int kh = 0; kh < g.ks; ++kh) {
+        if (!tap_row_live(g, y0, kh)) continue;
+        uint32_t sub_live = 3;
+        if (per_sub) {
+          sub_live = 0;
+          for (int sb = 0; sb < 2; ++sb) {
+            const int yy = y0 + sb + kh - g.pad;
+            if (yy >= 0 && yy < g.H) sub_live |= 1u << sb;
           }
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
-        if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        for (int rest = g.ks * live_kb_per_tap; rest > 0; --rest, ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+#pragma unroll
+            for (int sub = 0; sub < Cfg::kSub; ++sub) {
+              if (half >= 0 && sub != half) continue;  // split tail item: only this sub-tile
+              if (!((sub_live >> sub) & 1u)) continue;
+              // +2 in the (addr >> 4) field = 32 B = 16 bf16 along K inside the 128B swizzle row;
+              // sub-tile s starts 128 rows * 128 B = 16 KB further (1024-B aligned, swizzle phase preserved)
+              umma_bf16_ss(d_tmem + sub * BLOCK_N, adesc + 2 * k + sub * (kTileM * 128 / 16), bdesc + 2 * k, idesc,
+                           (started >> sub) & 1u);
+              started |= 1u << sub;
+            }
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
+          if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
       }
       if (++acc == Cfg::kNumAcc) { acc = 0; acc_phase ^= 1; }
     }
@@ -198,9 +217,8 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
       const int m_tile = tile - n_tile * g.num_m_tiles;
       const int grp = m_tile / g.tiles_per_img;
       const int yb = m_tile - grp * g.tiles_per_img;
-      const int b = grp * g.NB + (r >> g.bhw_shift);
-      const int y = yb * g.BH + ((r >> g.w_shift) & (g.BH - 1));
-      const int x = r & (g.W - 1);
+      int b, y, x;
+      tile_row_to_pixel(g, grp, yb, r, b, y, x);
       const bool valid = b < g.B;
       constexpr bool kLstm = (EPI == EPI_LSTM || EPI == EPI_LSTM_TRAIN);
       constexpr bool kTrain = (EPI == EPI_LSTM_TRAIN);
@@ -233,9 +251,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
       };
       // row index inside the tile -> output pixel (the coalesced activation store addresses 8 neighbouring rows)
       auto row_of = [&](int rr, int& ob, int& oy, int& ox, bool& ov) {
-        ob = grp * g.NB + (rr >> g.bhw_shift);
-        oy = yb * g.BH + ((rr >> g.w_shift) & (g.BH - 1));
-        ox = rr & (g.W - 1);
+        tile_row_to_pixel(g, grp, yb, rr, ob, oy, ox);
         ov = ob < g.B;
       };
       // Coalesced (warp-transposed) activation stores pay off where the epilogue is the bottleneck because the K loop
@@ -312,9 +328,8 @@ conv_simt_kernel(const ConvRaw raw, const ConvGeom g, const EpiParams e) {
   const int grp = m_tile / g.tiles_per_img;
   const int yb = m_tile - grp * g.tiles_per_img;
   const int r = threadIdx.x;
-  const int b = grp * g.NB + (r >> g.bhw_shift);
-  const int y = yb * g.BH + ((r >> g.w_shift) & (g.BH - 1));
-  const int x = r & (g.W - 1);
+  int b, y, x;
+  tile_row_to_pixel(g, grp, yb, r, b, y, x);
   const bool valid = b < g.B;
   const int n0 = n_tile * BLOCK_N + c * CH;
   const int ktot = g.ks * g.ks * g.ctot;

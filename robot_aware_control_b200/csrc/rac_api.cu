@@ -97,6 +97,7 @@ struct rac_handle {
   int gn_fuse_stats = 1;     // RAC_GN_FUSE=0: lstm_group_norm statistics by the 3-pass cell kernel instead of the gate-conv epilogue
   bool gn_fused = false;
   int first_conv_tc = 1;     // RAC_FIRST_TC=0: encoder.c1.0 on the CUDA cores (fp32 inputs) instead of the tensor-core kernel
+  int y_major = 1;           // RAC_YMAJOR=0: candidate-major LSTM tiles (no per-sub-tile skipping of padding taps)
   int split_tail = 1;        // RAC_SPLIT_TAIL=0: no tail splitting in conv_tc_kernel (A/B measurements)
   int act_block_n = 256;     // RAC_ACT_BN=128: 256x128 tiles (double-buffered TMEM) for the BN+LeakyReLU layers (A/B measurements)
   int use_halo = 1;          // RAC_HALO=0: generic kernel for the 64-wide full-resolution layers too (A/B measurements)
@@ -255,6 +256,22 @@ int encode_halo_map(rac_handle* h, CUtensorMap* m, const bf16* ptr, int C, int B
   return RAC_OK;
 }
 
+// (C, W, B, H) view of an activation tensor: box {64, W, NB, BH} -> tile rows ordered (row of the map, candidate, column)
+int encode_act_map_ymajor(rac_handle* h, CUtensorMap* m, const bf16* ptr, int C, int B, int H, int W, int BH, int NB) {
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(B),
+                        static_cast<cuuint64_t>(H)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(H) * W * C * 2,
+                           static_cast<cuuint64_t>(W) * C * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(W), static_cast<cuuint32_t>(NB),
+                       static_cast<cuuint32_t>(BH)};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(ptr), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, RAC_ERR_CUDA, "cuTensorMapEncodeTiled(y-major activation C=%d) failed: %d", C, (int)r);
+  return RAC_OK;
+}
+
 struct Src {
   const bf16* p;
   int C;
@@ -290,12 +307,17 @@ int make_conv(rac_handle* h, ConvOp* op, const char* name, int layer, int H, int
   if (H % g.BH != 0) return fail(h, RAC_ERR_INVALID, "feature-map height %d not divisible by tile rows %d", H, g.BH);
   g.nsrc = static_cast<int>(srcs.size());
   g.ctot = 0;
+  // ConvLSTM gate convolutions on the 6x8 maps: one map row per 128-row MMA sub-tile (see ConvGeom::y_major)
+  g.nbw_shift = ilog2(g.NB * W);
+  g.y_major = (h->y_major && h->cfg.conv_impl == 0 && epi == EPI_LSTM && big && g.BH == 2 && g.NB * W == 128 &&
+               !(h->two_cta & 1)) ? 1 : 0;
   for (int i = 0; i < g.nsrc; ++i) {
     if (srcs[i].C % kBlockK != 0) return fail(h, RAC_ERR_INVALID, "%s: source channels %d not a multiple of 64", name, srcs[i].C);
     g.src_kb[i] = srcs[i].C / kBlockK;
     g.ctot += srcs[i].C;
     op->raw.src[i] = srcs[i].p;
-    CKR(encode_act_map(h, &op->tm.a[i], srcs[i].p, srcs[i].C, B, H, W, g.BH, g.NB));
+    if (g.y_major) CKR(encode_act_map_ymajor(h, &op->tm.a[i], srcs[i].p, srcs[i].C, B, H, W, g.BH, g.NB));
+    else CKR(encode_act_map(h, &op->tm.a[i], srcs[i].p, srcs[i].C, B, H, W, g.BH, g.NB));
   }
   if (g.ctot != s.ctot) return fail(h, RAC_ERR_INVALID, "%s: channel mismatch %d vs packed %d", name, g.ctot, s.ctot);
   g.tiles_per_img = H / g.BH;
@@ -796,6 +818,7 @@ int rac_create(const rac_config* cfg, rac_handle** out) {
   if (const char* v = getenv("RAC_HALO")) h->use_halo = atoi(v) != 0;
   if (const char* v = getenv("RAC_ACT_BN")) h->act_block_n = atoi(v);
   if (const char* v = getenv("RAC_SPLIT_TAIL")) h->split_tail = atoi(v) != 0;
+  if (const char* v = getenv("RAC_YMAJOR")) h->y_major = atoi(v) != 0;
   if (const char* v = getenv("RAC_2CTA")) h->two_cta = atoi(v);
   if (const char* v = getenv("RAC_FIRST_TC")) h->first_conv_tc = atoi(v) != 0;
   if (const char* v = getenv("RAC_GN_FUSE")) h->gn_fuse_stats = atoi(v) != 0;
