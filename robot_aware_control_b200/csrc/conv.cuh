@@ -121,6 +121,8 @@ struct ConvOp {
   EpiParams e;
   ConvTmaps tm;
   ConvRaw raw;
+  ConvTmaps tm_mc;       // multicast kernel (conv_tc_mc.cu): 128-row y-major activation boxes, 256-row weight box
+  int mc;                // 1: launch conv_tc_mc_kernel (2-CTA cluster sharing the activation tile by TMA multicast)
   ConvTmaps tm2;         // CTA-pair kernel (conv_tc2.cu): 128-row activation boxes, 128-row weight box
   int two_cta;           // 1: launch conv_tc2_kernel (cta_group::2) instead of conv_tc_kernel
   CUtensorMap tm_halo;   // halo kernel (conv_halo.cu): activation map with a column-major box
@@ -141,6 +143,10 @@ bool conv_halo_supported(const ConvOp& op);
 cudaError_t launch_conv_halo(const ConvOp& op, const CUtensorMap& tm_a, int column_loads, int use_base_offset,
                              int num_sms, cudaStream_t stream);
 cudaError_t conv_halo_set_attributes();
+// LSTM gate convolution with the activation tile multicast inside a 2-CTA cluster (conv_tc_mc.cu)
+bool conv_tc_mc_supported(const ConvOp& op);
+cudaError_t launch_conv_tc_mc(const ConvOp& op, const ConvTmaps& tm_mc, int num_sms, cudaStream_t stream);
+cudaError_t conv_tc_mc_set_attributes();
 // CTA-pair (cta_group::2) kernel for the 256 x 256 tiles (conv_tc2.cu)
 bool conv_tc2_supported(const ConvOp& op);
 cudaError_t launch_conv_tc2(const ConvOp& op, const ConvTmaps& tm2, int num_sms, cudaStream_t stream);

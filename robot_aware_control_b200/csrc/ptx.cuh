@@ -195,6 +195,25 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_m256(int n) {
          (static_cast<uint32_t>(256 >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- cluster multicast (cta_group::1 MMAs)
+// TMA load whose box lands at the same shared-memory offset in every CTA of `mask` and completes transaction bytes on
+// the barrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                               int c3, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5, %6, %7}], [%2], %3;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// arrive on the barrier at this offset in every CTA of `mask` once the MMAs issued so far by this thread completed
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 // UMMA shared-memory matrix descriptor for a K-major bf16 tile stored as rows of 128 B (64 channels) with the
 // 128-byte swizzle TMA writes: 8-row groups are 1024 B apart (SBO), LBO is unused for swizzled K-major layouts.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {

@@ -97,6 +97,7 @@ struct rac_handle {
   int gn_fuse_stats = 1;     // RAC_GN_FUSE=0: lstm_group_norm statistics by the 3-pass cell kernel instead of the gate-conv epilogue
   bool gn_fused = false;
   int first_conv_tc = 1;     // RAC_FIRST_TC=0: encoder.c1.0 on the CUDA cores (fp32 inputs) instead of the tensor-core kernel
+  int lstm_mc = 1;           // RAC_LSTM_MC=0: LSTM gate convs without the 2-CTA cluster that shares the activation tile by TMA multicast
   int y_major = 1;           // RAC_YMAJOR=0: candidate-major LSTM tiles (no per-sub-tile skipping of padding taps)
   int split_tail = 1;        // RAC_SPLIT_TAIL=0: no tail splitting in conv_tc_kernel (A/B measurements)
   int act_block_n = 256;     // RAC_ACT_BN=128: 256x128 tiles (double-buffered TMEM) for the BN+LeakyReLU layers (A/B measurements)
@@ -339,6 +340,12 @@ int make_conv(rac_handle* h, ConvOp* op, const char* name, int layer, int H, int
     CKR(encode_w_map(h, &op->tm2.w, wp, s.ks * s.ks * s.ctot, s.n_packed, 128));
     op->two_cta = 1;
   }
+  if (h->lstm_mc && h->cfg.conv_impl == 0 && conv_tc_mc_supported(*op)) {
+    for (int i = 0; i < g.nsrc; ++i)
+      CKR(encode_act_map_ymajor(h, &op->tm_mc.a[i], srcs[i].p, srcs[i].C, B, H, W, 1, g.NB));
+    op->tm_mc.w = op->tm.w;
+    op->mc = 1;
+  }
   if (h->use_halo && h->cfg.conv_impl == 0 && h->tile_m == 256 && conv_halo_supported(*op)) {
     CKR(encode_halo_map(h, &op->tm_halo, srcs[0].p, srcs[0].C, B, H, W, &op->halo_column_loads));
     op->halo = 1;
@@ -385,6 +392,7 @@ int launch(rac_handle* h, const ConvOp& op, cudaStream_t st) {
     }
   }
   cudaError_t e = h->cfg.conv_impl == 1 ? launch_conv_simt(op, st)
+                  : op.mc ? launch_conv_tc_mc(op, op.tm_mc, h->num_sms, st)
                   : op.two_cta ? launch_conv_tc2(op, op.tm2, h->num_sms, st)
                   : op.halo ? launch_conv_halo(op, op.tm_halo, op.halo_column_loads, h->halo_base_offset, h->num_sms, st)
                             : launch_conv_tc(op, h->num_sms, st);
@@ -819,6 +827,8 @@ int rac_create(const rac_config* cfg, rac_handle** out) {
   if (const char* v = getenv("RAC_ACT_BN")) h->act_block_n = atoi(v);
   if (const char* v = getenv("RAC_SPLIT_TAIL")) h->split_tail = atoi(v) != 0;
   if (const char* v = getenv("RAC_YMAJOR")) h->y_major = atoi(v) != 0;
+  if (const char* v = getenv("RAC_LSTM_MC")) h->lstm_mc = atoi(v) != 0;
+  CK(conv_tc_mc_set_attributes());
   if (const char* v = getenv("RAC_2CTA")) h->two_cta = atoi(v);
   if (const char* v = getenv("RAC_FIRST_TC")) h->first_conv_tc = atoi(v) != 0;
   if (const char* v = getenv("RAC_GN_FUSE")) h->gn_fuse_stats = atoi(v) != 0;

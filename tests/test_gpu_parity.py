@@ -412,7 +412,9 @@ def test_cem_get_action_vs_oracle_and_fused_plan(scene):
 
 
 VARIANTS = {
-    "generic_only": {"RAC_HALO": "0", "RAC_2CTA": "0", "RAC_FIRST_TC": "0", "RAC_SPLIT_TAIL": "0", "RAC_C_TILED": "0"},
+    "generic_only": {"RAC_HALO": "0", "RAC_2CTA": "0", "RAC_FIRST_TC": "0", "RAC_SPLIT_TAIL": "0", "RAC_C_TILED": "0",
+                     "RAC_YMAJOR": "0", "RAC_LSTM_MC": "0"},
+    "no_multicast": {"RAC_LSTM_MC": "0"},
     "cta_pair_everywhere": {"RAC_2CTA": "3"},
     "halo_column_loads": {"RAC_HALO_COLUMNS": "1"},
     "tile128": {"RAC_TILE_M": "128"},
