@@ -61,7 +61,23 @@ conv_tc_mc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const 
     kb_per_tap += g.src_kb[s];
     if (!g.src_dead[s]) live_kb_per_tap += g.src_kb[s];
   }
-  auto row_live = [&](int y0, int kh) {  // any of the two map rows of the tile reads a real input row for filter row kh
+  // Tail splitting (as in conv_tc.cu): the pair tiles left over after the full rounds become two work items each, one
+  // per map row (= MMA sub-tile = activation half), when they then still fit into one round.
+  const int full_items = (num_tiles / num_pairs) * num_pairs;
+  const int rem = num_tiles - full_items;
+  const bool split_tail = !g.no_split_tail && rem > 0 && 2 * rem <= num_pairs;
+  const int num_items = split_tail ? full_items + 2 * rem : num_tiles;
+  auto item_tile = [&](int item, int& half) {  // half: -1 = both map rows
+    if (item < full_items || !split_tail) { half = -1; return item; }
+    half = (item - full_items) & 1;
+    return full_items + ((item - full_items) >> 1);
+  };
+  // filter row kh contributes to this work item: some (half < 0) / the (half >= 0) map row reads a real input row
+  auto row_live = [&](int y0, int kh, int half) {
+    if (half >= 0) {
+      const int yy = y0 + half + kh - g.pad;
+      return yy >= 0 && yy < g.H;
+    }
     const int ylo = y0 + kh - g.pad;
     return ylo + 2 > 0 && ylo < g.H;
   };
@@ -93,15 +109,20 @@ conv_tc_mc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const 
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+    for (int item = pair; item < num_items; item += num_pairs) {
+      int half;
+      const int tile = item_tile(item, half);
       const int np = tile / g.num_m_tiles;
       const int m_tile = tile - np * g.num_m_tiles;
       const int n_tile = 2 * np + rank;
       const int grp = m_tile / g.tiles_per_img;
       const int b0 = grp * g.NB;
       const int y0 = (m_tile - grp * g.tiles_per_img) * 2;
+      // a half item needs only activation half `half`: the CTA of that rank loads (and multicasts) it
+      const bool load_a = half < 0 || half == rank;
+      const uint32_t tx = (half < 0 ? Cfg::kABytes : Cfg::kABytes / 2) + Cfg::kBBytes;
       for (int kh = 0; kh < g.ks; ++kh) {
-        if (!row_live(y0, kh)) continue;
+        if (!row_live(y0, kh, half)) continue;
         for (int kw = 0; kw < g.ks; ++kw) {
           int kidx = (kh * g.ks + kw) * kb_per_tap;
           for (int s = 0; s < g.nsrc; ++s) {
@@ -110,10 +131,11 @@ conv_tc_mc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const 
               mbar_wait(&empty_bar[stage], phase ^ 1);  // both CTAs have consumed the previous contents
               uint8_t* sa = smem + stage * Cfg::kStageBytes;
               uint8_t* sb = sa + Cfg::kABytes;
-              mbar_arrive_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
+              mbar_arrive_expect_tx(&full_bar[stage], tx);
               // my half of the activation tile (map row y0 + rank) -> both CTAs
-              tma_load_4d_mc(&tm.a[s], &full_bar[stage], sa + rank * (Cfg::kABytes / 2), kb * kBlockK, kw - g.pad, b0,
-                             y0 + rank + kh - g.pad, 3);
+              if (load_a)
+                tma_load_4d_mc(&tm.a[s], &full_bar[stage], sa + rank * (Cfg::kABytes / 2), kb * kBlockK, kw - g.pad, b0,
+                               y0 + rank + kh - g.pad, 3);
               tma_load_2d(&tm.w, &full_bar[stage], sb, kidx * kBlockK, n_tile * BLOCK_N);
               if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
@@ -127,23 +149,25 @@ conv_tc_mc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const 
     int stage = 0;
     uint32_t phase = 0;
     uint32_t acc_phase = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+    for (int item = pair; item < num_items; item += num_pairs) {
+      int half;
+      const int tile = item_tile(item, half);
       const int np = tile / g.num_m_tiles;
       const int m_tile = tile - np * g.num_m_tiles;
       const int y0 = (m_tile % g.tiles_per_img) * 2;
       int live = 0;
-      for (int kh = 0; kh < g.ks; ++kh) live += row_live(y0, kh) ? 1 : 0;
+      for (int kh = 0; kh < g.ks; ++kh) live += row_live(y0, kh, half) ? 1 : 0;
       const int num_kb = live * g.ks * live_kb_per_tap;
       mbar_wait(tmem_empty, acc_phase ^ 1);
       tc_fence_after();
       uint32_t started = 0;
       int kb = 0;
       for (int kh = 0; kh < g.ks; ++kh) {
-        if (!row_live(y0, kh)) continue;
+        if (!row_live(y0, kh, half)) continue;
         uint32_t sub_live = 0;
         for (int sb = 0; sb < 2; ++sb) {
           const int yy = y0 + sb + kh - g.pad;
-          if (yy >= 0 && yy < g.H) sub_live |= 1u << sb;
+          if (yy >= 0 && yy < g.H && (half < 0 || half == sb)) sub_live |= 1u << sb;
         }
         for (int rest = g.ks * live_kb_per_tap; rest > 0; --rest, ++kb) {
           mbar_wait(&full_bar[stage], phase);
@@ -179,7 +203,10 @@ conv_tc_mc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const 
     constexpr int kChunks = BLOCK_N / CH;
     float* s_bias = reinterpret_cast<float*>(bar_base + 1024);
     int bias_tile = -1;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+    for (int item = pair; item < num_items; item += num_pairs) {
+      int half;
+      const int tile = item_tile(item, half);
+      const bool mine = half < 0 || half == sub;  // half item: the other map row belongs to another cluster
       const int np = tile / g.num_m_tiles;
       const int m_tile = tile - np * g.num_m_tiles;
       const int n_tile = 2 * np + rank;
@@ -207,20 +234,22 @@ conv_tc_mc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const 
       auto process = [&](int c, const float* acc_v, const float* cp) {
         epi_lstm<false>(g, e, b, y, x, valid, n_tile * BLOCK_N + c * CH, acc_v, cp, ctile, Cfg::kBlockM, s_bias + c * CH);
       };
-      issue(0, v[0]);
-      load_c(0, cprev[0]);
+      if (mine) {
+        issue(0, v[0]);
+        load_c(0, cprev[0]);
 #pragma unroll 1
-      for (int c = 0; c < kChunks; c += 2) {
-        tmem_ld_wait();
-        issue(c + 1, v[1]);
-        load_c(c + 1, cprev[1]);
-        process(c, v[0], cprev[0]);
-        tmem_ld_wait();
-        if (c + 2 < kChunks) {
-          issue(c + 2, v[0]);
-          load_c(c + 2, cprev[0]);
+        for (int c = 0; c < kChunks; c += 2) {
+          tmem_ld_wait();
+          issue(c + 1, v[1]);
+          load_c(c + 1, cprev[1]);
+          process(c, v[0], cprev[0]);
+          tmem_ld_wait();
+          if (c + 2 < kChunks) {
+            issue(c + 2, v[0]);
+            load_c(c + 2, cprev[0]);
+          }
+          process(c + 1, v[1], cprev[1]);
         }
-        process(c + 1, v[1], cprev[1]);
       }
       tc_fence_before();
       mbar_arrive(tmem_empty);
