@@ -160,7 +160,7 @@ int rac_rollout_cost(rac_handle* h, const rac_rollout* r, void* stream);
 /* Cross-GPU barrier after the fused cost exchange: every rank stores `seq` into slot [rank] of every peer's signal pad
  * (system-scope release), then waits until all peer_world slots of its own pad hold `seq` (acquire). signal_pads =
  * DEVICE array of peer_world pointers to the ranks' uint32 pads; words [slot_base, slot_base + peer_world) of each pad
- * are used (zero-initialised; seq must increase by one per call). A rank that never arrives makes the kernel trap after ~2 s instead of hanging. */
+ * are used (zero-initialised; seq must increase by one per call). A rank that never arrives makes the kernel trap after ~60 s instead of hanging for ever. */
 int rac_peer_barrier(uint32_t* const* signal_pads, int slot_base, int rank, int peer_world, uint32_t seq, void* stream);
 
 /* CEMPolicy.get_action pieces (cem.py:76-104). */
