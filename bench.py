@@ -458,11 +458,12 @@ def main():
     executed_frac = (24.0 / 30.0) * ((L_STEPS - 1) + 0.5) / L_STEPS
     roofline = {
         "bound": "tensor",
-        "kernel": "conv_tc_kernel<256, 256, EPI_LSTM> on {prior,frame_predictor}.lstm.0.gates (5x5, 1024->2048)",
+        "kernel": "conv_tc_mc_kernel (256x256 tcgen05 tiles, 2-CTA clusters with TMA multicast of the activation tile) on "
+                  "{prior,frame_predictor}.lstm.0.gates (5x5, 1024->2048)",
         "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2000 candidates, ncu --set full capture
-        # profiles/r01_lstm_gates_ncu_s2.txt (2.189 GB + 0.291 GB); not re-measured by this run
-        "traffic": 2.48e9 if n_local == 2000 else None,
+        # profiles/r01_lstm_gates_mc_ncu_s5.txt (1.576 GB + 0.293 GB); not re-measured by this run
+        "traffic": 1.87e9 if n_local == 2000 else None,
         "peak_source": peak_src, "launches_timed": int(pl.value), "avg_launch_ms": avg_ms,
         "algorithmic_flops_per_launch": flops_per_launch,
         "executed_flops_per_launch": flops_per_launch * executed_frac,
