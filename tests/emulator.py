@@ -17,6 +17,7 @@ class PackedEmulator:
         self.cfg = cfg
         self.rb = round_bf16
         self.layers = pack.pack_state_dict(state_dict, cfg)
+        self.norm = pack.pack_lstm_norm(state_dict, cfg) if getattr(cfg, "lstm_group_norm", False) else None
         self.state = None
 
     def _gemm(self, name, srcs, ks=3):
@@ -47,7 +48,42 @@ class PackedEmulator:
         z = lambda: torch.zeros(B, 6, 8, g)
         self.state = {k: [[z(), z()], [z(), z()]] for k in ("PRIOR", "POST", "FP")}
 
+    @staticmethod
+    def _gn_gates(raw, gamma, beta, g):
+        """csrc/norm_lstm.cu + EPI_GATES: raw [B,6,8,4g] in packed (channel, gate) column order; GroupNorm(16, 4g) groups
+        of the reference = (gate, quarter of the channels); gamma / beta in packed column order."""
+        B = raw.shape[0]
+        r = raw.reshape(B, 48, g, 4)                       # (pos, ch, gate)
+        q = g // 4
+        r5 = r.reshape(B, 48, 4, q, 4)                      # (pos, quarter, ch in quarter, gate)
+        mean = r5.mean(dim=(1, 3), keepdim=True)
+        var = r5.var(dim=(1, 3), unbiased=False, keepdim=True)
+        n = ((r5 - mean) / torch.sqrt(var + 1e-5)).reshape(B, 48, g, 4)
+        return (n * gamma.reshape(1, 1, g, 4) + beta.reshape(1, 1, g, 4)).reshape(B, 6, 8, g, 4)
+
+    def _lstm_gn(self, tag, x):
+        """NormConvLSTMCell data flow (lstm.py:177-198) on the packed ih / hh operands and norm vector."""
+        g = self.cfg.g_dim
+        for layer, ks in ((0, 5), (1, 3)):
+            h_prev, c_prev = self.state[tag][layer]
+            v = self.norm[f"{tag}_LSTM{layer}"]
+            ih = self._gemm(f"{tag}_LSTM{layer}", [x], ks)[..., :4 * g]
+            hh = self._gemm(f"{tag}_LSTM{layer}_HH", [h_prev], ks)[..., :4 * g]
+            acc = (self._gn_gates(ih, v[0:4 * g], v[4 * g:8 * g], g) +
+                   self._gn_gates(hh, v[8 * g:12 * g], v[12 * g:16 * g], g))
+            i, f, o, gg = (acc[..., k] for k in range(4))
+            c = torch.sigmoid(f) * c_prev + torch.sigmoid(i) * torch.tanh(gg)
+            c16 = c.reshape(c.shape[0], 48, 16, g // 16)
+            c16 = (c16 - c16.mean(dim=(1, 3), keepdim=True)) / torch.sqrt(c16.var(dim=(1, 3), unbiased=False, keepdim=True) + 1e-5)
+            c = c16.reshape(c.shape) * v[16 * g:17 * g] + v[17 * g:18 * g]
+            h = _q(torch.sigmoid(o) * torch.tanh(c), self.rb)
+            self.state[tag][layer] = [h, c]
+            x = h
+        return x
+
     def _lstm(self, tag, x):
+        if self.norm is not None:
+            return self._lstm_gn(tag, x)
         g = self.cfg.g_dim
         for layer, ks in ((0, 5), (1, 3)):
             h_prev, c_prev = self.state[tag][layer]

@@ -26,6 +26,7 @@ def _inputs(cfg, B, seed=3):
 
 CONFIGS = {
     "vanilla": dict(),
+    "group_norm": dict(lstm_group_norm=True, model_use_mask=True, model_use_robot_state=True),
     "ra": dict(model_use_mask=True, model_use_robot_state=True),
     "ra_future": dict(model_use_mask=True, model_use_future_mask=True, model_use_robot_state=True,
                       model_use_future_robot_state=True),
@@ -103,7 +104,7 @@ def test_model_spec_matches_oracle_spec():
     from robot_aware_control_b200.model import _spec
     from robot_aware_control_b200.config import svg_config_from
 
-    for kw in list(CONFIGS.values()) + [dict(lstm_group_norm=True)]:
+    for kw in list(CONFIGS.values()):
         cfg = so.make_cfg(g_dim=128, z_dim=10, **kw)
         mine = {k: tuple(v[0]) for k, v in _spec(svg_config_from(cfg)).items()}
         ref = {k: tuple(v) for k, v in so.state_dict_spec(cfg).items()}
