@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RAC_ABI_VERSION 3
+#define RAC_ABI_VERSION 4
 
 typedef enum {
   RAC_OK = 0,
@@ -249,6 +249,9 @@ typedef struct {
   int recon_kind;            /* 0 = l1, 1 = dontcare_l1 (cfg.reconstruction_loss) */
   int zero_robot;            /* "dontcare" in reconstruction_loss or black_robot_input */
   long long n_params, n_buffers;
+  int fixed_skip;            /* 1 = cfg.last_frame_skip False (the config default, src/config/__init__.py:217-222): every
+                                step decodes with the skips of the clip's FIRST frame (trainer.py:370-371,409-411;
+                                dynamics.py:586-588,644); 0 = skips of the step's own input frame */
 } rac_train_config;
 
 typedef struct {

@@ -46,10 +46,17 @@ def main():
     trainer_mod = importlib.import_module("src.prediction.trainer")
     feeder = EpsFeeder()
     lstm_mod.GaussianConvLSTM.reparameterize = lambda self, mu, logvar: feeder(self, mu, logvar)
+    only = sys.argv[1:]  # optional: tags to (re)generate; default all
     for tag, kw in (("vanilla", dict(robot_aware=False)), ("ra", dict(robot_aware=True, future_mask=True)),
-                    ("ra_sampled", dict(robot_aware=True, future_mask=True))):
-        cfg = ref_shim.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, extra=("--n_future", str(T - 1), "--batch_size", str(B),
-                                                                "--lr", "1e-3", "--beta", "1e-2"), **kw)
+                    ("ra_sampled", dict(robot_aware=True, future_mask=True)),
+                    ("ra_fixedskip", dict(robot_aware=True, future_mask=True)),
+                    ("vanilla_fixedskip_sampled", dict(robot_aware=False))):
+        if only and tag not in only:
+            continue
+        extra = ("--n_future", str(T - 1), "--batch_size", str(B), "--lr", "1e-3", "--beta", "1e-2")
+        if "fixedskip" in tag:  # the config default (src/config/__init__.py:217-222): decoder skips of the first frame
+            extra += ("--last_frame_skip", "False")
+        cfg = ref_shim.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, extra=extra, **kw)
         cfg.multiview = False
         sd = so.make_state_dict(cfg, 17)
         tr = trainer_mod.PredictionTrainer.__new__(trainer_mod.PredictionTrainer)

@@ -10,6 +10,13 @@
 // Scheduled sampling (trainer.py:132-147,353-356): per step the caller says whether the input frame is the ground
 // truth or the model's previous composited prediction; in the latter case the gradient flows back through the
 // composite and the encoder input into the previous step, as in the reference (x_pred.clone(), not detached).
+//
+// Decoder skips: with cfg.last_frame_skip True every step decodes with the skips of its own input frame; with False
+// (the config default, src/config/__init__.py:217-222) the reference keeps the skips of the FIRST frame for the whole
+// clip (trainer.py:370-371,409-411 with dynamics.py:586-588,644: the model returns the skip it used, so `skip` never
+// changes after i == 1, whatever n_past is). `fixed_skip` is that mode: steps t > 0 decode from their own concat
+// buffers (dcat*) whose skip halves are copies of step 0's, and the skip-half gradients of all steps are summed in
+// G_skip* and enter the encoder backward of step 0 only.
 // Not implemented: heatmaps, multiview, batch_weight.
 
 #include <algorithm>
@@ -46,6 +53,7 @@ struct Tape {  // everything the backward pass of one time step needs
   float* cs[3][2];
   float* gates[3][2];
   bf16 *d2a, *d2b, *d3a, *d3b, *d4a, *d5;
+  bf16 *dcat5, *dcat4, *dcat3;  // decoder concat buffers: == cat* unless fixed_skip and t > 0
   VggRt vgg[19];
   float *mu_p, *lv_p, *mu, *lv, *x4;
   float *eps_p, *eps_q;
@@ -65,6 +73,7 @@ struct TrainState {
   // gradient accumulators (fp32 NHWC)
   float *G_d5, *G_cat5, *G_d4a, *G_cat4, *G_d3b, *G_d3a, *G_cat3, *G_d2b, *G_d2a, *G_fin, *G_pin, *G_postin, *G_z, *G_h4;
   float *G_a4b, *G_a4a, *G_p3, *G_a3b, *G_a3a, *G_p2, *G_a2, *G_p1, *G_a1;
+  float *G_skip5, *G_skip4, *G_skip3;  // fixed_skip: skip-half gradients summed over the steps ([M, C] fp32)
   float* G_hs[3][2][2];
   float* G_dc[3][2];
   float* G_img[2];       // gradient w.r.t. a sampled input frame, ping-pong across steps
@@ -344,13 +353,23 @@ int train_forward_step(rac_handle* h, TrainState* T, const rac_train_batch* bt, 
   CKR(lstm_forward(h, T, 2, t, tp.fin, st));
   CKR(vgg_forward(h, T, tp.vgg[10], dec_def(h, 0), tp.hs[2][1], tp.d2a, 512, 0, 0, 1, st));
   CKR(vgg_forward(h, T, tp.vgg[11], dec_def(h, 1), tp.d2a, tp.d2b, 512, 0, 0, 1, st));
-  CKR(vgg_forward(h, T, tp.vgg[12], dec_def(h, 2), tp.d2b, tp.cat3, 512, 0, 1, 1, st));
-  CKR(vgg_forward(h, T, tp.vgg[13], dec_def(h, 3), tp.cat3, tp.d3a, 256, 0, 0, 1, st));
+  if (tp.dcat5 != tp.cat5) {
+    // fixed_skip, t > 0: the skip halves are those of the first frame
+    const Tape& t0 = T->tape[0];
+    CK(cudaMemcpy2DAsync(tp.dcat3 + 256, 512 * sizeof(bf16), t0.cat3 + 256, 512 * sizeof(bf16), 256 * sizeof(bf16),
+                         static_cast<size_t>(B) * 192, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpy2DAsync(tp.dcat4 + 128, 256 * sizeof(bf16), t0.cat4 + 128, 256 * sizeof(bf16), 128 * sizeof(bf16),
+                         static_cast<size_t>(B) * 768, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpy2DAsync(tp.dcat5 + 64, 128 * sizeof(bf16), t0.cat5 + 64, 128 * sizeof(bf16), 64 * sizeof(bf16),
+                         static_cast<size_t>(B) * 3072, cudaMemcpyDeviceToDevice, st));
+  }
+  CKR(vgg_forward(h, T, tp.vgg[12], dec_def(h, 2), tp.d2b, tp.dcat3, 512, 0, 1, 1, st));
+  CKR(vgg_forward(h, T, tp.vgg[13], dec_def(h, 3), tp.dcat3, tp.d3a, 256, 0, 0, 1, st));
   CKR(vgg_forward(h, T, tp.vgg[14], dec_def(h, 4), tp.d3a, tp.d3b, 256, 0, 0, 1, st));
-  CKR(vgg_forward(h, T, tp.vgg[15], dec_def(h, 5), tp.d3b, tp.cat4, 256, 0, 1, 1, st));
-  CKR(vgg_forward(h, T, tp.vgg[16], dec_def(h, 6), tp.cat4, tp.d4a, 128, 0, 0, 1, st));
-  CKR(vgg_forward(h, T, tp.vgg[17], dec_def(h, 7), tp.d4a, tp.cat5, 128, 0, 1, 1, st));
-  CKR(vgg_forward(h, T, tp.vgg[18], dec_def(h, 8), tp.cat5, tp.d5, 64, 0, 0, 1, st));
+  CKR(vgg_forward(h, T, tp.vgg[15], dec_def(h, 5), tp.d3b, tp.dcat4, 256, 0, 1, 1, st));
+  CKR(vgg_forward(h, T, tp.vgg[16], dec_def(h, 6), tp.dcat4, tp.d4a, 128, 0, 0, 1, st));
+  CKR(vgg_forward(h, T, tp.vgg[17], dec_def(h, 7), tp.d4a, tp.dcat5, 128, 0, 1, 1, st));
+  CKR(vgg_forward(h, T, tp.vgg[18], dec_def(h, 8), tp.dcat5, tp.d5, 64, 0, 0, 1, st));
   {
     const TLayer& L = T->L[RAC_L_DEC_UPC5_1];
     EpiParams e{};
@@ -387,18 +406,28 @@ int train_backward_step(rac_handle* h, TrainState* T, const rac_train_batch* bt,
   // ---- decoder
   seg[0] = {0, 64, T->G_d5, 64, 0, 0};
   CKR(conv_backward(h, T, RAC_L_DEC_UPC5_1, 48, 64, {{tp.d5, 64}}, T->dy_b, seg, 1, st));
-  seg[0] = {0, 128, T->G_cat5, 128, 0, 0};
-  CKR(vgg_backward(h, T, tp.vgg[18], dec_def(h, 8), tp.cat5, T->G_d5, 64, 0, 0, seg, 1, st));
+  // gradient of a concat buffer: [decoder half | skip half]. fixed_skip: the skip half is summed over the steps
+  // (first writer = the first processed step, t == S - 1) instead of going to this step's encoder
+  const bool fixed = T->cfg.fixed_skip != 0;
+  const int skip_acc = (t == S - 1) ? 0 : 1;
+  auto cat_segs = [&](float* G_cat, float* G_skip, int half) -> int {
+    if (!fixed) { seg[0] = {0, 2 * half, G_cat, 2 * half, 0, 0}; return 1; }
+    seg[0] = {0, half, G_cat, 2 * half, 0, 0};
+    seg[1] = {half, 2 * half, G_skip, half, 0, skip_acc};
+    return 2;
+  };
+  int ncat = cat_segs(T->G_cat5, T->G_skip5, 64);
+  CKR(vgg_backward(h, T, tp.vgg[18], dec_def(h, 8), tp.dcat5, T->G_d5, 64, 0, 0, seg, ncat, st));
   seg[0] = {0, 128, T->G_d4a, 128, 0, 0};
   CKR(vgg_backward(h, T, tp.vgg[17], dec_def(h, 7), tp.d4a, T->G_cat5, 128, 0, 1, seg, 1, st));
-  seg[0] = {0, 256, T->G_cat4, 256, 0, 0};
-  CKR(vgg_backward(h, T, tp.vgg[16], dec_def(h, 6), tp.cat4, T->G_d4a, 128, 0, 0, seg, 1, st));
+  ncat = cat_segs(T->G_cat4, T->G_skip4, 128);
+  CKR(vgg_backward(h, T, tp.vgg[16], dec_def(h, 6), tp.dcat4, T->G_d4a, 128, 0, 0, seg, ncat, st));
   seg[0] = {0, 256, T->G_d3b, 256, 0, 0};
   CKR(vgg_backward(h, T, tp.vgg[15], dec_def(h, 5), tp.d3b, T->G_cat4, 256, 0, 1, seg, 1, st));
   seg[0] = {0, 256, T->G_d3a, 256, 0, 0};
   CKR(vgg_backward(h, T, tp.vgg[14], dec_def(h, 4), tp.d3a, T->G_d3b, 256, 0, 0, seg, 1, st));
-  seg[0] = {0, 512, T->G_cat3, 512, 0, 0};
-  CKR(vgg_backward(h, T, tp.vgg[13], dec_def(h, 3), tp.cat3, T->G_d3a, 256, 0, 0, seg, 1, st));
+  ncat = cat_segs(T->G_cat3, T->G_skip3, 256);
+  CKR(vgg_backward(h, T, tp.vgg[13], dec_def(h, 3), tp.dcat3, T->G_d3a, 256, 0, 0, seg, ncat, st));
   seg[0] = {0, 512, T->G_d2b, 512, 0, 0};
   CKR(vgg_backward(h, T, tp.vgg[12], dec_def(h, 2), tp.d2b, T->G_cat3, 512, 0, 1, seg, 1, st));
   seg[0] = {0, 512, T->G_d2a, 512, 0, 0};
@@ -446,21 +475,32 @@ int train_backward_step(rac_handle* h, TrainState* T, const rac_train_batch* bt,
   CKR(vgg_backward(h, T, tp.vgg[8], enc_def(h, 8), tp.a4a, T->G_a4b, 512, 0, 0, seg, 1, st));
   seg[0] = {0, 256, T->G_p3, 256, 0, 0};
   CKR(vgg_backward(h, T, tp.vgg[7], enc_def(h, 7), tp.p3, T->G_a4a, 512, 0, 0, seg, 1, st));
-  CK(launch_pool_bwd(tp.cat3, 512, 256, T->G_p3, B, 12, 16, 256, T->G_cat3, 512, 256, 1, st));
+  // gradient of the encoder outputs that double as skips: pooling path + decoder skip path. fixed_skip: steps t > 0
+  // get the pooling path only; step 0 adds it to the all-steps skip sum
+  struct SkipGrad { float* p; int cstride, coff, acc; };
+  auto skip_grad = [&](float* G_cat, float* G_skip, int half) -> SkipGrad {
+    if (!fixed) return {G_cat, 2 * half, half, 1};
+    if (t > 0) return {G_cat, 2 * half, half, 0};
+    return {G_skip, half, 0, 1};
+  };
+  SkipGrad sk = skip_grad(T->G_cat3, T->G_skip3, 256);
+  CK(launch_pool_bwd(tp.cat3, 512, 256, T->G_p3, B, 12, 16, 256, sk.p, sk.cstride, sk.coff, sk.acc, st));
   seg[0] = {0, 256, T->G_a3b, 256, 0, 0};
-  CKR(vgg_backward(h, T, tp.vgg[6], enc_def(h, 6), tp.a3b, T->G_cat3, 512, 256, 0, seg, 1, st));
+  CKR(vgg_backward(h, T, tp.vgg[6], enc_def(h, 6), tp.a3b, sk.p, sk.cstride, sk.coff, 0, seg, 1, st));
   seg[0] = {0, 256, T->G_a3a, 256, 0, 0};
   CKR(vgg_backward(h, T, tp.vgg[5], enc_def(h, 5), tp.a3a, T->G_a3b, 256, 0, 0, seg, 1, st));
   seg[0] = {0, 128, T->G_p2, 128, 0, 0};
   CKR(vgg_backward(h, T, tp.vgg[4], enc_def(h, 4), tp.p2, T->G_a3a, 256, 0, 0, seg, 1, st));
-  CK(launch_pool_bwd(tp.cat4, 256, 128, T->G_p2, B, 24, 32, 128, T->G_cat4, 256, 128, 1, st));
+  sk = skip_grad(T->G_cat4, T->G_skip4, 128);
+  CK(launch_pool_bwd(tp.cat4, 256, 128, T->G_p2, B, 24, 32, 128, sk.p, sk.cstride, sk.coff, sk.acc, st));
   seg[0] = {0, 128, T->G_a2, 128, 0, 0};
-  CKR(vgg_backward(h, T, tp.vgg[3], enc_def(h, 3), tp.a2, T->G_cat4, 256, 128, 0, seg, 1, st));
+  CKR(vgg_backward(h, T, tp.vgg[3], enc_def(h, 3), tp.a2, sk.p, sk.cstride, sk.coff, 0, seg, 1, st));
   seg[0] = {0, 64, T->G_p1, 64, 0, 0};
   CKR(vgg_backward(h, T, tp.vgg[2], enc_def(h, 2), tp.p1, T->G_a2, 128, 0, 0, seg, 1, st));
-  CK(launch_pool_bwd(tp.cat5, 128, 64, T->G_p1, B, 48, 64, 64, T->G_cat5, 128, 64, 1, st));
+  sk = skip_grad(T->G_cat5, T->G_skip5, 64);
+  CK(launch_pool_bwd(tp.cat5, 128, 64, T->G_p1, B, 48, 64, 64, sk.p, sk.cstride, sk.coff, sk.acc, st));
   seg[0] = {0, 64, T->G_a1, 64, 0, 0};
-  CKR(vgg_backward(h, T, tp.vgg[1], enc_def(h, 1), tp.a1, T->G_cat5, 128, 64, 0, seg, 1, st));
+  CKR(vgg_backward(h, T, tp.vgg[1], enc_def(h, 1), tp.a1, sk.p, sk.cstride, sk.coff, 0, seg, 1, st));
   {
     // encoder.c1.0: BatchNorm backward, then the small-K weight gradient on CUDA cores (no input gradient needed)
     const TLayer& L = T->L[RAC_L_ENC_C1_0];
@@ -560,6 +600,10 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
         }
       tp.d2a = bp.take<bf16>(M3 * 512); tp.d2b = bp.take<bf16>(M3 * 512); tp.d3a = bp.take<bf16>(M2 * 256);
       tp.d3b = bp.take<bf16>(M2 * 256); tp.d4a = bp.take<bf16>(M1 * 128); tp.d5 = bp.take<bf16>(M0 * 64);
+      tp.dcat5 = tp.cat5; tp.dcat4 = tp.cat4; tp.dcat3 = tp.cat3;
+      if (cfg->fixed_skip && t > 0) {
+        tp.dcat5 = bp.take<bf16>(M0 * 128); tp.dcat4 = bp.take<bf16>(M1 * 256); tp.dcat3 = bp.take<bf16>(M2 * 512);
+      }
       for (int i = 0; i < 19; ++i) {
         const VggDef d = i < 10 ? enc_def(h, i) : dec_def(h, i - 10);
         tp.vgg[i].raw = bp.take<float>(static_cast<size_t>(B) * d.H * d.W * d.cout);
@@ -580,6 +624,7 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
     T->G_a4b = bp.take<float>(M3 * 512); T->G_a4a = bp.take<float>(M3 * 512); T->G_p3 = bp.take<float>(M3 * 256);
     T->G_a3b = bp.take<float>(M2 * 256); T->G_a3a = bp.take<float>(M2 * 256); T->G_p2 = bp.take<float>(M2 * 128);
     T->G_a2 = bp.take<float>(M1 * 128); T->G_p1 = bp.take<float>(M1 * 64); T->G_a1 = bp.take<float>(M0 * 64);
+    T->G_skip5 = bp.take<float>(M0 * 64); T->G_skip4 = bp.take<float>(M1 * 128); T->G_skip3 = bp.take<float>(M2 * 256);
     for (int s = 0; s < 3; ++s)
       for (int l = 0; l < 2; ++l) {
         T->G_hs[s][l][0] = bp.take<float>(M3 * g);
@@ -675,7 +720,8 @@ int rac_train_debug_buffer(rac_handle* h, const char* name, int step, void** ptr
       {"img4", tp.img4}, {"a1", tp.a1}, {"cat5", tp.cat5}, {"p1", tp.p1}, {"a2", tp.a2}, {"cat4", tp.cat4},
       {"p2", tp.p2}, {"a3a", tp.a3a}, {"a3b", tp.a3b}, {"cat3", tp.cat3}, {"p3", tp.p3}, {"a4a", tp.a4a},
       {"a4b", tp.a4b}, {"h4", tp.h4}, {"d2a", tp.d2a}, {"d2b", tp.d2b}, {"d3a", tp.d3a}, {"d3b", tp.d3b},
-      {"d4a", tp.d4a}, {"d5", tp.d5}, {"x4", tp.x4}, {"hfp1", tp.hs[2][1]}, {"xp", tp.xp},
+      {"d4a", tp.d4a}, {"d5", tp.d5}, {"dcat5", tp.dcat5}, {"dcat4", tp.dcat4}, {"dcat3", tp.dcat3},
+      {"G_skip5", T->G_skip5}, {"G_skip4", T->G_skip4}, {"G_skip3", T->G_skip3}, {"x4", tp.x4}, {"hfp1", tp.hs[2][1]}, {"xp", tp.xp},
       {"G_img0", T->G_img[0]}, {"G_img1", T->G_img[1]}, {"dbg_draw32", T->dbg_draw32}};
   for (auto& e : tab)
     if (!strcmp(e.n, name)) { *ptr = e.p; return RAC_OK; }

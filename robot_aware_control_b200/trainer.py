@@ -14,7 +14,7 @@ flat gradient buffer is all-reduced (NCCL) and averaged before the Adam update, 
 
 Scheduled sampling follows the reference (same probability schedule, same global numpy generator); when the model's
 own prediction is fed back, its gradient flows into the previous step as in the reference (`x_pred.clone()`).
-Limits (raise): heatmaps, multiview, movement weighting, last_frame_skip False, lstm_group_norm.
+Limits (raise): heatmaps, multiview, movement weighting, lstm_group_norm.
 """
 import ctypes as C
 
@@ -103,7 +103,8 @@ class RacTrainLayer(C.Structure):
 class RacTrainConfig(C.Structure):
     _fields_ = [("batch", C.c_int), ("steps", C.c_int), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
                 ("adam_eps", C.c_float), ("kl_beta", C.c_float), ("robot_pixel_weight", C.c_float),
-                ("recon_kind", C.c_int), ("zero_robot", C.c_int), ("n_params", C.c_longlong), ("n_buffers", C.c_longlong)]
+                ("recon_kind", C.c_int), ("zero_robot", C.c_int), ("n_params", C.c_longlong), ("n_buffers", C.c_longlong),
+                ("fixed_skip", C.c_int)]
 
 
 class RacTrainBatch(C.Structure):
@@ -119,16 +120,16 @@ class SVGTrainer:
         c = svg_config_from(config)
         self.n_future = getattr(config, "n_future", 5)
         self.n_past = getattr(config, "n_past", 1)
-        # n_past only sets the clip length (n_past + n_future frames, trainer.py:352) and, with last_frame_skip False
-        # (refused below), which step's skip tensors the decoder keeps (trainer.py:409-411)
+        # n_past only sets the clip length (n_past + n_future frames, trainer.py:352). With last_frame_skip False (the
+        # config default) the decoder keeps the skips of the clip's FIRST frame whatever n_past is: the model returns
+        # the skip it used (dynamics.py:586-588,644), so `skip = curr_skip` (trainer.py:409-411) never changes it
         self._scheduled_sampling = bool(getattr(config, "scheduled_sampling", False))
         self._ss_k = float(getattr(config, "scheduled_sampling_k", 4000))
         self._forced_tokens = None
         kind = c.reconstruction_loss
         if kind not in ("l1", "dontcare_l1"):
             raise NotImplementedError(f"reconstruction_loss {kind!r}: the B200 path implements l1 and dontcare_l1")
-        if not c.last_frame_skip:
-            raise NotImplementedError("last_frame_skip False is not implemented for training")
+        self._fixed_skip = int(not c.last_frame_skip)
         if c.lstm_group_norm:
             raise NotImplementedError("lstm_group_norm is implemented for inference / planning only")
         self.process_group = process_group
@@ -215,7 +216,8 @@ class SVGTrainer:
             return
         cfg = RacTrainConfig(batch=B, steps=S, lr=self._lr, beta1=self._beta1, beta2=0.999, adam_eps=1e-8,
                              kl_beta=self._kl_beta, robot_pixel_weight=self._rpw, recon_kind=self._kind,
-                             zero_robot=self._zero_robot, n_params=self.params.numel(), n_buffers=self.buffers.numel())
+                             zero_robot=self._zero_robot, n_params=self.params.numel(), n_buffers=self.buffers.numel(),
+                             fixed_skip=self._fixed_skip)
         m = self.model
         _lib.check(self._lib.rac_train_create(m.handle, C.byref(cfg), self._layers, _lib.ptr(self.params),
                                               _lib.ptr(self.buffers), _lib.ptr(self.grads), _lib.ptr(self.adam_m),

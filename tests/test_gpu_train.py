@@ -31,8 +31,9 @@ B = 4
 def _setup(tag, n_future, lr=1e-3, beta=1e-2):
     from robot_aware_control_b200 import SVGConvModel, SVGTrainer
 
-    kw = dict(lr=lr, beta=beta, beta1=0.9, n_future=n_future, n_past=1)
-    if tag == "vanilla":
+    # "...fixedskip": last_frame_skip False, the config default (decoder skips of the clip's first frame)
+    kw = dict(lr=lr, beta=beta, beta1=0.9, n_future=n_future, n_past=1, last_frame_skip="fixedskip" not in tag)
+    if tag.startswith("vanilla"):
         cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, **kw)
     else:
         cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, model_use_mask=True, model_use_future_mask=True,
@@ -42,7 +43,7 @@ def _setup(tag, n_future, lr=1e-3, beta=1e-2):
     model.load_state_dict(sd)
     model.train()
     trainer = SVGTrainer(cfg, model)
-    batch, ep, eq = make_batch(23, cfg, tag != "vanilla")
+    batch, ep, eq = make_batch(23, cfg, not tag.startswith("vanilla"))
     T = n_future + 1
     batch = {k: (v[:T] if k != "actions" else v[:T - 1]) for k, v in batch.items()}
     return cfg, sd, model, trainer, batch, ep[:T - 1], eq[:T - 1]
@@ -52,7 +53,7 @@ def _rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-20))
 
 
-@pytest.mark.parametrize("tag", ["vanilla", "ra", "ra_sampled"])
+@pytest.mark.parametrize("tag", ["vanilla", "ra", "ra_sampled", "ra_fixedskip", "vanilla_fixedskip_sampled"])
 def test_train_step_losses_smooth_grads_adam(golden_dir, tag):
     gold = np.load(os.path.join(golden_dir, f"train_{tag}.npz"))
     cfg, sd, model, trainer, batch, ep, eq = _setup(tag, 3)
@@ -200,6 +201,44 @@ def test_backward_is_locally_exact_on_its_own_tape():
     pool_check(cat5, Gcat5, dx5, G("G_p1", (B, 24, 32, 64)), 64)
     pool_check(cat4, Gcat4, dx4, G("G_p2", (B, 12, 16, 128)), 128)
     pool_check(cat3, Gcat3, dx3, G("G_p3", (B, 6, 8, 256)), 256)
+
+
+def test_fixed_skip_plumbing():
+    """last_frame_skip False (rac_train_config.fixed_skip). One step: the clip's first frame IS the step's own frame,
+    so every gradient must equal the last_frame_skip True run bit for bit. Two steps: step 1 decodes from its own
+    concat buffers whose skip halves are copies of step 0's encoder outputs, its own encoder outputs stay in cat*
+    (they feed the pooling path), and the decoder halves of the two buffers are the same tensor."""
+    grads = {}
+    for tag in ("ra", "ra_fixedskip"):
+        cfg, sd, model, trainer, batch, ep, eq = _setup(tag, 1)
+        trainer.set_noise(ep, eq)
+        losses = trainer.forward_backward(batch)
+        grads[tag] = (trainer.grads.clone(), losses.clone())
+    assert torch.equal(grads["ra"][0], grads["ra_fixedskip"][0]) and torch.equal(grads["ra"][1], grads["ra_fixedskip"][1])
+    assert float(grads["ra"][0].abs().sum()) > 0
+
+    cfg, sd, model, trainer, batch, ep, eq = _setup("ra_fixedskip", 2)
+    trainer.set_noise(ep, eq)
+    trainer.forward_backward(batch)
+    torch.cuda.synchronize()
+    for name, shape, half in (("cat5", (B, 48, 64, 128), 64), ("cat4", (B, 24, 32, 256), 128), ("cat3", (B, 12, 16, 512), 256)):
+        first = _tape(trainer, name, shape, step=0)
+        own = _tape(trainer, name, shape, step=1)
+        dec = _tape(trainer, "d" + name, shape, step=1)
+        assert torch.equal(_tape(trainer, "d" + name, shape, step=0), first)    # step 0: one buffer
+        assert torch.equal(dec[..., half:], first[..., half:])                   # skips of the first frame
+        assert not torch.equal(own[..., half:], first[..., half:])               # the step's own encoder outputs
+        assert float(dec[..., :half].abs().sum()) > 0
+    # skip-half gradient: sum over both steps + step 0's pooling path; it is what encoder.c1.1 of step 0 received.
+    # Lower bound check against step 0's own contributions, re-derived with torch from the saved tensors
+    G = lambda name, shape: _tape(trainer, name, shape, bf16=False)
+    gskip = G("G_skip5", (B, 48, 64, 64))
+    assert torch.isfinite(gskip).all() and float(gskip.abs().sum()) > 0
+    gcat5 = G("G_cat5", (B, 48, 64, 128))
+    # step 1 (t > 0) wrote the skip half of G_cat5 from its pooling path only, step 0 never touches it in this mode:
+    # a pooled gradient has at most one non-zero per 2x2 window
+    win = gcat5[..., 64:].view(B, 24, 2, 32, 2, 64).permute(0, 1, 3, 5, 2, 4).reshape(-1, 4)
+    assert int(((win != 0).sum(1) > 1).sum()) == 0 and float(win.abs().sum()) > 0
 
 
 def test_sampled_frame_gradient_is_locally_exact(monkeypatch):
