@@ -221,6 +221,25 @@ int rac_ssim(const float* img1, const float* img2, const float* mask, float* map
  * blend mask, x_j (n,3,H,W) -> out (n,3,H,W) = (1 - m) * x_j + m * rgb. */
 int rac_composite(const float* x_pred4, const float* x_j, float* out, int n, int hw, void* stream);
 
+/* ---- training-data path --------------------------------------------------------------------
+ * Replaces the per-clip CPU work of RoboNetDataset._preprocess_images_masks (src/dataset/robonet/robonet_dataset.py:
+ * 257-300: ToTensor, optional random crop + bilinear resize back to H x W, shuffled colour jitter :546-573, masks cast
+ * back to {0, 1}) and the batch-first -> time-first transposition of process_batch (:434-451) with one launch over the
+ * raw uint8 frames. The random draws stay on the host (data.py::sample_augment consumes the generators exactly as the
+ * reference does); the library gets their values. */
+typedef struct {
+  int crop_i, crop_j, crop_h, crop_w; /* F.crop window (top, left, height, width); (0, 0, H, W) = no crop / resize */
+  double factor[4];                   /* brightness, contrast, saturation, hue factors */
+  int order[4];                       /* colour transforms in application order: 0 brightness, 1 contrast,
+                                         2 saturation, 3 hue; -1 = none */
+} rac_augment;
+/* frames: device uint8 (B, T, H, W, 3) as stored / collated; masks: device (B, T, H, W) float32 (mask_is_u8 = 0) or
+ * uint8 (1), or NULL; aug: DEVICE rac_augment[B] (one per clip) or NULL (ToTensor only: bit-exact value / 255);
+ * images_out (T, B, 3, H, W), masks_out (T, B, 1, H, W) float32, time-first. H x W must be 48 x 64 and `frames`
+ * 16-byte aligned. */
+int rac_process_batch(const uint8_t* frames, const void* masks, int mask_is_u8, int B, int T, int H, int W,
+                      const rac_augment* aug, float* images_out, float* masks_out, void* stream);
+
 /* Test / inspection hook: device pointer and element count of a named internal buffer of the prepared workspace
  * ("h1".."h4", "prior_in", "z", "h_pred", "img", ...). */
 int rac_debug_buffer(rac_handle* h, const char* name, void** ptr, int64_t* elems, int* elem_bytes);

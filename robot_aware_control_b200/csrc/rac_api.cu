@@ -13,6 +13,11 @@
 #include "conv.cuh"
 #include "misc_kernels.cuh"
 
+namespace rac {  // data_kernels.cu
+cudaError_t launch_process_batch(const uint8_t* frames, const void* masks, int mask_u8, int B, int T,
+                                 const rac_augment* aug, float* img_out, float* mask_out, cudaStream_t s);
+}
+
 namespace {
 
 using namespace rac;
@@ -1174,6 +1179,17 @@ int rac_ssim(const float* img1, const float* img2, const float* mask, float* map
   if (!img1 || !img2 || (!map_out && !plane_mean_out) || n < 0 || c < 1 || h < 1 || w < 1) return RAC_ERR_INVALID;
   if (static_cast<size_t>(7) * h * w * 4 > 226 * 1024) return RAC_ERR_UNSUPPORTED;
   return launch_ssim(img1, img2, mask, map_out, plane_mean_out, n, c, h, w, static_cast<cudaStream_t>(stream)) == cudaSuccess ? RAC_OK : RAC_ERR_CUDA;
+}
+
+int rac_process_batch(const uint8_t* frames, const void* masks, int mask_is_u8, int B, int T, int H, int W,
+                      const rac_augment* aug, float* images_out, float* masks_out, void* stream) {
+  if (!frames || !images_out || B < 0 || T < 0 || (masks && !masks_out)) return RAC_ERR_INVALID;
+  if (H != 48 || W != 64) return RAC_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(frames) & 15) || (masks && !mask_is_u8 && (reinterpret_cast<uintptr_t>(masks) & 15)) ||
+      (aug && (reinterpret_cast<uintptr_t>(aug) & 7)))
+    return RAC_ERR_INVALID;
+  return rac::launch_process_batch(frames, masks, mask_is_u8, B, T, aug, images_out, masks_out,
+                                   static_cast<cudaStream_t>(stream)) == cudaSuccess ? RAC_OK : RAC_ERR_CUDA;
 }
 
 int rac_composite(const float* x_pred4, const float* x_j, float* out, int n, int hw, void* stream) {
