@@ -83,6 +83,7 @@ struct TrainState {
   int cur_t = 0;         // time step being processed by the backward pass (column block of the wgrad operands)
   float* bn_scratch;
   float* draw32;         // fp32 copy of the first layer's raw gradient
+  float* fw_part;        // per-CTA partial sums of the first layer's weight gradient [kFwBlocks][45 * 64]
   bf16* hzero;
   float* czero;
   float* loss_part;      // [B]
@@ -91,6 +92,8 @@ struct TrainState {
   int adam_t = 0;
   int M[4];
 };
+
+constexpr int kFwBlocks = 148;  // CTAs of the first layer's weight-gradient kernel (one partial sum each)
 
 inline int pick_bn(int n) { return n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : 64); }
 
@@ -508,7 +511,8 @@ int train_backward_step(rac_handle* h, TrainState* T, const rac_train_batch* bt,
                      T->params + L.d.beta_off, B, 48, 64, 64, T->bn_scratch, T->dy_a, T->draw32,
                      T->grads + L.d.gamma_off, T->grads + L.d.beta_off, st));
     CK(launch_first_wgrad(tp.img4, c.use_mask ? m_j : nullptr, (c.use_mask && c.use_future_mask) ? m_i : nullptr,
-                          static_cast<long long>(HW), T->draw32, T->grads + L.d.w_off, B, 48, 64, h->enc_cin, st));
+                          static_cast<long long>(HW), T->draw32, T->grads + L.d.w_off, B, 48, 64, h->enc_cin, T->fw_part,
+                          kFwBlocks, st));
     // a model-sampled input frame also receives gradient through the encoder (zeroed robot pixels get none)
     if (tp.sampled && T->dbg_keep)
       CK(cudaMemcpyAsync(T->dbg_draw32, T->draw32, sizeof(float) * static_cast<size_t>(B) * HW * 64, cudaMemcpyDeviceToDevice, st));
@@ -635,6 +639,7 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
     T->dy_a = bp.take<bf16>(dy_elems); T->dy_b = bp.take<bf16>(dy_elems);
     T->bn_scratch = bp.take<float>(2 * 2048);
     T->draw32 = bp.take<float>(M0 * 64);
+    T->fw_part = bp.take<float>(static_cast<size_t>(kFwBlocks) * 45 * 64);
     T->hzero = bp.take<bf16>(M3 * g); T->czero = bp.take<float>(M3 * g);
     T->G_img[0] = bp.take<float>(M0 * 3); T->G_img[1] = bp.take<float>(M0 * 3);
     T->dbg_draw32 = bp.take<float>(M0 * 64);

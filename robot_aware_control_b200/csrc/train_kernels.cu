@@ -97,53 +97,85 @@ cudaError_t launch_pack_first(const float* w, int cin, float* wf, cudaStream_t s
   return cudaGetLastError();
 }
 
-// dW[o][c][tap] += sum_pix in[pix][tap, c] * draw[pix][o]
+// dW[o][c][tap] += sum_pix in[pix][tap, c] * draw[pix][o]. Deterministic: every CTA walks its 64-pixel chunks in a
+// fixed order with its (k, o) products in registers and writes ONE partial per CTA; first_wgrad_fold_kernel then adds
+// the partials to gw in CTA order (no atomics: the same bits every run).
+constexpr int kFwPer = 12;  // ceil(45 * 64 / 256) (k, o) pairs per thread
 __global__ void __launch_bounds__(256)
 first_wgrad_kernel(const float* __restrict__ img4, const float* __restrict__ mask_a, const float* __restrict__ mask_b,
-                   long long mask_bstride, const float* __restrict__ draw, float* __restrict__ gw, int B, int H, int W,
+                   long long mask_bstride, const float* __restrict__ draw, float* __restrict__ part, int B, int H, int W,
                    int cin) {
   __shared__ float sin_[64][46];
   __shared__ float sdr[64][65];
   const size_t total = static_cast<size_t>(B) * H * W;
-  const size_t p0 = static_cast<size_t>(blockIdx.x) * 64;
   const int K = 9 * cin;
-  for (int i = threadIdx.x; i < 64 * K; i += blockDim.x) {
-    const int px = i / K, k = i - px * K;
-    const size_t pix = p0 + px;
-    float v = 0.f;
-    if (pix < total) {
-      const int tap = k / cin, c = k - tap * cin;
-      const int x = static_cast<int>(pix % W), y = static_cast<int>((pix / W) % H);
-      const size_t b = pix / (static_cast<size_t>(W) * H);
-      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-        if (c < 3) v = img4[((b * H + yy) * W + xx) * 4 + c];
-        else if (c == 3) v = mask_a[b * mask_bstride + static_cast<size_t>(yy) * W + xx];
-        else v = mask_b[b * mask_bstride + static_cast<size_t>(yy) * W + xx];
+  float acc[kFwPer];
+#pragma unroll
+  for (int j = 0; j < kFwPer; ++j) acc[j] = 0.f;
+  for (size_t p0 = static_cast<size_t>(blockIdx.x) * 64; p0 < total; p0 += static_cast<size_t>(gridDim.x) * 64) {
+    __syncthreads();  // the previous chunk has been consumed
+    for (int i = threadIdx.x; i < 64 * K; i += blockDim.x) {
+      const int px = i / K, k = i - px * K;
+      const size_t pix = p0 + px;
+      float v = 0.f;
+      if (pix < total) {
+        const int tap = k / cin, c = k - tap * cin;
+        const int x = static_cast<int>(pix % W), y = static_cast<int>((pix / W) % H);
+        const size_t b = pix / (static_cast<size_t>(W) * H);
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+          if (c < 3) v = img4[((b * H + yy) * W + xx) * 4 + c];
+          else if (c == 3) v = mask_a[b * mask_bstride + static_cast<size_t>(yy) * W + xx];
+          else v = mask_b[b * mask_bstride + static_cast<size_t>(yy) * W + xx];
+        }
+      }
+      sin_[px][k] = v;
+    }
+    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+      const int px = i >> 6, o = i & 63;
+      const size_t pix = p0 + px;
+      sdr[px][o] = pix < total ? draw[pix * 64 + o] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kFwPer; ++j) {
+      const int p = threadIdx.x + 256 * j;
+      if (p < K * 64) {
+        const int k = p >> 6, o = p & 63;
+        float a = acc[j];
+#pragma unroll 8
+        for (int px = 0; px < 64; ++px) a += sin_[px][k] * sdr[px][o];
+        acc[j] = a;
       }
     }
-    sin_[px][k] = v;
   }
-  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
-    const int px = i >> 6, o = i & 63;
-    const size_t pix = p0 + px;
-    sdr[px][o] = pix < total ? draw[pix * 64 + o] : 0.f;
-  }
-  __syncthreads();
-  for (int p = threadIdx.x; p < K * 64; p += blockDim.x) {
-    const int k = p >> 6, o = p & 63;
-    float acc = 0.f;
-#pragma unroll 8
-    for (int px = 0; px < 64; ++px) acc += sin_[px][k] * sdr[px][o];
-    const int tap = k / cin, c = k - tap * cin;
-    atomicAdd(&gw[(o * cin + c) * 9 + tap], acc);
+#pragma unroll
+  for (int j = 0; j < kFwPer; ++j) {
+    const int p = threadIdx.x + 256 * j;
+    if (p < K * 64) part[static_cast<size_t>(blockIdx.x) * K * 64 + p] = acc[j];
   }
 }
+__global__ void __launch_bounds__(256)
+first_wgrad_fold_kernel(const float* __restrict__ part, int nblk, float* __restrict__ gw, int cin) {
+  const int K = 9 * cin;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= K * 64) return;
+  float sum = 0.f;
+  for (int b = 0; b < nblk; ++b) sum += part[static_cast<size_t>(b) * K * 64 + p];
+  const int k = p >> 6, o = p & 63;
+  const int tap = k / cin, c = k - tap * cin;
+  gw[(o * cin + c) * 9 + tap] += sum;
+}
 cudaError_t launch_first_wgrad(const float* img4, const float* mask_a, const float* mask_b, long long mask_bstride,
-                               const float* draw, float* gw, int B, int H, int W, int cin, cudaStream_t s) {
+                               const float* draw, float* gw, int B, int H, int W, int cin, float* part, int max_blocks,
+                               cudaStream_t s) {
   const size_t total = static_cast<size_t>(B) * H * W;
-  first_wgrad_kernel<<<static_cast<unsigned>((total + 63) / 64), 256, 0, s>>>(img4, mask_a, mask_b, mask_bstride, draw,
-                                                                              gw, B, H, W, cin);
+  if (cin < 3 || cin > 5 || !part || max_blocks < 1) return cudaErrorInvalidValue;
+  int grid = static_cast<int>((total + 63) / 64);
+  if (grid > max_blocks) grid = max_blocks;
+  if (grid < 1) return cudaSuccess;
+  first_wgrad_kernel<<<grid, 256, 0, s>>>(img4, mask_a, mask_b, mask_bstride, draw, part, B, H, W, cin);
+  first_wgrad_fold_kernel<<<(9 * cin * 64 + 255) / 256, 256, 0, s>>>(part, grid, gw, cin);
   return cudaGetLastError();
 }
 

@@ -23,7 +23,8 @@ cudaError_t launch_unpack_grads(const float* dwp, const long long* row_off, cons
 cudaError_t launch_pack_first(const float* w, int cin, float* wf, cudaStream_t s);
 cudaError_t launch_first_wgrad(const float* img4, const float* mask_a, const float* mask_b, long long mask_bstride,
                                const float* draw /* [pix][64] fp32 */, float* gw /* master layout, += */, int B,
-                               int H, int W, int cin, cudaStream_t s);
+                               int H, int W, int cin, float* part /* scratch [max_blocks][9 * cin * 64] */,
+                               int max_blocks, cudaStream_t s);
 
 // ---- BatchNorm (train mode) + LeakyReLU(0.2)
 // raw: [M, C] fp32 (pre-BN conv output). mean / rstd: [C]. running stats updated `updates` times (momentum 0.1).

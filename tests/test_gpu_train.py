@@ -215,6 +215,10 @@ def test_fixed_skip_plumbing():
         losses = trainer.forward_backward(batch)
         grads[tag] = (trainer.grads.clone(), losses.clone())
     assert torch.equal(grads["ra"][0], grads["ra_fixedskip"][0]) and torch.equal(grads["ra"][1], grads["ra_fixedskip"][1])
+    # (bit equality also says the step is deterministic run to run: no atomics anywhere in the backward pass)
+    trainer.set_noise(ep, eq)
+    trainer.forward_backward(batch)
+    assert torch.equal(trainer.grads, grads["ra_fixedskip"][0])
     assert float(grads["ra"][0].abs().sum()) > 0
 
     cfg, sd, model, trainer, batch, ep, eq = _setup("ra_fixedskip", 2)
