@@ -53,7 +53,7 @@ def test_metric_kernels_edge_cases():
     assert M.psnr(torch.zeros(0, 3, 48, 64), torch.zeros(0, 3, 48, 64)).shape == (0,)
 
 
-@pytest.mark.parametrize("tag", ["vanilla", "ra"])
+@pytest.mark.parametrize("tag", ["vanilla", "ra", "ra_fixedskip"])
 def test_eval_step_matches_reference_golden(golden_dir, tag):
     from robot_aware_control_b200 import SVGConvModel, SVGTrainer
 
@@ -65,7 +65,7 @@ def test_eval_step_matches_reference_golden(golden_dir, tag):
     model.load_state_dict(so.make_state_dict(cfg, int(gold["weight_seed"])))
     trainer = SVGTrainer(cfg, model)
     model.eval()
-    batch, eps_p, eps_q = make_eval_batch(int(gold["input_seed"]), cfg, tag == "ra")
+    batch, eps_p, eps_q = make_eval_batch(int(gold["input_seed"]), cfg, tag != "vanilla")
     got = {}
     for autoreg in (False, True):
         trainer.set_noise(eps_p, eps_q)

@@ -38,6 +38,58 @@ def scene(golden_dir):
     return np.load(os.path.join(golden_dir, "scene.npz"))
 
 
+def test_keep_skip_decodes_with_the_held_skips():
+    """last_frame_skip False (the argparse default): a forward that is handed the skips of an earlier frame decodes
+    with THEM (dynamics.py:586-588) -- the evaluation loops do that for every frame after the first
+    (trainer.py:615-616,658-660). The handle keeps them in the skip halves of its concat buffers and sends the
+    encoder's own outputs to side buffers."""
+    cfg = _cfg("ra", last_frame_skip=False)
+    sd = so.make_state_dict(cfg, 5)
+    m = _model(cfg, sd, "tc")
+    n = 3
+    g = torch.Generator().manual_seed(1)
+    xa, xb = torch.rand(n, 3, 48, 64, generator=g), torch.rand(n, 3, 48, 64, generator=g)
+    mask = (torch.rand(n, 1, 48, 64, generator=g) > 0.8).float()
+    robot = torch.rand(n, 5, generator=g)
+    act = (torch.rand(n, 5, generator=g) - 0.5) * 0.1
+    eps = torch.randn(2, n, cfg.z_dim, 6, 8, generator=g)
+    bufs = (("cat5", (n, 48, 64, 128), 64), ("cat4", (n, 24, 32, 256), 128), ("cat3", (n, 12, 16, 512), 256))
+
+    def two_frames(explicit):
+        m.init_hidden(n)
+        m.set_noise(eps=eps[0])
+        out_a = m.forward(xa, mask, robot, None, act)
+        held = {name: m._buffer_view(name, shape).clone() for name, shape, _ in bufs}
+        skip = [t.clone() for t in out_a[1]] if explicit else out_a[1]
+        m.set_noise(eps=eps[1])
+        out_b = m.forward(xb, mask, robot, None, act, skip=skip)
+        return out_a, out_b, held
+
+    out_a, out_b, held = two_frames(False)
+    for name, shape, half in bufs:
+        now = m._buffer_view(name, shape)
+        assert torch.equal(now[..., half:], held[name][..., half:])          # the first frame's skips are still there
+        assert not torch.equal(now[..., :half], held[name][..., :half])      # the decoder half is frame B's
+    # the encoder's own outputs for frame B went elsewhere, and they differ from the held ones
+    m2 = _model(_cfg("ra", last_frame_skip=True), sd, "tc")
+    m2.init_hidden(n)
+    m2.set_noise(eps=eps[0])
+    m2.forward(xa, mask, robot, None, act)
+    m2.set_noise(eps=eps[1])
+    own = m2.forward(xb, mask, robot, None, act, skip=None)
+    assert not torch.equal(m2._buffer_view("cat5", bufs[0][1])[..., 64:], held["cat5"][..., 64:])
+    assert not torch.equal(own[0], out_b[0])                                 # and the prediction depends on the choice
+    # against the oracle run the same way
+    o = so.SVGOracle(cfg, sd)
+    o.init_hidden(n)
+    ra = o.forward(xa, mask, robot, act, eps[0])
+    rb = o.forward(xb, mask, robot, act, eps[1], skip=ra[1])
+    assert (out_a[0].cpu() - ra[0]).abs().max() < PIX_TOL and (out_b[0].cpu() - rb[0]).abs().max() < PIX_TOL
+    # caller-supplied tensors instead of the object forward() returned: the same bits
+    _, out_b2, _ = two_frames(True)
+    assert torch.equal(out_b2[0], out_b[0])
+
+
 # ------------------------------------------------------------------------------------------------ forward
 @pytest.mark.parametrize("impl", ["simt", "tc"])
 @pytest.mark.parametrize("tag", ["vanilla", "ra"])
