@@ -297,6 +297,10 @@ int rac_train_forward_backward(rac_handle* h, const rac_train_batch* batch, void
 int rac_train_debug_buffer(rac_handle* h, const char* name, int step, void** ptr);
 /* params <- Adam(params, grads) */
 int rac_train_adam_step(rac_handle* h, void* stream);
+/* Number of Adam steps already taken (the t of the bias corrections). rac_train_create starts at 0: a caller that
+ * re-creates the training state (another batch shape) or resumes from a checkpoint (torch.optim.Adam state "step",
+ * trainer.py:829-896) restores it here; the moments themselves live in the caller's adam_m / adam_v. */
+int rac_train_set_adam_step(rac_handle* h, int steps_taken);
 
 /* Live timing of one kernel family for the roofline line of bench.py: CUDA event pairs are recorded on the launch
  * stream around every convolution launch whose layer name contains `name_substr` (e.g. "lstm.0"), up to

@@ -91,6 +91,7 @@ EXPORTS = {
     "rac_train_destroy": (C.c_int, [C.c_void_p]),
     "rac_train_forward_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "rac_train_adam_step": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rac_train_set_adam_step": (C.c_int, [C.c_void_p, C.c_int]),
     "rac_train_debug_buffer": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
     "rac_profile_begin": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "rac_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),

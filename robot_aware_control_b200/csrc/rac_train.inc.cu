@@ -737,6 +737,13 @@ int rac_train_debug_buffer(rac_handle* h, const char* name, int step, void** ptr
   return fail(h, RAC_ERR_INVALID, "no training buffer named '%s'", name);
 }
 
+int rac_train_set_adam_step(rac_handle* h, int steps_taken) {
+  if (!h || !h->train) return fail(h, RAC_ERR_STATE, "rac_train_create first");
+  if (steps_taken < 0) return fail(h, RAC_ERR_INVALID, "negative Adam step count %d", steps_taken);
+  static_cast<TrainState*>(h->train)->adam_t = steps_taken;
+  return RAC_OK;
+}
+
 int rac_train_adam_step(rac_handle* h, void* stream) {
   if (!h || !h->train) return fail(h, RAC_ERR_STATE, "rac_train_create first");
   TrainState* T = static_cast<TrainState*>(h->train);

@@ -113,6 +113,54 @@ class RacTrainBatch(C.Structure):
                 ("true_token", C.c_void_p)]
 
 
+def adam_state_dict(m, v, steps_taken, layout, lr, beta1):
+    """Flat first / second moments + one step count -> the dict torch.optim.Adam.state_dict() returns. `layout`:
+    (offset, shape) per parameter in optimizer order. Like torch, no per-parameter state exists before the first step."""
+    state = {}
+    if steps_taken > 0:
+        for i, (off, shape) in enumerate(layout):
+            n = int(np.prod(shape)) if len(shape) else 1
+            state[i] = {"step": torch.tensor(float(steps_taken)), "exp_avg": m[off:off + n].view(shape).clone(),
+                        "exp_avg_sq": v[off:off + n].view(shape).clone()}
+    group = {"lr": lr, "betas": (beta1, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False, "maximize": False,
+             "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+             "decoupled_weight_decay": False, "params": list(range(len(layout)))}
+    return {"state": state, "param_groups": [group]}
+
+
+def load_adam_state_dict(state_dict, m, v, layout):
+    """Inverse of adam_state_dict for a dict saved by the reference trainer (any torch version: "step" is an int in
+    torch 1.x and a tensor later). Fills m / v in place; returns (steps_taken, lr, beta1)."""
+    groups = state_dict["param_groups"]
+    if len(groups) != 1:
+        raise ValueError("loaded state dict has a different number of parameter groups")
+    grp = groups[0]
+    ids = list(grp["params"])
+    if len(ids) != len(layout):
+        raise ValueError("loaded state dict contains a parameter group that doesn't match the size of optimizer's group")
+    if grp.get("amsgrad", False) or grp.get("weight_decay", 0) != 0 or grp.get("maximize", False):
+        raise NotImplementedError("the B200 Adam kernel implements the reference's plain Adam (no amsgrad / weight decay)")
+    if abs(float(grp.get("eps", 1e-8)) - 1e-8) > 0 or abs(float(grp["betas"][1]) - 0.999) > 0:
+        raise NotImplementedError("eps / beta2 other than the reference's 1e-8 / 0.999")
+    steps = set()
+    m.zero_()
+    v.zero_()
+    for pos, pid in enumerate(ids):
+        st = state_dict["state"].get(pid)
+        if st is None:
+            continue
+        off, shape = layout[pos]
+        if tuple(st["exp_avg"].shape) != tuple(shape):
+            raise ValueError(f"optimizer state of parameter {pos} has shape {tuple(st['exp_avg'].shape)}, expected {tuple(shape)}")
+        n = st["exp_avg"].numel()
+        m[off:off + n].copy_(st["exp_avg"].reshape(-1))
+        v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+        steps.add(int(st["step"]))
+    if len(steps) > 1:
+        raise ValueError(f"per-parameter Adam step counts differ ({sorted(steps)}): one flat update has one count")
+    return (steps.pop() if steps else 0), float(grp["lr"]), float(grp["betas"][0])
+
+
 class SVGTrainer:
     def __init__(self, config, model, process_group=None):
         self._config = config
@@ -192,6 +240,7 @@ class SVGTrainer:
         self._seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
         self._eps = None
         self._step = 0
+        self._adam_t = 0  # Adam steps taken (torch.optim.Adam state "step")
 
     # ---- scheduled sampling (reference trainer.py:132-147): same formula, same use of the global numpy generator
     def _schedule_prob(self):
@@ -222,6 +271,8 @@ class SVGTrainer:
         _lib.check(self._lib.rac_train_create(m.handle, C.byref(cfg), self._layers, _lib.ptr(self.params),
                                               _lib.ptr(self.buffers), _lib.ptr(self.grads), _lib.ptr(self.adam_m),
                                               _lib.ptr(self.adam_v)), m.handle, "rac_train_create")
+        # the bias-correction step count survives a re-creation (new batch shape, new hyper-parameters, resume)
+        _lib.check(self._lib.rac_train_set_adam_step(m.handle, self._adam_t), m.handle, "rac_train_set_adam_step")
         self._created_for = (B, S)
 
     def forward_backward(self, batch):
@@ -263,6 +314,7 @@ class SVGTrainer:
                 ev[1].record()
         _lib.check(self._lib.rac_train_adam_step(m.handle, _lib.stream_ptr()), m.handle, "rac_train_adam_step")
         m._packed_dirty = True  # the eval-mode packed copy (folded BatchNorm) is stale now
+        self._adam_t += 1
         self._step += 1
 
     def train_step(self, batch):
@@ -377,6 +429,37 @@ class SVGTrainer:
         if autoregressive:
             sampled.sort(key=lambda d: d["autoreg_psnr"], reverse=True)
         return {k: v / nwin for k, v in sampled[0].items()}
+
+    # ---- checkpoints (reference trainer.py:829-896): {"model", "optimizer", "step"} with torch.optim.Adam's state_dict
+    def _adam_layout(self):
+        return [(self._offsets[k], tuple(p.shape)) for k, p in self.model.named_parameters()]
+
+    def optimizer_state_dict(self):
+        """torch.optim.Adam(self.model.parameters(), lr, (beta1, 0.999)).state_dict() of the reference trainer
+        (trainer.py:109-122): parameter i of the group is the i-th entry of model.parameters(), same order as the
+        reference model's."""
+        return adam_state_dict(self.adam_m, self.adam_v, self._adam_t, self._adam_layout(), self._lr, self._beta1)
+
+    def load_optimizer_state_dict(self, state_dict):
+        t, lr, beta1 = load_adam_state_dict(state_dict, self.adam_m, self.adam_v, self._adam_layout())
+        self._adam_t, self._lr, self._beta1 = t, lr, beta1
+        self._created_for = None  # hyper-parameters and the step count are handed over at the next rac_train_create
+
+    def save_checkpoint(self, path):
+        """PredictionTrainer._save_checkpoint (trainer.py:829-837): the same three keys."""
+        torch.save({"model": self.model.state_dict(), "optimizer": self.optimizer_state_dict(), "step": self._step}, path)
+
+    def load_checkpoint(self, path):
+        """PredictionTrainer._load_checkpoint with a given path (trainer.py:884-896): loads the model; a "finetune"
+        experiment restarts at step 0 with a fresh optimizer, anything else resumes step and optimizer. Returns the step."""
+        ckpt = torch.load(path, map_location=self.model._device)
+        self.model.load_state_dict(ckpt["model"])
+        if "finetune" in str(getattr(self._config, "experiment", "")):
+            self._step = 0
+        else:
+            self._step = int(ckpt["step"])
+            self.load_optimizer_state_dict(ckpt["optimizer"])
+        return self._step
 
     def grad_of(self, key):
         o = self._offsets[key]

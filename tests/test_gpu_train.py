@@ -245,6 +245,65 @@ def test_fixed_skip_plumbing():
     assert int(((win != 0).sum(1) > 1).sum()) == 0 and float(win.abs().sum()) > 0
 
 
+def test_checkpoint_resume_equals_uninterrupted_run(tmp_path):
+    """Checkpoints in the reference's format (trainer.py:829-896: model, torch.optim.Adam state_dict, step): two steps,
+    save, load into a fresh model + trainer, one more step == three uninterrupted steps, bit for bit; the optimizer
+    entry loads into torch.optim.Adam over the model's parameters, as the reference's _load_checkpoint does."""
+    from robot_aware_control_b200 import SVGConvModel, SVGTrainer
+    from robot_aware_control_b200 import model as M
+
+    def run(trainer, n):
+        for _ in range(n):
+            trainer.set_noise(ep, eq)
+            trainer.train_step(batch)
+
+    cfg, sd, model, trainer, batch, ep, eq = _setup("ra", 2)
+    assert [k for k, _ in model.named_parameters()] == [k for k, (_, kind) in M._spec(model._c).items() if not kind.startswith("buf")]
+    assert trainer.optimizer_state_dict()["state"] == {}          # like torch: no state before the first step
+    run(trainer, 3)
+    want = trainer.params.clone()
+    want_buffers = trainer.buffers.clone()
+
+    cfg, sd, model, trainer, batch, ep, eq = _setup("ra", 2)
+    run(trainer, 2)
+    path = str(tmp_path / "ckpt_2.pt")
+    trainer.save_checkpoint(path)
+    ckpt = torch.load(path)
+    assert set(ckpt) == {"model", "optimizer", "step"} and ckpt["step"] == 2
+    model2 = SVGConvModel(cfg)
+    model2.train()
+    trainer2 = SVGTrainer(cfg, model2)
+    assert trainer2.load_checkpoint(path) == 2
+    run(trainer2, 1)
+    assert torch.equal(trainer2.params, want) and torch.equal(trainer2.buffers, want_buffers)
+    # another clip length re-creates the device state: the moments and the bias-correction count must survive
+    short = {k: (v[:2] if k != "actions" else v[:1]) for k, v in batch.items()}
+    trainer2.set_noise(ep[:1], eq[:1])
+    trainer2.forward_backward(short)
+    p0, g0, m0, v0, t = trainer2.params.clone(), trainer2.grads.clone(), trainer2.adam_m.clone(), trainer2.adam_v.clone(), 4
+    trainer2.optimizer_step()
+    assert trainer2._adam_t == t
+    m1, v1 = 0.9 * m0 + 0.1 * g0, 0.999 * v0 + 0.001 * g0 * g0
+    ref = p0 - 1e-3 * (m1 / (1 - 0.9 ** t)) / ((v1 / (1 - 0.999 ** t)).sqrt() + 1e-8)
+    np.testing.assert_allclose(trainer2.params.cpu().numpy(), ref.cpu().numpy(), rtol=2e-5, atol=2e-7)
+    # the reference's own loading path
+    opt = torch.optim.Adam(model2.parameters(), lr=1.0, betas=(0.5, 0.999))
+    opt.load_state_dict(ckpt["optimizer"])
+    assert opt.param_groups[0]["lr"] == 1e-3 and opt.param_groups[0]["betas"] == (0.9, 0.999)
+    st = opt.state_dict()["state"]
+    assert len(st) == len(list(model2.parameters())) and int(st[0]["step"]) == 2
+    k0 = next(iter(dict(model2.named_parameters())))
+    o = trainer._offsets[k0]
+    assert torch.equal(st[0]["exp_avg"].reshape(-1), trainer.adam_m[o:o + st[0]["exp_avg"].numel()])
+    # a "finetune" experiment restarts the step count and the optimizer (trainer.py:891-893)
+    cfg.experiment = "finetune_locobot"
+    model3 = SVGConvModel(cfg)
+    model3.train()
+    trainer3 = SVGTrainer(cfg, model3)
+    assert trainer3.load_checkpoint(path) == 0 and trainer3._adam_t == 0 and float(trainer3.adam_m.abs().sum()) == 0
+    assert torch.equal(trainer3.params, trainer.params)
+
+
 def test_sampled_frame_gradient_is_locally_exact(monkeypatch):
     """Scheduled sampling with the model's own frame at step 1 (T = 3): the gradient handed back to step 0's
     prediction = composite path (1 - m) * dL/dpred + encoder path (dgrad of encoder.c1.0, robot pixels masked),

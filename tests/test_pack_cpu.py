@@ -184,3 +184,42 @@ def test_product_path_fails_loudly_without_a_gpu():
     # stand-alone kernels: argument validation happens before any launch
     assert lib.rac_topk(None, 10, 3, None, None, None) < 0
     assert lib.rac_psnr(None, None, None, 0, None, 1, 3, 3072, None) < 0
+
+
+def test_adam_state_dict_round_trip_with_torch_adam():
+    """Checkpoint "optimizer" entry (reference trainer.py:829-896): flat moments <-> torch.optim.Adam.state_dict()."""
+    from robot_aware_control_b200.trainer import adam_state_dict, load_adam_state_dict
+
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(3, 4)), torch.nn.Parameter(torch.randn(5)), torch.nn.Parameter(torch.randn(2, 2, 3))]
+    opt = torch.optim.Adam(ps, lr=3e-4, betas=(0.85, 0.999))
+    for _ in range(3):
+        for p in ps:
+            p.grad = torch.randn_like(p)
+        opt.step()
+    layout, off = [], 0
+    for p in ps:
+        layout.append((off, tuple(p.shape)))
+        off += p.numel()
+    m, v = torch.empty(off), torch.empty(off)
+    assert load_adam_state_dict(opt.state_dict(), m, v, layout) == (3, 3e-4, 0.85)
+    ps2 = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    opt2 = torch.optim.Adam(ps2, lr=1.0)
+    opt2.load_state_dict(adam_state_dict(m, v, 3, layout, 3e-4, 0.85))
+    for p, q in zip(ps, ps2):
+        p.grad = torch.randn_like(p)
+        q.grad = p.grad.clone()
+    opt.step()
+    opt2.step()
+    assert all(torch.equal(p, q) for p, q in zip(ps, ps2))
+    old = opt.state_dict()  # torch 1.x stored the step as an int
+    for st in old["state"].values():
+        st["step"] = int(st["step"])
+    assert load_adam_state_dict(old, m, v, layout)[0] == 4
+    assert adam_state_dict(m, v, 0, layout, 1e-4, 0.9)["state"] == {}
+    with pytest.raises(ValueError):
+        load_adam_state_dict(opt.state_dict(), m, v, layout[:2])
+    bad = opt.state_dict()
+    bad["param_groups"][0]["amsgrad"] = True
+    with pytest.raises(NotImplementedError):
+        load_adam_state_dict(bad, m, v, layout)
