@@ -50,12 +50,15 @@ def main():
     for tag, kw in (("vanilla", dict(robot_aware=False)), ("ra", dict(robot_aware=True, future_mask=True)),
                     ("ra_sampled", dict(robot_aware=True, future_mask=True)),
                     ("ra_fixedskip", dict(robot_aware=True, future_mask=True)),
-                    ("vanilla_fixedskip_sampled", dict(robot_aware=False))):
+                    ("vanilla_fixedskip_sampled", dict(robot_aware=False)),
+                    ("ra_gn", dict(robot_aware=True, future_mask=True))):
         if only and tag not in only:
             continue
         extra = ("--n_future", str(T - 1), "--batch_size", str(B), "--lr", "1e-3", "--beta", "1e-2")
         if "fixedskip" in tag:  # the config default (src/config/__init__.py:217-222): decoder skips of the first frame
             extra += ("--last_frame_skip", "False")
+        if tag.endswith("_gn"):  # NormConvLSTMCell (lstm.py:151-198), the cell of the authors' deployed checkpoints
+            extra += ("--lstm_group_norm", "True")
         cfg = ref_shim.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, extra=extra, **kw)
         cfg.multiview = False
         sd = so.make_state_dict(cfg, 17)

@@ -74,8 +74,8 @@ class TrainOracle:
             recon = recon + vl
             kl = so.kl_criterion(mu, logvar, mu_p, logvar_p, B)
             kld = kld + kl
-            info["recon_loss"] += float(vl)
-            info["kld"] += float(kl)
+            info["recon_loss"] += float(vl.detach())
+            info["kld"] += float(kl.detach())
         loss = recon + kld * self.beta
         loss.backward()
         info["loss"] = float(loss)

@@ -12,14 +12,17 @@ from oracle.make_golden_train import make_batch, summarize
 from oracle.train_oracle import TrainOracle
 
 
-@pytest.mark.parametrize("tag", ["vanilla", "ra", "ra_sampled", "ra_fixedskip", "vanilla_fixedskip_sampled"])
+@pytest.mark.parametrize("tag", ["vanilla", "ra", "ra_sampled", "ra_fixedskip", "vanilla_fixedskip_sampled", "ra_gn"])
 def test_train_step_matches_reference(golden_dir, tag):
     gold = np.load(os.path.join(golden_dir, f"train_{tag}.npz"))
     lfs = "fixedskip" not in tag  # last_frame_skip False (the config default): decoder skips of the first frame
     if tag.startswith("vanilla"):
         cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, last_frame_skip=lfs)
     else:
+        # "ra_gn": NormConvLSTMCell -- the CUDA training step does not implement it yet (SVGTrainer raises); the golden
+        # and this oracle check are the parity pin for when it does
         cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, model_use_mask=True, model_use_future_mask=True, last_frame_skip=lfs,
+                          lstm_group_norm=tag.endswith("_gn"),
                           model_use_robot_state=True, reconstruction_loss="dontcare_l1", reward_type="dontcare")
     tr = TrainOracle(cfg, so.make_state_dict(cfg, int(gold["weight_seed"])), lr=float(gold["lr"]), beta=float(gold["beta"]))
     batch, eps_p, eps_q = make_batch(int(gold["input_seed"]), cfg, not tag.startswith("vanilla"))
