@@ -257,6 +257,10 @@ typedef struct {
   long long rmean_off, rvar_off;   /* BatchNorm running statistics in buffers */
   long long w_off;                 /* RAC_L_ENC_C1_0 only: offset of its (64, cin, 3, 3) weight */
   int flip;                        /* 1: ConvTranspose2d weight (taps stored flipped) */
+  /* cfg.lstm_group_norm (NormConvLSTMCell, lstm.py:151-198), RAC_L_*_LSTMk = ih_gates.0 and RAC_L_*_LSTMk_HH =
+   * hh_gates.0 entries only: gamma_off / beta_off above are then the GroupNorm(16, 4g) affine of ih_gates.1 /
+   * hh_gates.1, and on the ih entry these two are the cell's c_norm weight / bias */
+  long long cnorm_gamma_off, cnorm_beta_off;
 } rac_train_layer;
 
 typedef struct {
@@ -287,7 +291,8 @@ typedef struct {
                               (scheduled sampling, trainer.py:132-147,353-356); NULL = always the ground-truth frame */
 } rac_train_batch;
 
-int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train_layer* layers /* [RAC_L_COUNT] */,
+int rac_train_create(rac_handle* h, const rac_train_config* cfg,
+                     const rac_train_layer* layers /* [RAC_L_COUNT], [RAC_L_COUNT_GN] with lstm_group_norm */,
                      float* params, float* buffers, float* grads, float* adam_m, float* adam_v);
 int rac_train_destroy(rac_handle* h);
 /* forward (train-mode BatchNorm, posterior) + BPTT backward: fills `grads` (caller may all-reduce it) */

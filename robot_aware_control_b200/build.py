@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libracb200.so")
-SOURCES = ["conv_tc.cu", "conv_tc2.cu", "conv_tc_mc.cu", "conv_halo.cu", "first_conv_tc.cu", "misc_kernels.cu", "cem_kernels.cu", "train_kernels.cu", "norm_lstm.cu", "metric_kernels.cu", "data_kernels.cu", "rac_api.cu"]
+SOURCES = ["conv_tc.cu", "conv_tc2.cu", "conv_tc_mc.cu", "conv_halo.cu", "first_conv_tc.cu", "misc_kernels.cu", "cem_kernels.cu", "train_kernels.cu", "train_gn_kernels.cu", "norm_lstm.cu", "metric_kernels.cu", "data_kernels.cu", "rac_api.cu"]
 HEADERS = ["conv.cuh", "epilogue.cuh", "ptx.cuh", "misc_kernels.cuh", "train_kernels.cuh", "rac_train.inc.cu", os.path.join("..", "..", "include", "racb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared"]

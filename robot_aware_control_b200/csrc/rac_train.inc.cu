@@ -52,6 +52,7 @@ struct Tape {  // everything the backward pass of one time step needs
   bf16* hs[3][2];
   float* cs[3][2];
   float* gates[3][2];
+  float *raw_ih[3][2], *raw_hh[3][2], *c_raw[3][2], *gn_stats[3][2];  // lstm_group_norm only
   bf16 *d2a, *d2b, *d3a, *d3b, *d4a, *d5;
   bf16 *dcat5, *dcat4, *dcat3;  // decoder concat buffers: == cat* unless fixed_skip and t > 0
   VggRt vgg[19];
@@ -64,7 +65,11 @@ struct Tape {  // everything the backward pass of one time step needs
 
 struct TrainState {
   rac_train_config cfg{};
-  TLayer L[RAC_L_COUNT];
+  TLayer L[RAC_L_COUNT_GN];
+  int nlayers = RAC_L_COUNT;  // RAC_L_COUNT_GN with lstm_group_norm (separate ih / hh gate convolutions)
+  bool gn = false;
+  float* gn_dy = nullptr;     // [M3, 4g] gate pre-activation gradients of the cell being processed
+  float* gn_part = nullptr;   // [B][14 g] per-sample partials of the GroupNorm affine gradients
   float *params = nullptr, *buffers = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr;
   float* wfirst = nullptr;  // [9*cin][64]
   float* zero64 = nullptr;
@@ -236,7 +241,71 @@ int vgg_backward(rac_handle* h, TrainState* T, VggRt& rt, const VggDef& d, const
 const int kLstm0[3] = {RAC_L_PRIOR_LSTM0, RAC_L_POST_LSTM0, RAC_L_FP_LSTM0};
 const int kLstm1[3] = {RAC_L_PRIOR_LSTM1, RAC_L_POST_LSTM1, RAC_L_FP_LSTM1};
 
+const int kLstmHH[3] = {RAC_L_PRIOR_LSTM0_HH, RAC_L_POST_LSTM0_HH, RAC_L_FP_LSTM0_HH};  // + layer
+
+GnCellArgs gn_args(rac_handle* h, TrainState* T, int s, int l, int t) {
+  const int B = T->cfg.batch, g = h->cfg.g_dim;
+  Tape& tp = T->tape[t];
+  const TLayer& Li = T->L[l == 0 ? kLstm0[s] : kLstm1[s]];
+  const TLayer& Lh = T->L[kLstmHH[s] + l];
+  GnCellArgs a{};
+  a.raw_ih = tp.raw_ih[s][l]; a.raw_hh = tp.raw_hh[s][l]; a.params = T->params;
+  a.g_ih = Li.d.gamma_off; a.b_ih = Li.d.beta_off; a.g_hh = Lh.d.gamma_off; a.b_hh = Lh.d.beta_off;
+  a.g_c = Li.d.cnorm_gamma_off; a.b_c = Li.d.cnorm_beta_off;
+  a.c_prev = t > 0 ? T->tape[t - 1].cs[s][l] : T->czero;
+  a.gates = tp.gates[s][l]; a.c_raw = tp.c_raw[s][l]; a.c_out = tp.cs[s][l]; a.h_out = tp.hs[s][l];
+  a.stats = tp.gn_stats[s][l];
+  a.B = B; a.P = 48; a.hid = g;
+  return a;
+}
+
+// NormConvLSTMCell stack (lstm.py:151-198): two plain convolutions per cell, then the GroupNorm + cell kernel
+int lstm_forward_gn(rac_handle* h, TrainState* T, int s, int t, const bf16* xin, cudaStream_t st) {
+  const int B = T->cfg.batch, g = h->cfg.g_dim;
+  Tape& tp = T->tape[t];
+  const bf16* x = xin;
+  for (int l = 0; l < 2; ++l) {
+    const bf16* hprev = t > 0 ? T->tape[t - 1].hs[s][l] : T->hzero;
+    const int ks = l == 0 ? 5 : 3;
+    const int ids[2] = {l == 0 ? kLstm0[s] : kLstm1[s], kLstmHH[s] + l};
+    const bf16* in[2] = {x, hprev};
+    float* out[2] = {tp.raw_ih[s][l], tp.raw_hh[s][l]};
+    for (int k = 0; k < 2; ++k) {
+      const TLayer& L = T->L[ids[k]];
+      EpiParams e{};
+      e.bias = L.bias; e.cout = L.n_packed; e.nseg = 1;
+      e.seg[0] = {0, L.n_packed, out[k], 4 * g, 0, 0};
+      CKR(t_gemm(h, k == 0 ? "train.lstm.ih.fwd" : "train.lstm.hh.fwd", {B, 6, 8, ks, false}, {{in[k], g}}, L.wp,
+                 ks * ks * g, L.n_packed, pick_bn(L.n_packed), EPI_F32, e, st));
+    }
+    CK(launch_gn_cell_fwd(gn_args(h, T, s, l, t), st));
+    x = tp.hs[s][l];
+  }
+  return RAC_OK;
+}
+
+int lstm_backward_gn(rac_handle* h, TrainState* T, int s, int t, const bf16* xin, float* g_in, int cur, cudaStream_t st) {
+  const int g = h->cfg.g_dim;
+  Tape& tp = T->tape[t];
+  for (int l = 1; l >= 0; --l) {
+    GnCellArgs a = gn_args(h, T, s, l, t);
+    a.dh = T->G_hs[s][l][cur]; a.dc = T->G_dc[s][l]; a.dy = T->gn_dy; a.d_ih = T->dy_a; a.d_hh = T->dy_b;
+    a.part = T->gn_part;
+    CK(launch_gn_cell_bwd(a, T->grads, st));
+    const bf16* x = l == 0 ? xin : tp.hs[s][0];
+    const bf16* hprev = t > 0 ? T->tape[t - 1].hs[s][l] : T->hzero;
+    // input: layer 1 feeds layer 0's dh (+=), layer 0 feeds the stack input (=)
+    F32Seg seg = {0, g, l == 1 ? T->G_hs[s][0][cur] : g_in, g, 0, l == 1 ? 1 : 0};
+    CKR(conv_backward(h, T, l == 0 ? kLstm0[s] : kLstm1[s], 6, 8, {{x, g}}, T->dy_a, &seg, 1, st));
+    // h_prev: the same layer at step t-1 (first writer of that buffer for this step); nothing before the first step
+    F32Seg segh = {0, g, t > 0 ? T->G_hs[s][l][cur ^ 1] : nullptr, g, 0, 0};
+    CKR(conv_backward(h, T, kLstmHH[s] + l, 6, 8, {{hprev, g}}, T->dy_b, &segh, t > 0 ? 1 : 0, st));
+  }
+  return RAC_OK;
+}
+
 int lstm_forward(rac_handle* h, TrainState* T, int s, int t, const bf16* xin, cudaStream_t st) {
+  if (T->gn) return lstm_forward_gn(h, T, s, t, xin, st);
   const int B = T->cfg.batch, g = h->cfg.g_dim;
   Tape& tp = T->tape[t];
   const bf16* x = xin;
@@ -258,6 +327,7 @@ int lstm_forward(rac_handle* h, TrainState* T, int s, int t, const bf16* xin, cu
 
 // backward of one ConvLSTM stack at step t; the gradient w.r.t. the stack input lands in `g_in` (=)
 int lstm_backward(rac_handle* h, TrainState* T, int s, int t, const bf16* xin, float* g_in, int cur, cudaStream_t st) {
+  if (T->gn) return lstm_backward_gn(h, T, s, t, xin, g_in, cur, st);
   const int B = T->cfg.batch, g = h->cfg.g_dim, M = B * 48;
   Tape& tp = T->tape[t];
   for (int l = 1; l >= 0; --l) {
@@ -541,18 +611,19 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
   if (cfg->batch < 1 || cfg->steps < 1 || (cfg->batch * 48) % 64 != 0)
     return fail(h, RAC_ERR_INVALID, "training batch must be a positive multiple of 4 (rows per map must be 64-aligned)");
   if (h->cfg.g_dim % 128 != 0) return fail(h, RAC_ERR_INVALID, "training needs g_dim %% 128 == 0");
-  if (h->cfg.lstm_group_norm) return fail(h, RAC_ERR_UNSUPPORTED, "training with lstm_group_norm is not implemented (inference only)");
   train_free(h);
   TrainState* T = new TrainState();
   h->train = T;
   T->cfg = *cfg;
   T->params = params; T->buffers = buffers; T->grads = grads; T->m = adam_m; T->v = adam_v;
   if (const char* dk = getenv("RAC_TRAIN_DEBUG_KEEP")) T->dbg_keep = atoi(dk);
+  T->gn = h->cfg.lstm_group_norm != 0;
+  T->nlayers = T->gn ? RAC_L_COUNT_GN : RAC_L_COUNT;
   const int B = cfg->batch, S = cfg->steps, g = h->cfg.g_dim, z = h->cfg.z_dim;
   const size_t M0 = static_cast<size_t>(B) * 3072, M1 = static_cast<size_t>(B) * 768, M2 = static_cast<size_t>(B) * 192,
                M3 = static_cast<size_t>(B) * 48;
   T->M[0] = static_cast<int>(M0); T->M[1] = static_cast<int>(M1); T->M[2] = static_cast<int>(M2); T->M[3] = static_cast<int>(M3);
-  for (int i = 0; i < RAC_L_COUNT; ++i) {
+  for (int i = 0; i < T->nlayers; ++i) {
     TLayer& L = T->L[i];
     L.d = layers[i];
     const LayerSpec& sp = h->spec[i];
@@ -571,7 +642,7 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
   for (int pass = 0; pass < 2; ++pass) {
     Bump bp;
     bp.base = pass ? static_cast<char*>(T->arena) : nullptr;
-    for (int i = 1; i < RAC_L_COUNT; ++i) {
+    for (int i = 1; i < T->nlayers; ++i) {
       TLayer& L = T->L[i];
       L.wp = bp.take<bf16>(static_cast<size_t>(L.n_packed) * L.taps * L.ctot);
       {
@@ -601,6 +672,10 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
           tp.hs[s][l] = bp.take<bf16>(M3 * g);
           tp.cs[s][l] = bp.take<float>(M3 * g);
           tp.gates[s][l] = bp.take<float>(M3 * 4 * g);
+          if (T->gn) {
+            tp.raw_ih[s][l] = bp.take<float>(M3 * 4 * g); tp.raw_hh[s][l] = bp.take<float>(M3 * 4 * g);
+            tp.c_raw[s][l] = bp.take<float>(M3 * g); tp.gn_stats[s][l] = bp.take<float>(static_cast<size_t>(B) * 96);
+          }
         }
       tp.d2a = bp.take<bf16>(M3 * 512); tp.d2b = bp.take<bf16>(M3 * 512); tp.d3a = bp.take<bf16>(M2 * 256);
       tp.d3b = bp.take<bf16>(M2 * 256); tp.d4a = bp.take<bf16>(M1 * 128); tp.d5 = bp.take<bf16>(M0 * 64);
@@ -644,6 +719,10 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
     T->G_img[0] = bp.take<float>(M0 * 3); T->G_img[1] = bp.take<float>(M0 * 3);
     T->dbg_draw32 = bp.take<float>(M0 * 64);
     T->loss_part = bp.take<float>(B); T->kl_tmp = bp.take<float>(4);
+    if (T->gn) {
+      T->gn_dy = bp.take<float>(M3 * 4 * g);
+      T->gn_part = bp.take<float>(static_cast<size_t>(B) * 14 * g);
+    }
     if (!pass) {
       CK(cudaMalloc(&T->arena, bp.off + 1024));
       CK(cudaMemset(T->arena, 0, bp.off + 1024));
@@ -670,7 +749,7 @@ int rac_train_forward_backward(rac_handle* h, const rac_train_batch* bt, void* s
   const int B = T->cfg.batch, S = T->cfg.steps, g = c.g_dim, z = c.z_dim;
   const size_t M3 = static_cast<size_t>(B) * 48;
   // ---- parameters -> packed bf16 operands (forward + dgrad), packed biases; zero the gradient accumulators
-  for (int i = 1; i < RAC_L_COUNT; ++i) {
+  for (int i = 1; i < T->nlayers; ++i) {
     TLayer& L = T->L[i];
     CK(launch_pack_weights(T->params, L.d.row_off, L.d.col_off, L.n_packed, L.taps, L.ctot, L.d.flip, L.wp, st));
     CK(launch_transpose_flip(L.wp, L.n_packed, L.taps, L.ctot, L.kpad, L.wd, st));
@@ -703,7 +782,7 @@ int rac_train_forward_backward(rac_handle* h, const rac_train_batch* bt, void* s
     cur ^= 1;
   }
   // ---- packed weight gradients -> flat parameter layout
-  for (int i = 1; i < RAC_L_COUNT; ++i) {
+  for (int i = 1; i < T->nlayers; ++i) {
     TLayer& L = T->L[i];
     CK(launch_unpack_grads(L.dwp, L.d.row_off, L.d.col_off, L.n_packed, L.taps, L.ctot, L.d.flip, T->grads, st));
   }

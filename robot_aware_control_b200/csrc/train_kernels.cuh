@@ -41,6 +41,32 @@ cudaError_t launch_bn_bwd(const float* dy, int dy_cstride, int dy_coff, int upsa
                           int W, int C, float* scratch /* [2*C] */, __nv_bfloat16* draw, float* draw_f32_or_null,
                           float* dgamma, float* dbeta, cudaStream_t s);
 
+// ---- NormConvLSTMCell (cfg.lstm_group_norm), pointwise + GroupNorm part: train_gn_kernels.cu
+struct GnCellArgs {
+  const float* raw_ih;  // [B * P, 4 * hid] fp32 convolution outputs (bias included), packed columns (channel, gate)
+  const float* raw_hh;
+  const float* params;  // flat parameter buffer; the six affine vectors in the reference's order
+  long long g_ih, b_ih, g_hh, b_hh;  // GroupNorm(16, 4 * hid) weight / bias of ih_gates.1 and hh_gates.1 (gate * hid + ch)
+  long long g_c, b_c;                // c_norm weight / bias (ch)
+  const float* c_prev;  // [B * P, hid] normalised cell of the previous step (zeros at the first)
+  float* gates;         // [B * P, 4 * hid] post-activation (i, f, o, g)
+  float* c_raw;         // [B * P, hid] cell before c_norm
+  float* c_out;         // [B * P, hid] normalised cell
+  __nv_bfloat16* h_out; // [B * P, hid]
+  float* stats;         // [B][48][2] mean / rstd of the 32 gate groups and 16 cell groups
+  // backward only
+  const float* dh;      // [B * P, hid] gradient w.r.t. h
+  float* dc;            // [B * P, hid] in: gradient w.r.t. c_out from the later step; out: w.r.t. c_prev
+  float* dy;            // scratch [B * P, 4 * hid] gradient w.r.t. the gate pre-activations
+  __nv_bfloat16* d_ih;  // [B * P, 4 * hid] gradient w.r.t. raw_ih (GEMM operand of the ih convolution's backward)
+  __nv_bfloat16* d_hh;
+  float* part;          // scratch [B][14 * hid] per-sample partial sums of the affine-parameter gradients
+  int B, P, hid;
+};
+cudaError_t launch_gn_cell_fwd(const GnCellArgs& a, cudaStream_t s);
+// also adds the affine-parameter gradients to `grads` (flat, same offsets as `params`)
+cudaError_t launch_gn_cell_bwd(const GnCellArgs& a, float* grads, cudaStream_t s);
+
 // ---- ConvLSTM cell backward (elementwise). gates: saved post-activation (i,f,o,g) interleaved [M, 4*hid];
 // dgates: bf16 [M, 4*hid] w.r.t. the gate pre-activations; dc is updated in place (dc_next -> dc_prev).
 cudaError_t launch_lstm_bwd(const float* dh, float* dc, const float* gates, const float* c_prev_or_null,

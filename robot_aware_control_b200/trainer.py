@@ -14,7 +14,8 @@ flat gradient buffer is all-reduced (NCCL) and averaged before the Adam update, 
 
 Scheduled sampling follows the reference (same probability schedule, same global numpy generator); when the model's
 own prediction is fed back, its gradient flows into the previous step as in the reference (`x_pred.clone()`).
-Limits (raise): heatmaps, multiview, movement weighting, lstm_group_norm.
+`cfg.lstm_group_norm` (NormConvLSTMCell, the cell of the authors' deployed checkpoints) trains as well.
+Limits (raise): heatmaps, multiview, movement weighting.
 """
 import ctypes as C
 
@@ -72,7 +73,18 @@ def _layer_tables(model, offsets, boffsets):
     gate_cols = [gate * g + ch for ch in range(g) for gate in range(4)]
     for tag, prefix in (("PRIOR", "prior"), ("POST", "posterior"), ("FP", "frame_predictor")):
         for layer in (0, 1):
-            out[f"{tag}_LSTM{layer}"] = conv_entry(f"{prefix}.lstm.{layer}.gates", [(g, g), (g, g)], gate_cols, rup(4 * g, 128))
+            p = f"{prefix}.lstm.{layer}"
+            if not c.lstm_group_norm:
+                out[f"{tag}_LSTM{layer}"] = conv_entry(f"{p}.gates", [(g, g), (g, g)], gate_cols, rup(4 * g, 128))
+                continue
+            # NormConvLSTMCell (lstm.py:151-198): separate ih / hh convolutions, each followed by GroupNorm(16, 4g)
+            # (its affine offsets ride in gamma_off / beta_off), and the cell's c_norm on the ih entry
+            ih = conv_entry(f"{p}.ih_gates.0", [(g, g)], gate_cols, rup(4 * g, 128))
+            ih.update(gamma_off=offsets[f"{p}.ih_gates.1.weight"], beta_off=offsets[f"{p}.ih_gates.1.bias"],
+                      cnorm_gamma_off=offsets[f"{p}.c_norm.weight"], cnorm_beta_off=offsets[f"{p}.c_norm.bias"])
+            hh = conv_entry(f"{p}.hh_gates.0", [(g, g)], gate_cols, rup(4 * g, 128))
+            hh.update(gamma_off=offsets[f"{p}.hh_gates.1.weight"], beta_off=offsets[f"{p}.hh_gates.1.bias"])
+            out[f"{tag}_LSTM{layer}"], out[f"{tag}_LSTM{layer}_HH"] = ih, hh
     for tag, prefix in (("PRIOR", "prior"), ("POST", "posterior")):
         wm, wl = offsets[f"{prefix}.mu_net.weight"], offsets[f"{prefix}.logvar_net.weight"]
         bm, bl = offsets[f"{prefix}.mu_net.bias"], offsets[f"{prefix}.logvar_net.bias"]
@@ -97,7 +109,8 @@ def _layer_tables(model, offsets, boffsets):
 class RacTrainLayer(C.Structure):
     _fields_ = [("row_off", C.c_void_p), ("col_off", C.c_void_p), ("bias_off", C.c_void_p),
                 ("gamma_off", C.c_longlong), ("beta_off", C.c_longlong), ("rmean_off", C.c_longlong),
-                ("rvar_off", C.c_longlong), ("w_off", C.c_longlong), ("flip", C.c_int)]
+                ("rvar_off", C.c_longlong), ("w_off", C.c_longlong), ("flip", C.c_int),
+                ("cnorm_gamma_off", C.c_longlong), ("cnorm_beta_off", C.c_longlong)]
 
 
 class RacTrainConfig(C.Structure):
@@ -178,8 +191,6 @@ class SVGTrainer:
         if kind not in ("l1", "dontcare_l1"):
             raise NotImplementedError(f"reconstruction_loss {kind!r}: the B200 path implements l1 and dontcare_l1")
         self._fixed_skip = int(not c.last_frame_skip)
-        if c.lstm_group_norm:
-            raise NotImplementedError("lstm_group_norm is implemented for inference / planning only")
         self.process_group = process_group
         self.allreduce_events = None
         self._lib = _lib.load()
@@ -214,8 +225,9 @@ class SVGTrainer:
         self.losses = torch.zeros(4, device=dev)
         self._tables = _layer_tables(model, self._offsets, self._boffsets)
         self._keep = []  # device index arrays referenced by the library
-        layers = (RacTrainLayer * len(pack.LAYER_IDS))()
-        for i, name in enumerate(pack.LAYER_IDS):
+        names = pack.LAYER_IDS + (pack.GN_LAYER_IDS if c.lstm_group_norm else [])
+        layers = (RacTrainLayer * len(names))()
+        for i, name in enumerate(names):
             t = self._tables[name]
             ro = torch.tensor(t["row_off"], dtype=torch.int64, device=dev)
             co = torch.tensor(t["col_off"], dtype=torch.int32, device=dev)
@@ -225,7 +237,7 @@ class SVGTrainer:
                 bo = torch.tensor(t["bias_off"], dtype=torch.int64, device=dev)
                 self._keep.append(bo)
                 layers[i].bias_off = bo.data_ptr()
-            for f in ("gamma_off", "beta_off", "rmean_off", "rvar_off"):
+            for f in ("gamma_off", "beta_off", "rmean_off", "rvar_off", "cnorm_gamma_off", "cnorm_beta_off"):
                 setattr(layers[i], f, t.get(f, -1))
             layers[i].w_off = t["w_off"]
             layers[i].flip = t["flip"]

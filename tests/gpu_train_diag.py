@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE -- per-parameter comparison of the CUDA training step with the CPU training oracle on a B200:
-python -m tests.gpu_train_diag [vanilla|ra] [simt|tc]"""
+python -m tests.gpu_train_diag [vanilla|ra|ra_gn] [simt|tc]"""
 import sys
 
 import numpy as np
@@ -19,14 +19,14 @@ def setup(tag, impl="tc", lr=1e-3, beta=1e-2):
     else:
         cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, model_use_mask=True, model_use_future_mask=True,
                           model_use_robot_state=True, reconstruction_loss="dontcare_l1", reward_type="dontcare",
-                          lr=lr, beta=beta, beta1=0.9, n_future=3, n_past=1)
+                          lstm_group_norm=tag.endswith("_gn"), lr=lr, beta=beta, beta1=0.9, n_future=3, n_past=1)
     sd = so.make_state_dict(cfg, 17)
     model = SVGConvModel(cfg, conv_impl=1 if impl == "simt" else 0)
     model.load_state_dict(sd)
     model.train()
     trainer = SVGTrainer(cfg, model)
     oracle = TrainOracle(cfg, sd, lr=lr, beta=beta)
-    batch, eps_p, eps_q = make_batch(23, cfg, tag == "ra")
+    batch, eps_p, eps_q = make_batch(23, cfg, tag != "vanilla")
     return cfg, model, trainer, oracle, batch, eps_p, eps_q
 
 
@@ -47,7 +47,7 @@ def main():
         rel = float((g - r).norm() / (r.norm() + 1e-12))
         cos = float((g * r).sum() / (g.norm() * r.norm() + 1e-20))
         worst.append((rel, k, float(r.norm()), float(g.norm()), cos))
-    for rel, k, rn, gn, cos in sorted(worst, reverse=True)[::3]:
+    for rel, k, rn, gn, cos in sorted(worst, reverse=True)[::(1 if tag.endswith("_gn") else 3)]:
         print(f"{k:45s} rel_err {rel:9.4f}  |ref| {rn:10.4e} |gpu| {gn:10.4e} cos {cos:7.4f}")
     rels = np.array([w[0] for w in worst])
     print("median rel err", np.median(rels), "max", rels.max(), "n", len(rels))

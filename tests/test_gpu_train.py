@@ -37,7 +37,8 @@ def _setup(tag, n_future, lr=1e-3, beta=1e-2):
         cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, **kw)
     else:
         cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, model_use_mask=True, model_use_future_mask=True,
-                          model_use_robot_state=True, reconstruction_loss="dontcare_l1", reward_type="dontcare", **kw)
+                          model_use_robot_state=True, reconstruction_loss="dontcare_l1", reward_type="dontcare",
+                          lstm_group_norm=tag.endswith("_gn"), **kw)  # "..._gn": NormConvLSTMCell (lstm.py:151-198)
     sd = so.make_state_dict(cfg, 17)
     model = SVGConvModel(cfg)
     model.load_state_dict(sd)
@@ -53,7 +54,7 @@ def _rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-20))
 
 
-@pytest.mark.parametrize("tag", ["vanilla", "ra", "ra_sampled", "ra_fixedskip", "vanilla_fixedskip_sampled"])
+@pytest.mark.parametrize("tag", ["vanilla", "ra", "ra_sampled", "ra_fixedskip", "vanilla_fixedskip_sampled", "ra_gn"])
 def test_train_step_losses_smooth_grads_adam(golden_dir, tag):
     gold = np.load(os.path.join(golden_dir, f"train_{tag}.npz"))
     cfg, sd, model, trainer, batch, ep, eq = _setup(tag, 3)
@@ -73,7 +74,9 @@ def test_train_step_losses_smooth_grads_adam(golden_dir, tag):
     for k in oracle.param_keys:
         g = trainer.grad_of(k).cpu()
         if (k.startswith("prior.") or k.startswith("prior_input_conv")) and tokens is None:
-            assert _rel(g, ref[k]) < 2e-2, (k, _rel(g, ref[k]))  # (with sampled frames the prior input is chaotic too)
+            # (with sampled frames the prior input is chaotic too; the GroupNorm cells divide by per-sample statistics
+            # of bf16-rounded activations: more rounding noise on the same smooth path, measured 1-6 %, cos >= 0.998)
+            assert _rel(g, ref[k]) < (8e-2 if tag.endswith("_gn") else 2e-2), (k, _rel(g, ref[k]))
         # global sanity for every tensor: right scale and direction (chaos-limited, see module docstring)
         cos = float((g * ref[k]).sum() / (g.norm() * ref[k].norm() + 1e-30))
         assert cos > 0.85 and 0.8 < float(g.norm() / ref[k].norm()) < 1.25, (k, cos)

@@ -223,3 +223,62 @@ def test_adam_state_dict_round_trip_with_torch_adam():
     bad["param_groups"][0]["amsgrad"] = True
     with pytest.raises(NotImplementedError):
         load_adam_state_dict(bad, m, v, layout)
+
+
+@pytest.mark.parametrize("group_norm", [False, True])
+def test_trainer_layer_tables_rebuild_the_packed_operands(group_norm):
+    """The training step re-packs the weights on the device from per-layer offset tables (trainer._layer_tables ->
+    pack_weights_kernel). Emulated here on CPU: tables + flat parameter vector must give pack.py's operands for every
+    layer without BatchNorm folding (input convs, LSTM gates incl. the ih / hh split of lstm_group_norm, gaussian
+    heads, the final ConvTranspose) and the packed biases."""
+    from types import SimpleNamespace
+
+    from robot_aware_control_b200 import model as M
+    from robot_aware_control_b200 import pack
+    from robot_aware_control_b200.config import svg_config_from
+    from robot_aware_control_b200.trainer import _layer_tables
+
+    cfg = so.make_cfg(g_dim=128, z_dim=10, model_use_mask=True, model_use_robot_state=True, lstm_group_norm=group_norm)
+    c = svg_config_from(cfg)
+    sd = so.make_state_dict(cfg, 4)
+    spec = M._spec(c)
+    offsets, boffsets, n, nb = {}, {}, 0, 0
+    for k, (shape, kind) in spec.items():
+        if kind.startswith("buf"):
+            if kind != "buf_long":
+                boffsets[k] = nb
+                nb += int(np.prod(shape))
+        else:
+            offsets[k] = n
+            n += int(np.prod(shape))
+    flat = torch.zeros(n)
+    for k, o in offsets.items():
+        flat[o:o + sd[k].numel()] = sd[k].reshape(-1).float()
+    tables = _layer_tables(SimpleNamespace(_c=c, state_dict=lambda: sd), offsets, boffsets)
+    packed = pack.pack_state_dict(sd, cfg)
+    names = [k for k in packed if not (k.startswith("ENC_") or (k.startswith("DEC_") and k != "DEC_UPC5_1"))]
+    assert any(k.endswith("_HH") for k in names) == group_norm
+    for name in names:
+        t = tables[name]
+        w_ref, b_ref = packed[name]
+        n_packed = w_ref.shape[0]
+        ctot = len(t["col_off"])
+        taps = w_ref.shape[1] // ctot
+        ro = torch.tensor(t["row_off"])
+        co = torch.tensor(t["col_off"])
+        assert len(ro) == n_packed
+        idx = ro[:, None, None] + co[None, None, :] + torch.arange(taps)[None, :, None]
+        valid = (ro[:, None, None] >= 0) & (co[None, None, :] >= 0)
+        w = torch.where(valid, flat[idx.clamp(min=0)], torch.zeros(()))
+        if t["flip"]:
+            w = w.flip(1)
+        assert torch.equal(w.reshape(n_packed, taps * ctot).to(torch.bfloat16), w_ref.to(torch.bfloat16)), name
+        bo = torch.tensor(t["bias_off"])
+        b = torch.where(bo >= 0, flat[bo.clamp(min=0)], torch.zeros(()))
+        assert torch.equal(b, b_ref.float()), name
+        if group_norm and "LSTM" in name:
+            p = {"PRIOR": "prior", "POST": "posterior", "FP": "frame_predictor"}[name.split("_")[0]] + f".lstm.{name[name.index('LSTM') + 4]}"
+            gk = "hh_gates" if name.endswith("_HH") else "ih_gates"
+            assert t["gamma_off"] == offsets[f"{p}.{gk}.1.weight"] and t["beta_off"] == offsets[f"{p}.{gk}.1.bias"]
+            if not name.endswith("_HH"):
+                assert t["cnorm_gamma_off"] == offsets[f"{p}.c_norm.weight"] and t["cnorm_beta_off"] == offsets[f"{p}.c_norm.bias"]
