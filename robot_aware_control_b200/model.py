@@ -6,7 +6,7 @@ trainer.py:829-837) loads with `load_state_dict`. The arithmetic is done by libr
 into bf16 weights, tcgen05 implicit-GEMM convolutions with fused LSTM / z-sample / sigmoid epilogues.
 
 Not supported (raises): train-mode forward (batch-statistics BatchNorm + backward are not part of this round),
-heatmaps. lstm_group_norm=True (NormConvLSTMCell, lstm.py:151-198) is supported for inference / planning.
+heatmaps. lstm_group_norm=True (NormConvLSTMCell, lstm.py:151-198) is supported (training: SVGTrainer).
 """
 import ctypes as C
 from collections import OrderedDict
