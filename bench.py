@@ -238,6 +238,8 @@ def run_train_bench(args):
     ra = args.robot_aware
     kw = dict(lr=1e-4, beta=1e-4, beta1=0.9, n_future=5, n_past=1, robot_pixel_weight=0.0,
               scheduled_sampling=bool(args.scheduled_sampling), scheduled_sampling_k=4000)
+    if args.group_norm:  # NormConvLSTMCell, the cell of the authors' deployed checkpoints (lstm.py:151-198)
+        kw["lstm_group_norm"] = True
     np.random.seed(0)  # the reference draws the scheduled-sampling decisions from the global numpy generator
     if ra:
         cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, action_dim=A_DIM, model_use_mask=True, model_use_future_mask=True,
@@ -295,6 +297,7 @@ def run_train_bench(args):
             "config": {"workload": f"SVG training step, batch {Bt}/GPU, n_past 1 / n_future 5, g_dim {G_DIM} z_dim {Z_DIM}, "
                                    + ("dontcare_l1 robot-aware (mask + future mask + robot state)" if ra else "l1 vanilla")
                                    + (", scheduled sampling k=4000" if args.scheduled_sampling else "")
+                                   + (", lstm_group_norm" if args.group_norm else "")
                                    + ", Adam, data parallel (flat fp32 gradient all-reduce over NCCL)",
                        "algorithmic_tflop_per_step_per_gpu": 6.52},
             "achieved_tflops_per_gpu": 6.52 / (per * 1e-3), "last_losses": loss,
@@ -328,6 +331,8 @@ def main():
     ap.add_argument("--train", action="store_true",
                     help="BASELINE configs[0]/[3]: SVG training step (batch 16 per GPU, n_past 1 / n_future 5), "
                          "forward + BPTT backward + Adam; data parallel over --gpus")
+    ap.add_argument("--group-norm", action="store_true",
+                    help="with --train: cfg.lstm_group_norm (NormConvLSTMCell); extra, not a BASELINE config")
     ap.add_argument("--scheduled-sampling", action="store_true",
                     help="with --train: cfg.scheduled_sampling (k = 4000, numpy seed 0), as BASELINE configs[3]")
     ap.add_argument("--robot-aware", action="store_true",
