@@ -141,6 +141,24 @@ def make_state_dict(cfg, seed=0):
     return sd
 
 
+def trained_like(sd, gate_scale0=6.0, gate_scale1=12.0, head_scale=8.0):
+    """A "trained-like" variant of a synthetic state dict (SURVEY.md 8(d) caveat: random init is the forgiving case --
+    gate pre-activations of std 0.5-1 and a decoder head that outputs a nearly flat 0.5 +- 0.02 image). The ConvLSTM gate
+    weights are scaled so that the pre-activations have magnitude ~3-5 (saturating sigmoids / tanh, sharp gates) and
+    the final ConvTranspose is scaled so that predicted pixels and the compositing mask span a real range. A
+    deterministic transform of make_state_dict's output: the reference and the CUDA path both load the result."""
+    out = OrderedDict()
+    for k, v in sd.items():
+        if ".lstm.0.gates." in k:
+            v = v * gate_scale0
+        elif ".lstm.1.gates." in k:
+            v = v * gate_scale1
+        elif k == "decoder.upc5.1.weight":
+            v = v * head_scale
+        out[k] = v
+    return out
+
+
 # --------------------------------------------------------------------------------------------- model
 class SVGOracle:
     """Functional fp32 restatement of SVGConvModel in eval mode (dynamics.py:457-644)."""

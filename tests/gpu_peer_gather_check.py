@@ -40,11 +40,44 @@ def main():
     np.testing.assert_array_equal(out["0"][0], out["1"][0])
     np.testing.assert_array_equal(out["0"][1], out["1"][1])
     np.testing.assert_array_equal(out["0"][2], out["1"][2])
+    # sharded == unsharded: the same plan with every candidate on this GPU (process_group=None -> one rac_cem_plan
+    # call), same seed: Philox z noise and action noise are keyed on the GLOBAL candidate id, so costs, elites and the
+    # refit mean must be bit-equal to the R = 2 plan
+    torch.manual_seed(0)
+    single = CEMPolicy(cfg, model, horizon=4, opt_iter=4, action_candidates=301, topk=30, init_std=0.03,
+                       process_group=None, noise_source="philox")
+    single._seed = 1234
+    mean1 = single.get_action(start, goal, 0, 0)
+    np.testing.assert_array_equal(mean1, out["1"][0])
+    np.testing.assert_array_equal(single.last_costs.cpu().numpy(), out["1"][1])
+    np.testing.assert_array_equal(single.last_elite_idx.cpu().numpy(), out["1"][2])
+    # robot-aware model (configs[4]): precomputed per-candidate states / masks, sharded by pointer offset + time stride
+    cfg_ra = so.make_cfg(g_dim=128, z_dim=10, model_use_mask=True, model_use_future_mask=True, model_use_robot_state=True,
+                         reconstruction_loss="dontcare_l1", reward_type="dontcare")
+    model_ra = SVGConvModel(cfg_ra)
+    model_ra.load_state_dict(so.make_state_dict(cfg_ra, 1))
+    model_ra.eval()
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    N, L = 203, 3
+    states = torch.rand(L + 1, N, 5, device="cuda", generator=gen)
+    masks = (torch.rand(L + 1, N, 1, 48, 64, device="cuda", generator=gen) > 0.8).float()
+    goal_ra = DemoGoalState(imgs=goal.imgs, masks=[(rs.rand(1, 48, 64) > 0.8).astype(np.float32)])
+    res = []
+    for group in (dist.group.WORLD, None):
+        pol = CEMPolicy(cfg_ra, model_ra, horizon=L + 1, opt_iter=3, action_candidates=N, topk=20, init_std=0.03,
+                        process_group=group, noise_source="philox")
+        pol._seed = 99
+        pol.precomputed_robot = (states, masks)
+        mean = pol.get_action(start, goal_ra, 0, 0)
+        res.append((mean, pol.last_costs.cpu().numpy().copy(), pol.last_elite_idx.cpu().numpy().copy()))
+    for a, b in zip(res[0], res[1]):
+        np.testing.assert_array_equal(a, b)
     gathered = [None] * dist.get_world_size()
     dist.all_gather_object(gathered, out["1"][0].tolist())
     assert all(g == gathered[0] for g in gathered), "ranks disagree"
     if rank == 0:
         print("peer-memory cost exchange == NCCL all-gather: mean", out["1"][0][0], "(301 candidates, uneven shards)")
+        print("sharded plan (R = 2) == unsharded plan (R = 1): costs, elites, mean bit-equal (vanilla 301, robot-aware 203)")
     dist.destroy_process_group()
 
 
