@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RAC_ABI_VERSION 4
+#define RAC_ABI_VERSION 5
 
 typedef enum {
   RAC_OK = 0,
@@ -174,7 +174,41 @@ int rac_topk(const double* costs, int n, int k, int64_t* idx_out, double* val_ou
 int rac_cem_refit(const float* act2, int steps, const int64_t* elite_idx, int k, float std_floor, float* mean_out,
                   float* std_out, void* stream);
 
-/* Whole single-GPU plan: `iters` x (sample -> rollout+cost -> top-k -> refit), device resident. */
+/* ---- Robot state / mask producer: the device-side stand-in for
+ * `robot_model.predict_batch(data, thick=True)` of TrajectorySampler.generate_model_rollouts
+ * (trajectory_sampler.py:86-109), so that a robot-aware plan has no host round trip per CEM iteration.
+ *   states: planar end-effector integration of WX250sAnalyticalModel.predict_batch / predict_trajectory
+ *           (src/dataset/wx250s/wx250s_model.py:57-66,98-117,121-182) or FrankaAnalyticalModel.predict_batch
+ *           (src/dataset/franka/franka_model.py:30-80) with the reference's float32 / float64 mix: bit-equal.
+ *   masks:  the reference renders MuJoCo segmentation images of the arm meshes after an IK call (neither available
+ *           outside the authors' lab setup); here a capsule model of the arm is posed by closed-form planar IK and
+ *           rasterised through a pinhole camera. NOT reference-pinned (oracle: oracle/robot_oracle.py). Callers with
+ *           their own mask source keep passing `masks` to rac_rollout and use rac_predict_states alone. */
+enum { RAC_ROBOT_WX250S = 0, RAC_ROBOT_FRANKA = 1 };
+typedef struct {
+  int kind;               /* RAC_ROBOT_WX250S / RAC_ROBOT_FRANKA: which reference integration rule */
+  float low[5], high[5];  /* state normalisation bounds (trajectory_sampler.py:22-23) */
+  double frame_diff[2];   /* LOCO_WX250S_DIFF / LOCO_FRANKA_DIFF (src/utils/camera_calibration.py:176-177) */
+  double push_height;     /* WX250s: z of every predicted state (wx250s_model.py:65) */
+  /* capsule rasteriser (robot base frame, metres) */
+  float cam_center[3];    /* camera centre */
+  float cam_minv[9];      /* row-major 3x3: pixel (u, v, 1) of the H x W image -> ray direction, = (K R)^-1 */
+  float shoulder_z;       /* height of the shoulder joint above the base */
+  float l_upper, l_fore, l_wrist; /* link lengths: shoulder-elbow, elbow-wrist, wrist-finger tip */
+  float pitch;            /* gripper pitch (default_pitch of the controller), > 0 = pointing down */
+  float radius[4];        /* capsule radii: column, upper arm, forearm, wrist + gripper */
+} rac_robot_model;
+/* start_state: DEVICE (5) normalised start state (states[0, i] of the reference's `data`); actions (n, steps,
+ * action_dim); states_out (steps+1, *, 5) with `state_t_stride` elements between time steps. */
+int rac_predict_states(const rac_robot_model* m, const float* start_state, const float* actions, int n, int steps,
+                       int action_dim, float* states_out, int64_t state_t_stride, void* stream);
+/* states (steps+1, *, 5) normalised -> masks_out (steps+1, *, H, W) float {0,1}; extra_radius >= 0 thickens every
+ * capsule (the reference's thick=True masks). */
+int rac_render_masks(const rac_robot_model* m, const float* states, int64_t state_t_stride, int n, int steps, int H,
+                     int W, float extra_radius, float* masks_out, int64_t mask_t_stride, void* stream);
+
+/* Whole single-GPU plan: `iters` x (sample -> [robot states + masks] -> rollout+cost -> top-k -> refit), device
+ * resident. */
 typedef struct {
   int n;               /* action_candidates */
   int steps;           /* horizon - 1 */
@@ -185,6 +219,13 @@ typedef struct {
   float std_floor;     /* 0.001 */
   const float* noise;  /* (iters, n, steps, 2) standard normals or NULL -> Philox(seed) */
   rac_rollout rollout; /* template: actions / sum_cost / n / steps are filled by the library */
+  /* optional device-side robot model: when set, every iteration predicts the candidates' robot states (and, with
+   * robot_render_masks, their masks) from the sampled actions on the device and feeds them to the rollout;
+   * rollout.states / rollout.masks are then ignored (masks only when rendered here) */
+  const rac_robot_model* robot; /* HOST pointer or NULL */
+  const float* robot_start_state; /* DEVICE (5) normalised start state */
+  int robot_render_masks;
+  float robot_extra_radius;
 } rac_cem;
 int rac_cem_plan(rac_handle* h, const rac_cem* c, float* mean_out /* (steps,2) */, float* std_out /* (steps,2) */,
                  int64_t* elite_idx_out /* (topk) or NULL */, double* last_costs_out /* (n) or NULL */, void* stream);
@@ -198,6 +239,12 @@ int rac_masked_cost(const float* curr, const float* goal, const float* curr_mask
 int rac_l1_loss(const float* pred, const float* target, float* out, int64_t numel, void* stream);
 int rac_dontcare_l1_loss(const float* pred, const float* target, const float* mask, float robot_weight, float* out,
                          int n, int hw, void* stream);
+/* All four reconstruction criteria of PredictionTrainer._recon_loss (trainer.py:149-161; losses.py:11-50) in one entry:
+ * kind 0 = l1_criterion, 1 = dontcare_l1_criterion, 2 = mse_criterion (nn.MSELoss), 3 = dontcare_mse_criterion.
+ * mask (n,1,H,W) for the dontcare kinds; batch_weight (n) or NULL (the l1 kinds' movement weighting);
+ * per_sample: caller scratch of n floats (the per-sample terms, summed in index order); out = 1 fp32 scalar. */
+int rac_recon_loss(const float* pred, const float* target, const float* mask, const float* batch_weight, int kind,
+                   float robot_weight, float* per_sample, float* out, int n, int hw, void* stream);
 /* robot_mse_criterion / world_mse_criterion (losses.py:52-78): out2[0] += robot, out2[1] += world (accumulating). */
 int rac_robot_world_mse(const float* pred, const float* target, const float* mask, float* out2, int n, int hw,
                         void* stream);
@@ -269,7 +316,8 @@ typedef struct {
   float lr, beta1, beta2, adam_eps;
   float kl_beta;             /* cfg.beta */
   float robot_pixel_weight;  /* cfg.robot_pixel_weight */
-  int recon_kind;            /* 0 = l1, 1 = dontcare_l1 (cfg.reconstruction_loss) */
+  int recon_kind;            /* cfg.reconstruction_loss (trainer.py:149-161): 0 = l1, 1 = dontcare_l1, 2 = mse (the
+                                argparse default), 3 = dontcare_mse */
   int zero_robot;            /* "dontcare" in reconstruction_loss or black_robot_input */
   long long n_params, n_buffers;
   int fixed_skip;            /* 1 = cfg.last_frame_skip False (the config default, src/config/__init__.py:217-222): every
@@ -289,6 +337,11 @@ typedef struct {
                               are given) the logged robot_mse / world_mse metrics (trainer.py:436-439) */
   const int* true_token;   /* HOST int[steps] or NULL: 0 at step t >= 1 = feed the model's own previous prediction
                               (scheduled sampling, trainer.py:132-147,353-356); NULL = always the ground-truth frame */
+  unsigned long long noise_step; /* Philox counter base of the reparameterisation noise when eps_* are NULL: the
+                              caller's global training step (the "step" of the reference checkpoint, trainer.py:829-837),
+                              so that a resumed run or a re-created state never replays earlier noise */
+  const float* batch_weight; /* (B) or NULL: cfg.load_movement_info weighting of the l1 / dontcare_l1 loss
+                              (trainer.py:426-429; losses.py:13-19,35-50) */
 } rac_train_batch;
 
 int rac_train_create(rac_handle* h, const rac_train_config* cfg,

@@ -16,6 +16,7 @@ from oracle.make_golden import EpsFeeder, G_DIM, Z_DIM, synth_masks  # noqa: E40
 
 OUT = os.path.join(ROOT, "tests", "golden")
 B, T = 4, 4  # n_past 1 + n_future 3
+HIGH_MOVEMENT = torch.tensor([True, False, True, False])  # data["high_movement"] of the "ra_bw" case (trainer.py:426-429)
 
 
 def make_batch(seed, cfg, robot_aware):
@@ -51,10 +52,19 @@ def main():
                     ("ra_sampled", dict(robot_aware=True, future_mask=True)),
                     ("ra_fixedskip", dict(robot_aware=True, future_mask=True)),
                     ("vanilla_fixedskip_sampled", dict(robot_aware=False)),
-                    ("ra_gn", dict(robot_aware=True, future_mask=True))):
+                    ("ra_gn", dict(robot_aware=True, future_mask=True)),
+                    # the remaining cfg.reconstruction_loss kinds (trainer.py:149-161) and the movement weighting
+                    ("vanilla_mse", dict(robot_aware=False)), ("ra_dcmse", dict(robot_aware=True, future_mask=True)),
+                    ("ra_bw", dict(robot_aware=True, future_mask=True))):
         if only and tag not in only:
             continue
         extra = ("--n_future", str(T - 1), "--batch_size", str(B), "--lr", "1e-3", "--beta", "1e-2")
+        if tag == "vanilla_mse":
+            extra += ("--reconstruction_loss", "mse")
+        if tag == "ra_dcmse":
+            extra += ("--reconstruction_loss", "dontcare_mse", "--robot_pixel_weight", "0.25")
+        if tag == "ra_bw":
+            extra += ("--load_movement_info", "True", "--movement_weight", "3.0")
         if "fixedskip" in tag:  # the config default (src/config/__init__.py:217-222): decoder skips of the first frame
             extra += ("--last_frame_skip", "False")
         if tag.endswith("_gn"):  # NormConvLSTMCell (lstm.py:151-198), the cell of the authors' deployed checkpoints
@@ -76,6 +86,8 @@ def main():
         kw = dict(kw)
         batch, eps_p, eps_q = make_batch(23, cfg, kw["robot_aware"])
         batch_ref = dict(batch, qpos=torch.zeros(T, B, 6), robot=["sawyer"] * B, folder=["x"] * B)
+        if tag == "ra_bw":
+            batch_ref["high_movement"] = HIGH_MOVEMENT.clone()
         out = {}
         for step in range(2):
             feeder.queue = []

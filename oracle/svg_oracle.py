@@ -340,18 +340,36 @@ def img_dontcare_cost(curr, goal, curr_mask, goal_mask):
     return -dist.numpy()
 
 
-def l1_criterion(pred, target):
+def l1_criterion(pred, target, batch_weight=None):
     """losses.py:13-19."""
+    if batch_weight is not None:
+        return (batch_weight * (target - pred).abs().mean((1, 2, 3))).mean()
     return (target - pred).abs().mean()
 
 
-def dontcare_l1_criterion(pred, target, mask, robot_weight):
+def dontcare_l1_criterion(pred, target, mask, robot_weight, batch_weight=None):
     """losses.py:35-50 (3-channel world-pixel count, +1)."""
     m3 = mask.bool().expand(-1, 3, -1, -1)
     diff = target - pred
     diff = torch.where(m3, diff * robot_weight, diff)
     world = (~m3).sum((1, 2, 3)) + 1
+    if batch_weight is not None:
+        return (batch_weight * diff.abs().sum((1, 2, 3)) / world).mean()
     return (diff.abs().sum((1, 2, 3)) / world).mean()
+
+
+def mse_criterion(pred, target):
+    """nn.MSELoss() (losses.py:11)."""
+    return ((pred - target) ** 2).mean()
+
+
+def dontcare_mse_criterion(pred, target, mask, robot_weight):
+    """losses.py:21-33."""
+    m3 = mask.bool().expand(-1, 3, -1, -1)
+    diff = target - pred
+    diff = torch.where(m3, diff * robot_weight, diff)
+    world = (~m3).sum((1, 2, 3)) + 1
+    return ((diff ** 2).sum((1, 2, 3)) / world).mean()
 
 
 def robot_world_mse(pred, target, mask):

@@ -26,13 +26,17 @@ class TrainOracle:
         self.v = {k: torch.zeros_like(self.model.sd[k]) for k in self.param_keys}
         self.t = 0
 
-    def recon_loss(self, pred, target, mask):
-        """trainer.py:149-161."""
+    def recon_loss(self, pred, target, mask, batch_weight=None):
+        """trainer.py:149-161 (batch_weight reaches the two l1 criteria only, :426-431)."""
         kind = self.cfg.reconstruction_loss
         if kind == "l1":
-            return so.l1_criterion(pred, target)
+            return so.l1_criterion(pred, target, batch_weight)
         if kind == "dontcare_l1":
-            return so.dontcare_l1_criterion(pred, target, mask, self.robot_pixel_weight)
+            return so.dontcare_l1_criterion(pred, target, mask, self.robot_pixel_weight, batch_weight)
+        if kind == "mse":
+            return so.mse_criterion(pred, target)
+        if kind == "dontcare_mse":
+            return so.dontcare_mse_criterion(pred, target, mask, self.robot_pixel_weight)
         raise NotImplementedError(kind)
 
     def loss_and_grads(self, batch, eps_prior, eps_post, true_token=None):
@@ -70,7 +74,12 @@ class TrainOracle:
             x_pred = (1 - m_hat) * x_j + m_hat * rgb  # blends with the UN-blacked x_j (trainer.py:406-407)
             if i <= 1:  # n_past == 1
                 skip = curr_skip
-            vl = self.recon_loss(x_pred, x_i, m_i)
+            bw = None
+            if getattr(cfg, "load_movement_info", False):  # trainer.py:426-429
+                info_m = batch["high_movement"]
+                bw = (cfg.movement_weight * info_m).float()
+                bw[~info_m] = 1.0
+            vl = self.recon_loss(x_pred, x_i, m_i, bw)
             recon = recon + vl
             kl = so.kl_criterion(mu, logvar, mu_p, logvar_p, B)
             kld = kld + kl

@@ -9,7 +9,8 @@ from .state import State, DemoGoalState  # noqa: F401
 from .model import SVGConvModel  # noqa: F401
 from .losses import RobotWorldCost, ImgL2Cost, ImgDontcareCost, RobotL2Cost  # noqa: F401
 from .losses import l1_criterion, dontcare_l1_criterion, kl_criterion  # noqa: F401
-from .losses import robot_mse_criterion, world_mse_criterion  # noqa: F401
+from .losses import robot_mse_criterion, world_mse_criterion, mse_criterion, dontcare_mse_criterion  # noqa: F401
+from .robot import DeviceRobotModel  # noqa: F401
 from .metrics import psnr, ssim, world_psnr_criterion  # noqa: F401
 from .image import zero_robot_region  # noqa: F401
 from .cem import CEMPolicy, TrajectorySampler  # noqa: F401
@@ -21,4 +22,5 @@ __all__ = [
     "RobotL2Cost", "State", "DemoGoalState", "zero_robot_region", "l1_criterion", "dontcare_l1_criterion",
     "kl_criterion", "robot_mse_criterion", "world_mse_criterion", "svg_config_from", "SVGTrainer",
     "psnr", "ssim", "world_psnr_criterion", "process_batch", "preprocess_clips", "sample_augment",
+    "mse_criterion", "dontcare_mse_criterion", "DeviceRobotModel",
 ]

@@ -39,10 +39,21 @@ class RacRollout(C.Structure):
     ]
 
 
+class RacRobotModel(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int), ("low", C.c_float * 5), ("high", C.c_float * 5), ("frame_diff", C.c_double * 2),
+        ("push_height", C.c_double), ("cam_center", C.c_float * 3), ("cam_minv", C.c_float * 9),
+        ("shoulder_z", C.c_float), ("l_upper", C.c_float), ("l_fore", C.c_float), ("l_wrist", C.c_float),
+        ("pitch", C.c_float), ("radius", C.c_float * 4),
+    ]
+
+
 class RacCem(C.Structure):
     _fields_ = [
         ("n", C.c_int), ("steps", C.c_int), ("iters", C.c_int), ("topk", C.c_int), ("init_std", C.c_float),
         ("clamp", C.c_float), ("std_floor", C.c_float), ("noise", C.c_void_p), ("rollout", RacRollout),
+        ("robot", C.POINTER(RacRobotModel)), ("robot_start_state", C.c_void_p), ("robot_render_masks", C.c_int),
+        ("robot_extra_radius", C.c_float),
     ]
 
 
@@ -73,6 +84,12 @@ EXPORTS = {
     "rac_l1_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "rac_dontcare_l1_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int,
                                        C.c_void_p]),
+    "rac_recon_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p,
+                                 C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "rac_predict_states": (C.c_int, [C.POINTER(RacRobotModel), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_int64, C.c_void_p]),
+    "rac_render_masks": (C.c_int, [C.POINTER(RacRobotModel), C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_float, C.c_void_p, C.c_int64, C.c_void_p]),
     "rac_robot_world_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "rac_kl_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                               C.c_void_p]),

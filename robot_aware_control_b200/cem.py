@@ -17,6 +17,7 @@ import torch
 
 from . import _lib, parallel
 from .losses import RobotWorldCost
+from .robot import DeviceRobotModel, normalized_start_state
 from .state import DemoGoalState, State
 
 # frame offsets between robots (reference src/utils/camera_calibration.py:176-177)
@@ -78,9 +79,10 @@ class TrajectorySampler(object):
         start_state = torch.tensor(np.asarray(start.state, dtype=np.float32))
         exp = getattr(cfg, "experiment", "")
         if exp == "control_franka":
-            start_state[:2] = start_state[:2] + torch.from_numpy(LOCO_FRANKA_DIFF).float()
+            # (float32 tensor + float64 numpy constant: summed in double, stored back as float32, as the reference)
+            start_state[:2] = start_state[:2] + torch.from_numpy(LOCO_FRANKA_DIFF)
         elif exp == "control_wx250s":
-            start_state[:2] = start_state[:2] + torch.from_numpy(LOCO_WX250S_DIFF).float()
+            start_state[:2] = start_state[:2] + torch.from_numpy(LOCO_WX250S_DIFF)
         states[0, :] = (start_state - self.low) / (self.high - self.low)
         qpos[0, :] = torch.tensor(np.asarray(start.qpos, dtype=np.float32))
         data = {"states": states, "qpos": qpos, "actions": action_sequences.permute(1, 0, 2),
@@ -129,9 +131,11 @@ class TrajectorySampler(object):
     # ------------------------------------------------------------------ reference interface
     @torch.no_grad()
     def generate_model_rollouts(self, action_sequences, start: State, goal: DemoGoalState, opt_traj=None,
-                                ret_obs=False, ret_step_cost=False, suppress_print=True, states=None, masks=None):
+                                ret_obs=False, ret_step_cost=False, suppress_print=True, states=None, masks=None,
+                                opt_robot=None):
         """trajectory_sampler.py:35-199. Extra keywords `states` / `masks` feed precomputed robot states
-        (T+1, N, 5) and masks (T+1, N, 1, H, W) instead of calling robot_model.predict_batch."""
+        (T+1, N, 5) and masks (T+1, N, 1, H, W) instead of calling robot_model.predict_batch; `opt_robot` =
+        (states (T+1, 1, 5), masks (T+1, 1, 1, H, W)) of the expert trajectory `opt_traj` when no robot_model exists."""
         cfg = self.cfg
         m = self.model
         dev = m._device
@@ -171,9 +175,26 @@ class TrajectorySampler(object):
             ot = torch.cat([ot, torch.zeros((len(ot), actions.shape[2] - ot.shape[1]))], 1).to(dev)
             acts2 = actions.clone()
             acts2[0] = ot
+            states2, masks2 = states, masks
+            if _needs_robot(cfg):
+                # the reference appends the expert trajectory BEFORE robot_model.predict_batch (:62-68,101-109): its
+                # robot states / masks are those predicted for the expert's own actions, not candidate 0's
+                if opt_robot is not None:
+                    s_ot, m_ot = opt_robot
+                elif self.robot_model is not None:
+                    s_ot, m_ot = self._robot_inputs(ot[None].cpu(), start, 1, T)
+                else:
+                    raise ValueError("opt_traj with a robot-aware configuration needs the expert trajectory's robot "
+                                     "states / masks: pass opt_robot=(states (T+1,1,5), masks (T+1,1,1,H,W)) or a robot_model")
+                if states is not None:
+                    states2 = states.clone()
+                    states2[:, 0] = s_ot.to(dev, dtype=torch.float32)[:, 0]
+                if masks is not None:
+                    masks2 = masks.clone()
+                    masks2[:, 0] = m_ot.to(dev, dtype=torch.float32)[:, 0]
             sc2 = torch.empty(N, dtype=torch.float64, device=dev)
             obs2 = torch.empty(T, N, 48, 64, 4, device=dev)
-            self._rollout_device(acts2, start_img, goal_imgs, goal_masks, states, masks, None, N, T, sc2, obs2, None,
+            self._rollout_device(acts2, start_img, goal_imgs, goal_masks, states2, masks2, None, N, T, sc2, obs2, None,
                                  cand_offset=self.cand_offset)
             rollouts["optimal_sum_cost"] = float(sc2[0].item())
             rollouts["optimal_obs"] = obs2[:, 0, :, :, :3].permute(0, 3, 1, 2).cpu().numpy()
@@ -267,13 +288,24 @@ class CEMPolicy(object):
         world, rank = parallel.world_info(self.process_group)
         lo, hi = parallel.shard_range(N, rank, world)
         n_local = hi - lo
-        host_robot = _needs_robot(cfg) and self.precomputed_robot is None
+        # a DeviceRobotModel predicts states (and masks) on the GPU: no host round trip per iteration
+        dev_robot = ts.robot_model if isinstance(ts.robot_model, DeviceRobotModel) else None
+        if self.precomputed_robot is not None or not _needs_robot(cfg):
+            dev_robot = None
+        host_robot = _needs_robot(cfg) and self.precomputed_robot is None and dev_robot is None
+        start_norm = None
+        if dev_robot is not None:
+            if start is None or start.state is None:
+                raise ValueError("a robot model needs start.state (the current end-effector state)")
+            start_norm = normalized_start_state(start.state, getattr(cfg, "experiment", ""), ts.low, ts.high)
+            start_norm = start_norm.to(dev, dtype=torch.float32).contiguous()
+        fused_robot = dev_robot is None or dev_robot.mask_fn is None
         A = m._c.action_dim
         plan_seed = (self._seed + 0x9E3779B97F4A7C15 * (self._plans + 1)) & 0xFFFFFFFFFFFFFFFF
         self._plans += 1
         ts._seed = plan_seed
 
-        if world == 1 and not host_robot and opt_traj is None and not self.plot_rollouts:
+        if world == 1 and not host_robot and fused_robot and opt_traj is None and not self.plot_rollouts:
             # ---- whole plan on the device: one C call
             m.prepare(N)
             c = _lib.RacCem()
@@ -288,6 +320,11 @@ class CEMPolicy(object):
                 if getattr(cfg, "model_use_robot_state", False):
                     r.states, r.state_t_stride = _lib.ptr(states), states.stride(0)
                 r.masks, r.mask_t_stride = _lib.ptr(masks), masks.stride(0)
+            if dev_robot is not None:
+                c.robot = C.pointer(dev_robot.c_model)
+                c.robot_start_state = _lib.ptr(start_norm)
+                c.robot_render_masks = int(dev_robot.render_masks)
+                c.robot_extra_radius = float(dev_robot.thick_extra)
             r.seed, r.noise_ctr_base = plan_seed, 0
             r.sample_mean = int(bool(getattr(cfg, "sample_mean", False)))
             r.zero_robot = int(_zero_robot(cfg))
@@ -321,8 +358,14 @@ class CEMPolicy(object):
             last = i == I - 1
             if host_robot or (last and (opt_traj is not None or self.plot_rollouts)):
                 ts.cand_offset = lo
+                kw = {}
+                if self.precomputed_robot is not None:
+                    # this shard of the caller's device-resident states / masks (and the expert trajectory's, if given)
+                    ps, pm = self.precomputed_robot
+                    kw = dict(states=ps[:, lo:hi].contiguous(), masks=pm[:, lo:hi].contiguous(),
+                              opt_robot=getattr(self, "precomputed_opt_robot", None))
                 rollouts = ts.generate_model_rollouts(act5.cpu(), start, goal, opt_traj=opt_traj if last else None,
-                                                      ret_obs=self.plot_rollouts and last)
+                                                      ret_obs=self.plot_rollouts and last, **kw)
                 local_cost.copy_(torch.from_numpy(rollouts["sum_cost"]))
             else:
                 states = masks = None
@@ -332,6 +375,12 @@ class CEMPolicy(object):
                     # the time stride explicitly
                     states = _StridedView(states[:, lo:hi]) if getattr(cfg, "model_use_robot_state", False) else None
                     masks = _StridedView(masks[:, lo:hi])
+                elif dev_robot is not None:
+                    # robot_model.predict_batch on the device (trajectory_sampler.py:100-109), this shard only
+                    states = dev_robot.predict_states(start_norm, act5)
+                    masks = dev_robot.render(states, thick=True)
+                    if not getattr(cfg, "model_use_robot_state", False):
+                        states = None
                 fused = peer is not None and not (last and (opt_traj is not None or self.plot_rollouts))
                 ts._rollout_device(act5, start_img, goal_imgs, goal_masks, states, masks, None, n_local, L, local_cost,
                                    cand_offset=lo, noise_ctr=i * L, peer=peer.target(lo) if fused else None)

@@ -404,6 +404,54 @@ cudaError_t launch_dontcare_l1_loss(const float* pred, const float* target, cons
   dontcare_l1_kernel<<<1, 1024, 0, s>>>(pred, target, mask, robot_weight, out, B, HW);
   return cudaGetLastError();
 }
+// The four reconstruction criteria of the reference trainer (trainer.py:149-161; losses.py:11-50), one CTA per sample:
+// kind 0 l1 (mean |d|, optional batch weight), 1 dontcare_l1 (robot pixels x robot_weight, / (#world elements + 1)),
+// 2 mse (nn.MSELoss), 3 dontcare_mse. per_sample[b] = that sample's share of the batch mean; recon_loss_sum_kernel
+// adds them in index order (deterministic).
+__global__ void __launch_bounds__(512)
+recon_loss_kernel(const float* __restrict__ p, const float* __restrict__ t, const float* __restrict__ mask,
+                  const float* __restrict__ bw, int kind, float robot_weight, float* __restrict__ per_sample, int B,
+                  int HW) {
+  __shared__ double sh[32];
+  const int b = blockIdx.x;
+  const bool dontcare = (kind & 1) != 0, squared = kind >= 2;
+  double acc = 0.0, world = 0.0;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const bool rb = dontcare && mask[static_cast<size_t>(b) * HW + i] != 0.f;
+    float sd = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const size_t q = (static_cast<size_t>(b) * 3 + c) * HW + i;
+      float d = t[q] - p[q];
+      if (rb) d *= robot_weight;
+      sd += squared ? d * d : fabsf(d);
+    }
+    acc += sd;
+    world += rb ? 0.0 : 3.0;
+  }
+  acc = block_sum(acc, sh);
+  world = block_sum(world, sh);
+  if (threadIdx.x == 0) {
+    const double denom = dontcare ? world + 1.0 : 3.0 * HW;
+    const double w = (bw && !squared) ? static_cast<double>(bw[b]) : 1.0;
+    per_sample[b] = static_cast<float>(w * acc / denom / B);
+  }
+}
+__global__ void recon_loss_sum_kernel(const float* __restrict__ per_sample, int B, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int b = 0; b < B; ++b) s += static_cast<double>(per_sample[b]);
+    out[0] = static_cast<float>(s);
+  }
+}
+cudaError_t launch_recon_loss(const float* pred, const float* target, const float* mask, const float* batch_weight,
+                              int kind, float robot_weight, float* per_sample, float* out, int B, int HW,
+                              cudaStream_t s) {
+  recon_loss_kernel<<<B, 512, 0, s>>>(pred, target, mask, batch_weight, kind, robot_weight, per_sample, B, HW);
+  recon_loss_sum_kernel<<<1, 32, 0, s>>>(per_sample, B, out);
+  return cudaGetLastError();
+}
+
 // robot_mse_criterion / world_mse_criterion (losses.py:52-78): per sample sum(diff^2) over robot (world) pixels of
 // all 3 channels / (#those elements + 1), mean over the batch. out[0] += robot, out[1] += world.
 __global__ void __launch_bounds__(1024)

@@ -4,6 +4,8 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include "../../include/racb200.h"
+
 namespace rac {
 
 // encoder.c1.0 (reference vgg_64.py:99-101 via vgg_layer :8-18): 3x3 conv over [rgb | mask_t | mask_t+1], folded
@@ -48,6 +50,10 @@ cudaError_t launch_masked_cost(const float* curr, const float* goal, const float
 cudaError_t launch_l1_loss(const float* pred, const float* target, float* out, int64_t n, cudaStream_t s);
 cudaError_t launch_dontcare_l1_loss(const float* pred, const float* target, const float* mask, float robot_weight,
                                     float* out, int B, int HW, cudaStream_t s);
+// l1 / dontcare_l1 / mse / dontcare_mse (trainer.py:149-161) with optional per-sample batch weight
+cudaError_t launch_recon_loss(const float* pred, const float* target, const float* mask, const float* batch_weight,
+                              int kind, float robot_weight, float* per_sample, float* out, int B, int HW,
+                              cudaStream_t s);
 // out2[0] += robot_mse_criterion, out2[1] += world_mse_criterion (losses.py:52-78)
 cudaError_t launch_robot_world_mse(const float* pred, const float* target, const float* mask, float* out2, int B,
                                    int HW, cudaStream_t s);
@@ -77,6 +83,12 @@ cudaError_t launch_norm_lstm_cell_fused(const float* ih, const float* hh, const 
                                         const float* gn_params, float* c_state, float* obuf, __nv_bfloat16* h_out,
                                         int B, int P, int hid, cudaStream_t s);
 cudaError_t norm_lstm_set_attributes();
+
+// ---- robot state / mask producer (robot_kernels.cu; reference wx250s_model.py:57-182, franka_model.py:30-80) ----
+cudaError_t launch_robot_states(const rac_robot_model* m, const float* start_state, const float* actions, int n, int L,
+                                int adim, float* states, long long t_stride, cudaStream_t s);
+cudaError_t launch_robot_masks(const rac_robot_model* m, const float* states, long long st_stride, int n, int T1, int H,
+                               int W, float extra_radius, float* masks, long long m_stride, cudaStream_t s);
 
 // ---- CEM (cem_kernels.cu) ----
 cudaError_t launch_cem_sample(const float* mean, const float* stdv, const float* noise, unsigned long long seed,

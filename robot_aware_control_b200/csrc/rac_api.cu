@@ -59,6 +59,7 @@ struct Workspace {
   float* goal4 = nullptr;
   // CEM scratch
   float *act2 = nullptr, *act5 = nullptr, *mean = nullptr, *stdv = nullptr;
+  float *rob_states = nullptr, *rob_masks = nullptr;  // device-side robot model outputs of rac_cem_plan
   double* sum_cost = nullptr;
   int64_t* elite = nullptr;
   int cem_n = 0, cem_steps = 0;
@@ -615,6 +616,8 @@ void free_ws(rac_handle* h) {
   if (w.mean) cudaFree(w.mean);
   if (w.sum_cost) cudaFree(w.sum_cost);
   if (w.elite) cudaFree(w.elite);
+  if (w.rob_states) cudaFree(w.rob_states);
+  if (w.rob_masks) cudaFree(w.rob_masks);
   w = Workspace();
 }
 
@@ -1103,6 +1106,8 @@ int rac_cem_plan(rac_handle* h, const rac_cem* c, float* mean_out, float* std_ou
   if (w.cem_n != n || w.cem_steps != L) {
     CK(cudaStreamSynchronize(st));
     if (w.act2) { cudaFree(w.act2); cudaFree(w.act5); cudaFree(w.mean); cudaFree(w.sum_cost); cudaFree(w.elite); }
+    if (w.rob_states) { cudaFree(w.rob_states); w.rob_states = nullptr; }
+    if (w.rob_masks) { cudaFree(w.rob_masks); w.rob_masks = nullptr; }
     CK(cudaMalloc(reinterpret_cast<void**>(&w.act2), sizeof(float) * n * L * 2));
     CK(cudaMalloc(reinterpret_cast<void**>(&w.act5), sizeof(float) * n * L * A));
     CK(cudaMalloc(reinterpret_cast<void**>(&w.mean), sizeof(float) * 64 * 2));
@@ -1112,6 +1117,14 @@ int rac_cem_plan(rac_handle* h, const rac_cem* c, float* mean_out, float* std_ou
     w.cem_n = n; w.cem_steps = L;
   }
   if (2 * L > 32) return fail(h, RAC_ERR_INVALID, "cem: steps must be <= 16");
+  if (c->robot) {
+    if (!c->robot_start_state) return fail(h, RAC_ERR_INVALID, "cem: robot model without robot_start_state");
+    if (c->robot->kind != RAC_ROBOT_WX250S && c->robot->kind != RAC_ROBOT_FRANKA)
+      return fail(h, RAC_ERR_UNSUPPORTED, "cem: robot model kind %d", c->robot->kind);
+    if (!w.rob_states) CK(cudaMalloc(reinterpret_cast<void**>(&w.rob_states), sizeof(float) * (L + 1) * n * 5));
+    if (c->robot_render_masks && !w.rob_masks)
+      CK(cudaMalloc(reinterpret_cast<void**>(&w.rob_masks), sizeof(float) * (L + 1) * n * 48 * 64));
+  }
   // mean = 0, std = init_std (cem.py:71-73)
   CK(cudaMemsetAsync(w.mean, 0, sizeof(float) * 2 * L, st));
   fill_kernel<<<1, 64, 0, st>>>(w.stdv, c->init_std, 2 * L);
@@ -1124,6 +1137,19 @@ int rac_cem_plan(rac_handle* h, const rac_cem* c, float* mean_out, float* std_ou
     r.n = n; r.steps = L; r.cand_offset = 0; r.actions = w.act5; r.sum_cost = w.sum_cost;
     r.noise_ctr_base = c->rollout.noise_ctr_base + static_cast<unsigned>(it * L);
     if (c->rollout.eps) r.eps = c->rollout.eps + static_cast<size_t>(it) * L * n * h->cfg.z_dim * 48;
+    if (c->robot) {
+      // robot_model.predict_batch on the device (trajectory_sampler.py:100-109): no act5.cpu() per iteration
+      CK(launch_robot_states(c->robot, c->robot_start_state, w.act5, n, L, A, w.rob_states, static_cast<long long>(n) * 5, st));
+      r.states = w.rob_states; r.state_t_stride = static_cast<int64_t>(n) * 5;
+      h->launches++;
+      if (c->robot_render_masks) {
+        CK(launch_robot_masks(c->robot, w.rob_states, static_cast<long long>(n) * 5, n, L + 1, 48, 64, c->robot_extra_radius,
+                              w.rob_masks, static_cast<long long>(n) * 48 * 64, st));
+        r.masks = w.rob_masks; r.mask_t_stride = static_cast<int64_t>(n) * 48 * 64;
+        h->launches++;
+      }
+      if (!h->cfg.use_robot_state) { r.states = nullptr; }
+    }
     CKR(rac_rollout_cost(h, &r, stream));
     CK(launch_topk(w.sum_cost, n, c->topk, w.elite, nullptr, st));
     CK(launch_refit(w.act2, 2 * L, w.elite, c->topk, c->std_floor, w.mean, w.stdv, st));
@@ -1153,6 +1179,26 @@ int rac_dontcare_l1_loss(const float* pred, const float* target, const float* ma
                          int n, int hw, void* stream) {
   if (!pred || !target || !mask || !out || n < 1) return RAC_ERR_INVALID;
   return launch_dontcare_l1_loss(pred, target, mask, robot_weight, out, n, hw, static_cast<cudaStream_t>(stream)) == cudaSuccess ? RAC_OK : RAC_ERR_CUDA;
+}
+int rac_recon_loss(const float* pred, const float* target, const float* mask, const float* batch_weight, int kind,
+                   float robot_weight, float* per_sample, float* out, int n, int hw, void* stream) {
+  if (!pred || !target || !per_sample || !out || n < 1 || hw < 1 || kind < 0 || kind > 3) return RAC_ERR_INVALID;
+  if ((kind & 1) && !mask) return RAC_ERR_INVALID;
+  return launch_recon_loss(pred, target, mask, batch_weight, kind, robot_weight, per_sample, out, n, hw,
+                           static_cast<cudaStream_t>(stream)) == cudaSuccess ? RAC_OK : RAC_ERR_CUDA;
+}
+int rac_predict_states(const rac_robot_model* m, const float* start_state, const float* actions, int n, int steps,
+                       int action_dim, float* states_out, int64_t state_t_stride, void* stream) {
+  if (!m || !start_state || !actions || !states_out || n < 0 || steps < 1 || action_dim < 2) return RAC_ERR_INVALID;
+  if (m->kind != RAC_ROBOT_WX250S && m->kind != RAC_ROBOT_FRANKA) return RAC_ERR_UNSUPPORTED;
+  return launch_robot_states(m, start_state, actions, n, steps, action_dim, states_out, state_t_stride,
+                             static_cast<cudaStream_t>(stream)) == cudaSuccess ? RAC_OK : RAC_ERR_CUDA;
+}
+int rac_render_masks(const rac_robot_model* m, const float* states, int64_t state_t_stride, int n, int steps, int H,
+                     int W, float extra_radius, float* masks_out, int64_t mask_t_stride, void* stream) {
+  if (!m || !states || !masks_out || n < 0 || steps < 0 || H < 1 || W < 1 || extra_radius < 0.f) return RAC_ERR_INVALID;
+  return launch_robot_masks(m, states, state_t_stride, n, steps + 1, H, W, extra_radius, masks_out, mask_t_stride,
+                            static_cast<cudaStream_t>(stream)) == cudaSuccess ? RAC_OK : RAC_ERR_CUDA;
 }
 int rac_robot_world_mse(const float* pred, const float* target, const float* mask, float* out2, int n, int hw,
                         void* stream) {

@@ -93,7 +93,6 @@ struct TrainState {
   float* czero;
   float* loss_part;      // [B]
   float* kl_tmp;
-  int step_count = 0;
   int adam_t = 0;
   int M[4];
 };
@@ -473,7 +472,7 @@ int train_backward_step(rac_handle* h, TrainState* T, const rac_train_batch* bt,
   const float* m_i = bt->masks ? bt->masks + static_cast<size_t>(t + 1) * B * HW : nullptr;
   // ---- reconstruction loss and its gradient w.r.t. the decoder logits (trainer.py:406-433)
   CK(launch_frame_loss(tp.x4, x_j, x_i, m_i, T->cfg.recon_kind, T->cfg.robot_pixel_weight, B, static_cast<int>(HW),
-                       T->loss_part, T->dy_b, gp_in, gxj_out, st));
+                       T->loss_part, T->dy_b, gp_in, gxj_out, st, bt->batch_weight));
   CK(launch_sum_f32(T->loss_part, B, bt->losses + 0, st));
   F32Seg seg[3];
   // ---- decoder
@@ -742,7 +741,8 @@ int rac_train_forward_backward(rac_handle* h, const rac_train_batch* bt, void* s
   TrainState* T = static_cast<TrainState*>(h->train);
   const rac_config& c = h->cfg;
   if (!bt->images || !bt->actions || !bt->losses) return fail(h, RAC_ERR_INVALID, "images, actions, losses are required");
-  if ((c.use_mask || T->cfg.zero_robot || T->cfg.recon_kind == 1) && !bt->masks)
+  if (T->cfg.recon_kind < 0 || T->cfg.recon_kind > 3) return fail(h, RAC_ERR_INVALID, "recon_kind %d", T->cfg.recon_kind);
+  if ((c.use_mask || T->cfg.zero_robot || (T->cfg.recon_kind & 1)) && !bt->masks)
     return fail(h, RAC_ERR_INVALID, "this configuration needs masks");
   if (c.use_robot_state && !bt->states) return fail(h, RAC_ERR_INVALID, "model_use_robot_state needs states");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -760,12 +760,16 @@ int rac_train_forward_backward(rac_handle* h, const rac_train_batch* bt, void* s
   CK(cudaMemsetAsync(T->grads, 0, sizeof(float) * T->cfg.n_params, st));
   CK(cudaMemsetAsync(bt->losses, 0, sizeof(float) * 4, st));
   const size_t zn = static_cast<size_t>(B) * z * 48;
+  // Philox counter of the reparameterisation noise = the caller's global training step (persisted in checkpoints),
+  // NOT a count kept in this state: rac_train_create runs again after a resume or a new batch shape and must not
+  // replay the noise of steps 0..k
+  const unsigned int noise_step = static_cast<unsigned int>(bt->noise_step);
   for (int t = 0; t < S; ++t) {
     Tape& tp = T->tape[t];
     if (bt->eps_prior) CK(cudaMemcpyAsync(tp.eps_p, bt->eps_prior + t * zn, sizeof(float) * zn, cudaMemcpyDeviceToDevice, st));
-    else CK(launch_normal_fill(tp.eps_p, static_cast<long long>(zn), bt->seed, 2u * (T->step_count * S + t), st));
+    else CK(launch_normal_fill(tp.eps_p, static_cast<long long>(zn), bt->seed, 2u * (noise_step * S + t), st));
     if (bt->eps_post) CK(cudaMemcpyAsync(tp.eps_q, bt->eps_post + t * zn, sizeof(float) * zn, cudaMemcpyDeviceToDevice, st));
-    else CK(launch_normal_fill(tp.eps_q, static_cast<long long>(zn), bt->seed, 2u * (T->step_count * S + t) + 1u, st));
+    else CK(launch_normal_fill(tp.eps_q, static_cast<long long>(zn), bt->seed, 2u * (noise_step * S + t) + 1u, st));
     CKR(train_forward_step(h, T, bt, t, st));
   }
   // ---- BPTT
@@ -786,7 +790,6 @@ int rac_train_forward_backward(rac_handle* h, const rac_train_batch* bt, void* s
     TLayer& L = T->L[i];
     CK(launch_unpack_grads(L.dwp, L.d.row_off, L.d.col_off, L.n_packed, L.taps, L.ctot, L.d.flip, T->grads, st));
   }
-  T->step_count++;
   return RAC_OK;
 }
 

@@ -500,7 +500,8 @@ cudaError_t launch_gauss_bwd(const float* dz, const float* mu, const float* lv, 
 __global__ void __launch_bounds__(1024)
 frame_loss_kernel(const float* __restrict__ x4, const float* __restrict__ xj, const float* __restrict__ xi,
                   const float* __restrict__ mask, int kind, float rw, int B, int HW, float* __restrict__ loss_out,
-                  __nv_bfloat16* __restrict__ dlogit, const float* __restrict__ gp_in, float* __restrict__ gxj_out) {
+                  __nv_bfloat16* __restrict__ dlogit, const float* __restrict__ gp_in, float* __restrict__ gxj_out,
+                  const float* __restrict__ batch_weight) {
   __shared__ double sh[32];
   __shared__ float s_scale;
   const int b = blockIdx.x;
@@ -514,20 +515,24 @@ frame_loss_kernel(const float* __restrict__ x4, const float* __restrict__ xj, co
     for (int i = 0; i < 32; ++i) t += sh[i];
     return t;
   };
-  if (kind == 1) {
+  // kind: 0 l1, 1 dontcare_l1, 2 mse (nn.MSELoss), 3 dontcare_mse (trainer.py:149-161; losses.py:11-50). batch_weight
+  // (movement weighting, trainer.py:426-429) multiplies the per-sample term of the two l1 kinds only, as the reference
+  const bool dontcare = (kind & 1) != 0, squared = kind >= 2;
+  const float bw = (batch_weight && !squared) ? batch_weight[b] : 1.f;
+  if (dontcare) {
     double cnt = 0.0;
     for (int p = tid; p < HW; p += blockDim.x) cnt += mask[static_cast<size_t>(b) * HW + p] != 0.f ? 0.0 : 3.0;
     cnt = block_sum(cnt);
-    if (tid == 0) s_scale = static_cast<float>(1.0 / ((cnt + 1.0) * B));
+    if (tid == 0) s_scale = static_cast<float>(static_cast<double>(bw) / ((cnt + 1.0) * B));
   } else {
-    if (tid == 0) s_scale = 1.f / (static_cast<float>(B) * 3.f * HW);
+    if (tid == 0) s_scale = bw / (static_cast<float>(B) * 3.f * HW);
   }
   __syncthreads();
   const float scale = s_scale;
   double acc = 0.0;
   for (int p = tid; p < HW; p += blockDim.x) {
     const float mh = x4[(static_cast<size_t>(b) * 4 + 3) * HW + p];
-    const bool robot = kind == 1 && mask[static_cast<size_t>(b) * HW + p] != 0.f;
+    const bool robot = dontcare && mask[static_cast<size_t>(b) * HW + p] != 0.f;
     const float w = robot ? rw : 1.f;
     float dm = 0.f, dl[4];
 #pragma unroll
@@ -537,8 +542,8 @@ frame_loss_kernel(const float* __restrict__ x4, const float* __restrict__ xj, co
       const float t = xi[(static_cast<size_t>(b) * 3 + c) * HW + p];
       const float pr = (1.f - mh) * j + mh * xh;  // blends with the un-blacked x_j (trainer.py:406-407)
       const float diff = (t - pr) * w;
-      acc += fabsf(diff);
-      const float sg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+      acc += squared ? diff * diff : fabsf(diff);
+      const float sg = squared ? 2.f * diff : (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f));
       float dp = -sg * w * scale;                 // dL / d pred
       if (gp_in) dp += gp_in[(static_cast<size_t>(b) * 3 + c) * HW + p];
       if (gxj_out) gxj_out[(static_cast<size_t>(b) * 3 + c) * HW + p] = dp * (1.f - mh);
@@ -556,9 +561,10 @@ frame_loss_kernel(const float* __restrict__ x4, const float* __restrict__ xj, co
 }
 cudaError_t launch_frame_loss(const float* x4, const float* xj, const float* xi, const float* mask, int kind,
                               float robot_weight, int B, int HW, float* loss_out, __nv_bfloat16* dlogit,
-                              const float* gp_in, float* gxj_out, cudaStream_t s) {
-  if (kind == 1 && !mask) return cudaErrorInvalidValue;
-  frame_loss_kernel<<<B, 1024, 0, s>>>(x4, xj, xi, mask, kind, robot_weight, B, HW, loss_out, dlogit, gp_in, gxj_out);
+                              const float* gp_in, float* gxj_out, cudaStream_t s, const float* batch_weight) {
+  if ((kind & 1) && !mask) return cudaErrorInvalidValue;
+  frame_loss_kernel<<<B, 1024, 0, s>>>(x4, xj, xi, mask, kind, robot_weight, B, HW, loss_out, dlogit, gp_in, gxj_out,
+                                       batch_weight);
   return cudaGetLastError();
 }
 

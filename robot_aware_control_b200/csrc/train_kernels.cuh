@@ -85,13 +85,14 @@ cudaError_t launch_gauss_bwd(const float* dz, const float* mu, const float* lv, 
                              __nv_bfloat16* dpost, __nv_bfloat16* dprior, cudaStream_t s);
 
 // ---- frame loss (forward value + gradient w.r.t. the pre-sigmoid decoder output)
-// x4: (B,4,H,W) sigmoid outputs; xj, xi: (B,3,H,W); mask: (B,1,H,W) or null. kind 0 = l1, 1 = dontcare_l1.
+// x4: (B,4,H,W) sigmoid outputs; xj, xi: (B,3,H,W); mask: (B,1,H,W) or null. kind 0 = l1, 1 = dontcare_l1, 2 = mse,
+// 3 = dontcare_mse; batch_weight (B) or null: per-sample factor of the l1 kinds (movement weighting).
 // loss_out[b] = per-sample contribution (already scaled so that the step loss is sum_b loss_out[b]).
 // gp_in: extra gradient w.r.t. the composited prediction (from the next step when that step consumed this
 // prediction as its input, scheduled sampling) or null; gxj_out: gradient w.r.t. x_j through the composite (=) or null.
 cudaError_t launch_frame_loss(const float* x4, const float* xj, const float* xi, const float* mask, int kind,
                               float robot_weight, int B, int HW, float* loss_out, __nv_bfloat16* dlogit /* [B*HW, 64] */,
-                              const float* gp_in, float* gxj_out, cudaStream_t s);
+                              const float* gp_in, float* gxj_out, cudaStream_t s, const float* batch_weight = nullptr);
 // x_pred = (1 - m) * x_j + m * rgb (trainer.py:406-407), NCHW fp32 (B,3,H,W)
 cudaError_t launch_composite(const float* x4, const float* xj, float* xp, int B, int HW, cudaStream_t s);
 // gradient of encoder.c1.0 w.r.t. its rgb input channels, accumulated (+=) into gimg (B,3,H,W); robot pixels of

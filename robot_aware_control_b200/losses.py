@@ -119,9 +119,41 @@ class RobotWorldCost(Cost):
 
 
 # ---- training criteria: forward values (losses.py:13-19,35-50,97-106) ----
+def _recon(kind, prediction, target, mask=None, robot_weight=0.0, batch_weight=None):
+    """rac_recon_loss: the four criteria of PredictionTrainer._recon_loss (trainer.py:149-161) on (B,3,H,W) tensors."""
+    lib = _lib.load()
+    p, t = _dev(prediction), _dev(target)
+    m = _dev(mask) if mask is not None else None
+    bw = _dev(batch_weight).reshape(-1) if batch_weight is not None else None
+    n, _, h, w = p.shape
+    if bw is not None and bw.numel() != n:
+        raise ValueError(f"batch_weight has {bw.numel()} entries for a batch of {n}")
+    scratch = torch.empty(n + 1, device="cuda")
+    _lib.check(lib.rac_recon_loss(_lib.ptr(p), _lib.ptr(t), _lib.ptr(m), _lib.ptr(bw), kind, float(robot_weight),
+                                  _lib.ptr(scratch), C_void(scratch, n), n, h * w, _lib.stream_ptr()), None,
+               "rac_recon_loss")
+    return scratch[n]
+
+
+def C_void(t, index):
+    import ctypes
+
+    return ctypes.c_void_p(t.data_ptr() + index * t.element_size())
+
+
+def mse_criterion(prediction, target):
+    """nn.MSELoss() (losses.py:11), the reference's default reconstruction loss (src/config/__init__.py:235-238)."""
+    return _recon(2, prediction, target)
+
+
+def dontcare_mse_criterion(prediction, target, mask, robot_weight):
+    """losses.py:21-33."""
+    return _recon(3, prediction, target, mask, robot_weight)
+
+
 def l1_criterion(prediction, target, batch_weight=None):
-    if batch_weight is not None:
-        raise NotImplementedError("batch_weight is a training-only option (out of scope this round)")
+    if batch_weight is not None:  # movement weighting (losses.py:17-18)
+        return _recon(0, prediction, target, batch_weight=batch_weight)
     lib = _lib.load()
     p, t = _dev(prediction), _dev(target)
     out = torch.empty(1, device="cuda")
@@ -130,8 +162,8 @@ def l1_criterion(prediction, target, batch_weight=None):
 
 
 def dontcare_l1_criterion(prediction, target, mask, robot_weight, batch_weight=None):
-    if batch_weight is not None:
-        raise NotImplementedError("batch_weight is a training-only option (out of scope this round)")
+    if batch_weight is not None:  # losses.py:48-49
+        return _recon(1, prediction, target, mask, robot_weight, batch_weight)
     lib = _lib.load()
     p, t, m = _dev(prediction), _dev(target), _dev(mask)
     n, _, h, w = p.shape

@@ -15,7 +15,9 @@ flat gradient buffer is all-reduced (NCCL) and averaged before the Adam update, 
 Scheduled sampling follows the reference (same probability schedule, same global numpy generator); when the model's
 own prediction is fed back, its gradient flows into the previous step as in the reference (`x_pred.clone()`).
 `cfg.lstm_group_norm` (NormConvLSTMCell, the cell of the authors' deployed checkpoints) trains as well.
-Limits (raise): heatmaps, multiview, movement weighting.
+All four `cfg.reconstruction_loss` kinds (l1, dontcare_l1, mse -- the argparse default --, dontcare_mse) and the
+movement weighting (`cfg.load_movement_info`, batch["high_movement"]) are implemented. Limits (raise): heatmaps,
+multiview; the batch must be a multiple of 4 clips.
 """
 import ctypes as C
 
@@ -106,6 +108,9 @@ def _layer_tables(model, offsets, boffsets):
     return out
 
 
+RECON_KINDS = {"l1": 0, "dontcare_l1": 1, "mse": 2, "dontcare_mse": 3}  # cfg.reconstruction_loss (trainer.py:149-161)
+
+
 class RacTrainLayer(C.Structure):
     _fields_ = [("row_off", C.c_void_p), ("col_off", C.c_void_p), ("bias_off", C.c_void_p),
                 ("gamma_off", C.c_longlong), ("beta_off", C.c_longlong), ("rmean_off", C.c_longlong),
@@ -123,7 +128,7 @@ class RacTrainConfig(C.Structure):
 class RacTrainBatch(C.Structure):
     _fields_ = [("images", C.c_void_p), ("masks", C.c_void_p), ("states", C.c_void_p), ("actions", C.c_void_p),
                 ("eps_prior", C.c_void_p), ("eps_post", C.c_void_p), ("seed", C.c_ulonglong), ("losses", C.c_void_p),
-                ("true_token", C.c_void_p)]
+                ("true_token", C.c_void_p), ("noise_step", C.c_ulonglong), ("batch_weight", C.c_void_p)]
 
 
 def adam_state_dict(m, v, steps_taken, layout, lr, beta1):
@@ -188,8 +193,8 @@ class SVGTrainer:
         self._ss_k = float(getattr(config, "scheduled_sampling_k", 4000))
         self._forced_tokens = None
         kind = c.reconstruction_loss
-        if kind not in ("l1", "dontcare_l1"):
-            raise NotImplementedError(f"reconstruction_loss {kind!r}: the B200 path implements l1 and dontcare_l1")
+        if kind not in RECON_KINDS:  # the reference raises the same for anything else (trainer.py:160-161)
+            raise NotImplementedError(f"{kind}")
         self._fixed_skip = int(not c.last_frame_skip)
         self.process_group = process_group
         self.allreduce_events = None
@@ -223,6 +228,15 @@ class SVGTrainer:
         self.adam_m = torch.zeros(n, device=dev)
         self.adam_v = torch.zeros(n, device=dev)
         self.losses = torch.zeros(4, device=dev)
+        # BatchNorm2d.num_batches_tracked counters: one flat int64 tensor (the module buffers are views), advanced by
+        # one vector add per step -- the encoder runs twice per predicted frame (dynamics.py:566,619), the decoder once
+        tracked = [(k, b) for k, b in model.named_buffers() if k.endswith("num_batches_tracked")]
+        self._tracked = torch.zeros(max(len(tracked), 1), dtype=torch.long, device=dev)
+        for i, (k, b) in enumerate(tracked):
+            self._tracked[i] = b.to(dev)
+            b.data = self._tracked[i]
+        self._tracked_inc = torch.tensor([2 if k.startswith("encoder.") else 1 for k, _ in tracked] or [0],
+                                         dtype=torch.long, device=dev)
         self._tables = _layer_tables(model, self._offsets, self._boffsets)
         self._keep = []  # device index arrays referenced by the library
         names = pack.LAYER_IDS + (pack.GN_LAYER_IDS if c.lstm_group_norm else [])
@@ -247,9 +261,13 @@ class SVGTrainer:
         self._beta1 = float(getattr(config, "beta1", 0.9))
         self._kl_beta = float(getattr(config, "beta", 1e-4))
         self._rpw = float(getattr(config, "robot_pixel_weight", 0.0))
-        self._kind = 0 if kind == "l1" else 1
+        self._kind = RECON_KINDS[kind]
         self._zero_robot = int("dontcare" in kind or bool(c.black_robot_input))
-        self._seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        # reparameterisation noise: Philox keyed on (seed, global training step, time step). Data-parallel replicas
+        # seed alike (torch.initial_seed() is the same on every rank), so the rank is mixed in: every replica must
+        # draw its own eps for its own batch
+        rank = dist.get_rank(process_group) if process_group is not None else 0
+        self._seed = (int(torch.initial_seed()) + 0x9E3779B97F4A7C15 * rank) & 0xFFFFFFFFFFFFFFFF
         self._eps = None
         self._step = 0
         self._adam_t = 0  # Adam steps taken (torch.optim.Adam state "step")
@@ -294,7 +312,25 @@ class SVGTrainer:
         f32 = lambda t: None if t is None else t.to(device=dev, dtype=torch.float32).contiguous()
         images, actions = f32(batch["images"]), f32(batch["actions"])
         masks, states = f32(batch.get("masks")), f32(batch.get("states"))
+        # the reference unrolls range(1, n_past + n_future) whatever the clip length is (trainer.py:352) and uses the
+        # first min(batch_size, B) clips only implicitly (init_hidden, :349-350); a shorter clip is an IndexError there
+        T_ref = self.n_past + self.n_future
+        if images.shape[0] < T_ref:
+            raise IndexError(f"clip of {images.shape[0]} frames, n_past + n_future = {T_ref} (reference trainer.py:352)")
+        if images.shape[0] > T_ref:
+            images, actions = images[:T_ref].contiguous(), actions[:T_ref - 1].contiguous()
+            masks = None if masks is None else masks[:T_ref].contiguous()
+            states = None if states is None else states[:T_ref].contiguous()
         T, B = images.shape[0], images.shape[1]
+        if B % 4:
+            raise ValueError(f"batch of {B} clips: the B200 training step needs a multiple of 4 (64-row GEMM tiles on the "
+                             "6x8 latent map); drop or pad the trailing partial batch (DataLoader(drop_last=True))")
+        bw = None
+        if getattr(self._config, "load_movement_info", False):  # trainer.py:426-429
+            info = batch["high_movement"].to(dev).bool()
+            bw = (float(self._config.movement_weight) * info).float()
+            bw[~info] = 1.0
+            bw = bw.contiguous()
         self._ensure(B, T - 1)
         eps_p = eps_q = None
         if self._eps is not None:
@@ -308,10 +344,11 @@ class SVGTrainer:
         bt = RacTrainBatch(images=_lib.ptr(images), masks=_lib.ptr(masks), states=_lib.ptr(states),
                            actions=_lib.ptr(actions), eps_prior=_lib.ptr(eps_p), eps_post=_lib.ptr(eps_q),
                            seed=self._seed, losses=_lib.ptr(self.losses),
-                           true_token=None if all(tokens) else tokens.ctypes.data)
+                           true_token=None if all(tokens) else tokens.ctypes.data, noise_step=self._step,
+                           batch_weight=_lib.ptr(bw))
         _lib.check(self._lib.rac_train_forward_backward(m.handle, C.byref(bt), _lib.stream_ptr()), m.handle,
                    "rac_train_forward_backward")
-        self._keep_batch = (images, actions, masks, states, eps_p, eps_q)  # alive until the stream has consumed them
+        self._keep_batch = (images, actions, masks, states, eps_p, eps_q, bw)  # alive until the stream has consumed them
         return self.losses
 
     def optimizer_step(self):
@@ -326,6 +363,7 @@ class SVGTrainer:
                 ev[1].record()
         _lib.check(self._lib.rac_train_adam_step(m.handle, _lib.stream_ptr()), m.handle, "rac_train_adam_step")
         m._packed_dirty = True  # the eval-mode packed copy (folded BatchNorm) is stale now
+        self._tracked.add_(self._tracked_inc, alpha=self._created_for[1])  # num_batches_tracked += forwards this step
         self._adam_t += 1
         self._step += 1
 
@@ -458,7 +496,11 @@ class SVGTrainer:
         self._created_for = None  # hyper-parameters and the step count are handed over at the next rac_train_create
 
     def save_checkpoint(self, path):
-        """PredictionTrainer._save_checkpoint (trainer.py:829-837): the same three keys."""
+        """PredictionTrainer._save_checkpoint (trainer.py:829-837): the same three keys. Data parallel: BatchNorm running
+        statistics are per rank (as in per-process training of the reference); rank 0's are broadcast first so that every
+        rank holds -- and any rank may write -- the same checkpoint."""
+        if self.process_group is not None and dist.get_world_size(self.process_group) > 1:
+            dist.broadcast(self.buffers, src=dist.get_global_rank(self.process_group, 0), group=self.process_group)
         torch.save({"model": self.model.state_dict(), "optimizer": self.optimizer_state_dict(), "step": self._step}, path)
 
     def load_checkpoint(self, path):

@@ -21,7 +21,7 @@ import torch.nn.functional as F
 
 from oracle import svg_oracle as so
 from oracle.make_golden import G_DIM, Z_DIM
-from oracle.make_golden_train import make_batch
+from oracle.make_golden_train import HIGH_MOVEMENT, make_batch
 from oracle.train_oracle import TrainOracle
 
 pytestmark = pytest.mark.gpu
@@ -33,11 +33,15 @@ def _setup(tag, n_future, lr=1e-3, beta=1e-2):
 
     # "...fixedskip": last_frame_skip False, the config default (decoder skips of the clip's first frame)
     kw = dict(lr=lr, beta=beta, beta1=0.9, n_future=n_future, n_past=1, last_frame_skip="fixedskip" not in tag)
+    from tests.test_train_oracle_golden import loss_kw  # mse / dontcare_mse / movement-weighting variants
+
+    kw.update(loss_kw(tag))
     if tag.startswith("vanilla"):
         cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, **kw)
     else:
+        kw.setdefault("reconstruction_loss", "dontcare_l1")
         cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, model_use_mask=True, model_use_future_mask=True,
-                          model_use_robot_state=True, reconstruction_loss="dontcare_l1", reward_type="dontcare",
+                          model_use_robot_state=True, reward_type="dontcare",
                           lstm_group_norm=tag.endswith("_gn"), **kw)  # "..._gn": NormConvLSTMCell (lstm.py:151-198)
     sd = so.make_state_dict(cfg, 17)
     model = SVGConvModel(cfg)
@@ -47,6 +51,8 @@ def _setup(tag, n_future, lr=1e-3, beta=1e-2):
     batch, ep, eq = make_batch(23, cfg, not tag.startswith("vanilla"))
     T = n_future + 1
     batch = {k: (v[:T] if k != "actions" else v[:T - 1]) for k, v in batch.items()}
+    if tag == "ra_bw":
+        batch["high_movement"] = HIGH_MOVEMENT.clone()
     return cfg, sd, model, trainer, batch, ep[:T - 1], eq[:T - 1]
 
 
@@ -54,11 +60,12 @@ def _rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-20))
 
 
-@pytest.mark.parametrize("tag", ["vanilla", "ra", "ra_sampled", "ra_fixedskip", "vanilla_fixedskip_sampled", "ra_gn"])
+@pytest.mark.parametrize("tag", ["vanilla", "ra", "ra_sampled", "ra_fixedskip", "vanilla_fixedskip_sampled", "ra_gn",
+                                 "vanilla_mse", "ra_dcmse", "ra_bw"])
 def test_train_step_losses_smooth_grads_adam(golden_dir, tag):
     gold = np.load(os.path.join(golden_dir, f"train_{tag}.npz"))
     cfg, sd, model, trainer, batch, ep, eq = _setup(tag, 3)
-    oracle = TrainOracle(cfg, sd, lr=1e-3, beta=1e-2)
+    oracle = TrainOracle(cfg, sd, lr=1e-3, beta=1e-2, robot_pixel_weight=getattr(cfg, "robot_pixel_weight", 0.0))
     tokens = [True, False, False] if tag.endswith("sampled") else None  # scheduled sampling: model frame at i > 1
     info, ref = oracle.loss_and_grads(batch, ep, eq, true_token=None if tokens is None else tokens + [False])
     if tokens is not None:
@@ -281,6 +288,7 @@ def test_checkpoint_resume_equals_uninterrupted_run(tmp_path):
     assert torch.equal(trainer2.params, want) and torch.equal(trainer2.buffers, want_buffers)
     # another clip length re-creates the device state: the moments and the bias-correction count must survive
     short = {k: (v[:2] if k != "actions" else v[:1]) for k, v in batch.items()}
+    trainer2.n_future = 1  # the reference unrolls n_past + n_future frames whatever the clip holds (trainer.py:352)
     trainer2.set_noise(ep[:1], eq[:1])
     trainer2.forward_backward(short)
     p0, g0, m0, v0, t = trainer2.params.clone(), trainer2.grads.clone(), trainer2.adam_m.clone(), trainer2.adam_v.clone(), 4

@@ -8,24 +8,40 @@ import torch
 
 from oracle import svg_oracle as so
 from oracle.make_golden import G_DIM, Z_DIM
-from oracle.make_golden_train import make_batch, summarize
+from oracle.make_golden_train import HIGH_MOVEMENT, make_batch, summarize
 from oracle.train_oracle import TrainOracle
 
 
-@pytest.mark.parametrize("tag", ["vanilla", "ra", "ra_sampled", "ra_fixedskip", "vanilla_fixedskip_sampled", "ra_gn"])
+def loss_kw(tag):
+    """cfg entries of the reconstruction-loss variants (trainer.py:149-161,426-429) behind a golden tag."""
+    if tag == "vanilla_mse":
+        return dict(reconstruction_loss="mse")
+    if tag == "ra_dcmse":
+        return dict(reconstruction_loss="dontcare_mse", robot_pixel_weight=0.25)
+    if tag == "ra_bw":
+        return dict(load_movement_info=True, movement_weight=3.0)
+    return {}
+
+
+@pytest.mark.parametrize("tag", ["vanilla", "ra", "ra_sampled", "ra_fixedskip", "vanilla_fixedskip_sampled", "ra_gn",
+                                 "vanilla_mse", "ra_dcmse", "ra_bw"])
 def test_train_step_matches_reference(golden_dir, tag):
     gold = np.load(os.path.join(golden_dir, f"train_{tag}.npz"))
     lfs = "fixedskip" not in tag  # last_frame_skip False (the config default): decoder skips of the first frame
     if tag.startswith("vanilla"):
-        cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, last_frame_skip=lfs)
+        cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, last_frame_skip=lfs, **loss_kw(tag))
     else:
         # "ra_gn": NormConvLSTMCell -- the CUDA training step does not implement it yet (SVGTrainer raises); the golden
         # and this oracle check are the parity pin for when it does
         cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM, model_use_mask=True, model_use_future_mask=True, last_frame_skip=lfs,
                           lstm_group_norm=tag.endswith("_gn"),
-                          model_use_robot_state=True, reconstruction_loss="dontcare_l1", reward_type="dontcare")
-    tr = TrainOracle(cfg, so.make_state_dict(cfg, int(gold["weight_seed"])), lr=float(gold["lr"]), beta=float(gold["beta"]))
+                          model_use_robot_state=True, reward_type="dontcare",
+                          **{"reconstruction_loss": "dontcare_l1", **loss_kw(tag)})
+    tr = TrainOracle(cfg, so.make_state_dict(cfg, int(gold["weight_seed"])), lr=float(gold["lr"]), beta=float(gold["beta"]),
+                     robot_pixel_weight=getattr(cfg, "robot_pixel_weight", 0.0))
     batch, eps_p, eps_q = make_batch(int(gold["input_seed"]), cfg, not tag.startswith("vanilla"))
+    if tag == "ra_bw":
+        batch["high_movement"] = HIGH_MOVEMENT.clone()
     tokens = [True, False, False, False] if tag.endswith("sampled") else None  # model frame at every step i > 1
     for step in range(2):
         info, grads = tr.train_step(batch, eps_p, eps_q, true_token=tokens)
