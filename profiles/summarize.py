@@ -2,7 +2,13 @@
 
     python profiles/summarize.py launches gpurun_out/launches.csv > profiles/rNN_launches_summary.txt
     python profiles/summarize.py raw gpurun_out/prof.ncu-rep > profiles/rNN_kernel_ncu.txt
+
+The tensor-pipe metrics are not part of `--set full` on sm_100: capture with
+    ncu --set full --metrics $(python profiles/summarize.py tensor-metrics) ...
 """
+TENSOR_METRICS = ("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed,"
+                  "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed,"
+                  "sm__inst_executed_pipe_tc.sum,sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32.sum")
 import collections
 import csv
 import re
@@ -11,7 +17,9 @@ import sys
 
 KEYS = [
     "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
-    "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active_realtime.avg", "sm__inst_executed_pipe_tc.sum",
+    "sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32.sum", "sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32.sum.per_second", "dram__bytes_read.sum", "dram__bytes_write.sum",
     "dram__bytes_read.sum.per_second", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
     "lts__t_bytes.sum.per_second", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread",
@@ -51,4 +59,7 @@ def raw(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "tensor-metrics":
+        print(TENSOR_METRICS)
+    else:
+        {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
