@@ -282,7 +282,29 @@ int encode_act_map_ymajor(rac_handle* h, CUtensorMap* m, const bf16* ptr, int C,
 struct Src {
   const bf16* p;
   int C;
+  // training tape only (implicit-GEMM weight gradient over all time steps): the tensor this source is at step 0 of the
+  // tape (nullptr: p itself), and 1 when the source is that tensor one step EARLIER (h_{t-1} of a ConvLSTM)
+  const bf16* base0 = nullptr;
+  int tshift = 0;
 };
+
+// (C, W, H, B, S) view of per-step NHWC tensors that lie `step_bytes` apart: box {64, W, BH, NB, 1}
+int encode_act_map5(rac_handle* h, CUtensorMap* m, const bf16* ptr, int C, int B, int H, int W, int S,
+                    unsigned long long step_bytes, int BH, int NB) {
+  cuuint64_t dims[5] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(B), static_cast<cuuint64_t>(S)};
+  cuuint64_t strides[4] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
+                           static_cast<cuuint64_t>(H) * W * C * 2, static_cast<cuuint64_t>(step_bytes)};
+  cuuint32_t box[5] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(W), static_cast<cuuint32_t>(BH),
+                       static_cast<cuuint32_t>(NB), 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16*>(ptr), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(h, RAC_ERR_CUDA, "cuTensorMapEncodeTiled(5-D tape view C=%d S=%d stride=%llu) failed: %d", C, S, step_bytes, (int)r);
+  return RAC_OK;
+}
 
 int ilog2(int v) {
   int s = 0;

@@ -22,6 +22,7 @@
 #include <algorithm>
 
 #include "train_kernels.cuh"
+#include "wgrad_tc.cuh"
 
 namespace {
 
@@ -71,6 +72,12 @@ struct TrainState {
   float* gn_dy = nullptr;     // [M3, 4g] gate pre-activation gradients of the cell being processed
   float* gn_part = nullptr;   // [B][14 g] per-sample partials of the GroupNorm affine gradients
   float *params = nullptr, *buffers = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr;
+  // weight gradients: 1 = implicit GEMM over all time steps straight from the tape (wgrad_tc.cu); 0 = round-1 path
+  // (materialised im2col(X)^T / dY^T + plain GEMM; RAC_WGRAD_IM2COL=1, kept for A/B measurements and cross-checks)
+  int wgrad_implicit = 1;
+  unsigned long long step_bytes = 0;  // distance between the same tape buffer of two consecutive time steps
+  float* wg_part = nullptr;           // split-K partials of the layer being processed
+  size_t wg_part_elems = 0;
   float* wfirst = nullptr;  // [9*cin][64]
   float* zero64 = nullptr;
   std::vector<Tape> tape;
@@ -188,6 +195,82 @@ int vgg_forward(rac_handle* h, TrainState* T, VggRt& rt, const VggDef& d, const 
   return RAC_OK;
 }
 
+// Tiling of one layer's implicit-GEMM weight gradient (everything but the tensor maps / sources)
+WgradGeom wg_plan(const TLayer& L, int B, int H, int W, int S) {
+  WgradGeom g{};
+  g.ks = (L.taps == 25) ? 5 : 3;
+  g.pad = g.ks / 2;
+  switch (W) {
+    case 64: g.BH = 1; break;
+    case 32: g.BH = 2; break;
+    case 16: g.BH = 4; break;
+    default: g.BH = H; break;  // the 6 x 8 latent map: one whole image (48 positions) per k-block
+  }
+  g.NB = 1;
+  g.rows = W * g.BH * g.NB;
+  g.hgroups = H / g.BH;
+  g.bgroups = B / g.NB;
+  g.kb_total = S * g.bgroups * g.hgroups;
+  g.kpad = L.kpad;
+  g.n_tiles = (L.kpad + 127) / 128;
+  g.taps = L.taps;
+  g.ctot = L.ctot;
+  return g;
+}
+
+void wg_split(WgradGeom& g, int num_sms) {
+  const int tiles = g.n_tiles * g.num_ctiles * g.taps;
+  int splits = std::max(1, (2 * num_sms) / std::max(tiles, 1));
+  splits = std::min(splits, std::max(1, g.kb_total / 4));
+  g.kb_per_split = (g.kb_total + splits - 1) / splits;
+  g.splits = (g.kb_total + g.kb_per_split - 1) / g.kb_per_split;
+  g.out_split_stride = static_cast<long long>(g.kpad) * g.taps * g.ctot;
+}
+
+int wg_ctiles(WgradGeom& g, const int* src_c, int nsrc) {
+  int coff = 0, n = 0;
+  for (int s = 0; s < nsrc; ++s) {
+    g.src_coff[s] = coff;
+    for (int c0 = 0; c0 < src_c[s]; c0 += 256) {
+      if (n == kWgMaxCTiles) return -1;
+      g.ct_src[n] = s; g.ct_c0[n] = c0; g.ct_w[n] = std::min(256, src_c[s] - c0);
+      ++n;
+    }
+    coff += src_c[s];
+  }
+  g.num_ctiles = n;
+  return coff;
+}
+
+// dWp of one layer from the tape of ALL time steps (called once, after the last processed BPTT step)
+int wgrad_implicit(rac_handle* h, TrainState* T, TLayer& L, int H, int W, const std::vector<Src>& xs, cudaStream_t st) {
+  const int B = T->cfg.batch, S = T->cfg.steps;
+  WgradGeom g = wg_plan(L, B, H, W, S);
+  int src_c[kWgMaxSrc];
+  if (xs.size() > kWgMaxSrc) return fail(h, RAC_ERR_INVALID, "wgrad: %zu sources", xs.size());
+  for (size_t i = 0; i < xs.size(); ++i) { src_c[i] = xs[i].C; g.src_tshift[i] = xs[i].tshift; }
+  if (wg_ctiles(g, src_c, static_cast<int>(xs.size())) != L.ctot) return fail(h, RAC_ERR_INVALID, "wgrad: channel mismatch");
+  wg_split(g, h->num_sms);
+  const size_t out_elems = static_cast<size_t>(g.out_split_stride);
+  if (g.splits > 1 && out_elems * g.splits > T->wg_part_elems) return fail(h, RAC_ERR_STATE, "wgrad: split-K scratch too small");
+  g.out = g.splits > 1 ? T->wg_part : L.dwp;
+  WgradTmaps tm;
+  memset(&tm, 0, sizeof(tm));
+  const size_t M = static_cast<size_t>(B) * H * W;
+  CKR(encode_act_map5(h, &tm.dy, L.dyT, L.kpad, B, H, W, S, M * L.kpad * 2ull, g.BH, g.NB));
+  for (size_t i = 0; i < xs.size(); ++i) {
+    const bf16* base = xs[i].base0 ? xs[i].base0 : xs[i].p;
+    CKR(encode_act_map5(h, &tm.x[i], base, xs[i].C, B, H, W, S, T->step_bytes, g.BH, g.NB));
+  }
+  CK(launch_wgrad_tc(tm, g, st));
+  h->launches++;
+  if (g.splits > 1) {
+    CK(launch_wgrad_reduce(T->wg_part, g.splits, static_cast<long long>(out_elems), g.out_split_stride, L.dwp, st));
+    h->launches++;
+  }
+  return RAC_OK;
+}
+
 // dY (bf16 [M, kpad], packed column order) -> weight gradient (accumulated into L.dwp) and input gradient (segments)
 int conv_backward(rac_handle* h, TrainState* T, int layer, int H, int W, const std::vector<Src>& xs, const bf16* dY,
                   const F32Seg* segs, int nseg, cudaStream_t st) {
@@ -195,24 +278,38 @@ int conv_backward(rac_handle* h, TrainState* T, int layer, int H, int W, const s
   const int B = T->cfg.batch;
   const int M = B * H * W, mpad = round_up(M, 64);
   const int ks = (L.taps == 25) ? 5 : 3;
-  // ---- wgrad: dWp[n][tap*ctot + c] = sum_t sum_m dY_t[m][n] * X_t[shift_tap(m)][c]: this step's operands go to
-  // column block t of the layer's transposed buffers; the GEMM runs once, after the last processed step (t == 0)
   const int S = T->cfg.steps;
-  const int ld = S * mpad;
-  int coff = 0;
-  for (const Src& s : xs) {
-    CK(launch_im2col_t(s.p, B, H, W, s.C, ks, L.ctot, coff, mpad, L.xcolT + static_cast<size_t>(T->cur_t) * mpad, st, ld));
-    coff += s.C;
-  }
-  CK(launch_transpose_bf16(dY, M, L.kpad, mpad, L.kpad, L.dyT + static_cast<size_t>(T->cur_t) * mpad, st, ld));
-  if (T->cur_t == 0) {
-    EpiParams e{};
-    const int ncols = L.taps * L.ctot;
-    e.cout = ncols;
-    e.nseg = 1;
-    e.seg[0] = {0, ncols, L.dwp, ncols, 0, 1};
-    CKR(t_gemm(h, "train.wgrad", {L.kpad / 64, 1, 64, 1, true}, {{L.dyT, ld}}, L.xcolT, ld, ncols, pick_bn(ncols),
-               EPI_F32, e, st));
+  if (T->wgrad_implicit) {
+    // ---- wgrad, implicit GEMM: this step's dY is kept in slot t of the layer's all-steps buffer [S][M][kpad]; the
+    // inputs X_t already live on the tape. ONE launch per layer, after the last processed step (t == 0), contracts over
+    // the rows of all time steps (the weight gradient is a sum over time)
+    CK(cudaMemcpyAsync(L.dyT + static_cast<size_t>(T->cur_t) * M * L.kpad, dY, sizeof(bf16) * static_cast<size_t>(M) * L.kpad,
+                       cudaMemcpyDeviceToDevice, st));
+    if (T->cur_t == 0) {
+      CKR(wgrad_implicit(h, T, L, H, W, xs, st));
+      if (L.d.bias_off) CK(launch_bias_grad(L.dyT, S * M, L.kpad, L.n_packed, L.d.bias_off, T->grads, st));
+    }
+  } else {
+    // ---- wgrad (round-1 path): dWp[n][tap*ctot + c] = sum_t sum_m dY_t[m][n] * X_t[shift_tap(m)][c]: this step's
+    // operands go to column block t of the layer's transposed buffers; the GEMM runs once, after the last processed step
+    const int ld = S * mpad;
+    int coff = 0;
+    for (const Src& s : xs) {
+      CK(launch_im2col_t(s.p, B, H, W, s.C, ks, L.ctot, coff, mpad, L.xcolT + static_cast<size_t>(T->cur_t) * mpad, st, ld));
+      coff += s.C;
+    }
+    CK(launch_transpose_bf16(dY, M, L.kpad, mpad, L.kpad, L.dyT + static_cast<size_t>(T->cur_t) * mpad, st, ld));
+    if (T->cur_t == 0) {
+      EpiParams e{};
+      const int ncols = L.taps * L.ctot;
+      e.cout = ncols;
+      e.nseg = 1;
+      e.seg[0] = {0, ncols, L.dwp, ncols, 0, 1};
+      CKR(t_gemm(h, "train.wgrad", {L.kpad / 64, 1, 64, 1, true}, {{L.dyT, ld}}, L.xcolT, ld, ncols, pick_bn(ncols),
+                 EPI_F32, e, st));
+      // bias gradient = row sums of the all-time-steps dY^T: once, after the last processed step
+      if (L.d.bias_off) CK(launch_bias_grad_rows(L.dyT, ld, L.n_packed, L.d.bias_off, T->grads, st));
+    }
   }
   // ---- dgrad: dX = conv(dY, Wd)
   if (nseg > 0) {
@@ -223,8 +320,6 @@ int conv_backward(rac_handle* h, TrainState* T, int layer, int H, int W, const s
     CKR(t_gemm(h, "train.dgrad", {B, H, W, ks, false}, {{dY, L.kpad}}, L.wd, L.taps * L.kpad, L.ctot, pick_bn(L.ctot),
                EPI_F32, e, st));
   }
-  // bias gradient = row sums of the all-time-steps dY^T: once, after the last processed step
-  if (L.d.bias_off && T->cur_t == 0) CK(launch_bias_grad_rows(L.dyT, ld, L.n_packed, L.d.bias_off, T->grads, st));
   return RAC_OK;
 }
 
@@ -298,7 +393,7 @@ int lstm_backward_gn(rac_handle* h, TrainState* T, int s, int t, const bf16* xin
     CKR(conv_backward(h, T, l == 0 ? kLstm0[s] : kLstm1[s], 6, 8, {{x, g}}, T->dy_a, &seg, 1, st));
     // h_prev: the same layer at step t-1 (first writer of that buffer for this step); nothing before the first step
     F32Seg segh = {0, g, t > 0 ? T->G_hs[s][l][cur ^ 1] : nullptr, g, 0, 0};
-    CKR(conv_backward(h, T, kLstmHH[s] + l, 6, 8, {{hprev, g}}, T->dy_b, &segh, t > 0 ? 1 : 0, st));
+    CKR(conv_backward(h, T, kLstmHH[s] + l, 6, 8, {{hprev, g, T->tape[0].hs[s][l], 1}}, T->dy_b, &segh, t > 0 ? 1 : 0, st));
   }
   return RAC_OK;
 }
@@ -340,7 +435,7 @@ int lstm_backward(rac_handle* h, TrainState* T, int s, int t, const bf16* xin, f
     segs[0] = {0, g, l == 1 ? T->G_hs[s][0][cur] : g_in, g, 0, l == 1 ? 1 : 0};
     // h_prev half: the same layer at step t-1 (first writer of that buffer for this step)
     segs[1] = {g, 2 * g, t > 0 ? T->G_hs[s][l][cur ^ 1] : nullptr, g, 0, 0};
-    CKR(conv_backward(h, T, layer, 6, 8, {{x, g}, {hprev, g}}, T->dy_a, segs, 2, st));
+    CKR(conv_backward(h, T, layer, 6, 8, {{x, g}, {hprev, g, T->tape[0].hs[s][l], 1}}, T->dy_a, segs, 2, st));
   }
   return RAC_OK;
 }
@@ -616,6 +711,11 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
   T->cfg = *cfg;
   T->params = params; T->buffers = buffers; T->grads = grads; T->m = adam_m; T->v = adam_v;
   if (const char* dk = getenv("RAC_TRAIN_DEBUG_KEEP")) T->dbg_keep = atoi(dk);
+  if (const char* wg = getenv("RAC_WGRAD_IM2COL")) T->wgrad_implicit = atoi(wg) ? 0 : 1;
+  {
+    static bool attr = false;
+    if (!attr) { CK(wgrad_tc_set_attributes()); attr = true; }
+  }
   T->gn = h->cfg.lstm_group_norm != 0;
   T->nlayers = T->gn ? RAC_L_COUNT_GN : RAC_L_COUNT;
   const int B = cfg->batch, S = cfg->steps, g = h->cfg.g_dim, z = h->cfg.z_dim;
@@ -645,8 +745,10 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
       TLayer& L = T->L[i];
       L.wp = bp.take<bf16>(static_cast<size_t>(L.n_packed) * L.taps * L.ctot);
       {
+        // dyT: the output gradients of all time steps -- [S][M][kpad] for the implicit-GEMM weight gradient, or the
+        // transposed [kpad][S * mpad] (+ the im2col operand xcolT) of the round-1 path
         const size_t ld = static_cast<size_t>(S) * round_up(static_cast<int>(rows_of(i)), 64);
-        L.xcolT = bp.take<bf16>(static_cast<size_t>(L.taps) * L.ctot * ld);
+        if (!T->wgrad_implicit) L.xcolT = bp.take<bf16>(static_cast<size_t>(L.taps) * L.ctot * ld);
         L.dyT = bp.take<bf16>(static_cast<size_t>(L.kpad) * ld);
       }
       L.wd = bp.take<bf16>(static_cast<size_t>(L.ctot) * L.taps * L.kpad);
@@ -679,7 +781,10 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
       tp.d2a = bp.take<bf16>(M3 * 512); tp.d2b = bp.take<bf16>(M3 * 512); tp.d3a = bp.take<bf16>(M2 * 256);
       tp.d3b = bp.take<bf16>(M2 * 256); tp.d4a = bp.take<bf16>(M1 * 128); tp.d5 = bp.take<bf16>(M0 * 64);
       tp.dcat5 = tp.cat5; tp.dcat4 = tp.cat4; tp.dcat3 = tp.cat3;
-      if (cfg->fixed_skip && t > 0) {
+      // fixed_skip: every step decodes from its own concat buffers (skip halves = copies of step 0's encoder outputs).
+      // Step 0 could use cat* directly, but the all-time-steps weight gradient reads the decoder inputs through ONE
+      // tensor map with a constant step stride, so step 0 gets its own buffers too
+      if (cfg->fixed_skip && (t > 0 || T->wgrad_implicit)) {
         tp.dcat5 = bp.take<bf16>(M0 * 128); tp.dcat4 = bp.take<bf16>(M1 * 256); tp.dcat3 = bp.take<bf16>(M2 * 512);
       }
       for (int i = 0; i < 19; ++i) {
@@ -722,10 +827,41 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
       T->gn_dy = bp.take<float>(M3 * 4 * g);
       T->gn_part = bp.take<float>(static_cast<size_t>(B) * 14 * g);
     }
+    if (T->wgrad_implicit) {
+      // split-K scratch: the largest splits x |dWp| over the layers that need more than one slice
+      size_t need = 4;
+      for (int i = 1; i < T->nlayers; ++i) {
+        const TLayer& L = T->L[i];
+        const size_t rows = rows_of(i);
+        const int W = rows == M0 ? 64 : rows == M1 ? 32 : rows == M2 ? 16 : 8;
+        WgradGeom wg = wg_plan(L, B, W * 3 / 4, W, S);
+        int one_src[1] = {L.ctot};
+        wg_ctiles(wg, one_src, 1);  // (an upper bound on the tile count is enough: more tiles = fewer splits)
+        wg.num_ctiles = std::max(1, L.ctot / 256);
+        wg_split(wg, h->num_sms);
+        if (wg.splits > 1) need = std::max(need, static_cast<size_t>(wg.splits) * static_cast<size_t>(wg.out_split_stride));
+      }
+      T->wg_part_elems = need;
+      T->wg_part = bp.take<float>(need);
+    }
     if (!pass) {
       CK(cudaMalloc(&T->arena, bp.off + 1024));
       CK(cudaMemset(T->arena, 0, bp.off + 1024));
     }
+  }
+  // every step of the tape allocates the same sequence of buffers: one constant stride between time steps
+  T->step_bytes = S > 1 ? static_cast<unsigned long long>(reinterpret_cast<const char*>(T->tape[1].img4) -
+                                                          reinterpret_cast<const char*>(T->tape[0].img4))
+                        : (1ull << 20);
+  for (int t = 1; t < S; ++t) {
+    const Tape &a = T->tape[t - 1], &b = T->tape[t];
+    const char* pa[] = {reinterpret_cast<const char*>(a.img4), reinterpret_cast<const char*>(a.hs[2][1]),
+                        reinterpret_cast<const char*>(a.d5), reinterpret_cast<const char*>(a.dcat3), reinterpret_cast<const char*>(a.xp)};
+    const char* pb[] = {reinterpret_cast<const char*>(b.img4), reinterpret_cast<const char*>(b.hs[2][1]),
+                        reinterpret_cast<const char*>(b.d5), reinterpret_cast<const char*>(b.dcat3), reinterpret_cast<const char*>(b.xp)};
+    for (int k = 0; k < 5; ++k)
+      if (static_cast<unsigned long long>(pb[k] - pa[k]) != T->step_bytes && T->wgrad_implicit)
+        return fail(h, RAC_ERR_STATE, "training tape: time steps are not equally spaced");
   }
   return RAC_OK;
 }
@@ -754,7 +890,8 @@ int rac_train_forward_backward(rac_handle* h, const rac_train_batch* bt, void* s
     CK(launch_pack_weights(T->params, L.d.row_off, L.d.col_off, L.n_packed, L.taps, L.ctot, L.d.flip, L.wp, st));
     CK(launch_transpose_flip(L.wp, L.n_packed, L.taps, L.ctot, L.kpad, L.wd, st));
     if (L.d.bias_off) CK(launch_gather_f32(T->params, L.d.bias_off, L.n_packed, L.bias, st));
-    CK(cudaMemsetAsync(L.dwp, 0, sizeof(float) * L.kpad * L.taps * L.ctot, st));
+    // (the implicit-GEMM weight gradient writes every element of dWp; only the round-1 GEMM accumulates into it)
+    if (!T->wgrad_implicit) CK(cudaMemsetAsync(L.dwp, 0, sizeof(float) * L.kpad * L.taps * L.ctot, st));
   }
   CK(launch_pack_first(T->params + T->L[RAC_L_ENC_C1_0].d.w_off, h->enc_cin, T->wfirst, st));
   CK(cudaMemsetAsync(T->grads, 0, sizeof(float) * T->cfg.n_params, st));

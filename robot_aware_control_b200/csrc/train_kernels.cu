@@ -1,5 +1,7 @@
 // Non-GEMM kernels of the SVG training step (see train_kernels.cuh). Batch 16 per GPU: these are small,
 // memory-bound kernels; the FLOPs of the step live in conv_tc_kernel (forward, dgrad, wgrad).
+#include <algorithm>
+
 #include "train_kernels.cuh"
 #include "epilogue.cuh"
 
@@ -15,46 +17,71 @@ pack_weights_kernel(const float* __restrict__ params, const long long* __restric
                     const int* __restrict__ col_off, int n_packed, int taps, int ctot, int flip,
                     __nv_bfloat16* __restrict__ wp) {
   __shared__ float tile[25][65];
-  const int n = blockIdx.x, c0 = blockIdx.y * 64;
-  const long long ro = row_off[n];
-  for (int j = threadIdx.x; j < 64 * taps; j += blockDim.x) {
-    const int cl = j / taps, tap = j - cl * taps;
-    const int co = col_off[c0 + cl];
-    float v = 0.f;
-    if (ro >= 0 && co >= 0) v = params[ro + co + tap];
-    tile[flip ? taps - 1 - tap : tap][cl] = v;
-  }
-  __syncthreads();
-  for (int j = threadIdx.x; j < 64 * taps; j += blockDim.x) {
-    const int tap = j >> 6, cl = j & 63;
-    wp[(static_cast<long long>(n) * taps + tap) * ctot + c0 + cl] = __float2bfloat16(tile[tap][cl]);
+  const int c0 = blockIdx.y * 64;
+  // a CTA walks several packed rows (a few thousand CTAs of 1600 elements each were launch-bound, not HBM-bound)
+  for (int n = blockIdx.x; n < n_packed; n += gridDim.x) {
+    const long long ro = row_off[n];
+    for (int j = threadIdx.x; j < 64 * taps; j += blockDim.x) {
+      const int cl = j / taps, tap = j - cl * taps;
+      const int co = col_off[c0 + cl];
+      float v = 0.f;
+      if (ro >= 0 && co >= 0) v = __ldcs(params + ro + co + tap);
+      tile[flip ? taps - 1 - tap : tap][cl] = v;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 32 * taps; j += blockDim.x) {
+      const int tap = j >> 5, cl = (j & 31) * 2;
+      *reinterpret_cast<__nv_bfloat162*>(wp + (static_cast<long long>(n) * taps + tap) * ctot + c0 + cl) =
+          __floats2bfloat162_rn(tile[tap][cl], tile[tap][cl + 1]);
+    }
+    __syncthreads();
   }
 }
 cudaError_t launch_pack_weights(const float* params, const long long* row_off, const int* col_off, int n_packed,
                                 int taps, int ctot, int flip, __nv_bfloat16* wp, cudaStream_t s) {
   if (ctot % 64 != 0 || taps > 25) return cudaErrorInvalidValue;
-  pack_weights_kernel<<<dim3(n_packed, ctot / 64), 256, 0, s>>>(params, row_off, col_off, n_packed, taps, ctot, flip, wp);
+  const int gx = std::min(n_packed, std::max(1, 1184 / (ctot / 64)));
+  pack_weights_kernel<<<dim3(gx, ctot / 64), 256, 0, s>>>(params, row_off, col_off, n_packed, taps, ctot, flip, wp);
   return cudaGetLastError();
 }
 
-// wd[c][tap][n] = wp[n][taps - 1 - tap][c] (n padded to kpad with zeros): 32 x 32 shared-memory transposes per tap
-__global__ void __launch_bounds__(1024)
+// wd[c][tap][n] = wp[n][taps - 1 - tap][c] (n padded to kpad with zeros): 64 x 64 shared-memory transposes, one CTA per
+// (64 n, 64 c) block looping over the taps
+__global__ void __launch_bounds__(256)
 transpose_flip_kernel(const __nv_bfloat16* __restrict__ wp, int n_packed, int taps, int ctot, int kpad,
                       __nv_bfloat16* __restrict__ wd) {
-  __shared__ __nv_bfloat16 tile[32][33];
-  const int tap = blockIdx.z;
-  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const int n = n0 + threadIdx.y, c = c0 + threadIdx.x;
-  tile[threadIdx.y][threadIdx.x] =
-      (n < n_packed && c < ctot) ? wp[(static_cast<long long>(n) * taps + (taps - 1 - tap)) * ctot + c] : __float2bfloat16(0.f);
-  __syncthreads();
-  const int co = c0 + threadIdx.y, no = n0 + threadIdx.x;
-  if (co < ctot && no < kpad) wd[(static_cast<long long>(co) * taps + tap) * kpad + no] = tile[threadIdx.x][threadIdx.y];
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int n0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int tap = 0; tap < taps; ++tap) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int n = n0 + ty + r * 8;
+      __nv_bfloat162 v = __floats2bfloat162_rn(0.f, 0.f);
+      if (n < n_packed)
+        v = *reinterpret_cast<const __nv_bfloat162*>(wp + (static_cast<long long>(n) * taps + (taps - 1 - tap)) * ctot + c0 + tx * 2);
+      tile[ty + r * 8][tx * 2] = v.x;
+      tile[ty + r * 8][tx * 2 + 1] = v.y;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int c = c0 + ty + r * 8;
+      const int n = n0 + tx * 2;
+      if (n < kpad) {
+        __nv_bfloat162 v;
+        v.x = tile[tx * 2][ty + r * 8];
+        v.y = tile[tx * 2 + 1][ty + r * 8];
+        *reinterpret_cast<__nv_bfloat162*>(wd + (static_cast<long long>(c) * taps + tap) * kpad + n) = v;
+      }
+    }
+    __syncthreads();
+  }
 }
 cudaError_t launch_transpose_flip(const __nv_bfloat16* wp, int n_packed, int taps, int ctot, int kpad,
                                   __nv_bfloat16* wd, cudaStream_t s) {
-  transpose_flip_kernel<<<dim3((kpad + 31) / 32, (ctot + 31) / 32, taps), dim3(32, 32), 0, s>>>(wp, n_packed, taps, ctot,
-                                                                                              kpad, wd);
+  if (ctot % 64 != 0 || kpad % 2 != 0) return cudaErrorInvalidValue;
+  transpose_flip_kernel<<<dim3((kpad + 63) / 64, ctot / 64), 256, 0, s>>>(wp, n_packed, taps, ctot, kpad, wd);
   return cudaGetLastError();
 }
 
@@ -63,24 +90,29 @@ unpack_grads_kernel(const float* __restrict__ dwp, const long long* __restrict__
                     const int* __restrict__ col_off, int n_packed, int taps, int ctot, int flip,
                     float* __restrict__ grads) {
   __shared__ float tile[25][65];
-  const int n = blockIdx.x, c0 = blockIdx.y * 64;
-  const long long ro = row_off[n];
-  if (ro < 0) return;
-  for (int j = threadIdx.x; j < 64 * taps; j += blockDim.x) {
-    const int tap = j >> 6, cl = j & 63;
-    tile[tap][cl] = dwp[(static_cast<long long>(n) * taps + tap) * ctot + c0 + cl];
-  }
-  __syncthreads();
-  for (int j = threadIdx.x; j < 64 * taps; j += blockDim.x) {
-    const int cl = j / taps, tap = j - cl * taps;
-    const int co = col_off[c0 + cl];
-    if (co >= 0) grads[ro + co + tap] = tile[flip ? taps - 1 - tap : tap][cl];
+  const int c0 = blockIdx.y * 64;
+  for (int n = blockIdx.x; n < n_packed; n += gridDim.x) {
+    const long long ro = row_off[n];
+    if (ro < 0) continue;  // (uniform over the CTA)
+    for (int j = threadIdx.x; j < 16 * taps; j += blockDim.x) {
+      const int tap = j >> 4, cl = (j & 15) * 4;
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(dwp + (static_cast<long long>(n) * taps + tap) * ctot + c0 + cl));
+      tile[tap][cl] = v.x; tile[tap][cl + 1] = v.y; tile[tap][cl + 2] = v.z; tile[tap][cl + 3] = v.w;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 64 * taps; j += blockDim.x) {
+      const int cl = j / taps, tap = j - cl * taps;
+      const int co = col_off[c0 + cl];
+      if (co >= 0) grads[ro + co + tap] = tile[flip ? taps - 1 - tap : tap][cl];
+    }
+    __syncthreads();
   }
 }
 cudaError_t launch_unpack_grads(const float* dwp, const long long* row_off, const int* col_off, int n_packed, int taps,
                                 int ctot, int flip, float* grads, cudaStream_t s) {
   if (ctot % 64 != 0 || taps > 25) return cudaErrorInvalidValue;
-  unpack_grads_kernel<<<dim3(n_packed, ctot / 64), 256, 0, s>>>(dwp, row_off, col_off, n_packed, taps, ctot, flip, grads);
+  const int gx = std::min(n_packed, std::max(1, 1184 / (ctot / 64)));
+  unpack_grads_kernel<<<dim3(gx, ctot / 64), 256, 0, s>>>(dwp, row_off, col_off, n_packed, taps, ctot, flip, grads);
   return cudaGetLastError();
 }
 
@@ -217,26 +249,45 @@ __device__ __forceinline__ void column_partial2(int M, int C, F load) {
 __device__ __forceinline__ void column_fold2(int c, int nsplit, double& s1, double& s2) {
   s1 = s2 = 0.0;
   for (int r = 0; r < nsplit; ++r) {
-    s1 += g_red_part[(0 * kRedSplit + r) * 2048 + c];
-    s2 += g_red_part[(1 * kRedSplit + r) * 2048 + c];
+    s1 += __ldcg(&g_red_part[(0 * kRedSplit + r) * 2048 + c]);  // L2: written by other CTAs (of this launch, possibly)
+    s2 += __ldcg(&g_red_part[(1 * kRedSplit + r) * 2048 + c]);
   }
 }
 inline int red_split(int M) {
   int r = M / 512;
   return r < 1 ? 1 : (r > kRedSplit ? kRedSplit : r);
 }
+// "last block folds": every CTA of a column_partial2 grid publishes its partial sums, then takes a ticket; the CTA that
+// draws the last ticket of its channel block (blockIdx.x) sees all R partials of these 32 channels (release / acquire
+// through the fences around the atomic) and folds them in the fixed order r = 0 .. R-1 -- the result does not depend on
+// which CTA happens to be last, so the reduction stays deterministic while the separate fold launch disappears.
+__device__ unsigned int g_red_ticket[64];  // one counter per 32-channel block (C <= 2048), self-resetting
+__device__ __forceinline__ bool last_block_of_column_group() {
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    const unsigned int t = atomicAdd(&g_red_ticket[blockIdx.x], 1u);
+    s_last = (t == gridDim.y - 1);
+    if (s_last) g_red_ticket[blockIdx.x] = 0u;  // ready for the next launch (stream order)
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last;
+}
 
-__global__ void __launch_bounds__(1024) bn_stats_partial_kernel(const float* __restrict__ raw, int M, int C) {
+__global__ void __launch_bounds__(1024)
+bn_stats_kernel(const float* __restrict__ raw, int M, int C, float* __restrict__ mean, float* __restrict__ rstd,
+                float* __restrict__ rmean, float* __restrict__ rvar, int updates) {
   column_partial2(M, C, [&](int m, int c, float& v1, float& v2) {
     const float x = raw[static_cast<size_t>(m) * C + c];
     v1 = x;
     v2 = x * x;
   });
-}
-__global__ void bn_stats_final_kernel(int M, int C, int nsplit, float* __restrict__ mean, float* __restrict__ rstd,
-                                      float* __restrict__ rmean, float* __restrict__ rvar, int updates) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  if (!last_block_of_column_group()) return;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  if (threadIdx.y != 0 || c >= C) return;
+  const int nsplit = gridDim.y;
   double s1, s2;
   column_fold2(c, nsplit, s1, s2);
   const double mu = s1 / M;
@@ -257,8 +308,7 @@ cudaError_t launch_bn_stats(const float* raw, int M, int C, float* mean, float* 
                             float* running_var, int updates, cudaStream_t s) {
   if (C > 2048) return cudaErrorInvalidValue;
   const int R = red_split(M);
-  bn_stats_partial_kernel<<<dim3((C + 31) / 32, R), dim3(32, 32), 0, s>>>(raw, M, C);
-  bn_stats_final_kernel<<<(C + 127) / 128, 128, 0, s>>>(M, C, R, mean, rstd, running_mean, running_var, updates);
+  bn_stats_kernel<<<dim3((C + 31) / 32, R), dim3(32, 32), 0, s>>>(raw, M, C, mean, rstd, running_mean, running_var, updates);
   return cudaGetLastError();
 }
 
@@ -327,20 +377,20 @@ __device__ __forceinline__ void bn_bwd_point(const BnBwdArgs& a, int m, int c, f
   const float bn = xhat * a.gamma[c] + a.beta[c];
   dz = bn > 0.f ? g : 0.2f * g;
 }
-__global__ void __launch_bounds__(1024) bn_bwd_partial_kernel(BnBwdArgs a, int M) {
+__global__ void __launch_bounds__(1024)
+bn_bwd_sums_kernel(BnBwdArgs a, int M, float* __restrict__ scratch, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   column_partial2(M, a.C, [&](int m, int c, float& v1, float& v2) {
     float dz, xh;
     bn_bwd_point(a, m, c, dz, xh);
     v1 = dz;
     v2 = dz * xh;
   });
-}
-__global__ void bn_bwd_final_kernel(int C, int nsplit, float* __restrict__ scratch, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  if (!last_block_of_column_group()) return;
+  const int C = a.C;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  if (threadIdx.y != 0 || c >= C) return;
   double s1, s2;
-  column_fold2(c, nsplit, s1, s2);
+  column_fold2(c, gridDim.y, s1, s2);
   scratch[c] = static_cast<float>(s1);
   scratch[C + c] = static_cast<float>(s2);
   dbeta[c] += static_cast<float>(s1);
@@ -369,8 +419,7 @@ cudaError_t launch_bn_bwd(const float* dy, int dy_cstride, int dy_coff, int upsa
   const int M = B * H * W;
   if (C > 2048) return cudaErrorInvalidValue;
   const int R = red_split(M);
-  bn_bwd_partial_kernel<<<dim3((C + 31) / 32, R), dim3(32, 32), 0, s>>>(a, M);
-  bn_bwd_final_kernel<<<(C + 127) / 128, 128, 0, s>>>(C, R, scratch, dgamma, dbeta);
+  bn_bwd_sums_kernel<<<dim3((C + 31) / 32, R), dim3(32, 32), 0, s>>>(a, M, scratch, dgamma, dbeta);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const size_t total = static_cast<size_t>(M) * C;
@@ -738,23 +787,47 @@ cudaError_t launch_im2col_t(const __nv_bfloat16* src, int B, int H, int W, int C
 }
 
 // ------------------------------------------------------------------------------------------------ optimiser, noise
-__global__ void __launch_bounds__(256)
+// torch.optim.Adam (no weight decay / amsgrad): 7 fp32 streams (p, g, m, v read; p, m, v written), 128-bit accesses,
+// grid-stride over a grid of a few CTAs per SM, streaming cache hints (nothing is re-read before the next step)
+__global__ void __launch_bounds__(512)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float gi = g[i];
-  const float mi = b1 * m[i] + (1.f - b1) * gi;
-  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-  m[i] = mi;
-  v[i] = vi;
-  p[i] -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  const float step = lr / bc1;
+  auto upd = [&](float& pi, float gi, float& mi, float& vi) {
+    mi = b1 * mi + (1.f - b1) * gi;
+    vi = b2 * vi + (1.f - b2) * gi * gi;
+    pi -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  };
+  const long long n4 = n >> 2;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pi = __ldcs(reinterpret_cast<const float4*>(p) + i);
+    const float4 gi = __ldcs(reinterpret_cast<const float4*>(g) + i);
+    float4 mi = __ldcs(reinterpret_cast<const float4*>(m) + i);
+    float4 vi = __ldcs(reinterpret_cast<const float4*>(v) + i);
+    upd(pi.x, gi.x, mi.x, vi.x);
+    upd(pi.y, gi.y, mi.y, vi.y);
+    upd(pi.z, gi.z, mi.z, vi.z);
+    upd(pi.w, gi.w, mi.w, vi.w);
+    __stcs(reinterpret_cast<float4*>(m) + i, mi);
+    __stcs(reinterpret_cast<float4*>(v) + i, vi);
+    __stcs(reinterpret_cast<float4*>(p) + i, pi);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {  // tail
+    const long long i = (n4 << 2) + threadIdx.x;
+    float pi = p[i], mi = m[i], vi = v[i];
+    upd(pi, g[i], mi, vi);
+    m[i] = mi; v[i] = vi; p[i] = pi;
+  }
 }
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
                         float eps, int t, cudaStream_t s) {
   const float bc1 = 1.f - powf(b1, static_cast<float>(t));
   const float bc2 = sqrtf(1.f - powf(b2, static_cast<float>(t)));
-  adam_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2);
+  if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+       reinterpret_cast<uintptr_t>(v)) & 15)
+    return cudaErrorInvalidValue;
+  adam_kernel<<<148 * 8, 512, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,219 @@
+// Weight gradient of a convolution as an IMPLICIT GEMM on tcgen05, straight from the NHWC tensors of the tape:
+//
+//   dWp[n][tap * ctot + c] = sum over (t, b, y, x) of  dY_t[(b, y, x)][n] * X_t[(b, y + kh - pad, x + kw - pad)][c]
+//
+// (reference: the `.backward()` of every nn.Conv2d inside PredictionTrainer._train_step, src/prediction/trainer.py:459-460;
+// layers of vgg_64.py:8-18,87-121,196-221, lstm.py:121-127, dynamics.py:496-516). The contraction runs over the rows of
+// the activation maps, which are the SLOW dimension of an NHWC tensor, so both MMA operands are "MN-major": a TMA box
+// {64 channels, W, BH, NB, 1 step} lands in shared memory as rows of 128 B (64 channels of one position), and with the
+// 128-byte swizzle that is exactly the canonical MN-major SWIZZLE_128B layout of tcgen05 (8 K-rows x 64 MN-elements per
+// 1024-byte atom; SBO = 1024 B between groups of 8 positions, LBO = distance between two 64-channel boxes). Nothing is
+// transposed or replicated in memory: the filter tap is a shift of the TMA box coordinates with out-of-bounds zero fill
+// (the zero padding of the convolution), the sum over the time steps of BPTT is a fifth tensor-map dimension whose stride
+// is the size of one tape step, and `h_{t-1}` of a ConvLSTM is the `h` tensor read at step coordinate t - 1 (t = 0 is out
+// of bounds = the zero initial state). Round 1 materialised im2col(X)^T and dY^T in HBM instead (26 % of the step).
+//
+// One CTA = one output tile [128 packed output channels] x [<= 256 input channels of one source] of one filter tap, for
+// one slice of the contraction (split-K partials are summed in a fixed order by wgrad_reduce_kernel: deterministic).
+//   warp 0: TMA producer, warp 1: MMA issuer (one thread), warp 2: TMEM allocator, warps 4-7: epilogue (TMEM -> fp32 global)
+#include "ptx.cuh"
+#include "wgrad_tc.cuh"
+
+namespace rac {
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kMaxRows = 64;                       // positions per k-block (K of one pipeline stage)
+constexpr int kBoxBytesMax = kMaxRows * 128;       // one 64-channel box
+constexpr int kStageBytes = 6 * kBoxBytesMax;      // A: 2 boxes (128 output channels), B: up to 4 boxes (256 input channels)
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024;
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+// MN-major SWIZZLE_128B operand: 64 MN-elements (128 B) per K-row, 8 K-rows per 1024-byte atom
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);           // start address
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;     // leading byte offset: next 64-element MN group
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                     // stride byte offset: next group of 8 K-rows
+  d |= static_cast<uint64_t>(1) << 46;                             // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                             // SWIZZLE_128B
+  return d;
+}
+// bf16 x bf16 -> fp32, A and B both MN-major (bits 15 / 16), M = 128
+__device__ __forceinline__ uint32_t umma_idesc_bf16_mn(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(128 >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bar_base = smem + kStages * kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // tile decode: blockIdx.x = (tap, c tile, n tile), blockIdx.y = K split
+  int t_id = blockIdx.x;
+  const int n_tile = t_id % g.n_tiles;
+  t_id /= g.n_tiles;
+  const int ct = t_id % g.num_ctiles;
+  const int tap = t_id / g.num_ctiles;
+  const int kh = tap / g.ks, kw = tap - kh * g.ks;
+  const int src = g.ct_src[ct], c0 = g.ct_c0[ct], cw = g.ct_w[ct];
+  const int nb_boxes = cw >> 6;
+  const int n0 = n_tile * 128;
+  const int a_boxes = (g.kpad - n0) >= 128 ? 2 : 1;  // output channels beyond kpad do not exist: rows never written
+  const int kb_begin = blockIdx.y * g.kb_per_split;
+  const int kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
+  const uint32_t box_bytes = static_cast<uint32_t>(g.rows) * 128u;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm.dy);
+    tma_prefetch_desc(&tm.x[src]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      // k-block -> (step, candidate group, row group)
+      const int hg = kb % g.hgroups;
+      const int rest = kb / g.hgroups;
+      const int bg = rest % g.bgroups;
+      const int t = rest / g.bgroups;
+      const int y0 = hg * g.BH, b0 = bg * g.NB;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* sa = smem + stage * kStageBytes;
+      uint8_t* sb = sa + 2 * kBoxBytesMax;
+      mbar_arrive_expect_tx(&full_bar[stage], (a_boxes + nb_boxes) * box_bytes);
+      for (int j = 0; j < a_boxes; ++j)
+        tma_load_5d(&tm.dy, &full_bar[stage], sa + j * box_bytes, n0 + j * 64, 0, y0, b0, t);
+      for (int j = 0; j < nb_boxes; ++j)
+        tma_load_5d(&tm.x[src], &full_bar[stage], sb + j * box_bytes, c0 + j * 64, kw - g.pad, y0 + kh - g.pad, b0,
+                    t - g.src_tshift[src]);
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = umma_idesc_bf16_mn(cw);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t accumulate = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+      const uint32_t sb = sa + 2 * kBoxBytesMax;
+      const uint64_t adesc = umma_desc_sw128_mn(sa, box_bytes);
+      const uint64_t bdesc = umma_desc_sw128_mn(sb, box_bytes);
+      for (int k = 0; k < g.rows / 16; ++k) {
+        // 16 positions = two 1024-byte atoms = 2048 B further along K: + 128 in the (addr >> 4) field
+        umma_bf16_ss(tmem_base, adesc + 128u * k, bdesc + 128u * k, idesc, accumulate);
+        accumulate = 1;
+      }
+      umma_commit(&empty_bar[stage]);
+      if (kb == kb_end - 1) umma_commit(tmem_full);
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM lane = output channel n, column = input channel c =====================
+    const int q = warp - 4;  // TMEM lanes 32 q .. 32 q + 31
+    const int n = n0 + q * 32 + lane;
+    const long long ld = static_cast<long long>(g.taps) * g.ctot;
+    float* out = g.out + static_cast<long long>(blockIdx.y) * g.out_split_stride + static_cast<long long>(n) * ld +
+                 static_cast<long long>(tap) * g.ctot + g.src_coff[src] + c0;
+    if (kb_end > kb_begin) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+    }
+    for (int cc = 0; cc < cw; cc += 32) {
+      float v[32];
+      if (kb_end > kb_begin) {
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cc, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      }
+      if (n < g.kpad) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(out + cc + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// out[i] = sum over splits (in order) of part[s][i]
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float4* __restrict__ part, int splits, long long n4, long long stride4, float4* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = part[i];
+  for (int s = 1; s < splits; ++s) {
+    const float4 b = part[s * stride4 + i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  out[i] = a;
+}
+
+}  // namespace
+
+cudaError_t wgrad_tc_set_attributes() {
+  return cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+}
+
+cudaError_t launch_wgrad_tc(const WgradTmaps& tm, const WgradGeom& g, cudaStream_t s) {
+  if (g.rows % 16 || g.rows > kMaxRows || g.num_ctiles < 1 || g.num_ctiles > kWgMaxCTiles) return cudaErrorInvalidValue;
+  dim3 grid(static_cast<unsigned>(g.n_tiles * g.num_ctiles * g.taps), static_cast<unsigned>(g.splits));
+  wgrad_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(tm, g);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wgrad_reduce(const float* part, int splits, long long n, long long split_stride, float* out,
+                                cudaStream_t s) {
+  if ((n & 3) || (split_stride & 3)) return cudaErrorInvalidValue;
+  const long long n4 = n / 4;
+  wgrad_reduce_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, s>>>(
+      reinterpret_cast<const float4*>(part), splits, n4, split_stride / 4, reinterpret_cast<float4*>(out));
+  return cudaGetLastError();
+}
+
+}  // namespace rac
