@@ -46,7 +46,11 @@ struct VggRt {  // one vgg_layer (conv3x3 no bias + BatchNorm + LeakyReLU) at on
   float* rstd = nullptr;
 };
 
-struct Tape {  // everything the backward pass of one time step needs
+// Everything the backward pass of one time step needs. The tape is TIME-MAJOR: every field below is a slice of ONE
+// allocation [steps][...], so a tensor of `n` consecutive steps is also one contiguous NHWC tensor of n * B images.
+// That is what lets (a) every non-recurrent layer run ONCE per training step over all time steps (teacher-forced
+// clips) and (b) the weight-gradient kernel walk all steps through one 5-D tensor map.
+struct Tape {
   float* img4;
   bf16 *a1, *cat5, *p1, *a2, *cat4, *p2, *a3a, *a3b, *cat3, *p3, *a4a, *a4b, *h4;
   bf16 *aux, *auxp, *pin, *postin, *fin, *z, *zprior;
@@ -55,13 +59,26 @@ struct Tape {  // everything the backward pass of one time step needs
   float* gates[3][2];
   float *raw_ih[3][2], *raw_hh[3][2], *c_raw[3][2], *gn_stats[3][2];  // lstm_group_norm only
   bf16 *d2a, *d2b, *d3a, *d3b, *d4a, *d5;
-  bf16 *dcat5, *dcat4, *dcat3;  // decoder concat buffers: == cat* unless fixed_skip and t > 0
+  bf16 *dcat5, *dcat4, *dcat3;  // decoder concat buffers: == cat* unless fixed_skip
   VggRt vgg[19];
   float *mu_p, *lv_p, *mu, *lv, *x4;
   float *eps_p, *eps_q;
   float* xp;          // composited prediction (B,3,H,W): the next step's input under scheduled sampling
   const float* xj;    // this step's input frame (ground truth or the previous step's xp)
   int sampled;        // 1: xj is the model's own previous prediction (gradient flows back, trainer.py:354)
+};
+
+// time steps [t0, t0 + n) handled by ONE launch per layer: n = steps for a teacher-forced clip, n = 1 when a step
+// consumes the previous step's prediction (scheduled sampling) or with fixed_skip
+struct Span {
+  int t0, n;
+};
+
+// a gradient accumulator (fp32 NHWC) with one slot per time step, time-major like the tape
+struct GBuf {
+  float* p = nullptr;
+  size_t n = 0;
+  float* at(int t) const { return p + static_cast<size_t>(t) * n; }
 };
 
 struct TrainState {
@@ -72,34 +89,30 @@ struct TrainState {
   float* gn_dy = nullptr;     // [M3, 4g] gate pre-activation gradients of the cell being processed
   float* gn_part = nullptr;   // [B][14 g] per-sample partials of the GroupNorm affine gradients
   float *params = nullptr, *buffers = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr;
-  // weight gradients: 1 = implicit GEMM over all time steps straight from the tape (wgrad_tc.cu); 0 = round-1 path
-  // (materialised im2col(X)^T / dY^T + plain GEMM; RAC_WGRAD_IM2COL=1, kept for A/B measurements and cross-checks)
-  int wgrad_implicit = 1;
-  unsigned long long step_bytes = 0;  // distance between the same tape buffer of two consecutive time steps
+  int per_step = 0;                   // RAC_TRAIN_PER_STEP=1: never batch the time steps (A/B measurements, cross-checks)
   float* wg_part = nullptr;           // split-K partials of the layer being processed
   size_t wg_part_elems = 0;
   float* wfirst = nullptr;  // [9*cin][64]
   float* zero64 = nullptr;
   std::vector<Tape> tape;
   void* arena = nullptr;
-  // gradient accumulators (fp32 NHWC)
-  float *G_d5, *G_cat5, *G_d4a, *G_cat4, *G_d3b, *G_d3a, *G_cat3, *G_d2b, *G_d2a, *G_fin, *G_pin, *G_postin, *G_z, *G_h4;
-  float *G_a4b, *G_a4a, *G_p3, *G_a3b, *G_a3a, *G_p2, *G_a2, *G_p1, *G_a1;
+  GBuf G_d5, G_cat5, G_d4a, G_cat4, G_d3b, G_d3a, G_cat3, G_d2b, G_d2a, G_fin, G_pin, G_postin, G_z, G_h4;
+  GBuf G_a4b, G_a4a, G_p3, G_a3b, G_a3a, G_p2, G_a2, G_p1, G_a1;
   float *G_skip5, *G_skip4, *G_skip3;  // fixed_skip: skip-half gradients summed over the steps ([M, C] fp32)
-  float* G_hs[3][2][2];
+  // dL/dh_t of every ConvLSTM cell, one slot per step, zeroed before the backward pass; every contribution is added:
+  // decoder / gaussian heads / the cell above at step t, and the cell's own gate convolution of step t + 1
+  GBuf DH[3][2];
   float* G_dc[3][2];
   float* G_img[2];       // gradient w.r.t. a sampled input frame, ping-pong across steps
   float* dbg_draw32 = nullptr;  // RAC_TRAIN_DEBUG_KEEP=1: first-layer raw gradient of the last SAMPLED step (tests)
   int dbg_keep = 0;
-  bf16 *dy_a, *dy_b;     // bf16 gradient operands (largest [M, C])
-  int cur_t = 0;         // time step being processed by the backward pass (column block of the wgrad operands)
-  float* bn_scratch;
-  float* draw32;         // fp32 copy of the first layer's raw gradient
+  float* bn_scratch;     // [steps][2 * 2048]
+  GBuf draw32;           // fp32 copy of the first layer's raw gradient
   float* fw_part;        // per-CTA partial sums of the first layer's weight gradient [kFwBlocks][45 * 64]
   bf16* hzero;
   float* czero;
-  float* loss_part;      // [B]
-  float* kl_tmp;
+  float* loss_part;      // [steps * B]
+  float* metric_part;    // [max(2 * steps * B, 64)]
   int adam_t = 0;
   int M[4];
 };
@@ -177,21 +190,22 @@ int tile_block_n(int n_packed, int epi) {
 // ------------------------------------------------------------------ forward pieces
 struct VggDef { int layer, H, W, cin, cout; };
 
+// one vgg_layer over the n * B images of a span: convolution -> per-step BatchNorm statistics -> normalise + LeakyReLU
 int vgg_forward(rac_handle* h, TrainState* T, VggRt& rt, const VggDef& d, const bf16* in, bf16* out, int cstride,
-                int coff, int up, int updates, cudaStream_t st) {
+                int coff, int up, int updates, Span sp, cudaStream_t st) {
   const TLayer& L = T->L[d.layer];
-  const int B = T->cfg.batch;
+  const int B = T->cfg.batch, nb = sp.n * B;
   EpiParams e{};
   e.cout = L.n_packed;
   e.nseg = 1;
   e.seg[0] = {0, L.n_packed, rt.raw, d.cout, 0, 0};
   if (L.n_packed != d.cout) return fail(h, RAC_ERR_INVALID, "vgg layer %d: cout %d must be a multiple of the pack granularity", d.layer, d.cout);
-  CKR(t_gemm(h, "train.vgg.fwd", {B, d.H, d.W, 3, false}, {{in, d.cin}}, L.wp, 9 * d.cin, L.n_packed,
+  CKR(t_gemm(h, "train.vgg.fwd", {nb, d.H, d.W, 3, false}, {{in, d.cin}}, L.wp, 9 * d.cin, L.n_packed,
              pick_bn(L.n_packed), EPI_F32, e, st));
   const int M = B * d.H * d.W;
-  CK(launch_bn_stats(rt.raw, M, d.cout, rt.mean, rt.rstd, T->buffers + L.d.rmean_off, T->buffers + L.d.rvar_off, updates, st));
-  CK(launch_bn_act(rt.raw, rt.mean, rt.rstd, T->params + L.d.gamma_off, T->params + L.d.beta_off, B, d.H, d.W, d.cout,
-                   out, cstride, coff, up, st));
+  CK(launch_bn_stats(rt.raw, M, d.cout, rt.mean, rt.rstd, T->buffers + L.d.rmean_off, T->buffers + L.d.rvar_off, updates, st, sp.n));
+  CK(launch_bn_act(rt.raw, rt.mean, rt.rstd, T->params + L.d.gamma_off, T->params + L.d.beta_off, nb, d.H, d.W, d.cout,
+                   out, cstride, coff, up, st, sp.n));
   return RAC_OK;
 }
 
@@ -259,8 +273,9 @@ int wgrad_implicit(rac_handle* h, TrainState* T, TLayer& L, int H, int W, const 
   const size_t M = static_cast<size_t>(B) * H * W;
   CKR(encode_act_map5(h, &tm.dy, L.dyT, L.kpad, B, H, W, S, M * L.kpad * 2ull, g.BH, g.NB));
   for (size_t i = 0; i < xs.size(); ++i) {
+    // time-major tape: step t of a tensor lies B * H * W * C elements after step t - 1
     const bf16* base = xs[i].base0 ? xs[i].base0 : xs[i].p;
-    CKR(encode_act_map5(h, &tm.x[i], base, xs[i].C, B, H, W, S, T->step_bytes, g.BH, g.NB));
+    CKR(encode_act_map5(h, &tm.x[i], base, xs[i].C, B, H, W, S, M * xs[i].C * 2ull, g.BH, g.NB));
   }
   CK(launch_wgrad_tc(tm, g, st));
   h->launches++;
@@ -271,45 +286,32 @@ int wgrad_implicit(rac_handle* h, TrainState* T, TLayer& L, int H, int W, const 
   return RAC_OK;
 }
 
-// dY (bf16 [M, kpad], packed column order) -> weight gradient (accumulated into L.dwp) and input gradient (segments)
+// slot of time step t in a layer's all-steps output-gradient buffer [steps][M][kpad] (bf16 GEMM operand)
+bf16* dy_slot(TrainState* T, int layer, int H, int W, int t) {
+  const TLayer& L = T->L[layer];
+  return L.dyT + static_cast<size_t>(t) * T->cfg.batch * H * W * L.kpad;
+}
+
+// Backward of one convolution for the steps of `sp`. dY (bf16 [n * M, kpad], packed column order) normally IS the
+// layer's slot (its producer wrote it there). xs = the concatenated inputs at step sp.t0 (time-major: the following
+// steps are contiguous); for the weight gradient, which runs ONCE per training step after the last processed time step
+// (t0 == 0) and contracts over the rows of all steps, xs[i].base0 / tshift say where step 0 of that input lives.
 int conv_backward(rac_handle* h, TrainState* T, int layer, int H, int W, const std::vector<Src>& xs, const bf16* dY,
-                  const F32Seg* segs, int nseg, cudaStream_t st) {
+                  const F32Seg* segs, int nseg, Span sp, cudaStream_t st) {
   TLayer& L = T->L[layer];
-  const int B = T->cfg.batch;
-  const int M = B * H * W, mpad = round_up(M, 64);
+  const int B = T->cfg.batch, nb = sp.n * B;
+  const size_t M = static_cast<size_t>(B) * H * W;
   const int ks = (L.taps == 25) ? 5 : 3;
   const int S = T->cfg.steps;
-  if (T->wgrad_implicit) {
-    // ---- wgrad, implicit GEMM: this step's dY is kept in slot t of the layer's all-steps buffer [S][M][kpad]; the
-    // inputs X_t already live on the tape. ONE launch per layer, after the last processed step (t == 0), contracts over
-    // the rows of all time steps (the weight gradient is a sum over time)
-    CK(cudaMemcpyAsync(L.dyT + static_cast<size_t>(T->cur_t) * M * L.kpad, dY, sizeof(bf16) * static_cast<size_t>(M) * L.kpad,
-                       cudaMemcpyDeviceToDevice, st));
-    if (T->cur_t == 0) {
-      CKR(wgrad_implicit(h, T, L, H, W, xs, st));
-      if (L.d.bias_off) CK(launch_bias_grad(L.dyT, S * M, L.kpad, L.n_packed, L.d.bias_off, T->grads, st));
-    }
-  } else {
-    // ---- wgrad (round-1 path): dWp[n][tap*ctot + c] = sum_t sum_m dY_t[m][n] * X_t[shift_tap(m)][c]: this step's
-    // operands go to column block t of the layer's transposed buffers; the GEMM runs once, after the last processed step
-    const int ld = S * mpad;
-    int coff = 0;
-    for (const Src& s : xs) {
-      CK(launch_im2col_t(s.p, B, H, W, s.C, ks, L.ctot, coff, mpad, L.xcolT + static_cast<size_t>(T->cur_t) * mpad, st, ld));
-      coff += s.C;
-    }
-    CK(launch_transpose_bf16(dY, M, L.kpad, mpad, L.kpad, L.dyT + static_cast<size_t>(T->cur_t) * mpad, st, ld));
-    if (T->cur_t == 0) {
-      EpiParams e{};
-      const int ncols = L.taps * L.ctot;
-      e.cout = ncols;
-      e.nseg = 1;
-      e.seg[0] = {0, ncols, L.dwp, ncols, 0, 1};
-      CKR(t_gemm(h, "train.wgrad", {L.kpad / 64, 1, 64, 1, true}, {{L.dyT, ld}}, L.xcolT, ld, ncols, pick_bn(ncols),
-                 EPI_F32, e, st));
-      // bias gradient = row sums of the all-time-steps dY^T: once, after the last processed step
-      if (L.d.bias_off) CK(launch_bias_grad_rows(L.dyT, ld, L.n_packed, L.d.bias_off, T->grads, st));
-    }
+  bf16* slot = dy_slot(T, layer, H, W, sp.t0);
+  if (dY != slot)
+    CK(cudaMemcpyAsync(slot, dY, sizeof(bf16) * M * sp.n * L.kpad, cudaMemcpyDeviceToDevice, st));
+  if (sp.t0 == 0) {
+    std::vector<Src> x0 = xs;
+    for (Src& s : x0)
+      if (!s.base0) s.base0 = s.p;  // xs are the inputs of step t0 == 0
+    CKR(wgrad_implicit(h, T, L, H, W, x0, st));
+    if (L.d.bias_off) CK(launch_bias_grad(L.dyT, static_cast<int>(S * M), L.kpad, L.n_packed, L.d.bias_off, T->grads, st));
   }
   // ---- dgrad: dX = conv(dY, Wd)
   if (nseg > 0) {
@@ -317,19 +319,20 @@ int conv_backward(rac_handle* h, TrainState* T, int layer, int H, int W, const s
     e.cout = L.ctot;
     e.nseg = nseg;
     for (int i = 0; i < nseg; ++i) e.seg[i] = segs[i];
-    CKR(t_gemm(h, "train.dgrad", {B, H, W, ks, false}, {{dY, L.kpad}}, L.wd, L.taps * L.kpad, L.ctot, pick_bn(L.ctot),
+    CKR(t_gemm(h, "train.dgrad", {nb, H, W, ks, false}, {{slot, L.kpad}}, L.wd, L.taps * L.kpad, L.ctot, pick_bn(L.ctot),
                EPI_F32, e, st));
   }
   return RAC_OK;
 }
 
 int vgg_backward(rac_handle* h, TrainState* T, VggRt& rt, const VggDef& d, const bf16* in, const float* dy,
-                 int dy_cstride, int dy_coff, int up, const F32Seg* segs, int nseg, cudaStream_t st) {
+                 int dy_cstride, int dy_coff, int up, const F32Seg* segs, int nseg, Span sp, cudaStream_t st) {
   const TLayer& L = T->L[d.layer];
+  bf16* slot = dy_slot(T, d.layer, d.H, d.W, sp.t0);
   CK(launch_bn_bwd(dy, dy_cstride, dy_coff, up, rt.raw, rt.mean, rt.rstd, T->params + L.d.gamma_off,
-                   T->params + L.d.beta_off, T->cfg.batch, d.H, d.W, d.cout, T->bn_scratch, T->dy_a, nullptr,
-                   T->grads + L.d.gamma_off, T->grads + L.d.beta_off, st));
-  return conv_backward(h, T, d.layer, d.H, d.W, {{in, d.cin}}, T->dy_a, segs, nseg, st);
+                   T->params + L.d.beta_off, sp.n * T->cfg.batch, d.H, d.W, d.cout, T->bn_scratch, slot, nullptr,
+                   T->grads + L.d.gamma_off, T->grads + L.d.beta_off, st, sp.n));
+  return conv_backward(h, T, d.layer, d.H, d.W, {{in, d.cin}}, slot, segs, nseg, sp, st);
 }
 
 const int kLstm0[3] = {RAC_L_PRIOR_LSTM0, RAC_L_POST_LSTM0, RAC_L_FP_LSTM0};
@@ -378,22 +381,26 @@ int lstm_forward_gn(rac_handle* h, TrainState* T, int s, int t, const bf16* xin,
   return RAC_OK;
 }
 
-int lstm_backward_gn(rac_handle* h, TrainState* T, int s, int t, const bf16* xin, float* g_in, int cur, cudaStream_t st) {
+// backward of one NormConvLSTMCell stack at step t; dL/dh_t of both cells is complete in DH[s][l][t] by now
+int lstm_backward_gn(rac_handle* h, TrainState* T, int s, int t, const bf16* xin, float* g_in, cudaStream_t st) {
   const int g = h->cfg.g_dim;
   Tape& tp = T->tape[t];
+  const Span one{t, 1};
   for (int l = 1; l >= 0; --l) {
+    const int li = l == 0 ? kLstm0[s] : kLstm1[s], lh = kLstmHH[s] + l;
     GnCellArgs a = gn_args(h, T, s, l, t);
-    a.dh = T->G_hs[s][l][cur]; a.dc = T->G_dc[s][l]; a.dy = T->gn_dy; a.d_ih = T->dy_a; a.d_hh = T->dy_b;
+    a.dh = T->DH[s][l].at(t); a.dc = T->G_dc[s][l]; a.dy = T->gn_dy;
+    a.d_ih = dy_slot(T, li, 6, 8, t); a.d_hh = dy_slot(T, lh, 6, 8, t);
     a.part = T->gn_part;
     CK(launch_gn_cell_bwd(a, T->grads, st));
     const bf16* x = l == 0 ? xin : tp.hs[s][0];
     const bf16* hprev = t > 0 ? T->tape[t - 1].hs[s][l] : T->hzero;
     // input: layer 1 feeds layer 0's dh (+=), layer 0 feeds the stack input (=)
-    F32Seg seg = {0, g, l == 1 ? T->G_hs[s][0][cur] : g_in, g, 0, l == 1 ? 1 : 0};
-    CKR(conv_backward(h, T, l == 0 ? kLstm0[s] : kLstm1[s], 6, 8, {{x, g}}, T->dy_a, &seg, 1, st));
-    // h_prev: the same layer at step t-1 (first writer of that buffer for this step); nothing before the first step
-    F32Seg segh = {0, g, t > 0 ? T->G_hs[s][l][cur ^ 1] : nullptr, g, 0, 0};
-    CKR(conv_backward(h, T, kLstmHH[s] + l, 6, 8, {{hprev, g, T->tape[0].hs[s][l], 1}}, T->dy_b, &segh, t > 0 ? 1 : 0, st));
+    F32Seg seg = {0, g, l == 1 ? T->DH[s][0].at(t) : g_in, g, 0, l == 1 ? 1 : 0};
+    CKR(conv_backward(h, T, li, 6, 8, {{x, g}}, a.d_ih, &seg, 1, one, st));
+    // h_prev: the same cell at step t - 1 (+=); nothing before the first step
+    F32Seg segh = {0, g, t > 0 ? T->DH[s][l].at(t - 1) : nullptr, g, 0, 1};
+    CKR(conv_backward(h, T, lh, 6, 8, {{hprev, g, T->tape[0].hs[s][l], 1}}, a.d_hh, &segh, t > 0 ? 1 : 0, one, st));
   }
   return RAC_OK;
 }
@@ -420,22 +427,24 @@ int lstm_forward(rac_handle* h, TrainState* T, int s, int t, const bf16* xin, cu
 }
 
 // backward of one ConvLSTM stack at step t; the gradient w.r.t. the stack input lands in `g_in` (=)
-int lstm_backward(rac_handle* h, TrainState* T, int s, int t, const bf16* xin, float* g_in, int cur, cudaStream_t st) {
-  if (T->gn) return lstm_backward_gn(h, T, s, t, xin, g_in, cur, st);
+int lstm_backward(rac_handle* h, TrainState* T, int s, int t, const bf16* xin, float* g_in, cudaStream_t st) {
+  if (T->gn) return lstm_backward_gn(h, T, s, t, xin, g_in, st);
   const int B = T->cfg.batch, g = h->cfg.g_dim, M = B * 48;
   Tape& tp = T->tape[t];
+  const Span one{t, 1};
   for (int l = 1; l >= 0; --l) {
     const int layer = l == 0 ? kLstm0[s] : kLstm1[s];
     const float* cprev = t > 0 ? T->tape[t - 1].cs[s][l] : nullptr;
-    CK(launch_lstm_bwd(T->G_hs[s][l][cur], T->G_dc[s][l], tp.gates[s][l], cprev, tp.cs[s][l], M, g, T->dy_a, st));
+    bf16* slot = dy_slot(T, layer, 6, 8, t);
+    CK(launch_lstm_bwd(T->DH[s][l].at(t), T->G_dc[s][l], tp.gates[s][l], cprev, tp.cs[s][l], M, g, slot, st));
     const bf16* x = l == 0 ? xin : tp.hs[s][0];
     const bf16* hprev = t > 0 ? T->tape[t - 1].hs[s][l] : T->hzero;
     F32Seg segs[2];
     // input half: layer 1 feeds layer 0's dh (+=), layer 0 feeds the stack input (=)
-    segs[0] = {0, g, l == 1 ? T->G_hs[s][0][cur] : g_in, g, 0, l == 1 ? 1 : 0};
-    // h_prev half: the same layer at step t-1 (first writer of that buffer for this step)
-    segs[1] = {g, 2 * g, t > 0 ? T->G_hs[s][l][cur ^ 1] : nullptr, g, 0, 0};
-    CKR(conv_backward(h, T, layer, 6, 8, {{x, g}, {hprev, g, T->tape[0].hs[s][l], 1}}, T->dy_a, segs, 2, st));
+    segs[0] = {0, g, l == 1 ? T->DH[s][0].at(t) : g_in, g, 0, l == 1 ? 1 : 0};
+    // h_prev half: the same cell at step t - 1 (+=)
+    segs[1] = {g, 2 * g, t > 0 ? T->DH[s][l].at(t - 1) : nullptr, g, 0, 1};
+    CKR(conv_backward(h, T, layer, 6, 8, {{x, g}, {hprev, g, T->tape[0].hs[s][l], 1}}, slot, segs, 2, one, st));
   }
   return RAC_OK;
 }
@@ -451,77 +460,122 @@ const VggDef kDec[9] = {{RAC_L_DEC_UPC2_0, 6, 8, 0, 512},     {RAC_L_DEC_UPC2_1,
 VggDef enc_def(const rac_handle* h, int i) { VggDef d = kEnc[i]; if (i == 9) d.cout = h->cfg.g_dim; return d; }
 VggDef dec_def(const rac_handle* h, int i) { VggDef d = kDec[i]; if (i == 0) d.cin = h->cfg.g_dim; return d; }
 
-int train_forward_step(rac_handle* h, TrainState* T, const rac_train_batch* bt, int t, cudaStream_t st) {
+// ------------------------------------------------------------------ forward phases
+// Each phase handles the time steps of `sp` with ONE launch per layer (n * B images). A teacher-forced clip runs every
+// non-recurrent phase once for all steps; only the ConvLSTM cells are stepped through time.
+struct StepIO {
+  const float *x_j, *m_j, *m_i, *r_j, *r_i, *a_j, *x_i;
+};
+
+StepIO step_io(const rac_handle* h, const TrainState* T, const rac_train_batch* bt, int t) {
   const rac_config& c = h->cfg;
-  const int B = T->cfg.batch, g = c.g_dim, z = c.z_dim;
+  const size_t B = T->cfg.batch, HW = 48 * 64;
+  StepIO io{};
+  io.x_j = T->tape[t].xj;
+  io.x_i = bt->images + static_cast<size_t>(t + 1) * B * 3 * HW;
+  io.m_j = bt->masks ? bt->masks + static_cast<size_t>(t) * B * HW : nullptr;
+  io.m_i = bt->masks ? bt->masks + static_cast<size_t>(t + 1) * B * HW : nullptr;
+  io.r_j = bt->states ? bt->states + static_cast<size_t>(t) * B * c.robot_dim : nullptr;
+  io.r_i = bt->states ? bt->states + static_cast<size_t>(t + 1) * B * c.robot_dim : nullptr;
+  io.a_j = bt->actions + static_cast<size_t>(t) * B * c.action_dim;
+  return io;
+}
+
+// encoder (run twice per step in the reference: identical values, BatchNorm running stats updated twice) + the tiled
+// action / state channels + the prior / posterior input convolutions
+int forward_encoder(rac_handle* h, TrainState* T, const rac_train_batch* bt, Span sp, cudaStream_t st) {
+  const rac_config& c = h->cfg;
+  const int B = T->cfg.batch, nb = sp.n * B, g = c.g_dim;
   const size_t HW = 48 * 64;
-  Tape& tp = T->tape[t];
-  tp.sampled = (t > 0 && bt->true_token && !bt->true_token[t]) ? 1 : 0;
-  const float* x_j = tp.sampled ? T->tape[t - 1].xp : bt->images + static_cast<size_t>(t) * B * 3 * HW;
-  tp.xj = x_j;
-  const float* m_j = bt->masks ? bt->masks + static_cast<size_t>(t) * B * HW : nullptr;
-  const float* m_i = bt->masks ? bt->masks + static_cast<size_t>(t + 1) * B * HW : nullptr;
-  const float* r_j = bt->states ? bt->states + static_cast<size_t>(t) * B * c.robot_dim : nullptr;
-  const float* r_i = bt->states ? bt->states + static_cast<size_t>(t + 1) * B * c.robot_dim : nullptr;
-  const float* a_j = bt->actions + static_cast<size_t>(t) * B * c.action_dim;
-  CK(launch_img_prep_train(x_j, T->cfg.zero_robot ? m_j : nullptr, tp.img4, B, static_cast<int>(HW), st));
-  // ---- encoder (run twice per step in the reference: identical values, BatchNorm running stats updated twice)
-  CK(launch_first_conv(tp.img4, c.use_mask ? m_j : nullptr, (c.use_mask && c.use_future_mask) ? m_i : nullptr,
-                       static_cast<long long>(HW), T->wfirst, T->zero64, nullptr, B, 48, 64, h->enc_cin, st, tp.vgg[0].raw));
+  Tape& tp = T->tape[sp.t0];
+  for (int t = sp.t0; t < sp.t0 + sp.n; ++t) {
+    Tape& q = T->tape[t];
+    q.sampled = (t > 0 && bt->true_token && !bt->true_token[t]) ? 1 : 0;
+    q.xj = q.sampled ? T->tape[t - 1].xp : bt->images + static_cast<size_t>(t) * B * 3 * HW;
+  }
+  const StepIO io = step_io(h, T, bt, sp.t0);
+  CK(launch_img_prep_train(io.x_j, T->cfg.zero_robot ? io.m_j : nullptr, tp.img4, nb, static_cast<int>(HW), st));
+  CK(launch_first_conv(tp.img4, c.use_mask ? io.m_j : nullptr, (c.use_mask && c.use_future_mask) ? io.m_i : nullptr,
+                       static_cast<long long>(HW), T->wfirst, T->zero64, nullptr, nb, 48, 64, h->enc_cin, st, tp.vgg[0].raw));
   {
     const TLayer& L = T->L[RAC_L_ENC_C1_0];
     CK(launch_bn_stats(tp.vgg[0].raw, B * static_cast<int>(HW), 64, tp.vgg[0].mean, tp.vgg[0].rstd,
-                       T->buffers + L.d.rmean_off, T->buffers + L.d.rvar_off, 2, st));
+                       T->buffers + L.d.rmean_off, T->buffers + L.d.rvar_off, 2, st, sp.n));
     CK(launch_bn_act(tp.vgg[0].raw, tp.vgg[0].mean, tp.vgg[0].rstd, T->params + L.d.gamma_off, T->params + L.d.beta_off,
-                     B, 48, 64, 64, tp.a1, 64, 0, 0, st));
+                     nb, 48, 64, 64, tp.a1, 64, 0, 0, st, sp.n));
   }
-  CKR(vgg_forward(h, T, tp.vgg[1], enc_def(h, 1), tp.a1, tp.cat5, 128, 64, 0, 2, st));
-  CK(launch_maxpool2(tp.cat5, 128, 64, tp.p1, B, 48, 64, 64, st));
-  CKR(vgg_forward(h, T, tp.vgg[2], enc_def(h, 2), tp.p1, tp.a2, 128, 0, 0, 2, st));
-  CKR(vgg_forward(h, T, tp.vgg[3], enc_def(h, 3), tp.a2, tp.cat4, 256, 128, 0, 2, st));
-  CK(launch_maxpool2(tp.cat4, 256, 128, tp.p2, B, 24, 32, 128, st));
-  CKR(vgg_forward(h, T, tp.vgg[4], enc_def(h, 4), tp.p2, tp.a3a, 256, 0, 0, 2, st));
-  CKR(vgg_forward(h, T, tp.vgg[5], enc_def(h, 5), tp.a3a, tp.a3b, 256, 0, 0, 2, st));
-  CKR(vgg_forward(h, T, tp.vgg[6], enc_def(h, 6), tp.a3b, tp.cat3, 512, 256, 0, 2, st));
-  CK(launch_maxpool2(tp.cat3, 512, 256, tp.p3, B, 12, 16, 256, st));
-  CKR(vgg_forward(h, T, tp.vgg[7], enc_def(h, 7), tp.p3, tp.a4a, 512, 0, 0, 2, st));
-  CKR(vgg_forward(h, T, tp.vgg[8], enc_def(h, 8), tp.a4a, tp.a4b, 512, 0, 0, 2, st));
-  CKR(vgg_forward(h, T, tp.vgg[9], enc_def(h, 9), tp.a4b, tp.h4, g, 0, 0, 2, st));
-  // ---- prior
-  CK(launch_aux_tile(a_j, c.action_dim, c.action_dim, c.use_robot_state ? r_j : nullptr,
-                     (c.use_robot_state && c.use_future_robot_state) ? r_i : nullptr, c.robot_dim, tp.aux, B, 48, st));
-  auto input_conv = [&](int layer, std::vector<Src> srcs, bf16* out) -> int {
-    const TLayer& L = T->L[layer];
-    EpiParams e{};
-    e.bias = L.bias; e.cout = g; e.out = out; e.out_cstride = g; e.out_coff = 0; e.upsample = 0; e.lrelu = 0;
-    return t_gemm(h, "train.input_conv.fwd", {B, 6, 8, 3, false}, srcs, L.wp, 9 * L.ctot, L.n_packed,
-                  tile_block_n(L.n_packed, EPI_ACT), EPI_ACT, e, st);
-  };
-  auto gauss = [&](int layer, const bf16* hin, const float* eps, float* mu, float* lv, bf16* zout) -> int {
-    const TLayer& L = T->L[layer];
-    EpiParams e{};
-    e.bias = L.bias; e.cout = 128; e.eps = eps; e.mu_out = mu; e.logvar_out = lv; e.z_out = zout; e.z_dim = z;
-    return t_gemm(h, "train.gauss.fwd", {B, 6, 8, 3, false}, {{hin, g}}, L.wp, 9 * g, 128, 128, EPI_GAUSS, e, st);
-  };
-  CKR(input_conv(RAC_L_PRIOR_IN, {{tp.aux, 64}, {tp.h4, g}}, tp.pin));
-  CKR(lstm_forward(h, T, 0, t, tp.pin, st));
-  CKR(gauss(RAC_L_PRIOR_GAUSS, tp.hs[0][1], tp.eps_p, tp.mu_p, tp.lv_p, tp.zprior));
-  // ---- posterior (h_target == h4, dynamics.py:619)
+  CKR(vgg_forward(h, T, tp.vgg[1], enc_def(h, 1), tp.a1, tp.cat5, 128, 64, 0, 2, sp, st));
+  CK(launch_maxpool2(tp.cat5, 128, 64, tp.p1, nb, 48, 64, 64, st));
+  CKR(vgg_forward(h, T, tp.vgg[2], enc_def(h, 2), tp.p1, tp.a2, 128, 0, 0, 2, sp, st));
+  CKR(vgg_forward(h, T, tp.vgg[3], enc_def(h, 3), tp.a2, tp.cat4, 256, 128, 0, 2, sp, st));
+  CK(launch_maxpool2(tp.cat4, 256, 128, tp.p2, nb, 24, 32, 128, st));
+  CKR(vgg_forward(h, T, tp.vgg[4], enc_def(h, 4), tp.p2, tp.a3a, 256, 0, 0, 2, sp, st));
+  CKR(vgg_forward(h, T, tp.vgg[5], enc_def(h, 5), tp.a3a, tp.a3b, 256, 0, 0, 2, sp, st));
+  CKR(vgg_forward(h, T, tp.vgg[6], enc_def(h, 6), tp.a3b, tp.cat3, 512, 256, 0, 2, sp, st));
+  CK(launch_maxpool2(tp.cat3, 512, 256, tp.p3, nb, 12, 16, 256, st));
+  CKR(vgg_forward(h, T, tp.vgg[7], enc_def(h, 7), tp.p3, tp.a4a, 512, 0, 0, 2, sp, st));
+  CKR(vgg_forward(h, T, tp.vgg[8], enc_def(h, 8), tp.a4a, tp.a4b, 512, 0, 0, 2, sp, st));
+  CKR(vgg_forward(h, T, tp.vgg[9], enc_def(h, 9), tp.a4b, tp.h4, g, 0, 0, 2, sp, st));
+  CK(launch_aux_tile(io.a_j, c.action_dim, c.action_dim, c.use_robot_state ? io.r_j : nullptr,
+                     (c.use_robot_state && c.use_future_robot_state) ? io.r_i : nullptr, c.robot_dim, tp.aux, nb, 48, st));
+  return RAC_OK;
+}
+
+int input_conv_fwd(rac_handle* h, TrainState* T, int layer, std::vector<Src> srcs, bf16* out, int nb, cudaStream_t st) {
+  const TLayer& L = T->L[layer];
+  const int g = h->cfg.g_dim;
+  EpiParams e{};
+  e.bias = L.bias; e.cout = g; e.out = out; e.out_cstride = g; e.out_coff = 0; e.upsample = 0; e.lrelu = 0;
+  return t_gemm(h, "train.input_conv.fwd", {nb, 6, 8, 3, false}, srcs, L.wp, 9 * L.ctot, L.n_packed,
+                tile_block_n(L.n_packed, EPI_ACT), EPI_ACT, e, st);
+}
+
+// prior_input_conv / posterior_input_conv (dynamics.py:600-602,621-623; h_target == h4, :619)
+int forward_input_convs(rac_handle* h, TrainState* T, const rac_train_batch* bt, Span sp, cudaStream_t st) {
+  const rac_config& c = h->cfg;
+  const int nb = sp.n * T->cfg.batch, g = c.g_dim;
+  Tape& tp = T->tape[sp.t0];
+  const StepIO io = step_io(h, T, bt, sp.t0);
+  CKR(input_conv_fwd(h, T, RAC_L_PRIOR_IN, {{tp.aux, 64}, {tp.h4, g}}, tp.pin, nb, st));
   if (c.use_robot_state) {
-    CK(launch_aux_tile(nullptr, 0, 0, r_i, nullptr, c.robot_dim, tp.auxp, B, 48, st));
-    CKR(input_conv(RAC_L_POST_IN, {{tp.auxp, 64}, {tp.h4, g}}, tp.postin));
+    CK(launch_aux_tile(nullptr, 0, 0, io.r_i, nullptr, c.robot_dim, tp.auxp, nb, 48, st));
+    CKR(input_conv_fwd(h, T, RAC_L_POST_IN, {{tp.auxp, 64}, {tp.h4, g}}, tp.postin, nb, st));
   } else {
-    CKR(input_conv(RAC_L_POST_IN, {{tp.h4, g}}, tp.postin));
+    CKR(input_conv_fwd(h, T, RAC_L_POST_IN, {{tp.h4, g}}, tp.postin, nb, st));
   }
-  CKR(lstm_forward(h, T, 1, t, tp.postin, st));
-  CKR(gauss(RAC_L_POST_GAUSS, tp.hs[1][1], tp.eps_q, tp.mu, tp.lv, tp.z));
-  // ---- frame predictor + decoder
-  CKR(input_conv(RAC_L_FP_IN, {{tp.aux, 64}, {tp.h4, g}, {tp.z, 64}}, tp.fin));
-  CKR(lstm_forward(h, T, 2, t, tp.fin, st));
-  CKR(vgg_forward(h, T, tp.vgg[10], dec_def(h, 0), tp.hs[2][1], tp.d2a, 512, 0, 0, 1, st));
-  CKR(vgg_forward(h, T, tp.vgg[11], dec_def(h, 1), tp.d2a, tp.d2b, 512, 0, 0, 1, st));
+  return RAC_OK;
+}
+
+// mu_net / logvar_net + reparameterisation (lstm.py:276-286) of stack s (0 prior, 1 posterior)
+int forward_gauss(rac_handle* h, TrainState* T, int s, Span sp, cudaStream_t st) {
+  const int nb = sp.n * T->cfg.batch, g = h->cfg.g_dim;
+  Tape& tp = T->tape[sp.t0];
+  const TLayer& L = T->L[s == 0 ? RAC_L_PRIOR_GAUSS : RAC_L_POST_GAUSS];
+  EpiParams e{};
+  e.bias = L.bias; e.cout = 128; e.z_dim = h->cfg.z_dim;
+  e.eps = s == 0 ? tp.eps_p : tp.eps_q;
+  e.mu_out = s == 0 ? tp.mu_p : tp.mu;
+  e.logvar_out = s == 0 ? tp.lv_p : tp.lv;
+  e.z_out = s == 0 ? tp.zprior : tp.z;
+  return t_gemm(h, "train.gauss.fwd", {nb, 6, 8, 3, false}, {{tp.hs[s][1], g}}, L.wp, 9 * g, 128, 128, EPI_GAUSS, e, st);
+}
+
+int forward_fp_in(rac_handle* h, TrainState* T, Span sp, cudaStream_t st) {
+  Tape& tp = T->tape[sp.t0];
+  return input_conv_fwd(h, T, RAC_L_FP_IN, {{tp.aux, 64}, {tp.h4, h->cfg.g_dim}, {tp.z, 64}}, tp.fin, sp.n * T->cfg.batch, st);
+}
+
+// decoder + frame head + compositing + the step's logged metrics / KL value
+int forward_decoder(rac_handle* h, TrainState* T, const rac_train_batch* bt, Span sp, cudaStream_t st) {
+  const rac_config& c = h->cfg;
+  const int B = T->cfg.batch, nb = sp.n * B, z = c.z_dim;
+  const size_t HW = 48 * 64;
+  Tape& tp = T->tape[sp.t0];
+  const StepIO io = step_io(h, T, bt, sp.t0);
+  CKR(vgg_forward(h, T, tp.vgg[10], dec_def(h, 0), tp.hs[2][1], tp.d2a, 512, 0, 0, 1, sp, st));
+  CKR(vgg_forward(h, T, tp.vgg[11], dec_def(h, 1), tp.d2a, tp.d2b, 512, 0, 0, 1, sp, st));
   if (tp.dcat5 != tp.cat5) {
-    // fixed_skip, t > 0: the skip halves are those of the first frame
+    // fixed_skip (one step at a time): the skip halves are those of the first frame
     const Tape& t0 = T->tape[0];
     CK(cudaMemcpy2DAsync(tp.dcat3 + 256, 512 * sizeof(bf16), t0.cat3 + 256, 512 * sizeof(bf16), 256 * sizeof(bf16),
                          static_cast<size_t>(B) * 192, cudaMemcpyDeviceToDevice, st));
@@ -530,158 +584,183 @@ int train_forward_step(rac_handle* h, TrainState* T, const rac_train_batch* bt, 
     CK(cudaMemcpy2DAsync(tp.dcat5 + 64, 128 * sizeof(bf16), t0.cat5 + 64, 128 * sizeof(bf16), 64 * sizeof(bf16),
                          static_cast<size_t>(B) * 3072, cudaMemcpyDeviceToDevice, st));
   }
-  CKR(vgg_forward(h, T, tp.vgg[12], dec_def(h, 2), tp.d2b, tp.dcat3, 512, 0, 1, 1, st));
-  CKR(vgg_forward(h, T, tp.vgg[13], dec_def(h, 3), tp.dcat3, tp.d3a, 256, 0, 0, 1, st));
-  CKR(vgg_forward(h, T, tp.vgg[14], dec_def(h, 4), tp.d3a, tp.d3b, 256, 0, 0, 1, st));
-  CKR(vgg_forward(h, T, tp.vgg[15], dec_def(h, 5), tp.d3b, tp.dcat4, 256, 0, 1, 1, st));
-  CKR(vgg_forward(h, T, tp.vgg[16], dec_def(h, 6), tp.dcat4, tp.d4a, 128, 0, 0, 1, st));
-  CKR(vgg_forward(h, T, tp.vgg[17], dec_def(h, 7), tp.d4a, tp.dcat5, 128, 0, 1, 1, st));
-  CKR(vgg_forward(h, T, tp.vgg[18], dec_def(h, 8), tp.dcat5, tp.d5, 64, 0, 0, 1, st));
+  CKR(vgg_forward(h, T, tp.vgg[12], dec_def(h, 2), tp.d2b, tp.dcat3, 512, 0, 1, 1, sp, st));
+  CKR(vgg_forward(h, T, tp.vgg[13], dec_def(h, 3), tp.dcat3, tp.d3a, 256, 0, 0, 1, sp, st));
+  CKR(vgg_forward(h, T, tp.vgg[14], dec_def(h, 4), tp.d3a, tp.d3b, 256, 0, 0, 1, sp, st));
+  CKR(vgg_forward(h, T, tp.vgg[15], dec_def(h, 5), tp.d3b, tp.dcat4, 256, 0, 1, 1, sp, st));
+  CKR(vgg_forward(h, T, tp.vgg[16], dec_def(h, 6), tp.dcat4, tp.d4a, 128, 0, 0, 1, sp, st));
+  CKR(vgg_forward(h, T, tp.vgg[17], dec_def(h, 7), tp.d4a, tp.dcat5, 128, 0, 1, 1, sp, st));
+  CKR(vgg_forward(h, T, tp.vgg[18], dec_def(h, 8), tp.dcat5, tp.d5, 64, 0, 0, 1, sp, st));
   {
     const TLayer& L = T->L[RAC_L_DEC_UPC5_1];
     EpiParams e{};
     e.bias = L.bias; e.cout = 4; e.xpred_out = tp.x4;
-    CKR(t_gemm(h, "train.frame.fwd", {B, 48, 64, 3, false}, {{tp.d5, 64}}, L.wp, 9 * 64, 16, 16, EPI_FRAME, e, st));
+    CKR(t_gemm(h, "train.frame.fwd", {nb, 48, 64, 3, false}, {{tp.d5, 64}}, L.wp, 9 * 64, 16, 16, EPI_FRAME, e, st));
   }
-  CK(launch_composite(tp.x4, x_j, tp.xp, B, static_cast<int>(HW), st));
-  if (m_i)  // logging metrics of the reference step (trainer.py:436-439)
-    CK(launch_robot_world_mse(tp.xp, bt->images + static_cast<size_t>(t + 1) * B * 3 * HW, m_i, bt->losses + 2, B,
-                              static_cast<int>(HW), st));
+  CK(launch_composite(tp.x4, io.x_j, tp.xp, nb, static_cast<int>(HW), st));
+  if (io.m_i)  // logging metrics of the reference step (trainer.py:436-439)
+    CK(launch_robot_world_mse_batched(tp.xp, io.x_i, io.m_i, T->metric_part, bt->losses + 2, nb, B, static_cast<int>(HW), st));
   // KL(posterior || prior) value (trainer.py:454-458)
-  CK(launch_kl_loss(tp.mu, tp.lv, tp.mu_p, tp.lv_p, T->kl_tmp, static_cast<int64_t>(B) * z * 48, B, st));
-  CK(launch_sum_f32(T->kl_tmp, 1, bt->losses + 1, st));
+  CK(launch_kl_loss_batched(tp.mu, tp.lv, tp.mu_p, tp.lv_p, T->metric_part, bt->losses + 1,
+                            static_cast<long long>(nb) * z * 48, B, st));
   return RAC_OK;
 }
 
-int train_backward_step(rac_handle* h, TrainState* T, const rac_train_batch* bt, int t, int cur, cudaStream_t st) {
+// ------------------------------------------------------------------ backward phases
+// reconstruction loss + decoder; the gradient w.r.t. the frame predictor's output h lands in DH[2][1][t] (+=)
+int backward_decoder(rac_handle* h, TrainState* T, const rac_train_batch* bt, Span sp, cudaStream_t st) {
   const rac_config& c = h->cfg;
-  const int B = T->cfg.batch, g = c.g_dim, z = c.z_dim;
+  const int B = T->cfg.batch, nb = sp.n * B, g = c.g_dim, t0 = sp.t0;
   const size_t HW = 48 * 64;
-  Tape& tp = T->tape[t];
-  const float* x_j = tp.xj;
-  const float* x_i = bt->images + static_cast<size_t>(t + 1) * B * 3 * HW;
   const int S = T->cfg.steps;
-  const float* gp_in = (t + 1 < S && T->tape[t + 1].sampled) ? T->G_img[cur] : nullptr;
-  float* gxj_out = tp.sampled ? T->G_img[cur ^ 1] : nullptr;
-  const float* m_j = bt->masks ? bt->masks + static_cast<size_t>(t) * B * HW : nullptr;
-  const float* m_i = bt->masks ? bt->masks + static_cast<size_t>(t + 1) * B * HW : nullptr;
+  Tape& tp = T->tape[t0];
+  const StepIO io = step_io(h, T, bt, t0);
+  // scheduled sampling (one step at a time): gradient handed over by / to the neighbouring steps through the frame
+  const int cur = (S - 1 - t0) & 1;
+  const float* gp_in = (sp.n == 1 && t0 + 1 < S && T->tape[t0 + 1].sampled) ? T->G_img[cur] : nullptr;
+  float* gxj_out = (sp.n == 1 && tp.sampled) ? T->G_img[cur ^ 1] : nullptr;
   // ---- reconstruction loss and its gradient w.r.t. the decoder logits (trainer.py:406-433)
-  CK(launch_frame_loss(tp.x4, x_j, x_i, m_i, T->cfg.recon_kind, T->cfg.robot_pixel_weight, B, static_cast<int>(HW),
-                       T->loss_part, T->dy_b, gp_in, gxj_out, st, bt->batch_weight));
-  CK(launch_sum_f32(T->loss_part, B, bt->losses + 0, st));
+  bf16* dlogit = dy_slot(T, RAC_L_DEC_UPC5_1, 48, 64, t0);
+  CK(launch_frame_loss(tp.x4, io.x_j, io.x_i, io.m_i, T->cfg.recon_kind, T->cfg.robot_pixel_weight, nb, static_cast<int>(HW),
+                       T->loss_part, dlogit, gp_in, gxj_out, st, bt->batch_weight, B));
+  CK(launch_sum_f32(T->loss_part, nb, bt->losses + 0, st));
   F32Seg seg[3];
-  // ---- decoder
-  seg[0] = {0, 64, T->G_d5, 64, 0, 0};
-  CKR(conv_backward(h, T, RAC_L_DEC_UPC5_1, 48, 64, {{tp.d5, 64}}, T->dy_b, seg, 1, st));
+  seg[0] = {0, 64, T->G_d5.at(t0), 64, 0, 0};
+  CKR(conv_backward(h, T, RAC_L_DEC_UPC5_1, 48, 64, {{tp.d5, 64}}, dlogit, seg, 1, sp, st));
   // gradient of a concat buffer: [decoder half | skip half]. fixed_skip: the skip half is summed over the steps
   // (first writer = the first processed step, t == S - 1) instead of going to this step's encoder
   const bool fixed = T->cfg.fixed_skip != 0;
-  const int skip_acc = (t == S - 1) ? 0 : 1;
+  const int skip_acc = (t0 == S - 1) ? 0 : 1;
   auto cat_segs = [&](float* G_cat, float* G_skip, int half) -> int {
     if (!fixed) { seg[0] = {0, 2 * half, G_cat, 2 * half, 0, 0}; return 1; }
     seg[0] = {0, half, G_cat, 2 * half, 0, 0};
     seg[1] = {half, 2 * half, G_skip, half, 0, skip_acc};
     return 2;
   };
-  int ncat = cat_segs(T->G_cat5, T->G_skip5, 64);
-  CKR(vgg_backward(h, T, tp.vgg[18], dec_def(h, 8), tp.dcat5, T->G_d5, 64, 0, 0, seg, ncat, st));
-  seg[0] = {0, 128, T->G_d4a, 128, 0, 0};
-  CKR(vgg_backward(h, T, tp.vgg[17], dec_def(h, 7), tp.d4a, T->G_cat5, 128, 0, 1, seg, 1, st));
-  ncat = cat_segs(T->G_cat4, T->G_skip4, 128);
-  CKR(vgg_backward(h, T, tp.vgg[16], dec_def(h, 6), tp.dcat4, T->G_d4a, 128, 0, 0, seg, ncat, st));
-  seg[0] = {0, 256, T->G_d3b, 256, 0, 0};
-  CKR(vgg_backward(h, T, tp.vgg[15], dec_def(h, 5), tp.d3b, T->G_cat4, 256, 0, 1, seg, 1, st));
-  seg[0] = {0, 256, T->G_d3a, 256, 0, 0};
-  CKR(vgg_backward(h, T, tp.vgg[14], dec_def(h, 4), tp.d3a, T->G_d3b, 256, 0, 0, seg, 1, st));
-  ncat = cat_segs(T->G_cat3, T->G_skip3, 256);
-  CKR(vgg_backward(h, T, tp.vgg[13], dec_def(h, 3), tp.dcat3, T->G_d3a, 256, 0, 0, seg, ncat, st));
-  seg[0] = {0, 512, T->G_d2b, 512, 0, 0};
-  CKR(vgg_backward(h, T, tp.vgg[12], dec_def(h, 2), tp.d2b, T->G_cat3, 512, 0, 1, seg, 1, st));
-  seg[0] = {0, 512, T->G_d2a, 512, 0, 0};
-  CKR(vgg_backward(h, T, tp.vgg[11], dec_def(h, 1), tp.d2a, T->G_d2b, 512, 0, 0, seg, 1, st));
-  seg[0] = {0, g, T->G_hs[2][1][cur], g, 0, 1};
-  CKR(vgg_backward(h, T, tp.vgg[10], dec_def(h, 0), tp.hs[2][1], T->G_d2a, 512, 0, 0, seg, 1, st));
-  // ---- frame predictor
-  CKR(lstm_backward(h, T, 2, t, tp.fin, T->G_fin, cur, st));
-  CK(launch_cast_bf16(T->G_fin, static_cast<long long>(B) * 48 * g, T->dy_b, st));
+  int ncat = cat_segs(T->G_cat5.at(t0), T->G_skip5, 64);
+  CKR(vgg_backward(h, T, tp.vgg[18], dec_def(h, 8), tp.dcat5, T->G_d5.at(t0), 64, 0, 0, seg, ncat, sp, st));
+  seg[0] = {0, 128, T->G_d4a.at(t0), 128, 0, 0};
+  CKR(vgg_backward(h, T, tp.vgg[17], dec_def(h, 7), tp.d4a, T->G_cat5.at(t0), 128, 0, 1, seg, 1, sp, st));
+  ncat = cat_segs(T->G_cat4.at(t0), T->G_skip4, 128);
+  CKR(vgg_backward(h, T, tp.vgg[16], dec_def(h, 6), tp.dcat4, T->G_d4a.at(t0), 128, 0, 0, seg, ncat, sp, st));
+  seg[0] = {0, 256, T->G_d3b.at(t0), 256, 0, 0};
+  CKR(vgg_backward(h, T, tp.vgg[15], dec_def(h, 5), tp.d3b, T->G_cat4.at(t0), 256, 0, 1, seg, 1, sp, st));
+  seg[0] = {0, 256, T->G_d3a.at(t0), 256, 0, 0};
+  CKR(vgg_backward(h, T, tp.vgg[14], dec_def(h, 4), tp.d3a, T->G_d3b.at(t0), 256, 0, 0, seg, 1, sp, st));
+  ncat = cat_segs(T->G_cat3.at(t0), T->G_skip3, 256);
+  CKR(vgg_backward(h, T, tp.vgg[13], dec_def(h, 3), tp.dcat3, T->G_d3a.at(t0), 256, 0, 0, seg, ncat, sp, st));
+  seg[0] = {0, 512, T->G_d2b.at(t0), 512, 0, 0};
+  CKR(vgg_backward(h, T, tp.vgg[12], dec_def(h, 2), tp.d2b, T->G_cat3.at(t0), 512, 0, 1, seg, 1, sp, st));
+  seg[0] = {0, 512, T->G_d2a.at(t0), 512, 0, 0};
+  CKR(vgg_backward(h, T, tp.vgg[11], dec_def(h, 1), tp.d2a, T->G_d2b.at(t0), 512, 0, 0, seg, 1, sp, st));
+  seg[0] = {0, g, T->DH[2][1].at(t0), g, 0, 1};
+  CKR(vgg_backward(h, T, tp.vgg[10], dec_def(h, 0), tp.hs[2][1], T->G_d2a.at(t0), 512, 0, 0, seg, 1, sp, st));
+  return RAC_OK;
+}
+
+// frame_pred_input_conv: G_fin (from the frame predictor stack) -> G_h4 (=, first writer), G_z (=)
+int backward_fp_in(rac_handle* h, TrainState* T, Span sp, cudaStream_t st) {
+  const int nb = sp.n * T->cfg.batch, g = h->cfg.g_dim, t0 = sp.t0;
+  Tape& tp = T->tape[t0];
+  bf16* slot = dy_slot(T, RAC_L_FP_IN, 6, 8, t0);
+  CK(launch_cast_bf16(T->G_fin.at(t0), static_cast<long long>(nb) * 48 * g, slot, st));
+  F32Seg seg[3];
   seg[0] = {0, 64, nullptr, 0, 0, 0};
-  seg[1] = {64, 64 + g, T->G_h4, g, 0, 0};
-  seg[2] = {64 + g, 128 + g, T->G_z, 64, 0, 0};
-  CKR(conv_backward(h, T, RAC_L_FP_IN, 6, 8, {{tp.aux, 64}, {tp.h4, g}, {tp.z, 64}}, T->dy_b, seg, 3, st));
-  // ---- z sample + KL -> posterior and prior heads
-  CK(launch_gauss_bwd(T->G_z, tp.mu, tp.lv, tp.eps_q, tp.mu_p, tp.lv_p, B, z, 48, T->cfg.kl_beta, B, T->dy_a, T->dy_b, st));
-  // (conv_backward uses dy_a only through its dY argument; the two heads are processed one after the other)
-  {
-    // posterior head first: its operand lives in dy_a, which lstm_backward will overwrite later
-    seg[0] = {0, g, T->G_hs[1][1][cur], g, 0, 1};
-    CKR(conv_backward(h, T, RAC_L_POST_GAUSS, 6, 8, {{tp.hs[1][1], g}}, T->dy_a, seg, 1, st));
-    seg[0] = {0, g, T->G_hs[0][1][cur], g, 0, 1};
-    CKR(conv_backward(h, T, RAC_L_PRIOR_GAUSS, 6, 8, {{tp.hs[0][1], g}}, T->dy_b, seg, 1, st));
+  seg[1] = {64, 64 + g, T->G_h4.at(t0), g, 0, 0};
+  seg[2] = {64 + g, 128 + g, T->G_z.at(t0), 64, 0, 0};
+  return conv_backward(h, T, RAC_L_FP_IN, 6, 8, {{tp.aux, 64}, {tp.h4, g}, {tp.z, 64}}, slot, seg, 3, sp, st);
+}
+
+// z sample + KL -> posterior and prior heads; their input gradients land in DH[1][1] / DH[0][1] (+=)
+int backward_gauss(rac_handle* h, TrainState* T, Span sp, cudaStream_t st) {
+  const int B = T->cfg.batch, nb = sp.n * B, g = h->cfg.g_dim, z = h->cfg.z_dim, t0 = sp.t0;
+  Tape& tp = T->tape[t0];
+  bf16* dpost = dy_slot(T, RAC_L_POST_GAUSS, 6, 8, t0);
+  bf16* dprior = dy_slot(T, RAC_L_PRIOR_GAUSS, 6, 8, t0);
+  CK(launch_gauss_bwd(T->G_z.at(t0), tp.mu, tp.lv, tp.eps_q, tp.mu_p, tp.lv_p, nb, z, 48, T->cfg.kl_beta, B, dpost, dprior, st));
+  F32Seg seg = {0, g, T->DH[1][1].at(t0), g, 0, 1};
+  CKR(conv_backward(h, T, RAC_L_POST_GAUSS, 6, 8, {{tp.hs[1][1], g}}, dpost, &seg, 1, sp, st));
+  seg = {0, g, T->DH[0][1].at(t0), g, 0, 1};
+  CKR(conv_backward(h, T, RAC_L_PRIOR_GAUSS, 6, 8, {{tp.hs[0][1], g}}, dprior, &seg, 1, sp, st));
+  return RAC_OK;
+}
+
+// posterior_input_conv (s == 1) / prior_input_conv (s == 0): G_postin / G_pin -> G_h4 (+=)
+int backward_input_conv(rac_handle* h, TrainState* T, int s, Span sp, cudaStream_t st) {
+  const rac_config& c = h->cfg;
+  const int nb = sp.n * T->cfg.batch, g = c.g_dim, t0 = sp.t0;
+  Tape& tp = T->tape[t0];
+  const int layer = s == 1 ? RAC_L_POST_IN : RAC_L_PRIOR_IN;
+  bf16* slot = dy_slot(T, layer, 6, 8, t0);
+  CK(launch_cast_bf16((s == 1 ? T->G_postin : T->G_pin).at(t0), static_cast<long long>(nb) * 48 * g, slot, st));
+  F32Seg seg[2];
+  if (s == 1 && !c.use_robot_state) {
+    seg[0] = {0, g, T->G_h4.at(t0), g, 0, 1};
+    return conv_backward(h, T, layer, 6, 8, {{tp.h4, g}}, slot, seg, 1, sp, st);
   }
-  // ---- posterior stack
-  CKR(lstm_backward(h, T, 1, t, tp.postin, T->G_postin, cur, st));
-  CK(launch_cast_bf16(T->G_postin, static_cast<long long>(B) * 48 * g, T->dy_b, st));
-  if (c.use_robot_state) {
-    seg[0] = {0, 64, nullptr, 0, 0, 0};
-    seg[1] = {64, 64 + g, T->G_h4, g, 0, 1};
-    CKR(conv_backward(h, T, RAC_L_POST_IN, 6, 8, {{tp.auxp, 64}, {tp.h4, g}}, T->dy_b, seg, 2, st));
-  } else {
-    seg[0] = {0, g, T->G_h4, g, 0, 1};
-    CKR(conv_backward(h, T, RAC_L_POST_IN, 6, 8, {{tp.h4, g}}, T->dy_b, seg, 1, st));
-  }
-  // ---- prior stack
-  CKR(lstm_backward(h, T, 0, t, tp.pin, T->G_pin, cur, st));
-  CK(launch_cast_bf16(T->G_pin, static_cast<long long>(B) * 48 * g, T->dy_b, st));
   seg[0] = {0, 64, nullptr, 0, 0, 0};
-  seg[1] = {64, 64 + g, T->G_h4, g, 0, 1};
-  CKR(conv_backward(h, T, RAC_L_PRIOR_IN, 6, 8, {{tp.aux, 64}, {tp.h4, g}}, T->dy_b, seg, 2, st));
-  // ---- encoder (the gradients of the two reference passes are summed in G_h4 / the skip halves)
-  seg[0] = {0, 512, T->G_a4b, 512, 0, 0};
-  CKR(vgg_backward(h, T, tp.vgg[9], enc_def(h, 9), tp.a4b, T->G_h4, g, 0, 0, seg, 1, st));
-  seg[0] = {0, 512, T->G_a4a, 512, 0, 0};
-  CKR(vgg_backward(h, T, tp.vgg[8], enc_def(h, 8), tp.a4a, T->G_a4b, 512, 0, 0, seg, 1, st));
-  seg[0] = {0, 256, T->G_p3, 256, 0, 0};
-  CKR(vgg_backward(h, T, tp.vgg[7], enc_def(h, 7), tp.p3, T->G_a4a, 512, 0, 0, seg, 1, st));
+  seg[1] = {64, 64 + g, T->G_h4.at(t0), g, 0, 1};
+  return conv_backward(h, T, layer, 6, 8, {{s == 1 ? tp.auxp : tp.aux, 64}, {tp.h4, g}}, slot, seg, 2, sp, st);
+}
+
+// encoder (the gradients of the two reference passes are summed in G_h4 / the skip halves)
+int backward_encoder(rac_handle* h, TrainState* T, const rac_train_batch* bt, Span sp, cudaStream_t st) {
+  const rac_config& c = h->cfg;
+  const int B = T->cfg.batch, nb = sp.n * B, g = c.g_dim, t0 = sp.t0;
+  const size_t HW = 48 * 64;
+  Tape& tp = T->tape[t0];
+  const StepIO io = step_io(h, T, bt, t0);
+  const bool fixed = T->cfg.fixed_skip != 0;
+  F32Seg seg[3];
+  seg[0] = {0, 512, T->G_a4b.at(t0), 512, 0, 0};
+  CKR(vgg_backward(h, T, tp.vgg[9], enc_def(h, 9), tp.a4b, T->G_h4.at(t0), g, 0, 0, seg, 1, sp, st));
+  seg[0] = {0, 512, T->G_a4a.at(t0), 512, 0, 0};
+  CKR(vgg_backward(h, T, tp.vgg[8], enc_def(h, 8), tp.a4a, T->G_a4b.at(t0), 512, 0, 0, seg, 1, sp, st));
+  seg[0] = {0, 256, T->G_p3.at(t0), 256, 0, 0};
+  CKR(vgg_backward(h, T, tp.vgg[7], enc_def(h, 7), tp.p3, T->G_a4a.at(t0), 512, 0, 0, seg, 1, sp, st));
   // gradient of the encoder outputs that double as skips: pooling path + decoder skip path. fixed_skip: steps t > 0
   // get the pooling path only; step 0 adds it to the all-steps skip sum
   struct SkipGrad { float* p; int cstride, coff, acc; };
   auto skip_grad = [&](float* G_cat, float* G_skip, int half) -> SkipGrad {
     if (!fixed) return {G_cat, 2 * half, half, 1};
-    if (t > 0) return {G_cat, 2 * half, half, 0};
+    if (t0 > 0) return {G_cat, 2 * half, half, 0};
     return {G_skip, half, 0, 1};
   };
-  SkipGrad sk = skip_grad(T->G_cat3, T->G_skip3, 256);
-  CK(launch_pool_bwd(tp.cat3, 512, 256, T->G_p3, B, 12, 16, 256, sk.p, sk.cstride, sk.coff, sk.acc, st));
-  seg[0] = {0, 256, T->G_a3b, 256, 0, 0};
-  CKR(vgg_backward(h, T, tp.vgg[6], enc_def(h, 6), tp.a3b, sk.p, sk.cstride, sk.coff, 0, seg, 1, st));
-  seg[0] = {0, 256, T->G_a3a, 256, 0, 0};
-  CKR(vgg_backward(h, T, tp.vgg[5], enc_def(h, 5), tp.a3a, T->G_a3b, 256, 0, 0, seg, 1, st));
-  seg[0] = {0, 128, T->G_p2, 128, 0, 0};
-  CKR(vgg_backward(h, T, tp.vgg[4], enc_def(h, 4), tp.p2, T->G_a3a, 256, 0, 0, seg, 1, st));
-  sk = skip_grad(T->G_cat4, T->G_skip4, 128);
-  CK(launch_pool_bwd(tp.cat4, 256, 128, T->G_p2, B, 24, 32, 128, sk.p, sk.cstride, sk.coff, sk.acc, st));
-  seg[0] = {0, 128, T->G_a2, 128, 0, 0};
-  CKR(vgg_backward(h, T, tp.vgg[3], enc_def(h, 3), tp.a2, sk.p, sk.cstride, sk.coff, 0, seg, 1, st));
-  seg[0] = {0, 64, T->G_p1, 64, 0, 0};
-  CKR(vgg_backward(h, T, tp.vgg[2], enc_def(h, 2), tp.p1, T->G_a2, 128, 0, 0, seg, 1, st));
-  sk = skip_grad(T->G_cat5, T->G_skip5, 64);
-  CK(launch_pool_bwd(tp.cat5, 128, 64, T->G_p1, B, 48, 64, 64, sk.p, sk.cstride, sk.coff, sk.acc, st));
-  seg[0] = {0, 64, T->G_a1, 64, 0, 0};
-  CKR(vgg_backward(h, T, tp.vgg[1], enc_def(h, 1), tp.a1, sk.p, sk.cstride, sk.coff, 0, seg, 1, st));
+  SkipGrad sk = skip_grad(T->G_cat3.at(t0), T->G_skip3, 256);
+  CK(launch_pool_bwd(tp.cat3, 512, 256, T->G_p3.at(t0), nb, 12, 16, 256, sk.p, sk.cstride, sk.coff, sk.acc, st));
+  seg[0] = {0, 256, T->G_a3b.at(t0), 256, 0, 0};
+  CKR(vgg_backward(h, T, tp.vgg[6], enc_def(h, 6), tp.a3b, sk.p, sk.cstride, sk.coff, 0, seg, 1, sp, st));
+  seg[0] = {0, 256, T->G_a3a.at(t0), 256, 0, 0};
+  CKR(vgg_backward(h, T, tp.vgg[5], enc_def(h, 5), tp.a3a, T->G_a3b.at(t0), 256, 0, 0, seg, 1, sp, st));
+  seg[0] = {0, 128, T->G_p2.at(t0), 128, 0, 0};
+  CKR(vgg_backward(h, T, tp.vgg[4], enc_def(h, 4), tp.p2, T->G_a3a.at(t0), 256, 0, 0, seg, 1, sp, st));
+  sk = skip_grad(T->G_cat4.at(t0), T->G_skip4, 128);
+  CK(launch_pool_bwd(tp.cat4, 256, 128, T->G_p2.at(t0), nb, 24, 32, 128, sk.p, sk.cstride, sk.coff, sk.acc, st));
+  seg[0] = {0, 128, T->G_a2.at(t0), 128, 0, 0};
+  CKR(vgg_backward(h, T, tp.vgg[3], enc_def(h, 3), tp.a2, sk.p, sk.cstride, sk.coff, 0, seg, 1, sp, st));
+  seg[0] = {0, 64, T->G_p1.at(t0), 64, 0, 0};
+  CKR(vgg_backward(h, T, tp.vgg[2], enc_def(h, 2), tp.p1, T->G_a2.at(t0), 128, 0, 0, seg, 1, sp, st));
+  sk = skip_grad(T->G_cat5.at(t0), T->G_skip5, 64);
+  CK(launch_pool_bwd(tp.cat5, 128, 64, T->G_p1.at(t0), nb, 48, 64, 64, sk.p, sk.cstride, sk.coff, sk.acc, st));
+  seg[0] = {0, 64, T->G_a1.at(t0), 64, 0, 0};
+  CKR(vgg_backward(h, T, tp.vgg[1], enc_def(h, 1), tp.a1, sk.p, sk.cstride, sk.coff, 0, seg, 1, sp, st));
   {
     // encoder.c1.0: BatchNorm backward, then the small-K weight gradient on CUDA cores (no input gradient needed)
     const TLayer& L = T->L[RAC_L_ENC_C1_0];
-    CK(launch_bn_bwd(T->G_a1, 64, 0, 0, tp.vgg[0].raw, tp.vgg[0].mean, tp.vgg[0].rstd, T->params + L.d.gamma_off,
-                     T->params + L.d.beta_off, B, 48, 64, 64, T->bn_scratch, T->dy_a, T->draw32,
-                     T->grads + L.d.gamma_off, T->grads + L.d.beta_off, st));
-    CK(launch_first_wgrad(tp.img4, c.use_mask ? m_j : nullptr, (c.use_mask && c.use_future_mask) ? m_i : nullptr,
-                          static_cast<long long>(HW), T->draw32, T->grads + L.d.w_off, B, 48, 64, h->enc_cin, T->fw_part,
+    float* draw32 = T->draw32.at(t0);
+    CK(launch_bn_bwd(T->G_a1.at(t0), 64, 0, 0, tp.vgg[0].raw, tp.vgg[0].mean, tp.vgg[0].rstd, T->params + L.d.gamma_off,
+                     T->params + L.d.beta_off, nb, 48, 64, 64, T->bn_scratch, nullptr, draw32,
+                     T->grads + L.d.gamma_off, T->grads + L.d.beta_off, st, sp.n));
+    CK(launch_first_wgrad(tp.img4, c.use_mask ? io.m_j : nullptr, (c.use_mask && c.use_future_mask) ? io.m_i : nullptr,
+                          static_cast<long long>(HW), draw32, T->grads + L.d.w_off, nb, 48, 64, h->enc_cin, T->fw_part,
                           kFwBlocks, st));
     // a model-sampled input frame also receives gradient through the encoder (zeroed robot pixels get none)
-    if (tp.sampled && T->dbg_keep)
-      CK(cudaMemcpyAsync(T->dbg_draw32, T->draw32, sizeof(float) * static_cast<size_t>(B) * HW * 64, cudaMemcpyDeviceToDevice, st));
-    if (tp.sampled)
-      CK(launch_first_dgrad(T->draw32, T->wfirst, h->enc_cin, T->cfg.zero_robot ? m_j : nullptr, gxj_out, B, 48, 64, st));
+    if (sp.n == 1 && tp.sampled) {
+      float* gxj_out = T->G_img[((T->cfg.steps - 1 - t0) & 1) ^ 1];
+      if (T->dbg_keep)
+        CK(cudaMemcpyAsync(T->dbg_draw32, draw32, sizeof(float) * static_cast<size_t>(B) * HW * 64, cudaMemcpyDeviceToDevice, st));
+      CK(launch_first_dgrad(draw32, T->wfirst, h->enc_cin, T->cfg.zero_robot ? io.m_j : nullptr, gxj_out, B, 48, 64, st));
+    }
   }
   return RAC_OK;
 }
@@ -711,7 +790,7 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
   T->cfg = *cfg;
   T->params = params; T->buffers = buffers; T->grads = grads; T->m = adam_m; T->v = adam_v;
   if (const char* dk = getenv("RAC_TRAIN_DEBUG_KEEP")) T->dbg_keep = atoi(dk);
-  if (const char* wg = getenv("RAC_WGRAD_IM2COL")) T->wgrad_implicit = atoi(wg) ? 0 : 1;
+  if (const char* ps = getenv("RAC_TRAIN_PER_STEP")) T->per_step = atoi(ps);
   {
     static bool attr = false;
     if (!attr) { CK(wgrad_tc_set_attributes()); attr = true; }
@@ -744,13 +823,9 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
     for (int i = 1; i < T->nlayers; ++i) {
       TLayer& L = T->L[i];
       L.wp = bp.take<bf16>(static_cast<size_t>(L.n_packed) * L.taps * L.ctot);
-      {
-        // dyT: the output gradients of all time steps -- [S][M][kpad] for the implicit-GEMM weight gradient, or the
-        // transposed [kpad][S * mpad] (+ the im2col operand xcolT) of the round-1 path
-        const size_t ld = static_cast<size_t>(S) * round_up(static_cast<int>(rows_of(i)), 64);
-        if (!T->wgrad_implicit) L.xcolT = bp.take<bf16>(static_cast<size_t>(L.taps) * L.ctot * ld);
-        L.dyT = bp.take<bf16>(static_cast<size_t>(L.kpad) * ld);
-      }
+      // dyT: the output gradients of all time steps [steps][M][kpad] -- the dgrad operand of each step and, all steps
+      // together, the A operand of the weight-gradient GEMM
+      L.dyT = bp.take<bf16>(static_cast<size_t>(L.kpad) * S * rows_of(i));
       L.wd = bp.take<bf16>(static_cast<size_t>(L.ctot) * L.taps * L.kpad);
       L.dwp = bp.take<float>(static_cast<size_t>(L.kpad) * L.taps * L.ctot);
       L.bias = bp.take<float>(L.n_packed);
@@ -758,86 +833,92 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
     T->wfirst = bp.take<float>(45 * 64);
     T->zero64 = bp.take<float>(64);
     T->tape.resize(S);
-    for (int t = 0; t < S; ++t) {
-      Tape& tp = T->tape[t];
-      tp.img4 = bp.take<float>(M0 * 4);
-      tp.a1 = bp.take<bf16>(M0 * 64); tp.cat5 = bp.take<bf16>(M0 * 128); tp.p1 = bp.take<bf16>(M1 * 64);
-      tp.a2 = bp.take<bf16>(M1 * 128); tp.cat4 = bp.take<bf16>(M1 * 256); tp.p2 = bp.take<bf16>(M2 * 128);
-      tp.a3a = bp.take<bf16>(M2 * 256); tp.a3b = bp.take<bf16>(M2 * 256); tp.cat3 = bp.take<bf16>(M2 * 512);
-      tp.p3 = bp.take<bf16>(M3 * 256); tp.a4a = bp.take<bf16>(M3 * 512); tp.a4b = bp.take<bf16>(M3 * 512);
-      tp.h4 = bp.take<bf16>(M3 * g); tp.aux = bp.take<bf16>(M3 * 64); tp.auxp = bp.take<bf16>(M3 * 64);
-      tp.pin = bp.take<bf16>(M3 * g); tp.postin = bp.take<bf16>(M3 * g); tp.fin = bp.take<bf16>(M3 * g);
-      tp.z = bp.take<bf16>(M3 * 64); tp.zprior = bp.take<bf16>(M3 * 64);
-      for (int s = 0; s < 3; ++s)
-        for (int l = 0; l < 2; ++l) {
-          tp.hs[s][l] = bp.take<bf16>(M3 * g);
-          tp.cs[s][l] = bp.take<float>(M3 * g);
-          tp.gates[s][l] = bp.take<float>(M3 * 4 * g);
-          if (T->gn) {
-            tp.raw_ih[s][l] = bp.take<float>(M3 * 4 * g); tp.raw_hh[s][l] = bp.take<float>(M3 * 4 * g);
-            tp.c_raw[s][l] = bp.take<float>(M3 * g); tp.gn_stats[s][l] = bp.take<float>(static_cast<size_t>(B) * 96);
-          }
+    // time-major tape: one allocation [S][n] per tensor, step t = slice t
+    auto TA = [&](auto get, size_t n) {
+      using P = std::remove_reference_t<decltype(get(T->tape[0]))>;
+      using E = std::remove_pointer_t<P>;
+      E* b = bp.take<E>(static_cast<size_t>(S) * n);
+      for (int t = 0; t < S; ++t) get(T->tape[t]) = b ? b + static_cast<size_t>(t) * n : nullptr;
+    };
+#define TAPE(field, n) TA([&](Tape& tp) -> decltype(tp.field)& { return tp.field; }, (n))
+    TAPE(img4, M0 * 4);
+    TAPE(a1, M0 * 64); TAPE(cat5, M0 * 128); TAPE(p1, M1 * 64);
+    TAPE(a2, M1 * 128); TAPE(cat4, M1 * 256); TAPE(p2, M2 * 128);
+    TAPE(a3a, M2 * 256); TAPE(a3b, M2 * 256); TAPE(cat3, M2 * 512);
+    TAPE(p3, M3 * 256); TAPE(a4a, M3 * 512); TAPE(a4b, M3 * 512);
+    TAPE(h4, M3 * g); TAPE(aux, M3 * 64); TAPE(auxp, M3 * 64);
+    TAPE(pin, M3 * g); TAPE(postin, M3 * g); TAPE(fin, M3 * g);
+    TAPE(z, M3 * 64); TAPE(zprior, M3 * 64);
+    for (int s = 0; s < 3; ++s)
+      for (int l = 0; l < 2; ++l) {
+        TAPE(hs[s][l], M3 * g);
+        TAPE(cs[s][l], M3 * g);
+        TAPE(gates[s][l], M3 * 4 * g);
+        if (T->gn) {
+          TAPE(raw_ih[s][l], M3 * 4 * g); TAPE(raw_hh[s][l], M3 * 4 * g);
+          TAPE(c_raw[s][l], M3 * g); TAPE(gn_stats[s][l], static_cast<size_t>(B) * 96);
         }
-      tp.d2a = bp.take<bf16>(M3 * 512); tp.d2b = bp.take<bf16>(M3 * 512); tp.d3a = bp.take<bf16>(M2 * 256);
-      tp.d3b = bp.take<bf16>(M2 * 256); tp.d4a = bp.take<bf16>(M1 * 128); tp.d5 = bp.take<bf16>(M0 * 64);
-      tp.dcat5 = tp.cat5; tp.dcat4 = tp.cat4; tp.dcat3 = tp.cat3;
-      // fixed_skip: every step decodes from its own concat buffers (skip halves = copies of step 0's encoder outputs).
-      // Step 0 could use cat* directly, but the all-time-steps weight gradient reads the decoder inputs through ONE
-      // tensor map with a constant step stride, so step 0 gets its own buffers too
-      if (cfg->fixed_skip && (t > 0 || T->wgrad_implicit)) {
-        tp.dcat5 = bp.take<bf16>(M0 * 128); tp.dcat4 = bp.take<bf16>(M1 * 256); tp.dcat3 = bp.take<bf16>(M2 * 512);
       }
-      for (int i = 0; i < 19; ++i) {
-        const VggDef d = i < 10 ? enc_def(h, i) : dec_def(h, i - 10);
-        tp.vgg[i].raw = bp.take<float>(static_cast<size_t>(B) * d.H * d.W * d.cout);
-        tp.vgg[i].mean = bp.take<float>(d.cout);
-        tp.vgg[i].rstd = bp.take<float>(d.cout);
+    TAPE(d2a, M3 * 512); TAPE(d2b, M3 * 512); TAPE(d3a, M2 * 256);
+    TAPE(d3b, M2 * 256); TAPE(d4a, M1 * 128); TAPE(d5, M0 * 64);
+    if (cfg->fixed_skip) {
+      // every step decodes from its own concat buffers (skip halves = copies of step 0's encoder outputs); step 0 too,
+      // so that the decoder inputs of all steps are one time-major tensor for the weight gradient
+      TAPE(dcat5, M0 * 128); TAPE(dcat4, M1 * 256); TAPE(dcat3, M2 * 512);
+    } else {
+      for (int t = 0; t < S; ++t) {
+        Tape& tp = T->tape[t];
+        tp.dcat5 = tp.cat5; tp.dcat4 = tp.cat4; tp.dcat3 = tp.cat3;
       }
-      const size_t zn = static_cast<size_t>(B) * z * 48;
-      tp.mu_p = bp.take<float>(zn); tp.lv_p = bp.take<float>(zn); tp.mu = bp.take<float>(zn); tp.lv = bp.take<float>(zn);
-      tp.eps_p = bp.take<float>(zn); tp.eps_q = bp.take<float>(zn);
-      tp.x4 = bp.take<float>(M0 * 4);
-      tp.xp = bp.take<float>(M0 * 3);
     }
-    T->G_d5 = bp.take<float>(M0 * 64); T->G_cat5 = bp.take<float>(M0 * 128); T->G_d4a = bp.take<float>(M1 * 128);
-    T->G_cat4 = bp.take<float>(M1 * 256); T->G_d3b = bp.take<float>(M2 * 256); T->G_d3a = bp.take<float>(M2 * 256);
-    T->G_cat3 = bp.take<float>(M2 * 512); T->G_d2b = bp.take<float>(M3 * 512); T->G_d2a = bp.take<float>(M3 * 512);
-    T->G_fin = bp.take<float>(M3 * g); T->G_pin = bp.take<float>(M3 * g); T->G_postin = bp.take<float>(M3 * g);
-    T->G_z = bp.take<float>(M3 * 64); T->G_h4 = bp.take<float>(M3 * g);
-    T->G_a4b = bp.take<float>(M3 * 512); T->G_a4a = bp.take<float>(M3 * 512); T->G_p3 = bp.take<float>(M3 * 256);
-    T->G_a3b = bp.take<float>(M2 * 256); T->G_a3a = bp.take<float>(M2 * 256); T->G_p2 = bp.take<float>(M2 * 128);
-    T->G_a2 = bp.take<float>(M1 * 128); T->G_p1 = bp.take<float>(M1 * 64); T->G_a1 = bp.take<float>(M0 * 64);
+    for (int i = 0; i < 19; ++i) {
+      const VggDef d = i < 10 ? enc_def(h, i) : dec_def(h, i - 10);
+      TAPE(vgg[i].raw, static_cast<size_t>(B) * d.H * d.W * d.cout);
+      TAPE(vgg[i].mean, static_cast<size_t>(d.cout));
+      TAPE(vgg[i].rstd, static_cast<size_t>(d.cout));
+    }
+    const size_t zn = static_cast<size_t>(B) * z * 48;
+    TAPE(mu_p, zn); TAPE(lv_p, zn); TAPE(mu, zn); TAPE(lv, zn);
+    TAPE(eps_p, zn); TAPE(eps_q, zn);
+    TAPE(x4, M0 * 4);
+    TAPE(xp, M0 * 3);
+#undef TAPE
+    auto GB = [&](GBuf& b, size_t n) { b.n = n; b.p = bp.take<float>(static_cast<size_t>(S) * n); };
+    GB(T->G_d5, M0 * 64); GB(T->G_cat5, M0 * 128); GB(T->G_d4a, M1 * 128);
+    GB(T->G_cat4, M1 * 256); GB(T->G_d3b, M2 * 256); GB(T->G_d3a, M2 * 256);
+    GB(T->G_cat3, M2 * 512); GB(T->G_d2b, M3 * 512); GB(T->G_d2a, M3 * 512);
+    GB(T->G_fin, M3 * g); GB(T->G_pin, M3 * g); GB(T->G_postin, M3 * g);
+    GB(T->G_z, M3 * 64); GB(T->G_h4, M3 * g);
+    GB(T->G_a4b, M3 * 512); GB(T->G_a4a, M3 * 512); GB(T->G_p3, M3 * 256);
+    GB(T->G_a3b, M2 * 256); GB(T->G_a3a, M2 * 256); GB(T->G_p2, M2 * 128);
+    GB(T->G_a2, M1 * 128); GB(T->G_p1, M1 * 64); GB(T->G_a1, M0 * 64);
+    GB(T->draw32, M0 * 64);
     T->G_skip5 = bp.take<float>(M0 * 64); T->G_skip4 = bp.take<float>(M1 * 128); T->G_skip3 = bp.take<float>(M2 * 256);
     for (int s = 0; s < 3; ++s)
       for (int l = 0; l < 2; ++l) {
-        T->G_hs[s][l][0] = bp.take<float>(M3 * g);
-        T->G_hs[s][l][1] = bp.take<float>(M3 * g);
+        GB(T->DH[s][l], M3 * g);
         T->G_dc[s][l] = bp.take<float>(M3 * g);
       }
-    const size_t dy_elems = std::max(M0 * 64, M3 * static_cast<size_t>(4 * g));
-    T->dy_a = bp.take<bf16>(dy_elems); T->dy_b = bp.take<bf16>(dy_elems);
-    T->bn_scratch = bp.take<float>(2 * 2048);
-    T->draw32 = bp.take<float>(M0 * 64);
+    T->bn_scratch = bp.take<float>(static_cast<size_t>(S) * 2 * 2048);
     T->fw_part = bp.take<float>(static_cast<size_t>(kFwBlocks) * 45 * 64);
     T->hzero = bp.take<bf16>(M3 * g); T->czero = bp.take<float>(M3 * g);
     T->G_img[0] = bp.take<float>(M0 * 3); T->G_img[1] = bp.take<float>(M0 * 3);
     T->dbg_draw32 = bp.take<float>(M0 * 64);
-    T->loss_part = bp.take<float>(B); T->kl_tmp = bp.take<float>(4);
+    T->loss_part = bp.take<float>(static_cast<size_t>(S) * B);
+    T->metric_part = bp.take<float>(std::max<size_t>(static_cast<size_t>(2) * S * B, 64));
     if (T->gn) {
       T->gn_dy = bp.take<float>(M3 * 4 * g);
       T->gn_part = bp.take<float>(static_cast<size_t>(B) * 14 * g);
     }
-    if (T->wgrad_implicit) {
-      // split-K scratch: the largest splits x |dWp| over the layers that need more than one slice
+    {
+      // split-K scratch of the weight gradient: the largest splits x |dWp| over the layers that need more than one slice
       size_t need = 4;
       for (int i = 1; i < T->nlayers; ++i) {
         const TLayer& L = T->L[i];
         const size_t rows = rows_of(i);
         const int W = rows == M0 ? 64 : rows == M1 ? 32 : rows == M2 ? 16 : 8;
         WgradGeom wg = wg_plan(L, B, W * 3 / 4, W, S);
-        int one_src[1] = {L.ctot};
-        wg_ctiles(wg, one_src, 1);  // (an upper bound on the tile count is enough: more tiles = fewer splits)
-        wg.num_ctiles = std::max(1, L.ctot / 256);
+        wg.num_ctiles = std::max(1, L.ctot / 256);  // (a lower bound on the tile count: more tiles = fewer splits)
         wg_split(wg, h->num_sms);
         if (wg.splits > 1) need = std::max(need, static_cast<size_t>(wg.splits) * static_cast<size_t>(wg.out_split_stride));
       }
@@ -848,20 +929,6 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
       CK(cudaMalloc(&T->arena, bp.off + 1024));
       CK(cudaMemset(T->arena, 0, bp.off + 1024));
     }
-  }
-  // every step of the tape allocates the same sequence of buffers: one constant stride between time steps
-  T->step_bytes = S > 1 ? static_cast<unsigned long long>(reinterpret_cast<const char*>(T->tape[1].img4) -
-                                                          reinterpret_cast<const char*>(T->tape[0].img4))
-                        : (1ull << 20);
-  for (int t = 1; t < S; ++t) {
-    const Tape &a = T->tape[t - 1], &b = T->tape[t];
-    const char* pa[] = {reinterpret_cast<const char*>(a.img4), reinterpret_cast<const char*>(a.hs[2][1]),
-                        reinterpret_cast<const char*>(a.d5), reinterpret_cast<const char*>(a.dcat3), reinterpret_cast<const char*>(a.xp)};
-    const char* pb[] = {reinterpret_cast<const char*>(b.img4), reinterpret_cast<const char*>(b.hs[2][1]),
-                        reinterpret_cast<const char*>(b.d5), reinterpret_cast<const char*>(b.dcat3), reinterpret_cast<const char*>(b.xp)};
-    for (int k = 0; k < 5; ++k)
-      if (static_cast<unsigned long long>(pb[k] - pa[k]) != T->step_bytes && T->wgrad_implicit)
-        return fail(h, RAC_ERR_STATE, "training tape: time steps are not equally spaced");
   }
   return RAC_OK;
 }
@@ -890,37 +957,80 @@ int rac_train_forward_backward(rac_handle* h, const rac_train_batch* bt, void* s
     CK(launch_pack_weights(T->params, L.d.row_off, L.d.col_off, L.n_packed, L.taps, L.ctot, L.d.flip, L.wp, st));
     CK(launch_transpose_flip(L.wp, L.n_packed, L.taps, L.ctot, L.kpad, L.wd, st));
     if (L.d.bias_off) CK(launch_gather_f32(T->params, L.d.bias_off, L.n_packed, L.bias, st));
-    // (the implicit-GEMM weight gradient writes every element of dWp; only the round-1 GEMM accumulates into it)
-    if (!T->wgrad_implicit) CK(cudaMemsetAsync(L.dwp, 0, sizeof(float) * L.kpad * L.taps * L.ctot, st));
   }
   CK(launch_pack_first(T->params + T->L[RAC_L_ENC_C1_0].d.w_off, h->enc_cin, T->wfirst, st));
   CK(cudaMemsetAsync(T->grads, 0, sizeof(float) * T->cfg.n_params, st));
   CK(cudaMemsetAsync(bt->losses, 0, sizeof(float) * 4, st));
+  // ---- reparameterisation noise of all steps (the tape is time-major: one copy / one fill per tensor)
   const size_t zn = static_cast<size_t>(B) * z * 48;
-  // Philox counter of the reparameterisation noise = the caller's global training step (persisted in checkpoints),
-  // NOT a count kept in this state: rac_train_create runs again after a resume or a new batch shape and must not
-  // replay the noise of steps 0..k
+  // Philox counter = the caller's global training step (persisted in checkpoints), NOT a count kept in this state:
+  // rac_train_create runs again after a resume or a new batch shape and must not replay the noise of steps 0..k
   const unsigned int noise_step = static_cast<unsigned int>(bt->noise_step);
-  for (int t = 0; t < S; ++t) {
-    Tape& tp = T->tape[t];
-    if (bt->eps_prior) CK(cudaMemcpyAsync(tp.eps_p, bt->eps_prior + t * zn, sizeof(float) * zn, cudaMemcpyDeviceToDevice, st));
-    else CK(launch_normal_fill(tp.eps_p, static_cast<long long>(zn), bt->seed, 2u * (noise_step * S + t), st));
-    if (bt->eps_post) CK(cudaMemcpyAsync(tp.eps_q, bt->eps_post + t * zn, sizeof(float) * zn, cudaMemcpyDeviceToDevice, st));
-    else CK(launch_normal_fill(tp.eps_q, static_cast<long long>(zn), bt->seed, 2u * (noise_step * S + t) + 1u, st));
-    CKR(train_forward_step(h, T, bt, t, st));
+  if (bt->eps_prior) CK(cudaMemcpyAsync(T->tape[0].eps_p, bt->eps_prior, sizeof(float) * zn * S, cudaMemcpyDeviceToDevice, st));
+  else CK(launch_normal_fill(T->tape[0].eps_p, static_cast<long long>(zn) * S, bt->seed, 2u * noise_step, st));
+  if (bt->eps_post) CK(cudaMemcpyAsync(T->tape[0].eps_q, bt->eps_post, sizeof(float) * zn * S, cudaMemcpyDeviceToDevice, st));
+  else CK(launch_normal_fill(T->tape[0].eps_q, static_cast<long long>(zn) * S, bt->seed, 2u * noise_step + 1u, st));
+  // Teacher-forced clip (every input frame is ground truth) with per-step skips: nothing but the ConvLSTM cells depends
+  // on the previous time step, so every other layer runs ONCE over all S * B images. A step that consumes the model's
+  // own prediction (scheduled sampling), or fixed_skip (whose skip gradients are summed over time), goes step by step
+  bool batched = !T->per_step && !T->cfg.fixed_skip;
+  if (bt->true_token)
+    for (int t = 1; t < S; ++t) batched = batched && bt->true_token[t] != 0;
+  const Span all{0, S};
+  // ---- forward
+  if (batched) {
+    CKR(forward_encoder(h, T, bt, all, st));
+    CKR(forward_input_convs(h, T, bt, all, st));
+    for (int t = 0; t < S; ++t) CKR(lstm_forward(h, T, 0, t, T->tape[t].pin, st));
+    CKR(forward_gauss(h, T, 0, all, st));
+    for (int t = 0; t < S; ++t) CKR(lstm_forward(h, T, 1, t, T->tape[t].postin, st));
+    CKR(forward_gauss(h, T, 1, all, st));
+    CKR(forward_fp_in(h, T, all, st));
+    for (int t = 0; t < S; ++t) CKR(lstm_forward(h, T, 2, t, T->tape[t].fin, st));
+    CKR(forward_decoder(h, T, bt, all, st));
+  } else {
+    for (int t = 0; t < S; ++t) {
+      const Span one{t, 1};
+      CKR(forward_encoder(h, T, bt, one, st));
+      CKR(forward_input_convs(h, T, bt, one, st));
+      CKR(lstm_forward(h, T, 0, t, T->tape[t].pin, st));
+      CKR(forward_gauss(h, T, 0, one, st));
+      CKR(lstm_forward(h, T, 1, t, T->tape[t].postin, st));
+      CKR(forward_gauss(h, T, 1, one, st));
+      CKR(forward_fp_in(h, T, one, st));
+      CKR(lstm_forward(h, T, 2, t, T->tape[t].fin, st));
+      CKR(forward_decoder(h, T, bt, one, st));
+    }
   }
   // ---- BPTT
   for (int s = 0; s < 3; ++s)
     for (int l = 0; l < 2; ++l) {
-      CK(cudaMemsetAsync(T->G_hs[s][l][0], 0, sizeof(float) * M3 * g, st));
-      CK(cudaMemsetAsync(T->G_hs[s][l][1], 0, sizeof(float) * M3 * g, st));
+      CK(cudaMemsetAsync(T->DH[s][l].p, 0, sizeof(float) * M3 * g * S, st));
       CK(cudaMemsetAsync(T->G_dc[s][l], 0, sizeof(float) * M3 * g, st));
     }
-  int cur = 0;
-  for (int t = S - 1; t >= 0; --t) {
-    T->cur_t = t;
-    CKR(train_backward_step(h, T, bt, t, cur, st));
-    cur ^= 1;
+  if (batched) {
+    CKR(backward_decoder(h, T, bt, all, st));
+    for (int t = S - 1; t >= 0; --t) CKR(lstm_backward(h, T, 2, t, T->tape[t].fin, T->G_fin.at(t), st));
+    CKR(backward_fp_in(h, T, all, st));
+    CKR(backward_gauss(h, T, all, st));
+    for (int t = S - 1; t >= 0; --t) CKR(lstm_backward(h, T, 1, t, T->tape[t].postin, T->G_postin.at(t), st));
+    CKR(backward_input_conv(h, T, 1, all, st));
+    for (int t = S - 1; t >= 0; --t) CKR(lstm_backward(h, T, 0, t, T->tape[t].pin, T->G_pin.at(t), st));
+    CKR(backward_input_conv(h, T, 0, all, st));
+    CKR(backward_encoder(h, T, bt, all, st));
+  } else {
+    for (int t = S - 1; t >= 0; --t) {
+      const Span one{t, 1};
+      CKR(backward_decoder(h, T, bt, one, st));
+      CKR(lstm_backward(h, T, 2, t, T->tape[t].fin, T->G_fin.at(t), st));
+      CKR(backward_fp_in(h, T, one, st));
+      CKR(backward_gauss(h, T, one, st));
+      CKR(lstm_backward(h, T, 1, t, T->tape[t].postin, T->G_postin.at(t), st));
+      CKR(backward_input_conv(h, T, 1, one, st));
+      CKR(lstm_backward(h, T, 0, t, T->tape[t].pin, T->G_pin.at(t), st));
+      CKR(backward_input_conv(h, T, 0, one, st));
+      CKR(backward_encoder(h, T, bt, one, st));
+    }
   }
   // ---- packed weight gradients -> flat parameter layout
   for (int i = 1; i < T->nlayers; ++i) {
@@ -935,12 +1045,13 @@ int rac_train_debug_buffer(rac_handle* h, const char* name, int step, void** ptr
   TrainState* T = static_cast<TrainState*>(h->train);
   if (step < 0 || step >= static_cast<int>(T->tape.size())) return fail(h, RAC_ERR_INVALID, "bad step %d", step);
   Tape& tp = T->tape[step];
+  // gradient accumulators: the slot of step 0 (the last step the backward pass processes)
   struct { const char* n; void* p; } tab[] = {
-      {"G_d5", T->G_d5}, {"G_cat5", T->G_cat5}, {"G_d4a", T->G_d4a}, {"G_cat4", T->G_cat4}, {"G_d3b", T->G_d3b},
-      {"G_d3a", T->G_d3a}, {"G_cat3", T->G_cat3}, {"G_d2b", T->G_d2b}, {"G_d2a", T->G_d2a}, {"G_fin", T->G_fin},
-      {"G_pin", T->G_pin}, {"G_postin", T->G_postin}, {"G_z", T->G_z}, {"G_h4", T->G_h4}, {"G_a4b", T->G_a4b},
-      {"G_a4a", T->G_a4a}, {"G_p3", T->G_p3}, {"G_a3b", T->G_a3b}, {"G_a3a", T->G_a3a}, {"G_p2", T->G_p2},
-      {"G_a2", T->G_a2}, {"G_p1", T->G_p1}, {"G_a1", T->G_a1},
+      {"G_d5", T->G_d5.p}, {"G_cat5", T->G_cat5.p}, {"G_d4a", T->G_d4a.p}, {"G_cat4", T->G_cat4.p}, {"G_d3b", T->G_d3b.p},
+      {"G_d3a", T->G_d3a.p}, {"G_cat3", T->G_cat3.p}, {"G_d2b", T->G_d2b.p}, {"G_d2a", T->G_d2a.p}, {"G_fin", T->G_fin.p},
+      {"G_pin", T->G_pin.p}, {"G_postin", T->G_postin.p}, {"G_z", T->G_z.p}, {"G_h4", T->G_h4.p}, {"G_a4b", T->G_a4b.p},
+      {"G_a4a", T->G_a4a.p}, {"G_p3", T->G_p3.p}, {"G_a3b", T->G_a3b.p}, {"G_a3a", T->G_a3a.p}, {"G_p2", T->G_p2.p},
+      {"G_a2", T->G_a2.p}, {"G_p1", T->G_p1.p}, {"G_a1", T->G_a1.p},
       {"img4", tp.img4}, {"a1", tp.a1}, {"cat5", tp.cat5}, {"p1", tp.p1}, {"a2", tp.a2}, {"cat4", tp.cat4},
       {"p2", tp.p2}, {"a3a", tp.a3a}, {"a3b", tp.a3b}, {"cat3", tp.cat3}, {"p3", tp.p3}, {"a4a", tp.a4a},
       {"a4b", tp.a4b}, {"h4", tp.h4}, {"d2a", tp.d2a}, {"d2b", tp.d2b}, {"d3a", tp.d3a}, {"d3b", tp.d3b},

@@ -214,16 +214,19 @@ cudaError_t launch_first_wgrad(const float* img4, const float* mask_a, const flo
 // ------------------------------------------------------------------------------------------------ BatchNorm
 // Per-channel reductions over all M rows, fp64, deterministic: grid (C/32, R) blocks of (32 channels x 32 row lanes)
 // write R partial sums per channel; a second tiny kernel folds them in a fixed order.
-constexpr int kRedSplit = 64;
-__device__ double g_red_part[2 * kRedSplit * 2048];  // [which][split][channel], channels <= 2048
+constexpr int kRedSplit = 64;   // row splits per group
+constexpr int kRedSlots = 512;  // groups x splits (a group = the rows of one time step: BatchNorm statistics are per step)
+__device__ double g_red_part[2 * kRedSlots * 2048];  // [which][group * splits + split][channel], channels <= 2048
 
 template <typename F>
 __device__ __forceinline__ void column_partial2(int M, int C, F load) {
+  // M = rows per group; blockIdx.z = group (rows [z * M, (z + 1) * M) of the tensor)
   __shared__ double sh1[32][33], sh2[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int rows_per = (M + gridDim.y - 1) / gridDim.y;
-  const int m_lo = blockIdx.y * rows_per;
-  const int m_hi = min(M, m_lo + rows_per);
+  const int m_base = blockIdx.z * M;
+  const int m_lo = m_base + blockIdx.y * rows_per;
+  const int m_hi = min(m_base + M, m_lo + rows_per);
   double a = 0.0, b = 0.0;
   if (c < C) {
     for (int m = m_lo + threadIdx.y; m < m_hi; m += 32) {
@@ -242,15 +245,16 @@ __device__ __forceinline__ void column_partial2(int M, int C, F load) {
       s1 += sh1[i][threadIdx.x];
       s2 += sh2[i][threadIdx.x];
     }
-    g_red_part[(0 * kRedSplit + blockIdx.y) * 2048 + c] = s1;
-    g_red_part[(1 * kRedSplit + blockIdx.y) * 2048 + c] = s2;
+    const int slot = blockIdx.z * gridDim.y + blockIdx.y;
+    g_red_part[(0 * kRedSlots + slot) * 2048 + c] = s1;
+    g_red_part[(1 * kRedSlots + slot) * 2048 + c] = s2;
   }
 }
-__device__ __forceinline__ void column_fold2(int c, int nsplit, double& s1, double& s2) {
+__device__ __forceinline__ void column_fold2(int c, int nsplit, double& s1, double& s2, int group = 0) {
   s1 = s2 = 0.0;
-  for (int r = 0; r < nsplit; ++r) {
-    s1 += __ldcg(&g_red_part[(0 * kRedSplit + r) * 2048 + c]);  // L2: written by other CTAs (of this launch, possibly)
-    s2 += __ldcg(&g_red_part[(1 * kRedSplit + r) * 2048 + c]);
+  for (int r = group * nsplit; r < (group + 1) * nsplit; ++r) {
+    s1 += __ldcg(&g_red_part[(0 * kRedSlots + r) * 2048 + c]);  // L2: written by other CTAs (of this launch, possibly)
+    s2 += __ldcg(&g_red_part[(1 * kRedSlots + r) * 2048 + c]);
   }
 }
 inline int red_split(int M) {
@@ -268,7 +272,7 @@ __device__ __forceinline__ bool last_block_of_column_group() {
   __syncthreads();
   if (threadIdx.x == 0 && threadIdx.y == 0) {
     const unsigned int t = atomicAdd(&g_red_ticket[blockIdx.x], 1u);
-    s_last = (t == gridDim.y - 1);
+    s_last = (t == gridDim.y * gridDim.z - 1);
     if (s_last) g_red_ticket[blockIdx.x] = 0u;  // ready for the next launch (stream order)
   }
   __syncthreads();
@@ -287,41 +291,48 @@ bn_stats_kernel(const float* __restrict__ raw, int M, int C, float* __restrict__
   if (!last_block_of_column_group()) return;
   const int c = blockIdx.x * 32 + threadIdx.x;
   if (threadIdx.y != 0 || c >= C) return;
-  const int nsplit = gridDim.y;
-  double s1, s2;
-  column_fold2(c, nsplit, s1, s2);
-  const double mu = s1 / M;
-  double var = s2 / M - mu * mu;
-  if (var < 0.0) var = 0.0;
-  mean[c] = static_cast<float>(mu);
-  rstd[c] = static_cast<float>(1.0 / sqrt(var + 1e-5));
-  const double unbiased = var * M / (M - 1);
+  const int nsplit = gridDim.y, groups = gridDim.z;
   float rm = rmean[c], rv = rvar[c];
-  for (int u = 0; u < updates; ++u) {  // reference: momentum 0.1, the encoder runs twice per step (dynamics.py:619)
-    rm = 0.9f * rm + 0.1f * static_cast<float>(mu);
-    rv = 0.9f * rv + 0.1f * static_cast<float>(unbiased);
+  for (int grp = 0; grp < groups; ++grp) {  // groups = time steps, in order: the running statistics are a recurrence
+    double s1, s2;
+    column_fold2(c, nsplit, s1, s2, grp);
+    const double mu = s1 / M;
+    double var = s2 / M - mu * mu;
+    if (var < 0.0) var = 0.0;
+    mean[grp * C + c] = static_cast<float>(mu);
+    rstd[grp * C + c] = static_cast<float>(1.0 / sqrt(var + 1e-5));
+    const double unbiased = var * M / (M - 1);
+    for (int u = 0; u < updates; ++u) {  // reference: momentum 0.1, the encoder runs twice per step (dynamics.py:619)
+      rm = 0.9f * rm + 0.1f * static_cast<float>(mu);
+      rv = 0.9f * rv + 0.1f * static_cast<float>(unbiased);
+    }
   }
   rmean[c] = rm;
   rvar[c] = rv;
 }
 cudaError_t launch_bn_stats(const float* raw, int M, int C, float* mean, float* rstd, float* running_mean,
-                            float* running_var, int updates, cudaStream_t s) {
-  if (C > 2048) return cudaErrorInvalidValue;
-  const int R = red_split(M);
-  bn_stats_kernel<<<dim3((C + 31) / 32, R), dim3(32, 32), 0, s>>>(raw, M, C, mean, rstd, running_mean, running_var, updates);
+                            float* running_var, int updates, cudaStream_t s, int groups) {
+  if (C > 2048 || groups < 1) return cudaErrorInvalidValue;
+  int R = red_split(M);
+  while (R * groups > kRedSlots) R /= 2;
+  if (R < 1) return cudaErrorInvalidValue;
+  bn_stats_kernel<<<dim3((C + 31) / 32, R, groups), dim3(32, 32), 0, s>>>(raw, M, C, mean, rstd, running_mean, running_var, updates);
   return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(256)
 bn_act_kernel(const float* __restrict__ raw, const float* __restrict__ mean, const float* __restrict__ rstd,
               const float* __restrict__ gamma, const float* __restrict__ beta, int B, int H, int W, int C,
-              __nv_bfloat16* __restrict__ out, int cstride, int coff, int upsample) {
+              __nv_bfloat16* __restrict__ out, int cstride, int coff, int upsample, int rows_per_group) {
   const int C8 = C / 8;
   const size_t total = static_cast<size_t>(B) * H * W * C8;
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c0 = static_cast<int>(i % C8) * 8;
   const size_t m = i / C8;
+  const size_t so = (m / rows_per_group) * C;  // statistics of this row's group (time step)
+  mean += so;
+  rstd += so;
   const int x = static_cast<int>(m % W), y = static_cast<int>((m / W) % H);
   const size_t b = m / (static_cast<size_t>(W) * H);
   float v[8];
@@ -343,10 +354,11 @@ bn_act_kernel(const float* __restrict__ raw, const float* __restrict__ mean, con
 }
 cudaError_t launch_bn_act(const float* raw, const float* mean, const float* rstd, const float* gamma,
                           const float* beta, int B, int H, int W, int C, __nv_bfloat16* out, int cstride, int coff,
-                          int upsample, cudaStream_t s) {
+                          int upsample, cudaStream_t s, int groups) {
   const size_t total = static_cast<size_t>(B) * H * W * (C / 8);
+  if (groups < 1 || B % groups) return cudaErrorInvalidValue;
   bn_act_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(raw, mean, rstd, gamma, beta, B, H, W, C,
-                                                                           out, cstride, coff, upsample);
+                                                                           out, cstride, coff, upsample, B / groups * H * W);
   return cudaGetLastError();
 }
 
@@ -354,11 +366,12 @@ struct BnBwdArgs {
   const float* dy;
   int dy_cstride, dy_coff, upsample;
   const float* raw;
-  const float* mean;
+  const float* mean;   // [groups][C]
   const float* rstd;
   const float* gamma;
   const float* beta;
   int H, W, C;
+  int rows_per_group;  // rows of one time step (the unit of the BatchNorm statistics)
 };
 // gradient w.r.t. the BN output after the LeakyReLU derivative, and the normalised activation
 __device__ __forceinline__ void bn_bwd_point(const BnBwdArgs& a, int m, int c, float& dz, float& xhat) {
@@ -373,7 +386,8 @@ __device__ __forceinline__ void bn_bwd_point(const BnBwdArgs& a, int m, int c, f
       for (int dx = 0; dx < 2; ++dx)
         g += a.dy[((b * 2 * a.H + 2 * y + dy) * (2 * a.W) + 2 * x + dx) * a.dy_cstride + a.dy_coff + c];
   }
-  xhat = (a.raw[static_cast<size_t>(m) * a.C + c] - a.mean[c]) * a.rstd[c];
+  const int so = (m / a.rows_per_group) * a.C;
+  xhat = (a.raw[static_cast<size_t>(m) * a.C + c] - a.mean[so + c]) * a.rstd[so + c];
   const float bn = xhat * a.gamma[c] + a.beta[c];
   dz = bn > 0.f ? g : 0.2f * g;
 }
@@ -389,12 +403,17 @@ bn_bwd_sums_kernel(BnBwdArgs a, int M, float* __restrict__ scratch, float* __res
   const int C = a.C;
   const int c = blockIdx.x * 32 + threadIdx.x;
   if (threadIdx.y != 0 || c >= C) return;
-  double s1, s2;
-  column_fold2(c, gridDim.y, s1, s2);
-  scratch[c] = static_cast<float>(s1);
-  scratch[C + c] = static_cast<float>(s2);
-  dbeta[c] += static_cast<float>(s1);
-  dgamma[c] += static_cast<float>(s2);
+  double t1 = 0.0, t2 = 0.0;
+  for (int grp = 0; grp < static_cast<int>(gridDim.z); ++grp) {
+    double s1, s2;
+    column_fold2(c, gridDim.y, s1, s2, grp);
+    scratch[grp * 2 * C + c] = static_cast<float>(s1);
+    scratch[grp * 2 * C + C + c] = static_cast<float>(s2);
+    t1 += s1;
+    t2 += s2;
+  }
+  dbeta[c] += static_cast<float>(t1);
+  dgamma[c] += static_cast<float>(t2);
 }
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(BnBwdArgs a, int M, const float* __restrict__ scratch, __nv_bfloat16* __restrict__ draw,
@@ -406,20 +425,25 @@ bn_bwd_apply_kernel(BnBwdArgs a, int M, const float* __restrict__ scratch, __nv_
   const int m = static_cast<int>(i / a.C);
   float dz, xh;
   bn_bwd_point(a, m, c, dz, xh);
-  const float inv = 1.f / M;
-  const float dx = a.gamma[c] * a.rstd[c] * (dz - scratch[c] * inv - xh * scratch[a.C + c] * inv);
-  draw[i] = __float2bfloat16(dx);
+  const int grp = m / a.rows_per_group;
+  const float inv = 1.f / a.rows_per_group;
+  const float* sc = scratch + grp * 2 * a.C;
+  const float dx = a.gamma[c] * a.rstd[grp * a.C + c] * (dz - sc[c] * inv - xh * sc[a.C + c] * inv);
+  if (draw) draw[i] = __float2bfloat16(dx);
   if (draw32) draw32[i] = dx;
 }
 cudaError_t launch_bn_bwd(const float* dy, int dy_cstride, int dy_coff, int upsample, const float* raw,
                           const float* mean, const float* rstd, const float* gamma, const float* beta, int B, int H,
                           int W, int C, float* scratch, __nv_bfloat16* draw, float* draw_f32_or_null, float* dgamma,
-                          float* dbeta, cudaStream_t s) {
-  BnBwdArgs a{dy, dy_cstride, dy_coff, upsample, raw, mean, rstd, gamma, beta, H, W, C};
+                          float* dbeta, cudaStream_t s, int groups) {
+  if (C > 2048 || groups < 1 || B % groups) return cudaErrorInvalidValue;
+  const int Mg = B / groups * H * W;
+  BnBwdArgs a{dy, dy_cstride, dy_coff, upsample, raw, mean, rstd, gamma, beta, H, W, C, Mg};
   const int M = B * H * W;
-  if (C > 2048) return cudaErrorInvalidValue;
-  const int R = red_split(M);
-  bn_bwd_sums_kernel<<<dim3((C + 31) / 32, R), dim3(32, 32), 0, s>>>(a, M, scratch, dgamma, dbeta);
+  int R = red_split(Mg);
+  while (R * groups > kRedSlots) R /= 2;
+  if (R < 1) return cudaErrorInvalidValue;
+  bn_bwd_sums_kernel<<<dim3((C + 31) / 32, R, groups), dim3(32, 32), 0, s>>>(a, Mg, scratch, dgamma, dbeta);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const size_t total = static_cast<size_t>(M) * C;
@@ -550,7 +574,7 @@ __global__ void __launch_bounds__(1024)
 frame_loss_kernel(const float* __restrict__ x4, const float* __restrict__ xj, const float* __restrict__ xi,
                   const float* __restrict__ mask, int kind, float rw, int B, int HW, float* __restrict__ loss_out,
                   __nv_bfloat16* __restrict__ dlogit, const float* __restrict__ gp_in, float* __restrict__ gxj_out,
-                  const float* __restrict__ batch_weight) {
+                  const float* __restrict__ batch_weight, int Bdiv) {
   __shared__ double sh[32];
   __shared__ float s_scale;
   const int b = blockIdx.x;
@@ -567,7 +591,10 @@ frame_loss_kernel(const float* __restrict__ x4, const float* __restrict__ xj, co
   // kind: 0 l1, 1 dontcare_l1, 2 mse (nn.MSELoss), 3 dontcare_mse (trainer.py:149-161; losses.py:11-50). batch_weight
   // (movement weighting, trainer.py:426-429) multiplies the per-sample term of the two l1 kinds only, as the reference
   const bool dontcare = (kind & 1) != 0, squared = kind >= 2;
-  const float bw = (batch_weight && !squared) ? batch_weight[b] : 1.f;
+  // B = samples of this launch (one CTA each; several time steps when batched), Bdiv = batch size of ONE step: every
+  // step's loss is a mean over its own batch
+  const float bw = (batch_weight && !squared) ? batch_weight[b % Bdiv] : 1.f;
+  B = Bdiv;
   if (dontcare) {
     double cnt = 0.0;
     for (int p = tid; p < HW; p += blockDim.x) cnt += mask[static_cast<size_t>(b) * HW + p] != 0.f ? 0.0 : 3.0;
@@ -610,10 +637,10 @@ frame_loss_kernel(const float* __restrict__ x4, const float* __restrict__ xj, co
 }
 cudaError_t launch_frame_loss(const float* x4, const float* xj, const float* xi, const float* mask, int kind,
                               float robot_weight, int B, int HW, float* loss_out, __nv_bfloat16* dlogit,
-                              const float* gp_in, float* gxj_out, cudaStream_t s, const float* batch_weight) {
+                              const float* gp_in, float* gxj_out, cudaStream_t s, const float* batch_weight, int Bdiv) {
   if ((kind & 1) && !mask) return cudaErrorInvalidValue;
   frame_loss_kernel<<<B, 1024, 0, s>>>(x4, xj, xi, mask, kind, robot_weight, B, HW, loss_out, dlogit, gp_in, gxj_out,
-                                       batch_weight);
+                                       batch_weight, Bdiv > 0 ? Bdiv : B);
   return cudaGetLastError();
 }
 
@@ -891,6 +918,83 @@ img_prep_train_kernel(const float* __restrict__ img, const float* __restrict__ m
 cudaError_t launch_img_prep_train(const float* img_nchw, const float* mask, float* img4, int B, int HW, cudaStream_t s) {
   const size_t total = static_cast<size_t>(B) * HW;
   img_prep_train_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(img_nchw, mask, img4, B, HW);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ logged metrics
+// robot_mse_criterion / world_mse_criterion (losses.py:52-78) for n samples (several time steps at once): one CTA per
+// sample, then a single thread adds the per-sample terms in index order (deterministic). out2[0] += sum_b robot_b / Bdiv.
+__global__ void __launch_bounds__(256)
+robot_world_mse_part_kernel(const float* __restrict__ p, const float* __restrict__ t, const float* __restrict__ mask,
+                            float* __restrict__ part, int HW) {
+  __shared__ double sh[3][8];
+  const int b = blockIdx.x;
+  double sr = 0.0, sw = 0.0, cr = 0.0;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const bool rb = mask[static_cast<size_t>(b) * HW + i] != 0.f;
+    float sd = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const size_t q = (static_cast<size_t>(b) * 3 + c) * HW + i;
+      const float d = t[q] - p[q];
+      sd += d * d;
+    }
+    if (rb) { sr += sd; cr += 3.0; } else { sw += sd; }
+  }
+  double v[3] = {sr, sw, cr};
+  for (int k = 0; k < 3; ++k) {
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if ((threadIdx.x & 31) == 0) sh[k][threadIdx.x >> 5] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a[3] = {0.0, 0.0, 0.0};
+    for (int k = 0; k < 3; ++k)
+      for (int w = 0; w < 8; ++w) a[k] += sh[k][w];
+    part[2 * b] = static_cast<float>(a[0] / (a[2] + 1.0));
+    part[2 * b + 1] = static_cast<float>(a[1] / (3.0 * HW - a[2] + 1.0));
+  }
+}
+__global__ void metric_fold_kernel(const float* __restrict__ part, int n, int width, double scale, float* __restrict__ out) {
+  if (threadIdx.x < width && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += static_cast<double>(part[i * width + threadIdx.x]);
+    out[threadIdx.x] += static_cast<float>(s * scale);
+  }
+}
+cudaError_t launch_robot_world_mse_batched(const float* pred, const float* target, const float* mask, float* part,
+                                           float* out2, int n, int Bdiv, int HW, cudaStream_t s) {
+  robot_world_mse_part_kernel<<<n, 256, 0, s>>>(pred, target, mask, part, HW);
+  metric_fold_kernel<<<1, 32, 0, s>>>(part, n, 2, 1.0 / Bdiv, out2);
+  return cudaGetLastError();
+}
+
+// KL(N(mu1, s1) || N(mu2, s2)) summed over everything / bs (losses.py:97-106), n elements (several steps at once):
+// 64 CTAs of partial sums, folded in order; out[0] += sum / bs
+__global__ void __launch_bounds__(256)
+kl_part_kernel(const float* __restrict__ mu1, const float* __restrict__ lv1, const float* __restrict__ mu2,
+               const float* __restrict__ lv2, float* __restrict__ part, long long n) {
+  __shared__ double sh[8];
+  double acc = 0.0;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float s1 = expf(0.5f * lv1[i]), s2 = expf(0.5f * lv2[i]);
+    const float dm = mu1[i] - mu2[i];
+    acc += static_cast<double>(logf(s2 / s1) + (expf(lv1[i]) + dm * dm) / (2.f * expf(lv2[i])) - 0.5f);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    part[blockIdx.x] = static_cast<float>(t);
+  }
+}
+cudaError_t launch_kl_loss_batched(const float* mu1, const float* lv1, const float* mu2, const float* lv2, float* part,
+                                   float* out_accum, long long n, int bs, cudaStream_t s) {
+  kl_part_kernel<<<64, 256, 0, s>>>(mu1, lv1, mu2, lv2, part, n);
+  metric_fold_kernel<<<1, 32, 0, s>>>(part, 64, 1, 1.0 / bs, out_accum);
   return cudaGetLastError();
 }
 

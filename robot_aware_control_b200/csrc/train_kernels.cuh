@@ -28,18 +28,20 @@ cudaError_t launch_first_wgrad(const float* img4, const float* mask_a, const flo
 
 // ---- BatchNorm (train mode) + LeakyReLU(0.2)
 // raw: [M, C] fp32 (pre-BN conv output). mean / rstd: [C]. running stats updated `updates` times (momentum 0.1).
+// groups > 1: the tensor holds `groups` time steps of M rows each; statistics (mean / rstd [groups][C]) are per step and
+// the running statistics are updated step after step
 cudaError_t launch_bn_stats(const float* raw, int M, int C, float* mean, float* rstd, float* running_mean,
-                            float* running_var, int updates, cudaStream_t s);
+                            float* running_var, int updates, cudaStream_t s, int groups = 1);
 cudaError_t launch_bn_act(const float* raw, const float* mean, const float* rstd, const float* gamma,
                           const float* beta, int B, int H, int W, int C, __nv_bfloat16* out, int cstride, int coff,
-                          int upsample, cudaStream_t s);
+                          int upsample, cudaStream_t s, int groups = 1);
 // dy: gradient w.r.t. the layer output, fp32 rows of `dy_cstride` floats starting at channel dy_coff; with
 // upsample=1 it lives on the 2H x 2W grid and the four replicated positions are summed.
 // Produces draw [M, C] bf16 (gradient w.r.t. the raw conv output) and accumulates dgamma / dbeta.
 cudaError_t launch_bn_bwd(const float* dy, int dy_cstride, int dy_coff, int upsample, const float* raw,
                           const float* mean, const float* rstd, const float* gamma, const float* beta, int B, int H,
-                          int W, int C, float* scratch /* [2*C] */, __nv_bfloat16* draw, float* draw_f32_or_null,
-                          float* dgamma, float* dbeta, cudaStream_t s);
+                          int W, int C, float* scratch /* [groups][2*C] */, __nv_bfloat16* draw, float* draw_f32_or_null,
+                          float* dgamma, float* dbeta, cudaStream_t s, int groups = 1);
 
 // ---- NormConvLSTMCell (cfg.lstm_group_norm), pointwise + GroupNorm part: train_gn_kernels.cu
 struct GnCellArgs {
@@ -92,7 +94,14 @@ cudaError_t launch_gauss_bwd(const float* dz, const float* mu, const float* lv, 
 // prediction as its input, scheduled sampling) or null; gxj_out: gradient w.r.t. x_j through the composite (=) or null.
 cudaError_t launch_frame_loss(const float* x4, const float* xj, const float* xi, const float* mask, int kind,
                               float robot_weight, int B, int HW, float* loss_out, __nv_bfloat16* dlogit /* [B*HW, 64] */,
-                              const float* gp_in, float* gxj_out, cudaStream_t s, const float* batch_weight = nullptr);
+                              const float* gp_in, float* gxj_out, cudaStream_t s, const float* batch_weight = nullptr,
+                              int Bdiv = 0 /* batch size of one time step when B holds several; 0 = B */);
+// logged robot / world MSE (losses.py:52-78) and the KL term (losses.py:97-106) over several time steps at once;
+// part: scratch (2 * n resp. 64 floats); results are ADDED to out2[0..1] / out_accum[0]
+cudaError_t launch_robot_world_mse_batched(const float* pred, const float* target, const float* mask, float* part,
+                                           float* out2, int n, int Bdiv, int HW, cudaStream_t s);
+cudaError_t launch_kl_loss_batched(const float* mu1, const float* lv1, const float* mu2, const float* lv2, float* part,
+                                   float* out_accum, long long n, int bs, cudaStream_t s);
 // x_pred = (1 - m) * x_j + m * rgb (trainer.py:406-407), NCHW fp32 (B,3,H,W)
 cudaError_t launch_composite(const float* x4, const float* xj, float* xp, int B, int HW, cudaStream_t s);
 // gradient of encoder.c1.0 w.r.t. its rgb input channels, accumulated (+=) into gimg (B,3,H,W); robot pixels of

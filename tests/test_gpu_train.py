@@ -356,3 +356,26 @@ def test_train_oracle_bf16_sensitivity_is_inherent():
     _, gb = b.loss_and_grads(batch, ep[:1], eq[:1])
     assert _rel(gb["decoder.upc2.0.main.0.weight"], ga["decoder.upc2.0.main.0.weight"]) > 0.1
     assert _rel(gb["prior.lstm.0.gates.weight"], ga["prior.lstm.0.gates.weight"]) < 2e-2
+
+
+@pytest.mark.parametrize("tag", ["vanilla", "ra", "ra_gn"])
+def test_time_batched_step_matches_step_by_step(tag, monkeypatch):
+    """A teacher-forced clip runs every non-recurrent layer ONCE over all time steps (n * B images per launch, per-step
+    BatchNorm statistics); RAC_TRAIN_PER_STEP=1 walks the same clip step by step (the path scheduled sampling uses).
+    Same packed operands and fp32 accumulation; only the tile shapes / summation orders differ."""
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("RAC_TRAIN_PER_STEP", mode)
+        cfg, sd, model, trainer, batch, ep, eq = _setup(tag, 3)
+        trainer.set_noise(ep, eq)
+        losses = trainer.forward_backward(batch).cpu().numpy().copy()
+        out[mode] = (losses, trainer.grads.clone(), trainer.buffers.clone())
+    np.testing.assert_allclose(out["0"][0], out["1"][0], rtol=2e-4)
+    np.testing.assert_allclose(out["0"][2].cpu().numpy(), out["1"][2].cpu().numpy(), rtol=1e-4, atol=1e-6)  # running stats
+    for k in ("prior.lstm.0.gates.weight", "prior.mu_net.weight", "prior_input_conv.weight") if tag != "ra_gn" else (
+            "prior.lstm.0.ih_gates.0.weight", "prior.mu_net.weight"):
+        o = trainer._offsets[k]
+        n = dict(trainer.model.named_parameters())[k].numel()
+        assert _rel(out["0"][1][o:o + n], out["1"][1][o:o + n]) < 2e-2, k
+    cos = float((out["0"][1] * out["1"][1]).sum() / (out["0"][1].norm() * out["1"][1].norm()))
+    assert cos > 0.98, cos  # (the l1 path is chaos-limited: a few sign / ReLU decisions flip with the summation order)
