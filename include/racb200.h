@@ -350,8 +350,8 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg,
 int rac_train_destroy(rac_handle* h);
 /* forward (train-mode BatchNorm, posterior) + BPTT backward: fills `grads` (caller may all-reduce it) */
 int rac_train_forward_backward(rac_handle* h, const rac_train_batch* batch, void* stream);
-/* test hook: device pointer of a gradient accumulator ("G_d5", "G_cat5", ...: they hold the values of the LAST
- * processed step, i.e. step 0) or of a saved forward tensor of time step `step` ("cat5", "d5", "raw18", ...) */
+/* test hook: device pointer of a gradient accumulator ("G_d5", "G_cat5", ...) or of a saved forward tensor ("cat5",
+ * "d5", "raw18", ...) of time step `step` */
 int rac_train_debug_buffer(rac_handle* h, const char* name, int step, void** ptr);
 /* params <- Adam(params, grads) */
 int rac_train_adam_step(rac_handle* h, void* stream);

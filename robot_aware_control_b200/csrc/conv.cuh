@@ -17,7 +17,11 @@ namespace rac {
 // EPI_LSTM = inference cell (MUFU math, epilogue-private cell-state layout); EPI_LSTM_TRAIN = training cell (libm math,
 // NHWC cell state read from c_in, gates saved for the backward pass) -- separate instantiations keep each one's code small
 // EPI_GATES = raw fp32 gate pre-activations of a NormConvLSTMCell convolution + per-sample GroupNorm partial sums
-enum EpiMode : int { EPI_ACT = 0, EPI_LSTM = 1, EPI_GAUSS = 2, EPI_FRAME = 3, EPI_F32 = 4, EPI_LSTM_TRAIN = 5, EPI_GATES = 6 };
+// EPI_F32_BT = EPI_F32 with the weight operand read "transposed" straight from the FORWARD packing Wp[n][tap][c] (dgrad
+// of the training step: B[c][(tap, n)] = Wp[n][taps-1-tap][c] is an MN-major operand of tcgen05 -- no transposed,
+// flipped copy of the weights is ever materialised)
+enum EpiMode : int { EPI_ACT = 0, EPI_LSTM = 1, EPI_GAUSS = 2, EPI_FRAME = 3, EPI_F32 = 4, EPI_LSTM_TRAIN = 5, EPI_GATES = 6,
+                     EPI_F32_BT = 7 };
 
 // One destination of the fp32 epilogue: packed columns [n_begin, n_end) of the GEMM go to dst (row-major NHWC rows,
 // `cstride` floats per row, starting at channel `coff`); accumulate: += instead of =. Bounds are multiples of 32.

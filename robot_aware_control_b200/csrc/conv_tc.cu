@@ -51,6 +51,10 @@ template <int BLOCK_M, int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(TcCfg<BLOCK_M, BLOCK_N>::kThreads, 1)
 conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const EpiParams e) {
   using Cfg = TcCfg<BLOCK_M, BLOCK_N>;
+  // dgrad with the weights in their forward packing Wp[n][tap][c]: tm.w is a 3-D map (c, tap, n), a 64-channel box
+  // {64 c, 1 tap, 64 n} is one MN-major swizzle group of the B operand (K = n is the slow dimension), taps are flipped
+  constexpr bool kBmn = (EPI == EPI_F32_BT);
+  static_assert(!kBmn || BLOCK_N % 64 == 0, "MN-major weight boxes are 64 channels wide");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* bar_base = smem + Cfg::kStages * Cfg::kStageBytes;
@@ -131,7 +135,15 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
               mbar_arrive_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
               if (g.y_major) tma_load_4d(&tm.a[s], &full_bar[stage], sa, kb * kBlockK, kw - g.pad, b0, y0 + kh - g.pad);
               else tma_load_4d(&tm.a[s], &full_bar[stage], sa, kb * kBlockK, kw - g.pad, y0 + kh - g.pad, b0);
-              tma_load_2d(&tm.w, &full_bar[stage], sb, kidx * kBlockK, n_tile * BLOCK_N);
+              if constexpr (kBmn) {
+                const int taps = g.ks * g.ks;
+#pragma unroll
+                for (int j = 0; j < BLOCK_N / 64; ++j)
+                  tma_load_3d(&tm.w, &full_bar[stage], sb + j * 8192, n_tile * BLOCK_N + j * 64, taps - 1 - (kh * g.ks + kw),
+                              kb * kBlockK);
+              } else {
+                tma_load_2d(&tm.w, &full_bar[stage], sb, kidx * kBlockK, n_tile * BLOCK_N);
+              }
               if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
           }
@@ -140,7 +152,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_N);
+    constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_N) | (kBmn ? kIdescBMn : 0u);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -177,7 +189,8 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t adesc = umma_desc_sw128(sa);
-          const uint64_t bdesc = umma_desc_sw128(sa + Cfg::kABytes);
+          const uint64_t bdesc = kBmn ? umma_desc_sw128_mn(sa + Cfg::kABytes, 8192u) : umma_desc_sw128(sa + Cfg::kABytes);
+          constexpr uint32_t kBStep = kBmn ? 128u : 2u;  // 16 K-rows of an MN-major operand = 2048 B; 16 K-elements of a K-major row = 32 B
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
 #pragma unroll
@@ -186,7 +199,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
               if (!((sub_live >> sub) & 1u)) continue;
               // +2 in the (addr >> 4) field = 32 B = 16 bf16 along K inside the 128B swizzle row;
               // sub-tile s starts 128 rows * 128 B = 16 KB further (1024-B aligned, swizzle phase preserved)
-              umma_bf16_ss(d_tmem + sub * BLOCK_N, adesc + 2 * k + sub * (kTileM * 128 / 16), bdesc + 2 * k, idesc,
+              umma_bf16_ss(d_tmem + sub * BLOCK_N, adesc + 2 * k + sub * (kTileM * 128 / 16), bdesc + kBStep * k, idesc,
                            (started >> sub) & 1u);
               started |= 1u << sub;
             }
@@ -272,7 +285,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
         if constexpr (kLstm) epi_lstm<kTrain>(g, e, b, y, x, valid, n0, acc_v, cp, ctile, BLOCK_M, s_bias + c * CH);
         if constexpr (EPI == EPI_GAUSS) epi_gauss(g, e, b, y, x, valid, n0, acc_v);
         if constexpr (EPI == EPI_FRAME) epi_frame(g, e, b, y, x, valid, yb * (BLOCK_M / 32) + we, acc_v);
-        if constexpr (EPI == EPI_F32) epi_f32<CH>(g, e, b, y, x, valid, n0, acc_v);
+        if constexpr (EPI == EPI_F32 || EPI == EPI_F32_BT) epi_f32<CH>(g, e, b, y, x, valid, n0, acc_v);
         if constexpr (EPI == EPI_GATES) epi_gates(g, e, b, y, x, valid, n0, acc_v, gs, gq);
       };
       if (!mine) {
@@ -413,7 +426,12 @@ static cudaError_t launch_simt_t(const ConvOp& op, cudaStream_t stream) {
   X(256, 256, EPI_LSTM_TRAIN) \
   X(128, 128, EPI_LSTM_TRAIN) \
   X(128, 128, EPI_GAUSS)    \
-  X(128, 16, EPI_FRAME)
+  X(128, 16, EPI_FRAME)     \
+  X(256, 256, EPI_F32_BT)   \
+  X(256, 128, EPI_F32_BT)   \
+  X(256, 64, EPI_F32_BT)    \
+  X(128, 128, EPI_F32_BT)   \
+  X(128, 64, EPI_F32_BT)
 
 cudaError_t launch_conv_tc(const ConvOp& op, int num_sms, cudaStream_t stream) {
 #define X(M, N, E) if (op.block_m == M && op.block_n == N && op.epi == E) return launch_tc_t<M, N, E>(op, num_sms, stream);
@@ -422,6 +440,7 @@ cudaError_t launch_conv_tc(const ConvOp& op, int num_sms, cudaStream_t stream) {
   return cudaErrorInvalidValue;
 }
 cudaError_t launch_conv_simt(const ConvOp& op, cudaStream_t stream) {
+  if (op.epi == EPI_F32_BT) return cudaErrorNotSupported;  // (the training step keeps the transposed copy with conv_impl = 1)
 #define X(M, N, E) if (op.block_m == M && op.block_n == N && op.epi == E) return launch_simt_t<M, N, E>(op, stream);
   RAC_CONV_CASES(X)
 #undef X

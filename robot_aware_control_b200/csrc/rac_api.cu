@@ -234,6 +234,20 @@ int encode_w_map(rac_handle* h, CUtensorMap* m, const bf16* ptr, int K, int N, i
   return RAC_OK;
 }
 
+// Forward-packed weights Wp[n][tap][c] as the MN-major B operand of a dgrad GEMM (EPI_F32_BT): 3-D view (c, tap, n),
+// box {64 c, 1 tap, 64 n}; rows n >= n_packed (the K padding of the output-gradient operand) are out of bounds = zero
+int encode_w_map_bt(rac_handle* h, CUtensorMap* m, const bf16* ptr, int ctot, int taps, int n_packed) {
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(ctot), static_cast<cuuint64_t>(taps), static_cast<cuuint64_t>(n_packed)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ctot) * 2, static_cast<cuuint64_t>(taps) * ctot * 2};
+  cuuint32_t box[3] = {64, 1, 64};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(ptr), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, RAC_ERR_CUDA, "cuTensorMapEncodeTiled(forward weights as dgrad operand) failed: %d", (int)r);
+  return RAC_OK;
+}
+
 // Halo kernel activation map. Preferred: dims (C, H, W, B) -- H and W swapped through the strides -- so that ONE box
 // {64, 8, 34, 1} lands column-major (8 rows of a column = one swizzle atom). If the driver rejects the non-monotonic
 // strides: dims (C, W, H, B) with a one-column box {64, 1, 8, 1}, loaded 34 times per tile.

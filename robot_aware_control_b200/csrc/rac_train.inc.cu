@@ -32,10 +32,9 @@ struct TLayer {
   bf16* wd = nullptr;    // [ctot][taps*kpad]
   float* dwp = nullptr;  // [kpad][taps*ctot]
   float* bias = nullptr; // [n_packed]
-  // wgrad operands of ALL time steps, transposed: xcolT [taps*ctot][steps*mpad], dyT [kpad][steps*mpad]. The weight
-  // gradient is a sum over time, so the contraction simply runs over steps * rows: ONE GEMM per layer with K = steps *
-  // mpad after the last BPTT step instead of one K = mpad GEMM (+ a read-modify-write of dW) per step.
-  bf16* xcolT = nullptr;
+  // output gradients of ALL time steps [steps][M][kpad] (bf16): written by the layer's backward producers, read by the
+  // dgrad GEMM of each step and, all steps at once, by the implicit-GEMM weight gradient (the sum over time is part of
+  // its contraction)
   bf16* dyT = nullptr;
   int taps = 0, ctot = 0, n_packed = 0, kpad = 0;
 };
@@ -90,6 +89,7 @@ struct TrainState {
   float* gn_part = nullptr;   // [B][14 g] per-sample partials of the GroupNorm affine gradients
   float *params = nullptr, *buffers = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr;
   int per_step = 0;                   // RAC_TRAIN_PER_STEP=1: never batch the time steps (A/B measurements, cross-checks)
+  int dgrad_bt = 1;                   // dgrad reads the forward weight packing as an MN-major operand (0: transposed copy Wd)
   float* wg_part = nullptr;           // split-K partials of the layer being processed
   size_t wg_part_elems = 0;
   float* wfirst = nullptr;  // [9*cin][64]
@@ -128,7 +128,7 @@ struct GemmGeom {
 
 // Build + launch one conv_tc GEMM with an explicit operand description (tensor maps encoded on the fly).
 int t_gemm(rac_handle* h, const char* name, const GemmGeom& gg, const std::vector<Src>& srcs, const bf16* w, int ktotal,
-           int n_rows_w, int block_n, int epi, const EpiParams& ep, cudaStream_t st) {
+           int n_rows_w, int block_n, int epi, const EpiParams& ep, cudaStream_t st, int bt_rows = 0) {
   ConvOp op;
   memset(&op, 0, sizeof(op));
   op.name = name;
@@ -175,7 +175,8 @@ int t_gemm(rac_handle* h, const char* name, const GemmGeom& gg, const std::vecto
   g.w_shift = ilog2(gg.W);
   g.bhw_shift = ilog2(g.BH * gg.W);
   op.raw.w = w;
-  CKR(encode_w_map(h, &op.tm.w, w, ktotal, n_rows_w, block_n));
+  if (epi == EPI_F32_BT) CKR(encode_w_map_bt(h, &op.tm.w, w, n_rows_w, gg.ks * gg.ks, bt_rows));
+  else CKR(encode_w_map(h, &op.tm.w, w, ktotal, n_rows_w, block_n));
   op.e = ep;
   return launch(h, op, st);
 }
@@ -319,8 +320,14 @@ int conv_backward(rac_handle* h, TrainState* T, int layer, int H, int W, const s
     e.cout = L.ctot;
     e.nseg = nseg;
     for (int i = 0; i < nseg; ++i) e.seg[i] = segs[i];
-    CKR(t_gemm(h, "train.dgrad", {nb, H, W, ks, false}, {{slot, L.kpad}}, L.wd, L.taps * L.kpad, L.ctot, pick_bn(L.ctot),
-               EPI_F32, e, st));
+    // B operand = the forward packing Wp read as an MN-major operand (conv_tc.cu, EPI_F32_BT); the transposed + flipped
+    // copy Wd only exists for the SIMT cross-check configuration
+    if (T->dgrad_bt)
+      CKR(t_gemm(h, "train.dgrad", {nb, H, W, ks, false}, {{slot, L.kpad}}, L.wp, L.taps * L.kpad, L.ctot, pick_bn(L.ctot),
+                 EPI_F32_BT, e, st, L.n_packed));
+    else
+      CKR(t_gemm(h, "train.dgrad", {nb, H, W, ks, false}, {{slot, L.kpad}}, L.wd, L.taps * L.kpad, L.ctot, pick_bn(L.ctot),
+                 EPI_F32, e, st));
   }
   return RAC_OK;
 }
@@ -791,6 +798,8 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
   T->params = params; T->buffers = buffers; T->grads = grads; T->m = adam_m; T->v = adam_v;
   if (const char* dk = getenv("RAC_TRAIN_DEBUG_KEEP")) T->dbg_keep = atoi(dk);
   if (const char* ps = getenv("RAC_TRAIN_PER_STEP")) T->per_step = atoi(ps);
+  if (h->cfg.conv_impl == 1) T->dgrad_bt = 0;
+  if (const char* wd = getenv("RAC_DGRAD_WD")) T->dgrad_bt = atoi(wd) ? 0 : 1;
   {
     static bool attr = false;
     if (!attr) { CK(wgrad_tc_set_attributes()); attr = true; }
@@ -826,7 +835,7 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
       // dyT: the output gradients of all time steps [steps][M][kpad] -- the dgrad operand of each step and, all steps
       // together, the A operand of the weight-gradient GEMM
       L.dyT = bp.take<bf16>(static_cast<size_t>(L.kpad) * S * rows_of(i));
-      L.wd = bp.take<bf16>(static_cast<size_t>(L.ctot) * L.taps * L.kpad);
+      if (!T->dgrad_bt) L.wd = bp.take<bf16>(static_cast<size_t>(L.ctot) * L.taps * L.kpad);
       L.dwp = bp.take<float>(static_cast<size_t>(L.kpad) * L.taps * L.ctot);
       L.bias = bp.take<float>(L.n_packed);
     }
@@ -955,7 +964,7 @@ int rac_train_forward_backward(rac_handle* h, const rac_train_batch* bt, void* s
   for (int i = 1; i < T->nlayers; ++i) {
     TLayer& L = T->L[i];
     CK(launch_pack_weights(T->params, L.d.row_off, L.d.col_off, L.n_packed, L.taps, L.ctot, L.d.flip, L.wp, st));
-    CK(launch_transpose_flip(L.wp, L.n_packed, L.taps, L.ctot, L.kpad, L.wd, st));
+    if (!T->dgrad_bt) CK(launch_transpose_flip(L.wp, L.n_packed, L.taps, L.ctot, L.kpad, L.wd, st));
     if (L.d.bias_off) CK(launch_gather_f32(T->params, L.d.bias_off, L.n_packed, L.bias, st));
   }
   CK(launch_pack_first(T->params + T->L[RAC_L_ENC_C1_0].d.w_off, h->enc_cin, T->wfirst, st));
@@ -1045,13 +1054,13 @@ int rac_train_debug_buffer(rac_handle* h, const char* name, int step, void** ptr
   TrainState* T = static_cast<TrainState*>(h->train);
   if (step < 0 || step >= static_cast<int>(T->tape.size())) return fail(h, RAC_ERR_INVALID, "bad step %d", step);
   Tape& tp = T->tape[step];
-  // gradient accumulators: the slot of step 0 (the last step the backward pass processes)
+  // gradient accumulators: the slot of time step `step`
   struct { const char* n; void* p; } tab[] = {
-      {"G_d5", T->G_d5.p}, {"G_cat5", T->G_cat5.p}, {"G_d4a", T->G_d4a.p}, {"G_cat4", T->G_cat4.p}, {"G_d3b", T->G_d3b.p},
-      {"G_d3a", T->G_d3a.p}, {"G_cat3", T->G_cat3.p}, {"G_d2b", T->G_d2b.p}, {"G_d2a", T->G_d2a.p}, {"G_fin", T->G_fin.p},
-      {"G_pin", T->G_pin.p}, {"G_postin", T->G_postin.p}, {"G_z", T->G_z.p}, {"G_h4", T->G_h4.p}, {"G_a4b", T->G_a4b.p},
-      {"G_a4a", T->G_a4a.p}, {"G_p3", T->G_p3.p}, {"G_a3b", T->G_a3b.p}, {"G_a3a", T->G_a3a.p}, {"G_p2", T->G_p2.p},
-      {"G_a2", T->G_a2.p}, {"G_p1", T->G_p1.p}, {"G_a1", T->G_a1.p},
+      {"G_d5", T->G_d5.at(step)}, {"G_cat5", T->G_cat5.at(step)}, {"G_d4a", T->G_d4a.at(step)}, {"G_cat4", T->G_cat4.at(step)}, {"G_d3b", T->G_d3b.at(step)},
+      {"G_d3a", T->G_d3a.at(step)}, {"G_cat3", T->G_cat3.at(step)}, {"G_d2b", T->G_d2b.at(step)}, {"G_d2a", T->G_d2a.at(step)}, {"G_fin", T->G_fin.at(step)},
+      {"G_pin", T->G_pin.at(step)}, {"G_postin", T->G_postin.at(step)}, {"G_z", T->G_z.at(step)}, {"G_h4", T->G_h4.at(step)}, {"G_a4b", T->G_a4b.at(step)},
+      {"G_a4a", T->G_a4a.at(step)}, {"G_p3", T->G_p3.at(step)}, {"G_a3b", T->G_a3b.at(step)}, {"G_a3a", T->G_a3a.at(step)}, {"G_p2", T->G_p2.at(step)},
+      {"G_a2", T->G_a2.at(step)}, {"G_p1", T->G_p1.at(step)}, {"G_a1", T->G_a1.at(step)},
       {"img4", tp.img4}, {"a1", tp.a1}, {"cat5", tp.cat5}, {"p1", tp.p1}, {"a2", tp.a2}, {"cat4", tp.cat4},
       {"p2", tp.p2}, {"a3a", tp.a3a}, {"a3b", tp.a3b}, {"cat3", tp.cat3}, {"p3", tp.p3}, {"a4a", tp.a4a},
       {"a4b", tp.a4b}, {"h4", tp.h4}, {"d2a", tp.d2a}, {"d2b", tp.d2b}, {"d3a", tp.d3a}, {"d3b", tp.d3b},

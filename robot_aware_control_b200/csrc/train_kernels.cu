@@ -502,36 +502,6 @@ cudaError_t launch_bias_grad(const __nv_bfloat16* dy, int M, int ncols, int nval
   return cudaGetLastError();
 }
 
-// bias gradient from the all-time-steps transposed operand dyT [rows, ld] (row n = packed output column, the ld columns
-// = every output position of every time step, zero-padded): one warp per row, fixed summation order
-__global__ void __launch_bounds__(256)
-bias_grad_rows_kernel(const __nv_bfloat16* __restrict__ dyT, int ld, int nvalid, const long long* __restrict__ bias_off,
-                      float* __restrict__ grads) {
-  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (n >= nvalid) return;
-  const uint4* row = reinterpret_cast<const uint4*>(dyT + static_cast<size_t>(n) * ld);
-  float acc = 0.f;
-  for (int i = lane; i < ld / 8; i += 32) {
-    const uint4 v = row[i];
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __bfloat1622float2(h[j]);
-      acc += f.x + f.y;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0 && bias_off[n] >= 0) grads[bias_off[n]] += acc;
-}
-cudaError_t launch_bias_grad_rows(const __nv_bfloat16* dyT, int ld, int nvalid, const long long* bias_off, float* grads,
-                                  cudaStream_t s) {
-  if (ld % 8 != 0) return cudaErrorInvalidValue;
-  bias_grad_rows_kernel<<<(nvalid + 7) / 8, 256, 0, s>>>(dyT, ld, nvalid, bias_off, grads);
-  return cudaGetLastError();
-}
-
 // ------------------------------------------------------------------------------------------------ z / KL
 __global__ void __launch_bounds__(256)
 gauss_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ mu, const float* __restrict__ lv,
@@ -749,67 +719,6 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
 }
 cudaError_t launch_cast_bf16(const float* src, long long n, __nv_bfloat16* dst, cudaStream_t s) {
   cast_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(src, n, dst);
-  return cudaGetLastError();
-}
-
-// dst[c][m] = src[m][c], zero padded to [rows_pad][mpad]
-__global__ void __launch_bounds__(1024)
-transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int M, int C, int mpad, int rows_pad, int ld,
-                      __nv_bfloat16* __restrict__ dst) {
-  __shared__ __nv_bfloat16 tile[32][33];
-  const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const int m = m0 + threadIdx.y, c = c0 + threadIdx.x;
-  tile[threadIdx.y][threadIdx.x] = (m < M && c < C) ? src[static_cast<size_t>(m) * C + c] : __float2bfloat16(0.f);
-  __syncthreads();
-  const int co = c0 + threadIdx.y, mo = m0 + threadIdx.x;
-  if (co < rows_pad && mo < mpad) dst[static_cast<size_t>(co) * ld + mo] = tile[threadIdx.x][threadIdx.y];
-}
-cudaError_t launch_transpose_bf16(const __nv_bfloat16* src, int M, int C, int mpad, int rows_pad,
-                                  __nv_bfloat16* dst, cudaStream_t s, int ld) {
-  if (ld <= 0) ld = mpad;
-  transpose_bf16_kernel<<<dim3((mpad + 31) / 32, (rows_pad + 31) / 32), dim3(32, 32), 0, s>>>(src, M, C, mpad, rows_pad,
-                                                                                              ld, dst);
-  return cudaGetLastError();
-}
-
-// 64 (rows m) x 64 (channels) tiles, two bf16 per thread: 128-byte segments on both the NHWC read and the
-// transposed write side
-__global__ void __launch_bounds__(1024)
-im2col_t_kernel(const __nv_bfloat16* __restrict__ src, int B, int H, int W, int C, int ks, int ctot, int coff,
-                int ld, __nv_bfloat16* __restrict__ dst) {
-  __shared__ uint32_t tile[64][33];
-  const int M = B * H * W;
-  const int m0 = blockIdx.x * 64, c0 = blockIdx.y * 64, tap = blockIdx.z;
-  const int dy = tap / ks - ks / 2, dx = tap % ks - ks / 2;
-  const int tx = threadIdx.x, ty = threadIdx.y;
-#pragma unroll
-  for (int rr = 0; rr < 2; ++rr) {
-    const int m = m0 + ty + 32 * rr;
-    uint32_t v = 0u;
-    if (m < M) {
-      const int x = m % W, y = (m / W) % H, b = m / (W * H);
-      const int yy = y + dy, xx = x + dx;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
-        v = *reinterpret_cast<const uint32_t*>(src + (static_cast<size_t>(b * H + yy) * W + xx) * C + c0 + 2 * tx);
-    }
-    tile[ty + 32 * rr][tx] = v;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int rr = 0; rr < 2; ++rr) {
-    const int cl = ty + 32 * rr;  // channel inside the tile
-    const uint32_t a = tile[2 * tx][cl >> 1], b2 = tile[2 * tx + 1][cl >> 1];
-    const uint32_t lo = (cl & 1) ? (a >> 16) : (a & 0xffffu);
-    const uint32_t hi = (cl & 1) ? (b2 >> 16) : (b2 & 0xffffu);
-    *reinterpret_cast<uint32_t*>(dst + (static_cast<size_t>(tap) * ctot + coff + c0 + cl) * ld + m0 + 2 * tx) =
-        lo | (hi << 16);
-  }
-}
-cudaError_t launch_im2col_t(const __nv_bfloat16* src, int B, int H, int W, int C, int ks, int ctot, int coff, int mpad,
-                            __nv_bfloat16* dst, cudaStream_t s, int ld) {
-  if (ld <= 0) ld = mpad;
-  if (C % 64 != 0 || mpad % 64 != 0 || ld % 2 != 0) return cudaErrorInvalidValue;
-  im2col_t_kernel<<<dim3(mpad / 64, C / 64, ks * ks), dim3(32, 32), 0, s>>>(src, B, H, W, C, ks, ctot, coff, ld, dst);
   return cudaGetLastError();
 }
 

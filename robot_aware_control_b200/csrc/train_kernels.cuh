@@ -74,9 +74,6 @@ cudaError_t launch_gn_cell_bwd(const GnCellArgs& a, float* grads, cudaStream_t s
 cudaError_t launch_lstm_bwd(const float* dh, float* dc, const float* gates, const float* c_prev_or_null,
                             const float* c_new, int M, int hid, __nv_bfloat16* dgates, cudaStream_t s);
 // grads[bias_off[n]] += sum_m dy[m][n] for n < nvalid   (dy bf16 [M, ncols])
-// the same sum over ALL time steps at once, from the transposed wgrad operand dyT [rows, ld]
-cudaError_t launch_bias_grad_rows(const __nv_bfloat16* dyT, int ld, int nvalid, const long long* bias_off, float* grads,
-                                  cudaStream_t s);
 cudaError_t launch_bias_grad(const __nv_bfloat16* dy, int M, int ncols, int nvalid, const long long* bias_off,
                              float* grads, cudaStream_t s);
 
@@ -113,14 +110,8 @@ cudaError_t launch_first_dgrad(const float* draw, const float* wf, int cin, cons
 cudaError_t launch_pool_bwd(const __nv_bfloat16* in, int in_cstride, int in_coff, const float* dout, int B, int H,
                             int W, int C, float* din, int din_cstride, int din_coff, int accumulate, cudaStream_t s);
 
-// ---- layout helpers for wgrad: transposed operands (contraction dimension = rows m, padded to mpad); `ld` = leading
-// dimension of dst when the mpad columns are one block of a wider (all-time-steps) buffer (0: ld = mpad)
+// ---- layout helper
 cudaError_t launch_cast_bf16(const float* src, long long n, __nv_bfloat16* dst, cudaStream_t s);
-cudaError_t launch_transpose_bf16(const __nv_bfloat16* src /* [M, C] */, int M, int C, int mpad, int rows_pad,
-                                  __nv_bfloat16* dst /* [rows_pad, ld] */, cudaStream_t s, int ld = 0);
-// dst[(tap * ctot + coff + c) * mpad + m] = src[b, y + dy, x + dx, c]  (0 outside the image)
-cudaError_t launch_im2col_t(const __nv_bfloat16* src, int B, int H, int W, int C, int ks, int ctot, int coff, int mpad,
-                            __nv_bfloat16* dst, cudaStream_t s, int ld = 0);
 
 // ---- optimiser (torch.optim.Adam, no weight decay) and noise
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,

@@ -30,30 +30,8 @@ constexpr int kStageBytes = 6 * kBoxBytesMax;      // A: 2 boxes (128 output cha
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024;
 constexpr int kThreads = 256;
 
-__device__ __forceinline__ void tma_load_5d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
-      "[%2];" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-
-// MN-major SWIZZLE_128B operand: 64 MN-elements (128 B) per K-row, 8 K-rows per 1024-byte atom
-__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);           // start address
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;     // leading byte offset: next 64-element MN group
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;                     // stride byte offset: next group of 8 K-rows
-  d |= static_cast<uint64_t>(1) << 46;                             // descriptor version (Blackwell)
-  d |= static_cast<uint64_t>(2) << 61;                             // SWIZZLE_128B
-  return d;
-}
-// bf16 x bf16 -> fp32, A and B both MN-major (bits 15 / 16), M = 128
-__device__ __forceinline__ uint32_t umma_idesc_bf16_mn(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
-         (static_cast<uint32_t>(128 >> 4) << 24);
-}
+// bf16 x bf16 -> fp32, A and B both MN-major, M = 128
+__device__ __forceinline__ uint32_t umma_idesc_bf16_mn(int n) { return umma_idesc_bf16(n) | kIdescAMn | kIdescBMn; }
 
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {

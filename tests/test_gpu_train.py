@@ -250,8 +250,8 @@ def test_fixed_skip_plumbing():
     G = lambda name, shape: _tape(trainer, name, shape, bf16=False)
     gskip = G("G_skip5", (B, 48, 64, 64))
     assert torch.isfinite(gskip).all() and float(gskip.abs().sum()) > 0
-    gcat5 = G("G_cat5", (B, 48, 64, 128))
-    # step 1 (t > 0) wrote the skip half of G_cat5 from its pooling path only, step 0 never touches it in this mode:
+    gcat5 = _tape(trainer, "G_cat5", (B, 48, 64, 128), step=1, bf16=False)
+    # step 1 (t > 0) wrote the skip half of its G_cat5 slot from its pooling path only:
     # a pooled gradient has at most one non-zero per 2x2 window
     win = gcat5[..., 64:].view(B, 24, 2, 32, 2, 64).permute(0, 1, 3, 5, 2, 4).reshape(-1, 4)
     assert int(((win != 0).sum(1) > 1).sum()) == 0 and float(win.abs().sum()) > 0
