@@ -6,9 +6,11 @@
 The tensor-pipe metrics are not part of `--set full` on sm_100: capture with
     ncu --set full --metrics $(python profiles/summarize.py tensor-metrics) ...
 """
-TENSOR_METRICS = ("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed,"
-                  "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed,"
-                  "sm__inst_executed_pipe_tc.sum,sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32.sum")
+TENSOR_METRICS = ("sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed,"
+                  "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,"
+                  "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32.sum,"
+                  "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32.sum.pct_of_peak_sustained_elapsed,"
+                  "sm__inst_executed_pipe_tc.sum")
 import collections
 import csv
 import re
@@ -19,6 +21,8 @@ KEYS = [
     "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
     "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
     "sm__pipe_tensor_cycles_active_realtime.avg", "sm__inst_executed_pipe_tc.sum",
+    "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32.sum", "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32.sum.pct_of_peak_sustained_elapsed",
     "sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32.sum", "sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32.sum.per_second", "dram__bytes_read.sum", "dram__bytes_write.sum",
     "dram__bytes_read.sum.per_second", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",

@@ -227,7 +227,7 @@ WgradGeom wg_plan(const TLayer& L, int B, int H, int W, int S) {
   g.bgroups = B / g.NB;
   g.kb_total = S * g.bgroups * g.hgroups;
   g.kpad = L.kpad;
-  g.n_tiles = (L.kpad + 127) / 128;
+  g.n_tiles = (L.kpad + 255) / 256;
   g.taps = L.taps;
   g.ctot = L.ctot;
   return g;

@@ -415,22 +415,59 @@ bn_bwd_sums_kernel(BnBwdArgs a, int M, float* __restrict__ scratch, float* __res
   dbeta[c] += static_cast<float>(t1);
   dgamma[c] += static_cast<float>(t2);
 }
+// 8 channels per thread (C % 8 == 0): 128-bit loads of dy / raw, one 128-bit bf16 store
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(BnBwdArgs a, int M, const float* __restrict__ scratch, __nv_bfloat16* __restrict__ draw,
                     float* __restrict__ draw32) {
-  const size_t total = static_cast<size_t>(M) * a.C;
+  const int C8 = a.C >> 3;
+  const size_t total = static_cast<size_t>(M) * C8;
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int c = static_cast<int>(i % a.C);
-  const int m = static_cast<int>(i / a.C);
-  float dz, xh;
-  bn_bwd_point(a, m, c, dz, xh);
+  const int c0 = static_cast<int>(i % C8) * 8;
+  const int m = static_cast<int>(i / C8);
+  const int x = m % a.W, y = (m / a.W) % a.H;
+  const size_t b = static_cast<size_t>(m) / (a.W * a.H);
+  float g[8];
+  if (!a.upsample) {
+    const float4* p = reinterpret_cast<const float4*>(a.dy + static_cast<size_t>(m) * a.dy_cstride + a.dy_coff + c0);
+    const float4 u = p[0], v = p[1];
+    g[0] = u.x; g[1] = u.y; g[2] = u.z; g[3] = u.w; g[4] = v.x; g[5] = v.y; g[6] = v.z; g[7] = v.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = 0.f;
+    for (int dy = 0; dy < 2; ++dy)
+      for (int dx = 0; dx < 2; ++dx) {
+        const float4* p = reinterpret_cast<const float4*>(
+            a.dy + ((b * 2 * a.H + 2 * y + dy) * (2 * a.W) + 2 * x + dx) * a.dy_cstride + a.dy_coff + c0);
+        const float4 u = p[0], v = p[1];
+        g[0] += u.x; g[1] += u.y; g[2] += u.z; g[3] += u.w; g[4] += v.x; g[5] += v.y; g[6] += v.z; g[7] += v.w;
+      }
+  }
+  const float4* rp = reinterpret_cast<const float4*>(a.raw + static_cast<size_t>(m) * a.C + c0);
+  const float4 r0 = rp[0], r1 = rp[1];
+  const float raw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
   const int grp = m / a.rows_per_group;
   const float inv = 1.f / a.rows_per_group;
   const float* sc = scratch + grp * 2 * a.C;
-  const float dx = a.gamma[c] * a.rstd[grp * a.C + c] * (dz - sc[c] * inv - xh * sc[a.C + c] * inv);
-  if (draw) draw[i] = __float2bfloat16(dx);
-  if (draw32) draw32[i] = dx;
+  const float* mean = a.mean + grp * a.C;
+  const float* rstd = a.rstd + grp * a.C;
+  float dx[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    const float xh = (raw[j] - mean[c]) * rstd[c];
+    const float bn = xh * a.gamma[c] + a.beta[c];
+    const float dz = bn > 0.f ? g[j] : 0.2f * g[j];
+    dx[j] = a.gamma[c] * rstd[c] * (dz - sc[c] * inv - xh * sc[a.C + c] * inv);
+  }
+  if (draw)
+    *reinterpret_cast<uint4*>(draw + static_cast<size_t>(m) * a.C + c0) =
+        make_uint4(pack_bf16x2(dx[0], dx[1]), pack_bf16x2(dx[2], dx[3]), pack_bf16x2(dx[4], dx[5]), pack_bf16x2(dx[6], dx[7]));
+  if (draw32) {
+    float4* o = reinterpret_cast<float4*>(draw32 + static_cast<size_t>(m) * a.C + c0);
+    o[0] = make_float4(dx[0], dx[1], dx[2], dx[3]);
+    o[1] = make_float4(dx[4], dx[5], dx[6], dx[7]);
+  }
 }
 cudaError_t launch_bn_bwd(const float* dy, int dy_cstride, int dy_coff, int upsample, const float* raw,
                           const float* mean, const float* rstd, const float* gamma, const float* beta, int B, int H,
@@ -446,7 +483,8 @@ cudaError_t launch_bn_bwd(const float* dy, int dy_cstride, int dy_coff, int upsa
   bn_bwd_sums_kernel<<<dim3((C + 31) / 32, R, groups), dim3(32, 32), 0, s>>>(a, Mg, scratch, dgamma, dbeta);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const size_t total = static_cast<size_t>(M) * C;
+  if (C % 8 || dy_cstride % 4 || dy_coff % 4) return cudaErrorInvalidValue;
+  const size_t total = static_cast<size_t>(M) * (C / 8);
   bn_bwd_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(a, M, scratch, draw, draw_f32_or_null);
   return cudaGetLastError();
 }

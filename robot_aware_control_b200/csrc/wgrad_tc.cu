@@ -13,9 +13,12 @@
 // is the size of one tape step, and `h_{t-1}` of a ConvLSTM is the `h` tensor read at step coordinate t - 1 (t = 0 is out
 // of bounds = the zero initial state). Round 1 materialised im2col(X)^T and dY^T in HBM instead (26 % of the step).
 //
-// One CTA = one output tile [128 packed output channels] x [<= 256 input channels of one source] of one filter tap, for
-// one slice of the contraction (split-K partials are summed in a fixed order by wgrad_reduce_kernel: deterministic).
-//   warp 0: TMA producer, warp 1: MMA issuer (one thread), warp 2: TMEM allocator, warps 4-7: epilogue (TMEM -> fp32 global)
+// One CTA = one output tile [256 packed output channels = two M128 accumulators] x [<= 256 input channels of one source]
+// of one filter tap, for one slice of the contraction (split-K partials are summed in a fixed order by
+// wgrad_reduce_kernel: deterministic). The tile is as large as TMEM allows (2 x 256 columns): the ConvLSTM weight
+// gradients (K = 3840 rows only, 2048 x 1024 x 25 outputs) are bound by the L2 -> SM operand traffic, which a 256 x 256
+// tile cuts by a third against 128 x 256.
+//   warp 0: TMA producer, warp 1: MMA issuer (one thread), warp 2: TMEM allocator, warps 4-11: epilogue (TMEM -> fp32 global)
 #include "ptx.cuh"
 #include "wgrad_tc.cuh"
 
@@ -23,12 +26,12 @@ namespace rac {
 
 namespace {
 
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kMaxRows = 64;                       // positions per k-block (K of one pipeline stage)
 constexpr int kBoxBytesMax = kMaxRows * 128;       // one 64-channel box
-constexpr int kStageBytes = 6 * kBoxBytesMax;      // A: 2 boxes (128 output channels), B: up to 4 boxes (256 input channels)
+constexpr int kStageBytes = 8 * kBoxBytesMax;      // A: 4 boxes (256 output channels), B: up to 4 boxes (256 input channels)
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024;
-constexpr int kThreads = 256;
+constexpr int kThreads = 128 + 256;
 
 // bf16 x bf16 -> fp32, A and B both MN-major, M = 128
 __device__ __forceinline__ uint32_t umma_idesc_bf16_mn(int n) { return umma_idesc_bf16(n) | kIdescAMn | kIdescBMn; }
@@ -53,8 +56,9 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
   const int kh = tap / g.ks, kw = tap - kh * g.ks;
   const int src = g.ct_src[ct], c0 = g.ct_c0[ct], cw = g.ct_w[ct];
   const int nb_boxes = cw >> 6;
-  const int n0 = n_tile * 128;
-  const int a_boxes = (g.kpad - n0) >= 128 ? 2 : 1;  // output channels beyond kpad do not exist: rows never written
+  const int n0 = n_tile * 256;
+  const int a_boxes = min(4, (g.kpad - n0) >> 6);  // output channels beyond kpad do not exist: their rows are never written
+  const int subs = a_boxes > 2 ? 2 : 1;            // M128 accumulators in use
   const int kb_begin = blockIdx.y * g.kb_per_split;
   const int kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
   const uint32_t box_bytes = static_cast<uint32_t>(g.rows) * 128u;
@@ -72,7 +76,7 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -93,7 +97,7 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
       const int y0 = hg * g.BH, b0 = bg * g.NB;
       mbar_wait(&empty_bar[stage], phase ^ 1);
       uint8_t* sa = smem + stage * kStageBytes;
-      uint8_t* sb = sa + 2 * kBoxBytesMax;
+      uint8_t* sb = sa + 4 * kBoxBytesMax;
       mbar_arrive_expect_tx(&full_bar[stage], (a_boxes + nb_boxes) * box_bytes);
       for (int j = 0; j < a_boxes; ++j)
         tma_load_5d(&tm.dy, &full_bar[stage], sa + j * box_bytes, n0 + j * 64, 0, y0, b0, t);
@@ -112,12 +116,15 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
       const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-      const uint32_t sb = sa + 2 * kBoxBytesMax;
+      const uint32_t sb = sa + 4 * kBoxBytesMax;
       const uint64_t adesc = umma_desc_sw128_mn(sa, box_bytes);
       const uint64_t bdesc = umma_desc_sw128_mn(sb, box_bytes);
       for (int k = 0; k < g.rows / 16; ++k) {
-        // 16 positions = two 1024-byte atoms = 2048 B further along K: + 128 in the (addr >> 4) field
-        umma_bf16_ss(tmem_base, adesc + 128u * k, bdesc + 128u * k, idesc, accumulate);
+        // 16 positions = two 1024-byte atoms = 2048 B further along K: + 128 in the (addr >> 4) field; the second
+        // accumulator's 128 output channels are the A boxes 2 and 3 (2 * box_bytes further)
+        for (int sub = 0; sub < subs; ++sub)
+          umma_bf16_ss(tmem_base + sub * 256, adesc + 128u * k + sub * ((2u * box_bytes) >> 4), bdesc + 128u * k, idesc,
+                       accumulate);
         accumulate = 1;
       }
       umma_commit(&empty_bar[stage]);
@@ -126,8 +133,9 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM lane = output channel n, column = input channel c =====================
-    const int q = warp - 4;  // TMEM lanes 32 q .. 32 q + 31
-    const int n = n0 + q * 32 + lane;
+    const int q = (warp - 4) & 3;   // TMEM lanes 32 q .. 32 q + 31 (a warp may only touch the lane quarter warp % 4)
+    const int sub = (warp - 4) >> 2;  // accumulator: output channels n0 + 128 sub ..
+    const int n = n0 + sub * 128 + q * 32 + lane;
     const long long ld = static_cast<long long>(g.taps) * g.ctot;
     float* out = g.out + static_cast<long long>(blockIdx.y) * g.out_split_stride + static_cast<long long>(n) * ld +
                  static_cast<long long>(tap) * g.ctot + g.src_coff[src] + c0;
@@ -135,10 +143,10 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
       mbar_wait(tmem_full, 0);
       tc_fence_after();
     }
-    for (int cc = 0; cc < cw; cc += 32) {
+    for (int cc = 0; cc < cw && sub < subs; cc += 32) {
       float v[32];
       if (kb_end > kb_begin) {
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cc, v);
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + sub * 256 + cc, v);
         tmem_ld_wait();
       } else {
 #pragma unroll
@@ -155,7 +163,7 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 

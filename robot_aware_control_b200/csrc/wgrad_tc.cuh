@@ -20,7 +20,7 @@ struct WgradGeom {
   int hgroups, bgroups;        // H / BH, B / NB
   int kb_total;                // steps * bgroups * hgroups
   int splits, kb_per_split;    // split-K: grid.y slices of the contraction, summed afterwards in order
-  int n_tiles;                 // ceil(kpad / 128) output-channel tiles
+  int n_tiles;                 // ceil(kpad / 256) output-channel tiles
   int kpad;                    // packed output channels (rows of dWp)
   int taps, ctot;              // dWp row = taps * ctot floats
   int num_ctiles;              // input-channel tiles: (source, first channel, width in {64, 128, 192, 256})
