@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RAC_ABI_VERSION 5
+#define RAC_ABI_VERSION 6
 
 typedef enum {
   RAC_OK = 0,
@@ -359,6 +359,34 @@ int rac_train_adam_step(rac_handle* h, void* stream);
  * re-creates the training state (another batch shape) or resumes from a checkpoint (torch.optim.Adam state "step",
  * trainer.py:829-896) restores it here; the moments themselves live in the caller's adam_m / adam_v. */
 int rac_train_set_adam_step(rac_handle* h, int steps_taken);
+
+/* ---- Step API: the same training tape driven ONE time step per call, so that a train-mode SVGConvModel.forward
+ * (dynamics.py:544-644) can sit inside the caller's torch autograd graph and the reference's own _train_step body
+ * (trainer.py:326-465: compositing, _recon_loss, kl_criterion, loss.backward(), torch.optim.Adam) runs unchanged.
+ * rac_train_step_begin = model.init_hidden() in train mode (zero recurrent state, re-pack the bf16 operands from the
+ * current parameters, zero `grads`); _forward appends one step to the tape (posterior z, batch-statistics BatchNorm,
+ * running statistics updated as by two encoder passes); _backward must be called for the steps in reverse order
+ * (BPTT), with the gradients w.r.t. that step's outputs; after step 0 `grads` holds dL/d(parameters). */
+typedef struct {
+  const float* image;       /* (B, 3, H, W): the frame the model sees (robot pixels already zeroed by the caller) */
+  const float* mask;        /* (B, 1, H, W), or (B, 2, H, W) = cat([m_j, m_i]) with model_use_future_mask; NULL if unused */
+  const float* robot;       /* (B, robot_dim) r_j or NULL */
+  const float* next_robot;  /* (B, robot_dim) r_i: the future-state channels and the posterior's input, or NULL */
+  const float* action;      /* (B, action_dim) */
+  const float* eps_prior;   /* (B, z_dim, H/8, W/8) or NULL -> Philox(seed, noise_step) */
+  const float* eps_post;
+  unsigned long long seed, noise_step;
+  int keep_skip;            /* cfg.fixed_skip: 0 at the first step, 1 afterwards (decode with the first step's skips) */
+  float *x_pred;            /* out (B, 4, H, W): sigmoid(decoder logits), channel 3 = compositing mask */
+  float *mu, *logvar, *mu_p, *logvar_p; /* out (B, z_dim, H/8, W/8) */
+} rac_train_step;
+int rac_train_step_begin(rac_handle* h, void* stream);
+int rac_train_step_forward(rac_handle* h, const rac_train_step* step, void* stream);
+/* step: the same input pointers as the forward call of time step t (outputs ignored). d_*: gradients w.r.t. the
+ * outputs (NULL = zero). d_image: out (B, 3, H, W) gradient w.r.t. `image`, or NULL when not needed. */
+int rac_train_step_backward(rac_handle* h, int t, const rac_train_step* step, const float* d_x_pred, const float* d_mu,
+                            const float* d_logvar, const float* d_mu_p, const float* d_logvar_p, float* d_image,
+                            void* stream);
 
 /* Live timing of one kernel family for the roofline line of bench.py: CUDA event pairs are recorded on the launch
  * stream around every convolution launch whose layer name contains `name_substr` (e.g. "lstm.0"), up to

@@ -26,6 +26,15 @@ class RacStep(C.Structure):
     ]
 
 
+class RacTrainStep(C.Structure):
+    _fields_ = [
+        ("image", C.c_void_p), ("mask", C.c_void_p), ("robot", C.c_void_p), ("next_robot", C.c_void_p),
+        ("action", C.c_void_p), ("eps_prior", C.c_void_p), ("eps_post", C.c_void_p), ("seed", C.c_ulonglong),
+        ("noise_step", C.c_ulonglong), ("keep_skip", C.c_int), ("x_pred", C.c_void_p), ("mu", C.c_void_p),
+        ("logvar", C.c_void_p), ("mu_p", C.c_void_p), ("logvar_p", C.c_void_p),
+    ]
+
+
 class RacRollout(C.Structure):
     _fields_ = [
         ("n", C.c_int), ("steps", C.c_int), ("cand_offset", C.c_int), ("actions", C.c_void_p),
@@ -110,6 +119,10 @@ EXPORTS = {
     "rac_train_adam_step": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rac_train_set_adam_step": (C.c_int, [C.c_void_p, C.c_int]),
     "rac_train_debug_buffer": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "rac_train_step_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rac_train_step_forward": (C.c_int, [C.c_void_p, C.POINTER(RacTrainStep), C.c_void_p]),
+    "rac_train_step_backward": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(RacTrainStep), C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rac_profile_begin": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "rac_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
 }

@@ -52,6 +52,7 @@ struct ConvGeom {
   // padding are not issued at all (the ConvLSTM gate convolutions run at the power cap: fewer MMAs = faster).
   int y_major;
   int nbw_shift;                                // log2(NB * W)
+  int ksplit;                                   // > 1: split-K work items (conv_tc_kernel, 128-row fp32 epilogues only)
 };
 
 // row r of an M-tile -> (candidate, y, x)
@@ -83,6 +84,10 @@ struct EpiParams {
   // EPI_F32 (training: raw pre-BatchNorm conv output, dgrad into gradient accumulators, wgrad into packed dW)
   F32Seg seg[3];
   int nseg;
+  // split-K (ConvGeom::ksplit > 1): raw accumulators go to split_part[split][pixel][num_n_tiles * BLOCK_N] instead, and
+  // launch_splitk_reduce applies bias / segments afterwards
+  float* split_part;
+  long long split_stride;
   // EPI_GATES (lstm_group_norm, reference lstm.py:163-171,181-183): acc + bias -> seg[0].dst (fp32 [rows, 4*hid], packed
   // (channel, gate) columns) and GroupNorm(16, 4*hid) partial sums of this tile: gn_part[b][gn_tensor][gate*4 + quarter]
   // [slot][{sum, sumsq}], slot = row tile * gn_ntq + column tile inside the quarter (6 slots reserved)
@@ -142,6 +147,8 @@ struct ConvOp {
 cudaError_t launch_conv_tc(const ConvOp& op, int num_sms, cudaStream_t stream);
 cudaError_t launch_conv_simt(const ConvOp& op, cudaStream_t stream);
 cudaError_t conv_tc_set_attributes();
+// sums the split-K slices in order and applies the fp32 epilogue (bias, destination segments, accumulate flags)
+cudaError_t launch_splitk_reduce(const EpiParams& e, int ksplit, long long rows, int ncols, cudaStream_t stream);
 // halo-tile kernel for the 64-wide full-resolution 3x3 layers (conv_halo.cu)
 bool conv_halo_supported(const ConvOp& op);
 cudaError_t launch_conv_halo(const ConvOp& op, const CUtensorMap& tm_a, int column_loads, int use_base_offset,

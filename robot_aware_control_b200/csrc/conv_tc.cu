@@ -54,6 +54,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
   // dgrad with the weights in their forward packing Wp[n][tap][c]: tm.w is a 3-D map (c, tap, n), a 64-channel box
   // {64 c, 1 tap, 64 n} is one MN-major swizzle group of the B operand (K = n is the slow dimension), taps are flipped
   constexpr bool kBmn = (EPI == EPI_F32_BT);
+  constexpr bool kSplitK = (EPI == EPI_F32 || EPI == EPI_F32_BT) && BLOCK_M == 128;
   static_assert(!kBmn || BLOCK_N % 64 == 0, "MN-major weight boxes are 64 channels wide");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -67,6 +68,11 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = g.num_m_tiles * g.num_n_tiles;
+  int kb_per_tap = 0, live_kb_per_tap = 0;
+  for (int s = 0; s < g.nsrc; ++s) {
+    kb_per_tap += g.src_kb[s];
+    if (!g.src_dead[s]) live_kb_per_tap += g.src_kb[s];
+  }
   // Tail splitting against wave quantisation: the persistent grid processes floor(tiles / grid) full rounds; if the
   // remaining `rem` tiles would occupy at most half of the CTAs for one more full tile time (e.g. 3000 LSTM tiles =
   // 20 x 148 + 40), each of them becomes two work items, one per 128-row MMA sub-tile (same operand loads, half the
@@ -74,17 +80,27 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
   const int full_items = (num_tiles / static_cast<int>(gridDim.x)) * static_cast<int>(gridDim.x);
   const int rem = num_tiles - full_items;
   const bool split_tail = Cfg::kSub == 2 && !g.no_split_tail && rem > 0 && 2 * rem <= static_cast<int>(gridDim.x);
-  const int num_items = split_tail ? full_items + 2 * rem : num_tiles;
-  auto item_tile = [&](int item, int& half) {  // half: -1 = both sub-tiles
+  // Split-K (g.ksplit > 1, fp32 epilogues of the training step only): the recurrent GEMMs of a batch-16 training step have
+  // 768 rows = 48 tiles of 128 x 128 for 148 SMs but 288-800 k-blocks; every tile becomes ksplit work items over
+  // contiguous k-block ranges, each writes its raw accumulator to its own slice of e.split_part, and
+  // splitk_reduce_kernel sums the slices in a fixed order (deterministic) and applies the real epilogue.
+  const int ksplit = (kSplitK && g.ksplit > 1) ? g.ksplit : 1;
+  const int num_items = ksplit > 1 ? num_tiles * ksplit : (split_tail ? full_items + 2 * rem : num_tiles);
+  auto item_tile = [&](int item, int& half, int& split) {  // half: -1 = both sub-tiles
+    split = 0;
+    if (ksplit > 1) { half = -1; split = item / num_tiles; return item - split * num_tiles; }
     if (item < full_items || !split_tail) { half = -1; return item; }
     half = (item - full_items) & 1;
     return full_items + ((item - full_items) >> 1);
   };
-  int kb_per_tap = 0, live_kb_per_tap = 0;
-  for (int s = 0; s < g.nsrc; ++s) {
-    kb_per_tap += g.src_kb[s];
-    if (!g.src_dead[s]) live_kb_per_tap += g.src_kb[s];
-  }
+  // live k-blocks of a tile whose first map row is y0, and the range [lo, hi) of them that split `split` handles
+  auto kb_range = [&](int y0, int split, int& lo, int& hi) {
+    int live = 0;
+    for (int kh = 0; kh < g.ks; ++kh) live += tap_row_live(g, y0, kh) ? 1 : 0;
+    const int num_kb = live * g.ks * live_kb_per_tap;
+    lo = static_cast<int>(static_cast<long long>(split) * num_kb / ksplit);
+    hi = static_cast<int>(static_cast<long long>(split + 1) * num_kb / ksplit);
+  };
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < g.nsrc; ++s) tma_prefetch_desc(&tm.a[s]);
@@ -115,20 +131,23 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
     int stage = 0;
     uint32_t phase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      int half;
-      const int tile = item_tile(item, half);
+      int half, split;
+      const int tile = item_tile(item, half, split);
       const int n_tile = tile / g.num_m_tiles;
       const int m_tile = tile - n_tile * g.num_m_tiles;
       const int grp = m_tile / g.tiles_per_img;
       const int b0 = grp * g.NB;
       const int y0 = (m_tile - grp * g.tiles_per_img) * g.BH;
+      int lo = 0, hi = 0x7fffffff, kbi = 0;
+      if (ksplit > 1) kb_range(y0, split, lo, hi);
       for (int kh = 0; kh < g.ks; ++kh) {
         if (!tap_row_live(g, y0, kh)) continue;
         for (int kw = 0; kw < g.ks; ++kw) {
           int kidx = (kh * g.ks + kw) * kb_per_tap;
           for (int s = 0; s < g.nsrc; ++s) {
             if (g.src_dead[s]) { kidx += g.src_kb[s]; continue; }
-            for (int kb = 0; kb < g.src_kb[s]; ++kb, ++kidx) {
+            for (int kb = 0; kb < g.src_kb[s]; ++kb, ++kidx, ++kbi) {
+              if (kbi < lo || kbi >= hi) continue;
               mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* sa = smem + stage * Cfg::kStageBytes;
               uint8_t* sb = sa + Cfg::kABytes;
@@ -158,14 +177,13 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      int half;
-      const int tile = item_tile(item, half);
+      int half, split;
+      const int tile = item_tile(item, half, split);
       const int n_tile = tile / g.num_m_tiles;
       const int m_tile = tile - n_tile * g.num_m_tiles;
       const int y0 = (m_tile % g.tiles_per_img) * g.BH;
-      int live = 0;
-      for (int kh = 0; kh < g.ks; ++kh) live += tap_row_live(g, y0, kh) ? 1 : 0;
-      const int num_kb = live * g.ks * live_kb_per_tap;
+      int lo, hi;
+      kb_range(y0, split, lo, hi);  // (ksplit == 1: the whole range)
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
@@ -185,6 +203,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
           }
         }
         for (int rest = g.ks * live_kb_per_tap; rest > 0; --rest, ++kb) {
+          if (kb < lo || kb >= hi) continue;
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -205,7 +224,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
             }
           }
           umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
-          if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+          if (kb == hi - 1) umma_commit(&tmem_full[acc]);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -223,8 +242,8 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
     float* s_bias = reinterpret_cast<float*>(bar_base + 1024);
     int bias_tile = -1;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      int half;
-      const int tile = item_tile(item, half);
+      int half, split;
+      const int tile = item_tile(item, half, split);
       const bool mine = half < 0 || sub == half;  // split tail item: the other sub-tile's rows belong to another CTA
       const int n_tile = tile / g.num_m_tiles;
       const int m_tile = tile - n_tile * g.num_m_tiles;
@@ -285,7 +304,10 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
         if constexpr (kLstm) epi_lstm<kTrain>(g, e, b, y, x, valid, n0, acc_v, cp, ctile, BLOCK_M, s_bias + c * CH);
         if constexpr (EPI == EPI_GAUSS) epi_gauss(g, e, b, y, x, valid, n0, acc_v);
         if constexpr (EPI == EPI_FRAME) epi_frame(g, e, b, y, x, valid, yb * (BLOCK_M / 32) + we, acc_v);
-        if constexpr (EPI == EPI_F32 || EPI == EPI_F32_BT) epi_f32<CH>(g, e, b, y, x, valid, n0, acc_v);
+        if constexpr (EPI == EPI_F32 || EPI == EPI_F32_BT) {
+          if (kSplitK && ksplit > 1) epi_split<CH>(g, e, b, y, x, valid, n0, g.num_n_tiles * BLOCK_N, split, acc_v);
+          else epi_f32<CH>(g, e, b, y, x, valid, n0, acc_v);
+        }
         if constexpr (EPI == EPI_GATES) epi_gates(g, e, b, y, x, valid, n0, acc_v, gs, gq);
       };
       if (!mine) {
@@ -393,7 +415,7 @@ conv_simt_kernel(const ConvRaw raw, const ConvGeom g, const EpiParams e) {
 template <int BLOCK_M, int BLOCK_N, int EPI>
 static cudaError_t launch_tc_t(const ConvOp& op, int num_sms, cudaStream_t stream) {
   using Cfg = TcCfg<BLOCK_M, BLOCK_N>;
-  const int num_tiles = op.g.num_m_tiles * op.g.num_n_tiles;
+  const int num_tiles = op.g.num_m_tiles * op.g.num_n_tiles * (op.g.ksplit > 1 ? op.g.ksplit : 1);
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
   conv_tc_kernel<BLOCK_M, BLOCK_N, EPI><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(op.tm, op.g, op.e);
   return cudaGetLastError();
@@ -446,6 +468,45 @@ cudaError_t launch_conv_simt(const ConvOp& op, cudaStream_t stream) {
 #undef X
   return cudaErrorInvalidValue;
 }
+// ---------------------------------------------------------------------------------------------------------------
+// Split-K reduction: out = sum over the ksplit slices (fixed order: bit-reproducible) + bias, routed to the fp32
+// destination segments exactly as epi_f32 would have done. One thread per 4 columns of one row.
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const EpiParams e, int ksplit, long long rows, int ncols) {
+  const int q4 = ncols >> 2;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * q4) return;
+  const long long row = i / q4;
+  const int n = static_cast<int>(i - row * q4) * 4;
+  if (n + 4 > e.cout) return;
+  int s = 0;
+  for (; s < e.nseg; ++s)
+    if (n >= e.seg[s].n_begin && n < e.seg[s].n_end) break;
+  if (s == e.nseg || e.seg[s].dst == nullptr) return;
+  const F32Seg& sg = e.seg[s];
+  const float* p = e.split_part + row * ncols + n;
+  float4 v = *reinterpret_cast<const float4*>(p);
+  for (int k = 1; k < ksplit; ++k) {
+    const float4 o = *reinterpret_cast<const float4*>(p + k * e.split_stride);
+    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+  }
+  if (e.bias) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+  }
+  float4* d = reinterpret_cast<float4*>(sg.dst + row * sg.cstride + sg.coff + (n - sg.n_begin));
+  if (sg.accumulate) {
+    const float4 o = *d;
+    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+  }
+  *d = v;
+}
+cudaError_t launch_splitk_reduce(const EpiParams& e, int ksplit, long long rows, int ncols, cudaStream_t stream) {
+  const long long total = rows * (ncols >> 2);
+  splitk_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(e, ksplit, rows, ncols);
+  return cudaGetLastError();
+}
+
 cudaError_t conv_tc_set_attributes() {
   cudaError_t err;
 #define X(M, N, E)                                                                                         \

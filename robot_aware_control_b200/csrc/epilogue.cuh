@@ -257,6 +257,17 @@ __device__ __forceinline__ void epi_f32(const ConvGeom& g, const EpiParams& e, i
   }
 }
 
+// split-K work item: raw accumulator chunk -> this split's slice (the reduce kernel applies bias and segments)
+template <int CH>
+__device__ __forceinline__ void epi_split(const ConvGeom& g, const EpiParams& e, int b, int y, int x, bool valid, int n0,
+                                          int ncols, int split, const float* acc) {
+  if (!valid) return;
+  float4* d4 = reinterpret_cast<float4*>(e.split_part + static_cast<size_t>(split) * e.split_stride +
+                                         (static_cast<size_t>(b * g.H + y) * g.W + x) * ncols + n0);
+#pragma unroll
+  for (int q = 0; q < CH / 4; ++q) d4[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+}
+
 // ---------------------------------------------------------------- EPI_GATES
 // 32 columns = 8 channels x (in, remember, out, cell) raw gate pre-activations of one NormConvLSTMCell convolution:
 // bias added, stored fp32, and summed per gate for the GroupNorm statistics (gs / gq live in registers across the

@@ -17,7 +17,10 @@
 // changes after i == 1, whatever n_past is). `fixed_skip` is that mode: steps t > 0 decode from their own concat
 // buffers (dcat*) whose skip halves are copies of step 0's, and the skip-half gradients of all steps are summed in
 // G_skip* and enter the encoder backward of step 0 only.
-// Not implemented: heatmaps, multiview, batch_weight.
+// Step API (rac_train_step_begin / _forward / _backward): the same tape and kernels driven one time step per call, for a
+// train-mode SVGConvModel.forward inside the caller's torch autograd graph (the reference's own _train_step body then
+// runs unchanged: compositing, losses and the KL term stay in torch, their gradients come back in through _backward).
+// Not implemented: heatmaps, multiview.
 
 #include <algorithm>
 
@@ -67,6 +70,12 @@ struct Tape {
   int sampled;        // 1: xj is the model's own previous prediction (gradient flows back, trainer.py:354)
 };
 
+// the per-step inputs of the model: slices of the time-first batch, or (step API) the tensors of one forward() call
+struct StepIO {
+  const float *x_j, *m_j, *m_i, *r_j, *r_i, *a_j, *x_i;
+  long long mask_bstride;  // floats between the mask planes of consecutive samples
+};
+
 // time steps [t0, t0 + n) handled by ONE launch per layer: n = steps for a teacher-forced clip, n = 1 when a step
 // consumes the previous step's prediction (scheduled sampling) or with fixed_skip
 struct Span {
@@ -88,9 +97,20 @@ struct TrainState {
   float* gn_dy = nullptr;     // [M3, 4g] gate pre-activation gradients of the cell being processed
   float* gn_part = nullptr;   // [B][14 g] per-sample partials of the GroupNorm affine gradients
   float *params = nullptr, *buffers = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr;
+  // step API (train-mode SVGConvModel.forward under torch autograd): one forward / backward call per time step, the
+  // losses and the compositing live in the caller's autograd graph
+  int step_api = 0;
+  StepIO io{};
+  int active_steps = 0;               // steps on the tape (step API: forward calls so far; else cfg.steps)
+  const float *ext_dx4 = nullptr, *ext_dmu = nullptr, *ext_dlv = nullptr, *ext_dmu_p = nullptr, *ext_dlv_p = nullptr;
+  float* ext_dimg = nullptr;
+  int bwd_next = -1;                  // step API: the time step rac_train_step_backward must be called for next
   int per_step = 0;                   // RAC_TRAIN_PER_STEP=1: never batch the time steps (A/B measurements, cross-checks)
   int dgrad_bt = 1;                   // dgrad reads the forward weight packing as an MN-major operand (0: transposed copy Wd)
   float* wg_part = nullptr;           // split-K partials of the layer being processed
+  int splitk = 1;                     // RAC_TRAIN_SPLITK=0: no split-K in the small-M forward / dgrad GEMMs (A/B measurements)
+  float* sk_part = nullptr;           // their slices [ksplit][rows][N]
+  size_t sk_part_elems = 0;
   size_t wg_part_elems = 0;
   float* wfirst = nullptr;  // [9*cin][64]
   float* zero64 = nullptr;
@@ -178,6 +198,27 @@ int t_gemm(rac_handle* h, const char* name, const GemmGeom& gg, const std::vecto
   if (epi == EPI_F32_BT) CKR(encode_w_map_bt(h, &op.tm.w, w, n_rows_w, gg.ks * gg.ks, bt_rows));
   else CKR(encode_w_map(h, &op.tm.w, w, ktotal, n_rows_w, block_n));
   op.e = ep;
+  // Split-K for the small-M GEMMs (the per-step ConvLSTM dgrads: 768 rows = 48 tiles for 148 SMs, 288-800 k-blocks):
+  // see conv_tc_kernel. Only the fp32 epilogues; the slices are reduced in a fixed order by splitk_reduce_kernel.
+  TrainState* T = static_cast<TrainState*>(h->train);
+  if (T && T->splitk && op.block_m == 128 && (epi == EPI_F32 || epi == EPI_F32_BT) && h->cfg.conv_impl != 1) {
+    const int tiles = g.num_m_tiles * g.num_n_tiles;
+    const int min_kb = ((gg.ks + 1) / 2) * gg.ks * (g.ctot / kBlockK);  // fewest live k-blocks of any tile (border rows)
+    const long long rows = static_cast<long long>(gg.B) * gg.H * gg.W;
+    if (tiles * 2 <= h->num_sms) {
+      int ksplit = std::min(std::min(h->num_sms / tiles, min_kb / 16), 8);
+      while (ksplit > 1 && static_cast<size_t>(ksplit) * rows * n_rows_w > T->sk_part_elems) --ksplit;
+      if (ksplit > 1) {
+        op.g.ksplit = ksplit;
+        op.e.split_part = T->sk_part;
+        op.e.split_stride = rows * n_rows_w;
+        CKR(launch(h, op, st));
+        CK(launch_splitk_reduce(op.e, ksplit, rows, n_rows_w, st));
+        h->launches++;
+        return RAC_OK;
+      }
+    }
+  }
   return launch(h, op, st);
 }
 
@@ -259,7 +300,7 @@ int wg_ctiles(WgradGeom& g, const int* src_c, int nsrc) {
 
 // dWp of one layer from the tape of ALL time steps (called once, after the last processed BPTT step)
 int wgrad_implicit(rac_handle* h, TrainState* T, TLayer& L, int H, int W, const std::vector<Src>& xs, cudaStream_t st) {
-  const int B = T->cfg.batch, S = T->cfg.steps;
+  const int B = T->cfg.batch, S = T->active_steps;
   WgradGeom g = wg_plan(L, B, H, W, S);
   int src_c[kWgMaxSrc];
   if (xs.size() > kWgMaxSrc) return fail(h, RAC_ERR_INVALID, "wgrad: %zu sources", xs.size());
@@ -303,7 +344,7 @@ int conv_backward(rac_handle* h, TrainState* T, int layer, int H, int W, const s
   const int B = T->cfg.batch, nb = sp.n * B;
   const size_t M = static_cast<size_t>(B) * H * W;
   const int ks = (L.taps == 25) ? 5 : 3;
-  const int S = T->cfg.steps;
+  const int S = T->active_steps;
   bf16* slot = dy_slot(T, layer, H, W, sp.t0);
   if (dY != slot)
     CK(cudaMemcpyAsync(slot, dY, sizeof(bf16) * M * sp.n * L.kpad, cudaMemcpyDeviceToDevice, st));
@@ -470,14 +511,12 @@ VggDef dec_def(const rac_handle* h, int i) { VggDef d = kDec[i]; if (i == 0) d.c
 // ------------------------------------------------------------------ forward phases
 // Each phase handles the time steps of `sp` with ONE launch per layer (n * B images). A teacher-forced clip runs every
 // non-recurrent phase once for all steps; only the ConvLSTM cells are stepped through time.
-struct StepIO {
-  const float *x_j, *m_j, *m_i, *r_j, *r_i, *a_j, *x_i;
-};
-
 StepIO step_io(const rac_handle* h, const TrainState* T, const rac_train_batch* bt, int t) {
+  if (T->step_api) return T->io;  // rac_train_step_forward / _backward: the caller's tensors of this one step
   const rac_config& c = h->cfg;
   const size_t B = T->cfg.batch, HW = 48 * 64;
   StepIO io{};
+  io.mask_bstride = static_cast<long long>(HW);
   io.x_j = T->tape[t].xj;
   io.x_i = bt->images + static_cast<size_t>(t + 1) * B * 3 * HW;
   io.m_j = bt->masks ? bt->masks + static_cast<size_t>(t) * B * HW : nullptr;
@@ -497,13 +536,15 @@ int forward_encoder(rac_handle* h, TrainState* T, const rac_train_batch* bt, Spa
   Tape& tp = T->tape[sp.t0];
   for (int t = sp.t0; t < sp.t0 + sp.n; ++t) {
     Tape& q = T->tape[t];
+    if (T->step_api) { q.sampled = 0; q.xj = T->io.x_j; continue; }
     q.sampled = (t > 0 && bt->true_token && !bt->true_token[t]) ? 1 : 0;
     q.xj = q.sampled ? T->tape[t - 1].xp : bt->images + static_cast<size_t>(t) * B * 3 * HW;
   }
   const StepIO io = step_io(h, T, bt, sp.t0);
-  CK(launch_img_prep_train(io.x_j, T->cfg.zero_robot ? io.m_j : nullptr, tp.img4, nb, static_cast<int>(HW), st));
+  // (step API: the caller hands over the frame the model sees, robot pixels already zeroed, trainer.py:365-368)
+  CK(launch_img_prep_train(io.x_j, (T->cfg.zero_robot && !T->step_api) ? io.m_j : nullptr, tp.img4, nb, static_cast<int>(HW), st));
   CK(launch_first_conv(tp.img4, c.use_mask ? io.m_j : nullptr, (c.use_mask && c.use_future_mask) ? io.m_i : nullptr,
-                       static_cast<long long>(HW), T->wfirst, T->zero64, nullptr, nb, 48, 64, h->enc_cin, st, tp.vgg[0].raw));
+                       io.mask_bstride, T->wfirst, T->zero64, nullptr, nb, 48, 64, h->enc_cin, st, tp.vgg[0].raw));
   {
     const TLayer& L = T->L[RAC_L_ENC_C1_0];
     CK(launch_bn_stats(tp.vgg[0].raw, B * static_cast<int>(HW), 64, tp.vgg[0].mean, tp.vgg[0].rstd,
@@ -604,6 +645,7 @@ int forward_decoder(rac_handle* h, TrainState* T, const rac_train_batch* bt, Spa
     e.bias = L.bias; e.cout = 4; e.xpred_out = tp.x4;
     CKR(t_gemm(h, "train.frame.fwd", {nb, 48, 64, 3, false}, {{tp.d5, 64}}, L.wp, 9 * 64, 16, 16, EPI_FRAME, e, st));
   }
+  if (T->step_api) return RAC_OK;  // compositing, losses and metrics belong to the caller's autograd graph
   CK(launch_composite(tp.x4, io.x_j, tp.xp, nb, static_cast<int>(HW), st));
   if (io.m_i)  // logging metrics of the reference step (trainer.py:436-439)
     CK(launch_robot_world_mse_batched(tp.xp, io.x_i, io.m_i, T->metric_part, bt->losses + 2, nb, B, static_cast<int>(HW), st));
@@ -624,20 +666,25 @@ int backward_decoder(rac_handle* h, TrainState* T, const rac_train_batch* bt, Sp
   const StepIO io = step_io(h, T, bt, t0);
   // scheduled sampling (one step at a time): gradient handed over by / to the neighbouring steps through the frame
   const int cur = (S - 1 - t0) & 1;
-  const float* gp_in = (sp.n == 1 && t0 + 1 < S && T->tape[t0 + 1].sampled) ? T->G_img[cur] : nullptr;
+  const float* gp_in = (!T->step_api && sp.n == 1 && t0 + 1 < S && T->tape[t0 + 1].sampled) ? T->G_img[cur] : nullptr;
   float* gxj_out = (sp.n == 1 && tp.sampled) ? T->G_img[cur ^ 1] : nullptr;
   // ---- reconstruction loss and its gradient w.r.t. the decoder logits (trainer.py:406-433)
   bf16* dlogit = dy_slot(T, RAC_L_DEC_UPC5_1, 48, 64, t0);
-  CK(launch_frame_loss(tp.x4, io.x_j, io.x_i, io.m_i, T->cfg.recon_kind, T->cfg.robot_pixel_weight, nb, static_cast<int>(HW),
-                       T->loss_part, dlogit, gp_in, gxj_out, st, bt->batch_weight, B));
-  CK(launch_sum_f32(T->loss_part, nb, bt->losses + 0, st));
+  if (T->step_api) {
+    // dL/d(x_pred) comes from the caller's autograd graph: through the sigmoid to the logits
+    CK(launch_sigmoid_bwd(tp.x4, T->ext_dx4, dlogit, nb, static_cast<int>(HW), st));
+  } else {
+    CK(launch_frame_loss(tp.x4, io.x_j, io.x_i, io.m_i, T->cfg.recon_kind, T->cfg.robot_pixel_weight, nb, static_cast<int>(HW),
+                         T->loss_part, dlogit, gp_in, gxj_out, st, bt->batch_weight, B));
+    CK(launch_sum_f32(T->loss_part, nb, bt->losses + 0, st));
+  }
   F32Seg seg[3];
   seg[0] = {0, 64, T->G_d5.at(t0), 64, 0, 0};
   CKR(conv_backward(h, T, RAC_L_DEC_UPC5_1, 48, 64, {{tp.d5, 64}}, dlogit, seg, 1, sp, st));
   // gradient of a concat buffer: [decoder half | skip half]. fixed_skip: the skip half is summed over the steps
   // (first writer = the first processed step, t == S - 1) instead of going to this step's encoder
   const bool fixed = T->cfg.fixed_skip != 0;
-  const int skip_acc = (t0 == S - 1) ? 0 : 1;
+  const int skip_acc = (t0 == T->active_steps - 1) ? 0 : 1;
   auto cat_segs = [&](float* G_cat, float* G_skip, int half) -> int {
     if (!fixed) { seg[0] = {0, 2 * half, G_cat, 2 * half, 0, 0}; return 1; }
     seg[0] = {0, half, G_cat, 2 * half, 0, 0};
@@ -684,7 +731,11 @@ int backward_gauss(rac_handle* h, TrainState* T, Span sp, cudaStream_t st) {
   Tape& tp = T->tape[t0];
   bf16* dpost = dy_slot(T, RAC_L_POST_GAUSS, 6, 8, t0);
   bf16* dprior = dy_slot(T, RAC_L_PRIOR_GAUSS, 6, 8, t0);
-  CK(launch_gauss_bwd(T->G_z.at(t0), tp.mu, tp.lv, tp.eps_q, tp.mu_p, tp.lv_p, nb, z, 48, T->cfg.kl_beta, B, dpost, dprior, st));
+  if (T->step_api)  // the KL term lives in the caller's graph: its gradients w.r.t. (mu, logvar, mu_p, logvar_p) are inputs
+    CK(launch_gauss_bwd_ext(T->G_z.at(t0), tp.lv, tp.eps_q, T->ext_dmu, T->ext_dlv, T->ext_dmu_p, T->ext_dlv_p, nb, z, 48,
+                            dpost, dprior, st));
+  else
+    CK(launch_gauss_bwd(T->G_z.at(t0), tp.mu, tp.lv, tp.eps_q, tp.mu_p, tp.lv_p, nb, z, 48, T->cfg.kl_beta, B, dpost, dprior, st));
   F32Seg seg = {0, g, T->DH[1][1].at(t0), g, 0, 1};
   CKR(conv_backward(h, T, RAC_L_POST_GAUSS, 6, 8, {{tp.hs[1][1], g}}, dpost, &seg, 1, sp, st));
   seg = {0, g, T->DH[0][1].at(t0), g, 0, 1};
@@ -759,8 +810,12 @@ int backward_encoder(rac_handle* h, TrainState* T, const rac_train_batch* bt, Sp
                      T->params + L.d.beta_off, nb, 48, 64, 64, T->bn_scratch, nullptr, draw32,
                      T->grads + L.d.gamma_off, T->grads + L.d.beta_off, st, sp.n));
     CK(launch_first_wgrad(tp.img4, c.use_mask ? io.m_j : nullptr, (c.use_mask && c.use_future_mask) ? io.m_i : nullptr,
-                          static_cast<long long>(HW), draw32, T->grads + L.d.w_off, nb, 48, 64, h->enc_cin, T->fw_part,
+                          io.mask_bstride, draw32, T->grads + L.d.w_off, nb, 48, 64, h->enc_cin, T->fw_part,
                           kFwBlocks, st));
+    if (T->step_api && T->ext_dimg) {  // gradient w.r.t. the input frame (a model-sampled frame feeds the next step)
+      CK(cudaMemsetAsync(T->ext_dimg, 0, sizeof(float) * static_cast<size_t>(B) * 3 * HW, st));
+      CK(launch_first_dgrad(draw32, T->wfirst, h->enc_cin, nullptr, T->ext_dimg, B, 48, 64, st));
+    }
     // a model-sampled input frame also receives gradient through the encoder (zeroed robot pixels get none)
     if (sp.n == 1 && tp.sampled) {
       float* gxj_out = T->G_img[((T->cfg.steps - 1 - t0) & 1) ^ 1];
@@ -769,6 +824,20 @@ int backward_encoder(rac_handle* h, TrainState* T, const rac_train_batch* bt, Sp
       CK(launch_first_dgrad(draw32, T->wfirst, h->enc_cin, T->cfg.zero_robot ? io.m_j : nullptr, gxj_out, B, 48, 64, st));
     }
   }
+  return RAC_OK;
+}
+
+// parameters -> packed bf16 operands (forward + dgrad), packed biases; zero the flat gradient buffer
+int train_prologue(rac_handle* h, TrainState* T, cudaStream_t st) {
+  // ---- parameters -> packed bf16 operands (forward + dgrad), packed biases; zero the gradient accumulators
+  for (int i = 1; i < T->nlayers; ++i) {
+    TLayer& L = T->L[i];
+    CK(launch_pack_weights(T->params, L.d.row_off, L.d.col_off, L.n_packed, L.taps, L.ctot, L.d.flip, L.wp, st));
+    if (!T->dgrad_bt) CK(launch_transpose_flip(L.wp, L.n_packed, L.taps, L.ctot, L.kpad, L.wd, st));
+    if (L.d.bias_off) CK(launch_gather_f32(T->params, L.d.bias_off, L.n_packed, L.bias, st));
+  }
+  CK(launch_pack_first(T->params + T->L[RAC_L_ENC_C1_0].d.w_off, h->enc_cin, T->wfirst, st));
+  CK(cudaMemsetAsync(T->grads, 0, sizeof(float) * T->cfg.n_params, st));
   return RAC_OK;
 }
 
@@ -800,6 +869,7 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
   if (const char* ps = getenv("RAC_TRAIN_PER_STEP")) T->per_step = atoi(ps);
   if (h->cfg.conv_impl == 1) T->dgrad_bt = 0;
   if (const char* wd = getenv("RAC_DGRAD_WD")) T->dgrad_bt = atoi(wd) ? 0 : 1;
+  if (const char* sk = getenv("RAC_TRAIN_SPLITK")) T->splitk = atoi(sk);
   {
     static bool attr = false;
     if (!attr) { CK(wgrad_tc_set_attributes()); attr = true; }
@@ -934,6 +1004,9 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
       T->wg_part_elems = need;
       T->wg_part = bp.take<float>(need);
     }
+    // split-K slices of the small-M GEMMs: up to 8 slices of one step's widest output (the 4g gate pre-activations)
+    T->sk_part_elems = static_cast<size_t>(8) * M3 * 4 * g;
+    T->sk_part = bp.take<float>(T->sk_part_elems);
     if (!pass) {
       CK(cudaMalloc(&T->arena, bp.off + 1024));
       CK(cudaMemset(T->arena, 0, bp.off + 1024));
@@ -960,16 +1033,10 @@ int rac_train_forward_backward(rac_handle* h, const rac_train_batch* bt, void* s
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int B = T->cfg.batch, S = T->cfg.steps, g = c.g_dim, z = c.z_dim;
   const size_t M3 = static_cast<size_t>(B) * 48;
-  // ---- parameters -> packed bf16 operands (forward + dgrad), packed biases; zero the gradient accumulators
-  for (int i = 1; i < T->nlayers; ++i) {
-    TLayer& L = T->L[i];
-    CK(launch_pack_weights(T->params, L.d.row_off, L.d.col_off, L.n_packed, L.taps, L.ctot, L.d.flip, L.wp, st));
-    if (!T->dgrad_bt) CK(launch_transpose_flip(L.wp, L.n_packed, L.taps, L.ctot, L.kpad, L.wd, st));
-    if (L.d.bias_off) CK(launch_gather_f32(T->params, L.d.bias_off, L.n_packed, L.bias, st));
-  }
-  CK(launch_pack_first(T->params + T->L[RAC_L_ENC_C1_0].d.w_off, h->enc_cin, T->wfirst, st));
-  CK(cudaMemsetAsync(T->grads, 0, sizeof(float) * T->cfg.n_params, st));
+  CKR(train_prologue(h, T, st));
   CK(cudaMemsetAsync(bt->losses, 0, sizeof(float) * 4, st));
+  T->step_api = 0;
+  T->active_steps = S;
   // ---- reparameterisation noise of all steps (the tape is time-major: one copy / one fill per tensor)
   const size_t zn = static_cast<size_t>(B) * z * 48;
   // Philox counter = the caller's global training step (persisted in checkpoints), NOT a count kept in this state:
@@ -1045,6 +1112,133 @@ int rac_train_forward_backward(rac_handle* h, const rac_train_batch* bt, void* s
   for (int i = 1; i < T->nlayers; ++i) {
     TLayer& L = T->L[i];
     CK(launch_unpack_grads(L.dwp, L.d.row_off, L.d.col_off, L.n_packed, L.taps, L.ctot, L.d.flip, T->grads, st));
+  }
+  return RAC_OK;
+}
+
+// ------------------------------------------------------------------ step API
+namespace {
+int step_io_from(rac_handle* h, TrainState* T, const rac_train_step* io) {
+  const rac_config& c = h->cfg;
+  const long long HW = 48 * 64;
+  if (!io || !io->image || !io->action) return fail(h, RAC_ERR_INVALID, "train step: image and action are required");
+  if (c.use_mask && !io->mask) return fail(h, RAC_ERR_INVALID, "train step: model_use_mask needs mask");
+  if (c.use_robot_state && (!io->robot || !io->next_robot))
+    return fail(h, RAC_ERR_INVALID, "train step: model_use_robot_state needs robot and next_robot");
+  StepIO s{};
+  s.x_j = io->image;
+  s.m_j = io->mask;
+  s.m_i = (io->mask && c.use_future_mask) ? io->mask + HW : nullptr;  // mask = cat([m_j, m_i], 1) (trainer.py:373-375)
+  s.mask_bstride = (c.use_mask && c.use_future_mask) ? 2 * HW : HW;
+  s.r_j = io->robot;
+  s.r_i = io->next_robot;
+  s.a_j = io->action;
+  s.x_i = nullptr;
+  T->io = s;
+  return RAC_OK;
+}
+}  // namespace
+
+int rac_train_step_begin(rac_handle* h, void* stream) {
+  if (!h || !h->train) return fail(h, RAC_ERR_STATE, "rac_train_create first");
+  TrainState* T = static_cast<TrainState*>(h->train);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CKR(train_prologue(h, T, st));
+  T->step_api = 1;
+  T->active_steps = 0;
+  T->bwd_next = -1;
+  return RAC_OK;
+}
+
+int rac_train_step_forward(rac_handle* h, const rac_train_step* io, void* stream) {
+  if (!h || !h->train) return fail(h, RAC_ERR_STATE, "rac_train_create first");
+  TrainState* T = static_cast<TrainState*>(h->train);
+  if (!T->step_api) return fail(h, RAC_ERR_STATE, "rac_train_step_begin first");
+  if (T->bwd_next >= 0) return fail(h, RAC_ERR_STATE, "train step: forward after the backward pass has started (rac_train_step_begin first)");
+  const int t = T->active_steps;
+  if (t >= T->cfg.steps)
+    return fail(h, RAC_ERR_STATE, "train step: %d forward calls since rac_train_step_begin, the tape holds %d (n_past + n_future - 1)", t + 1, T->cfg.steps);
+  // last_frame_skip False: step 0 decodes with its own skips, every later step with step 0's (dynamics.py:586-588)
+  if ((io && io->keep_skip != 0) != (T->cfg.fixed_skip != 0 && t > 0))
+    return fail(h, RAC_ERR_INVALID, "train step %d: keep_skip %d does not match fixed_skip %d", t, io ? io->keep_skip : 0, T->cfg.fixed_skip);
+  CKR(step_io_from(h, T, io));
+  if (!io->x_pred || !io->mu || !io->logvar || !io->mu_p || !io->logvar_p) return fail(h, RAC_ERR_INVALID, "train step: null output");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const rac_config& c = h->cfg;
+  const size_t zn = static_cast<size_t>(T->cfg.batch) * c.z_dim * 48, M0 = static_cast<size_t>(T->cfg.batch) * 3072;
+  Tape& tp = T->tape[t];
+  const unsigned int ns = static_cast<unsigned int>(io->noise_step);
+  if (io->eps_prior) CK(cudaMemcpyAsync(tp.eps_p, io->eps_prior, sizeof(float) * zn, cudaMemcpyDeviceToDevice, st));
+  else CK(launch_normal_fill(tp.eps_p, static_cast<long long>(zn), io->seed, 2u * ns, st));
+  if (io->eps_post) CK(cudaMemcpyAsync(tp.eps_q, io->eps_post, sizeof(float) * zn, cudaMemcpyDeviceToDevice, st));
+  else CK(launch_normal_fill(tp.eps_q, static_cast<long long>(zn), io->seed, 2u * ns + 1u, st));
+  const Span one{t, 1};
+  CKR(forward_encoder(h, T, nullptr, one, st));
+  CKR(forward_input_convs(h, T, nullptr, one, st));
+  CKR(lstm_forward(h, T, 0, t, tp.pin, st));
+  CKR(forward_gauss(h, T, 0, one, st));
+  CKR(lstm_forward(h, T, 1, t, tp.postin, st));
+  CKR(forward_gauss(h, T, 1, one, st));
+  CKR(forward_fp_in(h, T, one, st));
+  CKR(lstm_forward(h, T, 2, t, tp.fin, st));
+  CKR(forward_decoder(h, T, nullptr, one, st));
+  CK(cudaMemcpyAsync(io->x_pred, tp.x4, sizeof(float) * M0 * 4, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(io->mu, tp.mu, sizeof(float) * zn, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(io->logvar, tp.lv, sizeof(float) * zn, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(io->mu_p, tp.mu_p, sizeof(float) * zn, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(io->logvar_p, tp.lv_p, sizeof(float) * zn, cudaMemcpyDeviceToDevice, st));
+  T->active_steps = t + 1;
+  return RAC_OK;
+}
+
+int rac_train_step_backward(rac_handle* h, int t, const rac_train_step* io, const float* d_x_pred, const float* d_mu,
+                            const float* d_logvar, const float* d_mu_p, const float* d_logvar_p, float* d_image,
+                            void* stream) {
+  if (!h || !h->train) return fail(h, RAC_ERR_STATE, "rac_train_create first");
+  TrainState* T = static_cast<TrainState*>(h->train);
+  if (!T->step_api || T->active_steps < 1) return fail(h, RAC_ERR_STATE, "train step backward: no forward step on the tape");
+  if (T->bwd_next == -2) return fail(h, RAC_ERR_STATE, "train step backward: this tape has been consumed (one backward pass per rac_train_step_begin)");
+  if (T->bwd_next == -1) {
+    // first call of the backward pass: the latest step whose outputs reached the loss; later steps got no gradient,
+    // so the tape is cut there (their contribution to every parameter gradient is zero)
+    if (t < 0 || t >= T->active_steps) return fail(h, RAC_ERR_INVALID, "train step backward: step %d of %d", t, T->active_steps);
+    T->active_steps = t + 1;
+  } else if (t != T->bwd_next) {
+    return fail(h, RAC_ERR_STATE, "train step backward: step %d requested, step %d is next (BPTT runs from the last step down to 0)", t, T->bwd_next);
+  }
+  const int S = T->active_steps;
+  CKR(step_io_from(h, T, io));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int B = T->cfg.batch, g = h->cfg.g_dim;
+  const size_t M3 = static_cast<size_t>(B) * 48;
+  if (t == S - 1)
+    for (int s = 0; s < 3; ++s)
+      for (int l = 0; l < 2; ++l) {
+        CK(cudaMemsetAsync(T->DH[s][l].p, 0, sizeof(float) * M3 * g * T->cfg.steps, st));
+        CK(cudaMemsetAsync(T->G_dc[s][l], 0, sizeof(float) * M3 * g, st));
+      }
+  T->ext_dx4 = d_x_pred; T->ext_dmu = d_mu; T->ext_dlv = d_logvar; T->ext_dmu_p = d_mu_p; T->ext_dlv_p = d_logvar_p;
+  T->ext_dimg = d_image;
+  Tape& tp = T->tape[t];
+  const Span one{t, 1};
+  CKR(backward_decoder(h, T, nullptr, one, st));
+  CKR(lstm_backward(h, T, 2, t, tp.fin, T->G_fin.at(t), st));
+  CKR(backward_fp_in(h, T, one, st));
+  CKR(backward_gauss(h, T, one, st));
+  CKR(lstm_backward(h, T, 1, t, tp.postin, T->G_postin.at(t), st));
+  CKR(backward_input_conv(h, T, 1, one, st));
+  CKR(lstm_backward(h, T, 0, t, tp.pin, T->G_pin.at(t), st));
+  CKR(backward_input_conv(h, T, 0, one, st));
+  CKR(backward_encoder(h, T, nullptr, one, st));
+  T->ext_dimg = nullptr;
+  if (t == 0) {
+    for (int i = 1; i < T->nlayers; ++i) {
+      TLayer& L = T->L[i];
+      CK(launch_unpack_grads(L.dwp, L.d.row_off, L.d.col_off, L.n_packed, L.taps, L.ctot, L.d.flip, T->grads, st));
+    }
+    T->bwd_next = -2;
+  } else {
+    T->bwd_next = t - 1;
   }
   return RAC_OK;
 }

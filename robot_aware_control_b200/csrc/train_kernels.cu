@@ -577,6 +577,68 @@ cudaError_t launch_gauss_bwd(const float* dz, const float* mu, const float* lv, 
   return cudaGetLastError();
 }
 
+// Step API (train-mode SVGConvModel.forward under torch autograd): the KL term is part of the caller's graph, so its
+// gradients w.r.t. (mu, logvar, mu_p, logvar_p) arrive as tensors (B, z, hw) and are added to the z-sample path
+__global__ void __launch_bounds__(256)
+gauss_bwd_ext_kernel(const float* __restrict__ dz, const float* __restrict__ lv, const float* __restrict__ eps,
+                     const float* __restrict__ dmu, const float* __restrict__ dlv, const float* __restrict__ dmu_p,
+                     const float* __restrict__ dlv_p, int B, int z_dim, int hw, __nv_bfloat16* __restrict__ dpost,
+                     __nv_bfloat16* __restrict__ dprior) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // (m, zc in 0..63)
+  const size_t total = static_cast<size_t>(B) * hw * 64;
+  if (i >= total) return;
+  const int zc = static_cast<int>(i & 63);
+  const size_t m = i >> 6;
+  float a0 = 0.f, a1 = 0.f, p0 = 0.f, p1 = 0.f;
+  if (zc < z_dim) {
+    const size_t b = m / hw;
+    const int pos = static_cast<int>(m % hw);
+    const size_t q = (b * z_dim + zc) * hw + pos;
+    const float g = dz ? dz[m * 64 + zc] : 0.f;
+    a0 = g + (dmu ? dmu[q] : 0.f);
+    a1 = g * eps[q] * 0.5f * expf(0.5f * lv[q]) + (dlv ? dlv[q] : 0.f);
+    p0 = dmu_p ? dmu_p[q] : 0.f;
+    p1 = dlv_p ? dlv_p[q] : 0.f;
+  }
+  reinterpret_cast<uint32_t*>(dpost)[i] = pack_bf16x2(a0, a1);
+  reinterpret_cast<uint32_t*>(dprior)[i] = pack_bf16x2(p0, p1);
+}
+cudaError_t launch_gauss_bwd_ext(const float* dz, const float* lv, const float* eps, const float* dmu, const float* dlv,
+                                 const float* dmu_p, const float* dlv_p, int B, int z_dim, int hw, __nv_bfloat16* dpost,
+                                 __nv_bfloat16* dprior, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(B) * hw * 64;
+  gauss_bwd_ext_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(dz, lv, eps, dmu, dlv, dmu_p, dlv_p, B,
+                                                                                  z_dim, hw, dpost, dprior);
+  return cudaGetLastError();
+}
+
+// Step API: dL/d(x_pred) (B, 4, HW; x_pred = sigmoid(logits), dynamics.py:640-642) -> the frame head's bf16 gradient
+// operand [B * HW][64] (4 real columns)
+__global__ void __launch_bounds__(256)
+sigmoid_bwd_kernel(const float* __restrict__ x4, const float* __restrict__ dx4, int B, int HW,
+                   __nv_bfloat16* __restrict__ dlogit) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // (b, p)
+  if (i >= static_cast<size_t>(B) * HW) return;
+  const size_t b = i / HW;
+  const int p = static_cast<int>(i % HW);
+  float dl[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const size_t q = (b * 4 + c) * HW + p;
+    const float y = x4[q];
+    dl[c] = (dx4 ? dx4[q] : 0.f) * y * (1.f - y);
+  }
+  uint4* d = reinterpret_cast<uint4*>(dlogit + i * 64);
+  d[0] = make_uint4(pack_bf16x2(dl[0], dl[1]), pack_bf16x2(dl[2], dl[3]), 0u, 0u);
+#pragma unroll
+  for (int q = 1; q < 8; ++q) d[q] = make_uint4(0u, 0u, 0u, 0u);
+}
+cudaError_t launch_sigmoid_bwd(const float* x4, const float* dx4, __nv_bfloat16* dlogit, int B, int HW, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(B) * HW;
+  sigmoid_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(x4, dx4, B, HW, dlogit);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ frame loss
 __global__ void __launch_bounds__(1024)
 frame_loss_kernel(const float* __restrict__ x4, const float* __restrict__ xj, const float* __restrict__ xi,

@@ -87,6 +87,11 @@ cudaError_t launch_gauss_bwd(const float* dz, const float* mu, const float* lv, 
 // x4: (B,4,H,W) sigmoid outputs; xj, xi: (B,3,H,W); mask: (B,1,H,W) or null. kind 0 = l1, 1 = dontcare_l1, 2 = mse,
 // 3 = dontcare_mse; batch_weight (B) or null: per-sample factor of the l1 kinds (movement weighting).
 // loss_out[b] = per-sample contribution (already scaled so that the step loss is sum_b loss_out[b]).
+// step API (losses in the caller's autograd graph): external KL / frame gradients
+cudaError_t launch_gauss_bwd_ext(const float* dz, const float* lv, const float* eps, const float* dmu, const float* dlv,
+                                 const float* dmu_p, const float* dlv_p, int B, int z_dim, int hw, __nv_bfloat16* dpost,
+                                 __nv_bfloat16* dprior, cudaStream_t s);
+cudaError_t launch_sigmoid_bwd(const float* x4, const float* dx4, __nv_bfloat16* dlogit, int B, int HW, cudaStream_t s);
 // gp_in: extra gradient w.r.t. the composited prediction (from the next step when that step consumed this
 // prediction as its input, scheduled sampling) or null; gxj_out: gradient w.r.t. x_j through the composite (=) or null.
 cudaError_t launch_frame_loss(const float* x4, const float* xj, const float* xi, const float* mask, int kind,

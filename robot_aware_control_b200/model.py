@@ -5,8 +5,14 @@ tuple, same `state_dict()` keys -- a checkpoint saved by the reference trainer (
 trainer.py:829-837) loads with `load_state_dict`. The arithmetic is done by libracb200.so: eval-mode BatchNorm folded
 into bf16 weights, tcgen05 implicit-GEMM convolutions with fused LSTM / z-sample / sigmoid epilogues.
 
-Not supported (raises): train-mode forward (batch-statistics BatchNorm + backward are not part of this round),
-heatmaps. lstm_group_norm=True (NormConvLSTMCell, lstm.py:151-198) is supported (training: SVGTrainer).
+Train mode (`model.train()`, the nn.Module default): `init_hidden` + `forward` run the training tape of
+libracb200.so one step per call inside the caller's torch autograd graph (`_TrainStep`), so the reference's
+`_train_step` body (trainer.py:326-465 -- compositing, `_recon_loss`, `kl_criterion`, `loss.backward()`,
+`torch.optim.Adam(model.parameters())`) runs unchanged on this class. `SVGTrainer.train_step` is the fused, faster
+way to do the same step (one C call for forward + BPTT, flat Adam).
+
+Not supported (raises): heatmaps; train-mode forward without `next_image` (the reference never trains on the prior's z).
+lstm_group_norm=True (NormConvLSTMCell, lstm.py:151-198) is supported.
 """
 import ctypes as C
 from collections import OrderedDict
@@ -70,6 +76,59 @@ def _spec(c):
     spec["decoder.upc5.1.weight"] = ((64, c.channels + 1, 3, 3), "conv_w")
     spec["decoder.upc5.1.bias"] = ((c.channels + 1,), "zero")
     return spec
+
+
+class _TrainSkips:
+    """`skip` returned by a train-mode forward: the skips live on the library's tape (their gradient flows there, not
+    through torch); handing the object back as `skip=` selects the first frame's skips (last_frame_skip False)."""
+
+    def __init__(self, epoch):
+        self.epoch = epoch
+
+
+class _TrainStep(torch.autograd.Function):
+    """One time step of the SVG model on the library's training tape. The hidden state and every intermediate stay
+    inside libracb200.so; `token` chains the steps so that autograd runs their backward passes in reverse time order
+    (BPTT through the ConvLSTM states happens inside the library)."""
+
+    @staticmethod
+    def forward(ctx, model, token, image, mask, robot, next_robot, action, eps_p, eps_q, keep_skip):
+        ts = model._ts
+        n, z = image.shape[0], model._c.z_dim
+        dev = image.device
+        x_pred = torch.empty(n, 4, 48, 64, device=dev)
+        mu, logvar, mu_p, logvar_p = (torch.empty(n, z, 6, 8, device=dev) for _ in range(4))
+        step = _lib.RacTrainStep(
+            image=_lib.ptr(image), mask=_lib.ptr(mask), robot=_lib.ptr(robot), next_robot=_lib.ptr(next_robot),
+            action=_lib.ptr(action), eps_prior=_lib.ptr(eps_p), eps_post=_lib.ptr(eps_q), seed=ts._seed,
+            noise_step=model._noise_ctr, keep_skip=int(keep_skip), x_pred=_lib.ptr(x_pred), mu=_lib.ptr(mu),
+            logvar=_lib.ptr(logvar), mu_p=_lib.ptr(mu_p), logvar_p=_lib.ptr(logvar_p))
+        _lib.check(model._lib.rac_train_step_forward(model._h, C.byref(step), _lib.stream_ptr()), model._h,
+                   "rac_train_step_forward")
+        ctx.model, ctx.t, ctx.epoch, ctx.keep_skip = model, model._train_t, model._train_epoch, int(keep_skip)
+        ctx.inputs = (image, mask, robot, next_robot, action)  # inputs only (no graph cycle): alive until backward
+        return x_pred, mu, logvar, mu_p, logvar_p, token.new_zeros(())
+
+    @staticmethod
+    def backward(ctx, dx, dmu, dlv, dmu_p, dlv_p, _dtoken):
+        model = ctx.model
+        if ctx.epoch != model._train_epoch:
+            raise RuntimeError("backward through a train-mode forward of an earlier init_hidden(): the library keeps "
+                               "one tape (retain_graph / second-order use is not supported)")
+        image, mask, robot, next_robot, action = ctx.inputs
+        f = lambda g: None if g is None else g.to(torch.float32).contiguous()
+        dx, dmu, dlv, dmu_p, dlv_p = f(dx), f(dmu), f(dlv), f(dmu_p), f(dlv_p)
+        dimage = torch.empty_like(image) if ctx.needs_input_grad[2] else None
+        step = _lib.RacTrainStep(image=_lib.ptr(image), mask=_lib.ptr(mask), robot=_lib.ptr(robot),
+                                 next_robot=_lib.ptr(next_robot), action=_lib.ptr(action), keep_skip=ctx.keep_skip)
+        _lib.check(model._lib.rac_train_step_backward(model._h, ctx.t, C.byref(step), _lib.ptr(dx), _lib.ptr(dmu),
+                                                      _lib.ptr(dlv), _lib.ptr(dmu_p), _lib.ptr(dlv_p),
+                                                      _lib.ptr(dimage), _lib.stream_ptr()), model._h,
+                   "rac_train_step_backward")
+        ctx.inputs = None
+        if ctx.t == 0:
+            model._ts._publish_grads()
+        return None, torch.zeros_like(_dtoken), dimage, None, None, None, None, None, None, None
 
 
 class _Holder(nn.Module):
@@ -148,6 +207,10 @@ class SVGConvModel(nn.Module):
         self._seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
         self._eps = None
         self._eps_post = None
+        self._ts = None           # SVGTrainer owning the flat parameter / gradient storage (train-mode forward)
+        self._train_epoch = 0     # init_hidden() calls in train mode: one library tape each
+        self._train_t = 0
+        self._train_token = None
         self.train(True)  # nn.Module default, as the reference; planning callers call .eval()
 
     # ------------------------------------------------------------------ parameter plumbing
@@ -240,6 +303,8 @@ class SVGConvModel(nn.Module):
         """dynamics.py:536-542."""
         if batch_size is None:
             batch_size = getattr(self._config, "batch_size", 16)
+        if self.training:
+            return self._train_begin(int(batch_size))
         self.prepare(batch_size)
         _lib.check(self._lib.rac_init_hidden(self._h, int(batch_size), _lib.stream_ptr()), self._h, "rac_init_hidden")
 
@@ -248,13 +313,70 @@ class SVGConvModel(nn.Module):
             return None
         return t.to(device=self._device, dtype=torch.float32).contiguous()
 
-    @torch.no_grad()
+    # ------------------------------------------------------------------ train mode (autograd step API)
+    def _train_begin(self, batch_size):
+        """init_hidden() in train mode: zero recurrent state = an empty tape; the bf16 operands are re-packed from the
+        current parameters (torch.optim.Adam has just stepped them) and the flat gradient buffer is zeroed."""
+        if self._ts is None:
+            from .trainer import SVGTrainer
+
+            SVGTrainer(self._config, self)  # flattens the parameters into one buffer and registers itself as _ts
+        ts = self._ts
+        steps = int(getattr(self._config, "n_past", 1)) + int(getattr(self._config, "n_future", 5)) - 1
+        ts._ensure(batch_size, steps)
+        _lib.check(self._lib.rac_train_step_begin(self._h, _lib.stream_ptr()), self._h, "rac_train_step_begin")
+        self._train_epoch += 1
+        self._train_t = 0
+        self._train_batch = batch_size
+        self._train_token = torch.zeros((), device=self._device, requires_grad=True)
+
+    def _train_forward(self, image, mask, robot, action, next_image, next_robot, skip, force_use_prior, sample_mean):
+        c = self._c
+        if next_image is None or force_use_prior or sample_mean:
+            raise NotImplementedError("train-mode forward is the training step of the reference (posterior z, "
+                                      "trainer.py:384-399): next_image is required; call .eval() for prior rollouts")
+        if self._train_token is None or image.shape[0] != self._train_batch:
+            raise RuntimeError(f"init_hidden({image.shape[0]}) must be called (in train mode) before a train-mode forward")
+        image, action = self._f32(image), self._f32(action)
+        mask = self._f32(mask) if c.model_use_mask else None
+        r = nr = None
+        if c.model_use_robot_state:
+            if c.model_use_future_robot_state:
+                r, r2 = self._f32(robot[0]), self._f32(robot[1])
+                nr = self._f32(next_robot)
+                if r2.data_ptr() != nr.data_ptr() and not torch.equal(r2, nr):
+                    raise NotImplementedError("train-mode forward: robot[1] and next_robot must be the same state (the "
+                                              "reference trainer passes r_i for both, trainer.py:376-399)")
+            else:
+                r, nr = self._f32(robot), self._f32(next_robot)
+        keep_skip = 0
+        if skip is not None and not c.last_frame_skip:
+            if not isinstance(skip, _TrainSkips) or skip.epoch != self._train_epoch or self._train_t == 0:
+                raise NotImplementedError("train-mode forward: `skip` must be the object returned by an earlier forward "
+                                          "of the same clip (the first frame's skips, trainer.py:370-371,409-411)")
+            keep_skip = 1
+        eps, eps_post = self._f32(self._eps), self._f32(self._eps_post)
+        out = _TrainStep.apply(self, self._train_token, image, mask, r, nr, action, eps, eps_post, keep_skip)
+        x_pred, mu, logvar, mu_p, logvar_p, self._train_token = out
+        self._train_t += 1
+        self._noise_ctr += 1
+        self._eps = self._eps_post = None
+        self._packed_dirty = True  # the eval-mode packed copy (folded BatchNorm) is stale: statistics moved
+        self._ts._tracked.add_(self._ts._tracked_inc)  # BatchNorm2d.num_batches_tracked (encoder runs twice, :566,619)
+        return x_pred, _TrainSkips(self._train_epoch), mu, logvar, mu_p, logvar_p
+
     def forward(self, image, mask, robot, heatmap, action, next_image=None, next_mask=None, next_robot=None,
                 next_heatmap=None, skip=None, force_use_prior=False, sample_mean=False):
         """dynamics.py:544-644. Returns (x_pred, skip, mu, logvar, mu_p, logvar_p)."""
         if self.training:
-            raise NotImplementedError("train-mode forward (batch-statistics BatchNorm, autograd) is not implemented on "
-                                      "the B200 path; call .eval() (reference controllers do, widowx_VMPC_controller.py:101)")
+            return self._train_forward(image, mask, robot, action, next_image, next_robot, skip, force_use_prior,
+                                       sample_mean)
+        with torch.no_grad():
+            return self._eval_forward(image, mask, robot, heatmap, action, next_image, next_mask, next_robot,
+                                      next_heatmap, skip, force_use_prior, sample_mean)
+
+    def _eval_forward(self, image, mask, robot, heatmap, action, next_image=None, next_mask=None, next_robot=None,
+                      next_heatmap=None, skip=None, force_use_prior=False, sample_mean=False):
         c = self._c
         n = image.shape[0]
         if self._batch != n:

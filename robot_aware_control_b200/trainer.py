@@ -271,6 +271,7 @@ class SVGTrainer:
         self._eps = None
         self._step = 0
         self._adam_t = 0  # Adam steps taken (torch.optim.Adam state "step")
+        model._ts = self  # the latest trainer owns the flat storage the model's train-mode forward works on
 
     # ---- scheduled sampling (reference trainer.py:132-147): same formula, same use of the global numpy generator
     def _schedule_prob(self):
@@ -514,6 +515,17 @@ class SVGTrainer:
             self._step = int(ckpt["step"])
             self.load_optimizer_state_dict(ckpt["optimizer"])
         return self._step
+
+    def _publish_grads(self):
+        """Train-mode SVGConvModel.forward under autograd: after the backward pass of step 0 every parameter's .grad
+        is its slice of the flat gradient buffer (what loss.backward() leaves behind for torch.optim.Adam)."""
+        for k, p in self.model.named_parameters():
+            o = self._offsets[k]
+            g = self.grads[o:o + p.numel()].view(p.shape)
+            if p.grad is None or p.grad.data_ptr() == g.data_ptr():
+                p.grad = g
+            else:  # gradients accumulate across backward() calls until zero_grad(), as in torch
+                p.grad = p.grad + g
 
     def grad_of(self, key):
         o = self._offsets[key]
