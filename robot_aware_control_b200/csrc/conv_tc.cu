@@ -305,7 +305,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
         if constexpr (EPI == EPI_GAUSS) epi_gauss(g, e, b, y, x, valid, n0, acc_v);
         if constexpr (EPI == EPI_FRAME) epi_frame(g, e, b, y, x, valid, yb * (BLOCK_M / 32) + we, acc_v);
         if constexpr (EPI == EPI_F32 || EPI == EPI_F32_BT) {
-          if (kSplitK && ksplit > 1) epi_split<CH>(g, e, b, y, x, valid, n0, g.num_n_tiles * BLOCK_N, split, acc_v);
+          if (kSplitK && e.split_part != nullptr) epi_split<CH>(g, e, b, y, x, valid, n0, g.num_n_tiles * BLOCK_N, split, acc_v);
           else epi_f32<CH>(g, e, b, y, x, valid, n0, acc_v);
         }
         if constexpr (EPI == EPI_GATES) epi_gates(g, e, b, y, x, valid, n0, acc_v, gs, gq);

@@ -108,6 +108,8 @@ struct TrainState {
   int per_step = 0;                   // RAC_TRAIN_PER_STEP=1: never batch the time steps (A/B measurements, cross-checks)
   int dgrad_bt = 1;                   // dgrad reads the forward weight packing as an MN-major operand (0: transposed copy Wd)
   float* wg_part = nullptr;           // split-K partials of the layer being processed
+  int lstm_fused = 0;                 // RAC_TRAIN_LSTM_FUSED=1: gate convolution with the fused cell epilogue, one launch per cell and step (A/B)
+  float* lstm_gx = nullptr;           // [steps][M3][4g] input-half gate pre-activations of the cell being processed
   int splitk = 1;                     // RAC_TRAIN_SPLITK=0: no split-K in the small-M forward / dgrad GEMMs (A/B measurements)
   float* sk_part = nullptr;           // their slices [ksplit][rows][N]
   size_t sk_part_elems = 0;
@@ -147,8 +149,27 @@ struct GemmGeom {
 };
 
 // Build + launch one conv_tc GEMM with an explicit operand description (tensor maps encoded on the fly).
+struct GemmOpt {
+  const int* src_dead = nullptr;  // per source: 1 = its k-blocks are skipped (known zero, or handled by another GEMM)
+  int partial_only = 0;           // 1: leave the raw split-K slices in T->sk_part (the caller's own kernel reduces them)
+  int* ksplit_out = nullptr;      //    ... and how many there are
+};
+
+// work items = tiles x k over `sms` CTAs, each item costs its k-blocks + a fixed fill / epilogue overhead
+int pick_ksplit(int tiles, int kb, int sms) {
+  int best = 1;
+  long long best_cost = 0;
+  for (int k = 1; k <= 8; ++k) {
+    if (k > 1 && kb / k < 16) break;
+    const long long cost = static_cast<long long>((tiles * k + sms - 1) / sms) * (kb / k + 8);
+    if (k == 1 || cost < best_cost) { best = k; best_cost = cost; }
+  }
+  return best;
+}
+
 int t_gemm(rac_handle* h, const char* name, const GemmGeom& gg, const std::vector<Src>& srcs, const bf16* w, int ktotal,
-           int n_rows_w, int block_n, int epi, const EpiParams& ep, cudaStream_t st, int bt_rows = 0) {
+           int n_rows_w, int block_n, int epi, const EpiParams& ep, cudaStream_t st, int bt_rows = 0,
+           const GemmOpt& opt = GemmOpt()) {
   ConvOp op;
   memset(&op, 0, sizeof(op));
   op.name = name;
@@ -172,7 +193,7 @@ int t_gemm(rac_handle* h, const char* name, const GemmGeom& gg, const std::vecto
   op.block_n = block_n;
   {
     const long long tiles = static_cast<long long>((gg.B + g.NB - 1) / g.NB) * (gg.H / g.BH) * (n_rows_w / block_n);
-    if (tiles < 120) {
+    if (tiles < 120 || opt.partial_only) {
       op.block_m = 128;
       geom(128);
       if (op.block_n > 128) op.block_n = 128;
@@ -183,6 +204,7 @@ int t_gemm(rac_handle* h, const char* name, const GemmGeom& gg, const std::vecto
   for (int i = 0; i < g.nsrc; ++i) {
     if (srcs[i].C % kBlockK) return fail(h, RAC_ERR_INVALID, "train gemm %s: source channels %d", name, srcs[i].C);
     g.src_kb[i] = srcs[i].C / kBlockK;
+    g.src_dead[i] = (opt.src_dead && opt.src_dead[i]) ? 1 : 0;
     g.ctot += srcs[i].C;
     op.raw.src[i] = srcs[i].p;
     CKR(encode_act_map(h, &op.tm.a[i], srcs[i].p, srcs[i].C, gg.B, gg.H, gg.W, g.BH, g.NB));
@@ -198,25 +220,34 @@ int t_gemm(rac_handle* h, const char* name, const GemmGeom& gg, const std::vecto
   if (epi == EPI_F32_BT) CKR(encode_w_map_bt(h, &op.tm.w, w, n_rows_w, gg.ks * gg.ks, bt_rows));
   else CKR(encode_w_map(h, &op.tm.w, w, ktotal, n_rows_w, block_n));
   op.e = ep;
-  // Split-K for the small-M GEMMs (the per-step ConvLSTM dgrads: 768 rows = 48 tiles for 148 SMs, 288-800 k-blocks):
-  // see conv_tc_kernel. Only the fp32 epilogues; the slices are reduced in a fixed order by splitk_reduce_kernel.
+  // Split-K for the small-M GEMMs (the per-step ConvLSTM gate convolutions and their dgrads: 768 rows = 48-96 tiles for
+  // 148 SMs, 200-800 k-blocks): see conv_tc_kernel. Only the fp32 epilogues; the slices are reduced in a fixed order
+  // by splitk_reduce_kernel, or by the caller's kernel (partial_only: the ConvLSTM cell).
   TrainState* T = static_cast<TrainState*>(h->train);
-  if (T && T->splitk && op.block_m == 128 && (epi == EPI_F32 || epi == EPI_F32_BT) && h->cfg.conv_impl != 1) {
+  const bool can_split = T && op.block_m == 128 && (epi == EPI_F32 || epi == EPI_F32_BT) && h->cfg.conv_impl != 1;
+  if (opt.partial_only && !can_split) return fail(h, RAC_ERR_STATE, "train gemm %s: split-K slices need the tcgen05 path", name);
+  if (can_split && (T->splitk || opt.partial_only)) {
     const int tiles = g.num_m_tiles * g.num_n_tiles;
-    const int min_kb = ((gg.ks + 1) / 2) * gg.ks * (g.ctot / kBlockK);  // fewest live k-blocks of any tile (border rows)
+    int live_c = 0;
+    for (int i = 0; i < g.nsrc; ++i) live_c += g.src_dead[i] ? 0 : g.src_kb[i];
+    const int min_kb = ((gg.ks + 1) / 2) * gg.ks * live_c;  // fewest live k-blocks of any tile (border rows)
     const long long rows = static_cast<long long>(gg.B) * gg.H * gg.W;
-    if (tiles * 2 <= h->num_sms) {
-      int ksplit = std::min(std::min(h->num_sms / tiles, min_kb / 16), 8);
-      while (ksplit > 1 && static_cast<size_t>(ksplit) * rows * n_rows_w > T->sk_part_elems) --ksplit;
-      if (ksplit > 1) {
-        op.g.ksplit = ksplit;
-        op.e.split_part = T->sk_part;
-        op.e.split_stride = rows * n_rows_w;
-        CKR(launch(h, op, st));
-        CK(launch_splitk_reduce(op.e, ksplit, rows, n_rows_w, st));
-        h->launches++;
+    int ksplit = T->splitk ? pick_ksplit(tiles, min_kb, h->num_sms) : 1;
+    while (ksplit > 1 && static_cast<size_t>(ksplit) * rows * n_rows_w > T->sk_part_elems) --ksplit;
+    if (opt.partial_only && static_cast<size_t>(rows) * n_rows_w > T->sk_part_elems)
+      return fail(h, RAC_ERR_STATE, "train gemm %s: split-K scratch too small", name);
+    if (ksplit > 1 || opt.partial_only) {
+      op.g.ksplit = ksplit;
+      op.e.split_part = T->sk_part;
+      op.e.split_stride = rows * n_rows_w;
+      CKR(launch(h, op, st));
+      if (opt.partial_only) {
+        if (opt.ksplit_out) *opt.ksplit_out = ksplit;
         return RAC_OK;
       }
+      CK(launch_splitk_reduce(op.e, ksplit, rows, n_rows_w, st));
+      h->launches++;
+      return RAC_OK;
     }
   }
   return launch(h, op, st);
@@ -470,6 +501,58 @@ int lstm_forward(rac_handle* h, TrainState* T, int s, int t, const bf16* xin, cu
     CKR(t_gemm(h, "train.lstm.fwd", {B, 6, 8, ks, false}, {{x, g}, {hprev, g}}, L.wp, ks * ks * 2 * g, L.n_packed,
                tile_block_n(L.n_packed, EPI_LSTM_TRAIN), EPI_LSTM_TRAIN, e, st));
     x = tp.hs[s][l];
+  }
+  return RAC_OK;
+}
+
+// ConvLSTM stack s over the steps of `sp`, layer-major (layer 1 only needs layer 0's outputs, never the other way).
+// The gate convolution never runs with its fused cell epilogue here: with 768 rows per step it is 96 tiles for 148 SMs,
+// so (a) for a teacher-forced clip the INPUT half of K (x_t: known for all steps up front -- the input convolution's
+// output for layer 0, layer 0's h of all steps for layer 1) is one GEMM over all n * B images into lstm_gx, (b) the
+// recurrent half (h_{t-1}; nothing at t == 0) runs as split-K work items whose slices (c) the cell kernel sums.
+int lstm_forward_span(rac_handle* h, TrainState* T, int s, Span sp, const bf16* xin0, cudaStream_t st) {
+  if (T->gn || T->lstm_fused) {
+    const size_t xn = static_cast<size_t>(T->cfg.batch) * 48 * h->cfg.g_dim;
+    for (int t = sp.t0; t < sp.t0 + sp.n; ++t) CKR(lstm_forward(h, T, s, t, xin0 + static_cast<size_t>(t - sp.t0) * xn, st));
+    return RAC_OK;
+  }
+  const int B = T->cfg.batch, g = h->cfg.g_dim, M = B * 48;
+  const size_t xn = static_cast<size_t>(M) * g;
+  const bf16* x0 = xin0;
+  const bool pre = sp.n > 1;
+  for (int l = 0; l < 2; ++l) {
+    const int layer = l == 0 ? kLstm0[s] : kLstm1[s];
+    const TLayer& L = T->L[layer];
+    const int ks = l == 0 ? 5 : 3;
+    if (L.n_packed != 4 * g) return fail(h, RAC_ERR_INVALID, "lstm gates: %d packed columns for hid %d", L.n_packed, g);
+    if (pre) {
+      const int dead[2] = {0, 1};
+      GemmOpt o; o.src_dead = dead;
+      EpiParams e{};
+      e.cout = L.n_packed; e.nseg = 1;
+      e.seg[0] = {0, L.n_packed, T->lstm_gx, 4 * g, 0, 0};
+      CKR(t_gemm(h, "train.lstm.x.fwd", {sp.n * B, 6, 8, ks, false}, {{x0, g}, {x0, g}}, L.wp, ks * ks * 2 * g, L.n_packed,
+                 pick_bn(L.n_packed), EPI_F32, e, st, 0, o));
+    }
+    for (int t = sp.t0; t < sp.t0 + sp.n; ++t) {
+      Tape& tp = T->tape[t];
+      const bf16* hprev = t > 0 ? T->tape[t - 1].hs[s][l] : T->hzero;
+      const bf16* x = x0 + static_cast<size_t>(t - sp.t0) * xn;
+      int nsplit = 0;
+      if (!pre || t > 0) {
+        const int dead[2] = {pre ? 1 : 0, t > 0 ? 0 : 1};
+        GemmOpt o; o.src_dead = dead; o.partial_only = 1; o.ksplit_out = &nsplit;
+        EpiParams e{};
+        e.cout = L.n_packed;
+        CKR(t_gemm(h, "train.lstm.h.fwd", {B, 6, 8, ks, false}, {{x, g}, {hprev, g}}, L.wp, ks * ks * 2 * g, L.n_packed,
+                   128, EPI_F32, e, st, 0, o));
+      }
+      CK(launch_lstm_cell_fwd(pre ? T->lstm_gx + static_cast<size_t>(t - sp.t0) * M * 4 * g : nullptr, T->sk_part, nsplit,
+                              static_cast<long long>(M) * L.n_packed, L.bias, t > 0 ? T->tape[t - 1].cs[s][l] : nullptr,
+                              tp.cs[s][l], tp.hs[s][l], tp.gates[s][l], M, g, st));
+      h->launches++;
+    }
+    x0 = T->tape[sp.t0].hs[s][l];  // time-major tape: the h of the following steps is contiguous
   }
   return RAC_OK;
 }
@@ -870,6 +953,8 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
   if (h->cfg.conv_impl == 1) T->dgrad_bt = 0;
   if (const char* wd = getenv("RAC_DGRAD_WD")) T->dgrad_bt = atoi(wd) ? 0 : 1;
   if (const char* sk = getenv("RAC_TRAIN_SPLITK")) T->splitk = atoi(sk);
+  if (const char* lf = getenv("RAC_TRAIN_LSTM_FUSED")) T->lstm_fused = atoi(lf);
+  if (h->cfg.conv_impl == 1) T->lstm_fused = 1;  // (the SIMT cross-check kernels have no split-K items)
   {
     static bool attr = false;
     if (!attr) { CK(wgrad_tc_set_attributes()); attr = true; }
@@ -1007,6 +1092,7 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
     // split-K slices of the small-M GEMMs: up to 8 slices of one step's widest output (the 4g gate pre-activations)
     T->sk_part_elems = static_cast<size_t>(8) * M3 * 4 * g;
     T->sk_part = bp.take<float>(T->sk_part_elems);
+    T->lstm_gx = bp.take<float>(static_cast<size_t>(S) * M3 * 4 * g);
     if (!pass) {
       CK(cudaMalloc(&T->arena, bp.off + 1024));
       CK(cudaMemset(T->arena, 0, bp.off + 1024));
@@ -1057,24 +1143,24 @@ int rac_train_forward_backward(rac_handle* h, const rac_train_batch* bt, void* s
   if (batched) {
     CKR(forward_encoder(h, T, bt, all, st));
     CKR(forward_input_convs(h, T, bt, all, st));
-    for (int t = 0; t < S; ++t) CKR(lstm_forward(h, T, 0, t, T->tape[t].pin, st));
+    CKR(lstm_forward_span(h, T, 0, all, T->tape[0].pin, st));
     CKR(forward_gauss(h, T, 0, all, st));
-    for (int t = 0; t < S; ++t) CKR(lstm_forward(h, T, 1, t, T->tape[t].postin, st));
+    CKR(lstm_forward_span(h, T, 1, all, T->tape[0].postin, st));
     CKR(forward_gauss(h, T, 1, all, st));
     CKR(forward_fp_in(h, T, all, st));
-    for (int t = 0; t < S; ++t) CKR(lstm_forward(h, T, 2, t, T->tape[t].fin, st));
+    CKR(lstm_forward_span(h, T, 2, all, T->tape[0].fin, st));
     CKR(forward_decoder(h, T, bt, all, st));
   } else {
     for (int t = 0; t < S; ++t) {
       const Span one{t, 1};
       CKR(forward_encoder(h, T, bt, one, st));
       CKR(forward_input_convs(h, T, bt, one, st));
-      CKR(lstm_forward(h, T, 0, t, T->tape[t].pin, st));
+      CKR(lstm_forward_span(h, T, 0, one, T->tape[t].pin, st));
       CKR(forward_gauss(h, T, 0, one, st));
-      CKR(lstm_forward(h, T, 1, t, T->tape[t].postin, st));
+      CKR(lstm_forward_span(h, T, 1, one, T->tape[t].postin, st));
       CKR(forward_gauss(h, T, 1, one, st));
       CKR(forward_fp_in(h, T, one, st));
-      CKR(lstm_forward(h, T, 2, t, T->tape[t].fin, st));
+      CKR(lstm_forward_span(h, T, 2, one, T->tape[t].fin, st));
       CKR(forward_decoder(h, T, bt, one, st));
     }
   }
@@ -1175,12 +1261,12 @@ int rac_train_step_forward(rac_handle* h, const rac_train_step* io, void* stream
   const Span one{t, 1};
   CKR(forward_encoder(h, T, nullptr, one, st));
   CKR(forward_input_convs(h, T, nullptr, one, st));
-  CKR(lstm_forward(h, T, 0, t, tp.pin, st));
+  CKR(lstm_forward_span(h, T, 0, one, tp.pin, st));
   CKR(forward_gauss(h, T, 0, one, st));
-  CKR(lstm_forward(h, T, 1, t, tp.postin, st));
+  CKR(lstm_forward_span(h, T, 1, one, tp.postin, st));
   CKR(forward_gauss(h, T, 1, one, st));
   CKR(forward_fp_in(h, T, one, st));
-  CKR(lstm_forward(h, T, 2, t, tp.fin, st));
+  CKR(lstm_forward_span(h, T, 2, one, tp.fin, st));
   CKR(forward_decoder(h, T, nullptr, one, st));
   CK(cudaMemcpyAsync(io->x_pred, tp.x4, sizeof(float) * M0 * 4, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(io->mu, tp.mu, sizeof(float) * zn, cudaMemcpyDeviceToDevice, st));

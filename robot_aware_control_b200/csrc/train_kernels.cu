@@ -490,6 +490,43 @@ cudaError_t launch_bn_bwd(const float* dy, int dy_cstride, int dy_coff, int upsa
 }
 
 // ------------------------------------------------------------------------------------------------ LSTM cell
+// Forward cell of the training step when the gate convolution ran as split-K work items (and, for a teacher-forced
+// clip, with the input half of K computed for all time steps by one earlier GEMM): pre-activation = gx + sum of the
+// slices (fixed order) + bias; then the ConvLSTMCell update (lstm.py:135-149) with the same libm math as EPI_LSTM_TRAIN.
+// Columns are (channel, gate) interleaved, gate order in / remember / out / cell: one thread per (row, channel).
+__global__ void __launch_bounds__(256)
+lstm_cell_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ part, int nsplit, long long split_stride,
+                     const float* __restrict__ bias, const float* __restrict__ c_prev, float* __restrict__ c_out,
+                     __nv_bfloat16* __restrict__ h_out, float* __restrict__ gates_out, size_t total, int hid) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // (m, channel)
+  if (i >= total) return;
+  const int ch = static_cast<int>(i % hid);
+  float4 v = __ldg(reinterpret_cast<const float4*>(bias) + ch);
+  if (gx) {
+    const float4 o = reinterpret_cast<const float4*>(gx)[i];
+    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+  }
+  for (int k = 0; k < nsplit; ++k) {
+    const float4 o = reinterpret_cast<const float4*>(part + k * split_stride)[i];
+    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+  }
+  const float ig = 1.0f / (1.0f + expf(-v.x)), fg = 1.0f / (1.0f + expf(-v.y)), og = 1.0f / (1.0f + expf(-v.z));
+  const float cg = tanhf(v.w);
+  const float cn = fg * (c_prev ? c_prev[i] : 0.f) + ig * cg;
+  c_out[i] = cn;
+  h_out[i] = __float2bfloat16_rn(og * tanhf(cn));
+  reinterpret_cast<float4*>(gates_out)[i] = make_float4(ig, fg, og, cg);
+}
+cudaError_t launch_lstm_cell_fwd(const float* gx, const float* part, int nsplit, long long split_stride,
+                                 const float* bias, const float* c_prev_or_null, float* c_out, __nv_bfloat16* h_out,
+                                 float* gates_out, int M, int hid, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(M) * hid;
+  lstm_cell_fwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(gx, part, nsplit, split_stride, bias,
+                                                                                  c_prev_or_null, c_out, h_out, gates_out,
+                                                                                  total, hid);
+  return cudaGetLastError();
+}
+
 __global__ void __launch_bounds__(256)
 lstm_bwd_kernel(const float* __restrict__ dh, float* __restrict__ dc, const float* __restrict__ gates,
                 const float* __restrict__ c_prev, const float* __restrict__ c_new, size_t total,

@@ -71,6 +71,10 @@ cudaError_t launch_gn_cell_bwd(const GnCellArgs& a, float* grads, cudaStream_t s
 
 // ---- ConvLSTM cell backward (elementwise). gates: saved post-activation (i,f,o,g) interleaved [M, 4*hid];
 // dgates: bf16 [M, 4*hid] w.r.t. the gate pre-activations; dc is updated in place (dc_next -> dc_prev).
+// ConvLSTM cell on gate pre-activations delivered as gx (or null) + nsplit split-K slices + bias (packed columns)
+cudaError_t launch_lstm_cell_fwd(const float* gx, const float* part, int nsplit, long long split_stride,
+                                 const float* bias, const float* c_prev_or_null, float* c_out, __nv_bfloat16* h_out,
+                                 float* gates_out, int M, int hid, cudaStream_t s);
 cudaError_t launch_lstm_bwd(const float* dh, float* dc, const float* gates, const float* c_prev_or_null,
                             const float* c_new, int M, int hid, __nv_bfloat16* dgates, cudaStream_t s);
 // grads[bias_off[n]] += sum_m dy[m][n] for n < nvalid   (dy bf16 [M, ncols])

@@ -114,7 +114,7 @@ def test_reference_train_step_body_runs_on_the_model_class(golden_dir, tag, monk
     # to the neighbouring bf16 value), so the difference climbs layer by layer from 1e-6 at decoder.upc5.1 to the
     # bf16 quantisation level (measured 7e-3 at encoder.c1.0, tests/gpu_autograd_diag.py) and stays there -- the
     # noise every bf16-operand gradient carries anyway.
-    np.testing.assert_allclose(losses["recon_loss"], fused_losses[0], rtol=1e-5)
+    np.testing.assert_allclose(losses["recon_loss"], fused_losses[0], rtol=1e-4 if tag.endswith("sampled") else 1e-5)
     np.testing.assert_allclose(losses["kld"], fused_losses[1], rtol=5e-4)  # (torch evaluates another form of the KL)
     # Scheduled sampling: torch composites the fed-back frame with another fp32 rounding than composite_kernel (FMA
     # contraction), so the forward of the later steps is perturbed and the comparison is chaos-limited like the one
