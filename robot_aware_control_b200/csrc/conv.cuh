@@ -52,7 +52,10 @@ struct ConvGeom {
   // padding are not issued at all (the ConvLSTM gate convolutions run at the power cap: fewer MMAs = faster).
   int y_major;
   int nbw_shift;                                // log2(NB * W)
-  int ksplit;                                   // > 1: split-K work items (conv_tc_kernel, 128-row fp32 epilogues only)
+  int ksplit;                                   // > 1: split-K work items (conv_tc_kernel, fp32 epilogues only)
+  unsigned long long* timeline;                 // debug (RAC_TRAIN_TIMELINE): per-CTA %globaltimer stamps [grid][8], or null
+  int w_prefetch;                               // > 0: a spare thread prefetches the weight boxes into L2 this many k-blocks ahead (conv_tc_kernel)
+  int w_tiled;                                  // 1: weights in the k-block-major packing [kb][n][64] (training; rac_api.cu::encode_w_map_tiled)
 };
 
 // row r of an M-tile -> (candidate, y, x)

@@ -54,7 +54,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
   // dgrad with the weights in their forward packing Wp[n][tap][c]: tm.w is a 3-D map (c, tap, n), a 64-channel box
   // {64 c, 1 tap, 64 n} is one MN-major swizzle group of the B operand (K = n is the slow dimension), taps are flipped
   constexpr bool kBmn = (EPI == EPI_F32_BT);
-  constexpr bool kSplitK = (EPI == EPI_F32 || EPI == EPI_F32_BT) && BLOCK_M == 128;
+  constexpr bool kSplitK = (EPI == EPI_F32 || EPI == EPI_F32_BT);
   static_assert(!kBmn || BLOCK_N % 64 == 0, "MN-major weight boxes are 64 channels wide");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -85,10 +85,11 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
   // contiguous k-block ranges, each writes its raw accumulator to its own slice of e.split_part, and
   // splitk_reduce_kernel sums the slices in a fixed order (deterministic) and applies the real epilogue.
   const int ksplit = (kSplitK && g.ksplit > 1) ? g.ksplit : 1;
-  const int num_items = ksplit > 1 ? num_tiles * ksplit : (split_tail ? full_items + 2 * rem : num_tiles);
+  const bool to_slices = kSplitK && e.split_part != nullptr;  // (one slice when ksplit == 1)
+  const int num_items = to_slices ? num_tiles * ksplit : (split_tail ? full_items + 2 * rem : num_tiles);
   auto item_tile = [&](int item, int& half, int& split) {  // half: -1 = both sub-tiles
     split = 0;
-    if (ksplit > 1) { half = -1; split = item / num_tiles; return item - split * num_tiles; }
+    if (to_slices) { half = -1; split = item / num_tiles; return item - split * num_tiles; }
     if (item < full_items || !split_tail) { half = -1; return item; }
     half = (item - full_items) & 1;
     return full_items + ((item - full_items) >> 1);
@@ -115,6 +116,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], Cfg::kEpiThreads);
     }
+    tmem_slot[1] = 0;  // (kb_issued)
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -125,49 +127,123 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  auto stamp = [&](int i) {
+    if (g.timeline) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      g.timeline[blockIdx.x * 8 + i] = t;
+    }
+  };
+  if (threadIdx.x == 0) stamp(0);
+
+  // the live k-blocks of one work item, in issue order: fn(n_tile, b0, y0, kh, kw, s, kb, kidx). A split-K item starts
+  // at its first k-block directly (walking there one block at a time cost the single thread ~30 ns per skipped block:
+  // up to 25 us before the first load of the last slice of an 800-block tile)
+  auto for_each_kb = [&](int item, auto&& fn) {
+    int half, split;
+    const int tile = item_tile(item, half, split);
+    const int n_tile = tile / g.num_m_tiles;
+    const int m_tile = tile - n_tile * g.num_m_tiles;
+    const int grp = m_tile / g.tiles_per_img;
+    const int b0 = grp * g.NB;
+    const int y0 = (m_tile - grp * g.tiles_per_img) * g.BH;
+    int lo, hi;
+    kb_range(y0, split, lo, hi);
+    if (lo >= hi) return;
+    const int per_row = g.ks * live_kb_per_tap;
+    int khl = lo / per_row;                 // index among the LIVE filter rows
+    int rem = lo - khl * per_row;
+    int kw = rem / live_kb_per_tap;
+    rem -= kw * live_kb_per_tap;            // live k-block inside the tap
+    int kh = -1;
+    for (int c = -1; c < khl;) { ++kh; if (tap_row_live(g, y0, kh)) ++c; }
+    int s = 0, soff = 0;                    // source and its first k-block inside a tap (dead sources included)
+    while (g.src_dead[s] || rem >= g.src_kb[s]) {
+      if (!g.src_dead[s]) rem -= g.src_kb[s];
+      soff += g.src_kb[s];
+      ++s;
+    }
+    int kb = rem;
+    for (int kbi = lo; kbi < hi; ++kbi) {
+      fn(n_tile, b0, y0, kh, kw, s, kb, (kh * g.ks + kw) * kb_per_tap + soff + kb);
+      if (++kb == g.src_kb[s]) {
+        kb = 0;
+        do { soff += g.src_kb[s]; ++s; } while (s < g.nsrc && g.src_dead[s]);
+        if (s == g.nsrc) {
+          s = 0; soff = 0;
+          while (g.src_dead[s]) { soff += g.src_kb[s]; ++s; }
+          if (++kw == g.ks) {
+            kw = 0;
+            do { ++kh; } while (kh < g.ks && !tap_row_live(g, y0, kh));
+          }
+        }
+      }
+    }
+  };
+  // weight-streaming GEMMs (g.w_prefetch > 0: few M-tiles, every weight box comes from DRAM and is used by 1-3 CTAs):
+  // the producer's count of issued k-blocks, read by the L2 prefetch thread (warp 3) to stay w_prefetch blocks ahead
+  volatile int* kb_issued = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
+    int issued = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      int half, split;
-      const int tile = item_tile(item, half, split);
-      const int n_tile = tile / g.num_m_tiles;
-      const int m_tile = tile - n_tile * g.num_m_tiles;
-      const int grp = m_tile / g.tiles_per_img;
-      const int b0 = grp * g.NB;
-      const int y0 = (m_tile - grp * g.tiles_per_img) * g.BH;
-      int lo = 0, hi = 0x7fffffff, kbi = 0;
-      if (ksplit > 1) kb_range(y0, split, lo, hi);
-      for (int kh = 0; kh < g.ks; ++kh) {
-        if (!tap_row_live(g, y0, kh)) continue;
-        for (int kw = 0; kw < g.ks; ++kw) {
-          int kidx = (kh * g.ks + kw) * kb_per_tap;
-          for (int s = 0; s < g.nsrc; ++s) {
-            if (g.src_dead[s]) { kidx += g.src_kb[s]; continue; }
-            for (int kb = 0; kb < g.src_kb[s]; ++kb, ++kidx, ++kbi) {
-              if (kbi < lo || kbi >= hi) continue;
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              uint8_t* sa = smem + stage * Cfg::kStageBytes;
-              uint8_t* sb = sa + Cfg::kABytes;
-              mbar_arrive_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
-              if (g.y_major) tma_load_4d(&tm.a[s], &full_bar[stage], sa, kb * kBlockK, kw - g.pad, b0, y0 + kh - g.pad);
-              else tma_load_4d(&tm.a[s], &full_bar[stage], sa, kb * kBlockK, kw - g.pad, y0 + kh - g.pad, b0);
-              if constexpr (kBmn) {
-                const int taps = g.ks * g.ks;
+      for_each_kb(item, [&](int n_tile, int b0, int y0, int kh, int kw, int s, int kb, int kidx) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::kStageBytes;
+        uint8_t* sb = sa + Cfg::kABytes;
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
+        if (g.y_major) tma_load_4d(&tm.a[s], &full_bar[stage], sa, kb * kBlockK, kw - g.pad, b0, y0 + kh - g.pad);
+        else tma_load_4d(&tm.a[s], &full_bar[stage], sa, kb * kBlockK, kw - g.pad, y0 + kh - g.pad, b0);
+        if constexpr (kBmn) {
+          const int taps = g.ks * g.ks;
+          const int tapf = taps - 1 - (kh * g.ks + kw);
 #pragma unroll
-                for (int j = 0; j < BLOCK_N / 64; ++j)
-                  tma_load_3d(&tm.w, &full_bar[stage], sb + j * 8192, n_tile * BLOCK_N + j * 64, taps - 1 - (kh * g.ks + kw),
-                              kb * kBlockK);
-              } else {
-                tma_load_2d(&tm.w, &full_bar[stage], sb, kidx * kBlockK, n_tile * BLOCK_N);
-              }
-              if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
-            }
+          for (int j = 0; j < BLOCK_N / 64; ++j) {
+            if (g.w_tiled)  // panel (flipped tap, 64-channel block of N), rows kb * 64 .. + 63 of it
+              tma_load_3d(&tm.w, &full_bar[stage], sb + j * 8192, 0, kb * kBlockK,
+                          tapf * (g.num_n_tiles * (BLOCK_N / 64)) + n_tile * (BLOCK_N / 64) + j);
+            else
+              tma_load_3d(&tm.w, &full_bar[stage], sb + j * 8192, n_tile * BLOCK_N + j * 64, tapf, kb * kBlockK);
           }
+        } else if (g.w_tiled) {
+          tma_load_3d(&tm.w, &full_bar[stage], sb, 0, n_tile * BLOCK_N, kidx);
+        } else {
+          tma_load_2d(&tm.w, &full_bar[stage], sb, kidx * kBlockK, n_tile * BLOCK_N);
         }
-      }
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        if (g.w_prefetch > 0) *kb_issued = ++issued;
+      });
+    }
+  } else if (warp == 3 && lane == 0 && g.w_prefetch > 0) {
+    // ===================== L2 prefetch of the weight boxes =====================
+    // The DRAM latency of a weight box (~2 us under load) is longer than the 2-5 stages of shared memory can cover
+    // (profiles/r02_dgrad5x5_ncu_s7.txt: 0.8 TB/s of DRAM reads, tensor pipe 37 % busy, nothing saturated): this thread
+    // walks the same k-blocks w_prefetch ahead of the producer and pulls their weight boxes into L2, so that the
+    // producer's loads are L2 hits.
+    int ahead = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      for_each_kb(item, [&](int n_tile, int, int, int kh, int kw, int, int kb, int kidx) {
+        while (ahead - *kb_issued >= g.w_prefetch) __nanosleep(64);
+        if constexpr (kBmn) {
+          const int taps = g.ks * g.ks;
+          const int tapf = taps - 1 - (kh * g.ks + kw);
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j) {
+            if (g.w_tiled)
+              tma_prefetch_l2_3d(&tm.w, 0, kb * kBlockK, tapf * (g.num_n_tiles * (BLOCK_N / 64)) + n_tile * (BLOCK_N / 64) + j);
+            else
+              tma_prefetch_l2_3d(&tm.w, n_tile * BLOCK_N + j * 64, tapf, kb * kBlockK);
+          }
+        } else if (g.w_tiled) {
+          tma_prefetch_l2_3d(&tm.w, 0, n_tile * BLOCK_N, kidx);
+        } else {
+          tma_prefetch_l2_2d(&tm.w, kidx * kBlockK, n_tile * BLOCK_N);
+        }
+        ++ahead;
+      });
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
@@ -191,9 +267,13 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
       // input row is zero padding (the operand rows TMA wrote are all zero)
       const bool per_sub = g.y_major != 0 && Cfg::kSub == 2;
       uint32_t started = 0;  // bit s: sub-tile s has received its first (non-accumulating) MMA
-      int kb = 0;
-      for (int kh = 0; kh < g.ks; ++kh) {
-        if (!tap_row_live(g, y0, kh)) continue;
+      const int per_row = g.ks * live_kb_per_tap;
+      const int khl = lo / per_row;            // first LIVE filter row of this item and the k-blocks already behind it
+      int in_row = lo - khl * per_row;
+      int kh = -1;
+      for (int c = -1; c < khl;) { ++kh; if (tap_row_live(g, y0, kh)) ++c; }
+      int kb = lo;
+      while (kb < hi) {
         uint32_t sub_live = 3;
         if (per_sub) {
           sub_live = 0;
@@ -202,10 +282,11 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
             if (yy >= 0 && yy < g.H) sub_live |= 1u << sb;
           }
         }
-        for (int rest = g.ks * live_kb_per_tap; rest > 0; --rest, ++kb) {
-          if (kb < lo || kb >= hi) continue;
+        const int row_end = min(hi, kb + per_row - in_row);
+        for (; kb < row_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (kb == lo && item == static_cast<int>(blockIdx.x)) stamp(1);
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t adesc = umma_desc_sw128(sa);
           const uint64_t bdesc = kBmn ? umma_desc_sw128_mn(sa + Cfg::kABytes, 8192u) : umma_desc_sw128(sa + Cfg::kABytes);
@@ -224,9 +305,11 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
             }
           }
           umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
-          if (kb == hi - 1) umma_commit(&tmem_full[acc]);
+          if (kb == hi - 1) { umma_commit(&tmem_full[acc]); if (item == static_cast<int>(blockIdx.x)) stamp(2); }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
+        in_row = 0;
+        do { ++kh; } while (kh < g.ks && !tap_row_live(g, y0, kh));
       }
       if (++acc == Cfg::kNumAcc) { acc = 0; acc_phase ^= 1; }
     }
@@ -267,6 +350,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (r == 0 && item == static_cast<int>(blockIdx.x)) stamp(3);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * Cfg::kAccCols + sub * BLOCK_N;
       // Software pipeline over column chunks, two chunks per (rolled) iteration: the TMEM load and, for the LSTM, the
       // cell-state load of the next chunk are in flight while a chunk is processed. The loop is NOT fully unrolled:
@@ -338,12 +422,14 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
+      if (r == 0 && item == static_cast<int>(blockIdx.x)) stamp(4);
       if (++acc == Cfg::kNumAcc) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) stamp(5);
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 

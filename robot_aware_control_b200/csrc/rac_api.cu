@@ -248,6 +248,24 @@ int encode_w_map_bt(rac_handle* h, CUtensorMap* m, const bf16* ptr, int ctot, in
   return RAC_OK;
 }
 
+// Training weights in the k-block-major ("tiled") packing Wt[kb][n][64] (kb = tap * ctot / 64 + c / 64): dims
+// (64, n_packed, kb_total). A forward box {64, block_n, 1} and a dgrad box {64 c, 64 n, 1} (MN-major operand, rows n
+// beyond n_packed are out of bounds = zero) are both ONE contiguous chunk of memory. With the row-major packing
+// Wp[n][tap * ctot + c] the 128-byte rows of a box lie taps * ctot * 2 bytes apart (a multiple of 2 KB for every layer),
+// and the weight-streaming GEMMs of the training step (768 rows, the weights reused by 3 CTAs only) ran at 0.8 TB/s of
+// DRAM reads with ~3 us per box (profiles/r02_dgrad5x5_ncu_s7.txt).
+int encode_w_map_tiled(rac_handle* h, CUtensorMap* m, const bf16* ptr, int n_packed, int kb_total, int box_rows) {
+  cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(n_packed), static_cast<cuuint64_t>(kb_total)};
+  cuuint64_t strides[2] = {128, static_cast<cuuint64_t>(n_packed) * 128};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(ptr), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, RAC_ERR_CUDA, "cuTensorMapEncodeTiled(tiled weights n=%d kb=%d) failed: %d", n_packed, kb_total, (int)r);
+  return RAC_OK;
+}
+
 // Halo kernel activation map. Preferred: dims (C, H, W, B) -- H and W swapped through the strides -- so that ONE box
 // {64, 8, 34, 1} lands column-major (8 rows of a column = one swizzle atom). If the driver rejects the non-monotonic
 // strides: dims (C, W, H, B) with a one-column box {64, 1, 8, 1}, loaded 34 times per tile.

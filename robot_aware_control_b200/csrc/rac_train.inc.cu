@@ -110,6 +110,9 @@ struct TrainState {
   float* wg_part = nullptr;           // split-K partials of the layer being processed
   int lstm_fused = 0;                 // RAC_TRAIN_LSTM_FUSED=1: gate convolution with the fused cell epilogue, one launch per cell and step (A/B)
   float* lstm_gx = nullptr;           // [steps][M3][4g] input-half gate pre-activations of the cell being processed
+  int w_prefetch = 8;                 // k-blocks of L2 weight prefetch distance in the weight-streaming GEMMs (RAC_TRAIN_W_PREFETCH, 0 = off)
+  int w_tiled = 1;                    // bf16 weights in the k-block-major packing (0: row-major Wp[n][tap][c]; RAC_TRAIN_W_TILED=0, SIMT, Wd)
+  int tile_model = 1;                 // RAC_TRAIN_TILE_MODEL=0: round-1 tile rule (256-row tiles unless < 120 of them), no split-K
   int splitk = 1;                     // RAC_TRAIN_SPLITK=0: no split-K in the small-M forward / dgrad GEMMs (A/B measurements)
   float* sk_part = nullptr;           // their slices [ksplit][rows][N]
   size_t sk_part_elems = 0;
@@ -155,16 +158,28 @@ struct GemmOpt {
   int* ksplit_out = nullptr;      //    ... and how many there are
 };
 
-// work items = tiles x k over `sms` CTAs, each item costs its k-blocks + a fixed fill / epilogue overhead
-int pick_ksplit(int tiles, int kb, int sms) {
-  int best = 1;
-  long long best_cost = 0;
-  for (int k = 1; k <= 8; ++k) {
-    if (k > 1 && kb / k < 16) break;
-    const long long cost = static_cast<long long>((tiles * k + sms - 1) / sms) * (kb / k + 8);
-    if (k == 1 || cost < best_cost) { best = k; best_cost = cost; }
+// Tile shape and split-K factor of an fp32-epilogue training GEMM. Two regimes, both settled by measurement
+// (profiles/r02_train_tile_sweep.txt, per-CTA phase timelines in profiles/r02_train_timeline_s10.txt):
+// * weight-streaming GEMMs -- at most 8 M-tiles of 256 rows, i.e. the per-step ConvLSTM gate convolutions and their
+//   dgrads (768 rows, 200-800 k-blocks, 50-100 MB of weights used once): 256-row tiles (a k-block of a 256 x 256 tile
+//   runs at the MMA rate, 0.61 us; 128 x 128 tiles took 0.5 us per k-block for a quarter of the work) and as many
+//   split-K slices as fill ONE wave of the SMs (12 slices of the 12 tiles of a dgrad: a second wave or fewer, longer
+//   slices both measured slower);
+// * everything else: 256-row tiles unless there are fewer than 120 of them, then 128 x <= 128 tiles; no split-K.
+struct TilePlan { int bm, bn, ksplit; };
+TilePlan plan_tiles(int mt256, int mt128, int n_cols, int max_bn, int min_kb, long long rows, bool allow_split,
+                    bool partial, int sms, size_t part_capacity) {
+  (void)partial;
+  const int tiles256 = mt256 * (n_cols / max_bn);
+  if (mt256 <= 8 && allow_split) {
+    int k = std::max(1, sms / std::max(tiles256, 1));
+    k = std::min(k, std::max(1, min_kb / 8));
+    while (k > 1 && static_cast<size_t>(k) * rows * n_cols > part_capacity) --k;
+    return {256, max_bn, k};
   }
-  return best;
+  if (tiles256 < 120) return {128, std::min(max_bn, 128), 1};
+  (void)mt128;
+  return {256, max_bn, 1};
 }
 
 int t_gemm(rac_handle* h, const char* name, const GemmGeom& gg, const std::vector<Src>& srcs, const bf16* w, int ktotal,
@@ -189,10 +204,38 @@ int t_gemm(rac_handle* h, const char* name, const GemmGeom& gg, const std::vecto
     }
   };
   if (!geom(256)) return fail(h, RAC_ERR_INVALID, "train gemm %s: bad width %d", name, gg.W);
+  TrainState* T = static_cast<TrainState*>(h->train);
+  const bool can_split = T && (epi == EPI_F32 || epi == EPI_F32_BT) && h->cfg.conv_impl != 1;
+  if (opt.partial_only && !can_split) return fail(h, RAC_ERR_STATE, "train gemm %s: split-K slices need the tcgen05 path", name);
+  const long long rows = static_cast<long long>(gg.B) * gg.H * gg.W;
+  const int mt256 = ((gg.B + g.NB - 1) / g.NB) * (gg.H / g.BH);
+  int ksplit = 1;
   op.block_m = 256;
   op.block_n = block_n;
-  {
-    const long long tiles = static_cast<long long>((gg.B + g.NB - 1) / g.NB) * (gg.H / g.BH) * (n_rows_w / block_n);
+  if (can_split && T->tile_model) {
+    geom(128);
+    const int mt128 = ((gg.B + g.NB - 1) / g.NB) * (gg.H / g.BH);
+    int live_c = 0;
+    for (size_t i = 0; i < srcs.size(); ++i) live_c += (opt.src_dead && opt.src_dead[i]) ? 0 : srcs[i].C / kBlockK;
+    const int min_kb = ((gg.ks + 1) / 2) * gg.ks * live_c;  // fewest live k-blocks of any tile (border rows)
+    const TilePlan tp = plan_tiles(mt256, mt128, n_rows_w, block_n, min_kb, rows, T->splitk != 0, opt.partial_only != 0,
+                                   h->num_sms, T->sk_part_elems);
+    TilePlan use = tp;
+    // RAC_TRAIN_FORCE_TILE="<name substring>:<block_m>:<ksplit>": overrides the plan of the matching small-M GEMMs (sweeps)
+    static const char* force = getenv("RAC_TRAIN_FORCE_TILE");
+    for (const char* f = (force && rows <= 1024) ? force : nullptr; f && *f;) {  // comma-separated entries
+      char sub[64]; int fbm = 0, fk = 0;
+      if (sscanf(f, "%63[^:]:%d:%d", sub, &fbm, &fk) == 3 && strstr(name, sub) && (fbm == 128 || fbm == 256) && fk >= 1 &&
+          static_cast<size_t>(fk) * rows * n_rows_w <= T->sk_part_elems && min_kb / fk >= 1)
+        use = {fbm, fbm == 256 ? block_n : std::min(block_n, 128), fk};
+      f = strchr(f, ',');
+      if (f) ++f;
+    }
+    op.block_m = use.bm; op.block_n = block_n = use.bn; ksplit = use.ksplit;
+    geom(use.bm);
+  } else {
+    // batch-16 training GEMMs are small: when 256-row tiles would leave most of the 148 SMs idle, use 128 x <=128 tiles
+    const long long tiles = static_cast<long long>(mt256) * (n_rows_w / block_n);
     if (tiles < 120 || opt.partial_only) {
       op.block_m = 128;
       geom(128);
@@ -217,38 +260,67 @@ int t_gemm(rac_handle* h, const char* name, const GemmGeom& gg, const std::vecto
   g.w_shift = ilog2(gg.W);
   g.bhw_shift = ilog2(g.BH * gg.W);
   op.raw.w = w;
-  if (epi == EPI_F32_BT) CKR(encode_w_map_bt(h, &op.tm.w, w, n_rows_w, gg.ks * gg.ks, bt_rows));
-  else CKR(encode_w_map(h, &op.tm.w, w, ktotal, n_rows_w, block_n));
+  // (EPI_F32_BT: the GEMM's N = n_rows_w is the layer's input-channel count, its K rows are the layer's bt_rows packed
+  // output columns; the weight buffer is the forward packing either way)
+  const bool tiled = T && T->w_tiled;
+  g.w_tiled = tiled ? 1 : 0;
+  // few M-tiles = every weight box is fetched from DRAM for 1-8 CTAs: let the spare thread run ahead in L2
+  if (T && T->w_prefetch > 0 && g.num_m_tiles <= 8 && h->cfg.conv_impl != 1) g.w_prefetch = T->w_prefetch;
+  if (epi == EPI_F32_BT) {
+    if (tiled) CKR(encode_w_map_tiled(h, &op.tm.w, w, bt_rows, gg.ks * gg.ks * (n_rows_w / kBlockK), 64));
+    else CKR(encode_w_map_bt(h, &op.tm.w, w, n_rows_w, gg.ks * gg.ks, bt_rows));
+  } else {
+    if (tiled) CKR(encode_w_map_tiled(h, &op.tm.w, w, n_rows_w, ktotal / kBlockK, block_n));
+    else CKR(encode_w_map(h, &op.tm.w, w, ktotal, n_rows_w, block_n));
+  }
   op.e = ep;
-  // Split-K for the small-M GEMMs (the per-step ConvLSTM gate convolutions and their dgrads: 768 rows = 48-96 tiles for
-  // 148 SMs, 200-800 k-blocks): see conv_tc_kernel. Only the fp32 epilogues; the slices are reduced in a fixed order
-  // by splitk_reduce_kernel, or by the caller's kernel (partial_only: the ConvLSTM cell).
-  TrainState* T = static_cast<TrainState*>(h->train);
-  const bool can_split = T && op.block_m == 128 && (epi == EPI_F32 || epi == EPI_F32_BT) && h->cfg.conv_impl != 1;
-  if (opt.partial_only && !can_split) return fail(h, RAC_ERR_STATE, "train gemm %s: split-K slices need the tcgen05 path", name);
-  if (can_split && (T->splitk || opt.partial_only)) {
-    const int tiles = g.num_m_tiles * g.num_n_tiles;
-    int live_c = 0;
-    for (int i = 0; i < g.nsrc; ++i) live_c += g.src_dead[i] ? 0 : g.src_kb[i];
-    const int min_kb = ((gg.ks + 1) / 2) * gg.ks * live_c;  // fewest live k-blocks of any tile (border rows)
-    const long long rows = static_cast<long long>(gg.B) * gg.H * gg.W;
-    int ksplit = T->splitk ? pick_ksplit(tiles, min_kb, h->num_sms) : 1;
-    while (ksplit > 1 && static_cast<size_t>(ksplit) * rows * n_rows_w > T->sk_part_elems) --ksplit;
-    if (opt.partial_only && static_cast<size_t>(rows) * n_rows_w > T->sk_part_elems)
-      return fail(h, RAC_ERR_STATE, "train gemm %s: split-K scratch too small", name);
-    if (ksplit > 1 || opt.partial_only) {
-      op.g.ksplit = ksplit;
-      op.e.split_part = T->sk_part;
-      op.e.split_stride = rows * n_rows_w;
-      CKR(launch(h, op, st));
-      if (opt.partial_only) {
-        if (opt.ksplit_out) *opt.ksplit_out = ksplit;
-        return RAC_OK;
+  // RAC_TRAIN_TIMELINE=<substring of the GEMM name>: per-CTA phase stamps of matching launches, printed to stderr
+  static const char* tl_name = getenv("RAC_TRAIN_TIMELINE");
+  unsigned long long* tl_buf = nullptr;
+  if (tl_name && *tl_name && strstr(name, tl_name)) {
+    CK(cudaMalloc(&tl_buf, sizeof(unsigned long long) * 8 * 160));
+    CK(cudaMemset(tl_buf, 0, sizeof(unsigned long long) * 8 * 160));
+    op.g.timeline = tl_buf;
+  }
+  struct TlPrint {
+    unsigned long long* buf; const char* name; const ConvOp* op; cudaStream_t st; int ksplit;
+    ~TlPrint() {
+      if (!buf) return;
+      cudaStreamSynchronize(st);
+      std::vector<unsigned long long> hst(8 * 160);
+      cudaMemcpy(hst.data(), buf, hst.size() * 8, cudaMemcpyDeviceToHost);
+      cudaFree(buf);
+      unsigned long long t0 = ~0ull, t5 = 0;
+      int n = 0;
+      double ph[5] = {0, 0, 0, 0, 0}, mx[5] = {0, 0, 0, 0, 0};
+      for (int c = 0; c < 160; ++c) {
+        const unsigned long long* t = &hst[c * 8];
+        if (!t[0] || !t[5]) continue;
+        ++n; t0 = std::min(t0, t[0]); t5 = std::max(t5, t[5]);
+        for (int i = 0; i < 5; ++i) { const double d = (double)((long long)t[i + 1] - (long long)t[i]) * 1e-3; ph[i] += d; mx[i] = std::max(mx[i], d); }
       }
-      CK(launch_splitk_reduce(op.e, ksplit, rows, n_rows_w, st));
-      h->launches++;
+      if (n) fprintf(stderr, "[timeline] %s tile %dx%d grid %d ksplit %d span %.1f us | avg(max) us: start->data %.1f(%.1f) mainloop %.1f(%.1f) "
+                     "mma->epi %.1f(%.1f) epilogue %.1f(%.1f) tail %.1f(%.1f)\n", name, op->block_m, op->block_n, n, ksplit,
+                     (double)(t5 - t0) * 1e-3, ph[0] / n, mx[0], ph[1] / n, mx[1], ph[2] / n, mx[2], ph[3] / n, mx[3], ph[4] / n, mx[4]);
+    }
+  } tl_print{tl_buf, name, &op, st, ksplit};
+  // Split-K for the small-M GEMMs (the per-step ConvLSTM gate convolutions and their dgrads: 768 rows, 200-800 k-blocks):
+  // see conv_tc_kernel. Only the fp32 epilogues; the slices are reduced in a fixed order by splitk_reduce_kernel, or by
+  // the caller's kernel (partial_only: the ConvLSTM cell).
+  if (can_split && (ksplit > 1 || opt.partial_only)) {
+    if (static_cast<size_t>(ksplit) * rows * n_rows_w > T->sk_part_elems)
+      return fail(h, RAC_ERR_STATE, "train gemm %s: split-K scratch too small", name);
+    op.g.ksplit = ksplit;
+    op.e.split_part = T->sk_part;
+    op.e.split_stride = rows * n_rows_w;
+    CKR(launch(h, op, st));
+    if (opt.partial_only) {
+      if (opt.ksplit_out) *opt.ksplit_out = ksplit;
       return RAC_OK;
     }
+    CK(launch_splitk_reduce(op.e, ksplit, rows, n_rows_w, st));
+    h->launches++;
+    return RAC_OK;
   }
   return launch(h, op, st);
 }
@@ -545,7 +617,7 @@ int lstm_forward_span(rac_handle* h, TrainState* T, int s, Span sp, const bf16* 
         EpiParams e{};
         e.cout = L.n_packed;
         CKR(t_gemm(h, "train.lstm.h.fwd", {B, 6, 8, ks, false}, {{x, g}, {hprev, g}}, L.wp, ks * ks * 2 * g, L.n_packed,
-                   128, EPI_F32, e, st, 0, o));
+                   pick_bn(L.n_packed), EPI_F32, e, st, 0, o));
       }
       CK(launch_lstm_cell_fwd(pre ? T->lstm_gx + static_cast<size_t>(t - sp.t0) * M * 4 * g : nullptr, T->sk_part, nsplit,
                               static_cast<long long>(M) * L.n_packed, L.bias, t > 0 ? T->tape[t - 1].cs[s][l] : nullptr,
@@ -915,7 +987,7 @@ int train_prologue(rac_handle* h, TrainState* T, cudaStream_t st) {
   // ---- parameters -> packed bf16 operands (forward + dgrad), packed biases; zero the gradient accumulators
   for (int i = 1; i < T->nlayers; ++i) {
     TLayer& L = T->L[i];
-    CK(launch_pack_weights(T->params, L.d.row_off, L.d.col_off, L.n_packed, L.taps, L.ctot, L.d.flip, L.wp, st));
+    CK(launch_pack_weights(T->params, L.d.row_off, L.d.col_off, L.n_packed, L.taps, L.ctot, L.d.flip, L.wp, st, T->w_tiled));
     if (!T->dgrad_bt) CK(launch_transpose_flip(L.wp, L.n_packed, L.taps, L.ctot, L.kpad, L.wd, st));
     if (L.d.bias_off) CK(launch_gather_f32(T->params, L.d.bias_off, L.n_packed, L.bias, st));
   }
@@ -954,6 +1026,11 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
   if (const char* wd = getenv("RAC_DGRAD_WD")) T->dgrad_bt = atoi(wd) ? 0 : 1;
   if (const char* sk = getenv("RAC_TRAIN_SPLITK")) T->splitk = atoi(sk);
   if (const char* lf = getenv("RAC_TRAIN_LSTM_FUSED")) T->lstm_fused = atoi(lf);
+  if (const char* tm = getenv("RAC_TRAIN_TILE_MODEL")) T->tile_model = atoi(tm);
+  if (const char* wt = getenv("RAC_TRAIN_W_TILED")) T->w_tiled = atoi(wt);
+  if (const char* wp = getenv("RAC_TRAIN_W_PREFETCH")) T->w_prefetch = atoi(wp);
+  if (!T->dgrad_bt || h->cfg.conv_impl == 1) T->w_tiled = 0;  // (the transposed copy and the SIMT kernels index Wp[n][tap][c])
+  if (!T->tile_model) T->lstm_fused = 1;
   if (h->cfg.conv_impl == 1) T->lstm_fused = 1;  // (the SIMT cross-check kernels have no split-K items)
   {
     static bool attr = false;
@@ -1089,8 +1166,8 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
       T->wg_part_elems = need;
       T->wg_part = bp.take<float>(need);
     }
-    // split-K slices of the small-M GEMMs: up to 8 slices of one step's widest output (the 4g gate pre-activations)
-    T->sk_part_elems = static_cast<size_t>(8) * M3 * 4 * g;
+    // split-K slices of the small-M GEMMs: up to 16 slices of one step's widest output (the 4g gate pre-activations)
+    T->sk_part_elems = static_cast<size_t>(16) * M3 * 4 * g;
     T->sk_part = bp.take<float>(T->sk_part_elems);
     T->lstm_gx = bp.take<float>(static_cast<size_t>(S) * M3 * 4 * g);
     if (!pass) {

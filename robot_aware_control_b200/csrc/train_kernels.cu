@@ -14,7 +14,7 @@ namespace rac {
 // read through a shared-memory tile with c fastest (coalesced too). col_off[c] < 0 marks padding channels.
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(const float* __restrict__ params, const long long* __restrict__ row_off,
-                    const int* __restrict__ col_off, int n_packed, int taps, int ctot, int flip,
+                    const int* __restrict__ col_off, int n_packed, int taps, int ctot, int flip, int tiled,
                     __nv_bfloat16* __restrict__ wp) {
   __shared__ float tile[25][65];
   const int c0 = blockIdx.y * 64;
@@ -31,17 +31,19 @@ pack_weights_kernel(const float* __restrict__ params, const long long* __restric
     __syncthreads();
     for (int j = threadIdx.x; j < 32 * taps; j += blockDim.x) {
       const int tap = j >> 5, cl = (j & 31) * 2;
-      *reinterpret_cast<__nv_bfloat162*>(wp + (static_cast<long long>(n) * taps + tap) * ctot + c0 + cl) =
-          __floats2bfloat162_rn(tile[tap][cl], tile[tap][cl + 1]);
+      // tiled: k-block-major panels [tap * ctot / 64 + c0 / 64][n][64] (every TMA weight box is one contiguous chunk)
+      const long long at = tiled ? ((static_cast<long long>(tap) * (ctot >> 6) + blockIdx.y) * n_packed + n) * 64 + cl
+                                 : (static_cast<long long>(n) * taps + tap) * ctot + c0 + cl;
+      *reinterpret_cast<__nv_bfloat162*>(wp + at) = __floats2bfloat162_rn(tile[tap][cl], tile[tap][cl + 1]);
     }
     __syncthreads();
   }
 }
 cudaError_t launch_pack_weights(const float* params, const long long* row_off, const int* col_off, int n_packed,
-                                int taps, int ctot, int flip, __nv_bfloat16* wp, cudaStream_t s) {
+                                int taps, int ctot, int flip, __nv_bfloat16* wp, cudaStream_t s, int tiled) {
   if (ctot % 64 != 0 || taps > 25) return cudaErrorInvalidValue;
   const int gx = std::min(n_packed, std::max(1, 1184 / (ctot / 64)));
-  pack_weights_kernel<<<dim3(gx, ctot / 64), 256, 0, s>>>(params, row_off, col_off, n_packed, taps, ctot, flip, wp);
+  pack_weights_kernel<<<dim3(gx, ctot / 64), 256, 0, s>>>(params, row_off, col_off, n_packed, taps, ctot, flip, tiled, wp);
   return cudaGetLastError();
 }
 

@@ -12,7 +12,7 @@ namespace rac {
 // ---- weights: fp32 master (flat) <-> packed bf16 GEMM operands
 // Wp[n][tap][c] = params[row_off[n] + col_off[c] + (flip ? taps-1-tap : tap)]  (0 where an offset is negative)
 cudaError_t launch_pack_weights(const float* params, const long long* row_off, const int* col_off, int n_packed,
-                                int taps, int ctot, int flip, __nv_bfloat16* wp, cudaStream_t s);
+                                int taps, int ctot, int flip, __nv_bfloat16* wp, cudaStream_t s, int tiled = 0);
 // dgrad operand: Wd[c][tap][n] = Wp[n][taps-1-tap][c], n padded with zeros to kpad
 cudaError_t launch_transpose_flip(const __nv_bfloat16* wp, int n_packed, int taps, int ctot, int kpad,
                                   __nv_bfloat16* wd, cudaStream_t s);

@@ -184,10 +184,12 @@ def test_state_dict_roundtrip_and_errors():
         assert torch.equal(out[k].cpu(), sd[k])
     with pytest.raises(RuntimeError):  # forward before init_hidden for that batch
         m.forward(torch.rand(2, 3, 48, 64), None, None, None, torch.zeros(2, 5))
-    m.train()
-    m.init_hidden(2)
-    with pytest.raises(NotImplementedError):
-        m.forward(torch.rand(2, 3, 48, 64), None, None, None, torch.zeros(2, 5))
+    m.train()  # train mode = the training tape (tests/test_gpu_train_autograd.py): batches of 4 clips, posterior needed
+    with pytest.raises(ValueError):
+        m.init_hidden(2)
+    m.init_hidden(4)
+    with pytest.raises(NotImplementedError):  # a prior-only forward is an eval-mode call
+        m.forward(torch.rand(4, 3, 48, 64), None, None, None, torch.zeros(4, 5))
 
 
 # ------------------------------------------------------------------------------------------------ rollout + cost
