@@ -282,6 +282,76 @@ __device__ __forceinline__ bool last_block_of_column_group() {
   return s_last;
 }
 
+// Bandwidth-oriented variant for C % 4 == 0 (the BatchNorm layers: 64-512 channels, up to 245 760 rows): 256 threads,
+// each owns 4 adjacent channels (one 128-bit load per row) of every RL-th row of the CTA's row range; the CTA covers
+// Qb = 256 / RL channel quads (blockIdx.x selects which), so a warp reads >= 128 contiguous bytes per row and the
+// loads of 4 rows are in flight per thread. (The one-channel-per-thread kernel above ran at 0.6 TB/s on the
+// full-resolution layers, profiles/r02_launches_train_summary_s10.txt.) Partials land in the same g_red_part slots.
+template <typename F>
+__device__ __forceinline__ void column_partial2_v4(int M, int C, int Qb, F load4) {
+  __shared__ double sh[8][256];
+  const int tid = threadIdx.x;
+  const int RL = 256 / Qb;
+  const int q = tid % Qb, rl = tid / Qb;
+  const int c0 = (blockIdx.x * Qb + q) * 4;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int m_base = blockIdx.z * M;
+  const int m_lo = m_base + blockIdx.y * rows_per;
+  const int m_hi = min(m_base + M, m_lo + rows_per);
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c0 < C) {
+    int m = m_lo + rl;
+    for (; m + 3 * RL < m_hi; m += 4 * RL) {
+      float4 a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load4(m + u * RL, c0, a[u], b[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[0] += a[u].x; acc[1] += a[u].y; acc[2] += a[u].z; acc[3] += a[u].w;
+        acc[4] += b[u].x; acc[5] += b[u].y; acc[6] += b[u].z; acc[7] += b[u].w;
+      }
+    }
+    for (; m < m_hi; m += RL) {
+      float4 a, b;
+      load4(m, c0, a, b);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+      acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[j][tid] = acc[j];
+  __syncthreads();
+  if (rl == 0 && c0 < C) {
+    const int slot = blockIdx.z * gridDim.y + blockIdx.y;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      double t = 0.0;
+      for (int r = 0; r < RL; ++r) t += sh[j][r * Qb + q];  // fixed order
+      g_red_part[((j >> 2) * kRedSlots + slot) * 2048 + c0 + (j & 3)] = t;
+    }
+  }
+}
+// channel quads per CTA of the v4 kernels: as few channel blocks as still give ~2 CTAs per SM
+inline int red_quads_per_cta(int C, int ctas_rows) {
+  int Qb = std::min(C / 4, 256);
+  while (Qb > 8 && (C / 4 / Qb) * ctas_rows < 296) Qb /= 2;
+  return Qb;
+}
+// the "last block folds" ticket of the v4 kernels (1-D thread blocks)
+__device__ __forceinline__ bool last_block_of_column_group_v4() {
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&g_red_ticket[blockIdx.x], 1u);
+    s_last = (t == gridDim.y * gridDim.z - 1);
+    if (s_last) g_red_ticket[blockIdx.x] = 0u;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last;
+}
+
 __global__ void __launch_bounds__(1024)
 bn_stats_kernel(const float* __restrict__ raw, int M, int C, float* __restrict__ mean, float* __restrict__ rstd,
                 float* __restrict__ rmean, float* __restrict__ rvar, int updates) {
@@ -312,12 +382,84 @@ bn_stats_kernel(const float* __restrict__ raw, int M, int C, float* __restrict__
   rmean[c] = rm;
   rvar[c] = rv;
 }
+// Collective fold of the last CTA (256 threads): the sums over the `nsplit` row-split partials of group `grp` for the
+// channels [cb0, cb0 + cn) (cn <= 256, a power of two). 256 / cn threads share a channel (each takes every SL-th slot,
+// 8 independent L2 loads in flight), lanes are combined in a fixed order: deterministic, and ~30x shorter than one
+// thread walking all slots with dependent loads (that serial fold was ~100 us of the full-resolution layers' kernels).
+// Returns the sums to the threads with tid < cn (channel cb0 + tid); every thread of the CTA must call it.
+__device__ __forceinline__ void column_fold2_cta(int cb0, int cn, int grp, int nsplit, double& s1, double& s2) {
+  __shared__ double shf[2][256];
+  const int tid = threadIdx.x;
+  const int SL = 256 / cn;
+  const int cl = tid % cn, sl = tid / cn;
+  double a = 0.0, b = 0.0;
+  const int r0 = grp * nsplit;
+  for (int r = sl; r < nsplit; r += 8 * SL) {
+    double va[8], vb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int rr = r + j * SL;
+      const bool ok = rr < nsplit;
+      va[j] = ok ? __ldcg(&g_red_part[(0 * kRedSlots + r0 + rr) * 2048 + cb0 + cl]) : 0.0;
+      vb[j] = ok ? __ldcg(&g_red_part[(1 * kRedSlots + r0 + rr) * 2048 + cb0 + cl]) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a += va[j]; b += vb[j]; }
+  }
+  __syncthreads();  // (previous call's readers are done)
+  shf[0][tid] = a;
+  shf[1][tid] = b;
+  __syncthreads();
+  s1 = s2 = 0.0;
+  if (tid < cn)
+    for (int l = 0; l < SL; ++l) { s1 += shf[0][l * cn + tid]; s2 += shf[1][l * cn + tid]; }
+}
+
+__global__ void __launch_bounds__(256)
+bn_stats_v4_kernel(const float* __restrict__ raw, int M, int C, int Qb, float* __restrict__ mean, float* __restrict__ rstd,
+                   float* __restrict__ rmean, float* __restrict__ rvar, int updates) {
+  column_partial2_v4(M, C, Qb, [&](int m, int c0, float4& v1, float4& v2) {
+    const float4 x = *reinterpret_cast<const float4*>(raw + static_cast<size_t>(m) * C + c0);
+    v1 = x;
+    v2 = make_float4(x.x * x.x, x.y * x.y, x.z * x.z, x.w * x.w);
+  });
+  if (!last_block_of_column_group_v4()) return;
+  const int nsplit = gridDim.y, groups = gridDim.z;
+  const int cb = blockIdx.x * Qb * 4, cend = min(C, cb + Qb * 4);
+  for (int cb0 = cb; cb0 < cend; cb0 += 256) {
+    const int cn = min(256, cend - cb0);
+    const int c = cb0 + threadIdx.x;
+    const bool mine = static_cast<int>(threadIdx.x) < cn;
+    float rm = mine ? rmean[c] : 0.f, rv = mine ? rvar[c] : 0.f;
+    for (int grp = 0; grp < groups; ++grp) {  // groups = time steps, in order: the running statistics are a recurrence
+      double s1, s2;
+      column_fold2_cta(cb0, cn, grp, nsplit, s1, s2);
+      if (!mine) continue;
+      const double mu = s1 / M;
+      double var = s2 / M - mu * mu;
+      if (var < 0.0) var = 0.0;
+      mean[grp * C + c] = static_cast<float>(mu);
+      rstd[grp * C + c] = static_cast<float>(1.0 / sqrt(var + 1e-5));
+      const double unbiased = var * M / (M - 1);
+      for (int u = 0; u < updates; ++u) {
+        rm = 0.9f * rm + 0.1f * static_cast<float>(mu);
+        rv = 0.9f * rv + 0.1f * static_cast<float>(unbiased);
+      }
+    }
+    if (mine) { rmean[c] = rm; rvar[c] = rv; }
+  }
+}
 cudaError_t launch_bn_stats(const float* raw, int M, int C, float* mean, float* rstd, float* running_mean,
                             float* running_var, int updates, cudaStream_t s, int groups) {
   if (C > 2048 || groups < 1) return cudaErrorInvalidValue;
   int R = red_split(M);
   while (R * groups > kRedSlots) R /= 2;
   if (R < 1) return cudaErrorInvalidValue;
+  if ((C & (C - 1)) == 0 && C >= 32 && C <= 1024) {
+    const int Qb = red_quads_per_cta(C, R * groups);
+    bn_stats_v4_kernel<<<dim3(C / 4 / Qb, R, groups), 256, 0, s>>>(raw, M, C, Qb, mean, rstd, running_mean, running_var, updates);
+    return cudaGetLastError();
+  }
   bn_stats_kernel<<<dim3((C + 31) / 32, R, groups), dim3(32, 32), 0, s>>>(raw, M, C, mean, rstd, running_mean, running_var, updates);
   return cudaGetLastError();
 }
@@ -417,6 +559,66 @@ bn_bwd_sums_kernel(BnBwdArgs a, int M, float* __restrict__ scratch, float* __res
   dbeta[c] += static_cast<float>(t1);
   dgamma[c] += static_cast<float>(t2);
 }
+__global__ void __launch_bounds__(256)
+bn_bwd_sums_v4_kernel(BnBwdArgs a, int M, int Qb, float* __restrict__ scratch, float* __restrict__ dgamma,
+                      float* __restrict__ dbeta) {
+  column_partial2_v4(M, a.C, Qb, [&](int m, int c0, float4& v1, float4& v2) {
+    float4 g;
+    if (!a.upsample) {
+      g = *reinterpret_cast<const float4*>(a.dy + static_cast<size_t>(m) * a.dy_cstride + a.dy_coff + c0);
+    } else {
+      const int x = m % a.W, y = (m / a.W) % a.H;
+      const size_t b = static_cast<size_t>(m) / (a.W * a.H);
+      g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const float4 t = *reinterpret_cast<const float4*>(
+              a.dy + ((b * 2 * a.H + 2 * y + dy) * (2 * a.W) + 2 * x + dx) * a.dy_cstride + a.dy_coff + c0);
+          g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+        }
+    }
+    const int so = (m / a.rows_per_group) * a.C + c0;
+    const float4 r = *reinterpret_cast<const float4*>(a.raw + static_cast<size_t>(m) * a.C + c0);
+    const float4 mu = *reinterpret_cast<const float4*>(a.mean + so), rs = *reinterpret_cast<const float4*>(a.rstd + so);
+    const float4 ga = *reinterpret_cast<const float4*>(a.gamma + c0), be = *reinterpret_cast<const float4*>(a.beta + c0);
+    const float gg[4] = {g.x, g.y, g.z, g.w}, rr[4] = {r.x, r.y, r.z, r.w}, mm[4] = {mu.x, mu.y, mu.z, mu.w};
+    const float ss[4] = {rs.x, rs.y, rs.z, rs.w}, gm[4] = {ga.x, ga.y, ga.z, ga.w}, bt[4] = {be.x, be.y, be.z, be.w};
+    float dz[4], dzx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float xh = (rr[j] - mm[j]) * ss[j];
+      const float bn = xh * gm[j] + bt[j];
+      dz[j] = bn > 0.f ? gg[j] : 0.2f * gg[j];
+      dzx[j] = dz[j] * xh;
+    }
+    v1 = make_float4(dz[0], dz[1], dz[2], dz[3]);
+    v2 = make_float4(dzx[0], dzx[1], dzx[2], dzx[3]);
+  });
+  if (!last_block_of_column_group_v4()) return;
+  const int C = a.C;
+  const int cb = blockIdx.x * Qb * 4, cend = min(C, cb + Qb * 4);
+  for (int cb0 = cb; cb0 < cend; cb0 += 256) {
+    const int cn = min(256, cend - cb0);
+    const int c = cb0 + threadIdx.x;
+    const bool mine = static_cast<int>(threadIdx.x) < cn;
+    double t1 = 0.0, t2 = 0.0;
+    for (int grp = 0; grp < static_cast<int>(gridDim.z); ++grp) {
+      double s1, s2;
+      column_fold2_cta(cb0, cn, grp, gridDim.y, s1, s2);
+      if (!mine) continue;
+      scratch[grp * 2 * C + c] = static_cast<float>(s1);
+      scratch[grp * 2 * C + C + c] = static_cast<float>(s2);
+      t1 += s1;
+      t2 += s2;
+    }
+    if (mine) {
+      dbeta[c] += static_cast<float>(t1);
+      dgamma[c] += static_cast<float>(t2);
+    }
+  }
+}
 // 8 channels per thread (C % 8 == 0): 128-bit loads of dy / raw, one 128-bit bf16 store
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(BnBwdArgs a, int M, const float* __restrict__ scratch, __nv_bfloat16* __restrict__ draw,
@@ -482,7 +684,12 @@ cudaError_t launch_bn_bwd(const float* dy, int dy_cstride, int dy_coff, int upsa
   int R = red_split(Mg);
   while (R * groups > kRedSlots) R /= 2;
   if (R < 1) return cudaErrorInvalidValue;
-  bn_bwd_sums_kernel<<<dim3((C + 31) / 32, R, groups), dim3(32, 32), 0, s>>>(a, Mg, scratch, dgamma, dbeta);
+  if ((C & (C - 1)) == 0 && C >= 32 && C <= 1024 && dy_cstride % 4 == 0 && dy_coff % 4 == 0) {
+    const int Qb = red_quads_per_cta(C, R * groups);
+    bn_bwd_sums_v4_kernel<<<dim3(C / 4 / Qb, R, groups), 256, 0, s>>>(a, Mg, Qb, scratch, dgamma, dbeta);
+  } else {
+    bn_bwd_sums_kernel<<<dim3((C + 31) / 32, R, groups), dim3(32, 32), 0, s>>>(a, Mg, scratch, dgamma, dbeta);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (C % 8 || dy_cstride % 4 || dy_coff % 4) return cudaErrorInvalidValue;
