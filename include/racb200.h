@@ -281,11 +281,33 @@ typedef struct {
                                          2 saturation, 3 hue; -1 = none */
 } rac_augment;
 /* frames: device uint8 (B, T, H, W, 3) as stored / collated; masks: device (B, T, H, W) float32 (mask_is_u8 = 0) or
- * uint8 (1), or NULL; aug: DEVICE rac_augment[B] (one per clip) or NULL (ToTensor only: bit-exact value / 255);
- * images_out (T, B, 3, H, W), masks_out (T, B, 1, H, W) float32, time-first. H x W must be 48 x 64 and `frames`
- * 16-byte aligned. */
+ * uint8 (1), or NULL; aug: DEVICE rac_augment[B] (one per clip) or NULL (no augmentation);
+ * images_out (T, B, 3, 48, 64), masks_out (T, B, 1, 48, 64) float32, time-first. H x W = the STORED frame size:
+ * 48 x 64 (ToTensor only, bit-exact value / 255; `frames` 16-byte aligned) or anything else (e.g. RoboNet's 240 x 320),
+ * in which case the dataset's `tf.Resize((48, 64))` runs first (robonet_dataset.py:58: bilinear, align_corners False,
+ * no antialiasing -- the behaviour of the torchvision 0.8 / 0.9 the reference pins). */
 int rac_process_batch(const uint8_t* frames, const void* masks, int mask_is_u8, int B, int T, int H, int W,
                       const rac_augment* aug, float* images_out, float* masks_out, void* stream);
+
+/* RoboNetDataset._preprocess_states (robonet_dataset.py:302-334), the autograsp column of _load_actions (:173-194) and
+ * process_batch's time-first layout (:434-451) for a collated batch. One record per clip (bounds after
+ * _preprocess_bounds, :222-255 -- computed by the host glue, data.py): */
+typedef struct {
+  int kind;             /* 0 = RoboNet file (states normalised in the bounds: denormalised first), 1 = locobot (raw
+                           metres), 2 = franka (raw metres, mapped onto the locobot frame: xy += frame_diff, z = 0.14) */
+  int camera;           /* 1 = "camera" in cfg.preprocess_action: end-effector position -> camera frame */
+  int grip_col;         /* column of the stored states that holds the gripper reading (the last stored column) */
+  int pad_;
+  double low[5], high[5];    /* normalisation bounds (camera-space box when camera) */
+  double world2cam[16];      /* row-major 4 x 4 (src/utils/camera_calibration.py world_to_camera_dict) */
+  double frame_diff[2];      /* LOCO_FRANKA_DIFF (robonet_dataset.py:22) */
+  double grip_low, grip_high;/* raw_low[4], raw_high[4] of _load_bounds: the two autograsp action values */
+} rac_clip_calib;
+/* states (B, T, R) float32 as loaded (padded to R = cfg.robot_dim), actions (B, T-1, A_in) or NULL; calib: DEVICE
+ * rac_clip_calib[B]; states_out (T, B, R), actions_out (T-1, B, A_out) time-first. A_out == A_in + 1 imputes the
+ * autograsp action column (cfg.impute_autograsp_action). */
+int rac_preprocess_states(const float* states, const float* actions, const rac_clip_calib* calib, int B, int T, int R,
+                          int A_in, int A_out, float* states_out, float* actions_out, void* stream);
 
 /* Test / inspection hook: device pointer and element count of a named internal buffer of the prepared workspace
  * ("h1".."h4", "prior_in", "z", "h_pred", "img", ...). */

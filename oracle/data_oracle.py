@@ -11,7 +11,8 @@ adjust_hue} on float tensors, restated below with plain torch ops:
   blend   = (ratio * a + (1 - ratio) * b).clamp(0, 1); brightness: b = 0; contrast: b = mean(gray); saturation: b = gray
   gray    = 0.2989 r + 0.587 g + 0.114 b
   hue     = rgb -> hsv (Pillow's formulas), h = (h + factor) % 1, hsv -> rgb
-Pinned by tests/golden/data_path.npz (oracle/make_golden_data.py runs the unmodified reference).
+Pinned by tests/golden/data_path.npz (oracle/make_golden_data.py runs the unmodified reference) and, for clips stored
+at another size, tests/golden/dataset_glue.npz (oracle/make_golden_dataset.py).
 Only tests/, __graft_entry__.smoke() and bench.py's CPU baseline may import this module."""
 import math
 
@@ -110,11 +111,17 @@ def color_jitter(x, factors, order):
     return x
 
 
-def preprocess_images_masks(frames_u8, masks, aug=None):
+def preprocess_images_masks(frames_u8, masks, aug=None, out_hw=(48, 64)):
     """One clip. frames (T, H, W, 3) uint8, masks (T, H, W) float32 -> (T, 3, H, W), (T, 1, H, W) float32.
     aug = None or (i, j, th, tw, [brightness, contrast, saturation, hue], order[4])."""
     x = to_tensor(frames_u8)
     m = torch.from_numpy(np.ascontiguousarray(masks, dtype=np.float32)).unsqueeze(1)
+    if tuple(x.shape[-2:]) != tuple(out_hw):
+        # stored at another size: the dataset's tf.Resize((h, w)) right after ToTensor (:58). Plain bilinear, no
+        # antialiasing (torchvision 0.8 / 0.9, see make_golden_dataset.py) = the crop-free case of crop_resize
+        hs, ws = x.shape[-2:]
+        x = crop_resize(x, 0, 0, hs, ws, *out_hw)
+        m = crop_resize(m, 0, 0, hs, ws, *out_hw)
     T, _, H, W = x.shape
     if aug is None:
         return x, m.bool().float()

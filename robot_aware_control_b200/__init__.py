@@ -16,11 +16,13 @@ from .image import zero_robot_region  # noqa: F401
 from .cem import CEMPolicy, TrajectorySampler  # noqa: F401
 from .trainer import SVGTrainer  # noqa: F401
 from .data import process_batch, preprocess_clips, sample_augment  # noqa: F401
+from .data import clip_calibration, preprocess_bounds, preprocess_states_actions  # noqa: F401
 
 __all__ = [
     "SVGConvModel", "CEMPolicy", "TrajectorySampler", "RobotWorldCost", "ImgL2Cost", "ImgDontcareCost",
     "RobotL2Cost", "State", "DemoGoalState", "zero_robot_region", "l1_criterion", "dontcare_l1_criterion",
     "kl_criterion", "robot_mse_criterion", "world_mse_criterion", "svg_config_from", "SVGTrainer",
     "psnr", "ssim", "world_psnr_criterion", "process_batch", "preprocess_clips", "sample_augment",
-    "mse_criterion", "dontcare_mse_criterion", "DeviceRobotModel",
+    "mse_criterion", "dontcare_mse_criterion", "DeviceRobotModel", "clip_calibration", "preprocess_bounds",
+    "preprocess_states_actions",
 ]

@@ -14,8 +14,10 @@
 #include "misc_kernels.cuh"
 
 namespace rac {  // data_kernels.cu
-cudaError_t launch_process_batch(const uint8_t* frames, const void* masks, int mask_u8, int B, int T,
+cudaError_t launch_process_batch(const uint8_t* frames, const void* masks, int mask_u8, int B, int T, int Hs, int Ws,
                                  const rac_augment* aug, float* img_out, float* mask_out, cudaStream_t s);
+cudaError_t launch_preprocess_states(const float* states, const float* actions, const rac_clip_calib* calib, int B, int T,
+                                     int R, int A_in, int A_out, float* states_out, float* actions_out, cudaStream_t s);
 }
 
 namespace {
@@ -1284,12 +1286,21 @@ int rac_ssim(const float* img1, const float* img2, const float* mask, float* map
 int rac_process_batch(const uint8_t* frames, const void* masks, int mask_is_u8, int B, int T, int H, int W,
                       const rac_augment* aug, float* images_out, float* masks_out, void* stream) {
   if (!frames || !images_out || B < 0 || T < 0 || (masks && !masks_out)) return RAC_ERR_INVALID;
-  if (H != 48 || W != 64) return RAC_ERR_UNSUPPORTED;
-  if ((reinterpret_cast<uintptr_t>(frames) & 15) || (masks && !mask_is_u8 && (reinterpret_cast<uintptr_t>(masks) & 15)) ||
+  if (H < 1 || W < 1) return RAC_ERR_INVALID;
+  const bool stored48 = H == 48 && W == 64;  // (16-byte staging loads on that path only)
+  if ((stored48 && ((reinterpret_cast<uintptr_t>(frames) & 15) || (masks && !mask_is_u8 && (reinterpret_cast<uintptr_t>(masks) & 15)))) ||
       (aug && (reinterpret_cast<uintptr_t>(aug) & 7)))
     return RAC_ERR_INVALID;
-  return rac::launch_process_batch(frames, masks, mask_is_u8, B, T, aug, images_out, masks_out,
+  return rac::launch_process_batch(frames, masks, mask_is_u8, B, T, H, W, aug, images_out, masks_out,
                                    static_cast<cudaStream_t>(stream)) == cudaSuccess ? RAC_OK : RAC_ERR_CUDA;
+}
+
+int rac_preprocess_states(const float* states, const float* actions, const rac_clip_calib* calib, int B, int T, int R,
+                          int A_in, int A_out, float* states_out, float* actions_out, void* stream) {
+  if (!states || !calib || !states_out || B < 0 || T < 1 || R < 5 || (actions && (!actions_out || A_in < 1 || A_out < A_in || A_out > A_in + 1)))
+    return RAC_ERR_INVALID;
+  return rac::launch_preprocess_states(states, actions, calib, B, T, R, A_in, A_out, states_out, actions_out,
+                                       static_cast<cudaStream_t>(stream)) == cudaSuccess ? RAC_OK : RAC_ERR_CUDA;
 }
 
 int rac_composite(const float* x_pred4, const float* x_j, float* out, int n, int hw, void* stream) {

@@ -11,8 +11,16 @@ colour jitter, mask binarisation and the time-first layout. The random draws sta
 python's `random` and torch's default generator exactly as the reference does, so a seeded run picks the same crop
 window, factors and transform order.
 
-Not built: reading HDF5 (h5py is not in this image), state / action normalisation (numpy glue of the dataset class),
-stored frames of another size than 48 x 64 (the reference's `tf.Resize` down-scaling before everything else).
+Stored frames of another size than 48 x 64 (RoboNet stores 240 x 320) go through the dataset's `tf.Resize((48, 64))`
+first, inside the same launch (bilinear without antialiasing: the torchvision 0.8 / 0.9 the reference pins).
+
+The per-clip state / action glue of the dataset class (`_load_bounds`, `_load_states`, `_load_actions` with the
+autograsp column, `_preprocess_bounds`, `_preprocess_states`, `_preprocess_actions`; robonet_dataset.py:173-255,
+302-393) is `preprocess_states_actions`: the bounds / calibration records are assembled on the host (a handful of
+numbers per clip, `clip_calibration`), the normalisation, camera-frame transform, action imputation and time-first
+layout of the whole batch are one launch (`rac_preprocess_states`).
+
+Not built: reading HDF5 itself (h5py is not in this image; any loader that yields the stored arrays works).
 """
 import random
 
@@ -75,11 +83,10 @@ def preprocess_clips(frames, masks=None, augment=None, device=None):
     frames = torch.as_tensor(frames)
     if frames.dtype != torch.uint8 or frames.dim() != 5 or frames.shape[-1] != 3:
         raise ValueError("frames must be uint8 (B, T, H, W, 3)")
-    B, T, H, W = (int(s) for s in frames.shape[:4])
-    if (H, W) != (48, 64):
-        raise NotImplementedError("the device data path handles stored 48 x 64 frames")
+    B, T, H, W = (int(s) for s in frames.shape[:4])  # H x W = the stored size; the model's frames are 48 x 64
+    OH, OW = 48, 64
     frames = frames.to(device, non_blocking=True).contiguous()
-    images = torch.empty(T, B, 3, H, W, device=device, dtype=torch.float32)
+    images = torch.empty(T, B, 3, OH, OW, device=device, dtype=torch.float32)
     m_dev = m_out = None
     mask_u8 = 0
     if masks is not None:
@@ -92,12 +99,12 @@ def preprocess_clips(frames, masks=None, augment=None, device=None):
             masks = masks.to(torch.float32)
         mask_u8 = int(masks.dtype == torch.uint8)
         m_dev = masks.to(device, non_blocking=True).contiguous()
-        m_out = torch.empty(T, B, 1, H, W, device=device, dtype=torch.float32)
+        m_out = torch.empty(T, B, 1, OH, OW, device=device, dtype=torch.float32)
     aug_dev = None
     if augment is not None:
         if len(augment) != B:
             raise ValueError(f"{len(augment)} augmentation tuples for {B} clips")
-        aug_dev = torch.from_numpy(pack_augment(augment, H, W).view(np.uint8).reshape(-1)).to(device)
+        aug_dev = torch.from_numpy(pack_augment(augment, OH, OW).view(np.uint8).reshape(-1)).to(device)
     if B * T:
         _lib.check(lib.rac_process_batch(_lib.ptr(frames), _lib.ptr(m_dev) if m_dev is not None else None, mask_u8, B, T,
                                          H, W, _lib.ptr(aug_dev) if aug_dev is not None else None, _lib.ptr(images),
@@ -124,3 +131,97 @@ def process_batch(data, device, augment=None):
         if k in data and not (raw and k in ("images", "masks")):
             out[k] = torch.as_tensor(data[k]).transpose(1, 0).to(device, non_blocking=True)
     return out
+
+
+# ---------------------------------------------------------------------------------------------- states / actions
+LOCO_FRANKA_DIFF = (-0.365, -0.06103333)  # robonet_dataset.py:22
+CLIP_CALIB_DTYPE = np.dtype([("kind", np.int32), ("camera", np.int32), ("grip_col", np.int32), ("pad_", np.int32),
+                             ("low", np.float64, 5), ("high", np.float64, 5), ("world2cam", np.float64, 16),
+                             ("frame_diff", np.float64, 2), ("grip_low", np.float64), ("grip_high", np.float64)], align=True)
+assert CLIP_CALIB_DTYPE.itemsize == 256  # rac_clip_calib (include/racb200.h)
+
+
+def load_bounds(robot_viewpoint, file_low=None, file_high=None):
+    """RoboNetDataset._load_bounds (:196-206): fixed workspace box for the locobot / franka data, the file's
+    low_bound / high_bound otherwise."""
+    if "locobot" in robot_viewpoint or "franka" in robot_viewpoint:
+        return (np.array([0.015, -0.3, 0.1, 0, 0], dtype=np.float32), np.array([0.55, 0.3, 0.4, 1, 1], dtype=np.float32))
+    if file_low is None or file_high is None:
+        raise ValueError(f"{robot_viewpoint}: RoboNet files carry their bounds (low_bound / high_bound)")
+    return np.asarray(file_low), np.asarray(file_high)
+
+
+def preprocess_bounds(low, high, preprocess_action="raw", world2cam=None):
+    """RoboNetDataset._preprocess_bounds (:222-255): with a camera-frame action space the workspace box is projected
+    into the camera frame and its axis-aligned hull becomes the normalisation box."""
+    low, high = np.array(low, copy=True), np.array(high, copy=True)
+    if "camera" in preprocess_action:
+        if world2cam is None:
+            raise ValueError("a camera-frame preprocess_action needs the world-to-camera matrix of the viewpoint")
+        corners = np.array([[x, y, z, 1.0] for x in (low[0], high[0]) for y in (low[1], high[1]) for z in (low[2], high[2])]).T
+        cam = (np.asarray(world2cam, np.float64) @ corners).T[:, :3]
+        low[:3] = cam.min(0)
+        high[:3] = cam.max(0)
+    return low, high
+
+
+def clip_calibration(robot_viewpoint, preprocess_action="raw", file_low=None, file_high=None, world2cam=None,
+                     stored_state_dim=5):
+    """One rac_clip_calib record (numpy, CLIP_CALIB_DTYPE) for a clip of `robot_viewpoint`: what _load_bounds and
+    _preprocess_bounds compute per __getitem__ (:104-121)."""
+    raw_low, raw_high = load_bounds(robot_viewpoint, file_low, file_high)
+    low, high = preprocess_bounds(raw_low, raw_high, preprocess_action, world2cam)
+    rec = np.zeros((), CLIP_CALIB_DTYPE)
+    rec["kind"] = 1 if "locobot" in robot_viewpoint else (2 if "franka" in robot_viewpoint else 0)
+    rec["camera"] = int("camera" in preprocess_action)
+    rec["grip_col"] = stored_state_dim - 1
+    rec["low"], rec["high"] = np.asarray(low, np.float64)[:5], np.asarray(high, np.float64)[:5]
+    rec["world2cam"] = (np.eye(4) if world2cam is None else np.asarray(world2cam, np.float64)).reshape(16)
+    rec["frame_diff"] = LOCO_FRANKA_DIFF
+    rec["grip_low"], rec["grip_high"] = float(raw_low[4]), float(raw_high[4])
+    return rec
+
+
+def preprocess_states_actions(states, actions, calibs, robot_dim=5, action_dim=None, preprocess_action="raw",
+                              impute_autograsp_action=True, device=None):
+    """Collated stored states (B, T, S) and actions (B, T-1, A) -> what the reference dataset + process_batch hand to
+    the trainer: normalised (camera-frame) states (T, B, robot_dim) and actions (T-1, B, action_dim), float32 on the
+    device, time-first. `calibs`: one clip_calibration() record per clip. Raises like the reference for an action
+    width that cannot be reconciled (:193-194) or a preprocess_action it does not implement (:341-352)."""
+    lib = _lib.load()
+    device = torch.device("cuda") if device is None else torch.device(device)
+    if preprocess_action not in ("raw", "camera_raw"):
+        raise NotImplementedError(preprocess_action)
+    states = torch.as_tensor(np.asarray(states)).to(torch.float32)
+    B, T, S = (int(v) for v in states.shape)
+    if len(calibs) != B:
+        raise ValueError(f"{len(calibs)} calibration records for {B} clips")
+    if S > robot_dim:
+        raise AssertionError("stored states are wider than cfg.robot_dim")  # (the reference asserts, :211)
+    cal = np.stack([np.asarray(c) for c in calibs]).astype(CLIP_CALIB_DTYPE)
+    if np.any(cal["grip_col"] >= S):
+        raise ValueError("grip_col beyond the stored state width")
+    if S < robot_dim:  # _load_states pads with zero columns (:210-213)
+        states = torch.nn.functional.pad(states, (0, robot_dim - S))
+    states = states.to(device).contiguous()
+    a_dev = a_out = None
+    A_in = A_out = 0
+    if actions is not None:
+        actions = torch.as_tensor(np.asarray(actions)).to(torch.float32)
+        A_in = int(actions.shape[-1])
+        A_out = A_in if action_dim is None else int(action_dim)
+        if tuple(actions.shape[:2]) != (B, T - 1):
+            raise ValueError(f"actions must be (B, T-1, A) = {(B, T - 1)}, got {tuple(actions.shape)}")
+        if not (A_out == A_in or (impute_autograsp_action and A_out == A_in + 1)):
+            raise ValueError(f"file adim {A_in}, target adim {A_out}")
+        a_dev = actions.to(device).contiguous()
+        a_out = torch.empty(T - 1, B, A_out, device=device, dtype=torch.float32)
+    s_out = torch.empty(T, B, robot_dim, device=device, dtype=torch.float32)
+    cal_dev = torch.from_numpy(cal.view(np.uint8).reshape(-1)).to(device)
+    _lib.check(lib.rac_preprocess_states(_lib.ptr(states), _lib.ptr(a_dev), _lib.ptr(cal_dev), B, T, robot_dim, A_in, A_out,
+                                         _lib.ptr(s_out), _lib.ptr(a_out), _lib.stream_ptr()), None, "rac_preprocess_states")
+    if a_out is not None and preprocess_action == "camera_raw":
+        # _make_camera_actions replaces the recorded actions by zeros before it uses them (`np.zeros_like`, :375): the
+        # camera-frame displacement it returns is identically zero in every column. Reproduced, not repaired.
+        a_out.zero_()
+    return s_out, a_out

@@ -75,8 +75,9 @@ def test_training_batch_vs_oracle_and_dict_api():
     assert torch.equal(o3["images"], out["images"])
     e = process_batch({"images": torch.zeros(0, T, 48, 64, 3, dtype=torch.uint8)}, "cuda")
     assert e["images"].shape == (T, 0, 3, 48, 64)
-    with pytest.raises(NotImplementedError):
-        process_batch({"images": torch.zeros(1, 1, 64, 85, 3, dtype=torch.uint8)}, "cuda")
+    # another stored size goes through the dataset's Resize first (test_stored_size_frames_vs_reference)
+    o4 = process_batch({"images": torch.zeros(1, 1, 64, 85, 3, dtype=torch.uint8)}, "cuda")
+    assert o4["images"].shape == (1, 1, 3, 48, 64) and float(o4["images"].abs().max()) == 0.0
 
 
 def test_feeds_the_training_step():
@@ -98,3 +99,56 @@ def test_feeds_the_training_step():
     batch = process_batch(data, "cuda", augment=[sample_augment() for _ in range(B)])
     out = trainer.train_step(batch)
     assert np.isfinite(out["recon_loss"]) and np.isfinite(out["kld"])
+
+
+@pytest.fixture(scope="module")
+def glue(golden_dir):
+    return np.load(os.path.join(golden_dir, "dataset_glue.npz"))
+
+
+@pytest.mark.parametrize("tag", ["s96", "s240"])
+def test_stored_size_frames_vs_reference(glue, tag):
+    """Clips stored at 96 x 128 / 240 x 320 (RoboNet's size): tf.Resize((48, 64)) of the reference dataset (bilinear, no
+    antialiasing: the pinned torchvision) + the rest of _preprocess_images_masks, in the same launch."""
+    from robot_aware_control_b200 import preprocess_clips
+
+    frames, masks = glue[f"{tag}_frames"], glue[f"{tag}_masks"]
+    x, m = preprocess_clips(frames, masks)
+    assert x.shape == (2, frames.shape[0], 3, 48, 64)
+    np.testing.assert_allclose(x.cpu().numpy(), glue[f"{tag}_images_plain"], rtol=0, atol=2e-6)
+    assert np.array_equal(m.cpu().numpy(), glue[f"{tag}_masks_plain"])
+    augs = [do.params_to_aug(r) for r in glue[f"{tag}_params"]]
+    x, m = preprocess_clips(frames, masks, augs)
+    np.testing.assert_allclose(x.cpu().numpy(), glue[f"{tag}_images_aug"], rtol=0, atol=3e-5)
+    assert (m.cpu().numpy() != glue[f"{tag}_masks_aug"]).mean() < 1e-3
+    xo, mo = do.process_batch(frames, masks, augs)
+    np.testing.assert_allclose(x.cpu().numpy(), xo.numpy(), rtol=0, atol=3e-5)
+    # uint8 masks: same result
+    x2, m2 = preprocess_clips(frames, masks.astype(np.uint8), augs)
+    assert torch.equal(x2, x) and torch.equal(m2, m)
+
+
+def test_states_actions_vs_reference(glue):
+    """RoboNetDataset._load_states / _load_actions / _preprocess_bounds / _preprocess_states / _preprocess_actions +
+    process_batch for all three robot kinds, world and camera frame, against the reference's own outputs."""
+    from robot_aware_control_b200.data import clip_calibration, preprocess_bounds, preprocess_states_actions
+
+    for tag, robot, mode, adim in zip(glue["case_tags"], glue["case_robots"], glue["case_modes"], glue["case_action_dims"]):
+        tag, robot, mode = str(tag), str(robot), str(mode)
+        g = lambda k: glue[f"{tag}_{k}"]
+        fs, fa = g("file_states"), g("file_actions")
+        low, high = preprocess_bounds(g("raw_low"), g("raw_high"), mode, g("world2cam"))
+        assert np.array_equal(low, g("low")) and np.array_equal(high, g("high"))
+        cal = clip_calibration(robot, mode, g("raw_low"), g("raw_high"), g("world2cam"), stored_state_dim=fs.shape[1])
+        # a batch of two clips (the second one time-reversed) exercises the batch-first -> time-first layout
+        states = np.stack([fs, fs[::-1]])
+        actions = np.stack([fa, fa[::-1]])
+        s, a = preprocess_states_actions(states, actions, [cal, cal], robot_dim=5, action_dim=int(adim), preprocess_action=mode)
+        assert s.shape == (fs.shape[0], 2, 5) and a.shape == (fa.shape[0], 2, int(adim)) and s.is_cuda
+        np.testing.assert_allclose(s[:, 0].cpu().numpy(), g("states"), rtol=0, atol=1e-6, err_msg=tag)
+        np.testing.assert_allclose(s[:, 1].cpu().numpy()[::-1], g("states"), rtol=0, atol=1e-6, err_msg=tag)
+        np.testing.assert_allclose(a[:, 0].cpu().numpy(), g("actions"), rtol=0, atol=1e-7, err_msg=tag)
+    with pytest.raises(ValueError):  # the reference raises for an action width it cannot reconcile (:193-194)
+        preprocess_states_actions(states, actions, [cal, cal], action_dim=actions.shape[-1] + 2)
+    with pytest.raises(NotImplementedError):  # state_infer / camera_state_infer (:341-352)
+        preprocess_states_actions(states, actions, [cal, cal], preprocess_action="state_infer")
