@@ -174,7 +174,7 @@ def run_reference_arm(args):
         "note": "reference arm = CPU port of the reference's own PyTorch path (oracle/svg_oracle.py, pinned to "
                 "reference outputs in tests/golden); the reference is Python and /root/reference is absent on this box",
     }
-    print(json.dumps(line))
+    emit_json(line)
 
 
 def workload_config(n_gpus, robot_aware=False, n_total=None, steps=L_STEPS):
@@ -264,7 +264,7 @@ def run_train_reference_arm(args):
     for _ in range(steps):
         tr.train_step(batch, eps[0], eps[1])
     per = (time.perf_counter() - t0) / steps
-    print(json.dumps({"impl": "reference", "metric": "svg_train_samples_per_sec", "value": Bt / per, "unit": "samples/s",
+    emit_json(({"impl": "reference", "metric": "svg_train_samples_per_sec", "value": Bt / per, "unit": "samples/s",
                       "n_gpus": args.gpus, "steps": steps, "warmup": 0, "ms_per_step": per * 1e3, "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": {"workload": f"SVG training step, batch {Bt}, n_past 1 / n_future 5, g_dim {G_DIM} z_dim {Z_DIM}, l1, Adam"},
@@ -294,6 +294,7 @@ def train_leg(dev, rank, world, group, robot_aware, scheduled_sampling, group_no
     model.load_state_dict(so.make_state_dict(cfg, 0))
     model.train()
     trainer = SVGTrainer(cfg, model, process_group=group)
+    trainer.overlap_allreduce = os.environ.get("RAC_TRAIN_NO_OVERLAP", "0") != "1"  # (A/B switch)
     Bt, T = 16, 6
     g = torch.Generator(device="cuda").manual_seed(rank)
     batch = {"images": torch.rand(T, Bt, 3, 48, 64, device=dev, generator=g),
@@ -341,12 +342,15 @@ def train_leg(dev, rank, world, group, robot_aware, scheduled_sampling, group_no
                     + ("dontcare_l1 robot-aware (mask + future mask + robot state)" if robot_aware else "l1 vanilla")
                     + (", scheduled sampling k=4000" if scheduled_sampling else "")
                     + (", lstm_group_norm" if group_norm else "")
-                    + ", Adam, data parallel (flat fp32 gradient all-reduce over NCCL)",
+                    + ", Adam, data parallel (fp32 gradient all-reduce over NCCL: the ConvLSTM layers' ranges start "
+                      "underneath the backward pass, the rest afterwards)",
         "baseline_config": "configs[3]" if (robot_aware and scheduled_sampling) else ("configs[0]" if not robot_aware else None),
         "algorithmic_tflop_per_step_per_gpu": TRAIN_TFLOP_PER_STEP,
         "achieved_tflops_per_gpu": TRAIN_TFLOP_PER_STEP / (per * 1e-3), "last_losses": loss,
         "gpu_launches_per_step": (model.launch_count() - launches0) / steps,
+        # (time between the end of the backward pass and the start of Adam: what the overlap did not hide)
         "allreduce_ms_per_step": ar_ms / steps, "allreduce_share": ar_ms / float(ms.item()),
+        "allreduce_overlapped": bool(trainer.overlap_allreduce) if world > 1 else None,
         "allreduce_bytes": int(trainer.grads.numel()) * 4 if world > 1 else 0,
         "ddp_params_identical_across_ranks": identical}
     del trainer, model
@@ -365,16 +369,40 @@ def run_train_bench(args):
                 "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": {"workload": r["workload"]}}
         line.update({k: v for k, v in r.items() if k not in line and k != "workload"})
-        print(json.dumps(line))
+        emit_json(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 def nccl_to_stderr():
-    """stdout must carry exactly one JSON line, so whatever NCCL prints (version banner, NCCL_DEBUG=INFO topology /
-    rank lines the driver may ask for) goes to stderr; NCCL_DEBUG itself is left as the caller set it."""
+    """stdout must carry exactly one JSON line, so whatever NCCL prints (NCCL_DEBUG=INFO topology / rank lines the
+    driver may ask for) goes to stderr; NCCL_DEBUG itself is left as the caller set it."""
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    claim_stdout()
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """NCCL's version banner ("NCCL version 2.28.9+cuda12.9") is written to file descriptor 1 whatever NCCL_DEBUG_FILE
+    says (seen in front of the JSON line of a 2-GPU run). From here on fd 1 IS stderr for every library in the process;
+    the one JSON line goes to the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(line):
+    text = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(text.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, text)
 
 
 def dist_setup():
@@ -624,7 +652,7 @@ def main():
         "roofline_whole_step": whole, "roofline_cost_kernel": cost_roof, "cpu_baseline": cpu,
     }
     line.update(extras)
-    print(json.dumps(line))
+    emit_json(line)
     if world > 1:
         dist.destroy_process_group()
 

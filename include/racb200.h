@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RAC_ABI_VERSION 6
+#define RAC_ABI_VERSION 7
 
 typedef enum {
   RAC_OK = 0,
@@ -330,6 +330,9 @@ typedef struct {
    * hh_gates.0 entries only: gamma_off / beta_off above are then the GroupNorm(16, 4g) affine of ih_gates.1 /
    * hh_gates.1, and on the ih entry these two are the cell's c_norm weight / bias */
   long long cnorm_gamma_off, cnorm_beta_off;
+  /* the contiguous range of the flat gradient buffer that holds this convolution's weight (+ bias) gradient and
+   * nothing else: final as soon as the layer's weight gradient has been unpacked (see rac_train_batch.grads_ready) */
+  long long grad_off, grad_count;
 } rac_train_layer;
 
 typedef struct {
@@ -364,6 +367,14 @@ typedef struct {
                               so that a resumed run or a re-created state never replays earlier noise */
   const float* batch_weight; /* (B) or NULL: cfg.load_movement_info weighting of the l1 / dontcare_l1 loss
                               (trainer.py:426-429; losses.py:13-19,35-50) */
+  /* Data-parallel overlap (NULL = off): called on the host, while rac_train_forward_backward is still enqueueing,
+   * right after the kernels that FINISH grads[off, off + count) have been put on the stream -- the weight gradient
+   * of a large layer (>= grads_ready_min elements; the ConvLSTM gate convolutions: 89 % of all parameters), which
+   * BPTT completes long before the encoder's. The caller starts its all-reduce of that range there (stream-ordered
+   * after everything enqueued so far) and it runs underneath the rest of the backward pass. */
+  void (*grads_ready)(void* user, long long off, long long count);
+  void* grads_ready_user;
+  long long grads_ready_min;
 } rac_train_batch;
 
 int rac_train_create(rac_handle* h, const rac_train_config* cfg,
@@ -377,6 +388,9 @@ int rac_train_forward_backward(rac_handle* h, const rac_train_batch* batch, void
 int rac_train_debug_buffer(rac_handle* h, const char* name, int step, void** ptr);
 /* params <- Adam(params, grads) */
 int rac_train_adam_step(rac_handle* h, void* stream);
+/* Factor applied to every gradient inside the Adam kernel (1 / world size after a SUM all-reduce: saves a pass over
+ * the gradient buffer). Stays in force until changed; rac_train_create resets it to 1. */
+int rac_train_set_grad_scale(rac_handle* h, float scale);
 /* Number of Adam steps already taken (the t of the bias corrections). rac_train_create starts at 0: a caller that
  * re-creates the training state (another batch shape) or resumes from a checkpoint (torch.optim.Adam state "step",
  * trainer.py:829-896) restores it here; the moments themselves live in the caller's adam_m / adam_v. */

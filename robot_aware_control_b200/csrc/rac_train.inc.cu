@@ -105,6 +105,9 @@ struct TrainState {
   const float *ext_dx4 = nullptr, *ext_dmu = nullptr, *ext_dlv = nullptr, *ext_dmu_p = nullptr, *ext_dlv_p = nullptr;
   float* ext_dimg = nullptr;
   int bwd_next = -1;                  // step API: the time step rac_train_step_backward must be called for next
+  const rac_train_batch* cur_bt = nullptr;  // the batch of the running rac_train_forward_backward (grads_ready callback)
+  bool unpacked[RAC_L_COUNT_GN] = {};       // layers whose weight gradient is already in the flat buffer
+  float grad_scale = 1.f;
   int per_step = 0;                   // RAC_TRAIN_PER_STEP=1: never batch the time steps (A/B measurements, cross-checks)
   int dgrad_bt = 1;                   // dgrad reads the forward weight packing as an MN-major operand (0: transposed copy Wd)
   float* wg_part = nullptr;           // split-K partials of the layer being processed
@@ -457,6 +460,14 @@ int conv_backward(rac_handle* h, TrainState* T, int layer, int H, int W, const s
       if (!s.base0) s.base0 = s.p;  // xs are the inputs of step t0 == 0
     CKR(wgrad_implicit(h, T, L, H, W, x0, st));
     if (L.d.bias_off) CK(launch_bias_grad(L.dyT, static_cast<int>(S * M), L.kpad, L.n_packed, L.d.bias_off, T->grads, st));
+    // data-parallel overlap: a large layer's gradient goes to the flat buffer now and is handed to the caller's all-reduce
+    const rac_train_batch* bt = T->cur_bt;
+    if (bt && bt->grads_ready && L.d.grad_count > 0 && L.d.grad_count >= bt->grads_ready_min) {
+      CK(launch_unpack_grads(L.dwp, L.d.row_off, L.d.col_off, L.n_packed, L.taps, L.ctot, L.d.flip, T->grads, st));
+      h->launches++;
+      T->unpacked[layer] = true;
+      bt->grads_ready(bt->grads_ready_user, L.d.grad_off, L.d.grad_count);
+    }
   }
   // ---- dgrad: dX = conv(dY, Wd)
   if (nseg > 0) {
@@ -1198,6 +1209,8 @@ int rac_train_forward_backward(rac_handle* h, const rac_train_batch* bt, void* s
   const size_t M3 = static_cast<size_t>(B) * 48;
   CKR(train_prologue(h, T, st));
   CK(cudaMemsetAsync(bt->losses, 0, sizeof(float) * 4, st));
+  T->cur_bt = bt;
+  for (bool& u : T->unpacked) u = false;
   T->step_api = 0;
   T->active_steps = S;
   // ---- reparameterisation noise of all steps (the tape is time-major: one copy / one fill per tensor)
@@ -1271,11 +1284,13 @@ int rac_train_forward_backward(rac_handle* h, const rac_train_batch* bt, void* s
       CKR(backward_encoder(h, T, bt, one, st));
     }
   }
-  // ---- packed weight gradients -> flat parameter layout
+  // ---- packed weight gradients -> flat parameter layout (layers not handed over earlier)
   for (int i = 1; i < T->nlayers; ++i) {
     TLayer& L = T->L[i];
+    if (T->unpacked[i]) continue;
     CK(launch_unpack_grads(L.dwp, L.d.row_off, L.d.col_off, L.n_packed, L.taps, L.ctot, L.d.flip, T->grads, st));
   }
+  T->cur_bt = nullptr;
   return RAC_OK;
 }
 
@@ -1445,7 +1460,14 @@ int rac_train_adam_step(rac_handle* h, void* stream) {
   TrainState* T = static_cast<TrainState*>(h->train);
   T->adam_t += 1;
   CK(launch_adam(T->params, T->grads, T->m, T->v, T->cfg.n_params, T->cfg.lr, T->cfg.beta1, T->cfg.beta2,
-                 T->cfg.adam_eps, T->adam_t, static_cast<cudaStream_t>(stream)));
+                 T->cfg.adam_eps, T->adam_t, static_cast<cudaStream_t>(stream), T->grad_scale));
+  return RAC_OK;
+}
+
+int rac_train_set_grad_scale(rac_handle* h, float scale) {
+  if (!h || !h->train) return fail(h, RAC_ERR_STATE, "rac_train_create first");
+  if (!(scale > 0.f)) return fail(h, RAC_ERR_INVALID, "gradient scale %g", scale);
+  static_cast<TrainState*>(h->train)->grad_scale = scale;
   return RAC_OK;
 }
 

@@ -1073,9 +1073,11 @@ cudaError_t launch_cast_bf16(const float* src, long long n, __nv_bfloat16* dst, 
 // grid-stride over a grid of a few CTAs per SM, streaming cache hints (nothing is re-read before the next step)
 __global__ void __launch_bounds__(512)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-            long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt) {
+            long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float gscale) {
   const float step = lr / bc1;
+  // gscale: 1 / world size after a SUM all-reduce (x * 1.0f is exact, so the single-GPU update is unchanged)
   auto upd = [&](float& pi, float gi, float& mi, float& vi) {
+    gi *= gscale;
     mi = b1 * mi + (1.f - b1) * gi;
     vi = b2 * vi + (1.f - b2) * gi * gi;
     pi -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
@@ -1103,13 +1105,13 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
 }
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
-                        float eps, int t, cudaStream_t s) {
+                        float eps, int t, cudaStream_t s, float grad_scale) {
   const float bc1 = 1.f - powf(b1, static_cast<float>(t));
   const float bc2 = sqrtf(1.f - powf(b2, static_cast<float>(t)));
   if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
        reinterpret_cast<uintptr_t>(v)) & 15)
     return cudaErrorInvalidValue;
-  adam_kernel<<<148 * 8, 512, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2);
+  adam_kernel<<<148 * 8, 512, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2, grad_scale);
   return cudaGetLastError();
 }
 

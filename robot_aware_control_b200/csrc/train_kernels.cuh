@@ -124,7 +124,7 @@ cudaError_t launch_cast_bf16(const float* src, long long n, __nv_bfloat16* dst, 
 
 // ---- optimiser (torch.optim.Adam, no weight decay) and noise
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
-                        float eps, int t, cudaStream_t s);
+                        float eps, int t, cudaStream_t s, float grad_scale = 1.f);
 cudaError_t launch_normal_fill(float* dst, long long n, unsigned long long seed, unsigned int ctr, cudaStream_t s);
 cudaError_t launch_sum_f32(const float* src, int n, float* dst_accum, cudaStream_t s);
 // dst[i] = off[i] >= 0 ? params[off[i]] : 0   (packed bias vector of a convolution)

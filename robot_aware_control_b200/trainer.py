@@ -10,7 +10,9 @@ robonet_dataset.py:434-451). Returned dict = the reference's logged losses (divi
 Parameters, BatchNorm running statistics, gradients and Adam moments live in flat fp32 CUDA tensors; the model's
 nn.Parameters are VIEWS into them, so `model.state_dict()` / checkpoints always see the trained values.
 Data parallel (new, the reference is single-process): pass `process_group`; every rank runs its own batch of B, the
-flat gradient buffer is all-reduced (NCCL) and averaged before the Adam update, BatchNorm statistics stay per rank.
+flat gradient buffer is all-reduced (NCCL, SUM; the 1 / world factor is applied inside the Adam kernel) -- the ConvLSTM
+gate convolutions (89 % of the parameters, whose BPTT finishes long before the encoder's) as soon as their gradient is
+complete, underneath the rest of the backward pass, the remainder afterwards. BatchNorm statistics stay per rank.
 
 Scheduled sampling follows the reference (same probability schedule, same global numpy generator); when the model's
 own prediction is fed back, its gradient flows into the previous step as in the reference (`x_pred.clone()`).
@@ -58,6 +60,12 @@ def _layer_tables(model, offsets, boffsets):
             b_off = offsets[f"{prefix}.bias"]
             b = [(b_off + cs) if cs >= 0 else -1 for cs in col_src] + [-1] * (n_packed - len(col_src))
         e = dict(row_off=rows, col_off=cols(splits, k2), bias_off=b, flip=0, w_off=w_off)
+        # the weight (and, when it directly follows in the flat buffer, the bias) of this convolution: nothing else
+        # writes that gradient range, so it is final once the layer's weight gradient has been unpacked
+        cnt = cout * cin * k2
+        if bias and offsets[f"{prefix}.bias"] == w_off + cnt:
+            cnt += cout
+        e.update(grad_off=w_off, grad_count=cnt)
         if bn is not None:
             e.update(gamma_off=offsets[f"{prefix}.main.1.weight"], beta_off=offsets[f"{prefix}.main.1.bias"],
                      rmean_off=boffsets[f"{prefix}.main.1.running_mean"], rvar_off=boffsets[f"{prefix}.main.1.running_var"])
@@ -115,7 +123,8 @@ class RacTrainLayer(C.Structure):
     _fields_ = [("row_off", C.c_void_p), ("col_off", C.c_void_p), ("bias_off", C.c_void_p),
                 ("gamma_off", C.c_longlong), ("beta_off", C.c_longlong), ("rmean_off", C.c_longlong),
                 ("rvar_off", C.c_longlong), ("w_off", C.c_longlong), ("flip", C.c_int),
-                ("cnorm_gamma_off", C.c_longlong), ("cnorm_beta_off", C.c_longlong)]
+                ("cnorm_gamma_off", C.c_longlong), ("cnorm_beta_off", C.c_longlong),
+                ("grad_off", C.c_longlong), ("grad_count", C.c_longlong)]
 
 
 class RacTrainConfig(C.Structure):
@@ -128,7 +137,28 @@ class RacTrainConfig(C.Structure):
 class RacTrainBatch(C.Structure):
     _fields_ = [("images", C.c_void_p), ("masks", C.c_void_p), ("states", C.c_void_p), ("actions", C.c_void_p),
                 ("eps_prior", C.c_void_p), ("eps_post", C.c_void_p), ("seed", C.c_ulonglong), ("losses", C.c_void_p),
-                ("true_token", C.c_void_p), ("noise_step", C.c_ulonglong), ("batch_weight", C.c_void_p)]
+                ("true_token", C.c_void_p), ("noise_step", C.c_ulonglong), ("batch_weight", C.c_void_p),
+                ("grads_ready", C.c_void_p), ("grads_ready_user", C.c_void_p), ("grads_ready_min", C.c_longlong)]
+
+
+GRADS_READY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_longlong, C.c_longlong)
+OVERLAP_MIN_ELEMS = 4 << 20  # layers with at least this many weights are all-reduced while the backward pass runs
+
+
+def complement_ranges(done, n):
+    """Sorted disjoint (offset, count) ranges covering [0, n) minus the `done` ranges."""
+    out, pos = [], 0
+    for off, cnt in sorted(done):
+        if off < pos:
+            raise ValueError("overlapping gradient ranges")
+        if off > pos:
+            out.append((pos, off - pos))
+        pos = off + cnt
+    if pos > n:
+        raise ValueError("gradient range beyond the buffer")
+    if pos < n:
+        out.append((pos, n - pos))
+    return out
 
 
 def adam_state_dict(m, v, steps_taken, layout, lr, beta1):
@@ -198,6 +228,9 @@ class SVGTrainer:
         self._fixed_skip = int(not c.last_frame_skip)
         self.process_group = process_group
         self.allreduce_events = None
+        self.overlap_allreduce = True   # start the all-reduce of the large layers underneath the backward pass
+        self._grad_scale_world = 1
+        self._pending = []
         self._lib = _lib.load()
         dev = model._device
         # ---- flat fp32 storage; the module's parameters / running stats become views into it
@@ -255,6 +288,7 @@ class SVGTrainer:
                 setattr(layers[i], f, t.get(f, -1))
             layers[i].w_off = t["w_off"]
             layers[i].flip = t["flip"]
+            layers[i].grad_off, layers[i].grad_count = t.get("grad_off", 0), t.get("grad_count", 0)
         self._layers = layers
         self._created_for = None
         self._lr = float(getattr(config, "lr", 1e-4))
@@ -304,6 +338,7 @@ class SVGTrainer:
                                               _lib.ptr(self.adam_v)), m.handle, "rac_train_create")
         # the bias-correction step count survives a re-creation (new batch shape, new hyper-parameters, resume)
         _lib.check(self._lib.rac_train_set_adam_step(m.handle, self._adam_t), m.handle, "rac_train_set_adam_step")
+        self._grad_scale_world = 1  # (a fresh training state scales by 1)
         self._created_for = (B, S)
 
     def forward_backward(self, batch):
@@ -347,21 +382,44 @@ class SVGTrainer:
                            seed=self._seed, losses=_lib.ptr(self.losses),
                            true_token=None if all(tokens) else tokens.ctypes.data, noise_step=self._step,
                            batch_weight=_lib.ptr(bw))
+        self._pending = []  # (offset, count, Work) of the all-reduces started underneath the backward pass
+        if self._dp_world() > 1 and self.overlap_allreduce:
+            def ready(_user, off, count):
+                # runs on this thread while the library is still enqueueing: NCCL orders the collective after
+                # everything enqueued on the current stream so far and runs it on its own stream
+                w = dist.all_reduce(self.grads[off:off + count], group=self.process_group, async_op=True)
+                self._pending.append((int(off), int(count), w))
+            self._ready_cb = GRADS_READY_FN(ready)  # (kept alive for the duration of the call)
+            bt.grads_ready = C.cast(self._ready_cb, C.c_void_p)
+            bt.grads_ready_min = OVERLAP_MIN_ELEMS
         _lib.check(self._lib.rac_train_forward_backward(m.handle, C.byref(bt), _lib.stream_ptr()), m.handle,
                    "rac_train_forward_backward")
         self._keep_batch = (images, actions, masks, states, eps_p, eps_q, bw)  # alive until the stream has consumed them
         return self.losses
 
+    def _dp_world(self):
+        return dist.get_world_size(self.process_group) if self.process_group is not None else 1
+
     def optimizer_step(self):
         m = self.model
-        if self.process_group is not None and dist.get_world_size(self.process_group) > 1:
-            ev = self.allreduce_events  # optional (start, end) CUDA events: bench.py reports the all-reduce share
+        world = self._dp_world()
+        if world > 1:
+            ev = self.allreduce_events  # optional (start, end) CUDA events: bench.py reports the EXPOSED all-reduce time
             if ev is not None:
                 ev[0].record()
-            dist.all_reduce(self.grads, group=self.process_group)
-            self.grads.div_(dist.get_world_size(self.process_group))
+            # the large layers were handed to NCCL while BPTT was still running (forward_backward); what is left is the
+            # complement of their ranges. The mean is taken inside the Adam kernel (gradient scale 1 / world).
+            pending = getattr(self, "_pending", [])
+            for off, cnt in complement_ranges([(o, c) for o, c, _ in pending], self.grads.numel()):
+                dist.all_reduce(self.grads[off:off + cnt], group=self.process_group)
+            for _, _, w in pending:
+                w.wait()
+            self._pending = []
             if ev is not None:
                 ev[1].record()
+        if world != self._grad_scale_world:
+            _lib.check(self._lib.rac_train_set_grad_scale(m.handle, 1.0 / world), m.handle, "rac_train_set_grad_scale")
+            self._grad_scale_world = world
         _lib.check(self._lib.rac_train_adam_step(m.handle, _lib.stream_ptr()), m.handle, "rac_train_adam_step")
         m._packed_dirty = True  # the eval-mode packed copy (folded BatchNorm) is stale now
         self._tracked.add_(self._tracked_inc, alpha=self._created_for[1])  # num_batches_tracked += forwards this step

@@ -21,3 +21,13 @@ def test_peer_memory_cost_exchange_matches_nccl():
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "peer-memory cost exchange == NCCL all-gather" in res.stdout
     assert "sharded plan (R = 2) == unsharded plan (R = 1)" in res.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_data_parallel_training_step():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29543", os.path.join(root, "tests", "gpu_dp_train_check.py")]
+    res = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "overlapped all-reduce == one all-reduce" in res.stdout

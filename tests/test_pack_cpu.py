@@ -97,7 +97,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.rac_abi_version() == 6
+    assert lib.rac_abi_version() == 7
 
 
 def test_model_spec_matches_oracle_spec():
@@ -282,3 +282,20 @@ def test_trainer_layer_tables_rebuild_the_packed_operands(group_norm):
             assert t["gamma_off"] == offsets[f"{p}.{gk}.1.weight"] and t["beta_off"] == offsets[f"{p}.{gk}.1.bias"]
             if not name.endswith("_HH"):
                 assert t["cnorm_gamma_off"] == offsets[f"{p}.c_norm.weight"] and t["cnorm_beta_off"] == offsets[f"{p}.c_norm.bias"]
+
+
+def test_complement_ranges_of_the_overlapped_allreduce():
+    from robot_aware_control_b200.trainer import complement_ranges
+
+    assert complement_ranges([], 10) == [(0, 10)]
+    assert complement_ranges([(2, 3), (7, 3)], 10) == [(0, 2), (5, 2)]
+    assert complement_ranges([(7, 3), (0, 7)], 10) == []
+    done = [(5, 5), (20, 1), (11, 4)]
+    rest = complement_ranges(done, 30)
+    cover = sorted(done + rest)
+    assert cover[0][0] == 0 and all(a + n == b for (a, n), (b, _) in zip(cover, cover[1:])) and sum(n for _, n in cover) == 30
+    import pytest
+    with pytest.raises(ValueError):
+        complement_ranges([(0, 5), (4, 2)], 10)
+    with pytest.raises(ValueError):
+        complement_ranges([(8, 5)], 10)
