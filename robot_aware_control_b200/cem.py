@@ -382,12 +382,20 @@ class CEMPolicy(object):
                     if not getattr(cfg, "model_use_robot_state", False):
                         states = None
                 fused = peer is not None and not (last and (opt_traj is not None or self.plot_rollouts))
-                ts._rollout_device(act5, start_img, goal_imgs, goal_masks, states, masks, None, n_local, L, local_cost,
-                                   cand_offset=lo, noise_ctr=i * L, peer=peer.target(lo) if fused else None)
+                try:
+                    ts._rollout_device(act5, start_img, goal_imgs, goal_masks, states, masks, None, n_local, L, local_cost,
+                                       cand_offset=lo, noise_ctr=i * L, peer=peer.target(lo) if fused else None)
+                    if fused:
+                        # the per-candidate costs are already in every rank's buffer (stored by the cost kernel through
+                        # NVLink peer memory); one flag barrier orders them against the replicated top-k
+                        costs = peer.finish(self._lib)
+                except Exception:
+                    # the exchange counts iterations on the host (buffer parity, flag sequence): a rank that failed
+                    # between target() and finish() would meet the others one count off next time. Drop it; the next
+                    # plan rendezvouses afresh (the other ranks of THIS plan are lost either way, as with any collective)
+                    self._peer_exchange = None
+                    raise
                 if fused:
-                    # the per-candidate costs are already in every rank's buffer (stored by the cost kernel through
-                    # NVLink peer memory); one flag barrier orders them against the replicated top-k
-                    costs = peer.finish(self._lib)
                     _lib.check(self._lib.rac_topk(_lib.ptr(costs), N, K, _lib.ptr(elite), None, _lib.stream_ptr()), None,
                                "rac_topk")
                     _lib.check(self._lib.rac_cem_refit(_lib.ptr(act2), L, _lib.ptr(elite), K, 0.001, _lib.ptr(mean),
