@@ -59,14 +59,22 @@ def peaks():
     return 1400.0, 6650.0, None, "fallback (B200_PROFILING.md)"
 
 
-def executed_flop_per_frame(steps):
+FLOP_ENCODER_PER_CAND = 1709.0e6    # the ten encoder convolutions, vanilla model
+
+
+def executed_flop_per_frame(steps, n_candidates=None):
     """MMAs actually issued per predicted frame: the LSTM gate convolutions run one 6x8-map row per MMA sub-tile and do
     not issue the (row, filter-row) pairs that only see zero padding (24 of 30 live for the 5x5 filter, 16 of 18 for the
-    3x3 one), and the all-zero h_prev half of K is skipped at the first step after init_hidden. Results unchanged."""
+    3x3 one), the all-zero h_prev half of K is skipped at the first step after init_hidden, and (vanilla model, given
+    `n_candidates`) the encoder of the first step runs for 16 candidates only -- every candidate starts from the same
+    frame -- and its outputs are copied to the others. Results unchanged."""
     f_h = ((steps - 1) + 0.5) / steps
     lstm_alg = 2 * (FLOP_LSTM0_PER_CAND + FLOP_LSTM1_PER_CAND)
     lstm_exec = 2 * (FLOP_LSTM0_PER_CAND * 24.0 / 30.0 + FLOP_LSTM1_PER_CAND * 16.0 / 18.0) * f_h
-    return FLOP_PER_FRAME - lstm_alg + lstm_exec
+    enc_saved = 0.0
+    if n_candidates and n_candidates > 16 and os.environ.get("RAC_ENC_DEDUP", "1") != "0":
+        enc_saved = FLOP_ENCODER_PER_CAND * (1.0 - 16.0 / n_candidates) / steps
+    return FLOP_PER_FRAME - lstm_alg + lstm_exec - enc_saved
 
 
 def ncu_traffic():
@@ -626,7 +634,7 @@ def main():
                 "(ncu, per launch) is ~2.4x the algorithmic DRAM bytes: weights are re-streamed per m-tile round "
                 "(L2 hit 94 %), at 4 % of DRAM peak",
     }
-    exec_per_frame = executed_flop_per_frame(L_STEPS)
+    exec_per_frame = executed_flop_per_frame(L_STEPS, n_local)
     whole = {"achieved": value * FLOP_PER_FRAME / world / 1e12, "peak": bf16_peak, "unit": "TFLOP/s per GPU",
              "frac": value * FLOP_PER_FRAME / world / 1e12 / bf16_peak, "flop_per_frame": FLOP_PER_FRAME,
              "executed_flop_per_frame": exec_per_frame,

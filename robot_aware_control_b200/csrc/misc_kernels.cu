@@ -509,4 +509,28 @@ cudaError_t launch_kl_loss(const float* mu1, const float* lv1, const float* mu2,
   return cudaGetLastError();
 }
 
+// Copies channels [coff, coff + C) of every pixel of candidate 0 to candidates first .. B-1 of an NHWC bf16 tensor
+// [B][HW][cstride] (encoder outputs at the first rollout step: identical for all candidates, rac_api.cu::run_step).
+// 16-byte accesses; the source (<= 393 KB) stays in L2.
+__global__ void __launch_bounds__(256)
+broadcast_candidate_kernel(__nv_bfloat16* __restrict__ buf, int HW, int cstride, int coff, int C8, int first, int B) {
+  const long long per = static_cast<long long>(HW) * C8;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= per * (B - first)) return;
+  const long long b = first + i / per;
+  const long long r = i - (b - first) * per;
+  const long long p = r / C8;
+  const int c = static_cast<int>(r - p * C8) * 8;
+  const uint4 v = *reinterpret_cast<const uint4*>(buf + p * cstride + coff + c);
+  *reinterpret_cast<uint4*>(buf + (b * HW + p) * cstride + coff + c) = v;
+}
+cudaError_t launch_broadcast_candidate(__nv_bfloat16* buf, int HW, int cstride, int coff, int C, int first, int B,
+                                       cudaStream_t s) {
+  if (B <= first) return cudaSuccess;
+  if (C % 8 || cstride % 8 || coff % 8) return cudaErrorInvalidValue;
+  const long long total = static_cast<long long>(HW) * (C / 8) * (B - first);
+  broadcast_candidate_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(buf, HW, cstride, coff, C / 8, first, B);
+  return cudaGetLastError();
+}
+
 }  // namespace rac

@@ -99,4 +99,8 @@ cudaError_t launch_refit(const float* act2, int L2, const int64_t* idx, int k, f
                          float* std_out, cudaStream_t s);
 cudaError_t cem_set_attributes();
 
+// encoder outputs of candidate 0 -> candidates first .. B-1 (channels [coff, coff + C) of an NHWC bf16 tensor)
+cudaError_t launch_broadcast_candidate(__nv_bfloat16* buf, int HW, int cstride, int coff, int C, int first, int B,
+                                       cudaStream_t s);
+
 }  // namespace rac

@@ -253,6 +253,43 @@ def test_rollout_is_batch_independent_and_deterministic(scene):
     assert np.all(np.isfinite(full)) and np.all(full < 0)
 
 
+def test_shared_first_frame_encoder_is_exact(scene, monkeypatch):
+    """First rollout step, image-only encoder input: the encoder runs for one tile group of candidates and candidate
+    0's outputs are copied to the others (rac_api.cu::run_step). Same bits as running it for every candidate
+    (RAC_ENC_DEDUP=0): costs, predicted frames and the encoder outputs themselves; a ragged candidate count too."""
+    from robot_aware_control_b200 import DemoGoalState, State, TrajectorySampler
+
+    cfg = so.make_cfg(g_dim=G_DIM, z_dim=Z_DIM)
+    sd = so.make_state_dict(cfg, 9)
+    start = State(img=scene["start_img"])
+    goal = DemoGoalState(imgs=list(scene["goal_imgs"]), masks=list(scene["goal_masks"]))
+    for N in (200, 37):
+        g = torch.Generator().manual_seed(N)
+        actions = torch.cat([(torch.rand(N, 3, 2, generator=g) - 0.5) * 0.1, torch.zeros(N, 3, 3)], 2)
+        out = {}
+        for flag in ("1", "0"):
+            monkeypatch.setenv("RAC_ENC_DEDUP", flag)  # (read at rac_create)
+            m = _model(cfg, sd)
+            ts = TrajectorySampler(cfg, m)
+            ts._noise_ctr = 0
+            r = ts.generate_model_rollouts(actions, start, goal, ret_obs=True)
+            h4 = m._buffer_view("h4", (N, 6, 8, G_DIM)).float().cpu()  # (last step's, computed per candidate in both)
+            out[flag] = (np.asarray(r["sum_cost"]), np.asarray(r["obs"]), h4, m.launch_count())
+        np.testing.assert_array_equal(out["1"][0], out["0"][0])
+        np.testing.assert_array_equal(out["1"][1], out["0"][1])
+        assert torch.equal(out["1"][2], out["0"][2])
+        assert out["1"][3] == out["0"][3] + 4  # the four broadcast launches of the first step
+    # one-step rollout: the workspace holds the FIRST step's encoder outputs -> the broadcast copies themselves
+    monkeypatch.setenv("RAC_ENC_DEDUP", "1")
+    m = _model(cfg, sd)
+    ts = TrajectorySampler(cfg, m)
+    ts.generate_model_rollouts(actions[:, :1], start, goal)
+    for name, shape, off in (("cat5", (37, 48, 64, 128), 64), ("cat4", (37, 24, 32, 256), 128), ("cat3", (37, 12, 16, 512), 256),
+                             ("h4", (37, 6, 8, G_DIM), 0)):
+        t = m._buffer_view(name, shape)[..., off:]
+        assert torch.equal(t, t[:1].expand_as(t)), name
+
+
 def test_baseline_size_plan_properties(scene):
     """BASELINE.json configs[1] at full size (g_dim 512, 2000 candidates, L = 5): too large for the CPU oracle, so the
     checks are the size-independent properties -- determinism, independence of a candidate's cost from the batch it is
