@@ -311,7 +311,7 @@ def train_leg(dev, rank, world, group, robot_aware, scheduled_sampling, group_no
              "masks": (torch.rand(T, Bt, 1, 48, 64, device=dev, generator=g) > 0.8).float()}
 
     def step():
-        trainer.forward_backward(batch)
+        trainer.forward_backward(batch, fused_update=os.environ.get("RAC_TRAIN_NO_FUSED_UPDATE", "0") != "1")
         trainer.optimizer_step()
 
     for _ in range(warmup):

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RAC_ABI_VERSION 7
+#define RAC_ABI_VERSION 8
 
 typedef enum {
   RAC_OK = 0,
@@ -333,6 +333,9 @@ typedef struct {
   /* the contiguous range of the flat gradient buffer that holds this convolution's weight (+ bias) gradient and
    * nothing else: final as soon as the layer's weight gradient has been unpacked (see rac_train_batch.grads_ready) */
   long long grad_off, grad_count;
+  /* > 0: the layer's weight is ONE tensor of w_count elements at w_off and every element of it appears in the packing
+   * tables -- such a layer can take the fused optimizer step (rac_train_batch.defer_unpack); 0 otherwise */
+  long long w_count;
 } rac_train_layer;
 
 typedef struct {
@@ -370,11 +373,21 @@ typedef struct {
   /* Data-parallel overlap (NULL = off): called on the host, while rac_train_forward_backward is still enqueueing,
    * right after the kernels that FINISH grads[off, off + count) have been put on the stream -- the weight gradient
    * of a large layer (>= grads_ready_min elements; the ConvLSTM gate convolutions: 89 % of all parameters), which
-   * BPTT completes long before the encoder's. The caller starts its all-reduce of that range there (stream-ordered
+   * BPTT completes long before the encoder's. The caller starts its all-reduce of `count` floats at `ptr` there (stream-ordered
    * after everything enqueued so far) and it runs underneath the rest of the backward pass. */
-  void (*grads_ready)(void* user, long long off, long long count);
+  void (*grads_ready)(void* user, float* ptr, long long count, long long flat_off, long long flat_count);
   void* grads_ready_user;
   long long grads_ready_min;
+  /* 1: the caller will run rac_train_adam_step right after this call and does not need the flat gradient of the large
+   * single-tensor convolutions (w_count >= defer_min): their packed weight gradient stays where the wgrad GEMM left
+   * it and rac_train_adam_step updates such a layer in ONE pass (packed gradient -> Adam on its parameter / moment
+   * slices -> bf16 operand of the next step) instead of unpack + flat Adam + re-pack: 30 instead of 46 bytes per
+   * weight. grads_ready then hands over ptr = the packed gradient buffer (count elements, to be all-reduced in place)
+   * and flat_off / flat_count = the flat range that is NOT going to be written (exclude it from the remainder);
+   * without defer_unpack ptr = grads + flat_off, count = flat_count. rac_train_unpack_deferred writes the flat
+   * gradient of the deferred layers after all (inspection, tests). */
+  int defer_unpack;
+  long long defer_min;
 } rac_train_batch;
 
 int rac_train_create(rac_handle* h, const rac_train_config* cfg,
@@ -391,6 +404,11 @@ int rac_train_adam_step(rac_handle* h, void* stream);
 /* Factor applied to every gradient inside the Adam kernel (1 / world size after a SUM all-reduce: saves a pass over
  * the gradient buffer). Stays in force until changed; rac_train_create resets it to 1. */
 int rac_train_set_grad_scale(rac_handle* h, float scale);
+/* flat gradient of the layers a defer_unpack step left packed (before rac_train_adam_step) */
+int rac_train_unpack_deferred(rac_handle* h, void* stream);
+/* the caller changed parameters behind the library's back (load_state_dict, an external optimizer): the bf16 operands
+ * kept from the last fused optimizer step are stale and are re-packed at the next step */
+int rac_train_invalidate_packed(rac_handle* h);
 /* Number of Adam steps already taken (the t of the bias corrections). rac_train_create starts at 0: a caller that
  * re-creates the training state (another batch shape) or resumes from a checkpoint (torch.optim.Adam state "step",
  * trainer.py:829-896) restores it here; the moments themselves live in the caller's adam_m / adam_v. */

@@ -121,6 +121,8 @@ EXPORTS = {
     "rac_train_adam_step": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rac_train_set_adam_step": (C.c_int, [C.c_void_p, C.c_int]),
     "rac_train_set_grad_scale": (C.c_int, [C.c_void_p, C.c_float]),
+    "rac_train_unpack_deferred": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rac_train_invalidate_packed": (C.c_int, [C.c_void_p]),
     "rac_train_debug_buffer": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
     "rac_train_step_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rac_train_step_forward": (C.c_int, [C.c_void_p, C.POINTER(RacTrainStep), C.c_void_p]),

@@ -107,6 +107,8 @@ struct TrainState {
   int bwd_next = -1;                  // step API: the time step rac_train_step_backward must be called for next
   const rac_train_batch* cur_bt = nullptr;  // the batch of the running rac_train_forward_backward (grads_ready callback)
   bool unpacked[RAC_L_COUNT_GN] = {};       // layers whose weight gradient is already in the flat buffer
+  bool deferred[RAC_L_COUNT_GN] = {};       // layers whose gradient stays packed for the fused optimizer step
+  bool packed_valid[RAC_L_COUNT_GN] = {};   // layers whose bf16 operand is current (written by the fused optimizer step)
   float grad_scale = 1.f;
   int per_step = 0;                   // RAC_TRAIN_PER_STEP=1: never batch the time steps (A/B measurements, cross-checks)
   int dgrad_bt = 1;                   // dgrad reads the forward weight packing as an MN-major operand (0: transposed copy Wd)
@@ -462,11 +464,16 @@ int conv_backward(rac_handle* h, TrainState* T, int layer, int H, int W, const s
     if (L.d.bias_off) CK(launch_bias_grad(L.dyT, static_cast<int>(S * M), L.kpad, L.n_packed, L.d.bias_off, T->grads, st));
     // data-parallel overlap: a large layer's gradient goes to the flat buffer now and is handed to the caller's all-reduce
     const rac_train_batch* bt = T->cur_bt;
-    if (bt && bt->grads_ready && L.d.grad_count > 0 && L.d.grad_count >= bt->grads_ready_min) {
+    if (bt && bt->defer_unpack && L.d.w_count > 0 && L.d.w_count >= bt->defer_min) {
+      // fused optimizer step: the gradient stays packed; (data parallel) all-reduced in place in that form
+      T->deferred[layer] = true;
+      if (bt->grads_ready)
+        bt->grads_ready(bt->grads_ready_user, L.dwp, static_cast<long long>(L.kpad) * L.taps * L.ctot, L.d.w_off, L.d.w_count);
+    } else if (bt && bt->grads_ready && L.d.grad_count > 0 && L.d.grad_count >= bt->grads_ready_min) {
       CK(launch_unpack_grads(L.dwp, L.d.row_off, L.d.col_off, L.n_packed, L.taps, L.ctot, L.d.flip, T->grads, st));
       h->launches++;
       T->unpacked[layer] = true;
-      bt->grads_ready(bt->grads_ready_user, L.d.grad_off, L.d.grad_count);
+      bt->grads_ready(bt->grads_ready_user, T->grads + L.d.grad_off, L.d.grad_count, L.d.grad_off, L.d.grad_count);
     }
   }
   // ---- dgrad: dX = conv(dY, Wd)
@@ -998,7 +1005,9 @@ int train_prologue(rac_handle* h, TrainState* T, cudaStream_t st) {
   // ---- parameters -> packed bf16 operands (forward + dgrad), packed biases; zero the gradient accumulators
   for (int i = 1; i < T->nlayers; ++i) {
     TLayer& L = T->L[i];
-    CK(launch_pack_weights(T->params, L.d.row_off, L.d.col_off, L.n_packed, L.taps, L.ctot, L.d.flip, L.wp, st, T->w_tiled));
+    // (a layer the fused optimizer step has just written keeps its operand; its bias is re-gathered below)
+    if (!T->packed_valid[i])
+      CK(launch_pack_weights(T->params, L.d.row_off, L.d.col_off, L.n_packed, L.taps, L.ctot, L.d.flip, L.wp, st, T->w_tiled));
     if (!T->dgrad_bt) CK(launch_transpose_flip(L.wp, L.n_packed, L.taps, L.ctot, L.kpad, L.wd, st));
     if (L.d.bias_off) CK(launch_gather_f32(T->params, L.d.bias_off, L.n_packed, L.bias, st));
   }
@@ -1211,6 +1220,7 @@ int rac_train_forward_backward(rac_handle* h, const rac_train_batch* bt, void* s
   CK(cudaMemsetAsync(bt->losses, 0, sizeof(float) * 4, st));
   T->cur_bt = bt;
   for (bool& u : T->unpacked) u = false;
+  for (bool& u : T->deferred) u = false;
   T->step_api = 0;
   T->active_steps = S;
   // ---- reparameterisation noise of all steps (the tape is time-major: one copy / one fill per tensor)
@@ -1287,7 +1297,7 @@ int rac_train_forward_backward(rac_handle* h, const rac_train_batch* bt, void* s
   // ---- packed weight gradients -> flat parameter layout (layers not handed over earlier)
   for (int i = 1; i < T->nlayers; ++i) {
     TLayer& L = T->L[i];
-    if (T->unpacked[i]) continue;
+    if (T->unpacked[i] || T->deferred[i]) continue;
     CK(launch_unpack_grads(L.dwp, L.d.row_off, L.d.col_off, L.n_packed, L.taps, L.ctot, L.d.flip, T->grads, st));
   }
   T->cur_bt = nullptr;
@@ -1321,6 +1331,7 @@ int rac_train_step_begin(rac_handle* h, void* stream) {
   if (!h || !h->train) return fail(h, RAC_ERR_STATE, "rac_train_create first");
   TrainState* T = static_cast<TrainState*>(h->train);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (bool& u : T->packed_valid) u = false;  // (an external optimizer has stepped the parameters)
   CKR(train_prologue(h, T, st));
   T->step_api = 1;
   T->active_steps = 0;
@@ -1458,9 +1469,50 @@ int rac_train_set_adam_step(rac_handle* h, int steps_taken) {
 int rac_train_adam_step(rac_handle* h, void* stream) {
   if (!h || !h->train) return fail(h, RAC_ERR_STATE, "rac_train_create first");
   TrainState* T = static_cast<TrainState*>(h->train);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   T->adam_t += 1;
-  CK(launch_adam(T->params, T->grads, T->m, T->v, T->cfg.n_params, T->cfg.lr, T->cfg.beta1, T->cfg.beta2,
-                 T->cfg.adam_eps, T->adam_t, static_cast<cudaStream_t>(stream), T->grad_scale));
+  // layers whose gradient stayed packed (rac_train_batch.defer_unpack): one fused pass each; everything else -- the
+  // complement of their weight ranges in the flat buffers -- through the flat kernel
+  std::vector<std::pair<long long, long long>> fused;
+  for (int i = 1; i < T->nlayers; ++i) {
+    TLayer& L = T->L[i];
+    if (!T->deferred[i]) { T->packed_valid[i] = false; continue; }
+    CK(launch_adam_pack(T->params, T->m, T->v, L.dwp, L.d.row_off, L.d.col_off, L.n_packed, L.taps, L.ctot, L.d.flip,
+                        T->w_tiled, L.wp, T->cfg.lr, T->cfg.beta1, T->cfg.beta2, T->cfg.adam_eps, T->adam_t, T->grad_scale, st));
+    h->launches++;
+    T->packed_valid[i] = true;
+    T->deferred[i] = false;
+    fused.push_back({L.d.w_off, L.d.w_count});
+  }
+  std::sort(fused.begin(), fused.end());
+  long long pos = 0;
+  fused.push_back({T->cfg.n_params, 0});
+  for (const auto& f : fused) {
+    if (f.first < pos) return fail(h, RAC_ERR_STATE, "overlapping weight ranges in the fused optimizer step");
+    if (f.first > pos)
+      CK(launch_adam(T->params + pos, T->grads + pos, T->m + pos, T->v + pos, f.first - pos, T->cfg.lr, T->cfg.beta1,
+                     T->cfg.beta2, T->cfg.adam_eps, T->adam_t, st, T->grad_scale));
+    pos = f.first + f.second;
+  }
+  return RAC_OK;
+}
+
+int rac_train_unpack_deferred(rac_handle* h, void* stream) {
+  if (!h || !h->train) return fail(h, RAC_ERR_STATE, "rac_train_create first");
+  TrainState* T = static_cast<TrainState*>(h->train);
+  for (int i = 1; i < T->nlayers; ++i) {
+    TLayer& L = T->L[i];
+    if (!T->deferred[i]) continue;
+    CK(launch_unpack_grads(L.dwp, L.d.row_off, L.d.col_off, L.n_packed, L.taps, L.ctot, L.d.flip, T->grads,
+                           static_cast<cudaStream_t>(stream)));
+  }
+  return RAC_OK;
+}
+
+int rac_train_invalidate_packed(rac_handle* h) {
+  if (!h) return RAC_ERR_INVALID;
+  if (!h->train) return RAC_OK;
+  for (bool& u : static_cast<TrainState*>(h->train)->packed_valid) u = false;
   return RAC_OK;
 }
 

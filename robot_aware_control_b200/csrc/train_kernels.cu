@@ -118,6 +118,101 @@ cudaError_t launch_unpack_grads(const float* dwp, const long long* row_off, cons
   return cudaGetLastError();
 }
 
+// torch.optim.Adam's update of one element with the contraction spelled out (the flat kernel and the fused per-layer
+// kernel must give the same bits whatever the compiler would fuse in either code shape)
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, float b1, float b2, float step,
+                                            float bc2_sqrt, float eps) {
+  m = __fmaf_rn(b1, m, __fmul_rn(1.f - b1, g));
+  v = __fmaf_rn(b2, v, __fmul_rn(__fmul_rn(1.f - b2, g), g));
+  p = __fsub_rn(p, __fdiv_rn(__fmul_rn(step, m), __fadd_rn(__fdiv_rn(sqrtf(v), bc2_sqrt), eps)));
+}
+
+// Fused optimizer step of ONE convolution: packed weight gradient (as the wgrad GEMM left it, dwp[n][tap][c]) -> Adam
+// on the layer's slice of the flat fp32 parameters / moments -> the bf16 operand of the next step, in one pass. Replaces
+// unpack_grads (4 B read + 4 B written per weight), the flat Adam's gradient read (4 B) and pack_weights (4 B read) for
+// the layer: 30 instead of 46 bytes per weight. Same update formula, element by element, as adam_kernel (bit-equal
+// parameters); the flat gradient buffer is NOT written for this layer (rac_train_unpack_deferred does it on demand).
+// Tiling as pack_weights_kernel: the flat side is walked linearly (64 channels x taps contiguous floats per packed
+// row), the packed side with c fastest, transposed through shared memory.
+__global__ void __launch_bounds__(256)
+adam_pack_kernel(float* __restrict__ params, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ dwp,
+                 const long long* __restrict__ row_off, const int* __restrict__ col_off, int n_packed, int taps, int ctot,
+                 int flip, int tiled, __nv_bfloat16* __restrict__ wp, float lr, float b1, float b2, float eps, float bc1,
+                 float bc2_sqrt, float gscale) {
+  __shared__ float tg[25][65], tp[25][65];
+  const int c0 = blockIdx.y * 64;
+  const float step = lr / bc1;
+  for (int n = blockIdx.x; n < n_packed; n += gridDim.x) {
+    const long long ro = row_off[n];
+    // (1) all parameter / moment loads of this thread's (up to 7) elements go out first: three 4-byte streams per
+    // element issued one element at a time left ~18 KB in flight per SM (the first version ran at 3 TB/s)
+    constexpr int kPer = 7;  // ceil(64 * 25 / 256)
+    float pi[kPer], mi[kPer], vi[kPer];
+    long long fo[kPer];  // (kept in registers: recomputing them in (3) to gain a CTA per SM measured slower)
+    int tfs[kPer], cls[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int j = threadIdx.x + k * 256;
+      fo[k] = -1;
+      if (j < 64 * taps) {
+        const int cl = j / taps, tap = j - cl * taps;
+        const int co = col_off[c0 + cl];
+        tfs[k] = flip ? taps - 1 - tap : tap;
+        cls[k] = cl;
+        if (ro >= 0 && co >= 0) {
+          fo[k] = ro + co + tap;
+          pi[k] = __ldcs(params + fo[k]); mi[k] = __ldcs(m + fo[k]); vi[k] = __ldcs(v + fo[k]);
+        } else {
+          fo[k] = -2;  // padding column / row: the operand gets a zero
+        }
+      }
+    }
+    // (2) the packed gradient of the row, transposed through shared memory
+    if (ro >= 0) {
+      for (int j = threadIdx.x; j < 16 * taps; j += blockDim.x) {
+        const int tap = j >> 4, cl = (j & 15) * 4;
+        const float4 g = __ldcs(reinterpret_cast<const float4*>(dwp + (static_cast<long long>(n) * taps + tap) * ctot + c0 + cl));
+        tg[tap][cl] = g.x; tg[tap][cl + 1] = g.y; tg[tap][cl + 2] = g.z; tg[tap][cl + 3] = g.w;
+      }
+    }
+    __syncthreads();  // (also: the previous row's operand write has finished reading tp)
+    // (3) update, store, and the new parameter into the operand tile
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      if (fo[k] == -1) continue;
+      float pn = 0.f;
+      if (fo[k] >= 0) {
+        adam_update(pi[k], tg[tfs[k]][cls[k]] * gscale, mi[k], vi[k], b1, b2, step, bc2_sqrt, eps);
+        __stcs(m + fo[k], mi[k]);
+        __stcs(v + fo[k], vi[k]);
+        __stcs(params + fo[k], pi[k]);
+        pn = pi[k];
+      }
+      tp[tfs[k]][cls[k]] = pn;
+    }
+    __syncthreads();
+    // (4) bf16 operand of the next step
+    for (int j = threadIdx.x; j < 32 * taps; j += blockDim.x) {
+      const int tap = j >> 5, cl = (j & 31) * 2;
+      const long long at = tiled ? ((static_cast<long long>(tap) * (ctot >> 6) + blockIdx.y) * n_packed + n) * 64 + cl
+                                 : (static_cast<long long>(n) * taps + tap) * ctot + c0 + cl;
+      *reinterpret_cast<__nv_bfloat162*>(wp + at) = __floats2bfloat162_rn(tp[tap][cl], tp[tap][cl + 1]);
+    }
+  }
+}
+cudaError_t launch_adam_pack(float* params, float* m, float* v, const float* dwp, const long long* row_off,
+                             const int* col_off, int n_packed, int taps, int ctot, int flip, int tiled,
+                             __nv_bfloat16* wp, float lr, float b1, float b2, float eps, int t, float grad_scale,
+                             cudaStream_t s) {
+  if (ctot % 64 != 0 || taps > 25) return cudaErrorInvalidValue;
+  const float bc1 = 1.f - powf(b1, static_cast<float>(t));
+  const float bc2 = sqrtf(1.f - powf(b2, static_cast<float>(t)));
+  const int gx = std::min(n_packed, std::max(1, 1184 / (ctot / 64)));
+  adam_pack_kernel<<<dim3(gx, ctot / 64), 256, 0, s>>>(params, m, v, dwp, row_off, col_off, n_packed, taps, ctot, flip, tiled,
+                                                      wp, lr, b1, b2, eps, bc1, bc2, grad_scale);
+  return cudaGetLastError();
+}
+
 __global__ void pack_first_kernel(const float* __restrict__ w, int cin, float* __restrict__ wf) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (tap, c, o)
   if (i >= 9 * cin * 64) return;
@@ -1073,15 +1168,20 @@ cudaError_t launch_cast_bf16(const float* src, long long n, __nv_bfloat16* dst, 
 // grid-stride over a grid of a few CTAs per SM, streaming cache hints (nothing is re-read before the next step)
 __global__ void __launch_bounds__(512)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-            long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float gscale) {
+            long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float gscale, int head) {
   const float step = lr / bc1;
   // gscale: 1 / world size after a SUM all-reduce (x * 1.0f is exact, so the single-GPU update is unchanged)
   auto upd = [&](float& pi, float gi, float& mi, float& vi) {
-    gi *= gscale;
-    mi = b1 * mi + (1.f - b1) * gi;
-    vi = b2 * vi + (1.f - b2) * gi * gi;
-    pi -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    adam_update(pi, gi * gscale, mi, vi, b1, b2, step, bc2_sqrt, eps);
   };
+  // `head` scalar elements bring the four streams to a 16-byte boundary (a range of the flat buffers may start anywhere)
+  if (blockIdx.x == 0 && static_cast<int>(threadIdx.x) < head) {
+    const int i = threadIdx.x;
+    float pi = p[i], mi = m[i], vi = v[i];
+    upd(pi, g[i], mi, vi);
+    m[i] = mi; v[i] = vi; p[i] = pi;
+  }
+  p += head; g += head; m += head; v += head; n -= head;
   const long long n4 = n >> 2;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -1097,8 +1197,8 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     __stcs(reinterpret_cast<float4*>(v) + i, vi);
     __stcs(reinterpret_cast<float4*>(p) + i, pi);
   }
-  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {  // tail
-    const long long i = (n4 << 2) + threadIdx.x;
+  if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x - 32 < (n & 3)) {  // tail (another warp than the head)
+    const long long i = (n4 << 2) + (threadIdx.x - 32);
     float pi = p[i], mi = m[i], vi = v[i];
     upd(pi, g[i], mi, vi);
     m[i] = mi; v[i] = vi; p[i] = pi;
@@ -1108,10 +1208,17 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long 
                         float eps, int t, cudaStream_t s, float grad_scale) {
   const float bc1 = 1.f - powf(b1, static_cast<float>(t));
   const float bc2 = sqrtf(1.f - powf(b2, static_cast<float>(t)));
-  if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
-       reinterpret_cast<uintptr_t>(v)) & 15)
+  if (n <= 0) return cudaSuccess;
+  // the four streams must be aligned alike (ranges of buffers that are themselves 16-byte aligned are)
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p) & 15;
+  if ((reinterpret_cast<uintptr_t>(g) & 15) != a || (reinterpret_cast<uintptr_t>(m) & 15) != a ||
+      (reinterpret_cast<uintptr_t>(v) & 15) != a || (a & 3))
     return cudaErrorInvalidValue;
-  adam_kernel<<<148 * 8, 512, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2, grad_scale);
+  int head = static_cast<int>(((16 - a) & 15) >> 2);
+  if (head > n) head = static_cast<int>(n);
+  const long long body = (n - head) >> 2;
+  const int blocks = static_cast<int>(std::min<long long>(148 * 8, std::max<long long>(1, (body + 511) / 512)));
+  adam_kernel<<<blocks, 512, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2, grad_scale, head);
   return cudaGetLastError();
 }
 

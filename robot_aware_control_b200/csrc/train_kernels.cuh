@@ -123,6 +123,11 @@ cudaError_t launch_pool_bwd(const __nv_bfloat16* in, int in_cstride, int in_coff
 cudaError_t launch_cast_bf16(const float* src, long long n, __nv_bfloat16* dst, cudaStream_t s);
 
 // ---- optimiser (torch.optim.Adam, no weight decay) and noise
+// one convolution: packed weight gradient -> Adam on its flat parameter / moment slices -> bf16 operand (one pass)
+cudaError_t launch_adam_pack(float* params, float* m, float* v, const float* dwp, const long long* row_off,
+                             const int* col_off, int n_packed, int taps, int ctot, int flip, int tiled,
+                             __nv_bfloat16* wp, float lr, float b1, float b2, float eps, int t, float grad_scale,
+                             cudaStream_t s);
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
                         float eps, int t, cudaStream_t s, float grad_scale = 1.f);
 cudaError_t launch_normal_fill(float* dst, long long n, unsigned long long seed, unsigned int ctr, cudaStream_t s);

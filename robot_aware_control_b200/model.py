@@ -228,14 +228,21 @@ class SVGConvModel(nn.Module):
 
     def load_state_dict(self, state_dict, strict=True, **kw):
         out = super().load_state_dict(state_dict, strict=strict, **kw)
-        self._packed_dirty = True
+        self._params_touched()
         return out
 
     def _apply(self, fn, *a, **k):
         # .to()/.cuda()/.float(): the packed copy inside the library is rebuilt from whatever the tensors become
         out = super()._apply(fn, *a, **k)
-        self._packed_dirty = True
+        self._params_touched()
         return out
+
+    def _params_touched(self):
+        """The parameter tensors changed behind the library's back: both packed copies are stale -- the eval-mode one
+        (folded BatchNorm) and the training operands the fused optimizer step keeps across steps."""
+        self._packed_dirty = True
+        if getattr(self, "_ts", None) is not None and getattr(self, "_h", None):
+            self._ts.invalidate_packed()
 
     def _ensure_packed(self):
         if not self._packed_dirty:

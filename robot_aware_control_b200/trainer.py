@@ -65,7 +65,7 @@ def _layer_tables(model, offsets, boffsets):
         cnt = cout * cin * k2
         if bias and offsets[f"{prefix}.bias"] == w_off + cnt:
             cnt += cout
-        e.update(grad_off=w_off, grad_count=cnt)
+        e.update(grad_off=w_off, grad_count=cnt, w_count=cout * cin * k2)
         if bn is not None:
             e.update(gamma_off=offsets[f"{prefix}.main.1.weight"], beta_off=offsets[f"{prefix}.main.1.bias"],
                      rmean_off=boffsets[f"{prefix}.main.1.running_mean"], rvar_off=boffsets[f"{prefix}.main.1.running_var"])
@@ -124,7 +124,7 @@ class RacTrainLayer(C.Structure):
                 ("gamma_off", C.c_longlong), ("beta_off", C.c_longlong), ("rmean_off", C.c_longlong),
                 ("rvar_off", C.c_longlong), ("w_off", C.c_longlong), ("flip", C.c_int),
                 ("cnorm_gamma_off", C.c_longlong), ("cnorm_beta_off", C.c_longlong),
-                ("grad_off", C.c_longlong), ("grad_count", C.c_longlong)]
+                ("grad_off", C.c_longlong), ("grad_count", C.c_longlong), ("w_count", C.c_longlong)]
 
 
 class RacTrainConfig(C.Structure):
@@ -138,11 +138,21 @@ class RacTrainBatch(C.Structure):
     _fields_ = [("images", C.c_void_p), ("masks", C.c_void_p), ("states", C.c_void_p), ("actions", C.c_void_p),
                 ("eps_prior", C.c_void_p), ("eps_post", C.c_void_p), ("seed", C.c_ulonglong), ("losses", C.c_void_p),
                 ("true_token", C.c_void_p), ("noise_step", C.c_ulonglong), ("batch_weight", C.c_void_p),
-                ("grads_ready", C.c_void_p), ("grads_ready_user", C.c_void_p), ("grads_ready_min", C.c_longlong)]
+                ("grads_ready", C.c_void_p), ("grads_ready_user", C.c_void_p), ("grads_ready_min", C.c_longlong),
+                ("defer_unpack", C.c_int), ("defer_min", C.c_longlong)]
 
 
-GRADS_READY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_longlong, C.c_longlong)
+GRADS_READY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong)
 OVERLAP_MIN_ELEMS = 4 << 20  # layers with at least this many weights are all-reduced while the backward pass runs
+FUSED_MIN_ELEMS = 1 << 20    # single-tensor convolutions with at least this many weights take the fused optimizer step
+
+
+def _device_f32_view(ptr, count, device):
+    """A float32 CUDA tensor over `count` elements at device address `ptr` (a buffer inside the library's arena)."""
+    class _W:
+        __cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
+
+    return torch.as_tensor(_W(), device=device)
 
 
 def complement_ranges(done, n):
@@ -229,6 +239,8 @@ class SVGTrainer:
         self.process_group = process_group
         self.allreduce_events = None
         self.overlap_allreduce = True   # start the all-reduce of the large layers underneath the backward pass
+        self.fused_update = True        # train_step: packed gradient -> Adam -> bf16 operand in one pass for the large layers
+        self._deferred = False
         self._grad_scale_world = 1
         self._pending = []
         self._lib = _lib.load()
@@ -289,6 +301,7 @@ class SVGTrainer:
             layers[i].w_off = t["w_off"]
             layers[i].flip = t["flip"]
             layers[i].grad_off, layers[i].grad_count = t.get("grad_off", 0), t.get("grad_count", 0)
+            layers[i].w_count = t.get("w_count", 0)
         self._layers = layers
         self._created_for = None
         self._lr = float(getattr(config, "lr", 1e-4))
@@ -341,8 +354,11 @@ class SVGTrainer:
         self._grad_scale_world = 1  # (a fresh training state scales by 1)
         self._created_for = (B, S)
 
-    def forward_backward(self, batch):
-        """Fills self.grads and self.losses (sum over steps of recon, of KL). Returns (recon_sum, kld_sum) tensors."""
+    def forward_backward(self, batch, fused_update=False):
+        """Fills self.grads and self.losses (sum over steps of recon, of KL). Returns the loss tensor.
+        fused_update=True (what train_step does): optimizer_step() follows immediately and nobody reads the flat gradient
+        of the large convolutions, so their gradient stays in the packed form the wgrad GEMM wrote and the optimizer
+        updates those layers in one pass (rac_train_batch.defer_unpack); `unpack_deferred()` materialises it after all."""
         m = self.model
         dev = m._device
         f32 = lambda t: None if t is None else t.to(device=dev, dtype=torch.float32).contiguous()
@@ -382,16 +398,23 @@ class SVGTrainer:
                            seed=self._seed, losses=_lib.ptr(self.losses),
                            true_token=None if all(tokens) else tokens.ctypes.data, noise_step=self._step,
                            batch_weight=_lib.ptr(bw))
-        self._pending = []  # (offset, count, Work) of the all-reduces started underneath the backward pass
-        if self._dp_world() > 1 and self.overlap_allreduce:
-            def ready(_user, off, count):
+        self._pending = []  # (flat offset, flat count, Work, tensor) of the all-reduces started underneath the backward pass
+        dp = self._dp_world() > 1
+        if dp and self.overlap_allreduce:
+            def ready(_user, ptr, count, flat_off, flat_count):
                 # runs on this thread while the library is still enqueueing: NCCL orders the collective after
-                # everything enqueued on the current stream so far and runs it on its own stream
-                w = dist.all_reduce(self.grads[off:off + count], group=self.process_group, async_op=True)
-                self._pending.append((int(off), int(count), w))
+                # everything enqueued on the current stream so far and runs it on its own stream. `ptr` is either a
+                # range of the flat gradient buffer or (fused optimizer step) a layer's packed gradient buffer.
+                t = _device_f32_view(ptr, count, dev)
+                w = dist.all_reduce(t, group=self.process_group, async_op=True)
+                self._pending.append((int(flat_off), int(flat_count), w, t))
             self._ready_cb = GRADS_READY_FN(ready)  # (kept alive for the duration of the call)
             bt.grads_ready = C.cast(self._ready_cb, C.c_void_p)
             bt.grads_ready_min = OVERLAP_MIN_ELEMS
+        # (data parallel without the overlap has no hook through which the packed gradients could be reduced)
+        self._deferred = bool(fused_update and self.fused_update and (not dp or self.overlap_allreduce))
+        bt.defer_unpack = int(self._deferred)
+        bt.defer_min = FUSED_MIN_ELEMS
         _lib.check(self._lib.rac_train_forward_backward(m.handle, C.byref(bt), _lib.stream_ptr()), m.handle,
                    "rac_train_forward_backward")
         self._keep_batch = (images, actions, masks, states, eps_p, eps_q, bw)  # alive until the stream has consumed them
@@ -410,10 +433,10 @@ class SVGTrainer:
             # the large layers were handed to NCCL while BPTT was still running (forward_backward); what is left is the
             # complement of their ranges. The mean is taken inside the Adam kernel (gradient scale 1 / world).
             pending = getattr(self, "_pending", [])
-            for off, cnt in complement_ranges([(o, c) for o, c, _ in pending], self.grads.numel()):
+            for off, cnt in complement_ranges([(p[0], p[1]) for p in pending], self.grads.numel()):
                 dist.all_reduce(self.grads[off:off + cnt], group=self.process_group)
-            for _, _, w in pending:
-                w.wait()
+            for p in pending:
+                p[2].wait()
             self._pending = []
             if ev is not None:
                 ev[1].record()
@@ -430,7 +453,7 @@ class SVGTrainer:
         """One reference `_train_step`: returns {"recon_loss", "kld"} averaged over n_future (trainer.py:463-464)."""
         if not self.model.training:
             raise RuntimeError("call model.train() before train_step (reference trainer.py:754)")
-        losses = self.forward_backward(batch)
+        losses = self.forward_backward(batch, fused_update=True)
         self.optimizer_step()
         # the reference divides the logged sums by cfg.n_future whatever the clip length is (trainer.py:463-464)
         nf = int(getattr(self._config, "n_future", batch["images"].shape[0] - 1))
@@ -573,6 +596,17 @@ class SVGTrainer:
             self._step = int(ckpt["step"])
             self.load_optimizer_state_dict(ckpt["optimizer"])
         return self._step
+
+    def unpack_deferred(self):
+        """After forward_backward(fused_update=True): write the flat gradient of the layers whose gradient stayed packed
+        (inspection; optimizer_step does not need it)."""
+        m = self.model
+        _lib.check(self._lib.rac_train_unpack_deferred(m.handle, _lib.stream_ptr()), m.handle, "rac_train_unpack_deferred")
+
+    def invalidate_packed(self):
+        """Parameters were changed from outside (load_state_dict, an external optimizer): re-pack at the next step."""
+        m = self.model
+        _lib.check(self._lib.rac_train_invalidate_packed(m.handle), m.handle, "rac_train_invalidate_packed")
 
     def _publish_grads(self):
         """Train-mode SVGConvModel.forward under autograd: after the backward pass of step 0 every parameter's .grad

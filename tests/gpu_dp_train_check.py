@@ -3,7 +3,9 @@
     the same averaged gradients as ONE all-reduce of the whole buffer after the backward pass, and both equal the
     mean of the two ranks' local gradients computed by hand;
 (b) the Adam update with the 1 / world factor inside the kernel equals torch.optim.Adam on the averaged gradient;
-(c) parameters stay bit-identical across ranks after the step."""
+(c) parameters stay bit-identical across ranks after the step;
+(d) the fused optimizer step (gradients of the large layers stay packed, are all-reduced in that form and consumed by
+    the Adam + re-pack kernel) ends in the same parameters bit for bit."""
 import os
 import sys
 
@@ -30,14 +32,15 @@ def main():
     out = {}
     import robot_aware_control_b200.trainer as tr
     tr.OVERLAP_MIN_ELEMS = 100_000  # (g128: the gate convolutions have 0.6-1.6 M weights)
-    for mode in ("overlap", "plain", "local"):
+    tr.FUSED_MIN_ELEMS = 100_000
+    for mode in ("overlap", "plain", "fused", "local"):
         model = SVGConvModel(cfg)
         model.load_state_dict(sd)
         model.train()
         trainer = SVGTrainer(cfg, model, process_group=None if mode == "local" else dist.group.WORLD)
-        trainer.overlap_allreduce = mode == "overlap"
+        trainer.overlap_allreduce = mode in ("overlap", "fused")
         trainer.set_noise(*eps)
-        trainer.forward_backward(batch)
+        trainer.forward_backward(batch, fused_update=mode == "fused")
         n_pending = len(trainer._pending)
         if mode == "local":
             out[mode] = trainer.grads.clone()
@@ -61,6 +64,8 @@ def main():
         dist.all_gather(chk, params)
         assert torch.equal(chk[0], chk[1]), mode
     assert torch.equal(out["overlap"][1], out["plain"][1])
+    # fused optimizer step (packed gradients all-reduced in place, Adam + re-pack in one pass): the same parameters
+    assert out["fused"][3] >= 6 and torch.equal(out["fused"][1], out["plain"][1])
     if rank == 0:
         print("overlapped all-reduce == one all-reduce == mean of the local gradients; replicas identical")
     dist.destroy_process_group()

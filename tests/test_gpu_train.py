@@ -382,3 +382,49 @@ def test_time_batched_step_matches_step_by_step(tag, monkeypatch):
         assert _rel(out["0"][1][o:o + n], out["1"][1][o:o + n]) < 2e-2, k
     cos = float((out["0"][1] * out["1"][1]).sum() / (out["0"][1].norm() * out["1"][1].norm()))
     assert cos > 0.98, cos  # (the l1 path is chaos-limited: a few sign / ReLU decisions flip with the summation order)
+
+
+@pytest.mark.parametrize("tag", ["vanilla", "ra_gn"])
+def test_fused_optimizer_step_equals_unpack_adam_pack(tag, monkeypatch):
+    """train_step keeps the gradient of the large convolutions packed and updates each of them in one pass (packed
+    gradient -> Adam -> bf16 operand, adam_pack_kernel) while the rest goes through the flat kernel on the complement
+    ranges. Same arithmetic element by element: parameters, both moments and the NEXT step's losses (which read the
+    operands the fused kernel wrote instead of a fresh pack) are bit-equal to unpack + flat Adam + pack."""
+    import robot_aware_control_b200.trainer as tr
+
+    monkeypatch.setattr(tr, "FUSED_MIN_ELEMS", 100_000)  # g128: the gate convolutions have 0.3-1.6 M weights
+    out = {}
+    for fused in (False, True):
+        cfg, sd, model, trainer, batch, ep, eq = _setup(tag, 3)
+        losses = []
+        for step in range(3):
+            trainer.set_noise(ep, eq)
+            if fused and step == 1:
+                # the flat gradient of the deferred layers on demand == the one the unfused path wrote
+                trainer.forward_backward(batch, fused_update=True)
+                assert trainer._deferred
+                k = "prior.lstm.0.gates.weight" if tag == "vanilla" else "prior.lstm.0.ih_gates.0.weight"
+                assert float(trainer.grad_of(k).abs().max()) == 0.0
+                trainer.unpack_deferred()
+                assert torch.equal(trainer.grads, out[False][3])
+            else:
+                trainer.forward_backward(batch, fused_update=fused)
+            if not fused and step == 1:
+                g1 = trainer.grads.clone()
+            losses.append(trainer.losses.clone())
+            trainer.optimizer_step()
+        out[fused] = (trainer.params.clone(), trainer.adam_m.clone(), trainer.adam_v.clone(), g1 if not fused else None,
+                      torch.stack(losses))
+    for i in (0, 1, 2, 4):
+        assert torch.equal(out[True][i], out[False][i]), i
+    # load_state_dict between fused steps: the kept operands are dropped and re-packed from the loaded values
+    cfg, sd, model, trainer, batch, ep, eq = _setup(tag, 3)
+    trainer.set_noise(ep, eq)
+    trainer.train_step(batch)
+    model.load_state_dict(sd)
+    trainer.set_noise(ep, eq)
+    l_after = trainer.forward_backward(batch).clone()
+    cfg, sd, model2, trainer2, batch, ep, eq = _setup(tag, 3)
+    trainer2.set_noise(ep, eq)
+    l_fresh = trainer2.forward_backward(batch).clone()
+    assert torch.equal(l_after[:2], l_fresh[:2])

@@ -97,7 +97,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.rac_abi_version() == 7
+    assert lib.rac_abi_version() == 8
 
 
 def test_model_spec_matches_oracle_spec():
