@@ -115,7 +115,7 @@ struct TrainState {
   float* wg_part = nullptr;           // split-K partials of the layer being processed
   int lstm_fused = 0;                 // RAC_TRAIN_LSTM_FUSED=1: gate convolution with the fused cell epilogue, one launch per cell and step (A/B)
   float* lstm_gx = nullptr;           // [steps][M3][4g] input-half gate pre-activations of the cell being processed
-  int w_prefetch = 8;                 // k-blocks of L2 weight prefetch distance in the weight-streaming GEMMs (RAC_TRAIN_W_PREFETCH, 0 = off)
+  int w_prefetch = 0;                 // k-blocks of L2 weight prefetch distance in the weight-streaming GEMMs (RAC_TRAIN_W_PREFETCH; off: measured no effect at 4-32)
   int w_tiled = 1;                    // bf16 weights in the k-block-major packing (0: row-major Wp[n][tap][c]; RAC_TRAIN_W_TILED=0, SIMT, Wd)
   int tile_model = 1;                 // RAC_TRAIN_TILE_MODEL=0: round-1 tile rule (256-row tiles unless < 120 of them), no split-K
   int splitk = 1;                     // RAC_TRAIN_SPLITK=0: no split-K in the small-M forward / dgrad GEMMs (A/B measurements)
