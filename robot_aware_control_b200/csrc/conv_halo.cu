@@ -104,6 +104,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();  // (PDL, ptx.cuh) the next kernel's prologue may start
+  griddep_wait();               // everything below reads / writes global memory of earlier kernels
   const int tiles_per_img = hg.ytiles * hg.xtiles;
 
   if (warp == 0 && lane == 0) {
@@ -218,7 +220,7 @@ static cudaError_t launch_halo_t(const ConvOp& op, const HaloGeom& hg, const CUt
                                  cudaStream_t stream) {
   using Cfg = HaloCfg<CIN_KB, BLOCK_N>;
   const int grid = hg.num_tiles < num_sms ? hg.num_tiles : num_sms;
-  conv_halo_kernel<CIN_KB, BLOCK_N, EPI><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tm_a, op.tm.w, hg, op.g, op.e);
+  return launch_pdl(conv_halo_kernel<CIN_KB, BLOCK_N, EPI>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, tm_a, op.tm.w, hg, op.g, op.e);
   return cudaGetLastError();
 }
 

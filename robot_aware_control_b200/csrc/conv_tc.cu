@@ -127,6 +127,8 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();  // (PDL, ptx.cuh) the next kernel's prologue may start
+  griddep_wait();               // everything below reads / writes global memory of earlier kernels
   auto stamp = [&](int i) {
     if (g.timeline) {
       unsigned long long t;
@@ -503,8 +505,7 @@ static cudaError_t launch_tc_t(const ConvOp& op, int num_sms, cudaStream_t strea
   using Cfg = TcCfg<BLOCK_M, BLOCK_N>;
   const int num_tiles = op.g.num_m_tiles * op.g.num_n_tiles * (op.g.ksplit > 1 ? op.g.ksplit : 1);
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  conv_tc_kernel<BLOCK_M, BLOCK_N, EPI><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(op.tm, op.g, op.e);
-  return cudaGetLastError();
+  return launch_pdl(conv_tc_kernel<BLOCK_M, BLOCK_N, EPI>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, op.tm, op.g, op.e);
 }
 template <int BLOCK_M, int BLOCK_N, int EPI>
 static cudaError_t launch_simt_t(const ConvOp& op, cudaStream_t stream) {

@@ -91,6 +91,8 @@ conv_tc2_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Ep
   cluster_sync_all();  // the peer's barriers are initialised before anything is signalled on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();  // (PDL, ptx.cuh) the next kernel's prologue may start
+  griddep_wait();               // everything below reads / writes global memory of earlier kernels
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -236,9 +238,9 @@ cudaError_t launch_conv_tc2(const ConvOp& op, const ConvTmaps& tm2, int num_sms,
   if (pairs > num_tiles) pairs = num_tiles;
   if (pairs < 1) return cudaErrorInvalidValue;
   if (op.epi == EPI_LSTM)
-    conv_tc2_kernel<EPI_LSTM><<<2 * pairs, Tc2Cfg::kThreads, Tc2Cfg::kSmemBytes, stream>>>(tm2, op.g, op.e);
+    return launch_pdl(conv_tc2_kernel<EPI_LSTM>, dim3(2 * pairs), dim3(Tc2Cfg::kThreads), Tc2Cfg::kSmemBytes, stream, tm2, op.g, op.e);
   else if (op.epi == EPI_ACT)
-    conv_tc2_kernel<EPI_ACT><<<2 * pairs, Tc2Cfg::kThreads, Tc2Cfg::kSmemBytes, stream>>>(tm2, op.g, op.e);
+    return launch_pdl(conv_tc2_kernel<EPI_ACT>, dim3(2 * pairs), dim3(Tc2Cfg::kThreads), Tc2Cfg::kSmemBytes, stream, tm2, op.g, op.e);
   else
     return cudaErrorInvalidValue;
   return cudaGetLastError();

@@ -104,6 +104,8 @@ conv_tc_mc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const 
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();  // (PDL, ptx.cuh) the next kernel's prologue may start
+  griddep_wait();               // everything below reads / writes global memory of earlier kernels
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -273,7 +275,7 @@ cudaError_t launch_conv_tc_mc(const ConvOp& op, const ConvTmaps& tm_mc, int num_
   int pairs = num_sms / 2;
   if (pairs > num_tiles) pairs = num_tiles;
   if (pairs < 1) return cudaErrorInvalidValue;
-  conv_tc_mc_kernel<<<2 * pairs, McCfg::kThreads, McCfg::kSmemBytes, stream>>>(tm_mc, op.g, op.e);
+  return launch_pdl(conv_tc_mc_kernel, dim3(2 * pairs), dim3(McCfg::kThreads), McCfg::kSmemBytes, stream, tm_mc, op.g, op.e);
   return cudaGetLastError();
 }
 

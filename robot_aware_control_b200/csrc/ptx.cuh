@@ -1,6 +1,7 @@
 // Thin inline-PTX wrappers for sm_100a: mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (MMA / TMEM).
 // Everything here is hand-written for B200; nothing is shared with other architectures.
 #pragma once
+#include <stdlib.h>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -55,6 +56,15 @@ __device__ __forceinline__ void epi_bar_sync(int nthreads) {
 }
 
 // ---------------------------------------------------------------- TMA
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor in the stream is still running, as soon as every CTA of the predecessor has executed
+// launch_dependents (or exited); it must execute griddep_wait() before it touches anything the predecessor (or any
+// earlier kernel) reads or writes -- the wait returns when the predecessor has completed and its memory is visible.
+// The tcgen05 kernels put their whole prologue (tensor-map prefetch, mbarrier init, TMEM allocation, cluster sync)
+// in front of the wait: a few microseconds per launch that now overlap the tail of the previous kernel.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
@@ -267,6 +277,23 @@ constexpr uint32_t kIdescBMn = 1u << 16;  // instruction descriptor: B operand M
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(128 >> 4) << 24);
+}
+
+// Host side: kernel launch with (pdl) or without the programmatic-stream-serialization attribute. RAC_PDL=0 turns it off.
+inline bool pdl_enabled() {
+  static const int on = [] { const char* v = getenv("RAC_PDL"); return v ? atoi(v) : 1; }();
+  return on != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 }  // namespace rac

@@ -83,6 +83,8 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();  // (PDL, ptx.cuh) the next kernel's prologue may start
+  griddep_wait();               // everything below reads / writes global memory of earlier kernels
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -189,8 +191,7 @@ cudaError_t wgrad_tc_set_attributes() {
 cudaError_t launch_wgrad_tc(const WgradTmaps& tm, const WgradGeom& g, cudaStream_t s) {
   if (g.rows % 16 || g.rows > kMaxRows || g.num_ctiles < 1 || g.num_ctiles > kWgMaxCTiles) return cudaErrorInvalidValue;
   dim3 grid(static_cast<unsigned>(g.n_tiles * g.num_ctiles * g.taps), static_cast<unsigned>(g.splits));
-  wgrad_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(tm, g);
-  return cudaGetLastError();
+  return launch_pdl(wgrad_tc_kernel, grid, dim3(kThreads), kSmemBytes, s, tm, g);
 }
 
 cudaError_t launch_wgrad_reduce(const float* part, int splits, long long n, long long split_stride, float* out,
