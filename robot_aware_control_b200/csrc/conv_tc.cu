@@ -560,6 +560,7 @@ cudaError_t launch_conv_simt(const ConvOp& op, cudaStream_t stream) {
 // destination segments exactly as epi_f32 would have done. One thread per 4 columns of one row.
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const EpiParams e, int ksplit, long long rows, int ncols) {
+  pdl_entry();
   const int q4 = ncols >> 2;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= rows * q4) return;
@@ -590,7 +591,7 @@ splitk_reduce_kernel(const EpiParams e, int ksplit, long long rows, int ncols) {
 }
 cudaError_t launch_splitk_reduce(const EpiParams& e, int ksplit, long long rows, int ncols, cudaStream_t stream) {
   const long long total = rows * (ncols >> 2);
-  splitk_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(e, ksplit, rows, ncols);
+  if (cudaError_t e_ = launch_pdl_small(splitk_reduce_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, e, ksplit, rows, ncols); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 

@@ -2,6 +2,7 @@
 // image preparation, planning-cost reductions and the training criteria (forward values).
 #include "misc_kernels.cuh"
 #include "epilogue.cuh"
+#include "ptx.cuh"
 
 namespace rac {
 
@@ -17,6 +18,7 @@ __global__ void __launch_bounds__(256, 2)
 first_conv_kernel(const float* __restrict__ img4, const float* __restrict__ mask_a, const float* __restrict__ mask_b,
                   long long mask_bstride, const float* __restrict__ w, const float* __restrict__ bias,
                   __nv_bfloat16* __restrict__ out, float* __restrict__ raw_out, int B, int H, int W) {
+  pdl_entry();
   __shared__ __align__(16) float sw[9 * CIN * 64];
   __shared__ float sb[64];
   for (int i = threadIdx.x; i < 9 * CIN * 64; i += blockDim.x) {
@@ -105,12 +107,14 @@ cudaError_t launch_first_conv(const float* img4, const float* mask_a, const floa
   if (static_cast<long long>(B) * H * (W / 4) >= (1ll << 31)) return cudaErrorInvalidValue;
   const long long cap = 148 * 2;
   const unsigned grid = static_cast<unsigned>(groups < cap ? groups : cap);
+  cudaError_t err;
   if (cin == 3)
-    first_conv_kernel<3><<<grid, 256, 0, s>>>(img4, mask_a, mask_b, mask_bstride, w, bias, out, raw_out, B, H, W);
+    err = launch_pdl_small(first_conv_kernel<3>, dim3(grid), dim3(256), 0, s, img4, mask_a, mask_b, mask_bstride, w, bias, out, raw_out, B, H, W);
   else if (cin == 4)
-    first_conv_kernel<4><<<grid, 256, 0, s>>>(img4, mask_a, mask_b, mask_bstride, w, bias, out, raw_out, B, H, W);
+    err = launch_pdl_small(first_conv_kernel<4>, dim3(grid), dim3(256), 0, s, img4, mask_a, mask_b, mask_bstride, w, bias, out, raw_out, B, H, W);
   else
-    first_conv_kernel<5><<<grid, 256, 0, s>>>(img4, mask_a, mask_b, mask_bstride, w, bias, out, raw_out, B, H, W);
+    err = launch_pdl_small(first_conv_kernel<5>, dim3(grid), dim3(256), 0, s, img4, mask_a, mask_b, mask_bstride, w, bias, out, raw_out, B, H, W);
+  if (err != cudaSuccess) return err;
   return cudaGetLastError();
 }
 
@@ -127,6 +131,7 @@ __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
 __global__ void __launch_bounds__(256)
 maxpool2_kernel(const __nv_bfloat16* __restrict__ in, int in_cstride, int in_coff, __nv_bfloat16* __restrict__ out,
                 int B, int H, int W, int C) {
+  pdl_entry();
   const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
   const size_t total = static_cast<size_t>(B) * Ho * Wo * C8;
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -146,7 +151,7 @@ maxpool2_kernel(const __nv_bfloat16* __restrict__ in, int in_cstride, int in_cof
 cudaError_t launch_maxpool2(const __nv_bfloat16* in, int in_cstride, int in_coff, __nv_bfloat16* out, int B, int H,
                             int W, int C, cudaStream_t s) {
   const size_t total = static_cast<size_t>(B) * (H / 2) * (W / 2) * (C / 8);
-  maxpool2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, in_cstride, in_coff, out, B, H, W, C);
+  if (cudaError_t e_ = launch_pdl_small(maxpool2_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, in, in_cstride, in_coff, out, B, H, W, C); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
@@ -154,6 +159,7 @@ cudaError_t launch_maxpool2(const __nv_bfloat16* in, int in_cstride, int in_coff
 __global__ void __launch_bounds__(256)
 aux_tile_kernel(const float* __restrict__ action, int astride, int adim, const float* __restrict__ r,
                 const float* __restrict__ r2, int rdim, __nv_bfloat16* __restrict__ aux, int B, int HW) {
+  pdl_entry();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // (b, pos, c8)
   const size_t total = static_cast<size_t>(B) * HW * 8;
   if (i >= total) return;
@@ -176,8 +182,8 @@ cudaError_t launch_aux_tile(const float* action, int astride, int adim, const fl
                             __nv_bfloat16* aux, int B, int HW, cudaStream_t s) {
   if (adim + (r ? rdim : 0) + (r2 ? rdim : 0) > 64) return cudaErrorInvalidValue;
   const size_t total = static_cast<size_t>(B) * HW * 8;
-  aux_tile_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(action, astride, adim, r, r2, rdim, aux, B,
-                                                                             HW);
+  if (cudaError_t e_ = launch_pdl_small(aux_tile_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, action, astride, adim, r, r2, rdim, aux, B,
+                                                                             HW); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
@@ -234,6 +240,7 @@ __global__ void __launch_bounds__(128)
 cost_finish_kernel(const float* __restrict__ part, int nparts, int dontcare, float weight, int accumulate,
                    double* __restrict__ sum_cost, float* __restrict__ step_cost, int B, double* const* peers,
                    int peer_world, long long peer_offset) {
+  pdl_entry();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const float* p = part + static_cast<size_t>(b) * nparts * 2;
@@ -282,8 +289,8 @@ cudaError_t launch_peer_barrier(uint32_t* const* pads, int base, int rank, int w
 cudaError_t launch_cost_finish(const float* cost_part, int nparts, int dontcare, float weight, int accumulate,
                                double* sum_cost, float* step_cost, int B, cudaStream_t s, double* const* peers,
                                int peer_world, long long peer_offset) {
-  cost_finish_kernel<<<(B + 127) / 128, 128, 0, s>>>(cost_part, nparts, dontcare, weight, accumulate, sum_cost,
-                                                     step_cost, B, peers, peer_world, peer_offset);
+  if (cudaError_t e_ = launch_pdl_small(cost_finish_kernel, dim3((B + 127) / 128), dim3(128), 0, s, cost_part, nparts, dontcare, weight, accumulate, sum_cost,
+                                                     step_cost, B, peers, peer_world, peer_offset); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
@@ -514,6 +521,7 @@ cudaError_t launch_kl_loss(const float* mu1, const float* lv1, const float* mu2,
 // 16-byte accesses; the source (<= 393 KB) stays in L2.
 __global__ void __launch_bounds__(256)
 broadcast_candidate_kernel(__nv_bfloat16* __restrict__ buf, int HW, int cstride, int coff, int C8, int first, int B) {
+  pdl_entry();
   const long long per = static_cast<long long>(HW) * C8;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= per * (B - first)) return;
@@ -529,7 +537,7 @@ cudaError_t launch_broadcast_candidate(__nv_bfloat16* buf, int HW, int cstride, 
   if (B <= first) return cudaSuccess;
   if (C % 8 || cstride % 8 || coff % 8) return cudaErrorInvalidValue;
   const long long total = static_cast<long long>(HW) * (C / 8) * (B - first);
-  broadcast_candidate_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(buf, HW, cstride, coff, C / 8, first, B);
+  if (cudaError_t e_ = launch_pdl_small(broadcast_candidate_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, buf, HW, cstride, coff, C / 8, first, B); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 

@@ -64,6 +64,15 @@ __device__ __forceinline__ void epi_bar_sync(int nthreads) {
 // in front of the wait: a few microseconds per launch that now overlap the tail of the previous kernel.
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// The small (non-tcgen05) kernels have no prologue worth overlapping; for them the point is the launch latency itself:
+// trigger + wait as the first statement lets the NEXT kernel's CTAs become resident (and, for a tcgen05 kernel, run
+// their prologue) during this kernel's last wave, and lets this kernel be resident before its predecessor has drained.
+// (The trigger only takes effect once EVERY CTA of the grid has executed it, i.e. when the last wave has started, so
+// early dependents never take SM slots from CTAs of this grid that have not started yet. No TMEM is held here.)
+__device__ __forceinline__ void pdl_entry() {
+  griddep_launch_dependents();
+  griddep_wait();
+}
 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -239,6 +248,14 @@ __device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* m, uint64_t* b
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d_mc(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                               int c3, int c4, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5, %6, %7, %8}], [%2], %3;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 // arrive on the barrier at this offset in every CTA of `mask` once the MMAs issued so far by this thread completed
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -293,6 +310,23 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// The same for the small kernels that begin with pdl_entry(); RAC_PDL_SMALL=0 launches those the plain way (A/B switch).
+inline bool pdl_small_enabled() {
+  static const int on = [] { const char* v = getenv("RAC_PDL_SMALL"); return v ? atoi(v) : 1; }();
+  return on != 0 && pdl_enabled();
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_small(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                    Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_small_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

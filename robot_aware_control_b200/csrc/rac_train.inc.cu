@@ -40,6 +40,7 @@ struct TLayer {
   // its contraction)
   bf16* dyT = nullptr;
   int taps = 0, ctot = 0, n_packed = 0, kpad = 0;
+  int vec_ok = 0;        // the fused optimizer step may walk the flat side as float4 (adam_pack_vec_ok)
 };
 
 struct VggRt {  // one vgg_layer (conv3x3 no bias + BatchNorm + LeakyReLU) at one time step
@@ -147,7 +148,7 @@ struct TrainState {
   int M[4];
 };
 
-constexpr int kFwBlocks = 148;  // CTAs of the first layer's weight-gradient kernel (one partial sum each)
+constexpr int kFwBlocks = 296;  // CTAs of the first layer's weight-gradient kernel (one partial sum each; two per SM)
 
 inline int pick_bn(int n) { return n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : 64); }
 
@@ -1067,6 +1068,8 @@ int rac_train_create(rac_handle* h, const rac_train_config* cfg, const rac_train
     L.d = layers[i];
     const LayerSpec& sp = h->spec[i];
     L.taps = sp.ks * sp.ks; L.ctot = sp.ctot; L.n_packed = sp.n_packed; L.kpad = round_up(sp.n_packed, 64);
+    if (i >= 1 && L.d.w_count > 0 && L.d.row_off && L.d.col_off)
+      CK(adam_pack_vec_ok(L.d.row_off, L.d.col_off, L.n_packed, L.taps, L.ctot, &L.vec_ok));
   }
   // geometry (rows) per layer for scratch sizing
   auto rows_of = [&](int layer) -> size_t {
@@ -1478,7 +1481,8 @@ int rac_train_adam_step(rac_handle* h, void* stream) {
     TLayer& L = T->L[i];
     if (!T->deferred[i]) { T->packed_valid[i] = false; continue; }
     CK(launch_adam_pack(T->params, T->m, T->v, L.dwp, L.d.row_off, L.d.col_off, L.n_packed, L.taps, L.ctot, L.d.flip,
-                        T->w_tiled, L.wp, T->cfg.lr, T->cfg.beta1, T->cfg.beta2, T->cfg.adam_eps, T->adam_t, T->grad_scale, st));
+                        T->w_tiled, L.wp, T->cfg.lr, T->cfg.beta1, T->cfg.beta2, T->cfg.adam_eps, T->adam_t, T->grad_scale, st,
+                        L.vec_ok));
     h->launches++;
     T->packed_valid[i] = true;
     T->deferred[i] = false;

@@ -14,6 +14,7 @@
 // The affine vectors are read from the flat parameter buffer in the reference's own order (gate * hid + channel).
 #include "train_kernels.cuh"
 #include "epilogue.cuh"
+#include "ptx.cuh"
 
 namespace rac {
 
@@ -62,6 +63,7 @@ __device__ __forceinline__ int stat_cell(int quarter, int k) { return 32 + quart
 
 __global__ void __launch_bounds__(kGnThreads)
 gn_cell_fwd_kernel(const GnCellArgs a) {
+  pdl_entry();
   __shared__ float sh[(kGnThreads / 32) * 16];
   const int hid = a.hid, P = a.P, QW = hid / 4, R = kGnThreads / QW;
   const int b = blockIdx.x, quarter = blockIdx.y;
@@ -149,6 +151,7 @@ gn_cell_fwd_kernel(const GnCellArgs a) {
 
 __global__ void __launch_bounds__(kGnThreads)
 gn_cell_bwd_kernel(const GnCellArgs a) {
+  pdl_entry();
   __shared__ float sh[(kGnThreads / 32) * 16];
   __shared__ float s_par[14][kGnThreads];
   const int hid = a.hid, P = a.P, QW = hid / 4, R = kGnThreads / QW;
@@ -266,6 +269,7 @@ gn_cell_bwd_kernel(const GnCellArgs a) {
 __global__ void __launch_bounds__(256)
 gn_affine_fold_kernel(const float* __restrict__ part, int B, int hid, float* __restrict__ grads, long long g_ih,
                       long long b_ih, long long g_hh, long long b_hh, long long g_c, long long b_c) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 14 * hid) return;
   float t = 0.f;
@@ -286,15 +290,15 @@ bool gn_shape_ok(const GnCellArgs& a) {
 
 cudaError_t launch_gn_cell_fwd(const GnCellArgs& a, cudaStream_t s) {
   if (!gn_shape_ok(a)) return cudaErrorInvalidValue;
-  gn_cell_fwd_kernel<<<dim3(a.B, 4), kGnThreads, 0, s>>>(a);
+  if (cudaError_t e_ = launch_pdl_small(gn_cell_fwd_kernel, dim3(a.B, 4), dim3(kGnThreads), 0, s, a); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
 cudaError_t launch_gn_cell_bwd(const GnCellArgs& a, float* grads, cudaStream_t s) {
   if (!gn_shape_ok(a) || !a.part || !a.dy || !a.d_ih || !a.d_hh || !a.dh || !a.dc) return cudaErrorInvalidValue;
-  gn_cell_bwd_kernel<<<dim3(a.B, 4), kGnThreads, 0, s>>>(a);
-  gn_affine_fold_kernel<<<(14 * a.hid + 255) / 256, 256, 0, s>>>(a.part, a.B, a.hid, grads, a.g_ih, a.b_ih, a.g_hh,
-                                                                a.b_hh, a.g_c, a.b_c);
+  if (cudaError_t e_ = launch_pdl_small(gn_cell_bwd_kernel, dim3(a.B, 4), dim3(kGnThreads), 0, s, a); e_ != cudaSuccess) return e_;
+  if (cudaError_t e_ = launch_pdl_small(gn_affine_fold_kernel, dim3((14 * a.hid + 255) / 256), dim3(256), 0, s, a.part, a.B, a.hid, grads, a.g_ih, a.b_ih, a.g_hh,
+                                                                a.b_hh, a.g_c, a.b_c); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 

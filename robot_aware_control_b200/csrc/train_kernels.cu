@@ -4,6 +4,7 @@
 
 #include "train_kernels.cuh"
 #include "epilogue.cuh"
+#include "ptx.cuh"
 
 namespace rac {
 
@@ -16,6 +17,7 @@ __global__ void __launch_bounds__(256)
 pack_weights_kernel(const float* __restrict__ params, const long long* __restrict__ row_off,
                     const int* __restrict__ col_off, int n_packed, int taps, int ctot, int flip, int tiled,
                     __nv_bfloat16* __restrict__ wp) {
+  pdl_entry();
   __shared__ float tile[25][65];
   const int c0 = blockIdx.y * 64;
   // a CTA walks several packed rows (a few thousand CTAs of 1600 elements each were launch-bound, not HBM-bound)
@@ -43,7 +45,7 @@ cudaError_t launch_pack_weights(const float* params, const long long* row_off, c
                                 int taps, int ctot, int flip, __nv_bfloat16* wp, cudaStream_t s, int tiled) {
   if (ctot % 64 != 0 || taps > 25) return cudaErrorInvalidValue;
   const int gx = std::min(n_packed, std::max(1, 1184 / (ctot / 64)));
-  pack_weights_kernel<<<dim3(gx, ctot / 64), 256, 0, s>>>(params, row_off, col_off, n_packed, taps, ctot, flip, tiled, wp);
+  if (cudaError_t e_ = launch_pdl_small(pack_weights_kernel, dim3(gx, ctot / 64), dim3(256), 0, s, params, row_off, col_off, n_packed, taps, ctot, flip, tiled, wp); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
@@ -52,6 +54,7 @@ cudaError_t launch_pack_weights(const float* params, const long long* row_off, c
 __global__ void __launch_bounds__(256)
 transpose_flip_kernel(const __nv_bfloat16* __restrict__ wp, int n_packed, int taps, int ctot, int kpad,
                       __nv_bfloat16* __restrict__ wd) {
+  pdl_entry();
   __shared__ __nv_bfloat16 tile[64][66];
   const int n0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -83,7 +86,7 @@ transpose_flip_kernel(const __nv_bfloat16* __restrict__ wp, int n_packed, int ta
 cudaError_t launch_transpose_flip(const __nv_bfloat16* wp, int n_packed, int taps, int ctot, int kpad,
                                   __nv_bfloat16* wd, cudaStream_t s) {
   if (ctot % 64 != 0 || kpad % 2 != 0) return cudaErrorInvalidValue;
-  transpose_flip_kernel<<<dim3((kpad + 63) / 64, ctot / 64), 256, 0, s>>>(wp, n_packed, taps, ctot, kpad, wd);
+  if (cudaError_t e_ = launch_pdl_small(transpose_flip_kernel, dim3((kpad + 63) / 64, ctot / 64), dim3(256), 0, s, wp, n_packed, taps, ctot, kpad, wd); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
@@ -91,6 +94,7 @@ __global__ void __launch_bounds__(256)
 unpack_grads_kernel(const float* __restrict__ dwp, const long long* __restrict__ row_off,
                     const int* __restrict__ col_off, int n_packed, int taps, int ctot, int flip,
                     float* __restrict__ grads) {
+  pdl_entry();
   __shared__ float tile[25][65];
   const int c0 = blockIdx.y * 64;
   for (int n = blockIdx.x; n < n_packed; n += gridDim.x) {
@@ -114,7 +118,7 @@ cudaError_t launch_unpack_grads(const float* dwp, const long long* row_off, cons
                                 int ctot, int flip, float* grads, cudaStream_t s) {
   if (ctot % 64 != 0 || taps > 25) return cudaErrorInvalidValue;
   const int gx = std::min(n_packed, std::max(1, 1184 / (ctot / 64)));
-  unpack_grads_kernel<<<dim3(gx, ctot / 64), 256, 0, s>>>(dwp, row_off, col_off, n_packed, taps, ctot, flip, grads);
+  if (cudaError_t e_ = launch_pdl_small(unpack_grads_kernel, dim3(gx, ctot / 64), dim3(256), 0, s, dwp, row_off, col_off, n_packed, taps, ctot, flip, grads); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
@@ -134,63 +138,118 @@ __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& 
 // parameters); the flat gradient buffer is NOT written for this layer (rac_train_unpack_deferred does it on demand).
 // Tiling as pack_weights_kernel: the flat side is walked linearly (64 channels x taps contiguous floats per packed
 // row), the packed side with c fastest, transposed through shared memory.
+// VEC: the 64 channels of every block are 64 * taps CONTIGUOUS, 16-byte aligned floats of the flat buffers (one
+// (cout, cin-range) slab of the PyTorch weight; adam_pack_vec_ok checks the layer's tables once): the flat side then
+// moves as float4 (quad q = elements 4q .. 4q+3 of the slab) and the index arithmetic is paid once per quad. ncu of the
+// scalar version on the 5x5 gate convolution (profiles/r02_train_top_ncu_s18.txt): 178 instructions per weight, issue
+// slots 64 % busy, DRAM 45 % of peak -- instruction-bound, not memory-bound. Same update, element by element.
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 adam_pack_kernel(float* __restrict__ params, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ dwp,
                  const long long* __restrict__ row_off, const int* __restrict__ col_off, int n_packed, int taps, int ctot,
                  int flip, int tiled, __nv_bfloat16* __restrict__ wp, float lr, float b1, float b2, float eps, float bc1,
                  float bc2_sqrt, float gscale) {
+  pdl_entry();
   __shared__ float tg[25][65], tp[25][65];
   const int c0 = blockIdx.y * 64;
   const float step = lr / bc1;
   for (int n = blockIdx.x; n < n_packed; n += gridDim.x) {
     const long long ro = row_off[n];
-    // (1) all parameter / moment loads of this thread's (up to 7) elements go out first: three 4-byte streams per
-    // element issued one element at a time left ~18 KB in flight per SM (the first version ran at 3 TB/s)
-    constexpr int kPer = 7;  // ceil(64 * 25 / 256)
-    float pi[kPer], mi[kPer], vi[kPer];
-    long long fo[kPer];  // (kept in registers: recomputing them in (3) to gain a CTA per SM measured slower)
-    int tfs[kPer], cls[kPer];
+    if constexpr (VEC) {
+      constexpr int kQ = 2;  // ceil(16 * 25 / 256) quads per thread
+      const int nq = 16 * taps;
+      const long long base = ro >= 0 ? ro + col_off[c0] : 0;
+      float4* p4 = reinterpret_cast<float4*>(params + base);
+      float4* m4 = reinterpret_cast<float4*>(m + base);
+      float4* v4 = reinterpret_cast<float4*>(v + base);
+      float4 pi[kQ], mi[kQ], vi[kQ];
+      if (ro >= 0) {
 #pragma unroll
-    for (int k = 0; k < kPer; ++k) {
-      const int j = threadIdx.x + k * 256;
-      fo[k] = -1;
-      if (j < 64 * taps) {
-        const int cl = j / taps, tap = j - cl * taps;
-        const int co = col_off[c0 + cl];
-        tfs[k] = flip ? taps - 1 - tap : tap;
-        cls[k] = cl;
-        if (ro >= 0 && co >= 0) {
-          fo[k] = ro + co + tap;
-          pi[k] = __ldcs(params + fo[k]); mi[k] = __ldcs(m + fo[k]); vi[k] = __ldcs(v + fo[k]);
-        } else {
-          fo[k] = -2;  // padding column / row: the operand gets a zero
+        for (int k = 0; k < kQ; ++k) {
+          const int q = threadIdx.x + k * 256;
+          if (q < nq) { pi[k] = __ldcs(p4 + q); mi[k] = __ldcs(m4 + q); vi[k] = __ldcs(v4 + q); }
+        }
+        for (int j = threadIdx.x; j < 16 * taps; j += blockDim.x) {
+          const int tap = j >> 4, cl = (j & 15) * 4;
+          const float4 g = __ldcs(reinterpret_cast<const float4*>(dwp + (static_cast<long long>(n) * taps + tap) * ctot + c0 + cl));
+          tg[tap][cl] = g.x; tg[tap][cl + 1] = g.y; tg[tap][cl + 2] = g.z; tg[tap][cl + 3] = g.w;
         }
       }
-    }
-    // (2) the packed gradient of the row, transposed through shared memory
-    if (ro >= 0) {
-      for (int j = threadIdx.x; j < 16 * taps; j += blockDim.x) {
-        const int tap = j >> 4, cl = (j & 15) * 4;
-        const float4 g = __ldcs(reinterpret_cast<const float4*>(dwp + (static_cast<long long>(n) * taps + tap) * ctot + c0 + cl));
-        tg[tap][cl] = g.x; tg[tap][cl + 1] = g.y; tg[tap][cl + 2] = g.z; tg[tap][cl + 3] = g.w;
-      }
-    }
-    __syncthreads();  // (also: the previous row's operand write has finished reading tp)
-    // (3) update, store, and the new parameter into the operand tile
+      __syncthreads();  // (also: the previous row's operand write has finished reading tp)
 #pragma unroll
-    for (int k = 0; k < kPer; ++k) {
-      if (fo[k] == -1) continue;
-      float pn = 0.f;
-      if (fo[k] >= 0) {
-        adam_update(pi[k], tg[tfs[k]][cls[k]] * gscale, mi[k], vi[k], b1, b2, step, bc2_sqrt, eps);
-        __stcs(m + fo[k], mi[k]);
-        __stcs(v + fo[k], vi[k]);
-        __stcs(params + fo[k], pi[k]);
-        pn = pi[k];
+      for (int k = 0; k < kQ; ++k) {
+        const int q = threadIdx.x + k * 256;
+        if (q >= nq) continue;
+        int cl = (4 * q) / taps, tap = 4 * q - cl * taps;
+        float pe[4] = {0.f, 0.f, 0.f, 0.f}, me[4], ve[4];
+        if (ro >= 0) {
+          pe[0] = pi[k].x; pe[1] = pi[k].y; pe[2] = pi[k].z; pe[3] = pi[k].w;
+          me[0] = mi[k].x; me[1] = mi[k].y; me[2] = mi[k].z; me[3] = mi[k].w;
+          ve[0] = vi[k].x; ve[1] = vi[k].y; ve[2] = vi[k].z; ve[3] = vi[k].w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int tf = flip ? taps - 1 - tap : tap;
+          if (ro >= 0) adam_update(pe[i], tg[tf][cl] * gscale, me[i], ve[i], b1, b2, step, bc2_sqrt, eps);
+          tp[tf][cl] = pe[i];  // (padding row: the operand gets zeros)
+          if (++tap == taps) { tap = 0; ++cl; }
+        }
+        if (ro >= 0) {
+          __stcs(m4 + q, make_float4(me[0], me[1], me[2], me[3]));
+          __stcs(v4 + q, make_float4(ve[0], ve[1], ve[2], ve[3]));
+          __stcs(p4 + q, make_float4(pe[0], pe[1], pe[2], pe[3]));
+        }
       }
-      tp[tfs[k]][cls[k]] = pn;
+      __syncthreads();
+    } else {
+      // (1) all parameter / moment loads of this thread's (up to 7) elements go out first: three 4-byte streams per
+      // element issued one element at a time left ~18 KB in flight per SM (the first version ran at 3 TB/s)
+      constexpr int kPer = 7;  // ceil(64 * 25 / 256)
+      float pi[kPer], mi[kPer], vi[kPer];
+      long long fo[kPer];  // (kept in registers: recomputing them in (3) to gain a CTA per SM measured slower)
+      int tfs[kPer], cls[kPer];
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) {
+        const int j = threadIdx.x + k * 256;
+        fo[k] = -1;
+        if (j < 64 * taps) {
+          const int cl = j / taps, tap = j - cl * taps;
+          const int co = col_off[c0 + cl];
+          tfs[k] = flip ? taps - 1 - tap : tap;
+          cls[k] = cl;
+          if (ro >= 0 && co >= 0) {
+            fo[k] = ro + co + tap;
+            pi[k] = __ldcs(params + fo[k]); mi[k] = __ldcs(m + fo[k]); vi[k] = __ldcs(v + fo[k]);
+          } else {
+            fo[k] = -2;  // padding column / row: the operand gets a zero
+          }
+        }
+      }
+      // (2) the packed gradient of the row, transposed through shared memory
+      if (ro >= 0) {
+        for (int j = threadIdx.x; j < 16 * taps; j += blockDim.x) {
+          const int tap = j >> 4, cl = (j & 15) * 4;
+          const float4 g = __ldcs(reinterpret_cast<const float4*>(dwp + (static_cast<long long>(n) * taps + tap) * ctot + c0 + cl));
+          tg[tap][cl] = g.x; tg[tap][cl + 1] = g.y; tg[tap][cl + 2] = g.z; tg[tap][cl + 3] = g.w;
+        }
+      }
+      __syncthreads();  // (also: the previous row's operand write has finished reading tp)
+      // (3) update, store, and the new parameter into the operand tile
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) {
+        if (fo[k] == -1) continue;
+        float pn = 0.f;
+        if (fo[k] >= 0) {
+          adam_update(pi[k], tg[tfs[k]][cls[k]] * gscale, mi[k], vi[k], b1, b2, step, bc2_sqrt, eps);
+          __stcs(m + fo[k], mi[k]);
+          __stcs(v + fo[k], vi[k]);
+          __stcs(params + fo[k], pi[k]);
+          pn = pi[k];
+        }
+        tp[tfs[k]][cls[k]] = pn;
+      }
+      __syncthreads();
     }
-    __syncthreads();
     // (4) bf16 operand of the next step
     for (int j = threadIdx.x; j < 32 * taps; j += blockDim.x) {
       const int tap = j >> 5, cl = (j & 31) * 2;
@@ -200,20 +259,62 @@ adam_pack_kernel(float* __restrict__ params, float* __restrict__ m, float* __res
     }
   }
 }
+// 1 in *ok (preset by the caller) survives iff every 64-channel block of the layer is a contiguous slab (col_off[cb + t] ==
+// col_off[cb] + t * taps >= 0) and every real row's slabs start on a 16-byte boundary: the conditions of adam_pack_kernel<true>
+__global__ void adam_pack_vec_check_kernel(const long long* __restrict__ row_off, const int* __restrict__ col_off,
+                                           int n_packed, int taps, int ctot, int* __restrict__ ok) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int nblk = ctot / 64;
+  bool good = true;
+  if (i < ctot) {
+    const int cb = static_cast<int>(i) / 64 * 64;
+    const int co0 = col_off[cb];
+    good = co0 >= 0 && col_off[i] == co0 + (static_cast<int>(i) - cb) * taps;
+  }
+  if (i < static_cast<long long>(n_packed) * nblk) {
+    const int n = static_cast<int>(i / nblk), cb = static_cast<int>(i % nblk) * 64;
+    const long long ro = row_off[n];
+    if (ro >= 0 && ((ro + col_off[cb]) & 3) != 0) good = false;
+  }
+  if (!good) *ok = 0;
+}
+cudaError_t adam_pack_vec_ok(const long long* row_off, const int* col_off, int n_packed, int taps, int ctot, int* ok_host) {
+  *ok_host = 0;
+  if (ctot % 64 != 0 || taps > 25 || n_packed < 1) return cudaSuccess;
+  // RAC_ADAM_PACK_VEC=0: always the scalar kernel (A/B switch)
+  if (const char* e = getenv("RAC_ADAM_PACK_VEC"))
+    if (!atoi(e)) return cudaSuccess;
+  int* d_ok = nullptr;
+  cudaError_t err = cudaMalloc(&d_ok, sizeof(int));
+  if (err != cudaSuccess) return err;
+  const int one = 1;
+  err = cudaMemcpy(d_ok, &one, sizeof(int), cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) {
+    const long long total = std::max<long long>(ctot, static_cast<long long>(n_packed) * (ctot / 64));
+    adam_pack_vec_check_kernel<<<static_cast<unsigned>((total + 255) / 256), 256>>>(row_off, col_off, n_packed, taps, ctot, d_ok);
+    err = cudaGetLastError();
+  }
+  if (err == cudaSuccess) err = cudaMemcpy(ok_host, d_ok, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(d_ok);
+  return err;
+}
 cudaError_t launch_adam_pack(float* params, float* m, float* v, const float* dwp, const long long* row_off,
                              const int* col_off, int n_packed, int taps, int ctot, int flip, int tiled,
                              __nv_bfloat16* wp, float lr, float b1, float b2, float eps, int t, float grad_scale,
-                             cudaStream_t s) {
+                             cudaStream_t s, int vec_ok) {
   if (ctot % 64 != 0 || taps > 25) return cudaErrorInvalidValue;
   const float bc1 = 1.f - powf(b1, static_cast<float>(t));
   const float bc2 = sqrtf(1.f - powf(b2, static_cast<float>(t)));
   const int gx = std::min(n_packed, std::max(1, 1184 / (ctot / 64)));
-  adam_pack_kernel<<<dim3(gx, ctot / 64), 256, 0, s>>>(params, m, v, dwp, row_off, col_off, n_packed, taps, ctot, flip, tiled,
-                                                      wp, lr, b1, b2, eps, bc1, bc2, grad_scale);
-  return cudaGetLastError();
+  if (vec_ok)
+    return launch_pdl_small(adam_pack_kernel<true>, dim3(gx, ctot / 64), dim3(256), 0, s, params, m, v, dwp, row_off, col_off,
+                            n_packed, taps, ctot, flip, tiled, wp, lr, b1, b2, eps, bc1, bc2, grad_scale);
+  return launch_pdl_small(adam_pack_kernel<false>, dim3(gx, ctot / 64), dim3(256), 0, s, params, m, v, dwp, row_off, col_off,
+                          n_packed, taps, ctot, flip, tiled, wp, lr, b1, b2, eps, bc1, bc2, grad_scale);
 }
 
 __global__ void pack_first_kernel(const float* __restrict__ w, int cin, float* __restrict__ wf) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (tap, c, o)
   if (i >= 9 * cin * 64) return;
   const int o = i & 63;
@@ -222,70 +323,89 @@ __global__ void pack_first_kernel(const float* __restrict__ w, int cin, float* _
   wf[i] = w[(o * cin + c) * 9 + tap];
 }
 cudaError_t launch_pack_first(const float* w, int cin, float* wf, cudaStream_t s) {
-  pack_first_kernel<<<(9 * cin * 64 + 255) / 256, 256, 0, s>>>(w, cin, wf);
+  if (cudaError_t e_ = launch_pdl_small(pack_first_kernel, dim3((9 * cin * 64 + 255) / 256), dim3(256), 0, s, w, cin, wf); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
 // dW[o][c][tap] += sum_pix in[pix][tap, c] * draw[pix][o]. Deterministic: every CTA walks its 64-pixel chunks in a
 // fixed order with its (k, o) products in registers and writes ONE partial per CTA; first_wgrad_fold_kernel then adds
 // the partials to gw in CTA order (no atomics: the same bits every run).
-constexpr int kFwPer = 12;  // ceil(45 * 64 / 256) (k, o) pairs per thread
+// Register tile per thread: 3 filter elements (kg, kg + 16, kg + 32) x 4 neighbouring outputs, so one pixel costs three
+// broadcast loads + one 128-bit load from shared memory for 12 FMAs (one (k, o) pair per thread and pixel meant two
+// loads per FMA: the kernel sat on the shared-memory pipe, 0.33 ms for 1.4 GFLOP).
+constexpr int kFwK = 48;  // 9 * cin <= 45 filter elements, padded with zero rows
 __global__ void __launch_bounds__(256)
 first_wgrad_kernel(const float* __restrict__ img4, const float* __restrict__ mask_a, const float* __restrict__ mask_b,
                    long long mask_bstride, const float* __restrict__ draw, float* __restrict__ part, int B, int H, int W,
                    int cin) {
-  __shared__ float sin_[64][46];
-  __shared__ float sdr[64][65];
-  const size_t total = static_cast<size_t>(B) * H * W;
+  pdl_entry();
+  __shared__ float sin_[kFwK][65];              // [filter element k = tap * cin + c][pixel]
+  __shared__ __align__(16) float sdr[64][68];   // [pixel][output channel]
+  const unsigned total = static_cast<unsigned>(B) * H * W;  // (< 2^31: checked by the launcher)
   const int K = 9 * cin;
-  float acc[kFwPer];
+  const int og = (threadIdx.x & 15) * 4, kg = threadIdx.x >> 4;
+  const int fpx = threadIdx.x & 63, fk0 = threadIdx.x >> 6;  // fill role: one pixel, filter elements fk0 + 4 j
+  float acc[3][4];
 #pragma unroll
-  for (int j = 0; j < kFwPer; ++j) acc[j] = 0.f;
-  for (size_t p0 = static_cast<size_t>(blockIdx.x) * 64; p0 < total; p0 += static_cast<size_t>(gridDim.x) * 64) {
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+  for (unsigned p0 = blockIdx.x * 64u; p0 < total; p0 += gridDim.x * 64u) {
     __syncthreads();  // the previous chunk has been consumed
-    for (int i = threadIdx.x; i < 64 * K; i += blockDim.x) {
-      const int px = i / K, k = i - px * K;
-      const size_t pix = p0 + px;
-      float v = 0.f;
-      if (pix < total) {
-        const int tap = k / cin, c = k - tap * cin;
-        const int x = static_cast<int>(pix % W), y = static_cast<int>((pix / W) % H);
-        const size_t b = pix / (static_cast<size_t>(W) * H);
-        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-          if (c < 3) v = img4[((b * H + yy) * W + xx) * 4 + c];
-          else if (c == 3) v = mask_a[b * mask_bstride + static_cast<size_t>(yy) * W + xx];
-          else v = mask_b[b * mask_bstride + static_cast<size_t>(yy) * W + xx];
+    {
+      const unsigned pix = p0 + fpx;
+      const bool live = pix < total;
+      const int x = static_cast<int>(pix % W), y = static_cast<int>((pix / W) % H);
+      const size_t b = pix / (static_cast<unsigned>(W) * H);
+#pragma unroll
+      for (int j = 0; j < kFwK / 4; ++j) {
+        const int k = fk0 + 4 * j;
+        float v = 0.f;
+        if (live && k < K) {
+          const int tap = cin == 3 ? k / 3 : (cin == 4 ? k >> 2 : k / 5);
+          const int c = k - tap * cin;
+          const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            if (c < 3) v = img4[((b * H + yy) * W + xx) * 4 + c];
+            else if (c == 3) v = mask_a[b * mask_bstride + static_cast<size_t>(yy) * W + xx];
+            else v = mask_b[b * mask_bstride + static_cast<size_t>(yy) * W + xx];
+          }
         }
+        sin_[k][fpx] = v;
       }
-      sin_[px][k] = v;
     }
-    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
-      const int px = i >> 6, o = i & 63;
-      const size_t pix = p0 + px;
-      sdr[px][o] = pix < total ? draw[pix * 64 + o] : 0.f;
+    for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
+      const int px = i >> 4, q = i & 15;
+      const unsigned pix = p0 + px;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pix < total) v = __ldcs(reinterpret_cast<const float4*>(draw + static_cast<size_t>(pix) * 64) + q);
+      *reinterpret_cast<float4*>(&sdr[px][q * 4]) = v;
     }
     __syncthreads();
-#pragma unroll
-    for (int j = 0; j < kFwPer; ++j) {
-      const int p = threadIdx.x + 256 * j;
-      if (p < K * 64) {
-        const int k = p >> 6, o = p & 63;
-        float a = acc[j];
-#pragma unroll 8
-        for (int px = 0; px < 64; ++px) a += sin_[px][k] * sdr[px][o];
-        acc[j] = a;
-      }
+#pragma unroll 4
+    for (int px = 0; px < 64; ++px) {
+      const float4 d = *reinterpret_cast<const float4*>(&sdr[px][og]);
+      const float a0 = sin_[kg][px], a1 = sin_[kg + 16][px], a2 = sin_[kg + 32][px];
+      acc[0][0] = fmaf(a0, d.x, acc[0][0]); acc[0][1] = fmaf(a0, d.y, acc[0][1]);
+      acc[0][2] = fmaf(a0, d.z, acc[0][2]); acc[0][3] = fmaf(a0, d.w, acc[0][3]);
+      acc[1][0] = fmaf(a1, d.x, acc[1][0]); acc[1][1] = fmaf(a1, d.y, acc[1][1]);
+      acc[1][2] = fmaf(a1, d.z, acc[1][2]); acc[1][3] = fmaf(a1, d.w, acc[1][3]);
+      acc[2][0] = fmaf(a2, d.x, acc[2][0]); acc[2][1] = fmaf(a2, d.y, acc[2][1]);
+      acc[2][2] = fmaf(a2, d.z, acc[2][2]); acc[2][3] = fmaf(a2, d.w, acc[2][3]);
     }
   }
+  // partial of this CTA: part[cta][k * 64 + o]
 #pragma unroll
-  for (int j = 0; j < kFwPer; ++j) {
-    const int p = threadIdx.x + 256 * j;
-    if (p < K * 64) part[static_cast<size_t>(blockIdx.x) * K * 64 + p] = acc[j];
+  for (int j = 0; j < 3; ++j) {
+    const int k = kg + 16 * j;
+    if (k < K)
+      *reinterpret_cast<float4*>(part + static_cast<size_t>(blockIdx.x) * K * 64 + k * 64 + og) =
+          make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
   }
 }
 __global__ void __launch_bounds__(256)
 first_wgrad_fold_kernel(const float* __restrict__ part, int nblk, float* __restrict__ gw, int cin) {
+  pdl_entry();
   const int K = 9 * cin;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= K * 64) return;
@@ -299,12 +419,12 @@ cudaError_t launch_first_wgrad(const float* img4, const float* mask_a, const flo
                                const float* draw, float* gw, int B, int H, int W, int cin, float* part, int max_blocks,
                                cudaStream_t s) {
   const size_t total = static_cast<size_t>(B) * H * W;
-  if (cin < 3 || cin > 5 || !part || max_blocks < 1) return cudaErrorInvalidValue;
+  if (cin < 3 || cin > 5 || !part || max_blocks < 1 || total >= (1ull << 31)) return cudaErrorInvalidValue;
   int grid = static_cast<int>((total + 63) / 64);
   if (grid > max_blocks) grid = max_blocks;
   if (grid < 1) return cudaSuccess;
-  first_wgrad_kernel<<<grid, 256, 0, s>>>(img4, mask_a, mask_b, mask_bstride, draw, part, B, H, W, cin);
-  first_wgrad_fold_kernel<<<(9 * cin * 64 + 255) / 256, 256, 0, s>>>(part, grid, gw, cin);
+  if (cudaError_t e_ = launch_pdl_small(first_wgrad_kernel, dim3(grid), dim3(256), 0, s, img4, mask_a, mask_b, mask_bstride, draw, part, B, H, W, cin); e_ != cudaSuccess) return e_;
+  if (cudaError_t e_ = launch_pdl_small(first_wgrad_fold_kernel, dim3((9 * cin * 64 + 255) / 256), dim3(256), 0, s, part, grid, gw, cin); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
@@ -450,6 +570,7 @@ __device__ __forceinline__ bool last_block_of_column_group_v4() {
 __global__ void __launch_bounds__(1024)
 bn_stats_kernel(const float* __restrict__ raw, int M, int C, float* __restrict__ mean, float* __restrict__ rstd,
                 float* __restrict__ rmean, float* __restrict__ rvar, int updates) {
+  pdl_entry();
   column_partial2(M, C, [&](int m, int c, float& v1, float& v2) {
     const float x = raw[static_cast<size_t>(m) * C + c];
     v1 = x;
@@ -513,6 +634,7 @@ __device__ __forceinline__ void column_fold2_cta(int cb0, int cn, int grp, int n
 __global__ void __launch_bounds__(256)
 bn_stats_v4_kernel(const float* __restrict__ raw, int M, int C, int Qb, float* __restrict__ mean, float* __restrict__ rstd,
                    float* __restrict__ rmean, float* __restrict__ rvar, int updates) {
+  pdl_entry();
   column_partial2_v4(M, C, Qb, [&](int m, int c0, float4& v1, float4& v2) {
     const float4 x = *reinterpret_cast<const float4*>(raw + static_cast<size_t>(m) * C + c0);
     v1 = x;
@@ -552,10 +674,10 @@ cudaError_t launch_bn_stats(const float* raw, int M, int C, float* mean, float* 
   if (R < 1) return cudaErrorInvalidValue;
   if ((C & (C - 1)) == 0 && C >= 32 && C <= 1024) {
     const int Qb = red_quads_per_cta(C, R * groups);
-    bn_stats_v4_kernel<<<dim3(C / 4 / Qb, R, groups), 256, 0, s>>>(raw, M, C, Qb, mean, rstd, running_mean, running_var, updates);
+    if (cudaError_t e_ = launch_pdl_small(bn_stats_v4_kernel, dim3(C / 4 / Qb, R, groups), dim3(256), 0, s, raw, M, C, Qb, mean, rstd, running_mean, running_var, updates); e_ != cudaSuccess) return e_;
     return cudaGetLastError();
   }
-  bn_stats_kernel<<<dim3((C + 31) / 32, R, groups), dim3(32, 32), 0, s>>>(raw, M, C, mean, rstd, running_mean, running_var, updates);
+  if (cudaError_t e_ = launch_pdl_small(bn_stats_kernel, dim3((C + 31) / 32, R, groups), dim3(32, 32), 0, s, raw, M, C, mean, rstd, running_mean, running_var, updates); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
@@ -563,6 +685,7 @@ __global__ void __launch_bounds__(256)
 bn_act_kernel(const float* __restrict__ raw, const float* __restrict__ mean, const float* __restrict__ rstd,
               const float* __restrict__ gamma, const float* __restrict__ beta, int B, int H, int W, int C,
               __nv_bfloat16* __restrict__ out, int cstride, int coff, int upsample, int rows_per_group) {
+  pdl_entry();
   const int C8 = C / 8;
   const size_t total = static_cast<size_t>(B) * H * W * C8;
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -575,10 +698,13 @@ bn_act_kernel(const float* __restrict__ raw, const float* __restrict__ mean, con
   const int x = static_cast<int>(m % W), y = static_cast<int>((m / W) % H);
   const size_t b = m / (static_cast<size_t>(W) * H);
   float v[8];
+  const float4* rp = reinterpret_cast<const float4*>(raw + m * C + c0);  // (C % 8 == 0: 32-byte aligned)
+  const float4 r0 = __ldcs(rp), r1 = __ldcs(rp + 1);                     // last use of the fp32 copy in the forward pass
+  const float rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = c0 + j;
-    float t = (raw[m * C + c] - mean[c]) * rstd[c] * gamma[c] + beta[c];
+    float t = (rw[j] - mean[c]) * rstd[c] * gamma[c] + beta[c];
     v[j] = t > 0.f ? t : 0.2f * t;
   }
   const uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
@@ -596,8 +722,8 @@ cudaError_t launch_bn_act(const float* raw, const float* mean, const float* rstd
                           int upsample, cudaStream_t s, int groups) {
   const size_t total = static_cast<size_t>(B) * H * W * (C / 8);
   if (groups < 1 || B % groups) return cudaErrorInvalidValue;
-  bn_act_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(raw, mean, rstd, gamma, beta, B, H, W, C,
-                                                                           out, cstride, coff, upsample, B / groups * H * W);
+  if (cudaError_t e_ = launch_pdl_small(bn_act_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, raw, mean, rstd, gamma, beta, B, H, W, C,
+                                                                           out, cstride, coff, upsample, B / groups * H * W); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
@@ -632,6 +758,7 @@ __device__ __forceinline__ void bn_bwd_point(const BnBwdArgs& a, int m, int c, f
 }
 __global__ void __launch_bounds__(1024)
 bn_bwd_sums_kernel(BnBwdArgs a, int M, float* __restrict__ scratch, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_entry();
   column_partial2(M, a.C, [&](int m, int c, float& v1, float& v2) {
     float dz, xh;
     bn_bwd_point(a, m, c, dz, xh);
@@ -657,6 +784,7 @@ bn_bwd_sums_kernel(BnBwdArgs a, int M, float* __restrict__ scratch, float* __res
 __global__ void __launch_bounds__(256)
 bn_bwd_sums_v4_kernel(BnBwdArgs a, int M, int Qb, float* __restrict__ scratch, float* __restrict__ dgamma,
                       float* __restrict__ dbeta) {
+  pdl_entry();
   column_partial2_v4(M, a.C, Qb, [&](int m, int c0, float4& v1, float4& v2) {
     float4 g;
     if (!a.upsample) {
@@ -718,6 +846,7 @@ bn_bwd_sums_v4_kernel(BnBwdArgs a, int M, int Qb, float* __restrict__ scratch, f
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(BnBwdArgs a, int M, const float* __restrict__ scratch, __nv_bfloat16* __restrict__ draw,
                     float* __restrict__ draw32) {
+  pdl_entry();
   const int C8 = a.C >> 3;
   const size_t total = static_cast<size_t>(M) * C8;
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -781,15 +910,15 @@ cudaError_t launch_bn_bwd(const float* dy, int dy_cstride, int dy_coff, int upsa
   if (R < 1) return cudaErrorInvalidValue;
   if ((C & (C - 1)) == 0 && C >= 32 && C <= 1024 && dy_cstride % 4 == 0 && dy_coff % 4 == 0) {
     const int Qb = red_quads_per_cta(C, R * groups);
-    bn_bwd_sums_v4_kernel<<<dim3(C / 4 / Qb, R, groups), 256, 0, s>>>(a, Mg, Qb, scratch, dgamma, dbeta);
+    if (cudaError_t e_ = launch_pdl_small(bn_bwd_sums_v4_kernel, dim3(C / 4 / Qb, R, groups), dim3(256), 0, s, a, Mg, Qb, scratch, dgamma, dbeta); e_ != cudaSuccess) return e_;
   } else {
-    bn_bwd_sums_kernel<<<dim3((C + 31) / 32, R, groups), dim3(32, 32), 0, s>>>(a, Mg, scratch, dgamma, dbeta);
+    if (cudaError_t e_ = launch_pdl_small(bn_bwd_sums_kernel, dim3((C + 31) / 32, R, groups), dim3(32, 32), 0, s, a, Mg, scratch, dgamma, dbeta); e_ != cudaSuccess) return e_;
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (C % 8 || dy_cstride % 4 || dy_coff % 4) return cudaErrorInvalidValue;
   const size_t total = static_cast<size_t>(M) * (C / 8);
-  bn_bwd_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(a, M, scratch, draw, draw_f32_or_null);
+  if (cudaError_t e_ = launch_pdl_small(bn_bwd_apply_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, a, M, scratch, draw, draw_f32_or_null); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
@@ -802,6 +931,7 @@ __global__ void __launch_bounds__(256)
 lstm_cell_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ part, int nsplit, long long split_stride,
                      const float* __restrict__ bias, const float* __restrict__ c_prev, float* __restrict__ c_out,
                      __nv_bfloat16* __restrict__ h_out, float* __restrict__ gates_out, size_t total, int hid) {
+  pdl_entry();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // (m, channel)
   if (i >= total) return;
   const int ch = static_cast<int>(i % hid);
@@ -825,9 +955,9 @@ cudaError_t launch_lstm_cell_fwd(const float* gx, const float* part, int nsplit,
                                  const float* bias, const float* c_prev_or_null, float* c_out, __nv_bfloat16* h_out,
                                  float* gates_out, int M, int hid, cudaStream_t s) {
   const size_t total = static_cast<size_t>(M) * hid;
-  lstm_cell_fwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(gx, part, nsplit, split_stride, bias,
+  if (cudaError_t e_ = launch_pdl_small(lstm_cell_fwd_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, gx, part, nsplit, split_stride, bias,
                                                                                   c_prev_or_null, c_out, h_out, gates_out,
-                                                                                  total, hid);
+                                                                                  total, hid); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
@@ -835,6 +965,7 @@ __global__ void __launch_bounds__(256)
 lstm_bwd_kernel(const float* __restrict__ dh, float* __restrict__ dc, const float* __restrict__ gates,
                 const float* __restrict__ c_prev, const float* __restrict__ c_new, size_t total,
                 __nv_bfloat16* __restrict__ dgates) {
+  pdl_entry();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // (m, channel)
   if (i >= total) return;
   const float4 gt = reinterpret_cast<const float4*>(gates)[i];  // i, f, o, g (post-activation)
@@ -852,13 +983,14 @@ lstm_bwd_kernel(const float* __restrict__ dh, float* __restrict__ dc, const floa
 cudaError_t launch_lstm_bwd(const float* dh, float* dc, const float* gates, const float* c_prev_or_null,
                             const float* c_new, int M, int hid, __nv_bfloat16* dgates, cudaStream_t s) {
   const size_t total = static_cast<size_t>(M) * hid;
-  lstm_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(dh, dc, gates, c_prev_or_null, c_new,
-                                                                             total, dgates);
+  if (cudaError_t e_ = launch_pdl_small(lstm_bwd_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, dh, dc, gates, c_prev_or_null, c_new,
+                                                                             total, dgates); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(1024) bias_grad_partial_kernel(const __nv_bfloat16* __restrict__ dy, int M, int ncols,
                                                                   int nvalid) {
+  pdl_entry();
   column_partial2(M, nvalid, [&](int m, int c, float& v1, float& v2) {
     v1 = __bfloat162float(dy[static_cast<size_t>(m) * ncols + c]);
     v2 = 0.f;
@@ -866,6 +998,7 @@ __global__ void __launch_bounds__(1024) bias_grad_partial_kernel(const __nv_bflo
 }
 __global__ void bias_grad_final_kernel(int nvalid, int nsplit, const long long* __restrict__ bias_off,
                                        float* __restrict__ grads) {
+  pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nvalid || bias_off[c] < 0) return;
   double s1, s2;
@@ -876,8 +1009,8 @@ cudaError_t launch_bias_grad(const __nv_bfloat16* dy, int M, int ncols, int nval
                              float* grads, cudaStream_t s) {
   if (nvalid > 2048) return cudaErrorInvalidValue;
   const int R = red_split(M);
-  bias_grad_partial_kernel<<<dim3((nvalid + 31) / 32, R), dim3(32, 32), 0, s>>>(dy, M, ncols, nvalid);
-  bias_grad_final_kernel<<<(nvalid + 127) / 128, 128, 0, s>>>(nvalid, R, bias_off, grads);
+  if (cudaError_t e_ = launch_pdl_small(bias_grad_partial_kernel, dim3((nvalid + 31) / 32, R), dim3(32, 32), 0, s, dy, M, ncols, nvalid); e_ != cudaSuccess) return e_;
+  if (cudaError_t e_ = launch_pdl_small(bias_grad_final_kernel, dim3((nvalid + 127) / 128), dim3(128), 0, s, nvalid, R, bias_off, grads); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
@@ -887,6 +1020,7 @@ gauss_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ mu, con
                  const float* __restrict__ eps, const float* __restrict__ mu_p, const float* __restrict__ lv_p, int B,
                  int z_dim, int hw, float klw, int bs, __nv_bfloat16* __restrict__ dpost,
                  __nv_bfloat16* __restrict__ dprior) {
+  pdl_entry();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // (m, zc in 0..63)
   const size_t total = static_cast<size_t>(B) * hw * 64;
   if (i >= total) return;
@@ -913,8 +1047,8 @@ cudaError_t launch_gauss_bwd(const float* dz, const float* mu, const float* lv, 
                              const float* lv_p, int B, int z_dim, int hw, float kl_weight, int bs,
                              __nv_bfloat16* dpost, __nv_bfloat16* dprior, cudaStream_t s) {
   const size_t total = static_cast<size_t>(B) * hw * 64;
-  gauss_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(dz, mu, lv, eps, mu_p, lv_p, B, z_dim, hw,
-                                                                              kl_weight, bs, dpost, dprior);
+  if (cudaError_t e_ = launch_pdl_small(gauss_bwd_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, dz, mu, lv, eps, mu_p, lv_p, B, z_dim, hw,
+                                                                              kl_weight, bs, dpost, dprior); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
@@ -925,6 +1059,7 @@ gauss_bwd_ext_kernel(const float* __restrict__ dz, const float* __restrict__ lv,
                      const float* __restrict__ dmu, const float* __restrict__ dlv, const float* __restrict__ dmu_p,
                      const float* __restrict__ dlv_p, int B, int z_dim, int hw, __nv_bfloat16* __restrict__ dpost,
                      __nv_bfloat16* __restrict__ dprior) {
+  pdl_entry();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // (m, zc in 0..63)
   const size_t total = static_cast<size_t>(B) * hw * 64;
   if (i >= total) return;
@@ -948,8 +1083,8 @@ cudaError_t launch_gauss_bwd_ext(const float* dz, const float* lv, const float* 
                                  const float* dmu_p, const float* dlv_p, int B, int z_dim, int hw, __nv_bfloat16* dpost,
                                  __nv_bfloat16* dprior, cudaStream_t s) {
   const size_t total = static_cast<size_t>(B) * hw * 64;
-  gauss_bwd_ext_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(dz, lv, eps, dmu, dlv, dmu_p, dlv_p, B,
-                                                                                  z_dim, hw, dpost, dprior);
+  if (cudaError_t e_ = launch_pdl_small(gauss_bwd_ext_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, dz, lv, eps, dmu, dlv, dmu_p, dlv_p, B,
+                                                                                  z_dim, hw, dpost, dprior); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
@@ -958,6 +1093,7 @@ cudaError_t launch_gauss_bwd_ext(const float* dz, const float* lv, const float* 
 __global__ void __launch_bounds__(256)
 sigmoid_bwd_kernel(const float* __restrict__ x4, const float* __restrict__ dx4, int B, int HW,
                    __nv_bfloat16* __restrict__ dlogit) {
+  pdl_entry();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // (b, p)
   if (i >= static_cast<size_t>(B) * HW) return;
   const size_t b = i / HW;
@@ -976,7 +1112,7 @@ sigmoid_bwd_kernel(const float* __restrict__ x4, const float* __restrict__ dx4, 
 }
 cudaError_t launch_sigmoid_bwd(const float* x4, const float* dx4, __nv_bfloat16* dlogit, int B, int HW, cudaStream_t s) {
   const size_t total = static_cast<size_t>(B) * HW;
-  sigmoid_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(x4, dx4, B, HW, dlogit);
+  if (cudaError_t e_ = launch_pdl_small(sigmoid_bwd_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, x4, dx4, B, HW, dlogit); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
@@ -986,6 +1122,7 @@ frame_loss_kernel(const float* __restrict__ x4, const float* __restrict__ xj, co
                   const float* __restrict__ mask, int kind, float rw, int B, int HW, float* __restrict__ loss_out,
                   __nv_bfloat16* __restrict__ dlogit, const float* __restrict__ gp_in, float* __restrict__ gxj_out,
                   const float* __restrict__ batch_weight, int Bdiv) {
+  pdl_entry();
   __shared__ double sh[32];
   __shared__ float s_scale;
   const int b = blockIdx.x;
@@ -1050,13 +1187,14 @@ cudaError_t launch_frame_loss(const float* x4, const float* xj, const float* xi,
                               float robot_weight, int B, int HW, float* loss_out, __nv_bfloat16* dlogit,
                               const float* gp_in, float* gxj_out, cudaStream_t s, const float* batch_weight, int Bdiv) {
   if ((kind & 1) && !mask) return cudaErrorInvalidValue;
-  frame_loss_kernel<<<B, 1024, 0, s>>>(x4, xj, xi, mask, kind, robot_weight, B, HW, loss_out, dlogit, gp_in, gxj_out,
-                                       batch_weight, Bdiv > 0 ? Bdiv : B);
+  if (cudaError_t e_ = launch_pdl_small(frame_loss_kernel, dim3(B), dim3(1024), 0, s, x4, xj, xi, mask, kind, robot_weight, B, HW, loss_out, dlogit, gp_in, gxj_out,
+                                       batch_weight, Bdiv > 0 ? Bdiv : B); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(256)
 composite_kernel(const float* __restrict__ x4, const float* __restrict__ xj, float* __restrict__ xp, int B, int HW) {
+  pdl_entry();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // (b, c, p)
   if (i >= static_cast<size_t>(B) * 3 * HW) return;
   const int p = static_cast<int>(i % HW);
@@ -1067,7 +1205,7 @@ composite_kernel(const float* __restrict__ x4, const float* __restrict__ xj, flo
 }
 cudaError_t launch_composite(const float* x4, const float* xj, float* xp, int B, int HW, cudaStream_t s) {
   const size_t total = static_cast<size_t>(B) * 3 * HW;
-  composite_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(x4, xj, xp, B, HW);
+  if (cudaError_t e_ = launch_pdl_small(composite_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, x4, xj, xp, B, HW); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
@@ -1075,6 +1213,7 @@ cudaError_t launch_composite(const float* x4, const float* xj, float* xp, int B,
 __global__ void __launch_bounds__(256)
 first_dgrad_kernel(const float* __restrict__ draw, const float* __restrict__ wf, int cin,
                    const float* __restrict__ zero_mask, float* __restrict__ gimg, int B, int H, int W) {
+  pdl_entry();
   __shared__ float sw[9 * 3 * 64];
   for (int i = threadIdx.x; i < 9 * 3 * 64; i += blockDim.x) {
     const int o = i & 63, c = (i >> 6) % 3, tap = (i >> 6) / 3;
@@ -1106,7 +1245,7 @@ first_dgrad_kernel(const float* __restrict__ draw, const float* __restrict__ wf,
 cudaError_t launch_first_dgrad(const float* draw, const float* wf, int cin, const float* zero_mask, float* gimg, int B,
                                int H, int W, cudaStream_t s) {
   const size_t total = static_cast<size_t>(B) * H * W;
-  first_dgrad_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(draw, wf, cin, zero_mask, gimg, B, H, W);
+  if (cudaError_t e_ = launch_pdl_small(first_dgrad_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, draw, wf, cin, zero_mask, gimg, B, H, W); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
@@ -1114,6 +1253,7 @@ cudaError_t launch_first_dgrad(const float* draw, const float* wf, int cin, cons
 __global__ void __launch_bounds__(256)
 pool_bwd_kernel(const __nv_bfloat16* __restrict__ in, int in_cstride, int in_coff, const float* __restrict__ dout,
                 int B, int H, int W, int C, float* __restrict__ din, int din_cstride, int din_coff, int accumulate) {
+  pdl_entry();
   const int Ho = H / 2, Wo = W / 2;
   const size_t total = static_cast<size_t>(B) * Ho * Wo * C;
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -1147,19 +1287,20 @@ pool_bwd_kernel(const __nv_bfloat16* __restrict__ in, int in_cstride, int in_cof
 cudaError_t launch_pool_bwd(const __nv_bfloat16* in, int in_cstride, int in_coff, const float* dout, int B, int H,
                             int W, int C, float* din, int din_cstride, int din_coff, int accumulate, cudaStream_t s) {
   const size_t total = static_cast<size_t>(B) * (H / 2) * (W / 2) * C;
-  pool_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, in_cstride, in_coff, dout, B, H, W, C,
-                                                                             din, din_cstride, din_coff, accumulate);
+  if (cudaError_t e_ = launch_pdl_small(pool_bwd_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, in, in_cstride, in_coff, dout, B, H, W, C,
+                                                                             din, din_cstride, din_coff, accumulate); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------ layout helpers
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, long long n,
                                                         __nv_bfloat16* __restrict__ dst) {
+  pdl_entry();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __float2bfloat16(src[i]);
 }
 cudaError_t launch_cast_bf16(const float* src, long long n, __nv_bfloat16* dst, cudaStream_t s) {
-  cast_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(src, n, dst);
+  if (cudaError_t e_ = launch_pdl_small(cast_bf16_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, s, src, n, dst); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
@@ -1169,6 +1310,7 @@ cudaError_t launch_cast_bf16(const float* src, long long n, __nv_bfloat16* dst, 
 __global__ void __launch_bounds__(512)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float gscale, int head) {
+  pdl_entry();
   const float step = lr / bc1;
   // gscale: 1 / world size after a SUM all-reduce (x * 1.0f is exact, so the single-GPU update is unchanged)
   auto upd = [&](float& pi, float gi, float& mi, float& vi) {
@@ -1218,12 +1360,13 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long 
   if (head > n) head = static_cast<int>(n);
   const long long body = (n - head) >> 2;
   const int blocks = static_cast<int>(std::min<long long>(148 * 8, std::max<long long>(1, (body + 511) / 512)));
-  adam_kernel<<<blocks, 512, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2, grad_scale, head);
+  if (cudaError_t e_ = launch_pdl_small(adam_kernel, dim3(blocks), dim3(512), 0, s, p, g, m, v, n, lr, b1, b2, eps, bc1, bc2, grad_scale, head); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(256)
 normal_fill_kernel(float* __restrict__ dst, long long n, unsigned long long seed, unsigned int ctr) {
+  pdl_entry();
   const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // 4 values per thread
   if (q * 4 >= n) return;
   const Philox4 r = philox4x32_10(static_cast<uint32_t>(q), static_cast<uint32_t>(q >> 32), ctr, 0x7a1u,
@@ -1235,11 +1378,12 @@ normal_fill_kernel(float* __restrict__ dst, long long n, unsigned long long seed
 }
 cudaError_t launch_normal_fill(float* dst, long long n, unsigned long long seed, unsigned int ctr, cudaStream_t s) {
   const long long quads = (n + 3) / 4;
-  normal_fill_kernel<<<static_cast<unsigned>((quads + 255) / 256), 256, 0, s>>>(dst, n, seed, ctr);
+  if (cudaError_t e_ = launch_pdl_small(normal_fill_kernel, dim3(static_cast<unsigned>((quads + 255) / 256)), dim3(256), 0, s, dst, n, seed, ctr); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(256) sum_f32_kernel(const float* __restrict__ src, int n, float* __restrict__ dst) {
+  pdl_entry();
   __shared__ double sh[8];
   double a = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) a += src[i];
@@ -1253,23 +1397,25 @@ __global__ void __launch_bounds__(256) sum_f32_kernel(const float* __restrict__ 
   }
 }
 cudaError_t launch_sum_f32(const float* src, int n, float* dst_accum, cudaStream_t s) {
-  sum_f32_kernel<<<1, 256, 0, s>>>(src, n, dst_accum);
+  if (cudaError_t e_ = launch_pdl_small(sum_f32_kernel, dim3(1), dim3(256), 0, s, src, n, dst_accum); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
 __global__ void gather_f32_kernel(const float* __restrict__ params, const long long* __restrict__ off, int n,
                                   float* __restrict__ dst) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = off[i] >= 0 ? params[off[i]] : 0.f;
 }
 cudaError_t launch_gather_f32(const float* params, const long long* off, int n, float* dst, cudaStream_t s) {
-  gather_f32_kernel<<<(n + 255) / 256, 256, 0, s>>>(params, off, n, dst);
+  if (cudaError_t e_ = launch_pdl_small(gather_f32_kernel, dim3((n + 255) / 256), dim3(256), 0, s, params, off, n, dst); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(256)
 img_prep_train_kernel(const float* __restrict__ img, const float* __restrict__ mask, float* __restrict__ img4, int B,
                       int HW) {
+  pdl_entry();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<size_t>(B) * HW) return;
   const size_t b = i / HW;
@@ -1281,7 +1427,7 @@ img_prep_train_kernel(const float* __restrict__ img, const float* __restrict__ m
 }
 cudaError_t launch_img_prep_train(const float* img_nchw, const float* mask, float* img4, int B, int HW, cudaStream_t s) {
   const size_t total = static_cast<size_t>(B) * HW;
-  img_prep_train_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(img_nchw, mask, img4, B, HW);
+  if (cudaError_t e_ = launch_pdl_small(img_prep_train_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, img_nchw, mask, img4, B, HW); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
@@ -1291,6 +1437,7 @@ cudaError_t launch_img_prep_train(const float* img_nchw, const float* mask, floa
 __global__ void __launch_bounds__(256)
 robot_world_mse_part_kernel(const float* __restrict__ p, const float* __restrict__ t, const float* __restrict__ mask,
                             float* __restrict__ part, int HW) {
+  pdl_entry();
   __shared__ double sh[3][8];
   const int b = blockIdx.x;
   double sr = 0.0, sw = 0.0, cr = 0.0;
@@ -1320,6 +1467,7 @@ robot_world_mse_part_kernel(const float* __restrict__ p, const float* __restrict
   }
 }
 __global__ void metric_fold_kernel(const float* __restrict__ part, int n, int width, double scale, float* __restrict__ out) {
+  pdl_entry();
   if (threadIdx.x < width && blockIdx.x == 0) {
     double s = 0.0;
     for (int i = 0; i < n; ++i) s += static_cast<double>(part[i * width + threadIdx.x]);
@@ -1328,8 +1476,8 @@ __global__ void metric_fold_kernel(const float* __restrict__ part, int n, int wi
 }
 cudaError_t launch_robot_world_mse_batched(const float* pred, const float* target, const float* mask, float* part,
                                            float* out2, int n, int Bdiv, int HW, cudaStream_t s) {
-  robot_world_mse_part_kernel<<<n, 256, 0, s>>>(pred, target, mask, part, HW);
-  metric_fold_kernel<<<1, 32, 0, s>>>(part, n, 2, 1.0 / Bdiv, out2);
+  if (cudaError_t e_ = launch_pdl_small(robot_world_mse_part_kernel, dim3(n), dim3(256), 0, s, pred, target, mask, part, HW); e_ != cudaSuccess) return e_;
+  if (cudaError_t e_ = launch_pdl_small(metric_fold_kernel, dim3(1), dim3(32), 0, s, part, n, 2, 1.0 / Bdiv, out2); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 
@@ -1338,6 +1486,7 @@ cudaError_t launch_robot_world_mse_batched(const float* pred, const float* targe
 __global__ void __launch_bounds__(256)
 kl_part_kernel(const float* __restrict__ mu1, const float* __restrict__ lv1, const float* __restrict__ mu2,
                const float* __restrict__ lv2, float* __restrict__ part, long long n) {
+  pdl_entry();
   __shared__ double sh[8];
   double acc = 0.0;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
@@ -1357,8 +1506,8 @@ kl_part_kernel(const float* __restrict__ mu1, const float* __restrict__ lv1, con
 }
 cudaError_t launch_kl_loss_batched(const float* mu1, const float* lv1, const float* mu2, const float* lv2, float* part,
                                    float* out_accum, long long n, int bs, cudaStream_t s) {
-  kl_part_kernel<<<64, 256, 0, s>>>(mu1, lv1, mu2, lv2, part, n);
-  metric_fold_kernel<<<1, 32, 0, s>>>(part, 64, 1, 1.0 / bs, out_accum);
+  if (cudaError_t e_ = launch_pdl_small(kl_part_kernel, dim3(64), dim3(256), 0, s, mu1, lv1, mu2, lv2, part, n); e_ != cudaSuccess) return e_;
+  if (cudaError_t e_ = launch_pdl_small(metric_fold_kernel, dim3(1), dim3(32), 0, s, part, 64, 1, 1.0 / bs, out_accum); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 

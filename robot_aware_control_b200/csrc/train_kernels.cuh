@@ -127,7 +127,9 @@ cudaError_t launch_cast_bf16(const float* src, long long n, __nv_bfloat16* dst, 
 cudaError_t launch_adam_pack(float* params, float* m, float* v, const float* dwp, const long long* row_off,
                              const int* col_off, int n_packed, int taps, int ctot, int flip, int tiled,
                              __nv_bfloat16* wp, float lr, float b1, float b2, float eps, int t, float grad_scale,
-                             cudaStream_t s);
+                             cudaStream_t s, int vec_ok);
+// one-time check of a layer's packing tables (synchronous): *ok_host = 1 if launch_adam_pack may take its float4 path
+cudaError_t adam_pack_vec_ok(const long long* row_off, const int* col_off, int n_packed, int taps, int ctot, int* ok_host);
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
                         float eps, int t, cudaStream_t s, float grad_scale = 1.f);
 cudaError_t launch_normal_fill(float* dst, long long n, unsigned long long seed, unsigned int ctr, cudaStream_t s);

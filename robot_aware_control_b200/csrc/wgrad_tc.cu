@@ -19,6 +19,17 @@
 // gradients (K = 3840 rows only, 2048 x 1024 x 25 outputs) are bound by the L2 -> SM operand traffic, which a 256 x 256
 // tile cuts by a third against 128 x 256.
 //   warp 0: TMA producer, warp 1: MMA issuer (one thread), warp 2: TMEM allocator, warps 4-11: epilogue (TMEM -> fp32 global)
+//
+// MC = true (layers with an even number of output-channel tiles AND of input-channel tiles): four CTAs of a cluster
+// compute a 2 x 2 block of tiles of one filter tap -- rank bit 0 picks the output-channel tile, bit 1 the input-channel
+// tile -- and share both operands through TMA multicast: a CTA loads every second box of its dY tile into itself and
+// the CTA with the same output-channel tile (rank ^ 2), and every second box of its X tile into itself and the CTA with
+// the same input-channel tile (rank ^ 1). L2 -> SM traffic per CTA and k-block drops from 8 boxes to 4. ncu of the
+// plain kernel on the 5x5 gate layers (profiles/r02_train_top_ncu_s18.txt): 436 us for 403 GFLOP, sm__throughput 45 %,
+// 800 CTAs x 80 k-blocks x 49 KB = 3.1 GB of operand reads in that time = 7.2 TB/s out of the L2: feed-bound.
+//   * full barrier (per CTA): own arrive.expect_tx(all boxes); the bytes come from this CTA and its two peers
+//   * empty barrier (per CTA): count 3 -- a stage is rewritten by this CTA and both peers, so the MMA threads of all
+//     three release it (tcgen05.commit multicast to {self, rank ^ 1, rank ^ 2})
 #include "ptx.cuh"
 #include "wgrad_tc.cuh"
 
@@ -36,6 +47,7 @@ constexpr int kThreads = 128 + 256;
 // bf16 x bf16 -> fp32, A and B both MN-major, M = 128
 __device__ __forceinline__ uint32_t umma_idesc_bf16_mn(int n) { return umma_idesc_bf16(n) | kIdescAMn | kIdescBMn; }
 
+template <bool MC>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
   extern __shared__ uint8_t smem_raw[];
@@ -47,12 +59,26 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // tile decode: blockIdx.x = (tap, c tile, n tile), blockIdx.y = K split
-  int t_id = blockIdx.x;
-  const int n_tile = t_id % g.n_tiles;
-  t_id /= g.n_tiles;
-  const int ct = t_id % g.num_ctiles;
-  const int tap = t_id / g.num_ctiles;
+  // tile decode: blockIdx.x = (tap, c tile, n tile), blockIdx.y = K split; MC: blockIdx.x = (tap, c pair, n pair, rank)
+  int n_tile, ct, tap;
+  uint32_t rank = 0;
+  if constexpr (MC) {
+    rank = cluster_ctarank();
+    int cid = blockIdx.x >> 2;
+    const int np = g.n_tiles >> 1, cp = g.num_ctiles >> 1;
+    n_tile = 2 * (cid % np) + static_cast<int>(rank & 1u);
+    cid /= np;
+    ct = 2 * (cid % cp) + static_cast<int>(rank >> 1);
+    tap = cid / cp;
+  } else {
+    int t_id = blockIdx.x;
+    n_tile = t_id % g.n_tiles;
+    t_id /= g.n_tiles;
+    ct = t_id % g.num_ctiles;
+    tap = t_id / g.num_ctiles;
+  }
+  const uint16_t mask_a = static_cast<uint16_t>((1u << rank) | (1u << (rank ^ 2u)));  // CTAs that read my dY boxes
+  const uint16_t mask_b = static_cast<uint16_t>((1u << rank) | (1u << (rank ^ 1u)));  // CTAs that read my X boxes
   const int kh = tap / g.ks, kw = tap - kh * g.ks;
   const int src = g.ct_src[ct], c0 = g.ct_c0[ct], cw = g.ct_w[ct];
   const int nb_boxes = cw >> 6;
@@ -70,7 +96,7 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], MC ? 3 : 1);
     }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
@@ -81,6 +107,7 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();  // the peers' barriers are initialised before anything is signalled on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   griddep_launch_dependents();  // (PDL, ptx.cuh) the next kernel's prologue may start
@@ -101,11 +128,20 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
       uint8_t* sa = smem + stage * kStageBytes;
       uint8_t* sb = sa + 4 * kBoxBytesMax;
       mbar_arrive_expect_tx(&full_bar[stage], (a_boxes + nb_boxes) * box_bytes);
-      for (int j = 0; j < a_boxes; ++j)
-        tma_load_5d(&tm.dy, &full_bar[stage], sa + j * box_bytes, n0 + j * 64, 0, y0, b0, t);
-      for (int j = 0; j < nb_boxes; ++j)
-        tma_load_5d(&tm.x[src], &full_bar[stage], sb + j * box_bytes, c0 + j * 64, kw - g.pad, y0 + kh - g.pad, b0,
-                    t - g.src_tshift[src]);
+      if constexpr (MC) {
+        // every second box of each operand, into this CTA and the peer that shares the operand
+        for (int j = static_cast<int>(rank >> 1); j < a_boxes; j += 2)
+          tma_load_5d_mc(&tm.dy, &full_bar[stage], sa + j * box_bytes, n0 + j * 64, 0, y0, b0, t, mask_a);
+        for (int j = static_cast<int>(rank & 1u); j < nb_boxes; j += 2)
+          tma_load_5d_mc(&tm.x[src], &full_bar[stage], sb + j * box_bytes, c0 + j * 64, kw - g.pad, y0 + kh - g.pad, b0,
+                         t - g.src_tshift[src], mask_b);
+      } else {
+        for (int j = 0; j < a_boxes; ++j)
+          tma_load_5d(&tm.dy, &full_bar[stage], sa + j * box_bytes, n0 + j * 64, 0, y0, b0, t);
+        for (int j = 0; j < nb_boxes; ++j)
+          tma_load_5d(&tm.x[src], &full_bar[stage], sb + j * box_bytes, c0 + j * 64, kw - g.pad, y0 + kh - g.pad, b0,
+                      t - g.src_tshift[src]);
+      }
       if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1 && lane == 0) {
@@ -129,7 +165,8 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
                        accumulate);
         accumulate = 1;
       }
-      umma_commit(&empty_bar[stage]);
+      if constexpr (MC) umma_commit_mc(&empty_bar[stage], static_cast<uint16_t>(mask_a | mask_b));
+      else umma_commit(&empty_bar[stage]);
       if (kb == kb_end - 1) umma_commit(tmem_full);
       if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
@@ -163,6 +200,7 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();  // the peers may still multicast into this CTA's shared memory / signal its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -172,6 +210,7 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
 // out[i] = sum over splits (in order) of part[s][i]
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float4* __restrict__ part, int splits, long long n4, long long stride4, float4* __restrict__ out) {
+  pdl_entry();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 a = part[i];
@@ -185,21 +224,42 @@ wgrad_reduce_kernel(const float4* __restrict__ part, int splits, long long n4, l
 }  // namespace
 
 cudaError_t wgrad_tc_set_attributes() {
-  return cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  cudaError_t err = cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (err != cudaSuccess) return err;
+  return cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+}
+
+// RAC_WGRAD_MC=0: never the 2 x 2 multicast clusters (A/B switch)
+static bool wgrad_mc_enabled() {
+  static const int on = [] { const char* v = getenv("RAC_WGRAD_MC"); return v ? atoi(v) : 1; }();
+  return on != 0;
 }
 
 cudaError_t launch_wgrad_tc(const WgradTmaps& tm, const WgradGeom& g, cudaStream_t s) {
   if (g.rows % 16 || g.rows > kMaxRows || g.num_ctiles < 1 || g.num_ctiles > kWgMaxCTiles) return cudaErrorInvalidValue;
   dim3 grid(static_cast<unsigned>(g.n_tiles * g.num_ctiles * g.taps), static_cast<unsigned>(g.splits));
-  return launch_pdl(wgrad_tc_kernel, grid, dim3(kThreads), kSmemBytes, s, tm, g);
+  if (wgrad_mc_enabled() && g.n_tiles % 2 == 0 && g.num_ctiles % 2 == 0) {
+    // (same CTA count; blockIdx.x is decoded as (tap, c pair, n pair, rank) instead)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<true>, tm, g);
+  }
+  return launch_pdl(wgrad_tc_kernel<false>, grid, dim3(kThreads), kSmemBytes, s, tm, g);
 }
 
 cudaError_t launch_wgrad_reduce(const float* part, int splits, long long n, long long split_stride, float* out,
                                 cudaStream_t s) {
   if ((n & 3) || (split_stride & 3)) return cudaErrorInvalidValue;
   const long long n4 = n / 4;
-  wgrad_reduce_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, s>>>(
-      reinterpret_cast<const float4*>(part), splits, n4, split_stride / 4, reinterpret_cast<float4*>(out));
+  if (cudaError_t e_ = launch_pdl_small(wgrad_reduce_kernel, dim3(static_cast<unsigned>((n4 + 255) / 256)), dim3(256), 0, s, 
+      reinterpret_cast<const float4*>(part), splits, n4, split_stride / 4, reinterpret_cast<float4*>(out)); e_ != cudaSuccess) return e_;
   return cudaGetLastError();
 }
 

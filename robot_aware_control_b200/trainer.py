@@ -22,6 +22,7 @@ movement weighting (`cfg.load_movement_info`, batch["high_movement"]) are implem
 multiview; the batch must be a multiple of 4 clips.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -144,7 +145,8 @@ class RacTrainBatch(C.Structure):
 
 GRADS_READY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong)
 OVERLAP_MIN_ELEMS = 4 << 20  # layers with at least this many weights are all-reduced while the backward pass runs
-FUSED_MIN_ELEMS = 1 << 20    # single-tensor convolutions with at least this many weights take the fused optimizer step
+# single-tensor convolutions with at least this many weights take the fused optimizer step (RAC_FUSED_MIN_ELEMS: A/B switch)
+FUSED_MIN_ELEMS = int(os.environ.get("RAC_FUSED_MIN_ELEMS", 1 << 20))
 
 
 def _device_f32_view(ptr, count, device):
