@@ -20,13 +20,14 @@
 // tile cuts by a third against 128 x 256.
 //   warp 0: TMA producer, warp 1: MMA issuer (one thread), warp 2: TMEM allocator, warps 4-11: epilogue (TMEM -> fp32 global)
 //
-// MC = true (layers with an even number of output-channel tiles AND of input-channel tiles): four CTAs of a cluster
+// MC = true (RAC_WGRAD_MC=1, off by default -- measured slower, see the pipeline-ring note below; layers with an even
+// number of output-channel tiles AND of input-channel tiles): four CTAs of a cluster
 // compute a 2 x 2 block of tiles of one filter tap -- rank bit 0 picks the output-channel tile, bit 1 the input-channel
 // tile -- and share both operands through TMA multicast: a CTA loads every second box of its dY tile into itself and
 // the CTA with the same output-channel tile (rank ^ 2), and every second box of its X tile into itself and the CTA with
 // the same input-channel tile (rank ^ 1). L2 -> SM traffic per CTA and k-block drops from 8 boxes to 4. ncu of the
 // plain kernel on the 5x5 gate layers (profiles/r02_train_top_ncu_s18.txt): 436 us for 403 GFLOP, sm__throughput 45 %,
-// 800 CTAs x 80 k-blocks x 49 KB = 3.1 GB of operand reads in that time = 7.2 TB/s out of the L2: feed-bound.
+// 800 CTAs x 80 k-blocks x 49 KB = 3.1 GB of operand reads in that time = 7.2 TB/s into the SMs.
 //   * full barrier (per CTA): own arrive.expect_tx(all boxes); the bytes come from this CTA and its two peers
 //   * empty barrier (per CTA): count 3 -- a stage is rewritten by this CTA and both peers, so the MMA threads of all
 //     three release it (tcgen05.commit multicast to {self, rank ^ 1, rank ^ 2})
@@ -37,11 +38,17 @@ namespace rac {
 
 namespace {
 
-constexpr int kStages = 3;
+// Pipeline ring: 192 KB cut into stages of (A boxes + B boxes) x rows x 128 bytes, A = up to 4 boxes (256 output
+// channels), B = up to 4 boxes (256 input channels), both the largest of the launch: 3 stages for a 256 x 256 tile with
+// 64-row k-blocks, 4 with the 48-row k-blocks of the 6 x 8 ConvLSTM maps, 8 for the 64 x 128 tiles of the 48 x 64 maps. The main loop is latency-bound, not bandwidth-bound (ncu on the 5x5 gate layers: L2 26 %, L2 ->
+// SM fabric 21 %, shared-memory operand pipe 31 %, tensor pipe 29 % of peak; 0.85 us per k-block against 0.42 us of
+// MMA time with 3 x 48 KB in flight), so every byte of the ring that is in flight counts. (Sharing the operands of a
+// 2 x 2 block of tiles by TMA multicast, RAC_WGRAD_MC=1, cuts the L2 reads in half and measured SLOWER, 436 -> 466 us:
+// the stage hand-back then waits for three CTAs.)
+constexpr int kMaxStages = 12;
 constexpr int kMaxRows = 64;                       // positions per k-block (K of one pipeline stage)
-constexpr int kBoxBytesMax = kMaxRows * 128;       // one 64-channel box
-constexpr int kStageBytes = 8 * kBoxBytesMax;      // A: 4 boxes (256 output channels), B: up to 4 boxes (256 input channels)
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024;
+constexpr int kRingBytes = 3 * 8 * kMaxRows * 128; // 192 KB
+constexpr int kSmemBytes = kRingBytes + 1024 + 1024;
 constexpr int kThreads = 128 + 256;
 
 // bf16 x bf16 -> fp32, A and B both MN-major, M = 128
@@ -52,10 +59,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* bar_base = smem + kStages * kStageBytes;
+  uint8_t* bar_base = smem + kRingBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -88,6 +95,8 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
   const int kb_begin = blockIdx.y * g.kb_per_split;
   const int kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
   const uint32_t box_bytes = static_cast<uint32_t>(g.rows) * 128u;
+  const uint32_t stage_bytes = static_cast<uint32_t>(g.stage_a_boxes + g.stage_b_boxes) * box_bytes;
+  const int kStages = min(g.max_stages > 0 ? g.max_stages : kMaxStages, static_cast<int>(kRingBytes / stage_bytes));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm.dy);
@@ -125,8 +134,8 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
       const int t = rest / g.bgroups;
       const int y0 = hg * g.BH, b0 = bg * g.NB;
       mbar_wait(&empty_bar[stage], phase ^ 1);
-      uint8_t* sa = smem + stage * kStageBytes;
-      uint8_t* sb = sa + 4 * kBoxBytesMax;
+      uint8_t* sa = smem + stage * stage_bytes;
+      uint8_t* sb = sa + g.stage_a_boxes * box_bytes;
       mbar_arrive_expect_tx(&full_bar[stage], (a_boxes + nb_boxes) * box_bytes);
       if constexpr (MC) {
         // every second box of each operand, into this CTA and the peer that shares the operand
@@ -153,8 +162,8 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
     for (int kb = kb_begin; kb < kb_end; ++kb) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
-      const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-      const uint32_t sb = sa + 4 * kBoxBytesMax;
+      const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+      const uint32_t sb = sa + g.stage_a_boxes * box_bytes;
       const uint64_t adesc = umma_desc_sw128_mn(sa, box_bytes);
       const uint64_t bdesc = umma_desc_sw128_mn(sb, box_bytes);
       for (int k = 0; k < g.rows / 16; ++k) {
@@ -229,13 +238,24 @@ cudaError_t wgrad_tc_set_attributes() {
   return cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
 }
 
-// RAC_WGRAD_MC=0: never the 2 x 2 multicast clusters (A/B switch)
+// RAC_WGRAD_MC=1: 2 x 2 multicast clusters where the tile counts allow (off by default: measured slower, see above)
 static bool wgrad_mc_enabled() {
-  static const int on = [] { const char* v = getenv("RAC_WGRAD_MC"); return v ? atoi(v) : 1; }();
+  static const int on = [] { const char* v = getenv("RAC_WGRAD_MC"); return v ? atoi(v) : 0; }();
   return on != 0;
 }
 
-cudaError_t launch_wgrad_tc(const WgradTmaps& tm, const WgradGeom& g, cudaStream_t s) {
+cudaError_t launch_wgrad_tc(const WgradTmaps& tm, const WgradGeom& g_in, cudaStream_t s) {
+  // RAC_WGRAD_MAX_STAGES=3: the fixed three stages of the first version (A/B switch)
+  static const int max_stages = [] { const char* v = getenv("RAC_WGRAD_MAX_STAGES"); return v ? atoi(v) : 0; }();
+  WgradGeom g = g_in;
+  g.max_stages = max_stages;
+  // a stage holds the largest tile pair of the launch, not always 4 + 4 boxes: the 64- / 128-channel layers of the
+  // 48 x 64 maps (3 boxes of 8 KB per k-block) get 8 stages in flight instead of 3
+  g.stage_a_boxes = g.kpad >= 256 ? 4 : g.kpad / 64;
+  g.stage_b_boxes = 1;
+  for (int i = 0; i < g.num_ctiles && i < kWgMaxCTiles; ++i) g.stage_b_boxes = g.ct_w[i] / 64 > g.stage_b_boxes ? g.ct_w[i] / 64 : g.stage_b_boxes;
+  if (max_stages > 0) { g.stage_a_boxes = 4; g.stage_b_boxes = 4; }  // (A/B: the first version's fixed 8-box stages)
+  if (g.stage_a_boxes < 1 || g.stage_b_boxes > 4) return cudaErrorInvalidValue;
   if (g.rows % 16 || g.rows > kMaxRows || g.num_ctiles < 1 || g.num_ctiles > kWgMaxCTiles) return cudaErrorInvalidValue;
   dim3 grid(static_cast<unsigned>(g.n_tiles * g.num_ctiles * g.taps), static_cast<unsigned>(g.splits));
   if (wgrad_mc_enabled() && g.n_tiles % 2 == 0 && g.num_ctiles % 2 == 0) {

@@ -27,6 +27,8 @@ struct WgradGeom {
   int ct_src[kWgMaxCTiles], ct_c0[kWgMaxCTiles], ct_w[kWgMaxCTiles];
   int src_coff[kWgMaxSrc];     // channel offset of source s inside ctot
   int src_tshift[kWgMaxSrc];   // 1: source s is read at step t - 1 (h_{t-1} of a ConvLSTM; step -1 = zeros)
+  int max_stages;              // 0 = as many pipeline stages as the shared-memory ring holds (set by launch_wgrad_tc)
+  int stage_a_boxes, stage_b_boxes;  // boxes per stage: the largest dY / X tile of this launch (set by launch_wgrad_tc)
   float* out;                  // [splits][kpad][taps * ctot]
   long long out_split_stride;  // floats between two split partials
 };
