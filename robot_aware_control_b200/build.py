@@ -18,8 +18,9 @@ OBJ = os.path.join(HERE, "lib", "obj")
 SOURCES = ["conv_tc.cu", "conv_tc2.cu", "conv_tc_mc.cu", "conv_halo.cu", "first_conv_tc.cu", "misc_kernels.cu",
            "cem_kernels.cu", "train_kernels.cu", "train_gn_kernels.cu", "norm_lstm.cu", "metric_kernels.cu",
            "data_kernels.cu", "robot_kernels.cu", "wgrad_tc.cu", "rac_api.cu"]
-HEADERS = ["conv.cuh", "epilogue.cuh", "ptx.cuh", "misc_kernels.cuh", "train_kernels.cuh", "rac_train.inc.cu",
-           os.path.join("..", "..", "include", "racb200.h")]
+# every header of csrc/ (a struct that crosses object files, e.g. WgradGeom, must rebuild all of its users)
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + ["rac_train.inc.cu",
+                                                                       os.path.join("..", "..", "include", "racb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

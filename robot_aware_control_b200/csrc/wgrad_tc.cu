@@ -40,11 +40,12 @@ namespace {
 
 // Pipeline ring: 192 KB cut into stages of (A boxes + B boxes) x rows x 128 bytes, A = up to 4 boxes (256 output
 // channels), B = up to 4 boxes (256 input channels), both the largest of the launch: 3 stages for a 256 x 256 tile with
-// 64-row k-blocks, 4 with the 48-row k-blocks of the 6 x 8 ConvLSTM maps, 8 for the 64 x 128 tiles of the 48 x 64 maps. The main loop is latency-bound, not bandwidth-bound (ncu on the 5x5 gate layers: L2 26 %, L2 ->
-// SM fabric 21 %, shared-memory operand pipe 31 %, tensor pipe 29 % of peak; 0.85 us per k-block against 0.42 us of
-// MMA time with 3 x 48 KB in flight), so every byte of the ring that is in flight counts. (Sharing the operands of a
-// 2 x 2 block of tiles by TMA multicast, RAC_WGRAD_MC=1, cuts the L2 reads in half and measured SLOWER, 436 -> 466 us:
-// the stage hand-back then waits for three CTAs.)
+// 64-row k-blocks, 4 with the 48-row k-blocks of the 6 x 8 ConvLSTM maps, 8 for the 64 x 128 tiles of the 48 x 64 maps.
+// The main loop is latency-bound, not bandwidth-bound (ncu on the 5x5 gate layers, profiles/r02_train_top_ncu_s18.txt:
+// L2 26 %, L2 -> SM fabric 21 %, shared-memory operand pipe 31 %, tensor pipe 29 % of peak; 0.85 us per k-block against
+// 0.42 us of MMA time with 3 x 48 KB in flight), so every byte of the ring that is in flight counts. (Sharing the
+// operands of a 2 x 2 block of tiles by TMA multicast, RAC_WGRAD_MC=1, halves the L2 reads and measured SLOWER,
+// 436 -> 466 us, profiles/r02_train_top_ncu_s19.txt: the stage hand-back then waits for three CTAs.)
 constexpr int kMaxStages = 12;
 constexpr int kMaxRows = 64;                       // positions per k-block (K of one pipeline stage)
 constexpr int kRingBytes = 3 * 8 * kMaxRows * 128; // 192 KB
