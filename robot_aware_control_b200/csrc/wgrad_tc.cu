@@ -123,8 +123,13 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
   griddep_launch_dependents();  // (PDL, ptx.cuh) the next kernel's prologue may start
   griddep_wait();               // everything below reads / writes global memory of earlier kernels
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+  const int pmode = MC ? 1 : g.producers;
+  const int plane = pmode == 3 ? 4 : 1;  // producer lanes per producer warp
+  if ((warp == 0 || (warp == 3 && pmode >= 2)) && lane < plane) {
+    // ===================== TMA producer(s) =====================
+    // one cp.async.bulk.tensor per 64-channel box (the 128-byte swizzle caps the inner box dimension): up to 8 per
+    // k-block; pmode says how many threads share them
+    const bool do_a = warp == 0, do_b = pmode == 1 || warp == 3;
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -137,20 +142,26 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
       mbar_wait(&empty_bar[stage], phase ^ 1);
       uint8_t* sa = smem + stage * stage_bytes;
       uint8_t* sb = sa + g.stage_a_boxes * box_bytes;
-      mbar_arrive_expect_tx(&full_bar[stage], (a_boxes + nb_boxes) * box_bytes);
-      if constexpr (MC) {
-        // every second box of each operand, into this CTA and the peer that shares the operand
-        for (int j = static_cast<int>(rank >> 1); j < a_boxes; j += 2)
-          tma_load_5d_mc(&tm.dy, &full_bar[stage], sa + j * box_bytes, n0 + j * 64, 0, y0, b0, t, mask_a);
-        for (int j = static_cast<int>(rank & 1u); j < nb_boxes; j += 2)
-          tma_load_5d_mc(&tm.x[src], &full_bar[stage], sb + j * box_bytes, c0 + j * 64, kw - g.pad, y0 + kh - g.pad, b0,
-                         t - g.src_tshift[src], mask_b);
+      if (g.experiment == 2) {  // (timing experiment: no loads, the MMAs run on whatever the ring holds)
+        if (warp == 0 && lane == 0) mbar_arrive(&full_bar[stage]);
       } else {
-        for (int j = 0; j < a_boxes; ++j)
-          tma_load_5d(&tm.dy, &full_bar[stage], sa + j * box_bytes, n0 + j * 64, 0, y0, b0, t);
-        for (int j = 0; j < nb_boxes; ++j)
-          tma_load_5d(&tm.x[src], &full_bar[stage], sb + j * box_bytes, c0 + j * 64, kw - g.pad, y0 + kh - g.pad, b0,
-                      t - g.src_tshift[src]);
+        if (warp == 0 && lane == 0) mbar_arrive_expect_tx(&full_bar[stage], (a_boxes + nb_boxes) * box_bytes);
+        if constexpr (MC) {
+          // every second box of each operand, into this CTA and the peer that shares the operand
+          for (int j = static_cast<int>(rank >> 1); j < a_boxes; j += 2)
+            tma_load_5d_mc(&tm.dy, &full_bar[stage], sa + j * box_bytes, n0 + j * 64, 0, y0, b0, t, mask_a);
+          for (int j = static_cast<int>(rank & 1u); j < nb_boxes; j += 2)
+            tma_load_5d_mc(&tm.x[src], &full_bar[stage], sb + j * box_bytes, c0 + j * 64, kw - g.pad, y0 + kh - g.pad, b0,
+                           t - g.src_tshift[src], mask_b);
+        } else {
+          if (do_a)
+            for (int j = lane; j < a_boxes; j += plane)
+              tma_load_5d(&tm.dy, &full_bar[stage], sa + j * box_bytes, n0 + j * 64, 0, y0, b0, t);
+          if (do_b)
+            for (int j = lane; j < nb_boxes; j += plane)
+              tma_load_5d(&tm.x[src], &full_bar[stage], sb + j * box_bytes, c0 + j * 64, kw - g.pad, y0 + kh - g.pad, b0,
+                          t - g.src_tshift[src]);
+        }
       }
       if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
@@ -170,7 +181,7 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
       for (int k = 0; k < g.rows / 16; ++k) {
         // 16 positions = two 1024-byte atoms = 2048 B further along K: + 128 in the (addr >> 4) field; the second
         // accumulator's 128 output channels are the A boxes 2 and 3 (2 * box_bytes further)
-        for (int sub = 0; sub < subs; ++sub)
+        for (int sub = 0; sub < subs && g.experiment != 1; ++sub)
           umma_bf16_ss(tmem_base + sub * 256, adesc + 128u * k + sub * ((2u * box_bytes) >> 4), bdesc + 128u * k, idesc,
                        accumulate);
         accumulate = 1;
@@ -250,6 +261,10 @@ cudaError_t launch_wgrad_tc(const WgradTmaps& tm, const WgradGeom& g_in, cudaStr
   static const int max_stages = [] { const char* v = getenv("RAC_WGRAD_MAX_STAGES"); return v ? atoi(v) : 0; }();
   WgradGeom g = g_in;
   g.max_stages = max_stages;
+  static const int producers = [] { const char* v = getenv("RAC_WGRAD_PRODUCERS"); return v ? atoi(v) : 1; }();
+  static const int experiment = [] { const char* v = getenv("RAC_WGRAD_EXP"); return v ? atoi(v) : 0; }();
+  g.producers = producers < 1 || producers > 3 ? 1 : producers;
+  g.experiment = experiment;
   // a stage holds the largest tile pair of the launch, not always 4 + 4 boxes: the 64- / 128-channel layers of the
   // 48 x 64 maps (3 boxes of 8 KB per k-block) get 8 stages in flight instead of 3
   g.stage_a_boxes = g.kpad >= 256 ? 4 : g.kpad / 64;

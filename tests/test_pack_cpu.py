@@ -100,6 +100,19 @@ def test_library_exports_every_declared_symbol():
     assert lib.rac_abi_version() == 8
 
 
+def test_build_tracks_every_header():
+    """A struct that crosses object files (WgradGeom, ConvGeom, ...) must rebuild all of its users: every header of
+    csrc/ and the public header are dependencies of every object (a stale rac_api.o once read WgradGeom.out from the
+    old offset: an illegal address on the GPU, nothing at build time)."""
+    from robot_aware_control_b200 import build
+    for f in os.listdir(build.CSRC):
+        if f.endswith(".cuh") or f.endswith(".inc.cu"):
+            assert f in build.HEADERS, f
+        elif f.endswith(".cu"):
+            assert f in build.SOURCES, f
+    assert any(h.endswith("racb200.h") for h in build.HEADERS)
+
+
 def test_model_spec_matches_oracle_spec():
     from robot_aware_control_b200.model import _spec
     from robot_aware_control_b200.config import svg_config_from
