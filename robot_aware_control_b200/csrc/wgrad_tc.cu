@@ -41,11 +41,16 @@ namespace {
 // Pipeline ring: 192 KB cut into stages of (A boxes + B boxes) x rows x 128 bytes, A = up to 4 boxes (256 output
 // channels), B = up to 4 boxes (256 input channels), both the largest of the launch: 3 stages for a 256 x 256 tile with
 // 64-row k-blocks, 4 with the 48-row k-blocks of the 6 x 8 ConvLSTM maps, 8 for the 64 x 128 tiles of the 48 x 64 maps.
-// The main loop is latency-bound, not bandwidth-bound (ncu on the 5x5 gate layers, profiles/r02_train_top_ncu_s18.txt:
-// L2 26 %, L2 -> SM fabric 21 %, shared-memory operand pipe 31 %, tensor pipe 29 % of peak; 0.85 us per k-block against
-// 0.42 us of MMA time with 3 x 48 KB in flight), so every byte of the ring that is in flight counts. (Sharing the
-// operands of a 2 x 2 block of tiles by TMA multicast, RAC_WGRAD_MC=1, halves the L2 reads and measured SLOWER,
-// 436 -> 466 us, profiles/r02_train_top_ncu_s19.txt: the stage hand-back then waits for three CTAs.)
+// What bounds the main loop (0.85 us per 48-row k-block of a 256 x 256 tile against 0.42 us of nominal MMA time),
+// measured on a B200 (profiles/r02_train_top_ncu_s18.txt, _s19.txt, r02_train_ab_s19/_s20/_s21.txt):
+//   * no unit is saturated: L2 26 %, L2 -> SM fabric 21 %, shared-memory operand pipe 31 %, tensor pipe 29 % of peak;
+//   * NOT the depth of the ring: 4 / 8 stages instead of a fixed 3 changed nothing (13.31 vs 13.31 ms per step);
+//   * NOT the L2 reads: sharing both operands of a 2 x 2 block of tiles by TMA multicast (RAC_WGRAD_MC=1) halves them
+//     and is SLOWER (436 -> 466 us on the 5x5 gate layers; the stage hand-back then waits for three CTAs): off;
+//   * the up-to-8 TMA instructions per k-block cost a little when ONE thread issues them: two producer warps (dY boxes /
+//     X boxes) gain 1 % of the training step (13.51 -> 13.38 ms), one lane per box nothing more: two warps it is;
+//   * with the MMAs left out (RAC_WGRAD_EXP=1) the step is only 0.35 ms shorter, with the loads left out (=2) not
+//     shorter at all: the load side and the MMA side (both operands MN-major) each need about the time the kernel takes.
 constexpr int kMaxStages = 12;
 constexpr int kMaxRows = 64;                       // positions per k-block (K of one pipeline stage)
 constexpr int kRingBytes = 3 * 8 * kMaxRows * 128; // 192 KB
@@ -261,7 +266,7 @@ cudaError_t launch_wgrad_tc(const WgradTmaps& tm, const WgradGeom& g_in, cudaStr
   static const int max_stages = [] { const char* v = getenv("RAC_WGRAD_MAX_STAGES"); return v ? atoi(v) : 0; }();
   WgradGeom g = g_in;
   g.max_stages = max_stages;
-  static const int producers = [] { const char* v = getenv("RAC_WGRAD_PRODUCERS"); return v ? atoi(v) : 1; }();
+  static const int producers = [] { const char* v = getenv("RAC_WGRAD_PRODUCERS"); return v ? atoi(v) : 2; }();
   static const int experiment = [] { const char* v = getenv("RAC_WGRAD_EXP"); return v ? atoi(v) : 0; }();
   g.producers = producers < 1 || producers > 3 ? 1 : producers;
   g.experiment = experiment;
