@@ -35,7 +35,9 @@ struct TcCfg {
   static constexpr int kEpiThreads = BLOCK_M;                // one thread per output row
   static constexpr int kThreads = 128 + kEpiThreads;
   static constexpr int kBarBytes = 2048;  // mbarriers + TMEM slot (first 512 B) + LSTM bias tile (BLOCK_N floats at +1024)
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024 alignment slack
+  static constexpr int kEpiStageBytes = (kEpiThreads / 32) * kStageWarpBytes;  // fp32 epilogues: per-warp transpose tiles
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kEpiStageBytes + 1024;  // +1024 alignment slack
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
   static_assert(kTmemNeed <= 512, "accumulators do not fit TMEM");
   static_assert(kStages >= 2, "pipeline needs at least two stages");
 };
@@ -325,6 +327,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
     uint32_t acc_phase = 0;
     constexpr int CH = (BLOCK_N >= 32) ? 32 : 16;
     float* s_bias = reinterpret_cast<float*>(bar_base + 1024);
+    float* s_stage = reinterpret_cast<float*>(bar_base + Cfg::kBarBytes + we * kStageWarpBytes);  // this warp's transpose tile
     int bias_tile = -1;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       int half, split;
@@ -391,6 +394,12 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvGeom g, const Epi
         if constexpr (EPI == EPI_GAUSS) epi_gauss(g, e, b, y, x, valid, n0, acc_v);
         if constexpr (EPI == EPI_FRAME) epi_frame(g, e, b, y, x, valid, yb * (BLOCK_M / 32) + we, acc_v);
         if constexpr (EPI == EPI_F32 || EPI == EPI_F32_BT) {
+          if constexpr (CH == 32) {
+            if (g.epi_staged) {  // (uniform) coalesced stores through the warp's shared-memory tile
+              epi_f32_staged<CH>(g, e, b, y, x, valid, n0, g.num_n_tiles * BLOCK_N, split, acc_v, s_stage, lane);
+              return;
+            }
+          }
           if (kSplitK && e.split_part != nullptr) epi_split<CH>(g, e, b, y, x, valid, n0, g.num_n_tiles * BLOCK_N, split, acc_v);
           else epi_f32<CH>(g, e, b, y, x, valid, n0, acc_v);
         }

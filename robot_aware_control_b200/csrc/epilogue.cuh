@@ -257,6 +257,65 @@ __device__ __forceinline__ void epi_f32(const ConvGeom& g, const EpiParams& e, i
   }
 }
 
+// Warp-collective store of 32 rows x 32 fp32 columns through a per-warp shared-memory tile (conv_tc_kernel's fp32
+// epilogues). TMEM hands every lane one ROW of the accumulator, so the direct store (epi_f32 / epi_split) writes 16 bytes
+// per lane to 32 different rows per instruction -- 32 memory requests of half a sector each; the epilogue of a 256 x 256
+// tile (256 KB) took 9.4 us that way, 22 % of the time of the training GEMMs (profiles/r02_train_timeline_s10.txt).
+// Here a 16-column half of the chunk goes to shared memory row by row (row stride 20 floats: the 128-bit stores of a
+// quarter warp hit 8 disjoint bank groups) and comes back TRANSPOSED: every store instruction writes 64 contiguous
+// bytes of two rows. Row offsets (elements from `base`, < 0 = do not write) travel through the tile's spare columns.
+constexpr int kStageRowFloats = 20;
+constexpr int kStageWarpBytes = 32 * kStageRowFloats * 4;  // 2560 B per epilogue warp
+__device__ __forceinline__ void warp_store_rows_f32(float* stage, float* base, long long row_off, const float* acc,
+                                                    const float* bias, bool accumulate, int lane) {
+  float* mine = stage + lane * kStageRowFloats;
+  const int rsel = lane >> 4, col = lane & 15;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    __syncwarp();  // the previous half has been read
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<float4*>(mine + 4 * q) =
+          make_float4(acc[16 * h + 4 * q], acc[16 * h + 4 * q + 1], acc[16 * h + 4 * q + 2], acc[16 * h + 4 * q + 3]);
+    if (h == 0) *reinterpret_cast<long long*>(mine + 16) = row_off;
+    __syncwarp();
+    const float bv = bias ? __ldg(bias + 16 * h + col) : 0.f;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const float* row = stage + (2 * i + rsel) * kStageRowFloats;
+      const long long off = *reinterpret_cast<const long long*>(row + 16);
+      if (off < 0) continue;
+      float* p = base + off + 16 * h + col;
+      float v = row[col] + bv;
+      if (accumulate) v += *p;
+      *p = v;
+    }
+  }
+}
+// epi_f32 / epi_split through the staged store: same destinations, same values (bias and accumulation included)
+template <int CH>
+__device__ __forceinline__ void epi_f32_staged(const ConvGeom& g, const EpiParams& e, int b, int y, int x, bool valid, int n0,
+                                               int ncols, int split, const float* acc, float* stage, int lane) {
+  static_assert(CH == 32, "the staged store handles 32-column chunks");
+  const long long pix = static_cast<long long>(b * g.H + y) * g.W + x;
+  if (e.split_part != nullptr) {
+    warp_store_rows_f32(stage, e.split_part + static_cast<size_t>(split) * e.split_stride + n0,
+                        valid ? pix * ncols : -1, acc, nullptr, false, lane);
+    return;
+  }
+  if (n0 + CH > e.cout) return;  // (uniform over the warp, like everything below that depends on n0 only)
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    if (s >= e.nseg) break;
+    const F32Seg& sg = e.seg[s];
+    if (n0 < sg.n_begin || n0 >= sg.n_end) continue;
+    if (sg.dst == nullptr) return;
+    warp_store_rows_f32(stage, sg.dst + sg.coff + (n0 - sg.n_begin), valid ? pix * sg.cstride : -1, acc,
+                        e.bias ? e.bias + n0 : nullptr, sg.accumulate != 0, lane);
+    return;
+  }
+}
+
 // split-K work item: raw accumulator chunk -> this split's slice (the reduce kernel applies bias and segments)
 template <int CH>
 __device__ __forceinline__ void epi_split(const ConvGeom& g, const EpiParams& e, int b, int y, int x, bool valid, int n0,
