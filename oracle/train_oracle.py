@@ -87,7 +87,7 @@ class TrainOracle:
             info["kld"] += float(kl.detach())
         loss = recon + kld * self.beta
         loss.backward()
-        info["loss"] = float(loss)
+        info["loss"] = float(loss.detach())
         return info, {k: model.sd[k].grad.detach().clone() for k in self.param_keys}
 
     @torch.no_grad()

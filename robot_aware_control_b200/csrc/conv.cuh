@@ -46,7 +46,7 @@ struct ConvGeom {
   int num_m_tiles, num_n_tiles, tiles_per_img;  // tiles_per_img = H / BH
   int w_shift, bhw_shift;                       // log2(W), log2(BH * W)
   int no_split_tail;                            // 1: disable the tail splitting of conv_tc_kernel (A/B measurements)
-  int epi_staged;                               // 1: fp32 epilogues store through the per-warp transpose tile (coalesced)
+  int epi_staged;                               // 1 / 2: fp32 epilogues store through the per-warp transpose tile (32- / 128-bit)
   // 1: the rows of an M-tile are ordered (row of the map, candidate, column) instead of (candidate, row, column): the TMA
   // box is {64, W, NB, BH} on a (C, W, B, H) view of the tensor. With NB * W == 128 each 128-row MMA sub-tile is then
   // ONE row of the 6x8 latent map, and the MMAs of a sub-tile whose input row for a filter tap lies in the zero

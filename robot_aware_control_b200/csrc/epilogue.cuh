@@ -292,12 +292,69 @@ __device__ __forceinline__ void warp_store_rows_f32(float* stage, float* base, l
     }
   }
 }
+// Same tile, 128-bit on the way back as well (g.epi_staged == 2): four lanes read one row's 16 columns as float4, so a
+// store instruction writes the 64 contiguous bytes of EIGHT rows -- 8 LDS.128 + 8 STG.128 per 32-column chunk and lane
+// instead of 32 scalar pairs. A quarter warp reads rows r and r + 4 of the tile: with the 80-byte row stride their
+// 16-byte bank groups {5r .. 5r+3} and {5r+20 .. 5r+23} (mod 8) are disjoint.
+__device__ __forceinline__ void warp_store_rows_f32_v4(float* stage, float* base, long long row_off, const float* acc,
+                                                       const float* bias, bool accumulate, int lane) {
+  float* mine = stage + lane * kStageRowFloats;
+  const int rsel = (lane >> 3) + 4 * ((lane >> 2) & 1), c4 = (lane & 3) * 4;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    __syncwarp();  // the previous half has been read
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<float4*>(mine + 4 * q) =
+          make_float4(acc[16 * h + 4 * q], acc[16 * h + 4 * q + 1], acc[16 * h + 4 * q + 2], acc[16 * h + 4 * q + 3]);
+    if (h == 0) *reinterpret_cast<long long*>(mine + 16) = row_off;
+    __syncwarp();
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) {
+      const float* bp = bias + 16 * h + c4;
+      bv = make_float4(__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float* row = stage + (8 * i + rsel) * kStageRowFloats;
+      const long long off = *reinterpret_cast<const long long*>(row + 16);
+      if (off < 0) continue;
+      float4* p = reinterpret_cast<float4*>(base + off + 16 * h + c4);
+      float4 v = *reinterpret_cast<const float4*>(row + c4);
+      v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+      if (accumulate) {
+        const float4 o = *p;
+        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+      }
+      *p = v;
+    }
+  }
+}
 // epi_f32 / epi_split through the staged store: same destinations, same values (bias and accumulation included)
 template <int CH>
 __device__ __forceinline__ void epi_f32_staged(const ConvGeom& g, const EpiParams& e, int b, int y, int x, bool valid, int n0,
                                                int ncols, int split, const float* acc, float* stage, int lane) {
   static_assert(CH == 32, "the staged store handles 32-column chunks");
   const long long pix = static_cast<long long>(b * g.H + y) * g.W + x;
+  if (g.epi_staged == 2) {  // (uniform) 128-bit variant, same control flow as below
+    if (e.split_part != nullptr) {
+      warp_store_rows_f32_v4(stage, e.split_part + static_cast<size_t>(split) * e.split_stride + n0,
+                             valid ? pix * ncols : -1, acc, nullptr, false, lane);
+      return;
+    }
+    if (n0 + CH > e.cout) return;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      if (s >= e.nseg) break;
+      const F32Seg& sg = e.seg[s];
+      if (n0 < sg.n_begin || n0 >= sg.n_end) continue;
+      if (sg.dst == nullptr) return;
+      warp_store_rows_f32_v4(stage, sg.dst + sg.coff + (n0 - sg.n_begin), valid ? pix * sg.cstride : -1, acc,
+                             e.bias ? e.bias + n0 : nullptr, sg.accumulate != 0, lane);
+      return;
+    }
+    return;
+  }
   if (e.split_part != nullptr) {
     warp_store_rows_f32(stage, e.split_part + static_cast<size_t>(split) * e.split_stride + n0,
                         valid ? pix * ncols : -1, acc, nullptr, false, lane);

@@ -249,10 +249,11 @@ int t_gemm(rac_handle* h, const char* name, const GemmGeom& gg, const std::vecto
       block_n = op.block_n;
     }
   }
-  // fp32 epilogues store through the per-warp transpose tile (epilogue.cuh, warp_store_rows_f32); RAC_EPI_STAGED=0:
-  // the direct per-row stores (A/B switch)
-  static const int epi_staged = [] { const char* v = getenv("RAC_EPI_STAGED"); return v ? atoi(v) : 1; }();
-  g.epi_staged = epi_staged;
+  // fp32 epilogues store through the per-warp transpose tile, 128 bits both ways (epilogue.cuh, warp_store_rows_f32_v4):
+  // 13.50 -> 13.22 ms per training step. RAC_EPI_STAGED=0: the direct per-row stores, =1: the 32-bit read-back (slower
+  // than the direct stores, 14.35 ms: 32 scalar LDS / STG pairs per chunk) -- profiles/r02_train_ab_s24.txt
+  static const int epi_staged = [] { const char* v = getenv("RAC_EPI_STAGED"); return v ? atoi(v) : 2; }();
+  g.epi_staged = (epi_staged >= 0 && epi_staged <= 2) ? epi_staged : 2;
   g.nsrc = static_cast<int>(srcs.size());
   for (int i = 0; i < g.nsrc; ++i) {
     if (srcs[i].C % kBlockK) return fail(h, RAC_ERR_INVALID, "train gemm %s: source channels %d", name, srcs[i].C);
