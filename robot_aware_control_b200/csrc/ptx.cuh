@@ -330,4 +330,79 @@ inline cudaError_t launch_pdl_small(void (*kernel)(KArgs...), dim3 grid, dim3 bl
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// ---------------------------------------------------------------- transposed fp32 stores (GEMM epilogues)
+// Warp-collective store of 32 rows x 32 fp32 columns through a per-warp shared-memory tile (conv_tc_kernel's fp32
+// epilogues). TMEM hands every lane one ROW of the accumulator, so the direct store (epi_f32 / epi_split) writes 16 bytes
+// per lane to 32 different rows per instruction -- 32 memory requests of half a sector each; the epilogue of a 256 x 256
+// tile (256 KB) took 9.4 us that way, 22 % of the time of the training GEMMs (profiles/r02_train_timeline_s10.txt).
+// Here a 16-column half of the chunk goes to shared memory row by row (row stride 20 floats: the 128-bit stores of a
+// quarter warp hit 8 disjoint bank groups) and comes back TRANSPOSED: every store instruction writes 64 contiguous
+// bytes of two rows. Row offsets (elements from `base`, < 0 = do not write) travel through the tile's spare columns.
+constexpr int kStageRowFloats = 20;
+constexpr int kStageWarpBytes = 32 * kStageRowFloats * 4;  // 2560 B per epilogue warp
+__device__ __forceinline__ void warp_store_rows_f32(float* stage, float* base, long long row_off, const float* acc,
+                                                    const float* bias, bool accumulate, int lane) {
+  float* mine = stage + lane * kStageRowFloats;
+  const int rsel = lane >> 4, col = lane & 15;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    __syncwarp();  // the previous half has been read
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<float4*>(mine + 4 * q) =
+          make_float4(acc[16 * h + 4 * q], acc[16 * h + 4 * q + 1], acc[16 * h + 4 * q + 2], acc[16 * h + 4 * q + 3]);
+    if (h == 0) *reinterpret_cast<long long*>(mine + 16) = row_off;
+    __syncwarp();
+    const float bv = bias ? __ldg(bias + 16 * h + col) : 0.f;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const float* row = stage + (2 * i + rsel) * kStageRowFloats;
+      const long long off = *reinterpret_cast<const long long*>(row + 16);
+      if (off < 0) continue;
+      float* p = base + off + 16 * h + col;
+      float v = row[col] + bv;
+      if (accumulate) v += *p;
+      *p = v;
+    }
+  }
+}
+// Same tile, 128-bit on the way back as well (g.epi_staged == 2): four lanes read one row's 16 columns as float4, so a
+// store instruction writes the 64 contiguous bytes of EIGHT rows -- 8 LDS.128 + 8 STG.128 per 32-column chunk and lane
+// instead of 32 scalar pairs. A quarter warp reads rows r and r + 4 of the tile: with the 80-byte row stride their
+// 16-byte bank groups {5r .. 5r+3} and {5r+20 .. 5r+23} (mod 8) are disjoint.
+__device__ __forceinline__ void warp_store_rows_f32_v4(float* stage, float* base, long long row_off, const float* acc,
+                                                       const float* bias, bool accumulate, int lane) {
+  float* mine = stage + lane * kStageRowFloats;
+  const int rsel = (lane >> 3) + 4 * ((lane >> 2) & 1), c4 = (lane & 3) * 4;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    __syncwarp();  // the previous half has been read
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<float4*>(mine + 4 * q) =
+          make_float4(acc[16 * h + 4 * q], acc[16 * h + 4 * q + 1], acc[16 * h + 4 * q + 2], acc[16 * h + 4 * q + 3]);
+    if (h == 0) *reinterpret_cast<long long*>(mine + 16) = row_off;
+    __syncwarp();
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) {
+      const float* bp = bias + 16 * h + c4;
+      bv = make_float4(__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float* row = stage + (8 * i + rsel) * kStageRowFloats;
+      const long long off = *reinterpret_cast<const long long*>(row + 16);
+      if (off < 0) continue;
+      float4* p = reinterpret_cast<float4*>(base + off + 16 * h + c4);
+      float4 v = *reinterpret_cast<const float4*>(row + c4);
+      v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+      if (accumulate) {
+        const float4 o = *p;
+        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+      }
+      *p = v;
+    }
+  }
+}
+
 }  // namespace rac

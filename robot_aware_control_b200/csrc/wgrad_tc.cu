@@ -54,8 +54,10 @@ namespace {
 constexpr int kMaxStages = 12;
 constexpr int kMaxRows = 64;                       // positions per k-block (K of one pipeline stage)
 constexpr int kRingBytes = 3 * 8 * kMaxRows * 128; // 192 KB
-constexpr int kSmemBytes = kRingBytes + 1024 + 1024;
-constexpr int kThreads = 128 + 256;
+constexpr int kEpiWarps = 8;
+constexpr int kSmemBytes = kRingBytes + 1024 + kEpiWarps * kStageWarpBytes + 1024;  // ring, barriers, transpose tiles, slack
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+constexpr int kThreads = 128 + 32 * kEpiWarps;
 
 // bf16 x bf16 -> fp32, A and B both MN-major, M = 128
 __device__ __forceinline__ uint32_t umma_idesc_bf16_mn(int n) { return umma_idesc_bf16(n) | kIdescAMn | kIdescBMn; }
@@ -208,6 +210,11 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
       mbar_wait(tmem_full, 0);
       tc_fence_after();
     }
+    // g.epi_staged: the 32 x 32 chunk goes through this warp's shared-memory transpose tile and leaves as 64 contiguous
+    // bytes of eight rows per store instruction (ptx.cuh, warp_store_rows_f32_v4) instead of 16 bytes of 32 rows
+    float* stage = reinterpret_cast<float*>(bar_base + 1024 + (warp - 4) * kStageWarpBytes);
+    const long long row_off = n < g.kpad ? static_cast<long long>(n) * ld : -1;
+    float* base = out - static_cast<long long>(n) * ld;  // row 0 of this (split, tap, source, c0) block
     for (int cc = 0; cc < cw && sub < subs; cc += 32) {
       float v[32];
       if (kb_end > kb_begin) {
@@ -217,7 +224,9 @@ wgrad_tc_kernel(const __grid_constant__ WgradTmaps tm, const WgradGeom g) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0.f;
       }
-      if (n < g.kpad) {
+      if (g.epi_staged) {  // (uniform)
+        warp_store_rows_f32_v4(stage, base + cc, row_off, v, nullptr, false, lane);
+      } else if (n < g.kpad) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4)
           *reinterpret_cast<float4*>(out + cc + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -268,6 +277,10 @@ cudaError_t launch_wgrad_tc(const WgradTmaps& tm, const WgradGeom& g_in, cudaStr
   g.max_stages = max_stages;
   static const int producers = [] { const char* v = getenv("RAC_WGRAD_PRODUCERS"); return v ? atoi(v) : 2; }();
   static const int experiment = [] { const char* v = getenv("RAC_WGRAD_EXP"); return v ? atoi(v) : 0; }();
+  // transposed 128-bit epilogue stores (see the kernel's epilogue): 13.22 -> 12.80 ms per training step
+  // (profiles/r02_train_ab_s25.txt); RAC_WGRAD_EPI_STAGED=0: the direct per-row stores (A/B switch)
+  static const int epi_staged = [] { const char* v = getenv("RAC_WGRAD_EPI_STAGED"); return v ? atoi(v) : 1; }();
+  g.epi_staged = epi_staged != 0;
   g.producers = producers < 1 || producers > 3 ? 1 : producers;
   g.experiment = experiment;
   // a stage holds the largest tile pair of the launch, not always 4 + 4 boxes: the 64- / 128-channel layers of the

@@ -30,6 +30,7 @@ struct WgradGeom {
   int max_stages;              // 0 = as many pipeline stages as the shared-memory ring holds (set by launch_wgrad_tc)
   int stage_a_boxes, stage_b_boxes;  // boxes per stage: the largest dY / X tile of this launch (set by launch_wgrad_tc)
   int producers;               // 1: one thread issues all TMA boxes; 2: warp 0 the dY boxes, warp 3 the X boxes; 3: same, one lane per box
+  int epi_staged;              // 1: the epilogue stores through per-warp shared-memory transpose tiles (set by launch_wgrad_tc)
   int experiment;              // timing experiments only (results are garbage): 1 = no MMAs issued, 2 = no TMA loads issued
   float* out;                  // [splits][kpad][taps * ctot]
   long long out_split_stride;  // floats between two split partials
