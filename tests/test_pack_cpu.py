@@ -199,6 +199,30 @@ def test_product_path_fails_loudly_without_a_gpu():
     assert lib.rac_psnr(None, None, None, 0, None, 1, 3, 3072, None) < 0
 
 
+def test_product_package_never_touches_the_oracle_or_a_torch_compute_fallback():
+    """The oracle is test infrastructure: only tests/, bench.py (cpu_baseline / --impl reference) and
+    __graft_entry__.smoke() may import it. The product package must not import `oracle`, must not read /root/reference,
+    and must not carry a torch implementation of the model's layers (no conv / LSTM / pooling through ATen)."""
+    import os
+    import re
+
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "robot_aware_control_b200")
+    banned = [r"^\s*(from|import)\s+oracle\b", r"/root/reference", r"\bF\.conv", r"\bconv2d\(", r"conv_transpose2d\(",
+              r"nn\.Conv2d\(", r"nn\.LSTM", r"max_pool2d\(", r"torch\.compile", r"\btriton\b"]
+    hits = []
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h")):
+                continue
+            path = os.path.join(dirpath, f)
+            for n, line in enumerate(open(path, errors="replace"), 1):
+                code = line.split("#", 1)[0] if f.endswith(".py") else line.split("//", 1)[0]
+                for pat in banned:
+                    if re.search(pat, code):
+                        hits.append(f"{os.path.relpath(path, root)}:{n}: {line.strip()[:100]}")
+    assert not hits, "\n".join(hits)
+
+
 def test_adam_state_dict_round_trip_with_torch_adam():
     """Checkpoint "optimizer" entry (reference trainer.py:829-896): flat moments <-> torch.optim.Adam.state_dict()."""
     from robot_aware_control_b200.trainer import adam_state_dict, load_adam_state_dict
